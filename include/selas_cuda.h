@@ -1,0 +1,332 @@
+/*
+ * selas_cuda.h -- C ABI of the B200-native Selas path-tracing hot path.
+ *
+ * The reference (schuttejoe/Selas) has no plugin/FFI layer; the replaceable seams are ordinary C++
+ * calls.  Each entry point below names the reference call it stands in for
+ * (file:line relative to the reference tree).  Conventions:
+ *   - every function returns int: 0 = ok, otherwise a SelasStatus; selas_cuda_last_error() gives the
+ *     message (mirrors Error::Message(), Source/Core/SystemLib/Error.h:33).
+ *   - handles are opaque; host pointers are borrowed for the call; device memory is owned by a handle.
+ *   - plain "host" entry points copy host buffers to the GPU, run, copy back and synchronise;
+ *     "_device" entry points take device pointers (the caller's CUDA stream, 0 = default) and do
+ *     not synchronise.
+ *   - there is NO CPU fallback: if no CUDA device is usable every call fails with SELAS_ERR_CUDA.
+ *   - vectors are row vectors, matrices row-major with translation in row 3
+ *     (Source/Core/MathLib/FloatFuncs.cpp:383-396); tangent space is y-up
+ *     (Source/Core/Shading/SurfaceParameters.cpp:217-219).
+ */
+#ifndef SELAS_CUDA_H
+#define SELAS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SELAS_INVALID_ID 0xFFFFFFFFu /* RTC_INVALID_GEOMETRY_ID, embree3/rtcore_common.h */
+
+typedef enum SelasStatus {
+    SELAS_OK            = 0,
+    SELAS_ERR_CUDA      = 1, /* CUDA runtime error / no device */
+    SELAS_ERR_ARGUMENT  = 2,
+    SELAS_ERR_MEMORY    = 3,
+    SELAS_ERR_FORMAT    = 4, /* malformed asset (ptex, material json, ...) */
+    SELAS_ERR_UNSUPPORTED = 5
+} SelasStatus;
+
+/* ShaderType, Source/Core/SceneLib/ModelResource.h:27-33 */
+enum { SELAS_SHADER_DISNEY_THIN = 0, SELAS_SHADER_DISNEY_SOLID = 1, SELAS_SHADER_DIRAC_TRANSPARENT = 2 };
+/* MaterialFlags, ModelResource.h:35-42 */
+enum { SELAS_MAT_TRANSPARENT = 1, SELAS_MAT_ALPHA_TESTED = 2, SELAS_MAT_DISPLACEMENT = 4,
+       SELAS_MAT_INVERT_DISPLACEMENT = 8, SELAS_MAT_USES_PTEX = 16 };
+/* ScalarMaterialProperties, ModelResource.h:44-64 */
+enum { SELAS_METALLIC = 0, SELAS_SPECULAR_TINT, SELAS_ROUGHNESS, SELAS_ANISOTROPIC, SELAS_SHEEN,
+       SELAS_SHEEN_TINT, SELAS_CLEARCOAT, SELAS_CLEARCOAT_GLOSS, SELAS_SPEC_TRANS, SELAS_DIFFUSE_TRANS,
+       SELAS_FLATNESS, SELAS_IOR, SELAS_SCATTER_DISTANCE, SELAS_DISPLACEMENT, SELAS_SCALAR_COUNT };
+/* SurfaceEventFlags / MediumPhaseFunction, Source/Core/Shading/Scattering.h:13-25 */
+enum { SELAS_EVENT_SCATTER = 1, SELAS_EVENT_TRANSMISSION = 2, SELAS_EVENT_DIRAC = 4 };
+enum { SELAS_MEDIUM_VACUUM = 0, SELAS_MEDIUM_ISOTROPIC = 1 };
+
+/* 88-byte payload of MaterialResourceData (ModelResource.h:68-88, minus the 512-byte texture path). */
+typedef struct SelasMaterial {
+    uint32_t shader;
+    uint32_t flags;
+    float    baseColor[3];
+    float    transmittanceColor[3];
+    float    scalars[SELAS_SCALAR_COUNT];
+} SelasMaterial;
+
+/* SceneLight, Source/Core/SceneLib/SceneResource.h:32-40 (64 bytes). position is the quad centre. */
+typedef struct SelasLight {
+    uint32_t type;
+    float    position[3];
+    float    direction[3];
+    float    x[3];
+    float    z[3];
+    float    radiance[3];
+} SelasLight;
+
+/* SceneLightSetRange, SceneResource.h:42-46 */
+typedef struct SelasLightSetRange { uint32_t start, count; } SelasLightSetRange;
+
+/* RayCastCameraSettings, Source/Core/GeometryLib/Camera.h:29-47 (104 bytes). */
+typedef struct SelasCamera {
+    float    cameraX[3];
+    float    cameraY[3];
+    float    cameraZ[3];
+    float    position[3];
+    float    forward[3];
+    float    viewportWidth;
+    float    viewportHeight;
+    float    znear;
+    float    zfar;
+    uint32_t pad0;   /* the reference's `uint` is 64-bit (SystemLib/BasicTypes.h:47): width sits at offset 80 */
+    uint64_t width;
+    uint64_t height;
+    float    aspect;
+    float    virtualImagePlaneDistance;
+} SelasCamera;
+
+/* CameraSettings numeric part, Camera.h:17-26 */
+typedef struct SelasCameraSettings {
+    float position[3];
+    float fovDegrees; /* horizontal */
+    float lookAt[3];
+    float znear;
+    float up[3];
+    float zfar;
+} SelasCameraSettings;
+
+/* SurfaceParameters, Source/Core/Shading/SurfaceParameters.h:18-49 (156 bytes), same field order. */
+typedef struct SelasSurface {
+    float    position[3];
+    float    worldToTangent[9]; /* rows r0,r1,r2 */
+    float    error;
+    float    view[3];
+    float    baseColor[3];
+    float    transmittanceColor[3];
+    float    sheen, sheenTint, clearcoat, clearcoatGloss, metallic, specTrans, diffTrans, flatness,
+             anisotropic, relativeIOR, specularTint, roughness, scatterDistance, ior;
+    uint32_t shader;
+    uint32_t materialFlags;
+    uint32_t lightSetIndex;
+} SelasSurface;
+
+/* BsdfSample, Source/Core/Shading/Scattering.h:34-43 (52 bytes) + the sampler-consumption count. */
+typedef struct SelasBsdfSample {
+    uint32_t flags;
+    uint32_t mediumPhase;
+    float    mediumExtinction[3];
+    float    reflectance[3];
+    float    wi[3];
+    float    forwardPdfW;
+    float    reversePdfW;
+    uint32_t valid;      /* return value of SampleBsdfFunction (SurfaceScattering.cpp:18) */
+    uint32_t randomsUsed;/* how many uniforms the call drew from its stream */
+} SelasBsdfSample;
+
+/* LightDirectSample, Source/Core/Shading/AreaLighting.h:47-54 */
+typedef struct SelasLightSample {
+    uint32_t index;
+    float    direction[3];
+    float    radiance[3];
+    float    distance;
+    float    pdfW;
+} SelasLightSample;
+
+/* Ray as the traversal kernels read it: two 16-byte vectors {o,tnear},{d,tfar}
+ * (subset of RTCRay, embree3/rtcore_ray.h:26-41). */
+typedef struct SelasRay {
+    float ox, oy, oz, tnear;
+    float dx, dy, dz, tfar;
+} SelasRay;
+
+/* Closest-hit record: two 16-byte vectors (RTCHit fields, rtcore_ray.h:44-55; Ng is optional, separate).
+ * Miss: geomID == SELAS_INVALID_ID and t == ray.tfar. */
+typedef struct SelasHit {
+    float    t, u, v;
+    uint32_t primID;
+    uint32_t geomID;
+    uint32_t instID0;
+    uint32_t instID1;
+    uint32_t pad;
+} SelasHit;
+
+/* One triangle/quad mesh = one Embree geometry (ModelResource.cpp:164-200, :236-297). */
+typedef struct SelasMeshDesc {
+    const float*    positions;      /* float3, stride 12 */
+    uint32_t        vertexCount;
+    const uint32_t* indices;        /* indicesPerFace per face */
+    uint32_t        faceCount;
+    uint32_t        indicesPerFace; /* 3 = RTC_GEOMETRY_TYPE_TRIANGLE, 4 = RTC_GEOMETRY_TYPE_QUAD */
+    const float*    normals;        /* float3 per vertex or NULL (attribute slot 0) */
+    const float*    tangents;       /* float4 per vertex or NULL (slot 1) */
+    const float*    uvs;            /* float2 per vertex or NULL (slot 2) */
+    uint32_t        materialIndex;
+    uint32_t        lightSetIndex;
+    void*           ptex;           /* SelasPtex* for SELAS_MAT_USES_PTEX materials, else NULL */
+} SelasMeshDesc;
+
+/* Instance of a mesh; localToWorld is a row-major row-vector 4x4 (translation in row 3). */
+typedef struct SelasInstanceDesc {
+    uint32_t meshIndex;
+    float    localToWorld[16];
+} SelasInstanceDesc;
+
+typedef struct SelasSceneDesc {
+    const SelasMeshDesc*      meshes;
+    uint32_t                  meshCount;
+    const SelasInstanceDesc*  instances;     /* NULL/0 => every mesh once, identity, instID0 = 0 */
+    uint32_t                  instanceCount;
+    const SelasMaterial*      materials;
+    uint32_t                  materialCount;
+    const SelasLight*         lights;
+    uint32_t                  lightCount;
+    const SelasLightSetRange* lightSets;
+    uint32_t                  lightSetCount;
+    float                     backgroundIntensity[4]; /* SceneResourceData::backgroundIntensity */
+} SelasSceneDesc;
+
+/* Compile-time macros of the reference integrator made runtime (PathTracer.cpp:42-46, :248). */
+typedef struct SelasRenderSettings {
+    uint32_t width, height;
+    uint32_t samplesPerPixel; /* PathsPerPixel_ */
+    uint32_t maxPathLength;   /* MaxBounceCount_ : loop bound bounceCount < maxPathLength */
+    uint32_t rrStartBounce;   /* Russian roulette when bounceCount > rrStartBounce (reference: 8) */
+    uint32_t layerCount;      /* 1 (radiance) or 2 (albedo-like Ld[0], radiance Ld[1]); LayerCount_ */
+    uint32_t seed;
+    uint32_t firstSample;     /* sample-pass shard: this call renders samples [firstSample, firstSample+samplesPerPixel) */
+    uint32_t misMode;         /* 0 = reference (weight 1.0, PathTracer.cpp:215); 1 = balance heuristic */
+    uint32_t reserved[3];
+} SelasRenderSettings;
+
+typedef struct SelasRenderStats {
+    uint64_t closestRays;
+    uint64_t occlusionRays;
+    uint64_t pathSamples;
+    uint64_t kernelLaunches;
+    float    renderMs; /* device time of the wavefront loop (CUDA events) */
+    float    pad;
+} SelasRenderStats;
+
+typedef struct SelasBvhStats {
+    uint32_t triangleCount;  /* triangles stored (quads count twice) */
+    uint32_t nodeCount;      /* 80-byte BVH8 nodes */
+    uint32_t maxDepth;
+    uint32_t reserved;
+    float    buildMs;
+    float    sahCost;
+    uint64_t deviceBytes;
+} SelasBvhStats;
+
+typedef struct SelasContext  SelasContext;
+typedef struct SelasScene    SelasScene;
+typedef struct SelasHashGrid SelasHashGrid;
+typedef struct SelasPtex     SelasPtex;
+
+/* ---- context --------------------------------------------------------------------------------- */
+/* rtcNewDevice / rtcReleaseDevice at Source/Applications/Selas/Source/main.cpp:99,:130 */
+int selas_cuda_context_create(int device, SelasContext** out);
+int selas_cuda_context_destroy(SelasContext* ctx);
+const char* selas_cuda_last_error(const SelasContext* ctx); /* ctx may be NULL: thread-local message */
+int selas_cuda_device_count(void);
+const char* selas_cuda_version(void);
+
+/* ---- scene: replaces the Embree scene construction ---------------------------------------------
+ * rtcSetSharedGeometryBuffer/rtcCommitGeometry/rtcCommitScene at ModelResource.cpp:164-200,:461-468,
+ * SubsceneResource.cpp:141-156, SceneResource.cpp:218-249.  Builds the compressed BVH8 on device. */
+int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* desc, SelasScene** out);
+int selas_cuda_scene_destroy(SelasScene* scene);
+int selas_cuda_scene_bvh_stats(const SelasScene* scene, SelasBvhStats* out);
+
+/* ---- ray cast: replaces rtcIntersect1 / rtcOccluded1 ---------------------------------------------
+ * PathTracer.cpp:116 (RayPick) and :88 (OcclusionRay); packet form DeferredPathTracer.cpp:191,:267.
+ * Closest hit in [tnear, tfar]; Ng (optional, float4 per ray, may be NULL) is the unnormalised
+ * geometric normal cross(v1-v0, v2-v0).  occluded[i] = 1 when any hit exists (Embree: tfar = -inf). */
+int selas_cuda_intersect(SelasScene* scene, size_t n, const SelasRay* rays, SelasHit* hits, float* Ng4);
+int selas_cuda_occluded(SelasScene* scene, size_t n, const SelasRay* rays, uint8_t* occluded);
+int selas_cuda_intersect_device(SelasScene* scene, size_t n, const SelasRay* d_rays, SelasHit* d_hits,
+                                float* d_Ng4, void* stream);
+int selas_cuda_occluded_device(SelasScene* scene, size_t n, const SelasRay* d_rays, uint8_t* d_occluded,
+                               void* stream);
+/* Per-ray traversal counters (nodes visited, triangles tested) from the counting build of the same
+ * kernels; used for the algorithmic-bytes roofline.  counts: 2 uint32 per ray. */
+int selas_cuda_intersect_counted(SelasScene* scene, size_t n, const SelasRay* rays, SelasHit* hits,
+                                 uint32_t* counts, int anyHit);
+
+/* ---- camera: InitializeRayCastCamera Camera.cpp:89-115; JitteredCameraRay Camera.cpp:63-74 ------- */
+int selas_cuda_camera_init(const SelasCameraSettings* settings, uint32_t width, uint32_t height,
+                           SelasCamera* out);
+/* rays[i] from pixel (px[i] + jitter[2i], py[i] + jitter[2i+1]); jitter NULL => pixel centre +0.5 */
+int selas_cuda_camera_rays(SelasContext* ctx, const SelasCamera* camera, size_t n, const float* px,
+                           const float* py, const float* jitter, SelasRay* rays);
+
+/* ---- BSDF operators: SurfaceScattering.h:15-16 ----------------------------------------------------
+ * EvaluateBsdf (SurfaceScattering.cpp:41): f*|cos| in rgb[3n], forward/reverse pdf.
+ * SampleBsdfFunction (SurfaceScattering.cpp:18): u holds SELAS_BSDF_RANDOMS uniforms per sample,
+ * consumed in the reference's order (lobe pick first; Disney.cpp:628). */
+#define SELAS_BSDF_RANDOMS 8
+int selas_cuda_bsdf_eval(SelasContext* ctx, size_t n, const SelasSurface* surfaces, const float* v3,
+                         const float* l3, float* rgb3, float* forwardPdfW, float* reversePdfW);
+int selas_cuda_bsdf_sample(SelasContext* ctx, size_t n, const SelasSurface* surfaces, const float* v3,
+                           const float* u, SelasBsdfSample* out);
+
+/* ---- lights: NextEventEstimation AreaLighting.cpp:353-373 (3 uniforms per sample) ----------------
+ * and LightingPdf AreaLighting.cpp:376-390. */
+int selas_cuda_light_sample(SelasContext* ctx, size_t n, const SelasLight* lights, uint32_t lightCount,
+                            const float* position3, const float* normal3, const float* u3,
+                            SelasLightSample* out);
+int selas_cuda_light_pdf(SelasContext* ctx, size_t n, const SelasLight* lights, uint32_t lightCount,
+                         const uint32_t* lightIndex, const float* position3, const float* wi3, float* pdf);
+
+/* ---- surface: CalculateSurfaceParams SurfaceParameters.cpp:144-247 over a batch of hits ---------- */
+int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays, const SelasHit* hits,
+                              SelasSurface* out);
+
+/* ---- integrator: PathTracer::GenerateImage PathTracer.cpp:301-350 --------------------------------
+ * film[layer] is width*height float3, receives the SUM over this call's samples (not yet scaled by
+ * 1/spp: FrameBuffer_Scale, Framebuffer.cpp:62-70, is the caller's / selas_cuda_film_scale's job). */
+int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera,
+                                 const SelasRenderSettings* settings, float* const* filmLayers,
+                                 SelasRenderStats* stats);
+/* Device-resident variant: d_film = layerCount consecutive width*height*3 float planes, accumulated into. */
+int selas_cuda_render_pathtracer_device(SelasScene* scene, const SelasCamera* camera,
+                                        const SelasRenderSettings* settings, float* d_film,
+                                        SelasRenderStats* stats, void* stream);
+/* FrameBuffer_Scale Framebuffer.cpp:62-70 on a device film. */
+int selas_cuda_film_scale_device(SelasContext* ctx, float* d_film, size_t floatCount, float scale, void* stream);
+
+/* ---- VCM hash grid: BuildHashGrid VCMHashGrid.cpp:48-97, SearchHashGrid :107-155 ------------------
+ * positions: float3 per vertex.  Query returns, per query point, the indices of vertices with
+ * dist^2 <= r^2 in the 2x2x2 neighbourhood, in the reference's visiting order. */
+int selas_cuda_hashgrid_build(SelasContext* ctx, size_t n, const float* positions3, float radius,
+                              uint32_t cellCount, SelasHashGrid** out);
+int selas_cuda_hashgrid_destroy(SelasHashGrid* grid);
+/* copies cellRangeEnds[cellCount] and cellIndices[n] (reference layout) to the host */
+int selas_cuda_hashgrid_read(const SelasHashGrid* grid, uint32_t* cellRangeEnds, uint32_t* cellIndices,
+                             float* aabbMinMax6);
+/* counts[m]; if indices != NULL, up to maxPerQuery indices per query are written at indices[q*maxPerQuery..] */
+int selas_cuda_hashgrid_query(const SelasHashGrid* grid, size_t m, const float* queries3,
+                              uint32_t* counts, uint32_t* indices, uint32_t maxPerQuery);
+int selas_cuda_hashgrid_build_device(SelasContext* ctx, size_t n, const float* d_positions3, float radius,
+                                     uint32_t cellCount, SelasHashGrid** inout, void* stream);
+int selas_cuda_hashgrid_query_device(const SelasHashGrid* grid, size_t m, const float* d_queries3,
+                                     uint32_t* d_counts, uint32_t* d_indices, uint32_t maxPerQuery,
+                                     void* stream);
+
+/* ---- Ptex: PtexFilter::eval(f_bspline) as called at SurfaceParameters.cpp:203 ---------------------
+ * (Ptexture.h:1010-1012; widths 0, width 1, blur 0).  rgb3: 3 floats per lookup. */
+int selas_cuda_ptex_load(SelasContext* ctx, const char* path, SelasPtex** out);
+int selas_cuda_ptex_load_memory(SelasContext* ctx, const void* data, size_t size, SelasPtex** out);
+int selas_cuda_ptex_destroy(SelasPtex* tex);
+int selas_cuda_ptex_eval(SelasPtex* tex, size_t n, const int32_t* faceid, const float* u, const float* v,
+                         float* rgb3);
+int selas_cuda_ptex_eval_device(SelasPtex* tex, size_t n, const int32_t* d_faceid, const float* d_u,
+                                const float* d_v, float* d_rgb3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELAS_CUDA_H */

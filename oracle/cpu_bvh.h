@@ -1,0 +1,279 @@
+// oracle/cpu_bvh.h -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+//
+// CPU restatement of the ray-cast semantics the reference gets from Embree 3.2.0 (third-party, not under
+// /root/reference; pinned by Middleware/embree-latest/include/embree3/rtcore_version.h:17-21).  The
+// semantics followed are the documented ones:
+//   * closest hit with t in [tnear, tfar]           share/man/man3/rtcIntersect1.3embree3:24
+//   * Ng unnormalised, object space, = cross(v1-v0, v2-v0)  rtcIntersect1.3embree3:53,
+//     RTC_GEOMETRY_TYPE_TRIANGLE.3embree3:52
+//   * triangle (u,v) are the weights of v1 and v2   RTC_GEOMETRY_TYPE_TRIANGLE.3embree3:47
+//   * quad = triangles (v0,v1,v3) and (v2,v3,v1); on the second u = 1-u', v = 1-v'
+//                                                   RTC_GEOMETRY_TYPE_QUAD.3embree3:38-41
+//   * no back-face culling; any-hit reports only "something in [tnear,tfar]"  rtcOccluded1.3embree3:43
+// "parity unpinned": the reference holds no golden vectors for this boundary and Embree itself cannot be
+// built here, so hit-ID parity is pinned only against the double-precision brute force below.
+//
+// A binned-SAH BVH2 with a scalar stack traversal; the triangle test is Moller-Trumbore evaluated in
+// Real (double for the hit-ID oracle, float for the timed CPU baseline).
+#pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace orc {
+
+struct Tri {
+    float v0[3], v1[3], v2[3];
+    uint32_t primID, geomID, instID;
+    uint32_t second;  // 1 = second half of a quad (u,v flipped on output)
+};
+
+struct RayHit {
+    double t, u, v;
+    uint32_t tri;  // index into tris, 0xFFFFFFFF = miss
+};
+
+template <typename Real>
+static inline bool intersect_tri(const Tri& T, const Real o[3], const Real d[3], Real tnear, Real tfar, Real& t,
+                                 Real& u, Real& v) {
+    Real e1[3], e2[3], p[3], s[3], q[3];
+    for (int k = 0; k < 3; ++k) {
+        e1[k] = (Real)T.v1[k] - (Real)T.v0[k];
+        e2[k] = (Real)T.v2[k] - (Real)T.v0[k];
+    }
+    p[0] = d[1] * e2[2] - d[2] * e2[1];
+    p[1] = d[2] * e2[0] - d[0] * e2[2];
+    p[2] = d[0] * e2[1] - d[1] * e2[0];
+    Real det = e1[0] * p[0] + e1[1] * p[1] + e1[2] * p[2];
+    if (det == (Real)0) return false;
+    Real inv = (Real)1 / det;
+    for (int k = 0; k < 3; ++k) s[k] = o[k] - (Real)T.v0[k];
+    Real uu = (s[0] * p[0] + s[1] * p[1] + s[2] * p[2]) * inv;
+    if (uu < (Real)0 || uu > (Real)1) return false;
+    q[0] = s[1] * e1[2] - s[2] * e1[1];
+    q[1] = s[2] * e1[0] - s[0] * e1[2];
+    q[2] = s[0] * e1[1] - s[1] * e1[0];
+    Real vv = (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]) * inv;
+    if (vv < (Real)0 || uu + vv > (Real)1) return false;
+    Real tt = (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) * inv;
+    if (!(tt >= tnear && tt <= tfar)) return false;
+    t = tt;
+    u = uu;
+    v = vv;
+    return true;
+}
+
+struct Node {
+    float lo[3], hi[3];
+    uint32_t left;   // inner: index of left child (right = left+1); leaf: first triangle
+    uint32_t count;  // 0 = inner
+};
+
+class Bvh {
+public:
+    std::vector<Tri> tris;
+    std::vector<Node> nodes;
+
+    void build() {
+        const size_t n = tris.size();
+        nodes.clear();
+        if (n == 0) return;
+        nodes.reserve(2 * n);
+        std::vector<float> cen(3 * n), blo(3 * n), bhi(3 * n);
+        order_.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            order_[i] = (uint32_t)i;
+            for (int k = 0; k < 3; ++k) {
+                float a = tris[i].v0[k], b = tris[i].v1[k], c = tris[i].v2[k];
+                float lo = std::min(a, std::min(b, c)), hi = std::max(a, std::max(b, c));
+                blo[3 * i + k] = lo;
+                bhi[3 * i + k] = hi;
+                cen[3 * i + k] = 0.5f * (lo + hi);
+            }
+        }
+        nodes.push_back(Node());
+        struct Job { uint32_t node, first, count; };
+        std::vector<Job> stack;
+        stack.push_back({0, 0, (uint32_t)n});
+        while (!stack.empty()) {
+            Job j = stack.back();
+            stack.pop_back();
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (uint32_t i = j.first; i < j.first + j.count; ++i) {
+                uint32_t t = order_[i];
+                for (int k = 0; k < 3; ++k) {
+                    lo[k] = std::min(lo[k], blo[3 * t + k]);
+                    hi[k] = std::max(hi[k], bhi[3 * t + k]);
+                    clo[k] = std::min(clo[k], cen[3 * t + k]);
+                    chi[k] = std::max(chi[k], cen[3 * t + k]);
+                }
+            }
+            Node nd;
+            for (int k = 0; k < 3; ++k) {
+                // pad one ulp-ish so that the double-precision triangle test never loses a hit to the box test
+                float pad = 4.0f * FLT_EPSILON * std::max(std::fabs(lo[k]), std::fabs(hi[k])) + FLT_MIN;
+                nd.lo[k] = lo[k] - pad;
+                nd.hi[k] = hi[k] + pad;
+            }
+            if (j.count <= 4) {
+                nd.left = j.first;
+                nd.count = j.count;
+                nodes[j.node] = nd;
+                continue;
+            }
+            // binned SAH, 16 bins per axis
+            const int B = 16;
+            int bestAxis = -1, bestSplit = 0;
+            float bestCost = FLT_MAX;
+            for (int ax = 0; ax < 3; ++ax) {
+                float ext = chi[ax] - clo[ax];
+                if (!(ext > 0.0f)) continue;
+                float scale = B / ext;
+                int cnt[B] = {0};
+                float bl[B][3], bh[B][3];
+                for (int b = 0; b < B; ++b)
+                    for (int k = 0; k < 3; ++k) { bl[b][k] = FLT_MAX; bh[b][k] = -FLT_MAX; }
+                for (uint32_t i = j.first; i < j.first + j.count; ++i) {
+                    uint32_t t = order_[i];
+                    int b = std::min(B - 1, (int)((cen[3 * t + ax] - clo[ax]) * scale));
+                    cnt[b]++;
+                    for (int k = 0; k < 3; ++k) {
+                        bl[b][k] = std::min(bl[b][k], blo[3 * t + k]);
+                        bh[b][k] = std::max(bh[b][k], bhi[3 * t + k]);
+                    }
+                }
+                float rarea[B];
+                int rcnt[B];
+                float al[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, ah[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+                int c = 0;
+                for (int b = B - 1; b > 0; --b) {
+                    c += cnt[b];
+                    for (int k = 0; k < 3; ++k) { al[k] = std::min(al[k], bl[b][k]); ah[k] = std::max(ah[k], bh[b][k]); }
+                    rarea[b] = c ? half_area(al, ah) : 0.0f;
+                    rcnt[b] = c;
+                }
+                for (int k = 0; k < 3; ++k) { al[k] = FLT_MAX; ah[k] = -FLT_MAX; }
+                c = 0;
+                for (int b = 0; b < B - 1; ++b) {
+                    c += cnt[b];
+                    for (int k = 0; k < 3; ++k) { al[k] = std::min(al[k], bl[b][k]); ah[k] = std::max(ah[k], bh[b][k]); }
+                    if (c == 0 || rcnt[b + 1] == 0) continue;
+                    float cost = half_area(al, ah) * c + rarea[b + 1] * rcnt[b + 1];
+                    if (cost < bestCost) { bestCost = cost; bestAxis = ax; bestSplit = b; }
+                }
+            }
+            uint32_t mid;
+            if (bestAxis < 0) {
+                mid = j.first + j.count / 2;  // all centroids coincide: median split
+            } else {
+                float scale = B / (chi[bestAxis] - clo[bestAxis]);
+                float c0 = clo[bestAxis];
+                int ax = bestAxis, sp = bestSplit;
+                auto it = std::partition(order_.begin() + j.first, order_.begin() + j.first + j.count, [&](uint32_t t) {
+                    int b = std::min(B - 1, (int)((cen[3 * t + ax] - c0) * scale));
+                    return b <= sp;
+                });
+                mid = (uint32_t)(it - order_.begin());
+                if (mid == j.first || mid == j.first + j.count) mid = j.first + j.count / 2;
+            }
+            nd.count = 0;
+            nd.left = (uint32_t)nodes.size();
+            nodes[j.node] = nd;
+            nodes.push_back(Node());
+            nodes.push_back(Node());
+            stack.push_back({nd.left, j.first, mid - j.first});
+            stack.push_back({nd.left + 1, mid, j.first + j.count - mid});
+        }
+        std::vector<Tri> sorted(n);
+        for (size_t i = 0; i < n; ++i) sorted[i] = tris[order_[i]];
+        tris.swap(sorted);
+        order_.clear();
+        order_.shrink_to_fit();
+    }
+
+    // Closest hit (anyHit=false) or any hit (anyHit=true) with t in [tnear,tfar].
+    template <typename Real>
+    bool trace(const float of[3], const float df[3], float tnear, float tfar, bool anyHit, RayHit& out) const {
+        out.tri = 0xFFFFFFFFu;
+        out.t = tfar;
+        out.u = out.v = 0;
+        if (nodes.empty()) return false;
+        Real o[3] = {(Real)of[0], (Real)of[1], (Real)of[2]}, d[3] = {(Real)df[0], (Real)df[1], (Real)df[2]};
+        Real inv[3];
+        for (int k = 0; k < 3; ++k) inv[k] = (Real)1 / d[k];  // +-inf on zero components is fine for the slab test
+        Real best = (Real)tfar, tn = (Real)tnear;
+        uint32_t stack[128];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const Node& nd = nodes[stack[--sp]];
+            if (!slab(nd, o, inv, tn, best)) continue;
+            if (nd.count) {
+                for (uint32_t i = nd.left; i < nd.left + nd.count; ++i) {
+                    Real t, u, v;
+                    if (intersect_tri<Real>(tris[i], o, d, tn, best, t, u, v)) {
+                        // strict '<' keeps the first-found on exact ties unless this one is closer
+                        if (out.tri == 0xFFFFFFFFu || t < best || (t == best && i < out.tri)) {
+                            best = t;
+                            out.t = (double)t;
+                            out.u = (double)u;
+                            out.v = (double)v;
+                            out.tri = i;
+                            if (anyHit) return true;
+                        }
+                    }
+                }
+            } else {
+                stack[sp++] = nd.left;
+                stack[sp++] = nd.left + 1;
+            }
+        }
+        return out.tri != 0xFFFFFFFFu;
+    }
+
+    // Exhaustive double-precision reference used to pin the BVH itself.
+    bool brute(const float of[3], const float df[3], float tnear, float tfar, RayHit& out) const {
+        double o[3] = {of[0], of[1], of[2]}, d[3] = {df[0], df[1], df[2]};
+        out.tri = 0xFFFFFFFFu;
+        out.t = tfar;
+        out.u = out.v = 0;
+        double best = tfar;
+        for (size_t i = 0; i < tris.size(); ++i) {
+            double t, u, v;
+            if (intersect_tri<double>(tris[i], o, d, (double)tnear, best, t, u, v)) {
+                if (out.tri == 0xFFFFFFFFu || t < best) {
+                    best = t;
+                    out.t = t; out.u = u; out.v = v;
+                    out.tri = (uint32_t)i;
+                }
+            }
+        }
+        return out.tri != 0xFFFFFFFFu;
+    }
+
+private:
+    std::vector<uint32_t> order_;
+    static float half_area(const float lo[3], const float hi[3]) {
+        float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return x * y + y * z + z * x;
+    }
+    template <typename Real>
+    static bool slab(const Node& nd, const Real o[3], const Real inv[3], Real tn, Real tf) {
+        Real t0 = tn, t1 = tf;
+        for (int k = 0; k < 3; ++k) {
+            Real a = ((Real)nd.lo[k] - o[k]) * inv[k], b = ((Real)nd.hi[k] - o[k]) * inv[k];
+            if (a != a || b != b) continue;  // 0*inf: ray lies in the slab plane, no constraint
+            if (a > b) std::swap(a, b);
+            // widen a hair so rounding in the slab test never rejects a box whose triangle is hit
+            t0 = std::max(t0, a - std::fabs(a) * (Real)1e-6);
+            t1 = std::min(t1, b + std::fabs(b) * (Real)1e-6);
+        }
+        return t0 <= t1;
+    }
+};
+
+}  // namespace orc

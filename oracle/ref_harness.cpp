@@ -1,0 +1,648 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+//
+// Thin extern "C" wrappers (prefix ref_) around the UNMODIFIED reference translation units, which
+// oracle/Makefile compiles in place from /root/reference into oracle/_ref/libselas_ref.so.  Nothing from the
+// reference is copied into this repository; this file only calls it.  It provides
+//   * the few link-time symbols the reference's platform layer would supply (allocator, asset path, file
+//     read) and a CSampler whose uniform stream can be scripted, so that SampleBsdfFunction /
+//     NextEventEstimation can be driven with the same numbers as the CUDA kernels;
+//   * ref_render_pathtracer: the reference's own EvaluateBsdf / SampleBsdfFunction / NextEventEstimation /
+//     medium functions driven by a restated EvaluatePath loop (PathTracer.cpp:142-258) over the oracle's
+//     CPU BVH, because Embree (the reference's ray caster) is not available.  This is BASELINE.md's tier B
+//     "reference shading + restated ray cast".
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include <xmmintrin.h>
+#include <pmmintrin.h>
+
+#include "Shading/SurfaceScattering.h"
+#include "Shading/SurfaceParameters.h"
+#include "Shading/AreaLighting.h"
+#include "Shading/IntegratorContexts.h"
+#include "Shading/VolumetricScattering.h"
+#include "Shading/Scattering.h"
+#include "SceneLib/SceneResource.h"
+#include "GeometryLib/Camera.h"
+#include "GeometryLib/Ray.h"
+#include "GeometryLib/CoordinateSystem.h"
+#include "MathLib/Sampler.h"
+#include "MathLib/CorrelatedMultiJitter.h"
+#include "MathLib/FloatFuncs.h"
+#include "IoLib/File.h"
+#include "Assets/AssetFileUtils.h"
+#include "VCMHashGrid.h"
+#include "VCMCommon.h"
+
+#include "../include/selas_cuda.h"
+#include "cpu_bvh.h"
+
+static_assert(sizeof(SelasSurface) == sizeof(Selas::SurfaceParameters), "SurfaceParameters layout");
+static_assert(sizeof(SelasLight) == sizeof(Selas::SceneLight), "SceneLight layout");
+static_assert(sizeof(SelasCamera) == sizeof(Selas::RayCastCameraSettings), "RayCastCameraSettings layout");
+static_assert(sizeof(Selas::BsdfSample) == 52, "BsdfSample layout");
+static_assert(sizeof(Selas::LightDirectSample) == sizeof(SelasLightSample), "LightDirectSample layout");
+
+// ---- scripted uniform source ------------------------------------------------------------------------------
+namespace {
+struct DrawSource {
+    const float* script;  // scripted values (bsdf/light unit tests) ...
+    uint32_t pos, count;
+    uint32_t pcg;  // ... or the product's PCG stream (integrator)
+    bool usePcg;
+};
+thread_local DrawSource g_src = {nullptr, 0, 0, 0, false};
+thread_local std::mt19937* g_mt = nullptr;
+
+inline uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+inline float pcgNext(uint32_t& state) {
+    state = state * 747796405u + 2891336453u;
+    uint32_t w = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+    w = (w >> 22u) ^ w;
+    return (float)(w >> 8) * (1.0f / 16777216.0f);
+}
+void setFtz() {
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+    _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
+}
+}  // namespace
+
+namespace Selas {
+// platform shims -------------------------------------------------------------------------------------------
+void* SelasMalloc(uint64 size, const char*, const char*, int) { return malloc(size); }
+void* SelasRealloc(void* p, uint64 size, const char*, const char*, int) { return realloc(p, size); }
+void SelasFree(void* p) { free(p); }
+void* SelasAlignedMalloc(uint64 size, uint64 alignment, const char*, const char*, int) {
+    void* p = nullptr;
+    if (posix_memalign(&p, alignment < sizeof(void*) ? sizeof(void*) : alignment, size)) return nullptr;
+    return p;
+}
+void SelasAlignedFree(void* p) { free(p); }
+namespace AssetFileUtils {
+void AssetFilePath(cpointer, uint64, cpointer, FilePathString& filepath) { filepath.Clear(); }
+}
+namespace File {
+Error ReadWholeFile(cpointer, void**, uint64*) { return Error_("oracle harness: no file IO"); }
+}
+// Shading/SurfaceParameters.cpp is not linked (it needs Embree + the caches); these two accessors are the
+// only symbols of it the BSDF code uses.  They read column 1 of worldToTangent (SurfaceParameters.cpp:391).
+float3 GeometricNormal(const SurfaceParameters& surface) {
+    return float3(surface.worldToTangent.r0.y, surface.worldToTangent.r1.y, surface.worldToTangent.r2.y);
+}
+float3 OffsetRayOrigin(const SurfaceParameters& surface, float3 direction, float biasScale) {
+    float directionOffset = Dot(direction, GeometricNormal(surface)) < 0.0f ? -1.0f : 1.0f;
+    float3 offset = directionOffset * surface.error * biasScale * GeometricNormal(surface);
+    return surface.position + offset;
+}
+
+// CSampler with a scriptable stream (MathLib/Sampler.cpp is not linked).
+void CSampler::Initialize(uint32 seed) {
+    if (!g_mt) g_mt = new std::mt19937();
+    g_mt->seed(seed);
+}
+void CSampler::Shutdown() {}
+void CSampler::Reseed(uint32 seed) { Initialize(seed); }
+float CSampler::UniformFloat() {
+    DrawSource& s = g_src;
+    if (s.usePcg) return pcgNext(s.pcg);
+    if (s.script) {
+        float v = s.pos < s.count ? s.script[s.pos] : 0.5f;
+        ++s.pos;
+        return v;
+    }
+    if (!g_mt) g_mt = new std::mt19937(0);
+    return (*g_mt)() / (float)(0xFFFFFFFF);  // MathLib/Random.cpp:47-50
+}
+uint32 CSampler::UniformUInt32() {
+    if (!g_mt) g_mt = new std::mt19937(0);
+    return (uint32)(*g_mt)();
+}
+float3 CSampler::UniformSphere() {  // MathLib/Sampler.cpp:44-54, restated because that TU is not linked
+    float r0 = UniformFloat();
+    float r1 = UniformFloat();
+    float u = 2.0f * r1 - 1.0f;
+    float norm = Math::Sqrtf(Max(0.0f, 1.0f - u * u));
+    float theta = Math::TwoPi_ * r0;
+    return float3(norm * Math::Cosf(theta), u, norm * Math::Sinf(theta));
+}
+float CSampler::UniformSpherePdf() { return Math::Inv4Pi_; }
+}  // namespace Selas
+
+using namespace Selas;
+
+namespace {
+
+// A GIIntegratorContext + SceneResource carved out of zeroed storage: their constructors live in TUs that
+// need Embree, and only `sampler`, `scene->lightSets`, `scene->data->backgroundIntensity`, `scene->iblResource`
+// are read by the functions called here.
+struct FakeContext {
+    alignas(16) unsigned char ctxBytes[sizeof(GIIntegratorContext)];
+    alignas(16) unsigned char sceneBytes[sizeof(SceneResource)];
+    alignas(16) unsigned char dataBytes[sizeof(SceneResourceData)];
+    std::vector<SceneLight> lights;
+    std::vector<SceneLightSet> sets;
+    GIIntegratorContext* ctx() { return reinterpret_cast<GIIntegratorContext*>(ctxBytes); }
+    SceneResource* scene() { return reinterpret_cast<SceneResource*>(sceneBytes); }
+    SceneResourceData* data() { return reinterpret_cast<SceneResourceData*>(dataBytes); }
+
+    void init(const SelasLight* L, uint32_t lightCount, const SelasLightSetRange* ranges, uint32_t setCount,
+              const float* background) {
+        memset(ctxBytes, 0, sizeof(ctxBytes));
+        memset(sceneBytes, 0, sizeof(sceneBytes));
+        memset(dataBytes, 0, sizeof(dataBytes));
+        lights.resize(lightCount);
+        if (lightCount) memcpy(lights.data(), L, sizeof(SceneLight) * lightCount);
+        sets.clear();
+        for (uint32_t i = 0; i < setCount; ++i) {
+            SceneLightSet s;
+            s.count = ranges[i].count;
+            s.lights = lights.data() + ranges[i].start;
+            sets.push_back(s);
+        }
+        // CArray<SceneLightSet> laid out as {flags,pad,count,capacity,data} (ContainersLib/CArray.h:57-62)
+        struct RawArray { uint32_t flags, pad; uint64_t count, capacity; void* data; };
+        static_assert(sizeof(RawArray) == sizeof(CArray<SceneLightSet>), "CArray layout");
+        RawArray raw = {0, 0, sets.size(), sets.size(), sets.data()};
+        memcpy(&scene()->lightSets, &raw, sizeof(raw));
+        if (background) data()->backgroundIntensity = float4(background[0], background[1], background[2], background[3]);
+        scene()->data = data();
+        scene()->iblResource = nullptr;
+        ctx()->scene = scene();
+    }
+    ~FakeContext() {
+        // make the borrowed CArray look empty so nothing is freed
+        memset(&scene()->lightSets, 0, sizeof(scene()->lightSets));
+    }
+};
+
+inline float3 f3(const float* p) { return float3(p[0], p[1], p[2]); }
+inline void st3(float* p, float3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+
+void copySample(const BsdfSample& b, bool ok, uint32_t used, SelasBsdfSample& o) {
+    o.flags = b.flags;
+    o.mediumPhase = (uint32_t)b.medium.phaseFunction;
+    st3(o.mediumExtinction, b.medium.extinction);
+    st3(o.reflectance, b.reflectance);
+    st3(o.wi, b.wi);
+    o.forwardPdfW = b.forwardPdfW;
+    o.reversePdfW = b.reversePdfW;
+    o.valid = ok ? 1u : 0u;
+    o.randomsUsed = used;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ref_sizeof(const char* name) {
+    if (!strcmp(name, "SurfaceParameters")) return (int)sizeof(SurfaceParameters);
+    if (!strcmp(name, "BsdfSample")) return (int)sizeof(BsdfSample);
+    if (!strcmp(name, "SceneLight")) return (int)sizeof(SceneLight);
+    if (!strcmp(name, "HitParameters")) return (int)sizeof(HitParameters);
+    if (!strcmp(name, "RayCastCameraSettings")) return (int)sizeof(RayCastCameraSettings);
+    if (!strcmp(name, "VCMVertex")) return (int)sizeof(VCMVertex);
+    if (!strcmp(name, "MaterialResourceData")) return (int)sizeof(MaterialResourceData);
+    return -1;
+}
+
+int ref_bsdf_eval(size_t n, const SelasSurface* s, const float* v, const float* l, float* rgb, float* fwd, float* rev) {
+    setFtz();
+    for (size_t i = 0; i < n; ++i) {
+        SurfaceParameters sp;
+        memcpy(&sp, &s[i], sizeof(sp));
+        float f = 0.f, r = 0.f;
+        float3 c = EvaluateBsdf(sp, f3(v + 3 * i), f3(l + 3 * i), f, r);
+        st3(rgb + 3 * i, c);
+        fwd[i] = f;
+        rev[i] = r;
+    }
+    return 0;
+}
+
+int ref_bsdf_sample(size_t n, const SelasSurface* s, const float* v, const float* u, SelasBsdfSample* out) {
+    setFtz();
+    CSampler sampler;
+    for (size_t i = 0; i < n; ++i) {
+        SurfaceParameters sp;
+        memcpy(&sp, &s[i], sizeof(sp));
+        g_src = DrawSource{u + SELAS_BSDF_RANDOMS * i, 0, SELAS_BSDF_RANDOMS, 0, false};
+        BsdfSample bs;
+        bs.flags = eScatterEvent;  // no default in Scattering.h:36; see SURVEY.md appendix B #4
+        bool ok = SampleBsdfFunction(&sampler, sp, f3(v + 3 * i), bs);
+        copySample(bs, ok, g_src.pos, out[i]);
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+
+int ref_light_sample(size_t n, const SelasLight* lights, uint32_t count, const float* pos, const float* nrm, const float* u3,
+                     SelasLightSample* out) {
+    setFtz();
+    FakeContext fc;
+    SelasLightSetRange range = {0, count};
+    fc.init(lights, count, &range, 1, nullptr);
+    for (size_t i = 0; i < n; ++i) {
+        // clamp the p0 == 1.0 overrun the same way the restatement does (appendix B #20)
+        float uu[3] = {u3[3 * i], u3[3 * i + 1], u3[3 * i + 2]};
+        if (count && (uint32_t)(uu[0] * count) >= count) uu[0] = nextafterf(1.0f, 0.0f);
+        g_src = DrawSource{uu, 0, 3, 0, false};
+        LightDirectSample ls;
+        memset(&ls, 0, sizeof(ls));
+        NextEventEstimation(fc.ctx(), 0, f3(pos + 3 * i), f3(nrm + 3 * i), ls);
+        memcpy(&out[i], &ls, sizeof(ls));
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+
+int ref_light_pdf(size_t n, const SelasLight* lights, uint32_t count, const uint32_t* index, const float* pos, const float* wi,
+                  float* pdf) {
+    setFtz();
+    FakeContext fc;
+    SelasLightSetRange range = {0, count};
+    fc.init(lights, count, &range, 1, nullptr);
+    for (size_t i = 0; i < n; ++i) {
+        LightDirectSample ls;
+        memset(&ls, 0, sizeof(ls));
+        ls.index = index[i];
+        pdf[i] = LightingPdf(fc.ctx(), 0, ls, f3(pos + 3 * i), f3(wi + 3 * i));
+    }
+    return 0;
+}
+
+int ref_camera_init(const SelasCameraSettings* st, uint32_t w, uint32_t h, SelasCamera* out) {
+    CameraSettings cs;
+    memset(&cs, 0, sizeof(cs));
+    cs.position = f3(st->position);
+    cs.fovDegrees = st->fovDegrees;
+    cs.lookAt = f3(st->lookAt);
+    cs.znear = st->znear;
+    cs.up = f3(st->up);
+    cs.zfar = st->zfar;
+    RayCastCameraSettings rc;
+    memset(&rc, 0, sizeof(rc));
+    InitializeRayCastCamera(cs, w, h, rc);
+    memcpy(out, &rc, sizeof(rc));
+    return 0;
+}
+
+int ref_camera_rays(const SelasCamera* cam, size_t n, const float* px, const float* py, const float* jitter, SelasRay* rays) {
+    RayCastCameraSettings rc;
+    memcpy(&rc, cam, sizeof(rc));
+    CSampler sampler;
+    for (size_t i = 0; i < n; ++i) {
+        float jj[2] = {jitter ? jitter[2 * i] : 0.5f, jitter ? jitter[2 * i + 1] : 0.5f};
+        g_src = DrawSource{jj, 0, 2, 0, false};
+        Ray r = JitteredCameraRay(&rc, &sampler, px[i], py[i]);
+        rays[i].ox = r.origin.x; rays[i].oy = r.origin.y; rays[i].oz = r.origin.z;
+        rays[i].tnear = 0.0f;
+        rays[i].dx = r.direction.x; rays[i].dy = r.direction.y; rays[i].dz = r.direction.z;
+        rays[i].tfar = FloatMax_;
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+
+int ref_cmj(size_t n, const int32_t* s, int32_t m, int32_t nn, const int32_t* p, float* out2) {
+    for (size_t i = 0; i < n; ++i) {
+        float2 r = CorrelatedMultiJitter(s[i], m, nn, p[i]);
+        out2[2 * i] = r.x;
+        out2[2 * i + 1] = r.y;
+    }
+    return 0;
+}
+
+int ref_medium(size_t n, const float* extinction3, const float* u2, const float* dist, float* sampled, float* trans3) {
+    CSampler sampler;
+    for (size_t i = 0; i < n; ++i) {
+        MediumParameters m;
+        m.phaseFunction = eIsotropic;
+        m.extinction = f3(extinction3 + 3 * i);
+        g_src = DrawSource{u2 + 2 * i, 0, 2, 0, false};
+        float pdf;
+        sampled[i] = SampleDistance(&sampler, m, &pdf);
+        st3(trans3 + 3 * i, Transmission(m, dist[i]));
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+
+// BuildHashGrid + readback of its arrays (VCMHashGrid.cpp:48-97)
+int ref_hashgrid_build(size_t n, const float* pos, float radius, uint32_t cellCount, uint32_t* cellRangeEnds,
+                       uint32_t* cellIndices, float* aabb6) {
+    CArray<VCMVertex> verts;
+    verts.Resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        memset(&verts[i], 0, sizeof(VCMVertex));
+        verts[i].hit.position = f3(pos + 3 * i);
+    }
+    VCMHashGrid grid;
+    BuildHashGrid(&grid, cellCount, radius, verts);
+    memcpy(cellRangeEnds, grid.cellRangeEnds.DataPointer(), sizeof(uint32_t) * cellCount);
+    memcpy(cellIndices, grid.cellIndices.DataPointer(), sizeof(uint32_t) * n);
+    st3(aabb6, grid.aaBox.min);
+    st3(aabb6 + 3, grid.aaBox.max);
+    ShutdownHashGrid(&grid);
+    verts.Shutdown();
+    return 0;
+}
+
+struct QueryCollect {
+    const VCMVertex* base;
+    uint32_t* indices;
+    uint32_t count, maxCount;
+};
+static void collectCallback(const VCMVertex& v, void* user) {
+    QueryCollect* q = (QueryCollect*)user;
+    if (q->indices && q->count < q->maxCount) q->indices[q->count] = (uint32_t)(&v - q->base);
+    ++q->count;
+}
+// BuildHashGrid then SearchHashGrid for every query (VCMHashGrid.cpp:107-155); returns build and query seconds
+int ref_hashgrid_query(size_t n, const float* pos, float radius, uint32_t cellCount, size_t m, const float* q, uint32_t* counts,
+                       uint32_t* indices, uint32_t maxPerQuery) {
+    CArray<VCMVertex> verts;
+    verts.Resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        memset(&verts[i], 0, sizeof(VCMVertex));
+        verts[i].hit.position = f3(pos + 3 * i);
+    }
+    VCMHashGrid grid;
+    BuildHashGrid(&grid, cellCount, radius, verts);
+    for (size_t i = 0; i < m; ++i) {
+        QueryCollect qc = {verts.DataPointer(), indices ? indices + i * maxPerQuery : nullptr, 0, maxPerQuery};
+        SearchHashGrid(&grid, verts, f3(q + 3 * i), &qc, collectCallback);
+        counts[i] = qc.count;
+    }
+    ShutdownHashGrid(&grid);
+    verts.Shutdown();
+    return 0;
+}
+
+int ref_vcm_iteration_constants(uint32_t vmCount, uint32_t vcCount, float baseRadius, float alpha, float iteration, float* out5) {
+    VCMIterationConstants c = VCMCommon::CalculateIterationConstants(vmCount, vcCount, baseRadius, alpha, iteration);
+    out5[0] = c.vmSearchRadius;
+    out5[1] = c.vmSearchRadiusSqr;
+    out5[2] = c.vmNormalization;
+    out5[3] = c.vmWeight;
+    out5[4] = c.vcWeight;
+    return 0;
+}
+
+// ---- tier-B CPU integrator: reference shading + restated ray cast --------------------------------------------
+struct RefScene {
+    struct Mesh {
+        std::vector<float> positions, normals, tangents;
+        std::vector<uint32_t> indices;
+        uint32_t indicesPerFace, materialIndex, lightSetIndex;
+    };
+    std::vector<Mesh> meshes;
+    std::vector<SelasMaterial> materials;
+    std::vector<SelasLight> lights;
+    std::vector<SelasLightSetRange> sets;
+    float background[4];
+    orc::Bvh bvh;
+};
+
+int ref_scene_create(const SelasSceneDesc* d, void** out) {
+    if (d->instanceCount) return 5;  // the tier-B integrator handles the identity single-instance scenes only
+    RefScene* sc = new RefScene();
+    sc->meshes.resize(d->meshCount);
+    for (uint32_t m = 0; m < d->meshCount; ++m) {
+        const SelasMeshDesc& md = d->meshes[m];
+        RefScene::Mesh& M = sc->meshes[m];
+        M.positions.assign(md.positions, md.positions + 3 * (size_t)md.vertexCount);
+        if (md.normals) M.normals.assign(md.normals, md.normals + 3 * (size_t)md.vertexCount);
+        if (md.tangents) M.tangents.assign(md.tangents, md.tangents + 4 * (size_t)md.vertexCount);
+        M.indices.assign(md.indices, md.indices + (size_t)md.faceCount * md.indicesPerFace);
+        M.indicesPerFace = md.indicesPerFace;
+        M.materialIndex = md.materialIndex;
+        M.lightSetIndex = md.lightSetIndex;
+        for (uint32_t f = 0; f < md.faceCount; ++f) {
+            const uint32_t* ix = &M.indices[(size_t)f * M.indicesPerFace];
+            orc::Tri T;
+            T.primID = f; T.geomID = m; T.instID = 0; T.second = 0;
+            auto P = [&](uint32_t vi, float* o) { memcpy(o, &M.positions[3 * (size_t)vi], 12); };
+            if (M.indicesPerFace == 3) {
+                P(ix[0], T.v0); P(ix[1], T.v1); P(ix[2], T.v2);
+                sc->bvh.tris.push_back(T);
+            } else {
+                P(ix[0], T.v0); P(ix[1], T.v1); P(ix[3], T.v2);
+                sc->bvh.tris.push_back(T);
+                T.second = 1;
+                P(ix[2], T.v0); P(ix[3], T.v1); P(ix[1], T.v2);
+                sc->bvh.tris.push_back(T);
+            }
+        }
+    }
+    sc->materials.assign(d->materials, d->materials + d->materialCount);
+    sc->lights.assign(d->lights, d->lights + d->lightCount);
+    sc->sets.assign(d->lightSets, d->lightSets + d->lightSetCount);
+    memcpy(sc->background, d->backgroundIntensity, sizeof(sc->background));
+    sc->bvh.build();
+    *out = sc;
+    return 0;
+}
+int ref_scene_destroy(void* s) {
+    delete (RefScene*)s;
+    return 0;
+}
+
+// CalculateSurfaceParams (SurfaceParameters.cpp:144-247) with the rtcInterpolate0 gathers and the
+// material/cache lookups replaced by direct array reads; everything downstream is reference code.
+static void refSurface(const RefScene& sc, const Ray& ray, float t, float u, float v, uint32_t geomID, uint32_t primID,
+                       SurfaceParameters& surface) {
+    const RefScene::Mesh& M = sc.meshes[geomID];
+    const SelasMaterial& mat = sc.materials[M.materialIndex];
+    const uint32_t* ix = &M.indices[(size_t)primID * M.indicesPerFace];
+    auto interp = [&](const std::vector<float>& a, int comps, float* o) {
+        for (int c = 0; c < comps; ++c) {
+            if (M.indicesPerFace == 3)
+                o[c] = (1.0f - u - v) * a[ix[0] * comps + c] + u * a[ix[1] * comps + c] + v * a[ix[2] * comps + c];
+            else
+                o[c] = (1.0f - v) * ((1.0f - u) * a[ix[0] * comps + c] + u * a[ix[1] * comps + c]) +
+                       v * ((1.0f - u) * a[ix[3] * comps + c] + u * a[ix[2] * comps + c]);
+        }
+    };
+    float3 normal;
+    if (!M.normals.empty()) {
+        float nn[3];
+        interp(M.normals, 3, nn);
+        normal = f3(nn);
+    } else {
+        const float* P = M.positions.data();
+        uint32_t i0, i1, i2;
+        if (M.indicesPerFace == 3) { i0 = ix[0]; i1 = ix[1]; i2 = ix[2]; }
+        else if (u + v <= 1.0f) { i0 = ix[0]; i1 = ix[1]; i2 = ix[3]; }
+        else { i0 = ix[2]; i1 = ix[3]; i2 = ix[1]; }
+        normal = Cross(f3(P + 3 * i1) - f3(P + 3 * i0), f3(P + 3 * i2) - f3(P + 3 * i0));
+    }
+    float3 n = Normalize(normal);
+    float3 tt, b;
+    if (!M.tangents.empty()) {
+        float tg[4];
+        interp(M.tangents, 4, tg);
+        tt = f3(tg);
+        b = Cross(n, tt) * tg[3];
+    } else {
+        MakeOrthogonalCoordinateSystem(n, &tt, &b);
+    }
+    surface.baseColor = Pow(f3(mat.baseColor), 2.2f);
+    float3x3 tangentToWorld = MakeFloat3x3(tt, n, b);
+    surface.worldToTangent = MatrixTranspose(tangentToWorld);
+    float3 pos = float3(ray.origin.x + t * ray.direction.x, ray.origin.y + t * ray.direction.y, ray.origin.z + t * ray.direction.z);
+    surface.position = pos;
+    const float kErr = 32.0f * 1.19209e-07f;
+    surface.error = kErr * Max(Max(Math::Absf(pos.x), Math::Absf(pos.y)), Max(Math::Absf(pos.z), t));
+    surface.materialFlags = mat.flags;
+    surface.transmittanceColor = f3(mat.transmittanceColor);
+    surface.sheen = mat.scalars[eSheen];
+    surface.sheenTint = mat.scalars[eSheenTint];
+    surface.clearcoat = mat.scalars[eClearcoat];
+    surface.clearcoatGloss = mat.scalars[eClearcoatGloss];
+    surface.specTrans = Saturate(mat.scalars[eSpecTrans]);
+    surface.diffTrans = mat.scalars[eDiffuseTrans] * 0.5f;
+    surface.flatness = mat.scalars[eFlatness];
+    surface.anisotropic = mat.scalars[eAnisotropic];
+    surface.specularTint = mat.scalars[eSpecularTint];
+    surface.roughness = mat.scalars[eRoughness];
+    surface.metallic = Saturate(mat.scalars[eMetallic]);
+    surface.scatterDistance = mat.scalars[eScatterDistance];
+    surface.ior = mat.scalars[eIor];
+    surface.lightSetIndex = M.lightSetIndex;
+    surface.shader = (ShaderType)mat.shader;
+    surface.view = -ray.direction;
+    surface.relativeIOR = ((mat.flags & eTransparent) && Dot(surface.view, n) < 0.0f) ? surface.ior : 1.0f / surface.ior;
+}
+
+int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSettings* rs, float* const* film,
+                          SelasRenderStats* stats, int nthreads) {
+    const RefScene& sc = *(RefScene*)s;
+    size_t pixels = (size_t)rs->width * rs->height;
+    for (uint32_t l = 0; l < rs->layerCount; ++l) memset(film[l], 0, pixels * 3 * sizeof(float));
+    RayCastCameraSettings rc;
+    memcpy(&rc, cam, sizeof(rc));
+    std::atomic<size_t> next(0);
+    std::atomic<uint64_t> closest(0), shadow(0);
+    auto worker = [&]() {
+        setFtz();
+        FakeContext fc;
+        fc.init(sc.lights.data(), (uint32_t)sc.lights.size(), sc.sets.data(), (uint32_t)sc.sets.size(), sc.background);
+        GIIntegratorContext* ctx = fc.ctx();
+        ctx->camera = &rc;
+        ctx->maxPathLength = rs->maxPathLength;
+        uint64_t c = 0, sh = 0;
+        for (;;) {
+            size_t b = next.fetch_add(1024);
+            if (b >= pixels) break;
+            size_t e = std::min(pixels, b + 1024);
+            for (size_t p = b; p < e; ++p) {
+                uint32_t y = (uint32_t)(p / rs->width), x = (uint32_t)(p - (size_t)y * rs->width);
+                for (uint32_t k = 0; k < rs->samplesPerPixel; ++k) {
+                    g_src = DrawSource{nullptr, 0, 0, mix32(rs->seed ^ mix32((uint32_t)p ^ mix32(rs->firstSample + k + 0x9e3779b9u))), true};
+                    Ray ray = JitteredCameraRay(&rc, &ctx->sampler, (float)x, (float)y);
+                    // ---- EvaluatePath, PathTracer.cpp:142-258 ----
+                    float3 Ld[2] = {float3::Zero_, float3::Zero_};
+                    float3 throughput = float3::One_;
+                    MediumParameters vacuum;
+                    MediumParameters currentMedium = vacuum;
+                    bool isDeltaOnly = true;
+                    uint32_t bounceCount = 0;
+                    while (bounceCount < ctx->maxPathLength) {
+                        float pdf;
+                        float rayDistance = SampleDistance(&ctx->sampler, currentMedium, &pdf);
+                        orc::RayHit rh;
+                        float o[3] = {ray.origin.x, ray.origin.y, ray.origin.z}, d[3] = {ray.direction.x, ray.direction.y, ray.direction.z};
+                        bool hit = sc.bvh.trace<float>(o, d, 0.0f, rayDistance, false, rh);
+                        ++c;
+                        SurfaceParameters surface;
+                        if (hit) {
+                            const orc::Tri& T = sc.bvh.tris[rh.tri];
+                            float hu = T.second ? (float)(1.0 - rh.u) : (float)rh.u, hv = T.second ? (float)(1.0 - rh.v) : (float)rh.v;
+                            refSurface(sc, ray, (float)rh.t, hu, hv, T.geomID, T.primID, surface);
+                            rayDistance = Length(surface.position - ray.origin);
+                        }
+                        throughput = throughput * Transmission(currentMedium, rayDistance);
+                        if (hit) {
+                            LightDirectSample lightSample;
+                            memset(&lightSample, 0, sizeof(lightSample));
+                            NextEventEstimation(ctx, surface.lightSetIndex, surface.position, GeometricNormal(surface), lightSample);
+                            if (Dot(lightSample.radiance, float3::One_) > 0) {
+                                float fw = 0, rv = 0;
+                                float3 reflectance = EvaluateBsdf(surface, -ray.direction, lightSample.direction, fw, rv);
+                                if (Dot(reflectance, float3::One_) > 0) {
+                                    float3 org = OffsetRayOrigin(surface, lightSample.direction, 0.1f);
+                                    float so[3] = {org.x, org.y, org.z}, sd[3] = {lightSample.direction.x, lightSample.direction.y, lightSample.direction.z};
+                                    orc::RayHit shh;
+                                    ++sh;
+                                    if (!sc.bvh.trace<float>(so, sd, surface.error, lightSample.distance, true, shh)) {
+                                        float3 smp = reflectance * lightSample.radiance * (1.0f / lightSample.pdfW);
+                                        Ld[1] += smp * throughput;
+                                    }
+                                }
+                            }
+                            BsdfSample bsdfSample;
+                            bsdfSample.flags = eScatterEvent;
+                            if (SampleBsdfFunction(&ctx->sampler, surface, -ray.direction, bsdfSample) == false) break;
+                            isDeltaOnly = isDeltaOnly && (bsdfSample.flags & SurfaceEventFlags::eDiracEvent);
+                            if (bsdfSample.flags == SurfaceEventFlags::eTransmissionEvent) {
+                                if (currentMedium.phaseFunction == eVacuum) currentMedium = bsdfSample.medium;
+                                else currentMedium = vacuum;
+                            }
+                            float weight = 1.0f;
+                            if (rs->misMode == 1) {
+                                float lightPdfW = LightingPdf(ctx, surface.lightSetIndex, lightSample, surface.position, bsdfSample.wi);
+                                weight = bsdfSample.forwardPdfW / (bsdfSample.forwardPdfW + lightPdfW);
+                            }
+                            throughput = weight * throughput * bsdfSample.reflectance;
+                            float3 offsetOrigin = OffsetRayOrigin(surface, bsdfSample.wi, 1.0f);
+                            ray = MakeRay(offsetOrigin, bsdfSample.wi);
+                            if (bounceCount == 0) Ld[0] = bsdfSample.reflectance;
+                        } else if (currentMedium.phaseFunction != MediumPhaseFunction::eVacuum) {
+                            float3 origin = ray.origin + rayDistance * ray.direction;
+                            float mediumPdf;
+                            float3 direction = SampleScatterDirection(&ctx->sampler, currentMedium, ray.direction, &mediumPdf);
+                            ray = MakeRay(origin, direction);
+                        } else {
+                            float3 smp = isDeltaOnly ? EvaluateBackgroundMiss(ctx, ray.direction) : EvaluateBackground(ctx, ray.direction);
+                            Ld[1] += smp * throughput;
+                            break;
+                        }
+                        ++bounceCount;
+                        if (bounceCount > rs->rrStartBounce) {
+                            float continuationProb = Max<float>(Max<float>(throughput.x, throughput.y), throughput.z);
+                            if (ctx->sampler.UniformFloat() > continuationProb) break;
+                            throughput = throughput * (1.0f / continuationProb);
+                        }
+                    }
+                    if (rs->layerCount == 1) {
+                        film[0][3 * p] += Ld[1].x; film[0][3 * p + 1] += Ld[1].y; film[0][3 * p + 2] += Ld[1].z;
+                    } else {
+                        for (int l = 0; l < 2; ++l) { film[l][3 * p] += Ld[l].x; film[l][3 * p + 1] += Ld[l].y; film[l][3 * p + 2] += Ld[l].z; }
+                    }
+                }
+            }
+        }
+        closest += c;
+        shadow += sh;
+        g_src = DrawSource{nullptr, 0, 0, 0, false};
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < std::max(1, nthreads); ++t) th.emplace_back(worker);
+    for (auto& x : th) x.join();
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        stats->closestRays = closest;
+        stats->occlusionRays = shadow;
+        stats->pathSamples = pixels * rs->samplesPerPixel;
+    }
+    return 0;
+}
+
+}  // extern "C"

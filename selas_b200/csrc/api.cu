@@ -1,0 +1,629 @@
+// api.cu -- the C ABI of libselas_cuda.so (include/selas_cuda.h): contexts, scene upload + BVH build, and
+// the host-buffer entry points (copy in, launch, copy out, synchronise).  No CPU fallback anywhere: every
+// entry point either runs its CUDA kernels or fails with SELAS_ERR_CUDA.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+#include "vec.cuh"
+
+namespace selas {
+
+static thread_local std::string g_threadError;
+
+void setError(SelasContext* ctx, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_threadError = buf;
+    if (ctx) ctx->lastError = buf;
+}
+
+namespace {
+
+// Device scratch that frees itself; used by the host-buffer entry points.
+struct Scratch {
+    SelasContext* ctx;
+    std::vector<void*> ptrs;
+    explicit Scratch(SelasContext* c) : ctx(c) {}
+    ~Scratch() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    int alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 16);
+        if (e != cudaSuccess) {
+            setError(ctx, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            return e == cudaErrorMemoryAllocation ? SELAS_ERR_MEMORY : SELAS_ERR_CUDA;
+        }
+        ptrs.push_back(p);
+        *out = (T*)p;
+        return SELAS_OK;
+    }
+    template <typename T>
+    int upload(T** out, const T* host, size_t count) {
+        int rc = alloc(out, count);
+        if (rc) return rc;
+        if (count) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(*out, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        return SELAS_OK;
+    }
+};
+
+#define SELAS_TRY(expr)          \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__) return rc__;   \
+    } while (0)
+
+int bind(SelasContext* ctx) {
+    if (!ctx) {
+        setError(nullptr, "null context");
+        return SELAS_ERR_ARGUMENT;
+    }
+    SELAS_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    return SELAS_OK;
+}
+
+template <typename T>
+int sceneUpload(SelasScene* scene, const T** out, const T* host, size_t count) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(T);
+    SelasContext* ctx = scene->ctx;
+    cudaError_t e = cudaMalloc(&p, bytes + 16);
+    if (e != cudaSuccess) {
+        setError(ctx, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return SELAS_ERR_MEMORY;
+    }
+    scene->allocations.push_back(p);
+    if (bytes) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = (const T*)p;
+    return SELAS_OK;
+}
+
+}  // namespace
+}  // namespace selas
+
+using namespace selas;
+
+extern "C" {
+
+// ---- context -------------------------------------------------------------------------------------------------
+int selas_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* selas_cuda_version(void) { return "selas-b200 0.1 (sm_100a)"; }
+
+const char* selas_cuda_last_error(const SelasContext* ctx) {
+    if (ctx) return ctx->lastError.c_str();
+    return g_threadError.c_str();
+}
+
+int selas_cuda_context_create(int device, SelasContext** out) {
+    if (!out) {
+        setError(nullptr, "selas_cuda_context_create: out is null");
+        return SELAS_ERR_ARGUMENT;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        setError(nullptr, "no CUDA device available (%s); this library has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return SELAS_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        setError(nullptr, "device %d out of range (0..%d)", device, count - 1);
+        return SELAS_ERR_ARGUMENT;
+    }
+    SelasContext* ctx = new (std::nothrow) SelasContext();
+    if (!ctx) return SELAS_ERR_MEMORY;
+    ctx->device = device;
+    SELAS_CUDA_CHECK(nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SELAS_CUDA_CHECK(nullptr, cudaGetDeviceProperties(&prop, device));
+    ctx->smCount = prop.multiProcessorCount;
+    SELAS_CUDA_CHECK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    SELAS_CUDA_CHECK(nullptr, cudaMalloc((void**)&ctx->d_counters, 256 * sizeof(uint32_t)));
+    SELAS_CUDA_CHECK(nullptr, cudaMemset(ctx->d_counters, 0, 256 * sizeof(uint32_t)));
+    *out = ctx;
+    return SELAS_OK;
+}
+
+int selas_cuda_context_destroy(SelasContext* ctx) {
+    if (!ctx) return SELAS_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    cudaFree(ctx->d_counters);
+    delete ctx;
+    return SELAS_OK;
+}
+
+// ---- scene ---------------------------------------------------------------------------------------------------
+int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasScene** out) {
+    SELAS_TRY(bind(ctx));
+    if (!d || !out) {
+        setError(ctx, "selas_cuda_scene_create: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    *out = nullptr;
+    if (d->meshCount && !d->meshes) {
+        setError(ctx, "meshCount > 0 but meshes is null");
+        return SELAS_ERR_ARGUMENT;
+    }
+    for (uint32_t m = 0; m < d->meshCount; ++m) {
+        const SelasMeshDesc& md = d->meshes[m];
+        if (md.indicesPerFace != 3 && md.indicesPerFace != 4) {
+            setError(ctx, "mesh %u: indicesPerFace must be 3 or 4 (got %u)", m, md.indicesPerFace);
+            return SELAS_ERR_ARGUMENT;
+        }
+        if (md.faceCount && (!md.positions || !md.indices)) {
+            setError(ctx, "mesh %u: positions/indices missing", m);
+            return SELAS_ERR_ARGUMENT;
+        }
+        if (md.materialIndex >= d->materialCount) {
+            setError(ctx, "mesh %u: materialIndex %u out of range (%u materials)", m, md.materialIndex, d->materialCount);
+            return SELAS_ERR_ARGUMENT;
+        }
+        const size_t nidx = (size_t)md.faceCount * md.indicesPerFace;
+        for (size_t k = 0; k < nidx; ++k)
+            if (md.indices[k] >= md.vertexCount) {
+                setError(ctx, "mesh %u: index %u at %zu out of range (%u vertices)", m, md.indices[k], k, md.vertexCount);
+                return SELAS_ERR_ARGUMENT;
+            }
+    }
+    for (uint32_t i = 0; i < d->instanceCount; ++i)
+        if (d->instances[i].meshIndex >= d->meshCount) {
+            setError(ctx, "instance %u: meshIndex %u out of range", i, d->instances[i].meshIndex);
+            return SELAS_ERR_ARGUMENT;
+        }
+    for (uint32_t i = 0; i < d->lightSetCount; ++i)
+        if ((uint64_t)d->lightSets[i].start + d->lightSets[i].count > d->lightCount) {
+            setError(ctx, "light set %u: range [%u, +%u) exceeds %u lights", i, d->lightSets[i].start, d->lightSets[i].count, d->lightCount);
+            return SELAS_ERR_ARGUMENT;
+        }
+
+    SelasScene* scene = new (std::nothrow) SelasScene();
+    if (!scene) return SELAS_ERR_MEMORY;
+    scene->ctx = ctx;
+    struct Guard {
+        SelasScene* s;
+        ~Guard() {
+            if (s) selas_cuda_scene_destroy(s);
+        }
+    } guard{scene};
+
+    std::vector<MeshGpu> meshes(d->meshCount);
+    for (uint32_t m = 0; m < d->meshCount; ++m) {
+        const SelasMeshDesc& md = d->meshes[m];
+        MeshGpu& g = meshes[m];
+        memset(&g, 0, sizeof(g));
+        SELAS_TRY(sceneUpload(scene, &g.positions, md.positions, 3 * (size_t)md.vertexCount));
+        SELAS_TRY(sceneUpload(scene, &g.indices, md.indices, (size_t)md.faceCount * md.indicesPerFace));
+        if (md.normals) SELAS_TRY(sceneUpload(scene, &g.normals, md.normals, 3 * (size_t)md.vertexCount));
+        if (md.tangents) SELAS_TRY(sceneUpload(scene, &g.tangents, md.tangents, 4 * (size_t)md.vertexCount));
+        if (md.uvs) SELAS_TRY(sceneUpload(scene, &g.uvs, md.uvs, 2 * (size_t)md.vertexCount));
+        g.ptex = md.ptex ? ptexDevicePointer((SelasPtex*)md.ptex) : nullptr;
+        g.faceCount = md.faceCount;
+        g.indicesPerFace = md.indicesPerFace;
+        g.materialIndex = md.materialIndex;
+        g.lightSetIndex = md.lightSetIndex;
+    }
+    std::vector<InstanceGpu> inst;
+    if (d->instanceCount) {
+        inst.resize(d->instanceCount);
+        for (uint32_t i = 0; i < d->instanceCount; ++i) {
+            memcpy(inst[i].m, d->instances[i].localToWorld, sizeof(inst[i].m));
+            inst[i].mesh = d->instances[i].meshIndex;
+            static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            inst[i].identity = memcmp(inst[i].m, I, sizeof(I)) == 0 ? 1u : 0u;
+            inst[i].pad[0] = inst[i].pad[1] = 0;
+        }
+    } else {  // every mesh once, identity, instID0 = 0
+        inst.resize(1);
+        memset(&inst[0], 0, sizeof(InstanceGpu));
+        inst[0].m[0] = inst[0].m[5] = inst[0].m[10] = inst[0].m[15] = 1.0f;
+        inst[0].mesh = 0xFFFFFFFFu;
+        inst[0].identity = 1;
+    }
+    SceneGpu& g = scene->gpu;
+    SELAS_TRY(sceneUpload(scene, &g.meshes, meshes.data(), meshes.size()));
+    SELAS_TRY(sceneUpload(scene, &g.instances, inst.data(), inst.size()));
+    SELAS_TRY(sceneUpload(scene, &g.materials, d->materials, d->materialCount));
+    SELAS_TRY(sceneUpload(scene, &g.lights, d->lights, d->lightCount));
+    SELAS_TRY(sceneUpload(scene, &g.lightSets, d->lightSets, d->lightSetCount));
+    g.meshCount = d->meshCount;
+    g.instanceCount = (uint32_t)inst.size();
+    g.materialCount = d->materialCount;
+    g.lightCount = d->lightCount;
+    g.lightSetCount = d->lightSetCount;
+    memcpy(g.background, d->backgroundIntensity, sizeof(g.background));
+
+    SELAS_TRY(buildBvh(scene, meshes, inst, g.instances));
+    uint64_t attrBytes = 0;
+    for (uint32_t m = 0; m < d->meshCount; ++m) {
+        const SelasMeshDesc& md = d->meshes[m];
+        attrBytes += 12ull * md.vertexCount + 4ull * md.faceCount * md.indicesPerFace;
+        if (md.normals) attrBytes += 12ull * md.vertexCount;
+        if (md.tangents) attrBytes += 16ull * md.vertexCount;
+        if (md.uvs) attrBytes += 8ull * md.vertexCount;
+    }
+    scene->stats.deviceBytes += attrBytes;
+    guard.s = nullptr;
+    *out = scene;
+    return SELAS_OK;
+}
+
+int selas_cuda_scene_destroy(SelasScene* scene) {
+    if (!scene) return SELAS_OK;
+    if (scene->ctx) {
+        cudaSetDevice(scene->ctx->device);
+        cudaStreamSynchronize(scene->ctx->stream);
+    }
+    freeWavefront(scene);
+    for (void* p : scene->allocations) cudaFree(p);
+    delete scene;
+    return SELAS_OK;
+}
+
+int selas_cuda_scene_bvh_stats(const SelasScene* scene, SelasBvhStats* out) {
+    if (!scene || !out) {
+        setError(nullptr, "selas_cuda_scene_bvh_stats: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    *out = scene->stats;
+    return SELAS_OK;
+}
+
+// ---- ray cast ------------------------------------------------------------------------------------------------
+static int checkRayCount(SelasContext* ctx, size_t n) {
+    if (n > 0xFFFFFFF0ull) {
+        setError(ctx, "ray batch of %zu exceeds the 32-bit queue index", n);
+        return SELAS_ERR_ARGUMENT;
+    }
+    return SELAS_OK;
+}
+
+int selas_cuda_intersect_device(SelasScene* scene, size_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_Ng4, void* stream) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SELAS_TRY(bind(scene->ctx));
+    SELAS_TRY(checkRayCount(scene->ctx, n));
+    cudaStream_t st = stream ? (cudaStream_t)stream : scene->ctx->stream;
+    return launchIntersect(scene, (uint32_t)n, d_rays, d_hits, d_Ng4, nullptr, scene->ctx->d_counters, st);
+}
+
+int selas_cuda_occluded_device(SelasScene* scene, size_t n, const SelasRay* d_rays, uint8_t* d_occluded, void* stream) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SELAS_TRY(bind(scene->ctx));
+    SELAS_TRY(checkRayCount(scene->ctx, n));
+    cudaStream_t st = stream ? (cudaStream_t)stream : scene->ctx->stream;
+    return launchOccluded(scene, (uint32_t)n, d_rays, d_occluded, nullptr, scene->ctx->d_counters + 1, st);
+}
+
+int selas_cuda_intersect(SelasScene* scene, size_t n, const SelasRay* rays, SelasHit* hits, float* Ng4) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    SELAS_TRY(checkRayCount(ctx, n));
+    if (n == 0) return SELAS_OK;
+    if (!rays || !hits) {
+        setError(ctx, "selas_cuda_intersect: null rays/hits");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    SelasRay* d_rays;
+    SelasHit* d_hits;
+    float* d_ng = nullptr;
+    SELAS_TRY(s.upload(&d_rays, rays, n));
+    SELAS_TRY(s.alloc(&d_hits, n));
+    if (Ng4) SELAS_TRY(s.alloc(&d_ng, 4 * n));
+    SELAS_TRY(launchIntersect(scene, (uint32_t)n, d_rays, d_hits, d_ng, nullptr, ctx->d_counters, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(SelasHit), cudaMemcpyDeviceToHost, ctx->stream));
+    if (Ng4) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(Ng4, d_ng, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_occluded(SelasScene* scene, size_t n, const SelasRay* rays, uint8_t* occluded) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    SELAS_TRY(checkRayCount(ctx, n));
+    if (n == 0) return SELAS_OK;
+    if (!rays || !occluded) {
+        setError(ctx, "selas_cuda_occluded: null rays/occluded");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    SelasRay* d_rays;
+    uint8_t* d_occ;
+    SELAS_TRY(s.upload(&d_rays, rays, n));
+    SELAS_TRY(s.alloc(&d_occ, n));
+    SELAS_TRY(launchOccluded(scene, (uint32_t)n, d_rays, d_occ, nullptr, ctx->d_counters + 1, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_intersect_counted(SelasScene* scene, size_t n, const SelasRay* rays, SelasHit* hits, uint32_t* counts, int anyHit) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    SELAS_TRY(checkRayCount(ctx, n));
+    if (n == 0) return SELAS_OK;
+    if (!rays || !counts) {
+        setError(ctx, "selas_cuda_intersect_counted: null rays/counts");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    SelasRay* d_rays;
+    SelasHit* d_hits;
+    uint8_t* d_occ;
+    uint32_t* d_counts;
+    SELAS_TRY(s.upload(&d_rays, rays, n));
+    SELAS_TRY(s.alloc(&d_hits, n));
+    SELAS_TRY(s.alloc(&d_occ, n));
+    SELAS_TRY(s.alloc(&d_counts, 2 * n));
+    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, 2 * n * sizeof(uint32_t), ctx->stream));
+    if (anyHit) {
+        SELAS_TRY(launchOccluded(scene, (uint32_t)n, d_rays, d_occ, d_counts, ctx->d_counters + 1, ctx->stream));
+        if (hits) {  // any-hit mode reports only geomID != INVALID for occluded rays
+            std::vector<uint8_t> occ(n);
+            SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(occ.data(), d_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
+            SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            for (size_t i = 0; i < n; ++i) {
+                memset(&hits[i], 0, sizeof(SelasHit));
+                hits[i].t = occ[i] ? -INFINITY : rays[i].tfar;
+                hits[i].geomID = hits[i].primID = hits[i].instID0 = hits[i].instID1 = occ[i] ? 0u : SELAS_INVALID_ID;
+            }
+        }
+    } else {
+        SELAS_TRY(launchIntersect(scene, (uint32_t)n, d_rays, d_hits, nullptr, d_counts, ctx->d_counters, ctx->stream));
+        if (hits) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(SelasHit), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, d_counts, 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+// ---- camera --------------------------------------------------------------------------------------------------
+// InitializeRayCastCamera, GeometryLib/Camera.cpp:89-115.  Load-time host arithmetic in the reference too.
+int selas_cuda_camera_init(const SelasCameraSettings* st, uint32_t width, uint32_t height, SelasCamera* cam) {
+    if (!st || !cam || width == 0 || height == 0) {
+        setError(nullptr, "selas_cuda_camera_init: bad argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    memset(cam, 0, sizeof(*cam));
+    const float pi = 3.141592653589793f;
+    float widthf = (float)width, heightf = (float)height;
+    float aspect = widthf / heightf;
+    float hfov = st->fovDegrees * (pi / 180.f);
+    float hLen = tanf(hfov * 0.5f);
+    float vfov = 2 * atanf(hLen / aspect);
+    float vLen = tanf(vfov * 0.5f);
+    V3 fwd = normalize(v3(st->lookAt) - v3(st->position));
+    V3 right = normalize(cross(v3(st->up), fwd));
+    store3(cam->cameraX, hLen * right);
+    store3(cam->cameraY, vLen * cross(fwd, right));
+    store3(cam->cameraZ, fwd);
+    store3(cam->forward, fwd);
+    store3(cam->position, v3(st->position));
+    cam->viewportWidth = widthf;
+    cam->viewportHeight = heightf;
+    cam->znear = st->znear;
+    cam->zfar = st->zfar;
+    cam->virtualImagePlaneDistance = widthf / (2.0f * tanf(hfov));
+    cam->width = width;
+    cam->height = height;
+    cam->aspect = aspect;
+    return SELAS_OK;
+}
+
+int selas_cuda_camera_rays(SelasContext* ctx, const SelasCamera* camera, size_t n, const float* px, const float* py, const float* jitter,
+                           SelasRay* rays) {
+    SELAS_TRY(bind(ctx));
+    if (n == 0) return SELAS_OK;
+    if (!camera || !px || !py || !rays) {
+        setError(ctx, "selas_cuda_camera_rays: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    float *d_px, *d_py, *d_j = nullptr;
+    SelasRay* d_rays;
+    SELAS_TRY(s.upload(&d_px, px, n));
+    SELAS_TRY(s.upload(&d_py, py, n));
+    if (jitter) SELAS_TRY(s.upload(&d_j, jitter, 2 * n));
+    SELAS_TRY(s.alloc(&d_rays, n));
+    SELAS_TRY(launchCameraRays(ctx, *camera, n, d_px, d_py, d_j, d_rays));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(rays, d_rays, n * sizeof(SelasRay), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+// ---- BSDF / light / surface operators ----------------------------------------------------------------------------
+int selas_cuda_bsdf_eval(SelasContext* ctx, size_t n, const SelasSurface* surfaces, const float* v3in, const float* l3in, float* rgb3,
+                         float* forwardPdfW, float* reversePdfW) {
+    SELAS_TRY(bind(ctx));
+    if (n == 0) return SELAS_OK;
+    if (!surfaces || !v3in || !l3in || !rgb3 || !forwardPdfW || !reversePdfW) {
+        setError(ctx, "selas_cuda_bsdf_eval: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    SelasSurface* d_s;
+    float *d_v, *d_l, *d_rgb, *d_f, *d_r;
+    SELAS_TRY(s.upload(&d_s, surfaces, n));
+    SELAS_TRY(s.upload(&d_v, v3in, 3 * n));
+    SELAS_TRY(s.upload(&d_l, l3in, 3 * n));
+    SELAS_TRY(s.alloc(&d_rgb, 3 * n));
+    SELAS_TRY(s.alloc(&d_f, n));
+    SELAS_TRY(s.alloc(&d_r, n));
+    SELAS_TRY(launchBsdfEval(ctx, n, d_s, d_v, d_l, d_rgb, d_f, d_r));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(rgb3, d_rgb, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(forwardPdfW, d_f, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(reversePdfW, d_r, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_bsdf_sample(SelasContext* ctx, size_t n, const SelasSurface* surfaces, const float* v3in, const float* u, SelasBsdfSample* out) {
+    SELAS_TRY(bind(ctx));
+    if (n == 0) return SELAS_OK;
+    if (!surfaces || !v3in || !u || !out) {
+        setError(ctx, "selas_cuda_bsdf_sample: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    SelasSurface* d_s;
+    float *d_v, *d_u;
+    SelasBsdfSample* d_o;
+    SELAS_TRY(s.upload(&d_s, surfaces, n));
+    SELAS_TRY(s.upload(&d_v, v3in, 3 * n));
+    SELAS_TRY(s.upload(&d_u, u, SELAS_BSDF_RANDOMS * n));
+    SELAS_TRY(s.alloc(&d_o, n));
+    SELAS_TRY(launchBsdfSample(ctx, n, d_s, d_v, d_u, d_o));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(SelasBsdfSample), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_light_sample(SelasContext* ctx, size_t n, const SelasLight* lights, uint32_t lightCount, const float* position3,
+                            const float* normal3, const float* u3, SelasLightSample* out) {
+    SELAS_TRY(bind(ctx));
+    if (n == 0) return SELAS_OK;
+    if ((lightCount && !lights) || !position3 || !normal3 || !u3 || !out) {
+        setError(ctx, "selas_cuda_light_sample: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    SelasLight* d_l;
+    float *d_p, *d_n, *d_u;
+    SelasLightSample* d_o;
+    SELAS_TRY(s.upload(&d_l, lights, lightCount));
+    SELAS_TRY(s.upload(&d_p, position3, 3 * n));
+    SELAS_TRY(s.upload(&d_n, normal3, 3 * n));
+    SELAS_TRY(s.upload(&d_u, u3, 3 * n));
+    SELAS_TRY(s.alloc(&d_o, n));
+    SELAS_TRY(launchLightSample(ctx, n, d_l, lightCount, d_p, d_n, d_u, d_o));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(SelasLightSample), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_light_pdf(SelasContext* ctx, size_t n, const SelasLight* lights, uint32_t lightCount, const uint32_t* lightIndex,
+                         const float* position3, const float* wi3, float* pdf) {
+    SELAS_TRY(bind(ctx));
+    if (n == 0) return SELAS_OK;
+    if ((lightCount && !lights) || !lightIndex || !position3 || !wi3 || !pdf) {
+        setError(ctx, "selas_cuda_light_pdf: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    for (size_t i = 0; i < n; ++i)
+        if (lightCount && lightIndex[i] >= lightCount) {
+            setError(ctx, "selas_cuda_light_pdf: lightIndex[%zu] = %u out of range", i, lightIndex[i]);
+            return SELAS_ERR_ARGUMENT;
+        }
+    Scratch s(ctx);
+    SelasLight* d_l;
+    uint32_t* d_i;
+    float *d_p, *d_w, *d_o;
+    SELAS_TRY(s.upload(&d_l, lights, lightCount));
+    SELAS_TRY(s.upload(&d_i, lightIndex, n));
+    SELAS_TRY(s.upload(&d_p, position3, 3 * n));
+    SELAS_TRY(s.upload(&d_w, wi3, 3 * n));
+    SELAS_TRY(s.alloc(&d_o, n));
+    SELAS_TRY(launchLightPdf(ctx, n, d_l, lightCount, d_i, d_p, d_w, d_o));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(pdf, d_o, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays, const SelasHit* hits, SelasSurface* out) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (n == 0) return SELAS_OK;
+    if (!rays || !hits || !out) {
+        setError(ctx, "selas_cuda_surface_params: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    for (size_t i = 0; i < n; ++i) {  // ModelDataFromRayIds asserts these in the reference (SceneResource.cpp:362-378)
+        const SelasHit& h = hits[i];
+        if (h.geomID == SELAS_INVALID_ID) continue;
+        if (h.geomID >= scene->gpu.meshCount || h.instID0 >= scene->gpu.instanceCount) {
+            setError(ctx, "selas_cuda_surface_params: hit %zu names geomID %u / instID %u outside the scene", i, h.geomID, h.instID0);
+            return SELAS_ERR_ARGUMENT;
+        }
+    }
+    Scratch s(ctx);
+    SelasRay* d_r;
+    SelasHit* d_h;
+    SelasSurface* d_o;
+    SELAS_TRY(s.upload(&d_r, rays, n));
+    SELAS_TRY(s.upload(&d_h, hits, n));
+    SELAS_TRY(s.alloc(&d_o, n));
+    SELAS_TRY(launchSurfaceParams(scene, n, d_r, d_h, d_o));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(SelasSurface), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+// ---- integrator ------------------------------------------------------------------------------------------------
+int selas_cuda_render_pathtracer_device(SelasScene* scene, const SelasCamera* camera, const SelasRenderSettings* settings, float* d_film,
+                                        SelasRenderStats* stats, void* stream) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (!camera || !settings || !d_film) {
+        setError(ctx, "selas_cuda_render_pathtracer_device: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    return renderPathTracer(scene, *camera, *settings, d_film, stats, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera, const SelasRenderSettings* settings,
+                                 float* const* filmLayers, SelasRenderStats* stats) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (!camera || !settings || !filmLayers) {
+        setError(ctx, "selas_cuda_render_pathtracer: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    if (settings->layerCount < 1 || settings->layerCount > 2) {
+        setError(ctx, "layerCount must be 1 or 2");
+        return SELAS_ERR_ARGUMENT;
+    }
+    const size_t plane = (size_t)settings->width * settings->height * 3;
+    Scratch s(ctx);
+    float* d_film;
+    SELAS_TRY(s.alloc(&d_film, plane * settings->layerCount));
+    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_film, 0, plane * settings->layerCount * sizeof(float), ctx->stream));
+    SELAS_TRY(renderPathTracer(scene, *camera, *settings, d_film, stats, ctx->stream));
+    for (uint32_t l = 0; l < settings->layerCount; ++l)
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(filmLayers[l], d_film + plane * l, plane * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_film_scale_device(SelasContext* ctx, float* d_film, size_t floatCount, float scale, void* stream) {
+    SELAS_TRY(bind(ctx));
+    return launchScale(ctx, d_film, floatCount, scale, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// bvh8.cuh -- compressed 8-wide BVH: node / triangle records and the closest-hit / any-hit traversal.
+//
+// Stands in for rtcIntersect1 / rtcOccluded1 (call sites PathTracer.cpp:88,:116; packet form
+// DeferredPathTracer.cpp:191,:267).  Embree semantics kept: closest hit with t in [tnear,tfar], no back-face
+// culling, (u,v) = weights of v1,v2, quads as (v0,v1,v3)+(v2,v3,v1) with u,v flipped on the second half,
+// Ng = cross(v1-v0, v2-v0) unnormalised (share/man/man3/rtcIntersect1.3embree3:24,:53,
+// RTC_GEOMETRY_TYPE_QUAD.3embree3:38-41).
+//
+// Node: 80 bytes = 5 x 16-byte vectors (compressed wide BVH after Ylitie, Karras, Laine 2017):
+//   n0 = { origin.x, origin.y, origin.z, (ex | ey<<8 | ez<<16 | imask<<24) }
+//   n1 = { childBase, triBase, meta[0..3], meta[4..7] }
+//   n2 = { qlo.x[0..3], qlo.x[4..7], qhi.x[0..3], qhi.x[4..7] }   n3 = same for y   n4 = same for z
+//   child box = origin + q * 2^(e-127) ; meta: 0 = empty, inner = 001|(24+slot), leaf = unary count|triOffset
+// Triangle: 48 bytes = 3 x float4 = { v0.xyz, primID }, { e1.xyz, geomID }, { e2.xyz, instID | second<<31 }.
+// A node's leaf triangles are contiguous from triBase (<= 24 per node, <= 3 per child).
+//
+// Algorithmic bytes per ray: 32 in + 32 out + 80 per visited node + 48 per tested triangle.
+#pragma once
+#include "../../include/selas_cuda.h"
+#include "vec.cuh"
+
+namespace selas {
+
+struct Bvh8 {
+    const float4* nodes;  // 5 per node
+    const float4* tris;   // 3 per triangle
+    uint32_t nodeCount, triCount;
+};
+
+#define SELAS_STACK_SIZE 48
+
+SELAS_D uint32_t extractByte(uint32_t x, uint32_t i) { return (x >> (i * 8)) & 0xff; }
+SELAS_D uint32_t signExtendS8x4(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+    return r;
+}
+SELAS_D float fmaxMax(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+SELAS_D float fminMin(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+struct TraceResult {
+    float t, u, v;
+    uint32_t tri;  // index into tris, 0xFFFFFFFF = none
+};
+
+// Ray-vs-8-children slab test on the quantised boxes; returns the hit mask in traversal-bit order.
+SELAS_D uint32_t intersectNode(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, V3 o,
+                               V3 idir, bool negx, bool negy, bool negz, uint32_t octInv4, float tmin, float tmax) {
+    uint32_t eimask = __float_as_uint(n0.w);
+    float sx = __uint_as_float(extractByte(eimask, 0) << 23) * idir.x;
+    float sy = __uint_as_float(extractByte(eimask, 1) << 23) * idir.y;
+    float sz = __uint_as_float(extractByte(eimask, 2) << 23) * idir.z;
+    float ox = (n0.x - o.x) * idir.x, oy = (n0.y - o.y) * idir.y, oz = (n0.z - o.z) * idir.z;
+    uint32_t hitMask = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        uint32_t meta4 = __float_as_uint(i == 0 ? n1.z : n1.w);
+        uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010;
+        uint32_t innerMask4 = signExtendS8x4(isInner4 << 3);
+        uint32_t bitIndex4 = (meta4 ^ (octInv4 & innerMask4)) & 0x1f1f1f1f;
+        uint32_t childBits4 = (meta4 >> 5) & 0x07070707;
+        uint32_t qlox = __float_as_uint(i == 0 ? n2.x : n2.y), qhix = __float_as_uint(i == 0 ? n2.z : n2.w);
+        uint32_t qloy = __float_as_uint(i == 0 ? n3.x : n3.y), qhiy = __float_as_uint(i == 0 ? n3.z : n3.w);
+        uint32_t qloz = __float_as_uint(i == 0 ? n4.x : n4.y), qhiz = __float_as_uint(i == 0 ? n4.z : n4.w);
+        uint32_t xmin = negx ? qhix : qlox, xmax = negx ? qlox : qhix;
+        uint32_t ymin = negy ? qhiy : qloy, ymax = negy ? qloy : qhiy;
+        uint32_t zmin = negz ? qhiz : qloz, zmax = negz ? qloz : qhiz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float tx0 = fmaf((float)extractByte(xmin, j), sx, ox), tx1 = fmaf((float)extractByte(xmax, j), sx, ox);
+            float ty0 = fmaf((float)extractByte(ymin, j), sy, oy), ty1 = fmaf((float)extractByte(ymax, j), sy, oy);
+            float tz0 = fmaf((float)extractByte(zmin, j), sz, oz), tz1 = fmaf((float)extractByte(zmax, j), sz, oz);
+            float t0 = fmaxMax(tx0, ty0, fmaxf(tz0, tmin));
+            float t1 = fminMin(tx1, ty1, fminf(tz1, tmax));
+            if (t0 <= t1) {
+                uint32_t childBits = extractByte(childBits4, j);
+                uint32_t bitIndex = extractByte(bitIndex4, j);
+                hitMask |= childBits << bitIndex;
+            }
+        }
+    }
+    return hitMask;
+}
+
+// Moller-Trumbore on the {v0,e1,e2} record.  Accepts t in [tnear, tmax].
+SELAS_D bool intersectTri(const float4 a, const float4 b, const float4 c, V3 o, V3 d, float tnear, float tmax, float& t,
+                          float& u, float& v) {
+    V3 v0 = v3(a.x, a.y, a.z), e1 = v3(b.x, b.y, b.z), e2 = v3(c.x, c.y, c.z);
+    V3 p = cross(d, e2);
+    float det = dot(e1, p);
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    V3 s = o - v0;
+    float uu = dot(s, p) * inv;
+    if (uu < 0.0f || uu > 1.0f) return false;
+    V3 q = cross(s, e1);
+    float vv = dot(d, q) * inv;
+    if (vv < 0.0f || uu + vv > 1.0f) return false;
+    float tt = dot(e2, q) * inv;
+    if (!(tt >= tnear && tt <= tmax)) return false;
+    t = tt;
+    u = uu;
+    v = vv;
+    return true;
+}
+
+// One ray through the BVH8.  ANY: stop at the first hit.  COUNT: tally visited nodes / tested triangles.
+template <bool ANY, bool COUNT>
+SELAS_D void traceRay(const Bvh8& bvh, V3 o, V3 d, float tnear, float tfar, TraceResult& res, uint32_t* counters) {
+    res.t = tfar;
+    res.u = res.v = 0.0f;
+    res.tri = 0xFFFFFFFFu;
+    if (bvh.nodeCount == 0) return;
+    uint2 stack[SELAS_STACK_SIZE];
+    int sp = 0;
+    // reciprocal direction; a zero component becomes a huge finite value so 0*inf never appears
+    const float tiny = 1e-30f;
+    V3 idir = v3(1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)), 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+                 1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+    bool negx = d.x < 0.0f, negy = d.y < 0.0f, negz = d.z < 0.0f;
+    uint32_t oct = (negx ? 4u : 0u) | (negy ? 2u : 0u) | (negz ? 1u : 0u);
+    uint32_t octInv4 = (7u - oct) * 0x01010101u;
+    float tmax = tfar;
+    uint32_t nNodes = 0, nTris = 0;
+
+    uint2 group = make_uint2(0u, 0x80000000u);  // root: child base 0, one pending inner child in bit 31
+    for (;;) {
+        uint2 triGroup;
+        if (group.y & 0xff000000u) {
+            uint32_t hitsImask = group.y;
+            uint32_t childBit = 31u - __clz(hitsImask);
+            group.y &= ~(1u << childBit);
+            if (group.y & 0xff000000u) {
+                if (sp < SELAS_STACK_SIZE) stack[sp++] = group;
+            }
+            uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
+            uint32_t rel = __popc(hitsImask & ~(0xffffffffu << slot));
+            uint32_t nodeIdx = group.x + rel;
+            const float4* np = bvh.nodes + (size_t)nodeIdx * 5;
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) ++nNodes;
+            uint32_t hitMask = intersectNode(n0, n1, n2, n3, n4, o, idir, negx, negy, negz, octInv4, tnear, tmax);
+            uint32_t imask = extractByte(__float_as_uint(n0.w), 3);
+            group.x = __float_as_uint(n1.x);
+            triGroup.x = __float_as_uint(n1.y);
+            group.y = (hitMask & 0xff000000u) | imask;
+            triGroup.y = hitMask & 0x00ffffffu;
+        } else {
+            triGroup = group;
+            group = make_uint2(0u, 0u);
+        }
+        while (triGroup.y != 0u) {
+            uint32_t bit = 31u - __clz(triGroup.y);
+            triGroup.y &= ~(1u << bit);
+            uint32_t ti = triGroup.x + bit;
+            const float4* tp = bvh.tris + (size_t)ti * 3;
+            float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+            if (COUNT) ++nTris;
+            float t, u, v;
+            if (intersectTri(a, b, c, o, d, tnear, tmax, t, u, v)) {
+                tmax = t;
+                res.t = t;
+                res.u = u;
+                res.v = v;
+                res.tri = ti;
+                if (ANY) {
+                    if (COUNT) { counters[0] = nNodes; counters[1] = nTris; }
+                    return;
+                }
+            }
+        }
+        if ((group.y & 0xff000000u) == 0u) {
+            if (sp == 0) break;
+            group = stack[--sp];
+        }
+    }
+    if (COUNT) { counters[0] = nNodes; counters[1] = nTris; }
+}
+
+// Fill the 32-byte hit record (and optional Ng) from a trace result.
+SELAS_D void writeHit(const Bvh8& bvh, const TraceResult& r, float tfar, SelasHit* out, float4* ng) {
+    float4 h0, h1;
+    if (r.tri == 0xFFFFFFFFu) {
+        h0 = make_float4(tfar, 0.0f, 0.0f, __uint_as_float(SELAS_INVALID_ID));
+        h1 = make_float4(__uint_as_float(SELAS_INVALID_ID), __uint_as_float(SELAS_INVALID_ID), __uint_as_float(SELAS_INVALID_ID), 0.0f);
+        if (ng) *ng = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        const float4* tp = bvh.tris + (size_t)r.tri * 3;
+        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        uint32_t w2 = __float_as_uint(c.w);
+        bool second = (w2 >> 31) != 0;
+        float u = second ? 1.0f - r.u : r.u, v = second ? 1.0f - r.v : r.v;
+        h0 = make_float4(r.t, u, v, a.w);
+        h1 = make_float4(b.w, __uint_as_float(w2 & 0x7fffffffu), __uint_as_float(0u), 0.0f);
+        if (ng) {
+            V3 n = cross(v3(b.x, b.y, b.z), v3(c.x, c.y, c.z));
+            *ng = make_float4(n.x, n.y, n.z, 0.f);
+        }
+    }
+    float4* o4 = reinterpret_cast<float4*>(out);
+    o4[0] = h0;
+    o4[1] = h1;
+}
+
+}  // namespace selas

@@ -1,0 +1,120 @@
+// internal.h -- host-side structures shared by the translation units of libselas_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/selas_cuda.h"
+
+namespace selas {
+
+struct Bvh8;
+
+// Device view of one mesh (= one Embree geometry: ModelGeometryUserData + its shared buffers,
+// ModelResource.h:97-105, ModelResource.cpp:164-200).
+struct MeshGpu {
+    const float* positions;
+    const uint32_t* indices;
+    const float* normals;   // float3 or null
+    const float* tangents;  // float4 or null
+    const float* uvs;       // float2 or null
+    const void* ptex;       // device PtexGpu* or null
+    uint32_t faceCount;
+    uint32_t indicesPerFace;
+    uint32_t materialIndex;
+    uint32_t lightSetIndex;
+};
+
+struct InstanceGpu {
+    float m[16];  // localToWorld, row-major row-vector
+    uint32_t mesh;  // 0xFFFFFFFF: identity over all meshes
+    uint32_t identity;
+    uint32_t pad[2];
+};
+
+// Everything the shade kernel needs, passed by value.
+struct SceneGpu {
+    const float4* nodes;
+    const float4* tris;
+    uint32_t nodeCount, triCount;
+    const MeshGpu* meshes;
+    const InstanceGpu* instances;
+    const SelasMaterial* materials;
+    const SelasLight* lights;
+    const SelasLightSetRange* lightSets;
+    uint32_t meshCount, instanceCount, materialCount, lightCount, lightSetCount;
+    float background[4];
+};
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace selas
+
+struct SelasContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int smCount = 0;
+    std::string lastError;
+    uint32_t* d_counters = nullptr;  // scratch counters (256 x u32)
+};
+
+struct SelasScene {
+    SelasContext* ctx = nullptr;
+    selas::SceneGpu gpu{};
+    std::vector<void*> allocations;  // everything cudaMalloc'ed for this scene
+    SelasBvhStats stats{};
+    // wavefront scratch, grown on demand
+    void* wf = nullptr;
+};
+
+namespace selas {
+
+// error plumbing
+void setError(SelasContext* ctx, const char* fmt, ...);
+#define SELAS_CUDA_CHECK(ctx, expr)                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            selas::setError(ctx, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return SELAS_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+// trace.cu
+int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::vector<InstanceGpu>& hostInstances,
+             const InstanceGpu* d_instances);
+int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_ng4, uint32_t* d_counts,
+                    uint32_t* d_rayCounter, cudaStream_t stream);
+int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_t* d_occ, uint32_t* d_counts, uint32_t* d_rayCounter,
+                   cudaStream_t stream);
+// shadow rays with film accumulation: payload = {contribution rgb, pixel}; film[pixel] += rgb when unoccluded
+int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
+                           float* d_film, uint32_t* d_rayCounter, cudaStream_t stream);
+int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
+                            uint32_t* d_rayCounter, cudaStream_t stream);
+
+// shade.cu
+int launchBsdfEval(SelasContext* ctx, size_t n, const SelasSurface* d_s, const float* d_v, const float* d_l, float* d_rgb, float* d_f,
+                   float* d_r);
+int launchBsdfSample(SelasContext* ctx, size_t n, const SelasSurface* d_s, const float* d_v, const float* d_u, SelasBsdfSample* d_out);
+int launchLightSample(SelasContext* ctx, size_t n, const SelasLight* d_lights, uint32_t count, const float* d_pos, const float* d_nrm,
+                      const float* d_u3, SelasLightSample* d_out);
+int launchLightPdf(SelasContext* ctx, size_t n, const SelasLight* d_lights, uint32_t count, const uint32_t* d_idx, const float* d_pos,
+                   const float* d_wi, float* d_pdf);
+int launchCameraRays(SelasContext* ctx, const SelasCamera& cam, size_t n, const float* d_px, const float* d_py, const float* d_jitter,
+                     SelasRay* d_rays);
+int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, const SelasHit* d_hits, SelasSurface* d_out);
+int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
+                     cudaStream_t stream);
+int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream);
+void freeWavefront(SelasScene* scene);
+
+// ptex.cu
+const void* ptexDevicePointer(SelasPtex* tex);
+
+}  // namespace selas

@@ -1,0 +1,495 @@
+// shade.cu -- shading-side kernels: the batch BSDF / light / camera / surface operators used for parity, and
+// the wavefront PathTracer (generate -> [trace -> shade -> shadow-trace+accumulate]*).
+//
+// This translation unit is compiled with -fmad=false -ftz=true -prec-div=true -prec-sqrt=true so that its
+// fp32 arithmetic rounds like the reference's SSE code (FTZ/DAZ on, main.cpp:84-85); only libm calls differ.
+//
+// Wavefront = device restatement of PathTracer::EvaluatePath (Applications/Selas/Source/PathTracer.cpp:142-258)
+// as a state machine over SoA queues:
+//   rays      32 B  {o,tnear,d,tfar}        hits   32 B  {t,u,v,prim,geom,inst0,inst1,-}
+//   thrPix    16 B  {throughput rgb, pixel} rngFlags 8 B {pcg state, bounce | deltaOnly<<16 | inMedium<<17}
+//   medium    16 B  {extinction rgb, -}  (touched only by paths inside a medium)
+//   shadow    32 B ray + 16 B {contribution rgb, pixel}
+// Paths that survive a bounce are appended to the next queue with one atomicAdd per warp (ballot-ranked),
+// so every launch works on a dense queue.
+#include <cstdarg>
+#include <cstdio>
+
+#include "disney.cuh"
+#include "internal.h"
+#include "lights.cuh"
+#include "surface.cuh"
+
+namespace selas {
+
+namespace {
+inline uint32_t divUp(size_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// batch operators (parity levels (b): SURVEY.md 8)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void bsdfEvalKernel(size_t n, const SelasSurface* __restrict__ surfaces, const float* __restrict__ v3in,
+                               const float* __restrict__ l3in, float* __restrict__ rgb, float* __restrict__ fwd, float* __restrict__ rev) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Surface s;
+    loadSurface(surfaces[i], s);
+    DisneyFrame f;
+    makeDisneyFrame(s, s.shader == SELAS_SHADER_DISNEY_THIN, f);
+    float fp = 0.f, rp = 0.f;
+    V3 c = evaluateBsdf(s, f, v3(v3in + 3 * i), v3(l3in + 3 * i), fp, rp);
+    store3(rgb + 3 * i, c);
+    fwd[i] = fp;
+    rev[i] = rp;
+}
+
+__global__ void bsdfSampleKernel(size_t n, const SelasSurface* __restrict__ surfaces, const float* __restrict__ v3in,
+                                 const float* __restrict__ u, SelasBsdfSample* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Surface s;
+    loadSurface(surfaces[i], s);
+    DisneyFrame f;
+    makeDisneyFrame(s, s.shader == SELAS_SHADER_DISNEY_THIN, f);
+    ArrayRng rng{u + SELAS_BSDF_RANDOMS * i, 0};
+    BsdfResult r;
+    bool ok = sampleBsdf(rng, s, f, v3(v3in + 3 * i), r);
+    SelasBsdfSample o;
+    o.flags = r.flags;
+    o.mediumPhase = r.mediumPhase;
+    store3(o.mediumExtinction, r.mediumExtinction);
+    store3(o.reflectance, r.reflectance);
+    store3(o.wi, r.wi);
+    o.forwardPdfW = r.forwardPdfW;
+    o.reversePdfW = r.reversePdfW;
+    o.valid = ok ? 1u : 0u;
+    o.randomsUsed = rng.pos;
+    out[i] = o;
+}
+
+__global__ void lightSampleKernel(size_t n, const SelasLight* __restrict__ lights, uint32_t count, const float* __restrict__ pos,
+                                  const float* __restrict__ nrm, const float* __restrict__ u3, SelasLightSample* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ArrayRng rng{u3 + 3 * i, 0};
+    LightSample ls;
+    nextEventEstimation(rng, lights, count, v3(pos + 3 * i), v3(nrm + 3 * i), ls);
+    SelasLightSample o;
+    o.index = ls.index;
+    store3(o.direction, ls.direction);
+    store3(o.radiance, ls.radiance);
+    o.distance = ls.distance;
+    o.pdfW = ls.pdfW;
+    out[i] = o;
+}
+
+__global__ void lightPdfKernel(size_t n, const SelasLight* __restrict__ lights, uint32_t count, const uint32_t* __restrict__ idx,
+                               const float* __restrict__ pos, const float* __restrict__ wi, float* __restrict__ pdf) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pdf[i] = lightingPdf(lights, count, idx[i], v3(pos + 3 * i), v3(wi + 3 * i));
+}
+
+__global__ void cameraRaysKernel(SelasCamera cam, size_t n, const float* __restrict__ px, const float* __restrict__ py,
+                                 const float* __restrict__ jitter, SelasRay* __restrict__ rays) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float jx = jitter ? jitter[2 * i] : 0.5f, jy = jitter ? jitter[2 * i + 1] : 0.5f;
+    V3 d = imageToWorldDirection(cam, px[i] + jx, py[i] + jy);
+    float4* o = reinterpret_cast<float4*>(rays + i);
+    o[0] = make_float4(cam.position[0], cam.position[1], cam.position[2], 0.0f);
+    o[1] = make_float4(d.x, d.y, d.z, SELAS_FLOAT_MAX);
+}
+
+__global__ void surfaceParamsKernel(SceneGpu sc, size_t n, const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
+                                    SelasSurface* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SelasHit h = hits[i];
+    SelasSurface o;
+    memset(&o, 0, sizeof(o));
+    if (h.geomID != SELAS_INVALID_ID) {
+        SelasRay r = rays[i];
+        Surface s;
+        surfaceFromHit(sc, v3(r.ox, r.oy, r.oz), v3(r.dx, r.dy, r.dz), h.t, h.u, h.v, h.primID, h.geomID, h.instID0, s);
+        storeSurface(s, v3(-r.dx, -r.dy, -r.dz), o);
+    }
+    out[i] = o;
+}
+
+__global__ void scaleKernel(float* __restrict__ d, size_t n, float s) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] *= s;
+}
+
+int launchBsdfEval(SelasContext* ctx, size_t n, const SelasSurface* d_s, const float* d_v, const float* d_l, float* d_rgb, float* d_f, float* d_r) {
+    if (!n) return SELAS_OK;
+    bsdfEvalKernel<<<divUp(n, 128), 128, 0, ctx->stream>>>(n, d_s, d_v, d_l, d_rgb, d_f, d_r);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchBsdfSample(SelasContext* ctx, size_t n, const SelasSurface* d_s, const float* d_v, const float* d_u, SelasBsdfSample* d_out) {
+    if (!n) return SELAS_OK;
+    bsdfSampleKernel<<<divUp(n, 128), 128, 0, ctx->stream>>>(n, d_s, d_v, d_u, d_out);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchLightSample(SelasContext* ctx, size_t n, const SelasLight* d_lights, uint32_t count, const float* d_pos, const float* d_nrm,
+                      const float* d_u3, SelasLightSample* d_out) {
+    if (!n) return SELAS_OK;
+    lightSampleKernel<<<divUp(n, 128), 128, 0, ctx->stream>>>(n, d_lights, count, d_pos, d_nrm, d_u3, d_out);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchLightPdf(SelasContext* ctx, size_t n, const SelasLight* d_lights, uint32_t count, const uint32_t* d_idx, const float* d_pos,
+                   const float* d_wi, float* d_pdf) {
+    if (!n) return SELAS_OK;
+    lightPdfKernel<<<divUp(n, 128), 128, 0, ctx->stream>>>(n, d_lights, count, d_idx, d_pos, d_wi, d_pdf);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchCameraRays(SelasContext* ctx, const SelasCamera& cam, size_t n, const float* d_px, const float* d_py, const float* d_jitter,
+                     SelasRay* d_rays) {
+    if (!n) return SELAS_OK;
+    cameraRaysKernel<<<divUp(n, 256), 256, 0, ctx->stream>>>(cam, n, d_px, d_py, d_jitter, d_rays);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, const SelasHit* d_hits, SelasSurface* d_out) {
+    if (!n) return SELAS_OK;
+    surfaceParamsKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_out);
+    SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream) {
+    if (!n) return SELAS_OK;
+    scaleKernel<<<divUp(n, 256), 256, 0, stream>>>(d, n, s);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wavefront path tracer
+// ---------------------------------------------------------------------------------------------------------------
+#define FLAG_DELTA_ONLY (1u << 16)
+#define FLAG_IN_MEDIUM (1u << 17)
+
+struct WavefrontBuffers {
+    uint32_t capacity = 0;
+    SelasRay* rays[2] = {nullptr, nullptr};
+    SelasHit* hits = nullptr;
+    float4* thrPix[2] = {nullptr, nullptr};
+    uint2* rngFlags[2] = {nullptr, nullptr};
+    float4* medium[2] = {nullptr, nullptr};
+    SelasRay* shadowRays = nullptr;
+    float4* shadowPayload = nullptr;
+    uint32_t* counters = nullptr;  // 4 per iteration: nextPaths, shadowRays, closestFetch, shadowFetch
+    uint32_t counterSlots = 0;
+    uint32_t* h_counts = nullptr;  // pinned readback
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+void freeWavefront(SelasScene* scene) {
+    WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
+    if (!w) return;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(w->rays[k]);
+        cudaFree(w->thrPix[k]);
+        cudaFree(w->rngFlags[k]);
+        cudaFree(w->medium[k]);
+    }
+    cudaFree(w->hits);
+    cudaFree(w->shadowRays);
+    cudaFree(w->shadowPayload);
+    cudaFree(w->counters);
+    if (w->h_counts) cudaFreeHost(w->h_counts);
+    if (w->ev0) cudaEventDestroy(w->ev0);
+    if (w->ev1) cudaEventDestroy(w->ev1);
+    delete w;
+    scene->wf = nullptr;
+}
+
+static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterations) {
+    SelasContext* ctx = scene->ctx;
+    WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
+    uint32_t slots = (iterations + 2) * 4;
+    if (w && w->capacity >= capacity && w->counterSlots >= slots) return SELAS_OK;
+    if (w) freeWavefront(scene);
+    w = new WavefrontBuffers();
+    scene->wf = w;
+    w->capacity = capacity;
+    w->counterSlots = slots;
+    for (int k = 0; k < 2; ++k) {
+        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->rays[k], sizeof(SelasRay) * (size_t)capacity));
+        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->thrPix[k], sizeof(float4) * (size_t)capacity));
+        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->rngFlags[k], sizeof(uint2) * (size_t)capacity));
+        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->medium[k], sizeof(float4) * (size_t)capacity));
+    }
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->hits, sizeof(SelasHit) * (size_t)capacity));
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowRays, sizeof(SelasRay) * (size_t)capacity));
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity));
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->counters, sizeof(uint32_t) * slots));
+    SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4));
+    SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev0));
+    SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev1));
+    return SELAS_OK;
+}
+
+// JitteredCameraRay (Camera.cpp:63-74) for path ids [first, first+count): pixel = id % pixels, sample = id / pixels.
+__global__ void generateKernel(SelasCamera cam, uint32_t width, uint32_t height, uint32_t seed, uint32_t firstSample, uint64_t firstPath,
+                               uint32_t count, SelasRay* __restrict__ rays, float4* __restrict__ thrPix, uint2* __restrict__ rngFlags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t id = firstPath + i;
+    uint32_t pixels = width * height;
+    uint32_t pixel = (uint32_t)(id % pixels), sample = firstSample + (uint32_t)(id / pixels);
+    uint32_t y = pixel / width, x = pixel - y * width;
+    PathRng rng;
+    rng.init(seed, pixel, sample);
+    float vx = (float)x + rng.next();
+    float vy = (float)y + rng.next();
+    V3 d = imageToWorldDirection(cam, vx, vy);
+    float4* o = reinterpret_cast<float4*>(rays + i);
+    o[0] = make_float4(cam.position[0], cam.position[1], cam.position[2], 0.0f);
+    o[1] = make_float4(d.x, d.y, d.z, SELAS_FLOAT_MAX);
+    thrPix[i] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel));
+    rngFlags[i] = make_uint2(rng.state, FLAG_DELTA_ONLY);
+}
+
+struct ShadeParams {
+    uint32_t maxPathLength, rrStartBounce, layerCount, pixels;
+};
+
+__global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ nPtr, uint32_t nMax,
+                                                   const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
+                                                   const float4* __restrict__ thrPix, const uint2* __restrict__ rngFlags,
+                                                   const float4* __restrict__ mediumIn, SelasRay* __restrict__ raysOut,
+                                                   float4* __restrict__ thrPixOut, uint2* __restrict__ rngFlagsOut,
+                                                   float4* __restrict__ mediumOut, SelasRay* __restrict__ shadowRays,
+                                                   float4* __restrict__ shadowPayload, uint32_t* __restrict__ counters,
+                                                   float* __restrict__ film) {
+    const uint32_t n = nPtr ? min(nMax, *nPtr) : nMax;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    bool alive = false, wantShadow = false;
+    SelasRay outRay;
+    float4 outThrPix = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint2 outRngFlags = make_uint2(0u, 0u);
+    float4 outMedium = make_float4(0.f, 0.f, 0.f, 0.f);
+    SelasRay shRay;
+    float4 shPayload = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (i < n) {
+        const float4* rp = reinterpret_cast<const float4*>(rays + i);
+        float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        const float4* hp = reinterpret_cast<const float4*>(hits + i);
+        float4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        float4 tp = __ldg(thrPix + i);
+        uint2 rf = __ldg(rngFlags + i);
+        V3 o = v3(r0.x, r0.y, r0.z), d = v3(r1.x, r1.y, r1.z);
+        V3 thr = v3(tp.x, tp.y, tp.z);
+        const uint32_t pixel = __float_as_uint(tp.w);
+        PathRng rng;
+        rng.state = rf.x;
+        uint32_t bounce = rf.y & 0xffffu;
+        bool deltaOnly = (rf.y & FLAG_DELTA_ONLY) != 0;
+        Medium medium{SELAS_MEDIUM_VACUUM, v3(0.0f)};
+        if (rf.y & FLAG_IN_MEDIUM) {
+            float4 m = __ldg(mediumIn + i);
+            medium.phase = SELAS_MEDIUM_ISOTROPIC;
+            medium.extinction = v3(m.x, m.y, m.z);
+        }
+        float rayDistance = r1.w;  // the distance sampled for this segment (FLT_MAX in vacuum), PathTracer.cpp:160
+        const uint32_t geomID = __float_as_uint(h1.x);
+        const bool isHit = geomID != SELAS_INVALID_ID;
+        float* filmRadiance = film + (prm.layerCount == 2 ? 3 * (size_t)prm.pixels : 0);
+
+        Surface s;
+        if (isHit) {
+            surfaceFromHit(sc, o, d, h0.x, h0.y, h0.z, __float_as_uint(h0.w), geomID, __float_as_uint(h1.y), s);
+            rayDistance = length(s.position - o);  // :165-167
+        }
+        thr = thr * transmission(medium, rayDistance);  // :168-169
+
+        if (isHit) {
+            DisneyFrame frame;
+            makeDisneyFrame(s, s.shader == SELAS_SHADER_DISNEY_THIN, frame);
+            V3 view = -d;
+            // ---- next-event estimation, :176-194 ----
+            LightSample ls;
+            ls.radiance = v3(0.0f);
+            ls.index = 0; ls.direction = v3(0.f); ls.distance = 0.f; ls.pdfW = 0.f;
+            uint32_t lightCount = 0;
+            const SelasLight* lights = nullptr;
+            if (s.lightSetIndex < sc.lightSetCount) {
+                SelasLightSetRange range = sc.lightSets[s.lightSetIndex];
+                lightCount = range.count;
+                lights = sc.lights + range.start;
+            }
+            if (lightCount > 0) nextEventEstimation(rng, lights, lightCount, s.position, shadingNormal(s), ls);
+            if (dot(ls.radiance, v3(1.0f)) > 0) {
+                float fp, rpdf;
+                V3 refl = evaluateBsdf(s, frame, view, ls.direction, fp, rpdf);
+                if (dot(refl, v3(1.0f)) > 0) {
+                    // OcclusionRay, :71-92: origin offset 0.1*error along +-N, tnear = error, tfar = light distance
+                    V3 so = offsetRayOrigin(s, ls.direction, 0.1f);
+                    V3 smp = refl * ls.radiance * (1.0f / ls.pdfW);
+                    V3 c = smp * thr;
+                    shRay.ox = so.x; shRay.oy = so.y; shRay.oz = so.z; shRay.tnear = s.error;
+                    shRay.dx = ls.direction.x; shRay.dy = ls.direction.y; shRay.dz = ls.direction.z; shRay.tfar = ls.distance;
+                    shPayload = make_float4(c.x, c.y, c.z, __uint_as_float(pixel));
+                    wantShadow = true;
+                }
+            }
+            // ---- BSDF sampling, :197-226 ----
+            BsdfResult bs;
+            if (sampleBsdf(rng, s, frame, view, bs)) {
+                deltaOnly = deltaOnly && (bs.flags & SELAS_EVENT_DIRAC);
+                if (bs.flags == SELAS_EVENT_TRANSMISSION) {  // exact equality, :206
+                    if (medium.phase == SELAS_MEDIUM_VACUUM) {
+                        medium.phase = bs.mediumPhase;
+                        medium.extinction = bs.mediumExtinction;
+                    } else {
+                        medium.phase = SELAS_MEDIUM_VACUUM;
+                        medium.extinction = v3(0.0f);
+                    }
+                }
+                float weight = 1.0f;  // QUIRK :214-216: MIS weight forced to 1
+                thr = weight * thr * bs.reflectance;
+                V3 no = offsetRayOrigin(s, bs.wi, 1.0f);
+                o = no;
+                d = bs.wi;
+                if (bounce == 0 && prm.layerCount == 2) {  // Ld[0], :223-225
+                    atomicAdd(film + 3 * (size_t)pixel, bs.reflectance.x);
+                    atomicAdd(film + 3 * (size_t)pixel + 1, bs.reflectance.y);
+                    atomicAdd(film + 3 * (size_t)pixel + 2, bs.reflectance.z);
+                }
+                alive = true;
+            }
+        } else if (medium.phase != SELAS_MEDIUM_VACUUM) {  // scatter inside the medium, :228-233
+            o = o + rayDistance * d;
+            d = uniformSphere(rng);
+            alive = true;
+        } else {  // escaped: background, :234-243 (no IBL: both background variants are the constant)
+            V3 c = v3(sc.background[0], sc.background[1], sc.background[2]) * thr;
+            atomicAdd(filmRadiance + 3 * (size_t)pixel, c.x);
+            atomicAdd(filmRadiance + 3 * (size_t)pixel + 1, c.y);
+            atomicAdd(filmRadiance + 3 * (size_t)pixel + 2, c.z);
+        }
+
+        if (alive) {
+            ++bounce;
+            if (bounce > prm.rrStartBounce) {  // Russian roulette, :248-254; QUIRK: p is not clamped to 1
+                float p = maxf_(maxf_(thr.x, thr.y), thr.z);
+                if (rng.next() > p) alive = false;
+                thr = thr * (1.0f / p);
+            }
+            if (bounce >= prm.maxPathLength) alive = false;  // loop condition, :157
+        }
+        if (alive) {
+            float nextDistance = sampleDistance(rng, medium);  // next iteration's :160
+            outRay.ox = o.x; outRay.oy = o.y; outRay.oz = o.z; outRay.tnear = 0.0f;
+            outRay.dx = d.x; outRay.dy = d.y; outRay.dz = d.z; outRay.tfar = nextDistance;
+            outThrPix = make_float4(thr.x, thr.y, thr.z, __uint_as_float(pixel));
+            uint32_t fl = (bounce & 0xffffu) | (deltaOnly ? FLAG_DELTA_ONLY : 0u) | (medium.phase != SELAS_MEDIUM_VACUUM ? FLAG_IN_MEDIUM : 0u);
+            outRngFlags = make_uint2(rng.state, fl);
+            outMedium = make_float4(medium.extinction.x, medium.extinction.y, medium.extinction.z, 0.f);
+        }
+    }
+
+    // ---- warp-aggregated queue appends ----
+    uint32_t aliveMask = __ballot_sync(0xffffffffu, alive);
+    uint32_t shadowMask = __ballot_sync(0xffffffffu, wantShadow);
+    uint32_t baseA = 0, baseS = 0;
+    if (lane == 0) {
+        if (aliveMask) baseA = atomicAdd(counters + 0, (uint32_t)__popc(aliveMask));
+        if (shadowMask) baseS = atomicAdd(counters + 1, (uint32_t)__popc(shadowMask));
+    }
+    baseA = __shfl_sync(0xffffffffu, baseA, 0);
+    baseS = __shfl_sync(0xffffffffu, baseS, 0);
+    if (alive) {
+        uint32_t slot = baseA + __popc(aliveMask & ltMask);
+        float4* ro = reinterpret_cast<float4*>(raysOut + slot);
+        ro[0] = make_float4(outRay.ox, outRay.oy, outRay.oz, outRay.tnear);
+        ro[1] = make_float4(outRay.dx, outRay.dy, outRay.dz, outRay.tfar);
+        thrPixOut[slot] = outThrPix;
+        rngFlagsOut[slot] = outRngFlags;
+        if (outRngFlags.y & FLAG_IN_MEDIUM) mediumOut[slot] = outMedium;
+    }
+    if (wantShadow) {
+        uint32_t slot = baseS + __popc(shadowMask & ltMask);
+        float4* so = reinterpret_cast<float4*>(shadowRays + slot);
+        so[0] = make_float4(shRay.ox, shRay.oy, shRay.oz, shRay.tnear);
+        so[1] = make_float4(shRay.dx, shRay.dy, shRay.dz, shRay.tfar);
+        shadowPayload[slot] = shPayload;
+    }
+}
+
+int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
+                     cudaStream_t stream) {
+    SelasContext* ctx = scene->ctx;
+    if (rs.width == 0 || rs.height == 0 || rs.layerCount < 1 || rs.layerCount > 2 || rs.maxPathLength > 65535u) {
+        setError(ctx, "render settings out of range (width/height > 0, layerCount 1..2, maxPathLength <= 65535)");
+        return SELAS_ERR_ARGUMENT;
+    }
+    if (rs.misMode != 0) {
+        setError(ctx, "misMode %u not implemented (0 = reference weighting)", rs.misMode);
+        return SELAS_ERR_UNSUPPORTED;
+    }
+    const uint32_t pixels = rs.width * rs.height;
+    const uint64_t totalPaths = (uint64_t)pixels * rs.samplesPerPixel;
+    // paths in flight per pass: whole sample passes, about 8M
+    uint32_t sppPerPass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rs.samplesPerPixel, (8u << 20) / std::max(1u, pixels)));
+    const uint32_t capacity = (uint32_t)std::min<uint64_t>(totalPaths, (uint64_t)pixels * sppPerPass);
+    if (capacity == 0) return SELAS_OK;
+    int rc = ensureWavefront(scene, capacity, rs.maxPathLength);
+    if (rc) return rc;
+    WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
+    ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels};
+
+    SelasRenderStats st{};
+    cudaEventRecord(w->ev0, stream);
+    for (uint64_t first = 0; first < totalPaths; first += capacity) {
+        uint32_t count = (uint32_t)std::min<uint64_t>(capacity, totalPaths - first);
+        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
+        generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, w->rays[0],
+                                                              w->thrPix[0], w->rngFlags[0]);
+        ++st.kernelLaunches;
+        uint32_t n = count;
+        int cur = 0;
+        for (uint32_t it = 0; it < rs.maxPathLength && n > 0; ++it) {
+            uint32_t* ctr = w->counters + 4 * (size_t)it;
+            // closest hit over the dense path queue
+            rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, stream);
+            if (rc) return rc;
+            st.closestRays += n;
+            shadeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, nullptr, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
+                                                            w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
+                                                            w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film);
+            SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+            SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
+            uint32_t nNext = w->h_counts[0], nShadow = w->h_counts[1];
+            st.kernelLaunches += 2;
+            if (nShadow) {
+                float* filmRadiance = d_film + (rs.layerCount == 2 ? 3 * (size_t)pixels : 0);
+                rc = launchShadowAccumulate(scene, nullptr, nShadow, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3, stream);
+                if (rc) return rc;
+                st.occlusionRays += nShadow;
+                ++st.kernelLaunches;
+            }
+            n = nNext;
+            cur ^= 1;
+        }
+    }
+    cudaEventRecord(w->ev1, stream);
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
+    cudaEventElapsedTime(&st.renderMs, w->ev0, w->ev1);
+    st.pathSamples = totalPaths;
+    if (stats) *stats = st;
+    return SELAS_OK;
+}
+
+}  // namespace selas

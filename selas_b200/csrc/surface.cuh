@@ -1,0 +1,126 @@
+// surface.cuh -- hit -> shading point (frame + material), the device restatement of
+// CalculateSurfaceParams (Source/Core/Shading/SurfaceParameters.cpp:144-247) and of the HitParameters
+// fill-in done by RayPick (Source/Applications/Selas/Source/PathTracer.cpp:119-136).
+//
+// rtcInterpolate0 (SurfaceParameters.cpp:162-189) becomes direct gathers from the per-mesh attribute arrays:
+// triangles   t = (1-u-v) t0 + u t1 + v t2                              RTC_GEOMETRY_TYPE_TRIANGLE.3embree3:47
+// quads       t = (1-v)((1-u) t0 + u t1) + v ((1-u) t3 + u t2)          RTC_GEOMETRY_TYPE_QUAD.3embree3:52
+#pragma once
+#include "disney.cuh"
+#include "internal.h"
+#include "ptex_eval.cuh"
+
+namespace selas {
+
+SELAS_D float interpAttr(const float* a, const uint32_t* ix, uint32_t ipf, int comps, int c, float u, float v) {
+    if (ipf == 3) {
+        float t0 = __ldg(a + (size_t)ix[0] * comps + c), t1 = __ldg(a + (size_t)ix[1] * comps + c), t2 = __ldg(a + (size_t)ix[2] * comps + c);
+        return (1.0f - u - v) * t0 + u * t1 + v * t2;
+    }
+    float t0 = __ldg(a + (size_t)ix[0] * comps + c), t1 = __ldg(a + (size_t)ix[1] * comps + c), t2 = __ldg(a + (size_t)ix[2] * comps + c),
+          t3 = __ldg(a + (size_t)ix[3] * comps + c);
+    return (1.0f - v) * ((1.0f - u) * t0 + u * t1) + v * ((1.0f - u) * t3 + u * t2);
+}
+
+SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, float v, uint32_t primID, uint32_t geomID,
+                            uint32_t instID, Surface& s) {
+    const MeshGpu mesh = sc.meshes[geomID];
+    const InstanceGpu* inst = sc.instances + instID;
+    const SelasMaterial* mat = sc.materials + mesh.materialIndex;
+    uint32_t ix[4];
+    const uint32_t* ip = mesh.indices + (size_t)primID * mesh.indicesPerFace;
+    ix[0] = __ldg(ip); ix[1] = __ldg(ip + 1); ix[2] = __ldg(ip + 2);
+    ix[3] = mesh.indicesPerFace == 4 ? __ldg(ip + 3) : 0u;
+    const bool identity = inst->identity != 0;
+    float m[16];
+    if (!identity)
+        for (int k = 0; k < 16; ++k) m[k] = inst->m[k];
+
+    V3 normal;
+    if (mesh.normals) {
+        normal = v3(interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 0, u, v), interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 1, u, v),
+                    interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 2, u, v));
+    } else {
+        // hit->normal = Embree's Ng: object-space cross(v1-v0, v2-v0) of the triangle that was hit
+        uint32_t i0, i1, i2;
+        if (mesh.indicesPerFace == 3) { i0 = ix[0]; i1 = ix[1]; i2 = ix[2]; }
+        else if ((u + v) <= 1.0f) { i0 = ix[0]; i1 = ix[1]; i2 = ix[3]; }
+        else { i0 = ix[2]; i1 = ix[3]; i2 = ix[1]; }
+        V3 p0 = v3(mesh.positions + 3 * (size_t)i0), p1 = v3(mesh.positions + 3 * (size_t)i1), p2 = v3(mesh.positions + 3 * (size_t)i2);
+        normal = cross(p1 - p0, p2 - p0);
+    }
+    // QUIRK SurfaceParameters.cpp:165-171: normals go through localToWorld as plain vectors (no inverse transpose)
+    if (!identity) normal = mulVec44(normal, m);
+    V3 n = normalize(normal);
+    V3 tg, b;
+    if (mesh.tangents) {
+        V3 lt = v3(interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 0, u, v), interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 1, u, v),
+                   interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 2, u, v));
+        float w = interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 3, u, v);
+        tg = identity ? lt : mulVec44(lt, m);
+        b = cross(n, tg) * w;
+    } else {  // MakeOrthogonalCoordinateSystem, GeometryLib/CoordinateSystem.h:14-21
+        if (fabsf(n.x) > fabsf(n.y))
+            tg = v3(-n.z, 0.f, n.x) * (1.0f / sqrtf(n.x * n.x + n.z * n.z));
+        else
+            tg = v3(0.f, n.z, -n.y) * (1.0f / sqrtf(n.y * n.y + n.z * n.z));
+        b = cross(n, tg);
+    }
+
+    V3 base;
+    if ((mat->flags & SELAS_MAT_USES_PTEX) && mesh.ptex) {
+        // SurfaceParameters.cpp:196-208: filter->eval(faceid = primId, u, v, widths 0), then pow 2.2 only
+        float rgb[3];
+        ptexEvalBspline((const PtexGpu*)mesh.ptex, (int)primID, u, v, rgb);
+        base = v3(rgb[0], rgb[1], rgb[2]);
+    } else {
+        base = v3(mat->baseColor);  // non-Ptex textures: SURVEY.md 8(f)4, not in this round
+    }
+    // QUIRK SurfaceParameters.cpp:204,:211-212: pow(x, 2.2) applied on top of everything
+    s.baseColor = v3(powf(base.x, 2.2f), powf(base.y, 2.2f), powf(base.z, 2.2f));
+
+    // worldToTangent = transpose(rows(t, n, b))
+    s.w2t[0] = tg.x; s.w2t[1] = n.x; s.w2t[2] = b.x;
+    s.w2t[3] = tg.y; s.w2t[4] = n.y; s.w2t[5] = b.y;
+    s.w2t[6] = tg.z; s.w2t[7] = n.z; s.w2t[8] = b.z;
+    // RayPick: position recomputed from the ray, error bound from |p| and t  (PathTracer.cpp:119-136)
+    V3 pos = v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z);
+    s.position = pos;
+    const float kErr = 32.0f * 1.19209e-07f;
+    s.error = kErr * maxf_(maxf_(fabsf(pos.x), fabsf(pos.y)), maxf_(fabsf(pos.z), t));
+    s.materialFlags = mat->flags;
+    s.transmittance = v3(mat->transmittanceColor);
+    s.sheen = mat->scalars[SELAS_SHEEN];
+    s.sheenTint = mat->scalars[SELAS_SHEEN_TINT];
+    s.clearcoat = mat->scalars[SELAS_CLEARCOAT];
+    s.clearcoatGloss = mat->scalars[SELAS_CLEARCOAT_GLOSS];
+    s.specTrans = saturate_(mat->scalars[SELAS_SPEC_TRANS]);
+    s.diffTrans = mat->scalars[SELAS_DIFFUSE_TRANS] * 0.5f;  // QUIRK :229
+    s.flatness = mat->scalars[SELAS_FLATNESS];
+    s.anisotropic = mat->scalars[SELAS_ANISOTROPIC];
+    s.specularTint = mat->scalars[SELAS_SPECULAR_TINT];
+    s.roughness = mat->scalars[SELAS_ROUGHNESS];
+    s.metallic = saturate_(mat->scalars[SELAS_METALLIC]);
+    s.scatterDistance = mat->scalars[SELAS_SCATTER_DISTANCE];
+    s.ior = mat->scalars[SELAS_IOR];
+    s.lightSetIndex = mesh.lightSetIndex;
+    s.shader = mat->shader;
+    V3 view = v3(-d.x, -d.y, -d.z);
+    s.relativeIOR = ((mat->flags & SELAS_MAT_TRANSPARENT) && dot(view, n) < 0.0f) ? s.ior : 1.0f / s.ior;
+}
+
+SELAS_D void storeSurface(const Surface& s, V3 view, SelasSurface& o) {
+    store3(o.position, s.position);
+    for (int i = 0; i < 9; ++i) o.worldToTangent[i] = s.w2t[i];
+    o.error = s.error;
+    store3(o.view, view);
+    store3(o.baseColor, s.baseColor);
+    store3(o.transmittanceColor, s.transmittance);
+    o.sheen = s.sheen; o.sheenTint = s.sheenTint; o.clearcoat = s.clearcoat; o.clearcoatGloss = s.clearcoatGloss;
+    o.metallic = s.metallic; o.specTrans = s.specTrans; o.diffTrans = s.diffTrans; o.flatness = s.flatness;
+    o.anisotropic = s.anisotropic; o.relativeIOR = s.relativeIOR; o.specularTint = s.specularTint; o.roughness = s.roughness;
+    o.scatterDistance = s.scatterDistance; o.ior = s.ior;
+    o.shader = s.shader; o.materialFlags = s.materialFlags; o.lightSetIndex = s.lightSetIndex;
+}
+
+}  // namespace selas

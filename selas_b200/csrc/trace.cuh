@@ -1,0 +1,142 @@
+// trace.cuh -- ray-cast kernels over the BVH8: persistent warps with per-lane refill.
+//
+// Launch shape: grid = SMs x resident CTAs, 128 threads per CTA; every warp keeps pulling rays from a
+// global counter.  A lane that finishes its ray waits until fewer than REFILL_THRESHOLD lanes of its warp
+// are still traversing, then the idle lanes are refilled together (one atomicAdd per refill, ballot-ranked
+// slots) -- the warp-ballot compaction the north star asks for.  Ray and hit records are 32 bytes and are
+// moved as two 16-byte vectors.
+#pragma once
+#include "bvh8.cuh"
+
+namespace selas {
+
+#define SELAS_TRACE_THREADS 128
+#define SELAS_REFILL_THRESHOLD 20
+
+// MODE 0: closest hit -> hits (+Ng); 1: any hit -> occluded byte; 2: any hit -> film[pixel] += payload.rgb when
+// unoccluded (the NEE shadow ray of PathTracer.cpp:186-191 fused with FramebufferWriter_Write).
+// nPtr != null: the ray count is read from device memory (wavefront queues), n is then only an upper bound.
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n,
+                                                                   const uint32_t* __restrict__ nPtr,
+                                                                   SelasHit* __restrict__ hits, uint8_t* __restrict__ occluded,
+                                                                   float4* __restrict__ ng, uint32_t* __restrict__ counts,
+                                                                   const float4* __restrict__ payload, float* __restrict__ film,
+                                                                   uint32_t* __restrict__ nextRay) {
+    constexpr bool ANY = MODE != 0;
+    if (nPtr) n = min(n, *nPtr);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ltMask = (1u << lane) - 1u;
+
+    // per-lane traversal state
+    uint2 stack[SELAS_STACK_SIZE];
+    int sp = 0;
+    uint2 group = make_uint2(0u, 0u);
+    V3 o = v3(0.f), d = v3(0.f), idir = v3(0.f);
+    float tnear = 0.f, tfar = 0.f, tmax = 0.f;
+    bool negx = false, negy = false, negz = false;
+    uint32_t octInv4 = 0;
+    TraceResult res;
+    res.t = 0.f; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
+    uint32_t rayIdx = 0xFFFFFFFFu;
+    uint32_t nNodes = 0, nTris = 0;
+    bool active = false;
+    bool exhausted = false;
+
+    for (;;) {
+        // ---- refill idle lanes ----
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(nextRay, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n) exhausted = true;
+            if (!active) {
+                uint32_t idx = base + __popc(idle & ltMask);
+                if (idx < n) {
+                    const float4* rp = reinterpret_cast<const float4*>(rays + idx);
+                    float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                    o = v3(r0.x, r0.y, r0.z);
+                    d = v3(r1.x, r1.y, r1.z);
+                    tnear = r0.w;
+                    tfar = r1.w;
+                    tmax = tfar;
+                    const float tiny = 1e-30f;
+                    idir = v3(1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)),
+                              1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+                              1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+                    negx = d.x < 0.0f; negy = d.y < 0.0f; negz = d.z < 0.0f;
+                    uint32_t oct = (negx ? 4u : 0u) | (negy ? 2u : 0u) | (negz ? 1u : 0u);
+                    octInv4 = (7u - oct) * 0x01010101u;
+                    res.t = tfar; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
+                    sp = 0;
+                    group = make_uint2(0u, bvh.nodeCount ? 0x80000000u : 0u);
+                    rayIdx = idx;
+                    nNodes = 0; nTris = 0;
+                    active = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+
+        // ---- traverse until this lane finishes or the warp runs thin ----
+        while (active) {
+            bool finished = false;
+            uint2 triGroup;
+            if (group.y & 0xff000000u) {
+                uint32_t hitsImask = group.y;
+                uint32_t childBit = 31u - __clz(hitsImask);
+                group.y &= ~(1u << childBit);
+                if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
+                uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
+                uint32_t rel = __popc(hitsImask & ~(0xffffffffu << slot));
+                const float4* np = bvh.nodes + (size_t)(group.x + rel) * 5;
+                float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                if (COUNT) ++nNodes;
+                uint32_t hitMask = intersectNode(n0, n1, n2, n3, n4, o, idir, negx, negy, negz, octInv4, tnear, tmax);
+                group.x = __float_as_uint(n1.x);
+                triGroup.x = __float_as_uint(n1.y);
+                group.y = (hitMask & 0xff000000u) | extractByte(__float_as_uint(n0.w), 3);
+                triGroup.y = hitMask & 0x00ffffffu;
+            } else {
+                triGroup = group;
+                group = make_uint2(0u, 0u);
+            }
+            while (triGroup.y != 0u) {
+                uint32_t bit = 31u - __clz(triGroup.y);
+                triGroup.y &= ~(1u << bit);
+                uint32_t ti = triGroup.x + bit;
+                const float4* tp = bvh.tris + (size_t)ti * 3;
+                float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) ++nTris;
+                float t, u, v;
+                if (intersectTri(a, b, c, o, d, tnear, tmax, t, u, v)) {
+                    tmax = t;
+                    res.t = t; res.u = u; res.v = v; res.tri = ti;
+                    if (ANY) { finished = true; break; }
+                }
+            }
+            if (!finished && (group.y & 0xff000000u) == 0u) {
+                if (sp == 0) finished = true;
+                else group = stack[--sp];
+            }
+            if (finished) {
+                if (MODE == 1) occluded[rayIdx] = res.tri != 0xFFFFFFFFu ? 1 : 0;
+                else if (MODE == 2) {
+                    if (res.tri == 0xFFFFFFFFu) {
+                        float4 pl = __ldg(payload + rayIdx);
+                        float* px = film + 3 * (size_t)__float_as_uint(pl.w);
+                        atomicAdd(px, pl.x);
+                        atomicAdd(px + 1, pl.y);
+                        atomicAdd(px + 2, pl.z);
+                    }
+                } else writeHit(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
+                if (COUNT) { counts[2 * (size_t)rayIdx] = nNodes; counts[2 * (size_t)rayIdx + 1] = nTris; }
+                active = false;
+            }
+            if (!exhausted && __popc(__activemask()) < SELAS_REFILL_THRESHOLD) break;
+        }
+    }
+}
+
+}  // namespace selas
