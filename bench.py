@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- path samples/s of the wavefront PathTracer on BASELINE.json's config 3 (full Disney BSDF, synthetic
+~10M-triangle scene, 1920x1080, depth 16), sample passes sharded over N GPUs.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            # the reference's CPU path (tier B) on the host cores
+
+A "step" is one pass of --spp-per-step samples per pixel over the whole 1080p frame on every GPU (weak scaling: per-GPU
+work is fixed, rank r renders its own sample indices).  `value` = paths/s with the scene, BVH and film resident in HBM
+(CUDA events on the render stream, max over ranks, one NCCL reduce of the film inside the timed region when N > 1);
+`e2e` = the same metric through the host-buffer C-ABI call selas_cuda_render_pathtracer (pinned host film buffers,
+device->host copy of the film every step).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "path_samples_per_s_1080p"
+UNIT = "samples/s"
+WIDTH, HEIGHT, MAX_DEPTH, RR_START = 1920, 1080, 16, 8
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="selas_b200", choices=["selas_b200", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=4)
+    ap.add_argument("--grid", type=int, default=2236, help="heightfield cells per side (2236 -> ~10M triangles)")
+    ap.add_argument("--cpu-stride", type=int, default=16, help="pixel stride of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-raycast", action="store_true", help="skip the config-2 Mrays/s side measurement")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus, tris):
+    return {
+        "workload": "BASELINE configs[2]: full Disney BSDF (metallic/clearcoat/sheen/specTrans/thin), synthetic heightfield+spheres, "
+                    f"{tris} triangles, 1920x1080, depth 16, RR after 8, 4 quad lights, constant background",
+        "triangles": int(tris), "width": WIDTH, "height": HEIGHT, "max_depth": MAX_DEPTH,
+        "spp_per_step_per_gpu": args.spp_per_step, "paths_per_step": WIDTH * HEIGHT * args.spp_per_step * n_gpus,
+        "sharding": f"sample passes over {n_gpus} GPU(s), scene replicated, one NCCL reduce of the film",
+        "mis": "reference (weight 1.0, PathTracer.cpp:215)",
+        "l2": "no explicit flush: BVH+triangles (~1 GB) and the wavefront queues (~1 GB) exceed the 126 MB L2",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+                power.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_cpu_arm(data, camera, args, steps, warmup, which="auto"):
+    """The reference's CPU path for this workload: EvaluatePath over the reference's own Shading objects when
+    oracle/_ref was built here ("reference"), else over the restatement ("port"); ray casting by the oracle's
+    scalar SAH BVH in both (Embree is not available: BASELINE.md tier B).  Bounded sample: every cpu-stride-th pixel."""
+    from selas_b200 import capi
+    from tests import oracle_binding
+
+    lib, kind = None, "port"
+    if which in ("auto", "reference"):
+        lib = oracle_binding.load_ref()
+        kind = "reference"
+    if lib is None:
+        lib, kind = oracle_binding.load_oracle(), "port"
+    threads = cpu_threads()
+    t0 = time.perf_counter()
+    h = lib.scene_create(data)
+    build_s = time.perf_counter() - t0
+    rs = capi.render_settings(WIDTH, HEIGHT, 1, MAX_DEPTH, RR_START, layers=1, seed=1, pixel_stride=args.cpu_stride)
+    times, paths, rays = [], 0, 0
+    for i in range(warmup + steps):
+        rs.firstSample = i
+        t0 = time.perf_counter()
+        _, st = lib.render(h, camera, rs, nthreads=threads)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            paths += st.pathSamples
+            rays += st.closestRays + st.occlusionRays
+    lib.scene_destroy(h)
+    total = sum(times)
+    return {"value": paths / total, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"every {args.cpu_stride}th pixel of the 1080p frame, 1 spp per step, {steps} steps "
+                      f"({paths} paths, {total:.1f} s; CPU BVH build {build_s:.1f} s excluded)",
+            "mrays_per_s": rays / total / 1e6, "ms_per_step": 1e3 * total / max(1, len(times)), "paths_per_step": paths // max(1, len(times)),
+            "ray_cast": "oracle scalar SAH-BVH2 (Embree 3.2.0 absent: headers only in the reference tree)"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+
+    from selas_b200 import capi, scenes
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        t0 = time.perf_counter()
+        data = scenes.disney_heightfield(grid=args.grid)
+        camera = scenes.heightfield_camera(WIDTH, HEIGHT)
+        log(f"[reference arm] scene generated in {time.perf_counter() - t0:.1f} s")
+        steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+        r = run_cpu_arm(data, camera, args, steps, warmup)
+        cfg = workload_config(args, n_gpus, data.triangle_count())
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": cfg,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ray_cast")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    t0 = time.perf_counter()
+    data = scenes.disney_heightfield(grid=args.grid)
+    camera = scenes.heightfield_camera(WIDTH, HEIGHT)
+    tris = data.triangle_count()
+    if rank == 0:
+        log(f"scene generated: {tris} triangles in {time.perf_counter() - t0:.1f} s")
+    ctx = capi.Context(local_rank)  # raises if libselas_cuda.so or the GPU is missing: no fallback
+    t0 = time.perf_counter()
+    scene = capi.Scene(ctx, data)
+    upload_s = time.perf_counter() - t0
+    bvh = scene.bvh_stats()
+    if rank == 0:
+        log(f"scene upload + BVH8 build: {upload_s:.2f} s (device build {bvh.buildMs:.1f} ms, {bvh.nodeCount} nodes, "
+            f"{bvh.deviceBytes / 1e9:.2f} GB)")
+
+    S = args.spp_per_step
+    pixels = WIDTH * HEIGHT
+    film = torch.zeros(pixels * 3, dtype=torch.float32, device=dev)
+    stream = torch.cuda.Stream(dev)  # explicit stream: the library launches on it and the CUDA events below are recorded on it
+    torch.cuda.set_stream(stream)
+
+    def settings(step_index, flags=0):
+        # rank r renders sample indices [(step*world + r) * S, +S): disjoint streams across ranks and steps
+        return capi.render_settings(WIDTH, HEIGHT, S, MAX_DEPTH, RR_START, layers=1, seed=1,
+                                    first_sample=(step_index * world + rank) * S, flags=flags)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident arm: value ---------------------------------------------------------------------------
+    for i in range(args.warmup):
+        scene.render_device(camera, settings(i), film.data_ptr(), stream.cuda_stream)
+    film.zero_()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"closestMs": 0.0, "shadeMs": 0.0, "shadowMs": 0.0, "generateMs": 0.0, "closestRays": 0, "occlusionRays": 0, "launches": 0,
+           "closestLaunches": 0}
+    e0.record(stream)
+    for i in range(args.steps):
+        st = scene.render_device(camera, settings(args.warmup + i), film.data_ptr(), stream.cuda_stream)
+        for k in ("closestMs", "shadeMs", "shadowMs", "generateMs"):
+            agg[k] += getattr(st, k)
+        agg["closestRays"] += st.closestRays
+        agg["occlusionRays"] += st.occlusionRays
+        agg["launches"] += st.kernelLaunches
+        agg["closestLaunches"] += st.closestLaunches
+    if world > 1:
+        dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)  # the path's only collective
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    paths_total = pixels * S * args.steps * world
+    value = paths_total / (total_ms * 1e-3)
+    # FrameBuffer_Scale (Framebuffer.cpp:62-70) on the reduced film, outside the timed region like the reference's save path
+    if rank == 0:
+        ctx.check(ctx.lib.selas_cuda_film_scale_device(ctx.handle, capi.C.c_void_p(film.data_ptr()), capi.C.c_size_t(film.numel()),
+                                                       capi.f32(1.0 / (S * args.steps * world)), capi.C.c_void_p(stream.cuda_stream)))
+        torch.cuda.synchronize(dev)
+        mean_radiance = float(film.mean().item())
+        assert np.isfinite(mean_radiance) and mean_radiance > 0.0, "film is empty or not finite"
+
+    # ---- end-to-end arm through the host-buffer C ABI ---------------------------------------------------------------
+    host_film = torch.zeros(pixels * 3, dtype=torch.float32).pin_memory()
+    host_np = host_film.numpy()
+    ptrs = (capi.C.c_void_p * 1)(host_np.ctypes.data)
+    e2e_steps = max(1, min(args.steps, 3))
+    stats = capi.RenderStats()
+
+    def e2e_step(i):
+        rs = settings(1000 + i)
+        ctx.check(ctx.lib.selas_cuda_render_pathtracer(scene.handle, capi.C.byref(camera), capi.C.byref(rs), ptrs, capi.C.byref(stats)))
+        return float(host_np[::4099].sum())  # the step's result is read on the host
+
+    e2e_step(-1)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = pixels * S * e2e_steps * world / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (closest-hit traversal) -------------------------------------------------------
+    cst = scene.render_device(camera, settings(2000, flags=capi.RENDER_COUNT_TRAVERSAL), film.data_ptr(), stream.cuda_stream)
+    n_node = cst.closestNodes / max(1, cst.closestRays)
+    n_tri = cst.closestTris / max(1, cst.closestRays)
+    s_node = cst.shadowNodes / max(1, cst.occlusionRays)
+    s_tri = cst.shadowTris / max(1, cst.occlusionRays)
+    bytes_per_ray = 64.0 + 80.0 * n_node + 48.0 * n_tri        # 32 in + 32 out + 80/node + 48/triangle
+    shadow_bytes_per_ray = 36.0 + 80.0 * s_node + 48.0 * s_tri
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per_ray * agg["closestRays"] / (agg["closestMs"] * 1e-3) / 1e9 if agg["closestMs"] > 0 else 0.0
+    kernel_ms = agg["closestMs"] + agg["shadeMs"] + agg["shadowMs"] + agg["generateMs"]
+    roofline = {"bound": "hbm", "kernel": "traceKernel<0> (BVH8 closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
+                "rays_per_launch": agg["closestRays"] / max(1, agg["closestLaunches"]),
+                "avg_launch_ms": agg["closestMs"] / max(1, agg["closestLaunches"]),
+                "kernel_share_of_step": {"closest": agg["closestMs"] / kernel_ms, "shade": agg["shadeMs"] / kernel_ms,
+                                         "shadow": agg["shadowMs"] / kernel_ms, "generate": agg["generateMs"] / kernel_ms},
+                "shadow": {"algorithmic_bytes_per_ray": shadow_bytes_per_ray, "nodes_per_ray": s_node, "tris_per_ray": s_tri,
+                           "achieved": shadow_bytes_per_ray * agg["occlusionRays"] / (agg["shadowMs"] * 1e-3) / 1e9 if agg["shadowMs"] > 0 else 0.0}}
+    mrays = {"closest": agg["closestRays"] / (agg["closestMs"] * 1e-3) / 1e6 if agg["closestMs"] > 0 else 0.0,
+             "occlusion": agg["occlusionRays"] / (agg["shadowMs"] * 1e-3) / 1e6 if agg["shadowMs"] > 0 else 0.0,
+             "whole_step": (agg["closestRays"] + agg["occlusionRays"]) * world / (total_ms * 1e-3) / 1e6}
+
+    raycast = None
+    if not args.no_raycast:
+        try:
+            raycast = raycast_microbench(ctx, torch, dev, stream)
+        except Exception as ex:  # side measurement only: never hide the headline
+            raycast = {"error": str(ex)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        scene.close()
+        r = run_cpu_arm(data, camera, args, steps=2, warmup=0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ray_cast", "mrays_per_s")}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, world, tris), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.RenderSettings),
+                    "d2h_bytes_per_step": pixels * 3 * 4, "steps": e2e_steps,
+                    "api": "selas_cuda_render_pathtracer (pinned host film, scene resident as in the reference's GenerateImage)"},
+            "gpu_launches": int(agg["launches"]), "roofline": roofline, "cpu_baseline": cpu, "mrays_per_s": mrays, "raycast_config2": raycast,
+            "bvh": {"build_ms": bvh.buildMs, "nodes": bvh.nodeCount, "triangles": bvh.triangleCount, "device_gb": bvh.deviceBytes / 1e9,
+                    "upload_plus_build_s": upload_s},
+            "mean_radiance": mean_radiance}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def raycast_microbench(ctx, torch, dev, stream):
+    """BASELINE configs[1]: 1M-triangle displaced sphere, 1920x1080 primary rays + one shadow ray per hit toward (5,5,5)
+    + incoherent cosine bounce rays; Mrays/s of the device-resident entry points (CUDA events, median of 10)."""
+    from selas_b200 import capi, scenes
+
+    data = scenes.raycast_scene()
+    sc = capi.Scene(ctx, data)
+    cam = scenes.raycast_camera(WIDTH, HEIGHT)
+    rays = scenes.primary_rays(cam, WIDTH, HEIGHT)
+    hits, ng = sc.intersect(rays, want_ng=True)
+    sh = scenes.shadow_rays_toward(rays, hits, ng, (5.0, 5.0, 5.0))
+    inc = scenes.cosine_bounce_rays(rays, hits, ng)
+    out = {"triangles": data.triangle_count(), "bvh_build_ms": sc.bvh_stats().buildMs, "primary_hit_fraction": float((hits["geomID"] != capi.SELAS_INVALID_ID).mean())}
+    peak, _ = measured_peaks()
+
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+
+    for name, r, anyhit in (("primary_closest", rays, False), ("shadow_occlusion", sh, True), ("incoherent_closest", inc, False)):
+        d_r = to_dev(r)
+        n = r.size
+        d_h = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+        d_o = torch.empty(n, dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(13):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            if anyhit:
+                sc.occluded_device(n, d_r.data_ptr(), d_o.data_ptr(), stream.cuda_stream)
+            else:
+                sc.intersect_device(n, d_r.data_ptr(), d_h.data_ptr(), 0, stream.cuda_stream)
+            b.record(stream)
+            torch.cuda.synchronize(dev)
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        _, counts = sc.intersect_counted(r, any_hit=anyhit)
+        nn, nt = float(counts[:, 0].mean()), float(counts[:, 1].mean())
+        bpr = (36.0 if anyhit else 64.0) + 80.0 * nn + 48.0 * nt
+        out[name] = {"rays": int(n), "ms": ms, "mrays_per_s": n / ms / 1e3, "nodes_per_ray": nn, "tris_per_ray": nt,
+                     "algorithmic_bytes_per_ray": bpr, "achieved_gbs": bpr * n / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": bpr * n / (ms * 1e-3) / 1e9 / peak}
+    sc.close()
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -190,6 +190,9 @@ typedef struct SelasSceneDesc {
 } SelasSceneDesc;
 
 /* Compile-time macros of the reference integrator made runtime (PathTracer.cpp:42-46, :248). */
+/* SelasRenderSettings.flags */
+enum { SELAS_RENDER_COUNT_TRAVERSAL = 1 /* use the counting build of the trace kernels and fill the node/triangle totals */ };
+
 typedef struct SelasRenderSettings {
     uint32_t width, height;
     uint32_t samplesPerPixel; /* PathsPerPixel_ */
@@ -199,7 +202,9 @@ typedef struct SelasRenderSettings {
     uint32_t seed;
     uint32_t firstSample;     /* sample-pass shard: this call renders samples [firstSample, firstSample+samplesPerPixel) */
     uint32_t misMode;         /* 0 = reference (weight 1.0, PathTracer.cpp:215); 1 = balance heuristic */
-    uint32_t reserved[3];
+    uint32_t flags;           /* SELAS_RENDER_* */
+    uint32_t pixelStride;     /* 0/1 = every pixel; k = only pixels p with p % k == 0 (bounded samples of a workload) */
+    uint32_t reserved;
 } SelasRenderSettings;
 
 typedef struct SelasRenderStats {
@@ -207,8 +212,14 @@ typedef struct SelasRenderStats {
     uint64_t occlusionRays;
     uint64_t pathSamples;
     uint64_t kernelLaunches;
-    float    renderMs; /* device time of the wavefront loop (CUDA events) */
-    float    pad;
+    float    renderMs;   /* device time of the whole wavefront loop (CUDA events on the render stream) */
+    float    generateMs; /* per-kernel device time, summed over launches (CUDA events around every launch) */
+    float    closestMs;
+    float    shadeMs;
+    float    shadowMs;
+    uint32_t closestLaunches, shadeLaunches, shadowLaunches;
+    /* filled only with SELAS_RENDER_COUNT_TRAVERSAL: BVH8 nodes visited / triangles tested, summed over rays */
+    uint64_t closestNodes, closestTris, shadowNodes, shadowTris;
 } SelasRenderStats;
 
 typedef struct SelasBvhStats {

@@ -530,6 +530,7 @@ int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
     memcpy(&rc, cam, sizeof(rc));
     std::atomic<size_t> next(0);
     std::atomic<uint64_t> closest(0), shadow(0);
+    const size_t stride = rs->pixelStride > 1 ? rs->pixelStride : 1;
     auto worker = [&]() {
         setFtz();
         FakeContext fc;
@@ -543,6 +544,7 @@ int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
             if (b >= pixels) break;
             size_t e = std::min(pixels, b + 1024);
             for (size_t p = b; p < e; ++p) {
+                if (stride > 1 && (p % stride) != 0) continue;  // bounded sample (SelasRenderSettings.pixelStride)
                 uint32_t y = (uint32_t)(p / rs->width), x = (uint32_t)(p - (size_t)y * rs->width);
                 for (uint32_t k = 0; k < rs->samplesPerPixel; ++k) {
                     g_src = DrawSource{nullptr, 0, 0, mix32(rs->seed ^ mix32((uint32_t)p ^ mix32(rs->firstSample + k + 0x9e3779b9u))), true};
@@ -640,7 +642,7 @@ int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
         memset(stats, 0, sizeof(*stats));
         stats->closestRays = closest;
         stats->occlusionRays = shadow;
-        stats->pathSamples = pixels * rs->samplesPerPixel;
+        stats->pathSamples = ((pixels + stride - 1) / stride) * rs->samplesPerPixel;
     }
     return 0;
 }

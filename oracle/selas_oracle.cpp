@@ -575,9 +575,11 @@ int orc_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
     size_t pixels = (size_t)rs->width * rs->height;
     for (uint32_t l = 0; l < rs->layerCount; ++l) memset(film[l], 0, pixels * 3 * sizeof(float));
     std::atomic<uint64_t> closest(0), shadow(0);
+    const size_t stride = rs->pixelStride > 1 ? rs->pixelStride : 1;
     parallelFor(pixels, nthreads, [&](size_t b, size_t e, int) {
         uint64_t c = 0, sh = 0;
         for (size_t p = b; p < e; ++p) {
+            if (stride > 1 && (p % stride) != 0) continue;  // bounded sample of a workload (SelasRenderSettings.pixelStride)
             uint32_t py = (uint32_t)(p / rs->width), px = (uint32_t)(p - (size_t)py * rs->width);
             for (uint32_t k = 0; k < rs->samplesPerPixel; ++k) {
                 V3 Ld[2];
@@ -598,7 +600,7 @@ int orc_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
         memset(stats, 0, sizeof(*stats));
         stats->closestRays = closest;
         stats->occlusionRays = shadow;
-        stats->pathSamples = pixels * rs->samplesPerPixel;
+        stats->pathSamples = ((pixels + stride - 1) / stride) * rs->samplesPerPixel;
     }
     return 0;
 }

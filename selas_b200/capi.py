@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from pathlib import Path
 
 import numpy as np
@@ -70,12 +71,14 @@ class SceneDesc(C.Structure):
 class RenderSettings(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("samplesPerPixel", u32), ("maxPathLength", u32),
                 ("rrStartBounce", u32), ("layerCount", u32), ("seed", u32), ("firstSample", u32), ("misMode", u32),
-                ("reserved", u32 * 3)]
+                ("flags", u32), ("pixelStride", u32), ("reserved", u32)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("closestRays", u64), ("occlusionRays", u64), ("pathSamples", u64), ("kernelLaunches", u64),
-                ("renderMs", f32), ("pad", f32)]
+                ("renderMs", f32), ("generateMs", f32), ("closestMs", f32), ("shadeMs", f32), ("shadowMs", f32),
+                ("closestLaunches", u32), ("shadeLaunches", u32), ("shadowLaunches", u32),
+                ("closestNodes", u64), ("closestTris", u64), ("shadowNodes", u64), ("shadowTris", u64)]
 
 
 class BvhStats(C.Structure):
@@ -172,6 +175,10 @@ class Context:
         if rc:
             raise SelasError(rc, self.lib.selas_cuda_last_error(None).decode())
         self.device = device
+        self._children = weakref.WeakSet()  # scenes / grids / textures: destroyed before the context
+
+    def adopt(self, child):
+        self._children.add(child)
 
     def check(self, rc: int):
         if rc:
@@ -179,6 +186,8 @@ class Context:
 
     def close(self):
         if self.handle:
+            for child in list(self._children):
+                child.close()
             self.lib.selas_cuda_context_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -335,6 +344,7 @@ class Scene:
         desc, keep = data.to_desc()
         self.handle = C.c_void_p()
         ctx.check(self.lib.selas_cuda_scene_create(ctx.handle, C.byref(desc), C.byref(self.handle)))
+        ctx.adopt(self)
         del keep
 
     def close(self):
@@ -406,8 +416,13 @@ class Scene:
                                                            C.c_void_p(stream)))
 
 
-def render_settings(width, height, spp, max_path_length=8, rr_start=8, layers=1, seed=1, first_sample=0, mis_mode=0):
+RENDER_COUNT_TRAVERSAL = 1
+
+
+def render_settings(width, height, spp, max_path_length=8, rr_start=8, layers=1, seed=1, first_sample=0, mis_mode=0,
+                    flags=0, pixel_stride=0):
     rs = RenderSettings()
+    rs.flags, rs.pixelStride = flags, pixel_stride
     rs.width, rs.height, rs.samplesPerPixel = width, height, spp
     rs.maxPathLength, rs.rrStartBounce, rs.layerCount = max_path_length, rr_start, layers
     rs.seed, rs.firstSample, rs.misMode = seed, first_sample, mis_mode
@@ -426,6 +441,7 @@ class HashGrid:
         self.handle = C.c_void_p()
         ctx.check(self.lib.selas_cuda_hashgrid_build(ctx.handle, C.c_size_t(self.n), _ptr(positions), f32(radius),
                                                      u32(cell_count), C.byref(self.handle)))
+        ctx.adopt(self)
 
     def read(self):
         ends = np.zeros(self.cell_count, np.uint32)
@@ -463,6 +479,7 @@ class Ptex:
         self.lib = ctx.lib
         self.handle = C.c_void_p()
         ctx.check(self.lib.selas_cuda_ptex_load(ctx.handle, str(path).encode(), C.byref(self.handle)))
+        ctx.adopt(self)
 
     def eval(self, faceid, u, v):
         faceid = np.ascontiguousarray(faceid, dtype=np.int32)

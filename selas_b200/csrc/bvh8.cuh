@@ -177,27 +177,28 @@ SELAS_D void traceRay(const Bvh8& bvh, V3 o, V3 d, float tnear, float tfar, Trac
     if (COUNT) { counters[0] = nNodes; counters[1] = nTris; }
 }
 
-// Fill the 32-byte hit record (and optional Ng) from a trace result.
+// Fill the 32-byte hit record (and optional Ng) from a trace result.  The ids travel as integers: bit-casting a
+// small id to float and masking it lets the compiler emit abs.ftz.f32, which flushes the (denormal) pattern to 0.
 SELAS_D void writeHit(const Bvh8& bvh, const TraceResult& r, float tfar, SelasHit* out, float4* ng) {
-    float4 h0, h1;
+    uint4 h0, h1;
     if (r.tri == 0xFFFFFFFFu) {
-        h0 = make_float4(tfar, 0.0f, 0.0f, __uint_as_float(SELAS_INVALID_ID));
-        h1 = make_float4(__uint_as_float(SELAS_INVALID_ID), __uint_as_float(SELAS_INVALID_ID), __uint_as_float(SELAS_INVALID_ID), 0.0f);
+        h0 = make_uint4(__float_as_uint(tfar), 0u, 0u, SELAS_INVALID_ID);
+        h1 = make_uint4(SELAS_INVALID_ID, SELAS_INVALID_ID, SELAS_INVALID_ID, 0u);
         if (ng) *ng = make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
-        const float4* tp = bvh.tris + (size_t)r.tri * 3;
-        float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-        uint32_t w2 = __float_as_uint(c.w);
-        bool second = (w2 >> 31) != 0;
+        const uint4* tp = reinterpret_cast<const uint4*>(bvh.tris + (size_t)r.tri * 3);
+        uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        bool second = (c.w >> 31) != 0;
         float u = second ? 1.0f - r.u : r.u, v = second ? 1.0f - r.v : r.v;
-        h0 = make_float4(r.t, u, v, a.w);
-        h1 = make_float4(b.w, __uint_as_float(w2 & 0x7fffffffu), __uint_as_float(0u), 0.0f);
+        h0 = make_uint4(__float_as_uint(r.t), __float_as_uint(u), __float_as_uint(v), a.w);
+        h1 = make_uint4(b.w, c.w & 0x7fffffffu, 0u, 0u);
         if (ng) {
-            V3 n = cross(v3(b.x, b.y, b.z), v3(c.x, c.y, c.z));
+            V3 n = cross(v3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)),
+                         v3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z)));
             *ng = make_float4(n.x, n.y, n.z, 0.f);
         }
     }
-    float4* o4 = reinterpret_cast<float4*>(out);
+    uint4* o4 = reinterpret_cast<uint4*>(out);
     o4[0] = h0;
     o4[1] = h1;
 }

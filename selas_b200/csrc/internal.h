@@ -94,9 +94,9 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
                    cudaStream_t stream);
 // shadow rays with film accumulation: payload = {contribution rgb, pixel}; film[pixel] += rgb when unoccluded
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
-                           float* d_film, uint32_t* d_rayCounter, cudaStream_t stream);
+                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream);
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
-                            uint32_t* d_rayCounter, cudaStream_t stream);
+                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream);
 
 // shade.cu
 int launchBsdfEval(SelasContext* ctx, size_t n, const SelasSurface* d_s, const float* d_v, const float* d_l, float* d_rgb, float* d_f,

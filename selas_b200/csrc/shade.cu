@@ -12,8 +12,10 @@
 //   shadow    32 B ray + 16 B {contribution rgb, pixel}
 // Paths that survive a bounce are appended to the next queue with one atomicAdd per warp (ballot-ranked),
 // so every launch works on a dense queue.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <vector>
 
 #include "disney.cuh"
 #include "internal.h"
@@ -238,12 +240,12 @@ static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterat
 
 // JitteredCameraRay (Camera.cpp:63-74) for path ids [first, first+count): pixel = id % pixels, sample = id / pixels.
 __global__ void generateKernel(SelasCamera cam, uint32_t width, uint32_t height, uint32_t seed, uint32_t firstSample, uint64_t firstPath,
-                               uint32_t count, SelasRay* __restrict__ rays, float4* __restrict__ thrPix, uint2* __restrict__ rngFlags) {
+                               uint32_t count, uint32_t activePixels, uint32_t pixelStride, SelasRay* __restrict__ rays,
+                               float4* __restrict__ thrPix, uint2* __restrict__ rngFlags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     uint64_t id = firstPath + i;
-    uint32_t pixels = width * height;
-    uint32_t pixel = (uint32_t)(id % pixels), sample = firstSample + (uint32_t)(id / pixels);
+    uint32_t pixel = (uint32_t)(id % activePixels) * pixelStride, sample = firstSample + (uint32_t)(id / activePixels);
     uint32_t y = pixel / width, x = pixel - y * width;
     PathRng rng;
     rng.init(seed, pixel, sample);
@@ -284,8 +286,8 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
     if (i < n) {
         const float4* rp = reinterpret_cast<const float4*>(rays + i);
         float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-        const float4* hp = reinterpret_cast<const float4*>(hits + i);
-        float4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+        const uint4* hp = reinterpret_cast<const uint4*>(hits + i);
+        uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
         float4 tp = __ldg(thrPix + i);
         uint2 rf = __ldg(rngFlags + i);
         V3 o = v3(r0.x, r0.y, r0.z), d = v3(r1.x, r1.y, r1.z);
@@ -302,13 +304,13 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
             medium.extinction = v3(m.x, m.y, m.z);
         }
         float rayDistance = r1.w;  // the distance sampled for this segment (FLT_MAX in vacuum), PathTracer.cpp:160
-        const uint32_t geomID = __float_as_uint(h1.x);
+        const uint32_t geomID = h1.x;
         const bool isHit = geomID != SELAS_INVALID_ID;
         float* filmRadiance = film + (prm.layerCount == 2 ? 3 * (size_t)prm.pixels : 0);
 
         Surface s;
         if (isHit) {
-            surfaceFromHit(sc, o, d, h0.x, h0.y, h0.z, __float_as_uint(h0.w), geomID, __float_as_uint(h1.y), s);
+            surfaceFromHit(sc, o, d, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, geomID, h1.y, s);
             rayDistance = length(s.position - o);  // :165-167
         }
         thr = thr * transmission(medium, rayDistance);  // :168-169
@@ -427,10 +429,52 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
     }
 }
 
+// CUDA events around every launch of the loop: per-kernel device time for the roofline report.
+struct KernelTimers {
+    std::vector<cudaEvent_t> pool;
+    struct Span { int kind; size_t a, b; };
+    std::vector<Span> spans;
+    size_t used = 0;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    size_t begin(cudaStream_t st) {
+        cudaEvent_t e = get();
+        cudaEventRecord(e, st);
+        return used - 1;
+    }
+    void end(int kind, size_t a, cudaStream_t st) {
+        cudaEvent_t e = get();
+        cudaEventRecord(e, st);
+        spans.push_back({kind, a, used - 1});
+    }
+    void collect(SelasRenderStats& st) {
+        for (const Span& sp : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pool[sp.a], pool[sp.b]);
+            if (sp.kind == 0) st.generateMs += ms;
+            else if (sp.kind == 1) { st.closestMs += ms; ++st.closestLaunches; }
+            else if (sp.kind == 2) { st.shadeMs += ms; ++st.shadeLaunches; }
+            else { st.shadowMs += ms; ++st.shadowLaunches; }
+        }
+        spans.clear();
+        used = 0;
+    }
+    ~KernelTimers() {
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+};
+
 int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
                      cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
-    if (rs.width == 0 || rs.height == 0 || rs.layerCount < 1 || rs.layerCount > 2 || rs.maxPathLength > 65535u) {
+    if (rs.width == 0 || rs.height == 0 || rs.layerCount < 1 || rs.layerCount > 2 || rs.maxPathLength > 65535u ||
+        (uint64_t)rs.width * rs.height > 0x7fffffffull) {
         setError(ctx, "render settings out of range (width/height > 0, layerCount 1..2, maxPathLength <= 65535)");
         return SELAS_ERR_ARGUMENT;
     }
@@ -439,35 +483,54 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         return SELAS_ERR_UNSUPPORTED;
     }
     const uint32_t pixels = rs.width * rs.height;
-    const uint64_t totalPaths = (uint64_t)pixels * rs.samplesPerPixel;
+    const uint32_t stride = rs.pixelStride > 1 ? rs.pixelStride : 1u;
+    const uint32_t activePixels = (pixels + stride - 1) / stride;
+    const uint64_t totalPaths = (uint64_t)activePixels * rs.samplesPerPixel;
     // paths in flight per pass: whole sample passes, about 8M
-    uint32_t sppPerPass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rs.samplesPerPixel, (8u << 20) / std::max(1u, pixels)));
-    const uint32_t capacity = (uint32_t)std::min<uint64_t>(totalPaths, (uint64_t)pixels * sppPerPass);
-    if (capacity == 0) return SELAS_OK;
+    uint32_t sppPerPass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rs.samplesPerPixel, (8u << 20) / std::max(1u, activePixels)));
+    const uint32_t capacity = (uint32_t)std::min<uint64_t>(totalPaths, (uint64_t)activePixels * sppPerPass);
+    SelasRenderStats st{};
+    if (capacity == 0 || rs.maxPathLength == 0) {
+        st.pathSamples = totalPaths;
+        if (stats) *stats = st;
+        return SELAS_OK;
+    }
     int rc = ensureWavefront(scene, capacity, rs.maxPathLength);
     if (rc) return rc;
     WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
     ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels};
+    const bool counting = (rs.flags & SELAS_RENDER_COUNT_TRAVERSAL) != 0;
+    unsigned long long* d_totals = nullptr;
+    if (counting) {
+        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&d_totals, 4 * sizeof(unsigned long long)));
+        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_totals, 0, 4 * sizeof(unsigned long long), stream));
+    }
+    KernelTimers timers;
 
-    SelasRenderStats st{};
     cudaEventRecord(w->ev0, stream);
     for (uint64_t first = 0; first < totalPaths; first += capacity) {
         uint32_t count = (uint32_t)std::min<uint64_t>(capacity, totalPaths - first);
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
-        generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, w->rays[0],
-                                                              w->thrPix[0], w->rngFlags[0]);
+        size_t t0 = timers.begin(stream);
+        generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, activePixels,
+                                                              stride, w->rays[0], w->thrPix[0], w->rngFlags[0]);
+        timers.end(0, t0, stream);
         ++st.kernelLaunches;
         uint32_t n = count;
         int cur = 0;
         for (uint32_t it = 0; it < rs.maxPathLength && n > 0; ++it) {
             uint32_t* ctr = w->counters + 4 * (size_t)it;
             // closest hit over the dense path queue
-            rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, stream);
+            t0 = timers.begin(stream);
+            rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, d_totals, stream);
             if (rc) return rc;
+            timers.end(1, t0, stream);
             st.closestRays += n;
+            t0 = timers.begin(stream);
             shadeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, nullptr, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
                                                             w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
                                                             w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film);
+            timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
             SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
@@ -475,8 +538,11 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             st.kernelLaunches += 2;
             if (nShadow) {
                 float* filmRadiance = d_film + (rs.layerCount == 2 ? 3 * (size_t)pixels : 0);
-                rc = launchShadowAccumulate(scene, nullptr, nShadow, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3, stream);
+                t0 = timers.begin(stream);
+                rc = launchShadowAccumulate(scene, nullptr, nShadow, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
+                                            d_totals ? d_totals + 2 : nullptr, stream);
                 if (rc) return rc;
+                timers.end(3, t0, stream);
                 st.occlusionRays += nShadow;
                 ++st.kernelLaunches;
             }
@@ -487,6 +553,13 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     cudaEventRecord(w->ev1, stream);
     SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
     cudaEventElapsedTime(&st.renderMs, w->ev0, w->ev1);
+    timers.collect(st);
+    if (counting) {
+        unsigned long long h[4];
+        SELAS_CUDA_CHECK(ctx, cudaMemcpy(h, d_totals, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d_totals);
+        st.closestNodes = h[0]; st.closestTris = h[1]; st.shadowNodes = h[2]; st.shadowTris = h[3];
+    }
     st.pathSamples = totalPaths;
     if (stats) *stats = st;
     return SELAS_OK;

@@ -203,10 +203,10 @@ int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, Selas
     int grid = traceGrid(ctx);
     if (d_counts)
         traceKernel<0, true><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts,
-                                                                        nullptr, nullptr, d_rayCounter);
+                                                                        nullptr, nullptr, d_rayCounter, nullptr);
     else
         traceKernel<0, false><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, nullptr,
-                                                                         nullptr, nullptr, d_rayCounter);
+                                                                         nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -219,29 +219,38 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
     int grid = traceGrid(ctx);
     if (d_counts)
         traceKernel<1, true><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr,
-                                                                        nullptr, d_rayCounter);
+                                                                        nullptr, d_rayCounter, nullptr);
     else
         traceKernel<1, false><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, nullptr, nullptr,
-                                                                         nullptr, d_rayCounter);
+                                                                         nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
 
-// Wavefront variants: the queue length lives in device memory; d_rayCounter must already be zero.
+// Wavefront variants: the queue length lives in device memory (or n is exact when d_n is null); d_rayCounter must
+// already be zero.  totals != null selects the counting build of the same kernel (SELAS_RENDER_COUNT_TRAVERSAL).
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
-                            uint32_t* d_rayCounter, cudaStream_t stream) {
+                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
-    traceKernel<0, false><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
-                                                                               nullptr, nullptr, d_rayCounter);
+    if (d_totals)
+        traceKernel<0, true><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
+                                                                                  nullptr, nullptr, d_rayCounter, d_totals);
+    else
+        traceKernel<0, false><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
+                                                                                   nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
 
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
-                           float* d_film, uint32_t* d_rayCounter, cudaStream_t stream) {
+                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
-    traceKernel<2, false><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
-                                                                               d_payload, d_film, d_rayCounter);
+    if (d_totals)
+        traceKernel<2, true><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
+                                                                                  d_payload, d_film, d_rayCounter, d_totals);
+    else
+        traceKernel<2, false><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
+                                                                                   d_payload, d_film, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }

@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                                                                    SelasHit* __restrict__ hits, uint8_t* __restrict__ occluded,
                                                                    float4* __restrict__ ng, uint32_t* __restrict__ counts,
                                                                    const float4* __restrict__ payload, float* __restrict__ film,
-                                                                   uint32_t* __restrict__ nextRay) {
+                                                                   uint32_t* __restrict__ nextRay,
+                                                                   unsigned long long* __restrict__ totals) {
     constexpr bool ANY = MODE != 0;
     if (nPtr) n = min(n, *nPtr);
     const uint32_t lane = threadIdx.x & 31u;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
     res.t = 0.f; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
     uint32_t rayIdx = 0xFFFFFFFFu;
     uint32_t nNodes = 0, nTris = 0;
+    unsigned long long sumNodes = 0, sumTris = 0;
     bool active = false;
     bool exhausted = false;
 
@@ -131,10 +133,24 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                         atomicAdd(px + 2, pl.z);
                     }
                 } else writeHit(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
-                if (COUNT) { counts[2 * (size_t)rayIdx] = nNodes; counts[2 * (size_t)rayIdx + 1] = nTris; }
+                if (COUNT) {
+                    if (counts) { counts[2 * (size_t)rayIdx] = nNodes; counts[2 * (size_t)rayIdx + 1] = nTris; }
+                    sumNodes += nNodes;
+                    sumTris += nTris;
+                }
                 active = false;
             }
             if (!exhausted && __popc(__activemask()) < SELAS_REFILL_THRESHOLD) break;
+        }
+    }
+    if (COUNT && totals) {
+        for (int s = 16; s > 0; s >>= 1) {
+            sumNodes += __shfl_xor_sync(0xffffffffu, sumNodes, s);
+            sumTris += __shfl_xor_sync(0xffffffffu, sumTris, s);
+        }
+        if (lane == 0) {
+            atomicAdd(totals, sumNodes);
+            atomicAdd(totals + 1, sumTris);
         }
     }
 }
