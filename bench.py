@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument("--impl", default="selas_b200", choices=["selas_b200", "reference"])
     ap.add_argument("--spp-per-step", type=int, default=4)
     ap.add_argument("--grid", type=int, default=2236, help="heightfield cells per side (2236 -> ~10M triangles)")
-    ap.add_argument("--cpu-stride", type=int, default=16, help="pixel stride of the bounded CPU sample")
+    ap.add_argument("--cpu-stride", type=int, default=1, help="pixel stride of the bounded CPU sample (1 = whole frame)")
+    ap.add_argument("--cpu-spp", type=int, default=1, help="samples per pixel of one CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raycast", action="store_true", help="skip the config-2 Mrays/s side measurement")
     return ap.parse_args()
@@ -144,10 +145,10 @@ def run_cpu_arm(data, camera, args, steps, warmup, which="auto"):
     t0 = time.perf_counter()
     h = lib.scene_create(data)
     build_s = time.perf_counter() - t0
-    rs = capi.render_settings(WIDTH, HEIGHT, 1, MAX_DEPTH, RR_START, layers=1, seed=1, pixel_stride=args.cpu_stride)
+    rs = capi.render_settings(WIDTH, HEIGHT, args.cpu_spp, MAX_DEPTH, RR_START, layers=1, seed=1, pixel_stride=args.cpu_stride)
     times, paths, rays = [], 0, 0
     for i in range(warmup + steps):
-        rs.firstSample = i
+        rs.firstSample = i * args.cpu_spp
         t0 = time.perf_counter()
         _, st = lib.render(h, camera, rs, nthreads=threads)
         dt = time.perf_counter() - t0
@@ -158,7 +159,7 @@ def run_cpu_arm(data, camera, args, steps, warmup, which="auto"):
     lib.scene_destroy(h)
     total = sum(times)
     return {"value": paths / total, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"every {args.cpu_stride}th pixel of the 1080p frame, 1 spp per step, {steps} steps "
+            "sample": f"pixel stride {args.cpu_stride} over the 1080p frame, {args.cpu_spp} spp per step, {steps} steps "
                       f"({paths} paths, {total:.1f} s; CPU BVH build {build_s:.1f} s excluded)",
             "mrays_per_s": rays / total / 1e6, "ms_per_step": 1e3 * total / max(1, len(times)), "paths_per_step": paths // max(1, len(times)),
             "ray_cast": "oracle scalar SAH-BVH2 (Embree 3.2.0 absent: headers only in the reference tree)"}
@@ -337,7 +338,7 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         scene.close()
-        r = run_cpu_arm(data, camera, args, steps=2, warmup=0)
+        r = run_cpu_arm(data, camera, args, steps=6, warmup=0)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ray_cast", "mrays_per_s")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,

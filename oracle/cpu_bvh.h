@@ -202,6 +202,10 @@ public:
         out.t = tfar;
         out.u = out.v = 0;
         if (nodes.empty()) return false;
+        // non-finite rays are misses (Embree behaviour); without this they would pass every slab test
+        for (int k = 0; k < 3; ++k)
+            if (!std::isfinite(of[k]) || !std::isfinite(df[k])) return false;
+        if (!(tnear <= tfar)) return false;
         Real o[3] = {(Real)of[0], (Real)of[1], (Real)of[2]}, d[3] = {(Real)df[0], (Real)df[1], (Real)df[2]};
         Real inv[3];
         for (int k = 0; k < 3; ++k) inv[k] = (Real)1 / d[k];  // +-inf on zero components is fine for the slab test

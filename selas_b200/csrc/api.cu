@@ -219,6 +219,7 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
         if (md.tangents) SELAS_TRY(sceneUpload(scene, &g.tangents, md.tangents, 4 * (size_t)md.vertexCount));
         if (md.uvs) SELAS_TRY(sceneUpload(scene, &g.uvs, md.uvs, 2 * (size_t)md.vertexCount));
         g.ptex = md.ptex ? ptexDevicePointer((SelasPtex*)md.ptex) : nullptr;
+        if (g.ptex) scene->usesPtex = true;
         g.faceCount = md.faceCount;
         g.indicesPerFace = md.indicesPerFace;
         g.materialIndex = md.materialIndex;

@@ -68,6 +68,7 @@ struct SelasScene {
     selas::SceneGpu gpu{};
     std::vector<void*> allocations;  // everything cudaMalloc'ed for this scene
     SelasBvhStats stats{};
+    bool usesPtex = false;  // any mesh carries a Ptex texture: selects the shade kernel built with the lookup
     // wavefront scratch, grown on demand
     void* wf = nullptr;
 };

@@ -1,10 +1,649 @@
-// ptex_eval.cuh -- device-side Ptex b-spline lookup (see ptex.cu for the loader and the data layout).
+// ptex_eval.cuh -- device-side Ptex lookup: PtexFilter::eval with the f_bspline filter, exactly as the reference's
+// shading calls it (SurfaceParameters.cpp:203: eval(rgb, 0, 3, primId, u, v, 0, 0, 0, 0), width 1, blur 0).
+//
+// Restates, for the GPU (paths relative to Middleware/ptex/Include):
+//   PtexSeparableFilter::eval / splitAndApply / applyAcrossEdge / applyToCorner / applyToCornerFace / apply
+//                                                     PtexSeparableFilter.cpp:47-132, :135-213, :215-255, :257-330, :333-345, :348-401
+//   PtexWidth4Filter::buildKernelAxis                 PtexFilters.cpp:141-248 (lerp = false, as PtexFilter::Options defaults)
+//   PtexBicubicFilter coefficients + kernelFn         PtexFilters.cpp:256-284 (sharpness 0 => B = 1, the cubic B-spline)
+//   PtexSeparableKernel (split/merge/rotate/downres/upres/adjust*/makeSymmetric/apply)   PtexSeparableKernel.h:55-457,
+//                                                     PtexSeparableKernel.cpp:45-75 (row-wise accumulate, then rows * kv)
+//   PtexReader::getData(faceid, res) selection rules  PtexReader.cpp:785-830 (constant face or res 0 => per-face constant;
+//                                                     otherwise native or reduced data, here pre-built by the loader in ptex.cu)
+//
+// Data layout in HBM (built by ptex.cu):
+//   faces[f]    32 B = { ulog2 | vlog2<<8 | adjedges<<16 | flags<<24, adjfaces[4], dataOffset16, redStart, redCount }
+//   reds[i]      8 B = { ulog2 | vlog2<<8, dataOffset16 }   reduced-resolution copies a neighbour's kernel can ask for
+//   texels      native data type (u8 / u16 / half / float), nchan interleaved, row-major u fastest, every block 16-B aligned
+//   constData   one pixel per face (the file's constdata block)
+// Algorithmic bytes per lookup: 32 B face record + 16 texels x pixel size (x2 when the 4x4 straddles an edge).
+//
+// The one structural change against the library: the recursion splitAndApply -> applyAcrossEdge -> splitAndApply (taken
+// only when a kernel crosses onto a subface) is unrolled into a small work list, so partial sums may be added in a
+// different order (fp32 reassociation, far inside the 1e-4 parity bound).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "vec.cuh"
 
 namespace selas {
 
-struct PtexGpu;
-SELAS_D void ptexEvalBspline(const PtexGpu* tex, int faceid, float u, float v, float* rgb) { rgb[0] = rgb[1] = rgb[2] = 0.f; }
+struct PtexRed {
+    uint32_t res;       // ulog2 | vlog2 << 8
+    uint32_t offset16;  // texel block offset in 16-byte units
+};
+
+struct PtexGpu {
+    const uint4* faces;  // 2 per face
+    const PtexRed* reds;
+    const uint8_t* texels;
+    const uint8_t* constData;
+    int numFaces;
+    int nchan;       // channels in the texture
+    int dataType;    // 0 u8, 1 u16, 2 half, 3 float
+    int pixelSize;   // bytes
+    int uMode, vMode;  // BorderMode: 0 clamp, 1 black, 2 periodic
+    int edgeFilterMode;
+    int pad;
+};
+
+enum { kPtexFlagConstant = 1, kPtexFlagNbConstant = 4, kPtexFlagSubface = 8 };
+enum { kEdgeBottom = 0, kEdgeRight = 1, kEdgeTop = 2, kEdgeLeft = 3 };
+
+struct PtexFace {
+    int ulog2, vlog2;
+    uint32_t adjedges, flags;
+    int adjfaces[4];
+    uint32_t dataOffset16, redStart, redCount;
+    SELAS_D int adjface(int e) const { return adjfaces[e]; }
+    SELAS_D int adjedge(int e) const { return (int)((adjedges >> (2 * e)) & 3u); }
+    SELAS_D bool isSubface() const { return (flags & kPtexFlagSubface) != 0; }
+    SELAS_D bool isConstant() const { return (flags & kPtexFlagConstant) != 0; }
+};
+
+SELAS_D PtexFace ptexLoadFace(const PtexGpu& tx, int faceid) {
+    uint4 a = __ldg(tx.faces + 2 * (size_t)faceid), b = __ldg(tx.faces + 2 * (size_t)faceid + 1);
+    PtexFace f;
+    f.ulog2 = (int)(int8_t)(a.x & 0xff);
+    f.vlog2 = (int)(int8_t)((a.x >> 8) & 0xff);
+    f.adjedges = (a.x >> 16) & 0xff;
+    f.flags = (a.x >> 24) & 0xff;
+    f.adjfaces[0] = (int)a.y; f.adjfaces[1] = (int)a.z; f.adjfaces[2] = (int)a.w; f.adjfaces[3] = (int)b.x;
+    f.dataOffset16 = b.y; f.redStart = b.z; f.redCount = b.w;
+    return f;
+}
+
+#define PTEX_KMAX 10
+
+// PtexSeparableKernel.  ku/kv are offsets into the fixed buffers instead of moving pointers.
+struct PtexKernel {
+    int ulog2, vlog2;
+    int u, v, uw, vw;
+    int ku0, kv0;  // start of the live weights inside kub / kvb
+    int rot;
+    float kub[PTEX_KMAX], kvb[PTEX_KMAX];
+
+    SELAS_D int resu() const { return 1 << ulog2; }
+    SELAS_D int resv() const { return 1 << vlog2; }
+    SELAS_D float& ku(int i) { return kub[ku0 + i]; }
+    SELAS_D float& kv(int i) { return kvb[kv0 + i]; }
+    SELAS_D float kuc(int i) const { return kub[ku0 + i]; }
+    SELAS_D float kvc(int i) const { return kvb[kv0 + i]; }
+
+    SELAS_D void set(int ul, int vl, int u_, int v_, int uw_, int vw_, const float* kuSrc, const float* kvSrc, int rot_) {
+        ulog2 = ul; vlog2 = vl; u = u_; v = v_; uw = uw_; vw = vw_;
+        for (int i = 0; i < uw_; ++i) kub[i] = kuSrc[i];
+        for (int i = 0; i < vw_; ++i) kvb[i] = kvSrc[i];
+        ku0 = 0; kv0 = 0; rot = rot_;
+    }
+    SELAS_D void copyFrom(const PtexKernel& k) { set(k.ulog2, k.vlog2, k.u, k.v, k.uw, k.vw, k.kub + k.ku0, k.kvb + k.kv0, k.rot); }
+
+    SELAS_D static float accumulate(const float* p, int n) {
+        float r = 0;
+        for (int i = 0; i < n; ++i) r += p[i];
+        return r;
+    }
+    SELAS_D float weight() const { return accumulate(kub + ku0, uw) * accumulate(kvb + kv0, vw); }
+
+    SELAS_D void stripZeros() {  // :97-104
+        while (ku(0) == 0) { ku0++; u++; uw--; }
+        while (ku(uw - 1) == 0) { uw--; }
+        while (kv(0) == 0) { kv0++; v++; vw--; }
+        while (kv(vw - 1) == 0) { vw--; }
+    }
+    // merge*: fold the part hanging over a border without neighbour back onto the edge texel (:111-147)
+    SELAS_D void mergeL(int mode) {
+        int w = -u;
+        if (mode != 1) ku(w) += accumulate(kub + ku0, w);
+        ku0 += w; uw -= w; u = 0;
+    }
+    SELAS_D void mergeR(int mode) {
+        int w = uw + u - resu();
+        int kp = uw - w;
+        if (mode != 1) ku(kp - 1) += accumulate(kub + ku0 + kp, w);
+        uw -= w;
+    }
+    SELAS_D void mergeB(int mode) {
+        int w = -v;
+        if (mode != 1) kv(w) += accumulate(kvb + kv0, w);
+        kv0 += w; vw -= w; v = 0;
+    }
+    SELAS_D void mergeT(int mode) {
+        int w = vw + v - resv();
+        int kp = vw - w;
+        if (mode != 1) kv(kp - 1) += accumulate(kvb + kv0 + kp, w);
+        vw -= w;
+    }
+    // split*: cut the overhanging piece off into k (:149-237)
+    SELAS_D void splitL(PtexKernel& k) {
+        int w = -u;
+        if (w < uw) {
+            k.set(ulog2, vlog2, resu() - w, v, w, vw, kub + ku0, kvb + kv0, 0);
+            u = 0; uw -= w; ku0 += w;
+        } else {
+            k.copyFrom(*this);
+            k.u += resu();
+            u = 0; uw = 0;
+        }
+    }
+    SELAS_D void splitR(PtexKernel& k) {
+        int w = u + uw - resu();
+        if (w < uw) {
+            k.set(ulog2, vlog2, 0, v, w, vw, kub + ku0 + uw - w, kvb + kv0, 0);
+            uw -= w;
+        } else {
+            k.copyFrom(*this);
+            k.u -= resu();
+            u = 0; uw = 0;
+        }
+    }
+    SELAS_D void splitB(PtexKernel& k) {
+        int w = -v;
+        if (w < vw) {
+            k.set(ulog2, vlog2, u, resv() - w, uw, w, kub + ku0, kvb + kv0, 0);
+            v = 0; vw -= w; kv0 += w;
+        } else {
+            k.copyFrom(*this);
+            k.v += resv();
+            v = 0; vw = 0;
+        }
+    }
+    SELAS_D void splitT(PtexKernel& k) {
+        int w = v + vw - resv();
+        if (w < vw) {
+            k.set(ulog2, vlog2, u, 0, uw, w, kub + ku0, kvb + kv0 + vw - w, 0);
+            vw -= w;
+        } else {
+            k.copyFrom(*this);
+            k.v -= resv();
+            v = 0; vw = 0;
+        }
+    }
+    SELAS_D void flipU() {
+        u = resu() - u - uw;
+        for (int i = 0; i < uw / 2; ++i) { float t = ku(i); ku(i) = ku(uw - 1 - i); ku(uw - 1 - i) = t; }
+    }
+    SELAS_D void flipV() {
+        v = resv() - v - vw;
+        for (int i = 0; i < vw / 2; ++i) { float t = kv(i); kv(i) = kv(vw - 1 - i); kv(vw - 1 - i) = t; }
+    }
+    SELAS_D void swapUV() {
+        const int oldUw = uw, oldVw = vw;
+        float tmpU[PTEX_KMAX], tmpV[PTEX_KMAX];
+        for (int i = 0; i < oldUw; ++i) tmpU[i] = kub[ku0 + i];
+        for (int i = 0; i < oldVw; ++i) tmpV[i] = kvb[kv0 + i];
+        for (int i = 0; i < oldVw; ++i) kub[i] = tmpV[i];
+        for (int i = 0; i < oldUw; ++i) kvb[i] = tmpU[i];
+        ku0 = 0; kv0 = 0;
+        int t = ulog2; ulog2 = vlog2; vlog2 = t;
+        t = u; u = v; v = t;
+        uw = oldVw; vw = oldUw;
+    }
+    SELAS_D void rotate(int r) {  // :260-270, 'r' steps counter-clockwise
+        switch (r & 3) {
+            default: return;
+            case 1: flipU(); swapUV(); break;
+            case 2: flipU(); flipV(); break;
+            case 3: flipV(); swapUV(); break;
+        }
+        rot = (rot + r) & 3;
+    }
+    SELAS_D void compactU() {
+        if (ku0) { for (int i = 0; i < uw; ++i) kub[i] = kub[ku0 + i]; ku0 = 0; }
+    }
+    SELAS_D void compactV() {
+        if (kv0) { for (int i = 0; i < vw; ++i) kvb[i] = kvb[kv0 + i]; kv0 = 0; }
+    }
+    SELAS_D void downresU() {  // :313-339
+        int src = 0, dst = 0;
+        if (u & 1) { dst++; src++; uw--; }
+        for (int i = uw / 2; i > 0; i--) { ku(dst++) = ku(src) + ku(src + 1); src += 2; }
+        if (uw & 1) { ku(dst++) = ku(src++); }
+        u /= 2;
+        uw = dst;
+        ulog2--;
+    }
+    SELAS_D void downresV() {
+        int src = 0, dst = 0;
+        if (v & 1) { dst++; src++; vw--; }
+        for (int i = vw / 2; i > 0; i--) { kv(dst++) = kv(src) + kv(src + 1); src += 2; }
+        if (vw & 1) { kv(dst++) = kv(src++); }
+        v /= 2;
+        vw = dst;
+        vlog2--;
+    }
+    SELAS_D void upresU() {  // :369-379 (only reached with uw <= 5: the result fits the buffer)
+        compactU();
+        for (int i = uw - 1; i >= 0; --i) { float h = kub[i] / 2; kub[2 * i] = h; kub[2 * i + 1] = h; }
+        uw *= 2; u *= 2; ulog2++;
+    }
+    SELAS_D void upresV() {
+        compactV();
+        for (int i = vw - 1; i >= 0; --i) { float h = kvb[i] / 2; kvb[2 * i] = h; kvb[2 * i + 1] = h; }
+        vw *= 2; v *= 2; vlog2++;
+    }
+    SELAS_D bool adjustMainToSubface(int eid) {  // :272-303
+        if (ulog2 == 0) upresU();
+        if (vlog2 == 0) upresV();
+        if (ulog2 > 0) ulog2--;
+        if (vlog2 > 0) vlog2--;
+        bool primary = false;
+        int ru = resu(), rv = resv();
+        switch (eid & 3) {
+            case kEdgeBottom: primary = (u < ru); v -= rv; if (!primary) u -= ru; break;
+            case kEdgeRight: primary = (v < rv); if (!primary) v -= rv; break;
+            case kEdgeTop: primary = (u >= ru); if (primary) u -= ru; break;
+            case kEdgeLeft: primary = (v >= rv); u -= ru; if (primary) v -= rv; break;
+        }
+        return primary;
+    }
+    SELAS_D void adjustSubfaceToMain(int eid) {  // :305-313
+        switch (eid & 3) {
+            case kEdgeBottom: v += resv(); break;
+            case kEdgeRight: break;
+            case kEdgeTop: u += resu(); break;
+            case kEdgeLeft: u += resu(); v += resv(); break;
+        }
+        ulog2++; vlog2++;
+    }
+    SELAS_D float makeSymmetric(float initialWeight) {  // :397-455
+        if (ulog2 > vlog2) { do { downresU(); } while (ulog2 > vlog2); }
+        else if (vlog2 > ulog2) { do { downresV(); } while (vlog2 > ulog2); }
+        uw = vw = (uw < vw ? uw : vw);
+        float newWeight = 0;
+        for (int i = 0; i < uw; i++) {
+            float sum = ku(i) + kv(i);
+            ku(i) = sum; kv(i) = sum;
+            newWeight += sum;
+        }
+        newWeight *= newWeight;
+        float scale = newWeight == 0 ? 1.f : initialWeight / newWeight;
+        if (scale >= 1) {
+        } else if (scale < -1) {
+            for (int i = 0; i < uw; i++) ku(i) *= -1;
+            newWeight = -newWeight;
+        } else {
+            for (int i = 0; i < uw; i++) ku(i) *= scale;
+            newWeight = initialWeight;
+        }
+        return newWeight;
+    }
+};
+
+SELAS_D float ptexTexel(const uint8_t* base, int dataType, size_t idx) {
+    switch (dataType) {
+        case 0: return (float)__ldg(base + idx);
+        case 1: return (float)__ldg(reinterpret_cast<const uint16_t*>(base) + idx);
+        case 2: return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const uint16_t*>(base) + idx)));
+        default: return __ldg(reinterpret_cast<const float*>(base) + idx);
+    }
+}
+
+struct PtexEvalState {
+    float result[3];
+    float weight;
+    int nchan;  // channels evaluated (<= 3)
+};
+
+// PtexSeparableKernel::applyConst (PtexUtils.cpp:643-651): result += pixel * weight
+SELAS_D void ptexApplyConst(const PtexGpu& tx, PtexEvalState& st, const uint8_t* pixel, float w) {
+    for (int c = 0; c < st.nchan; ++c) st.result[c] += ptexTexel(pixel, tx.dataType, c) * w;
+}
+
+// PtexSeparableFilter::apply, :348-401
+SELAS_D void ptexApply(const PtexGpu& tx, PtexEvalState& st, PtexKernel& k, int faceid, const PtexFace& f) {
+    if (k.uw <= 0 || k.vw <= 0) return;
+    while (k.ulog2 > f.ulog2) k.downresU();
+    while (k.vlog2 > f.vlog2) k.downresV();
+    // PtexReader::getData(faceid, k.res), PtexReader.cpp:785-830
+    const uint8_t* constPixel = tx.constData + (size_t)faceid * tx.pixelSize;
+    if (f.isConstant() || (k.ulog2 == 0 && k.vlog2 == 0)) {
+        ptexApplyConst(tx, st, constPixel, k.weight());
+        return;
+    }
+    const uint8_t* data = nullptr;
+    if (k.ulog2 == f.ulog2 && k.vlog2 == f.vlog2) {
+        data = tx.texels + (size_t)f.dataOffset16 * 16;
+    } else {
+        uint32_t want = (uint32_t)(k.ulog2 & 0xff) | ((uint32_t)(k.vlog2 & 0xff) << 8);
+        for (uint32_t i = 0; i < f.redCount; ++i) {
+            PtexRed r = tx.reds[f.redStart + i];
+            if (r.res == want) { data = tx.texels + (size_t)r.offset16 * 16; break; }
+        }
+        if (!data) return;  // a reduction the loader did not foresee: contributes nothing (PtexReader errorData is zero too)
+    }
+    // PtexSeparableKernel.cpp:45-75 Apply<T,nChan> / ApplyS: per row sum_u texel*ku, then result += row * kv
+    const int resu = k.resu();
+    const int nt = tx.nchan;
+    for (int y = 0; y < k.vw; ++y) {
+        float row[3] = {0.f, 0.f, 0.f};
+        size_t rowBase = ((size_t)(k.v + y) * resu + k.u) * nt;
+        for (int c = 0; c < st.nchan; ++c) row[c] = ptexTexel(data, tx.dataType, rowBase + c) * k.kuc(0);
+        for (int x = 1; x < k.uw; ++x) {
+            float w = k.kuc(x);
+            for (int c = 0; c < st.nchan; ++c) row[c] += ptexTexel(data, tx.dataType, rowBase + (size_t)x * nt + c) * w;
+        }
+        float wv = k.kvc(y);
+        for (int c = 0; c < st.nchan; ++c) st.result[c] += row[c] * wv;
+    }
+}
+
+// PtexBicubicFilter::kernelFn with B = 1 (PtexFilters.cpp:256-284)
+SELAS_D float ptexBsplineFn(float x) {
+    const float B = 1.0f;
+    const float c0 = 1.5f - B, c1 = 1.5f * B - 2.5f, c2 = 1.0f - float(1.0 / 3.0) * B;
+    const float c3 = float(1.0 / 3.0) * B - 0.5f, c4 = 2.5f - 1.5f * B, c5 = 2.0f * B - 4.0f, c6 = 2.0f - float(2.0 / 3.0) * B;
+    x = fabsf(x);
+    if (x < 1.0f) return (c0 * x + c1) * x * x + c2;
+    else if (x < 2.0f) return ((c3 * x + c4) * x + c5) * x + c6;
+    return 0.0f;
+}
+SELAS_D float ptexBlur(float x) {  // PtexFilters.cpp:133-139
+    x = fabsf(x);
+    return x < 1.0f ? (2.0f * x - 3.0f) * x * x + 1.0f : 0.0f;
+}
+
+// PtexWidth4Filter::buildKernelAxis with options.lerp == false (PtexFilters.cpp:141-248)
+SELAS_D void ptexBuildKernelAxis(int& kReslog2, int& kU, int& kUw, float* ku, float u, float uw, int fReslog2) {
+    float minw = __uint_as_float((uint32_t)(127 - fReslog2) << 23);  // reciprocalPow2
+    uw = uw > minw ? uw : minw;                                       // PtexUtils::max(uw, 1/res)
+    kReslog2 = 127 - (int)((__float_as_uint(uw) >> 23) & 0xff);      // calcResFromWidth
+    int resu = 1 << kReslog2;
+    if (uw >= .25f) {
+        if (uw < .5f) {
+            kReslog2 = 2;
+            float upix = u * 4.0f - 0.5f;
+            int u1 = (int)ceilf(upix - 2), u2 = (int)ceilf(upix + 2);
+            u1 = u1 & ~1;
+            u2 = (u2 + 1) & ~1;
+            kU = u1;
+            kUw = u2 - u1;
+            float x1 = (float)u1 - upix;
+            for (int i = 0; i < kUw; i += 2) {
+                float xa = x1 + (float)i, xb = xa + 1.0f;
+                ku[i] = ptexBsplineFn(xa) * 1.0f;  // lerp1 = 1, lerp2 = 0: "ka*lerp1 + kc*lerp2"
+                ku[i + 1] = ptexBsplineFn(xb) * 1.0f;
+            }
+            return;
+        } else if (uw < 1) {
+            kReslog2 = 1;
+            float upix = u * 2.0f - 0.5f;
+            kU = (int)floorf(u - .5f) * 2;
+            kUw = 4;
+            float x1 = (float)kU - upix;
+            float s = 1.0f / (uw * 1.5f + .5f);
+            for (int i = 0; i < kUw; i += 2) {
+                float xa = x1 + (float)i, xb = xa + 1.0f;
+                ku[i] = ptexBlur(xa * s);
+                ku[i + 1] = ptexBlur(xb * s);
+            }
+            return;
+        } else {
+            kReslog2 = 0;
+            float upix = u - .5f;
+            kUw = 2;
+            float ui = floorf(upix);
+            kU = (int)ui;
+            ku[0] = ptexBlur(upix - ui);
+            ku[1] = 1 - ku[0];
+            return;
+        }
+    }
+    float upix = u * (float)resu - 0.5f;
+    float uwpix = uw * (float)resu;
+    float dupix = 2.0f * uwpix;
+    int u1 = (int)ceilf(upix - dupix), u2 = (int)ceilf(upix + dupix);
+    kU = u1;
+    kUw = u2 - u1;
+    float x1 = ((float)u1 - upix) / uwpix, step = 1.0f / uwpix;
+    for (int i = 0; i < kUw; i++) ku[i] = ptexBsplineFn(x1 + (float)i * step);
+}
+
+struct PtexWork {
+    PtexKernel k;
+    int faceid;
+};
+#define PTEX_WORK_MAX 6
+
+struct PtexWorkList {
+    PtexWork items[PTEX_WORK_MAX];
+    int count;
+    SELAS_D void push(const PtexKernel& k, int faceid) {
+        if (count < PTEX_WORK_MAX) {
+            items[count].k.copyFrom(k);
+            items[count].faceid = faceid;
+            ++count;
+        }
+    }
+};
+
+// PtexSeparableFilter::applyToCornerFace, :333-345
+SELAS_D void ptexApplyToCornerFace(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, const PtexFace& f, int eid,
+                                   int cfid, const PtexFace& cf, int ceid) {
+    bool fIsSubface = f.isSubface(), cfIsSubface = cf.isSubface();
+    if (fIsSubface != cfIsSubface) {
+        if (cfIsSubface) k.adjustMainToSubface(eid + 3);
+        else k.adjustSubfaceToMain(eid + 3);
+    }
+    k.rotate(eid - ceid + 2);
+    if (cfIsSubface) wl.push(k, cfid);
+    else ptexApply(tx, st, k, cfid, cf);
+}
+
+// PtexSeparableFilter::applyToCorner, :257-330
+SELAS_D void ptexApplyToCorner(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f,
+                               int eid) {
+    int afid = faceid, aeid = eid;
+    PtexFace af = f;
+    bool prevIsSubface = af.isSubface();
+    const int MaxValence = 10;
+    int cfaceId[MaxValence];
+    int cedgeId[MaxValence];
+    int numCorners = 0;
+    for (int i = 0; i < MaxValence; i++) {
+        int prevFace = afid;
+        int nextFace = af.adjface(aeid);
+        aeid = (af.adjedge(aeid) + 1) % 4;
+        afid = nextFace;
+        if (afid < 0 || (afid == faceid && aeid == eid)) {
+            numCorners = i - 2;
+            break;
+        }
+        af = ptexLoadFace(tx, afid);
+        cfaceId[i] = afid;
+        cedgeId[i] = aeid;
+        bool isSubface = af.isSubface();
+        if (prevIsSubface && !isSubface && af.adjface((aeid + 3) % 4) == prevFace) {
+            // subface "tee": the corner is the middle of a main-face edge
+            bool primary = (i == 1);
+            k.adjustSubfaceToMain(eid + primary * 2);
+            k.rotate(eid - aeid + 3 - primary);
+            wl.push(k, afid);
+            return;
+        }
+        prevIsSubface = isSubface;
+    }
+    if (numCorners == 1) {
+        PtexFace cf = ptexLoadFace(tx, cfaceId[1]);
+        ptexApplyToCornerFace(tx, st, wl, k, f, eid, cfaceId[1], cf, cedgeId[1]);
+    } else if (numCorners > 1) {
+        // valence 5+: make the kernel symmetric and apply it equally to each corner face
+        k.rotate(eid + 2);
+        float initialWeight = k.weight();
+        float newWeight = k.makeSymmetric(initialWeight);
+        for (int i = 1; i <= numCorners; i++) {
+            PtexKernel kc;
+            kc.copyFrom(k);
+            PtexFace cf = ptexLoadFace(tx, cfaceId[i]);
+            ptexApplyToCornerFace(tx, st, wl, kc, f, 2, cfaceId[i], cf, cedgeId[i]);
+        }
+        st.weight += newWeight * (float)numCorners - initialWeight;
+    } else {
+        // valence 2 or 3: ignore the corner face, just take its weight out
+        st.weight -= k.weight();
+    }
+}
+
+// PtexSeparableFilter::applyAcrossEdge, :215-255
+SELAS_D void ptexApplyAcrossEdge(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f,
+                                 int eid) {
+    int afid = f.adjface(eid), aeid = f.adjedge(eid);
+    PtexFace af = ptexLoadFace(tx, afid);
+    int rot = eid - aeid + 2;
+    bool fIsSubface = f.isSubface(), afIsSubface = af.isSubface();
+    if (fIsSubface != afIsSubface) {
+        if (afIsSubface) {
+            bool primary = k.adjustMainToSubface(eid);
+            if (!primary) {
+                int neid = (aeid + 3) % 4;
+                int nfid = af.adjface(neid);
+                aeid = af.adjedge(neid);
+                afid = nfid;
+                af = ptexLoadFace(tx, afid);
+                rot += neid - aeid + 2;
+            }
+        } else {
+            bool primary = (af.adjface(aeid) == faceid);
+            k.adjustSubfaceToMain(eid - primary);
+        }
+    }
+    k.rotate(rot);
+    if (afIsSubface) wl.push(k, afid);
+    else ptexApply(tx, st, k, afid, af);
+}
+
+// PtexSeparableFilter::splitAndApply, :135-213 (noedgeblend = false)
+SELAS_D void ptexSplitAndApply(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f) {
+    bool splitR = (k.u + k.uw > k.resu()), splitL = (k.u < 0);
+    bool splitT = (k.v + k.vw > k.resv()), splitB = (k.v < 0);
+    if (splitR || splitL || splitT || splitB) {
+        PtexKernel ka, kc;
+        if (splitR) {
+            if (f.adjface(kEdgeRight) >= 0) {
+                k.splitR(ka);
+                if (splitT) {
+                    if (f.adjface(kEdgeTop) >= 0) { ka.splitT(kc); ptexApplyToCorner(tx, st, wl, kc, faceid, f, kEdgeTop); }
+                    else ka.mergeT(tx.vMode);
+                }
+                if (splitB) {
+                    if (f.adjface(kEdgeBottom) >= 0) { ka.splitB(kc); ptexApplyToCorner(tx, st, wl, kc, faceid, f, kEdgeRight); }
+                    else ka.mergeB(tx.vMode);
+                }
+                ptexApplyAcrossEdge(tx, st, wl, ka, faceid, f, kEdgeRight);
+            } else k.mergeR(tx.uMode);
+        }
+        if (splitL) {
+            if (f.adjface(kEdgeLeft) >= 0) {
+                k.splitL(ka);
+                if (splitT) {
+                    if (f.adjface(kEdgeTop) >= 0) { ka.splitT(kc); ptexApplyToCorner(tx, st, wl, kc, faceid, f, kEdgeLeft); }
+                    else ka.mergeT(tx.vMode);
+                }
+                if (splitB) {
+                    if (f.adjface(kEdgeBottom) >= 0) { ka.splitB(kc); ptexApplyToCorner(tx, st, wl, kc, faceid, f, kEdgeBottom); }
+                    else ka.mergeB(tx.vMode);
+                }
+                ptexApplyAcrossEdge(tx, st, wl, ka, faceid, f, kEdgeLeft);
+            } else k.mergeL(tx.uMode);
+        }
+        if (splitT) {
+            if (f.adjface(kEdgeTop) >= 0) { k.splitT(ka); ptexApplyAcrossEdge(tx, st, wl, ka, faceid, f, kEdgeTop); }
+            else k.mergeT(tx.vMode);
+        }
+        if (splitB) {
+            if (f.adjface(kEdgeBottom) >= 0) { k.splitB(ka); ptexApplyAcrossEdge(tx, st, wl, ka, faceid, f, kEdgeBottom); }
+            else k.mergeB(tx.vMode);
+        }
+    }
+    ptexApply(tx, st, k, faceid, f);
+}
+
+// PtexSeparableFilter::eval, :47-132, with firstChan 0, nChannels 3, all widths 0, width 1, blur 0.
+// Channels the texture does not have are returned as 0 (the reference leaves them uninitialised).
+static __device__ __noinline__ void ptexEvalBspline(const PtexGpu* texPtr, int faceid, float u, float v, float* rgb) {
+    const PtexGpu tx = *texPtr;
+    rgb[0] = rgb[1] = rgb[2] = 0.f;
+    if (faceid < 0 || faceid >= tx.numFaces) return;
+    PtexEvalState st;
+    st.nchan = tx.nchan < 3 ? tx.nchan : 3;
+    st.result[0] = st.result[1] = st.result[2] = 0.f;
+    const float oneValueInv = tx.dataType == 0 ? 1.f / 255.f : (tx.dataType == 1 ? 1.f / 65535.f : 1.f);
+    const float oneValue = tx.dataType == 0 ? 255.f : (tx.dataType == 1 ? 65535.f : 1.f);
+    PtexFace f = ptexLoadFace(tx, faceid);
+    if (f.flags & kPtexFlagNbConstant) {  // :62-69, ConvertToFloat of the face's constant pixel
+        const uint8_t* px = tx.constData + (size_t)faceid * tx.pixelSize;
+        for (int c = 0; c < st.nchan; ++c) {
+            float t = ptexTexel(px, tx.dataType, c);
+            rgb[c] = tx.dataType == 3 ? t : t * oneValueInv;
+        }
+        return;
+    }
+    float uw = 0.f, vw = 0.f;
+    bool black = false;
+    switch (tx.uMode) {
+        case 0: u = clampf_(u, 0.0f, 1.0f); break;
+        case 2: u = u - floorf(u); break;
+        case 1: if (u <= -1.0f || u >= 2.0f) black = true; break;
+    }
+    switch (tx.vMode) {
+        case 0: v = clampf_(v, 0.0f, 1.0f); break;
+        case 2: v = v - floorf(v); break;
+        case 1: if (v <= -1.0f || v >= 2.0f) black = true; break;
+    }
+    if (black) return;
+
+    PtexWorkList wl;
+    wl.count = 0;
+    PtexKernel k;
+    k.ku0 = k.kv0 = 0;
+    k.rot = 0;
+    if (f.isSubface()) {
+        uw = uw * 1.0f + 0.0f * 2.0f;
+        vw = vw * 1.0f + 0.0f * 2.0f;
+        ptexBuildKernelAxis(k.ulog2, k.u, k.uw, k.kub, u * .5f, uw * .5f, f.ulog2 + 1);
+        ptexBuildKernelAxis(k.vlog2, k.v, k.vw, k.kvb, v * .5f, vw * .5f, f.vlog2 + 1);
+        if (k.ulog2 == 0) k.upresU();
+        if (k.vlog2 == 0) k.upresV();
+        k.ulog2--;
+        k.vlog2--;
+    } else {
+        ptexBuildKernelAxis(k.ulog2, k.u, k.uw, k.kub, u, uw, f.ulog2);
+        ptexBuildKernelAxis(k.vlog2, k.v, k.vw, k.kvb, v, vw, f.vlog2);
+    }
+    k.stripZeros();
+    st.weight = k.weight();
+    ptexSplitAndApply(tx, st, wl, k, faceid, f);
+    // kernels that crossed onto a subface are re-split there (the library recurses; see the header comment)
+    for (int guard = 0; wl.count > 0 && guard < 32; ++guard) {
+        --wl.count;
+        PtexKernel kk;
+        kk.copyFrom(wl.items[wl.count].k);
+        int fid = wl.items[wl.count].faceid;
+        PtexFace ff = ptexLoadFace(tx, fid);
+        ptexSplitAndApply(tx, st, wl, kk, fid, ff);
+    }
+    float scale = 1.0f / (st.weight * oneValue);
+    for (int c = 0; c < st.nchan; ++c) rgb[c] = st.result[c] * scale;
+}
 
 }  // namespace selas

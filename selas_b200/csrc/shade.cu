@@ -104,6 +104,7 @@ __global__ void cameraRaysKernel(SelasCamera cam, size_t n, const float* __restr
     o[1] = make_float4(d.x, d.y, d.z, SELAS_FLOAT_MAX);
 }
 
+template <bool PTEX>
 __global__ void surfaceParamsKernel(SceneGpu sc, size_t n, const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                     SelasSurface* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,7 +115,7 @@ __global__ void surfaceParamsKernel(SceneGpu sc, size_t n, const SelasRay* __res
     if (h.geomID != SELAS_INVALID_ID) {
         SelasRay r = rays[i];
         Surface s;
-        surfaceFromHit(sc, v3(r.ox, r.oy, r.oz), v3(r.dx, r.dy, r.dz), h.t, h.u, h.v, h.primID, h.geomID, h.instID0, s);
+        surfaceFromHit<PTEX>(sc, v3(r.ox, r.oy, r.oz), v3(r.dx, r.dy, r.dz), h.t, h.u, h.v, h.primID, h.geomID, h.instID0, s);
         storeSurface(s, v3(-r.dx, -r.dy, -r.dz), o);
     }
     out[i] = o;
@@ -160,7 +161,10 @@ int launchCameraRays(SelasContext* ctx, const SelasCamera& cam, size_t n, const 
 }
 int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, const SelasHit* d_hits, SelasSurface* d_out) {
     if (!n) return SELAS_OK;
-    surfaceParamsKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_out);
+    if (scene->usesPtex)
+        surfaceParamsKernel<true><<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_out);
+    else
+        surfaceParamsKernel<false><<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_out);
     SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -263,6 +267,7 @@ struct ShadeParams {
     uint32_t maxPathLength, rrStartBounce, layerCount, pixels;
 };
 
+template <bool PTEX>
 __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ nPtr, uint32_t nMax,
                                                    const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                                    const float4* __restrict__ thrPix, const uint2* __restrict__ rngFlags,
@@ -310,7 +315,7 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
 
         Surface s;
         if (isHit) {
-            surfaceFromHit(sc, o, d, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, geomID, h1.y, s);
+            surfaceFromHit<PTEX>(sc, o, d, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, geomID, h1.y, s);
             rayDistance = length(s.position - o);  // :165-167
         }
         thr = thr * transmission(medium, rayDistance);  // :168-169
@@ -527,9 +532,16 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             timers.end(1, t0, stream);
             st.closestRays += n;
             t0 = timers.begin(stream);
-            shadeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, nullptr, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
-                                                            w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
-                                                            w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film);
+            if (scene->usesPtex)
+                shadeKernel<true><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, nullptr, n, w->rays[cur], w->hits, w->thrPix[cur],
+                                                                      w->rngFlags[cur], w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1],
+                                                                      w->rngFlags[cur ^ 1], w->medium[cur ^ 1], w->shadowRays, w->shadowPayload,
+                                                                      ctr, d_film);
+            else
+                shadeKernel<false><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, nullptr, n, w->rays[cur], w->hits, w->thrPix[cur],
+                                                                       w->rngFlags[cur], w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1],
+                                                                       w->rngFlags[cur ^ 1], w->medium[cur ^ 1], w->shadowRays, w->shadowPayload,
+                                                                       ctr, d_film);
             timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));

@@ -22,6 +22,8 @@ SELAS_D float interpAttr(const float* a, const uint32_t* ix, uint32_t ipf, int c
     return (1.0f - v) * ((1.0f - u) * t0 + u * t1) + v * ((1.0f - u) * t3 + u * t2);
 }
 
+// PTEX = false compiles the Ptex lookup out (scenes without Ptex materials keep the leaner kernel).
+template <bool PTEX>
 SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, float v, uint32_t primID, uint32_t geomID,
                             uint32_t instID, Surface& s) {
     const MeshGpu mesh = sc.meshes[geomID];
@@ -68,7 +70,7 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
     }
 
     V3 base;
-    if ((mat->flags & SELAS_MAT_USES_PTEX) && mesh.ptex) {
+    if (PTEX && (mat->flags & SELAS_MAT_USES_PTEX) && mesh.ptex) {
         // SurfaceParameters.cpp:196-208: filter->eval(faceid = primId, u, v, widths 0), then pow 2.2 only
         float rgb[3];
         ptexEvalBspline((const PtexGpu*)mesh.ptex, (int)primID, u, v, rgb);

@@ -72,7 +72,11 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                     octInv4 = (7u - oct) * 0x01010101u;
                     res.t = tfar; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
                     sp = 0;
-                    group = make_uint2(0u, bvh.nodeCount ? 0x80000000u : 0u);
+                    // A ray with a non-finite origin / direction would pass every slab test (NaN compares false both ways)
+                    // and walk the whole tree; Embree reports such rays as misses, and so does this kernel, immediately.
+                    const bool valid = isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z) &&
+                                       tnear <= tfar;
+                    group = make_uint2(0u, (bvh.nodeCount && valid) ? 0x80000000u : 0u);
                     rayIdx = idx;
                     nNodes = 0; nTris = 0;
                     active = true;
