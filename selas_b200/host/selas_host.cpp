@@ -1,0 +1,468 @@
+// selas_host.cpp -- see selas_host.h.  Host-side glue only: everything on the hot path happens behind the C ABI.
+#include "selas_host.h"
+
+#include <sys/stat.h>
+
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+namespace Selas {
+
+Error MakeError(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    return Error(buf);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A minimal JSON reader: objects of numbers / strings / bools / flat number arrays is all the material files use
+// (Content/Materials/*.json; the reference reads them with rapidjson through UtilityLib/JsonUtilities).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct JsonValue {
+    enum Kind { kNull, kNumber, kString, kBool, kArray, kObject } kind = kNull;
+    double number = 0;
+    bool boolean = false;
+    std::string string;
+    std::vector<JsonValue> array;
+    std::map<std::string, JsonValue> object;
+};
+struct JsonParser {
+    const char* p;
+    std::string error;
+    void ws() {
+        while (*p && isspace((unsigned char)*p)) ++p;
+    }
+    bool fail(const char* m) {
+        if (error.empty()) error = m;
+        return false;
+    }
+    bool parseString(std::string& out) {
+        if (*p != '"') return fail("expected string");
+        ++p;
+        out.clear();
+        while (*p && *p != '"') {
+            if (*p == '\\' && p[1]) {
+                ++p;
+                switch (*p) {
+                    case 'n': out += '\n'; break;
+                    case 't': out += '\t'; break;
+                    default: out += *p;
+                }
+                ++p;
+            } else out += *p++;
+        }
+        if (*p != '"') return fail("unterminated string");
+        ++p;
+        return true;
+    }
+    bool parseValue(JsonValue& v) {
+        ws();
+        if (*p == '{') {
+            v.kind = JsonValue::kObject;
+            ++p;
+            ws();
+            if (*p == '}') { ++p; return true; }
+            for (;;) {
+                ws();
+                std::string key;
+                if (!parseString(key)) return false;
+                ws();
+                if (*p != ':') return fail("expected ':'");
+                ++p;
+                if (!parseValue(v.object[key])) return false;
+                ws();
+                if (*p == ',') { ++p; continue; }
+                if (*p == '}') { ++p; return true; }
+                return fail("expected ',' or '}'");
+            }
+        }
+        if (*p == '[') {
+            v.kind = JsonValue::kArray;
+            ++p;
+            ws();
+            if (*p == ']') { ++p; return true; }
+            for (;;) {
+                v.array.emplace_back();
+                if (!parseValue(v.array.back())) return false;
+                ws();
+                if (*p == ',') { ++p; continue; }
+                if (*p == ']') { ++p; return true; }
+                return fail("expected ',' or ']'");
+            }
+        }
+        if (*p == '"') {
+            v.kind = JsonValue::kString;
+            return parseString(v.string);
+        }
+        if (!strncmp(p, "true", 4)) { v.kind = JsonValue::kBool; v.boolean = true; p += 4; return true; }
+        if (!strncmp(p, "false", 5)) { v.kind = JsonValue::kBool; v.boolean = false; p += 5; return true; }
+        if (!strncmp(p, "null", 4)) { v.kind = JsonValue::kNull; p += 4; return true; }
+        char* end = nullptr;
+        double d = strtod(p, &end);
+        if (end == p) return fail("unexpected character");
+        v.kind = JsonValue::kNumber;
+        v.number = d;
+        p = end;
+        return true;
+    }
+};
+
+const char* kAttributes[SELAS_SCALAR_COUNT] = {"metallic", "specularTint", "roughness", "anisotropic", "sheen", "sheenTint", "clearcoat",
+                                               "clearcoatGloss", "specTrans", "diffTrans", "flatness", "ior", "scatterDistance", "displacement"};
+// ImportMaterial.cpp:36-52
+const float kAttributeDefaults[SELAS_SCALAR_COUNT] = {0.3f, 0.0f, 0.5f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.5f, 0.0f, 0.0f};
+
+bool equalsIgnoreCase(const std::string& a, const char* b) {
+    size_t n = strlen(b);
+    if (a.size() != n) return false;
+    for (size_t i = 0; i < n; ++i)
+        if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+    return true;
+}
+void readFloat3(const JsonValue& doc, const char* key, float* out, float d0, float d1, float d2) {
+    out[0] = d0; out[1] = d1; out[2] = d2;
+    auto it = doc.object.find(key);
+    if (it == doc.object.end() || it->second.kind != JsonValue::kArray || it->second.array.size() < 3) return;
+    for (int i = 0; i < 3; ++i)
+        if (it->second.array[i].kind == JsonValue::kNumber) out[i] = (float)it->second.array[i].number;
+}
+}  // namespace
+
+Error ImportMaterialFromString(const char* json, ImportedMaterialData* material) {
+    JsonParser parser{json, ""};
+    JsonValue doc;
+    parser.ws();
+    if (*parser.p == 0) doc.kind = JsonValue::kObject;  // an empty file behaves like "{}" (Default.json is "{ }")
+    else if (!parser.parseValue(doc) || doc.kind != JsonValue::kObject)
+        return Error_("material json: %s", parser.error.empty() ? "top-level value is not an object" : parser.error.c_str());
+
+    auto str = [&](const char* key, std::string& out) {
+        auto it = doc.object.find(key);
+        out = (it != doc.object.end() && it->second.kind == JsonValue::kString) ? it->second.string : std::string();
+    };
+    auto isString = [&](const char* key) {
+        auto it = doc.object.find(key);
+        return it != doc.object.end() && it->second.kind == JsonValue::kString;
+    };
+    auto boolean = [&](const char* key, bool dflt) {
+        auto it = doc.object.find(key);
+        return (it != doc.object.end() && it->second.kind == JsonValue::kBool) ? it->second.boolean : dflt;
+    };
+    str("shaderName", material->shaderName);
+    material->baseColorTexture.clear();
+    if (isString("baseColor")) {  // ImportMaterial.cpp:63-67
+        str("baseColor", material->baseColorTexture);
+        material->baseColor[0] = material->baseColor[1] = material->baseColor[2] = 0.6f;
+    } else {
+        readFloat3(doc, "baseColor", material->baseColor, 0.6f, 0.6f, 0.6f);
+    }
+    readFloat3(doc, "transmittanceColor", material->transmittanceColor, 0.f, 0.f, 0.f);
+    for (int i = 0; i < SELAS_SCALAR_COUNT; ++i) {
+        material->scalarAttributeTextures[i].clear();
+        material->scalarAttributes[i] = kAttributeDefaults[i];
+        if (isString(kAttributes[i])) str(kAttributes[i], material->scalarAttributeTextures[i]);
+        else {
+            auto it = doc.object.find(kAttributes[i]);
+            if (it != doc.object.end() && it->second.kind == JsonValue::kNumber) material->scalarAttributes[i] = (float)it->second.number;
+        }
+    }
+    material->alphaTested = boolean("alphaTesting", false);
+    material->invertDisplacement = boolean("invertDisplacement", false);
+    material->usesPtex = boolean("usesPtex", false);
+    return Success_;
+}
+
+Error ImportMaterial(const char* filepath, ImportedMaterialData* material) {
+    FILE* fp = fopen(filepath, "rb");
+    if (!fp) return Error_("Failed to open material file: %s", filepath);
+    std::string text;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, n);
+    fclose(fp);
+    return ImportMaterialFromString(text.c_str(), material);
+}
+
+void BuildMaterial(const ImportedMaterialData& imported, SelasMaterial& material) {  // BuildModel.cpp:22-66
+    memset(&material, 0, sizeof(material));
+    if (imported.alphaTested) material.flags |= SELAS_MAT_ALPHA_TESTED;
+    if (imported.invertDisplacement) material.flags |= SELAS_MAT_INVERT_DISPLACEMENT;
+    if (imported.usesPtex) material.flags |= SELAS_MAT_USES_PTEX;
+    static const char* shaderNames[] = {"DisneyThin", "DisneySolid", "DeltaTransparent"};
+    material.shader = SELAS_SHADER_DISNEY_SOLID;
+    for (uint32_t i = 0; i < 3; ++i)
+        if (equalsIgnoreCase(imported.shaderName, shaderNames[i])) material.shader = i;
+    memcpy(material.baseColor, imported.baseColor, sizeof(material.baseColor));
+    memcpy(material.transmittanceColor, imported.transmittanceColor, sizeof(material.transmittanceColor));
+    for (int i = 0; i < SELAS_SCALAR_COUNT; ++i) material.scalars[i] = imported.scalarAttributes[i];
+    if (material.shader == SELAS_SHADER_DISNEY_SOLID && (material.scalars[SELAS_DIFFUSE_TRANS] > 0.0f || material.scalars[SELAS_SPEC_TRANS] > 0.0f))
+        material.flags |= SELAS_MAT_TRANSPARENT;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// film
+// ---------------------------------------------------------------------------------------------------------------
+void FrameBuffer_Initialize(Framebuffer* frame, uint32_t width, uint32_t height, uint32_t layerCount) {
+    frame->width = width;
+    frame->height = height;
+    frame->layerCount = layerCount;
+    frame->buffers.assign(layerCount, std::vector<float3>((size_t)width * height, float3{0.f, 0.f, 0.f}));
+}
+void FrameBuffer_Shutdown(Framebuffer* frame) {
+    frame->buffers.clear();
+    frame->width = frame->height = frame->layerCount = 0;
+}
+void FrameBuffer_Scale(Framebuffer* frame, float scale) {  // Framebuffer.cpp:62-70
+    for (auto& layer : frame->buffers)
+        for (float3& p : layer) {
+            p.x = p.x * scale;
+            p.y = p.y * scale;
+            p.z = p.z * scale;
+        }
+}
+
+// Radiance RGBE, flat (non-RLE) scanlines: "#?RADIANCE", FORMAT=32-bit_rle_rgbe, "-Y h +X w".
+Error WriteRadianceHdr(const char* path, uint32_t width, uint32_t height, const float3* pixels) {
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return Error_("Failed to open %s for writing", path);
+    fprintf(fp, "#?RADIANCE\n# Written by selas-b200\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n-Y %u +X %u\n", height, width);
+    std::vector<unsigned char> row((size_t)width * 4);
+    for (uint32_t y = 0; y < height; ++y) {
+        for (uint32_t x = 0; x < width; ++x) {
+            const float3& p = pixels[(size_t)y * width + x];
+            float r = p.x > 0.f ? p.x : 0.f, g = p.y > 0.f ? p.y : 0.f, b = p.z > 0.f ? p.z : 0.f;
+            float m = r > g ? (r > b ? r : b) : (g > b ? g : b);
+            unsigned char* o = &row[(size_t)x * 4];
+            if (!(m >= 1e-32f) || !std::isfinite(m)) {
+                o[0] = o[1] = o[2] = o[3] = 0;
+            } else {
+                int e;
+                float norm = frexpf(m, &e) * 256.0f / m;
+                o[0] = (unsigned char)(r * norm);
+                o[1] = (unsigned char)(g * norm);
+                o[2] = (unsigned char)(b * norm);
+                o[3] = (unsigned char)(e + 128);
+            }
+        }
+        if (fwrite(row.data(), 1, row.size(), fp) != row.size()) {
+            fclose(fp);
+            return Error_("short write on %s", path);
+        }
+    }
+    fclose(fp);
+    return Success_;
+}
+
+Error FrameBuffer_Save(Framebuffer* frame, const char* name) {  // Framebuffer.cpp:43-59: _Images/<name>_<layer>.hdr
+    mkdir("_Images", 0755);
+    for (uint32_t l = 0; l < frame->layerCount; ++l) {
+        char path[1024];
+        snprintf(path, sizeof(path), "_Images/%s_%u.hdr", name, l);
+        ReturnError_(WriteRadianceHdr(path, frame->width, frame->height, frame->buffers[l].data()));
+    }
+    return Success_;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// camera / scene
+// ---------------------------------------------------------------------------------------------------------------
+void InitializeRayCastCamera(const CameraSettings& settings, uint32_t width, uint32_t height, RayCastCameraSettings& camera) {
+    SelasCameraSettings st;
+    memcpy(st.position, settings.position, sizeof(st.position));
+    st.fovDegrees = settings.fovDegrees;
+    memcpy(st.lookAt, settings.lookAt, sizeof(st.lookAt));
+    st.znear = settings.znear;
+    memcpy(st.up, settings.up, sizeof(st.up));
+    st.zfar = settings.zfar;
+    selas_cuda_camera_init(&st, width, height, &camera);
+}
+
+Error InitializeSceneResource(SceneResource* scene, int device) {
+    if (selas_cuda_context_create(device, &scene->gpu) != SELAS_OK) return Error_("%s", selas_cuda_last_error(nullptr));
+    std::vector<SelasMeshDesc> meshes(scene->meshes.size());
+    for (size_t i = 0; i < meshes.size(); ++i) {
+        const SceneMesh& m = scene->meshes[i];
+        SelasMeshDesc& d = meshes[i];
+        memset(&d, 0, sizeof(d));
+        d.positions = m.positions.data();
+        d.vertexCount = (uint32_t)(m.positions.size() / 3);
+        d.indices = m.indices.data();
+        d.indicesPerFace = m.indicesPerFace;
+        d.faceCount = (uint32_t)(m.indices.size() / m.indicesPerFace);
+        d.normals = m.normals.empty() ? nullptr : m.normals.data();
+        d.tangents = m.tangents.empty() ? nullptr : m.tangents.data();
+        d.uvs = m.uvs.empty() ? nullptr : m.uvs.data();
+        d.materialIndex = m.materialIndex;
+        d.lightSetIndex = m.lightSetIndex;
+        d.ptex = m.ptex;
+    }
+    SelasSceneDesc desc;
+    memset(&desc, 0, sizeof(desc));
+    desc.meshes = meshes.data();
+    desc.meshCount = (uint32_t)meshes.size();
+    desc.instances = scene->instances.empty() ? nullptr : scene->instances.data();
+    desc.instanceCount = (uint32_t)scene->instances.size();
+    desc.materials = scene->materials.data();
+    desc.materialCount = (uint32_t)scene->materials.size();
+    desc.lights = scene->lights.data();
+    desc.lightCount = (uint32_t)scene->lights.size();
+    desc.lightSets = scene->lightSets.data();
+    desc.lightSetCount = (uint32_t)scene->lightSets.size();
+    memcpy(desc.backgroundIntensity, scene->backgroundIntensity, sizeof(desc.backgroundIntensity));
+    if (selas_cuda_scene_create(scene->gpu, &desc, &scene->gpuScene) != SELAS_OK) {
+        Error e = Error_("%s", selas_cuda_last_error(scene->gpu));
+        ShutdownSceneResource(scene);
+        return e;
+    }
+    return Success_;
+}
+
+void ShutdownSceneResource(SceneResource* scene) {
+    if (scene->gpuScene) selas_cuda_scene_destroy(scene->gpuScene);
+    if (scene->gpu) selas_cuda_context_destroy(scene->gpu);
+    scene->gpuScene = nullptr;
+    scene->gpu = nullptr;
+}
+
+namespace {
+void addQuad(SceneMesh& m, const float a[3], const float b[3], const float c[3], const float d[3]) {
+    uint32_t base = (uint32_t)(m.positions.size() / 3);
+    const float* v[4] = {a, b, c, d};
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 3; ++k) m.positions.push_back(v[i][k]);
+    for (uint32_t i = 0; i < 4; ++i) m.indices.push_back(base + i);
+}
+void addBlock(SceneMesh& m, float sx, float sy, float sz, float rotDeg, float cx, float cz) {
+    const float c = cosf(rotDeg * 3.14159265358979f / 180.f), s = sinf(rotDeg * 3.14159265358979f / 180.f);
+    auto P = [&](float x, float y, float z, float* o) {
+        x -= sx / 2;
+        z -= sz / 2;
+        o[0] = cx + c * x + s * z;
+        o[1] = y;
+        o[2] = cz - s * x + c * z;
+    };
+    float v[8][3];
+    P(0, 0, 0, v[0]); P(sx, 0, 0, v[1]); P(sx, 0, sz, v[2]); P(0, 0, sz, v[3]);
+    P(0, sy, 0, v[4]); P(sx, sy, 0, v[5]); P(sx, sy, sz, v[6]); P(0, sy, sz, v[7]);
+    addQuad(m, v[4], v[7], v[6], v[5]);
+    addQuad(m, v[0], v[4], v[5], v[1]);
+    addQuad(m, v[1], v[5], v[6], v[2]);
+    addQuad(m, v[2], v[6], v[7], v[3]);
+    addQuad(m, v[3], v[7], v[4], v[0]);
+}
+SelasMaterial makeMaterial(const char* json) {
+    ImportedMaterialData imp;
+    ImportMaterialFromString(json, &imp);
+    SelasMaterial m;
+    BuildMaterial(imp, m);
+    return m;
+}
+}  // namespace
+
+// BASELINE config 1; identical to selas_b200/scenes.py:cornell_box.
+void MakeCornellBoxScene(SceneResource* scene, float copperRoughness) {
+    const float X = 556.0f, Y = 548.8f, Z = 559.2f;
+    scene->meshes.assign(4, SceneMesh());
+    for (auto& m : scene->meshes) m.indicesPerFace = 4;
+    SceneMesh& white = scene->meshes[0];
+    {
+        float a[3] = {0, 0, 0}, b[3] = {0, 0, Z}, c[3] = {X, 0, Z}, d[3] = {X, 0, 0};
+        addQuad(white, a, b, c, d);
+        float e[3] = {0, Y, 0}, f[3] = {X, Y, 0}, g[3] = {X, Y, Z}, h[3] = {0, Y, Z};
+        addQuad(white, e, f, g, h);
+        float i[3] = {0, 0, Z}, j[3] = {0, Y, Z}, k[3] = {X, Y, Z}, l[3] = {X, 0, Z};
+        addQuad(white, i, j, k, l);
+        addBlock(white, 165, 330, 165, 17.0f, 368.0f, 351.0f);
+    }
+    {
+        float a[3] = {X, 0, 0}, b[3] = {X, 0, Z}, c[3] = {X, Y, Z}, d[3] = {X, Y, 0};
+        addQuad(scene->meshes[1], a, b, c, d);
+        float e[3] = {0, 0, 0}, f[3] = {0, Y, 0}, g[3] = {0, Y, Z}, h[3] = {0, 0, Z};
+        addQuad(scene->meshes[2], e, f, g, h);
+    }
+    addBlock(scene->meshes[3], 165, 165, 165, -18.0f, 185.0f, 169.0f);
+    for (uint32_t i = 0; i < 4; ++i) scene->meshes[i].materialIndex = i;
+    const char* rough = "{\"shaderName\":\"DisneySolid\",\"baseColor\":[%g,%g,%g],\"ior\":1.2,\"metallic\":0.0,\"specularTint\":0.0,"
+                        "\"roughness\":0.8,\"flatness\":0.5}";
+    char buf[512];
+    const float colors[3][3] = {{0.725f, 0.71f, 0.68f}, {0.63f, 0.065f, 0.05f}, {0.14f, 0.45f, 0.091f}};
+    scene->materials.clear();
+    for (int i = 0; i < 3; ++i) {
+        snprintf(buf, sizeof(buf), rough, colors[i][0], colors[i][1], colors[i][2]);
+        scene->materials.push_back(makeMaterial(buf));
+    }
+    snprintf(buf, sizeof(buf),
+             "{\"shaderName\":\"DisneySolid\",\"baseColor\":[0.955008,0.637427,0.538163],\"ior\":1.5,\"metallic\":1.0,\"specularTint\":0.3,"
+             "\"roughness\":%g,\"clearcoatGloss\":1.0}", copperRoughness);
+    scene->materials.push_back(makeMaterial(buf));
+    SelasLight L;
+    memset(&L, 0, sizeof(L));
+    const float pos[3] = {278.0f, 548.7f, 279.5f}, dir[3] = {0, -1, 0}, lx[3] = {130, 0, 0}, lz[3] = {0, 0, 105}, rad[3] = {17, 12, 4};
+    memcpy(L.position, pos, 12); memcpy(L.direction, dir, 12); memcpy(L.x, lx, 12); memcpy(L.z, lz, 12); memcpy(L.radiance, rad, 12);
+    scene->lights.assign(1, L);
+    scene->lightSets.assign(1, SelasLightSetRange{0, 1});
+    memset(scene->backgroundIntensity, 0, sizeof(scene->backgroundIntensity));
+}
+
+void SetupCornellCamera(uint32_t width, uint32_t height, RayCastCameraSettings& camera) {
+    CameraSettings cs = {{278.0f, 273.0f, -800.0f}, 37.0f, {278.0f, 273.0f, 0.0f}, 0.1f, {0.0f, 1.0f, 0.0f}, 10000.0f};
+    InitializeRayCastCamera(cs, width, height, camera);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// integrator entry point
+// ---------------------------------------------------------------------------------------------------------------
+namespace PathTracer {
+Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, const char* imageName, const PathTracerSettings& settings,
+                    SelasRenderStats* stats, Framebuffer* keep) {
+    if (!scene->gpuScene) return Error_("PathTracer::GenerateImage: scene is not initialised on a GPU (there is no CPU fallback)");
+    const uint32_t width = (uint32_t)camera.width, height = (uint32_t)camera.height;
+    Framebuffer frame;
+    FrameBuffer_Initialize(&frame, width, height, settings.layerCount);
+    SelasRenderSettings rs;
+    memset(&rs, 0, sizeof(rs));
+    rs.width = width;
+    rs.height = height;
+    rs.samplesPerPixel = settings.pathsPerPixel;
+    rs.maxPathLength = settings.maxBounceCount;
+    rs.rrStartBounce = settings.rrStartBounce;
+    rs.layerCount = settings.layerCount;
+    rs.seed = settings.seed;
+    std::vector<float*> layers(settings.layerCount);
+    for (uint32_t l = 0; l < settings.layerCount; ++l) layers[l] = &frame.buffers[l][0].x;
+    if (selas_cuda_render_pathtracer(scene->gpuScene, &camera, &rs, layers.data(), stats) != SELAS_OK)
+        return Error_("%s", selas_cuda_last_error(scene->gpu));
+    FrameBuffer_Scale(&frame, 1.0f / (float)settings.pathsPerPixel);  // PathTracer.cpp:346
+    ReturnError_(FrameBuffer_Save(&frame, imageName));
+    if (keep) *keep = frame;
+    FrameBuffer_Shutdown(&frame);
+    return Success_;
+}
+}  // namespace PathTracer
+
+}  // namespace Selas
+
+extern "C" {
+int selas_host_import_material_json(const char* json, SelasMaterial* out, char* errorOut, int errorCapacity) {
+    Selas::ImportedMaterialData imp;
+    Selas::Error e = Selas::ImportMaterialFromString(json, &imp);
+    if (e.Failed()) {
+        if (errorOut && errorCapacity > 0) snprintf(errorOut, errorCapacity, "%s", e.Message());
+        return SELAS_ERR_FORMAT;
+    }
+    Selas::BuildMaterial(imp, *out);
+    return SELAS_OK;
+}
+int selas_host_write_hdr(const char* path, uint32_t width, uint32_t height, const float* rgb) {
+    return Selas::WriteRadianceHdr(path, width, height, (const Selas::float3*)rgb).Failed() ? SELAS_ERR_ARGUMENT : SELAS_OK;
+}
+}

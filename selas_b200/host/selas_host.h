@@ -1,0 +1,126 @@
+// selas_host.h -- C++ host surface above the C ABI (include/selas_cuda.h), mirroring the reference's own entry points
+// for this path: same names, argument meaning and error behaviour, re-based on the C++ standard library instead of
+// the reference's platform layer.
+//
+//   Error / Success_ / Error_                         Source/Core/SystemLib/Error.h:11-58
+//   ImportMaterial / BuildMaterial                    Source/Core/BuildCommon/ImportMaterial.cpp:17-90, BuildModel.cpp:41-66
+//   Framebuffer, FrameBuffer_* / FramebufferWriter    Source/Core/TextureLib/Framebuffer.h:17-48, Framebuffer.cpp:18-138
+//   RayCastCameraSettings / InitializeRayCastCamera   Source/Core/GeometryLib/Camera.h:17-47, Camera.cpp:89-115
+//   PathTracer::GenerateImage                         Source/Applications/Selas/Source/PathTracer.h:20-21, PathTracer.cpp:301-350
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/selas_cuda.h"
+
+namespace Selas {
+
+// ---- Error: null message == success (Error.h:11-36) ---------------------------------------------------------------
+class Error {
+public:
+    Error() {}
+    explicit Error(const std::string& msg) : message_(msg), failed_(true) {}
+    bool Success() const { return !failed_; }
+    bool Failed() const { return failed_; }
+    const char* Message() const { return failed_ ? message_.c_str() : nullptr; }
+
+private:
+    std::string message_;
+    bool failed_ = false;
+};
+#define Success_ ::Selas::Error()
+Error MakeError(const char* fmt, ...);
+#define Error_(...) ::Selas::MakeError(__VA_ARGS__)
+#define ReturnError_(expr)                 \
+    do {                                   \
+        ::Selas::Error e__ = (expr);       \
+        if (e__.Failed()) return e__;      \
+    } while (0)
+
+// ---- materials ------------------------------------------------------------------------------------------------------
+struct ImportedMaterialData {  // ImportMaterial.h
+    std::string shaderName;
+    std::string baseColorTexture;
+    float baseColor[3];
+    float transmittanceColor[3];
+    float scalarAttributes[SELAS_SCALAR_COUNT];
+    std::string scalarAttributeTextures[SELAS_SCALAR_COUNT];
+    bool alphaTested, invertDisplacement, usesPtex;
+};
+Error ImportMaterial(const char* filepath, ImportedMaterialData* material);
+Error ImportMaterialFromString(const char* json, ImportedMaterialData* material);
+void BuildMaterial(const ImportedMaterialData& imported, SelasMaterial& material);
+
+// ---- film -----------------------------------------------------------------------------------------------------------
+struct float3 {
+    float x, y, z;
+};
+struct Framebuffer {  // Framebuffer.h:17-25
+    uint32_t width = 0, height = 0, layerCount = 0;
+    std::vector<std::vector<float3>> buffers;  // [layer][y * width + x]
+};
+void FrameBuffer_Initialize(Framebuffer* frame, uint32_t width, uint32_t height, uint32_t layerCount);
+void FrameBuffer_Shutdown(Framebuffer* frame);
+void FrameBuffer_Scale(Framebuffer* frame, float scale);
+Error FrameBuffer_Save(Framebuffer* frame, const char* name);  // writes _Images/<name>_<layer>.hdr (Framebuffer.cpp:43-59)
+Error WriteRadianceHdr(const char* path, uint32_t width, uint32_t height, const float3* pixels);
+
+// ---- camera ---------------------------------------------------------------------------------------------------------
+typedef SelasCamera RayCastCameraSettings;  // layout-identical (104 bytes)
+struct CameraSettings {                     // Camera.h:17-26
+    float position[3];
+    float fovDegrees;
+    float lookAt[3];
+    float znear;
+    float up[3];
+    float zfar;
+};
+void InitializeRayCastCamera(const CameraSettings& settings, uint32_t width, uint32_t height, RayCastCameraSettings& camera);
+
+// ---- scene ----------------------------------------------------------------------------------------------------------
+// What the reference keeps in SceneResource + the Embree handles, reduced to what the path needs.
+struct SceneMesh {
+    std::vector<float> positions, normals, tangents, uvs;
+    std::vector<uint32_t> indices;
+    uint32_t indicesPerFace = 3, materialIndex = 0, lightSetIndex = 0;
+    SelasPtex* ptex = nullptr;
+};
+struct SceneResource {
+    std::vector<SceneMesh> meshes;
+    std::vector<SelasInstanceDesc> instances;
+    std::vector<SelasMaterial> materials;
+    std::vector<SelasLight> lights;
+    std::vector<SelasLightSetRange> lightSets;
+    float backgroundIntensity[4] = {0, 0, 0, 0};
+    // device side
+    SelasContext* gpu = nullptr;
+    SelasScene* gpuScene = nullptr;
+};
+Error InitializeSceneResource(SceneResource* scene, int device);  // context + upload + BVH8 build
+void ShutdownSceneResource(SceneResource* scene);
+void MakeCornellBoxScene(SceneResource* scene, float copperRoughness);  // BASELINE config 1
+void SetupCornellCamera(uint32_t width, uint32_t height, RayCastCameraSettings& camera);
+
+// ---- integrator -----------------------------------------------------------------------------------------------------
+// The reference's compile-time macros (PathTracer.cpp:42-46, :248) as runtime settings; defaults = reference values.
+struct PathTracerSettings {
+    uint32_t maxBounceCount = 2048;  // MaxBounceCount_
+    uint32_t pathsPerPixel = 16;     // PathsPerPixel_
+    uint32_t layerCount = 2;         // LayerCount_
+    uint32_t rrStartBounce = 8;
+    uint32_t seed = 0;
+};
+namespace PathTracer {
+// Renders, scales by 1/pathsPerPixel and writes _Images/<imageName>_<layer>.hdr, like the reference.  `stats` optional.
+Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, const char* imageName,
+                    const PathTracerSettings& settings = PathTracerSettings(), SelasRenderStats* stats = nullptr, Framebuffer* keep = nullptr);
+}  // namespace PathTracer
+
+}  // namespace Selas
+
+extern "C" {
+// C handles for tests (ctypes): material JSON -> 88-byte payload; Radiance writer.
+int selas_host_import_material_json(const char* json, SelasMaterial* out, char* errorOut, int errorCapacity);
+int selas_host_write_hdr(const char* path, uint32_t width, uint32_t height, const float* rgb);
+}

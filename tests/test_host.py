@@ -1,0 +1,82 @@
+"""The C++ host surface (selas_b200/host): material JSON import + BuildMaterial against the Python restatement of the same
+reference rules for the six material files the reference ships, the Radiance .hdr writer, and (GPU) the selas_render
+executable = the reference's main() for the Cornell scene, whose image must equal the one rendered through the C ABI."""
+import ctypes as C
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from selas_b200 import capi, scenes
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "selas_b200" / "lib"
+
+
+@pytest.fixture(scope="module")
+def host():
+    path = LIB / "libselas_host.so"
+    if not path.exists():
+        subprocess.run(["make", "-C", str(ROOT / "selas_b200" / "host")], check=True, stdout=subprocess.DEVNULL)
+    capi.load_library()
+    return C.CDLL(str(path))
+
+
+def read_hdr(path):
+    data = Path(path).read_bytes()
+    head, _, rest = data.partition(b"\n\n")
+    assert head.startswith(b"#?RADIANCE") and b"FORMAT=32-bit_rle_rgbe" in head
+    line, _, pix = rest.partition(b"\n")
+    _, h, _, w = line.split()
+    w, h = int(w), int(h)
+    a = np.frombuffer(pix, np.uint8).reshape(h, w, 4).astype(np.float32)
+    scale = np.where(a[..., 3] > 0, np.exp2(a[..., 3] - 136.0), 0.0).astype(np.float32)
+    return a[..., :3] * scale[..., None]
+
+
+def test_material_import_matches_reference_rules(host):
+    for name, d in scenes.REFERENCE_MATERIALS.items():
+        want = scenes.material(**d)
+        got = capi.Material()
+        err = C.create_string_buffer(256)
+        assert host.selas_host_import_material_json(json.dumps(d).encode(), C.byref(got), err, 256) == 0, err.value
+        assert bytes(got) == want.tobytes(), name
+    got = capi.Material()
+    assert host.selas_host_import_material_json(b" ", C.byref(got), None, 0) == 0  # Default.json is an empty object
+    assert bytes(got) == scenes.material().tobytes()
+    err = C.create_string_buffer(256)
+    assert host.selas_host_import_material_json(b'{"roughness": ', C.byref(got), err, 256) == 4 and b"json" in err.value
+    assert host.selas_host_import_material_json(b'{"shaderName":"disneythin","usesPtex":true,"alphaTesting":true}', C.byref(got), None, 0) == 0
+    assert got.shader == capi.SHADER_DISNEY_THIN and got.flags == (capi.MAT_USES_PTEX | capi.MAT_ALPHA_TESTED)
+
+
+def test_hdr_writer_roundtrip(host, tmp_path):
+    rng = np.random.default_rng(3)
+    img = (rng.uniform(0, 1, size=(7, 13, 3)) ** 4 * 50).astype(np.float32)
+    img[0, 0] = 0
+    path = tmp_path / "t.hdr"
+    assert host.selas_host_write_hdr(str(path).encode(), 13, 7, img.ctypes.data_as(C.c_void_p)) == 0
+    back = read_hdr(path)
+    m = img.max(axis=2, keepdims=True)
+    assert np.all(np.abs(back - img) <= m / 128.0 + 1e-6)  # 8-bit mantissa shared exponent
+
+
+@pytest.mark.gpu
+def test_selas_render_cornell(ctx, host, tmp_path):
+    exe = LIB / "selas_render"
+    out = subprocess.run([str(exe), "--width", "96", "--height", "96", "--spp", "8", "--depth", "6", "--roughness", "0.1", "--seed", "1",
+                          "--name", "t"], cwd=tmp_path, capture_output=True, text=True, check=True).stdout
+    assert "Scene render time" in out
+    stats = json.loads(out.strip().splitlines()[-1])
+    assert stats["paths"] == 96 * 96 * 8 and stats["kernel_launches"] > 0
+    radiance = read_hdr(tmp_path / "_Images" / "t_1.hdr")
+    albedo = read_hdr(tmp_path / "_Images" / "t_0.hdr")
+    sc = capi.Scene(ctx, scenes.cornell_box(copper_roughness=0.1))
+    film, _ = sc.render(scenes.cornell_camera(96, 96), capi.render_settings(96, 96, 8, max_path_length=6, rr_start=8, layers=2, seed=1))
+    for got, want in ((albedo, film[0] / 8.0), (radiance, film[1] / 8.0)):
+        m = want.max(axis=2, keepdims=True)
+        close = np.abs(got - want) <= m / 100.0 + 1e-4
+        assert close.mean() > 0.995  # RGBE quantisation + atomic float accumulation order
+    sc.close()
