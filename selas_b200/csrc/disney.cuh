@@ -63,7 +63,7 @@ SELAS_HD V3 schlickColor(V3 r0, float c) {  // :19-23, powf form
     return r0 + (v3(1.0f) - r0) * e;
 }
 SELAS_HD float schlickR0(float eta) { return sq(eta - 1.0f) / sq(eta + 1.0f); }  // :78-82
-SELAS_HD float fresnelDielectric(float cosI, float ni, float nt) {               // :47-76
+static SELAS_HDN float fresnelDielectric(float cosI, float ni, float nt) {               // :47-76
     cosI = clampf_(cosI, -1.0f, 1.0f);
     if (cosI < 0.0f) {
         float t = ni;
@@ -81,7 +81,7 @@ SELAS_HD float fresnelDielectric(float cosI, float ni, float nt) {              
 }
 
 // ---- GGX (Ggx.cpp) --------------------------------------------------------------------------------------------
-SELAS_HD float smithG1Aniso(V3 w, float ax, float ay) {  // :19-37; QUIRK: the half vector argument is unused
+static SELAS_HDN float smithG1Aniso(V3 w, float ax, float ay) {  // :19-37; QUIRK: the half vector argument is unused
     float absTan = fabsf(tanTheta(w));
     if (isinf(absTan)) return 0.0f;
     float c = cosPhi(w), s = sinPhi(w);
@@ -95,11 +95,11 @@ SELAS_HD float smithG1Iso(V3 w, float a) {  // :40-46
     float c = absCosTheta(w);
     return 2.0f / (1.0f + sqrtf(a2 + (1 - a2) * c * c));
 }
-SELAS_HD float ggxD(V3 wm, float ax, float ay) {  // :75-84
+static SELAS_HDN float ggxD(V3 wm, float ax, float ay) {  // :75-84
     float hx2 = sq(wm.x), hy2 = sq(wm.z), c2 = cos2Theta(wm);
     return 1.0f / (SELAS_PI * ax * ay * sq(hx2 / sq(ax) + hy2 / sq(ay) + c2));
 }
-SELAS_HD V3 sampleVndf(V3 wo, float ax, float ay, float u1, float u2) {  // :105-126
+static SELAS_HDN V3 sampleVndf(V3 wo, float ax, float ay, float u1, float u2) {  // :105-126
     V3 v = normalize(v3(wo.x * ax, wo.y, wo.z * ay));
     V3 t1 = (v.y < 0.9999f) ? normalize(cross(v, v3(0.f, 1.f, 0.f))) : v3(1.f, 0.f, 0.f);
     V3 t2 = cross(t1, v);
@@ -111,7 +111,7 @@ SELAS_HD V3 sampleVndf(V3 wo, float ax, float ay, float u1, float u2) {  // :105
     V3 n = p1 * t1 + p2 * t2 + sqrtf(maxf_(0.0f, 1.0f - p1 * p1 - p2 * p2)) * v;
     return normalize(v3(ax * n.x, n.y, ay * n.z));
 }
-SELAS_HD void vndfPdf(V3 wi, V3 wm, V3 wo, float ax, float ay, float& fwd, float& rev) {  // :141-155
+static SELAS_HDN void vndfPdf(V3 wi, V3 wm, V3 wo, float ax, float ay, float& fwd, float& rev) {  // :141-155
     float D = ggxD(wm, ax, ay);
     fwd = smithG1Aniso(wo, ax, ay) * fabsf(dot(wm, wi)) * D / absCosTheta(wi);
     rev = smithG1Aniso(wi, ax, ay) * fabsf(dot(wm, wo)) * D / absCosTheta(wo);
@@ -166,7 +166,7 @@ SELAS_HD V3 sheenTerm(const Surface& s, const DisneyFrame& f, V3 wm, V3 wi) {  /
     return s.sheen * lerp3(v3(1.0f), f.tint, s.sheenTint) * schlickWeight(dotHL);
 }
 
-SELAS_HD V3 disneyFresnel(const Surface& s, const DisneyFrame& f, V3 wo, V3 wm, V3 wi) {  // :122-137
+static SELAS_HDN V3 disneyFresnel(const Surface& s, const DisneyFrame& f, V3 wo, V3 wm, V3 wi) {  // :122-137
     float dotHV = dot(wm, wo);
     V3 R0 = schlickR0(s.relativeIOR) * lerp3(v3(1.0f), f.tint, s.specularTint);
     R0 = lerp3(R0, s.baseColor, s.metallic);
@@ -175,7 +175,7 @@ SELAS_HD V3 disneyFresnel(const Surface& s, const DisneyFrame& f, V3 wo, V3 wm, 
     return lerp3(v3(dielectric), metallic, s.metallic);
 }
 
-SELAS_HD float diffuseTerm(const Surface& s, V3 wo, V3 wm, V3 wi, bool thin) {  // :248-290
+static SELAS_HDN float diffuseTerm(const Surface& s, V3 wo, V3 wm, V3 wi, bool thin) {  // :248-290
     float dotNL = absCosTheta(wi), dotNV = absCosTheta(wo);
     float fl = schlickWeight(dotNL), fv = schlickWeight(dotNV);
     float hk = 0.0f;

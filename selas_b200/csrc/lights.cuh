@@ -47,7 +47,7 @@ struct RectSampler {
     V3 o, x, y, z;
     float z0, z0sq, x0, y0, y0sq, x1, y1, y1sq, b0, b1, b0sq, k, S;
 };
-SELAS_HD void initRectSampler(V3 s, V3 eX, V3 eY, V3 o, RectSampler& r) {
+static SELAS_HDN void initRectSampler(V3 s, V3 eX, V3 eY, V3 o, RectSampler& r) {
     r.o = o;
     float exl = length(eX), eyl = length(eY);
     r.x = eX * (1.0f / exl);
@@ -81,7 +81,7 @@ SELAS_HD void initRectSampler(V3 s, V3 eX, V3 eY, V3 o, RectSampler& r) {
     r.k = 2 * SELAS_PI - g2 - g3;
     r.S = g0 + g1 - r.k;
 }
-SELAS_HD V3 sampleRect(const RectSampler& r, float u, float v) {
+static SELAS_HDN V3 sampleRect(const RectSampler& r, float u, float v) {
     float au = u * r.S + r.k;
     float fu = (cosf(au) * r.b0 - r.b1) / sinf(au);
     float cu = 1 / sqrtf(fu * fu + r.b0sq) * (fu > 0 ? +1 : -1);
@@ -144,7 +144,7 @@ SELAS_HD void nextEventEstimation(Rng& rng, const SelasLight* lights, uint32_t c
     o.index = idx;
 }
 
-SELAS_HD bool rayQuad(V3 o, V3 d, V3 v00, V3 v10, V3 v01, V3 v11) {
+static SELAS_HDN bool rayQuad(V3 o, V3 d, V3 v00, V3 v10, V3 v01, V3 v11) {
     const float eps = 0.00001f;
     V3 e01 = v10 - v00, e03 = v01 - v00;
     V3 p = cross(d, e03);

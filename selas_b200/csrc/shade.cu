@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "disney.cuh"
@@ -178,6 +179,7 @@ int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t str
 // ---------------------------------------------------------------------------------------------------------------
 // wavefront path tracer
 // ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kBinCount = 64;  // material bins of the pre-shade counting sort (63 materials + miss)
 #define FLAG_DELTA_ONLY (1u << 16)
 #define FLAG_IN_MEDIUM (1u << 17)
 
@@ -190,6 +192,8 @@ struct WavefrontBuffers {
     float4* medium[2] = {nullptr, nullptr};
     SelasRay* shadowRays = nullptr;
     float4* shadowPayload = nullptr;
+    uint32_t* order = nullptr;     // material-sorted visiting order of the hit queue
+    uint32_t* bins = nullptr;      // per iteration: 64 counts + 64 cursors
     uint32_t* counters = nullptr;  // 4 per iteration: nextPaths, shadowRays, closestFetch, shadowFetch
     uint32_t counterSlots = 0;
     uint32_t* h_counts = nullptr;  // pinned readback
@@ -209,6 +213,8 @@ void freeWavefront(SelasScene* scene) {
     cudaFree(w->shadowRays);
     cudaFree(w->shadowPayload);
     cudaFree(w->counters);
+    cudaFree(w->order);
+    cudaFree(w->bins);
     if (w->h_counts) cudaFreeHost(w->h_counts);
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
@@ -236,6 +242,8 @@ static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterat
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowRays, sizeof(SelasRay) * (size_t)capacity));
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity));
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->counters, sizeof(uint32_t) * slots));
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->order, sizeof(uint32_t) * (size_t)capacity));
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->bins, sizeof(uint32_t) * 2 * kBinCount * (size_t)(iterations + 2)));
     SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4));
     SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev0));
     SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev1));
@@ -263,12 +271,78 @@ __global__ void generateKernel(SelasCamera cam, uint32_t width, uint32_t height,
     rngFlags[i] = make_uint2(rng.state, FLAG_DELTA_ONLY);
 }
 
+// ---- material binning: counting sort of the hit queue by material (misses last) -------------------------------------
+// The fused shade kernel is large; with paths of many materials in one warp it ran at 6 of 32 lanes on bounce >= 1 and
+// stalled on instruction fetch (profiles/r1a).  Sorting the queue by material makes warps (and neighbouring warps) walk
+// the same code.  Keys: materialIndex (< kBinCount-1), last bin = miss.
+
+SELAS_D uint32_t binOf(const SceneGpu& sc, const SelasHit* hits, uint32_t i) {
+    uint32_t geomID = __ldg(reinterpret_cast<const uint32_t*>(hits + i) + 4);
+    if (geomID == SELAS_INVALID_ID) return kBinCount - 1;
+    uint32_t m = sc.meshes[geomID].materialIndex;
+    return m < kBinCount - 1 ? m : kBinCount - 2;
+}
+
+__global__ void __launch_bounds__(256) binCountKernel(SceneGpu sc, uint32_t n, const SelasHit* __restrict__ hits, uint32_t* __restrict__ bins) {
+    __shared__ uint32_t local[kBinCount];
+    if (threadIdx.x < kBinCount) local[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&local[binOf(sc, hits, i)], 1u);
+    __syncthreads();
+    if (threadIdx.x < kBinCount && local[threadIdx.x]) atomicAdd(bins + threadIdx.x, local[threadIdx.x]);
+}
+
+// one warp: exclusive scan of the 64 bin counts into the cursors
+__global__ void binScanKernel(const uint32_t* __restrict__ bins, uint32_t* __restrict__ cursor) {
+    uint32_t lane = threadIdx.x;
+    uint32_t a = bins[lane], b = bins[lane + 32];
+    uint32_t xa = a, xb = b;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= (uint32_t)o) { xa += ya; xb += yb; }
+    }
+    uint32_t totalA = __shfl_sync(0xffffffffu, xa, 31);
+    cursor[lane] = xa - a;
+    cursor[lane + 32] = totalA + xb - b;
+}
+
+__global__ void __launch_bounds__(256) binScatterKernel(SceneGpu sc, uint32_t n, const SelasHit* __restrict__ hits, uint32_t* __restrict__ cursor,
+                                                        uint32_t* __restrict__ order) {
+    // per-CTA: local histogram -> one global atomic per bin reserves a contiguous range -> ranks inside the CTA
+    __shared__ uint32_t local[kBinCount];
+    __shared__ uint32_t base[kBinCount];
+    const uint32_t tile = blockDim.x * 8;
+    for (uint32_t start = blockIdx.x * tile; start < n; start += gridDim.x * tile) {
+        if (threadIdx.x < kBinCount) local[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t key[8], rank[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t i = start + k * blockDim.x + threadIdx.x;
+            key[k] = 0xFFFFFFFFu;
+            if (i < n) {
+                key[k] = binOf(sc, hits, i);
+                rank[k] = atomicAdd(&local[key[k]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kBinCount) base[threadIdx.x] = local[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, local[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t i = start + k * blockDim.x + threadIdx.x;
+            if (i < n) order[base[key[k]] + rank[k]] = i;
+        }
+        __syncthreads();
+    }
+}
+
 struct ShadeParams {
-    uint32_t maxPathLength, rrStartBounce, layerCount, pixels;
+    uint32_t maxPathLength, rrStartBounce, layerCount, pixels, misMode;
 };
 
 template <bool PTEX>
-__global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ nPtr, uint32_t nMax,
+__global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ order, uint32_t nMax,
                                                    const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                                    const float4* __restrict__ thrPix, const uint2* __restrict__ rngFlags,
                                                    const float4* __restrict__ mediumIn, SelasRay* __restrict__ raysOut,
@@ -276,8 +350,10 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
                                                    float4* __restrict__ mediumOut, SelasRay* __restrict__ shadowRays,
                                                    float4* __restrict__ shadowPayload, uint32_t* __restrict__ counters,
                                                    float* __restrict__ film) {
-    const uint32_t n = nPtr ? min(nMax, *nPtr) : nMax;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = nMax;
+    const uint32_t slotIndex = blockIdx.x * blockDim.x + threadIdx.x;
+    // material-sorted visiting order (binScatterKernel): lanes of a warp share a material, hence code path
+    const uint32_t i = (order && slotIndex < n) ? __ldg(order + slotIndex) : slotIndex;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ltMask = (1u << lane) - 1u;
     bool alive = false, wantShadow = false;
@@ -288,7 +364,7 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
     SelasRay shRay;
     float4 shPayload = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    if (i < n) {
+    if (slotIndex < n) {
         const float4* rp = reinterpret_cast<const float4*>(rays + i);
         float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
         const uint4* hp = reinterpret_cast<const uint4*>(hits + i);
@@ -363,7 +439,11 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
                         medium.extinction = v3(0.0f);
                     }
                 }
-                float weight = 1.0f;  // QUIRK :214-216: MIS weight forced to 1
+                float weight = 1.0f;  // QUIRK :214-216: MIS weight forced to 1 (misMode 0 = reference)
+                if (prm.misMode == 1) {  // the balance heuristic the reference computes and discards (ImportanceSampling.cpp:19-22)
+                    float lightPdfW = lightingPdf(lights, lightCount, ls.index, s.position, bs.wi);
+                    weight = bs.forwardPdfW / (bs.forwardPdfW + lightPdfW);
+                }
                 thr = weight * thr * bs.reflectance;
                 V3 no = offsetRayOrigin(s, bs.wi, 1.0f);
                 o = no;
@@ -483,9 +563,9 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         setError(ctx, "render settings out of range (width/height > 0, layerCount 1..2, maxPathLength <= 65535)");
         return SELAS_ERR_ARGUMENT;
     }
-    if (rs.misMode != 0) {
-        setError(ctx, "misMode %u not implemented (0 = reference weighting)", rs.misMode);
-        return SELAS_ERR_UNSUPPORTED;
+    if (rs.misMode > 1) {
+        setError(ctx, "misMode %u unknown (0 = reference weighting, 1 = balance heuristic)", rs.misMode);
+        return SELAS_ERR_ARGUMENT;
     }
     const uint32_t pixels = rs.width * rs.height;
     const uint32_t stride = rs.pixelStride > 1 ? rs.pixelStride : 1u;
@@ -503,7 +583,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     int rc = ensureWavefront(scene, capacity, rs.maxPathLength);
     if (rc) return rc;
     WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
-    ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels};
+    ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels, rs.misMode};
     const bool counting = (rs.flags & SELAS_RENDER_COUNT_TRAVERSAL) != 0;
     unsigned long long* d_totals = nullptr;
     if (counting) {
@@ -511,11 +591,14 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_totals, 0, 4 * sizeof(unsigned long long), stream));
     }
     KernelTimers timers;
+    // tuning knob: first bounce whose hit queue is sorted by material before shading (SELAS_SORT_FROM_BOUNCE, default 0)
+    static const uint32_t sortFromBounce = getenv("SELAS_SORT_FROM_BOUNCE") ? (uint32_t)atoi(getenv("SELAS_SORT_FROM_BOUNCE")) : 0u;
 
     cudaEventRecord(w->ev0, stream);
     for (uint64_t first = 0; first < totalPaths; first += capacity) {
         uint32_t count = (uint32_t)std::min<uint64_t>(capacity, totalPaths - first);
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
+        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->bins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)(rs.maxPathLength + 2), stream));
         size_t t0 = timers.begin(stream);
         generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, activePixels,
                                                               stride, w->rays[0], w->thrPix[0], w->rngFlags[0]);
@@ -532,13 +615,23 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             timers.end(1, t0, stream);
             st.closestRays += n;
             t0 = timers.begin(stream);
+            const uint32_t* order = nullptr;
+            if (it >= sortFromBounce && n >= 4096) {
+                uint32_t* bins = w->bins + 2 * kBinCount * (size_t)it;
+                int grid = (int)std::min<uint32_t>(divUp(n, 2048), (uint32_t)ctx->smCount * 8);
+                binCountKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, w->hits, bins);
+                binScanKernel<<<1, 32, 0, stream>>>(bins, bins + kBinCount);
+                binScatterKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, w->hits, bins + kBinCount, w->order);
+                order = w->order;
+                st.kernelLaunches += 3;
+            }
             if (scene->usesPtex)
-                shadeKernel<true><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, nullptr, n, w->rays[cur], w->hits, w->thrPix[cur],
+                shadeKernel<true><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur],
                                                                       w->rngFlags[cur], w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1],
                                                                       w->rngFlags[cur ^ 1], w->medium[cur ^ 1], w->shadowRays, w->shadowPayload,
                                                                       ctr, d_film);
             else
-                shadeKernel<false><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, nullptr, n, w->rays[cur], w->hits, w->thrPix[cur],
+                shadeKernel<false><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur],
                                                                        w->rngFlags[cur], w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1],
                                                                        w->rngFlags[cur ^ 1], w->medium[cur ^ 1], w->shadowRays, w->shadowPayload,
                                                                        ctr, d_film);

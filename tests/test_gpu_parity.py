@@ -274,6 +274,25 @@ def test_render_small_scene_matches_oracle(ctx, oracle):
     sc.close()
 
 
+def test_render_mis_balance_mode(ctx, oracle):
+    """misMode 1: the balance-heuristic weight the reference computes and then overrides (PathTracer.cpp:214-216)."""
+    data = inputs.small_scene()
+    cam = capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 64, 48)
+    rs = capi.render_settings(64, 48, 16, max_path_length=6, rr_start=8, layers=1, seed=4, mis_mode=1)
+    sc, hs = capi.Scene(ctx, data), oracle.scene_create(data)
+    g = sc.render(cam, rs)[0][0] / 16.0
+    o = oracle.render(hs, cam, rs, nthreads=8)[0][0] / 16.0
+    fin = np.isfinite(o).all(axis=2)
+    assert np.array_equal(fin, np.isfinite(g).all(axis=2))  # 0/0 weights (pdf 0) are NaN on both sides
+    assert abs(g[fin].mean() / o[fin].mean() - 1.0) < 3e-3 and _relmse(g[fin], o[fin]) < 3e-3
+    plain = sc.render(cam, capi.render_settings(64, 48, 16, 6, 8, 1, seed=4))[0][0] / 16.0
+    assert g[fin].mean() < plain[fin].mean()  # weights <= 1 only remove energy in this estimator
+    with pytest.raises(capi.SelasError):
+        sc.render(cam, capi.render_settings(8, 8, 1, mis_mode=7))
+    oracle.scene_destroy(hs)
+    sc.close()
+
+
 def test_render_cornell_config1_reduced(ctx, oracle):
     """Config 1 (Cornell, Disney diffuse + copper) at 128x128, 16 spp, depth 8 against the oracle, plus the noise-floor
     criterion of SURVEY.md 8(d): relMSE(gpu, ref-hi) <= 1.5 x relMSE(oracle, ref-hi) with an independent seed."""
