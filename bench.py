@@ -290,9 +290,14 @@ def main():
     e2e_step(-1)
     barrier()
     t0 = time.perf_counter()
+    e2e_each = []
     for i in range(e2e_steps):
+        t1 = time.perf_counter()
         e2e_step(i)
+        e2e_each.append((time.perf_counter() - t1) * 1e3)
     barrier()
+    if rank == 0:
+        log("e2e per-step ms:", [round(x, 2) for x in e2e_each], "device ms of last:", round(stats.renderMs, 2))
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)

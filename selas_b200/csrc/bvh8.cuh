@@ -16,6 +16,8 @@
 //
 // Algorithmic bytes per ray: 32 in + 32 out + 80 per visited node + 48 per tested triangle.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "../../include/selas_cuda.h"
 #include "vec.cuh"
 
@@ -43,6 +45,21 @@ struct TraceResult {
     uint32_t tri;  // index into tris, 0xFFFFFFFF = none
 };
 
+// Quantised plane byte -> float without the conversion (XU) pipe.  The first version used (float)byte = I2F.U8, 48 per
+// node, and ncu showed the XU pipe as the busiest unit of the kernel (65 % of peak, profiles/r1a).  Here two bytes at a
+// time are dropped into the mantissas of a half2 holding {1024, 1024} (one PRMT): 0x6400 | b == 1024 + b exactly; the
+// half -> float step is an HADD2.F32 on the FMA pipe, and the -1024 is folded into the plane offset (o - 1024 s), whose
+// rounding error is 2^-14 of a quantisation step, far inside the builder's 1e-3-step slack.
+SELAS_D void bytesToBiasedFloats(uint32_t w, float& f0, float& f1, float& f2, float& f3) {
+    uint32_t lo = __byte_perm(w, 0x64646464u, 0x4140);  // {b0, 0x64, b1, 0x64}
+    uint32_t hi = __byte_perm(w, 0x64646464u, 0x4342);  // {b2, 0x64, b3, 0x64}
+    __half2 hl = *reinterpret_cast<__half2*>(&lo), hh = *reinterpret_cast<__half2*>(&hi);
+    f0 = __low2float(hl);
+    f1 = __high2float(hl);
+    f2 = __low2float(hh);
+    f3 = __high2float(hh);
+}
+
 // Ray-vs-8-children slab test on the quantised boxes; returns the hit mask in traversal-bit order.
 SELAS_D uint32_t intersectNode(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, V3 o,
                                V3 idir, bool negx, bool negy, bool negz, uint32_t octInv4, float tmin, float tmax) {
@@ -50,7 +67,9 @@ SELAS_D uint32_t intersectNode(const float4 n0, const float4 n1, const float4 n2
     float sx = __uint_as_float(extractByte(eimask, 0) << 23) * idir.x;
     float sy = __uint_as_float(extractByte(eimask, 1) << 23) * idir.y;
     float sz = __uint_as_float(extractByte(eimask, 2) << 23) * idir.z;
-    float ox = (n0.x - o.x) * idir.x, oy = (n0.y - o.y) * idir.y, oz = (n0.z - o.z) * idir.z;
+    // plane t = (origin + q*scale - o) * idir = q*s + ox, with q delivered as 1024 + q
+    float ox = fmaf(-1024.0f, sx, (n0.x - o.x) * idir.x), oy = fmaf(-1024.0f, sy, (n0.y - o.y) * idir.y),
+          oz = fmaf(-1024.0f, sz, (n0.z - o.z) * idir.z);
     uint32_t hitMask = 0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -65,11 +84,18 @@ SELAS_D uint32_t intersectNode(const float4 n0, const float4 n1, const float4 n2
         uint32_t xmin = negx ? qhix : qlox, xmax = negx ? qlox : qhix;
         uint32_t ymin = negy ? qhiy : qloy, ymax = negy ? qloy : qhiy;
         uint32_t zmin = negz ? qhiz : qloz, zmax = negz ? qloz : qhiz;
+        float x0[4], x1[4], y0[4], y1[4], z0[4], z1[4];
+        bytesToBiasedFloats(xmin, x0[0], x0[1], x0[2], x0[3]);
+        bytesToBiasedFloats(xmax, x1[0], x1[1], x1[2], x1[3]);
+        bytesToBiasedFloats(ymin, y0[0], y0[1], y0[2], y0[3]);
+        bytesToBiasedFloats(ymax, y1[0], y1[1], y1[2], y1[3]);
+        bytesToBiasedFloats(zmin, z0[0], z0[1], z0[2], z0[3]);
+        bytesToBiasedFloats(zmax, z1[0], z1[1], z1[2], z1[3]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float tx0 = fmaf((float)extractByte(xmin, j), sx, ox), tx1 = fmaf((float)extractByte(xmax, j), sx, ox);
-            float ty0 = fmaf((float)extractByte(ymin, j), sy, oy), ty1 = fmaf((float)extractByte(ymax, j), sy, oy);
-            float tz0 = fmaf((float)extractByte(zmin, j), sz, oz), tz1 = fmaf((float)extractByte(zmax, j), sz, oz);
+            float tx0 = fmaf(x0[j], sx, ox), tx1 = fmaf(x1[j], sx, ox);
+            float ty0 = fmaf(y0[j], sy, oy), ty1 = fmaf(y1[j], sy, oy);
+            float tz0 = fmaf(z0[j], sz, oz), tz1 = fmaf(z1[j], sz, oz);
             float t0 = fmaxMax(tx0, ty0, fmaxf(tz0, tmin));
             float t1 = fminMin(tx1, ty1, fminf(tz1, tmax));
             if (t0 <= t1) {

@@ -90,7 +90,7 @@ struct PtexKernel {
     SELAS_D float kuc(int i) const { return kub[ku0 + i]; }
     SELAS_D float kvc(int i) const { return kvb[kv0 + i]; }
 
-    SELAS_D void set(int ul, int vl, int u_, int v_, int uw_, int vw_, const float* kuSrc, const float* kvSrc, int rot_) {
+    __device__ __noinline__ void set(int ul, int vl, int u_, int v_, int uw_, int vw_, const float* kuSrc, const float* kvSrc, int rot_) {
         ulog2 = ul; vlog2 = vl; u = u_; v = v_; uw = uw_; vw = vw_;
         for (int i = 0; i < uw_; ++i) kub[i] = kuSrc[i];
         for (int i = 0; i < vw_; ++i) kvb[i] = kvSrc[i];
@@ -105,37 +105,37 @@ struct PtexKernel {
     }
     SELAS_D float weight() const { return accumulate(kub + ku0, uw) * accumulate(kvb + kv0, vw); }
 
-    SELAS_D void stripZeros() {  // :97-104
+    __device__ __noinline__ void stripZeros() {  // :97-104
         while (ku(0) == 0) { ku0++; u++; uw--; }
         while (ku(uw - 1) == 0) { uw--; }
         while (kv(0) == 0) { kv0++; v++; vw--; }
         while (kv(vw - 1) == 0) { vw--; }
     }
     // merge*: fold the part hanging over a border without neighbour back onto the edge texel (:111-147)
-    SELAS_D void mergeL(int mode) {
+    __device__ __noinline__ void mergeL(int mode) {
         int w = -u;
         if (mode != 1) ku(w) += accumulate(kub + ku0, w);
         ku0 += w; uw -= w; u = 0;
     }
-    SELAS_D void mergeR(int mode) {
+    __device__ __noinline__ void mergeR(int mode) {
         int w = uw + u - resu();
         int kp = uw - w;
         if (mode != 1) ku(kp - 1) += accumulate(kub + ku0 + kp, w);
         uw -= w;
     }
-    SELAS_D void mergeB(int mode) {
+    __device__ __noinline__ void mergeB(int mode) {
         int w = -v;
         if (mode != 1) kv(w) += accumulate(kvb + kv0, w);
         kv0 += w; vw -= w; v = 0;
     }
-    SELAS_D void mergeT(int mode) {
+    __device__ __noinline__ void mergeT(int mode) {
         int w = vw + v - resv();
         int kp = vw - w;
         if (mode != 1) kv(kp - 1) += accumulate(kvb + kv0 + kp, w);
         vw -= w;
     }
     // split*: cut the overhanging piece off into k (:149-237)
-    SELAS_D void splitL(PtexKernel& k) {
+    __device__ __noinline__ void splitL(PtexKernel& k) {
         int w = -u;
         if (w < uw) {
             k.set(ulog2, vlog2, resu() - w, v, w, vw, kub + ku0, kvb + kv0, 0);
@@ -146,7 +146,7 @@ struct PtexKernel {
             u = 0; uw = 0;
         }
     }
-    SELAS_D void splitR(PtexKernel& k) {
+    __device__ __noinline__ void splitR(PtexKernel& k) {
         int w = u + uw - resu();
         if (w < uw) {
             k.set(ulog2, vlog2, 0, v, w, vw, kub + ku0 + uw - w, kvb + kv0, 0);
@@ -157,7 +157,7 @@ struct PtexKernel {
             u = 0; uw = 0;
         }
     }
-    SELAS_D void splitB(PtexKernel& k) {
+    __device__ __noinline__ void splitB(PtexKernel& k) {
         int w = -v;
         if (w < vw) {
             k.set(ulog2, vlog2, u, resv() - w, uw, w, kub + ku0, kvb + kv0, 0);
@@ -168,7 +168,7 @@ struct PtexKernel {
             v = 0; vw = 0;
         }
     }
-    SELAS_D void splitT(PtexKernel& k) {
+    __device__ __noinline__ void splitT(PtexKernel& k) {
         int w = v + vw - resv();
         if (w < vw) {
             k.set(ulog2, vlog2, u, 0, uw, w, kub + ku0, kvb + kv0 + vw - w, 0);
@@ -179,15 +179,15 @@ struct PtexKernel {
             v = 0; vw = 0;
         }
     }
-    SELAS_D void flipU() {
+    __device__ __noinline__ void flipU() {
         u = resu() - u - uw;
         for (int i = 0; i < uw / 2; ++i) { float t = ku(i); ku(i) = ku(uw - 1 - i); ku(uw - 1 - i) = t; }
     }
-    SELAS_D void flipV() {
+    __device__ __noinline__ void flipV() {
         v = resv() - v - vw;
         for (int i = 0; i < vw / 2; ++i) { float t = kv(i); kv(i) = kv(vw - 1 - i); kv(vw - 1 - i) = t; }
     }
-    SELAS_D void swapUV() {
+    __device__ __noinline__ void swapUV() {
         const int oldUw = uw, oldVw = vw;
         float tmpU[PTEX_KMAX], tmpV[PTEX_KMAX];
         for (int i = 0; i < oldUw; ++i) tmpU[i] = kub[ku0 + i];
@@ -199,7 +199,7 @@ struct PtexKernel {
         t = u; u = v; v = t;
         uw = oldVw; vw = oldUw;
     }
-    SELAS_D void rotate(int r) {  // :260-270, 'r' steps counter-clockwise
+    __device__ __noinline__ void rotate(int r) {  // :260-270, 'r' steps counter-clockwise
         switch (r & 3) {
             default: return;
             case 1: flipU(); swapUV(); break;
@@ -214,7 +214,7 @@ struct PtexKernel {
     SELAS_D void compactV() {
         if (kv0) { for (int i = 0; i < vw; ++i) kvb[i] = kvb[kv0 + i]; kv0 = 0; }
     }
-    SELAS_D void downresU() {  // :313-339
+    __device__ __noinline__ void downresU() {  // :313-339
         int src = 0, dst = 0;
         if (u & 1) { dst++; src++; uw--; }
         for (int i = uw / 2; i > 0; i--) { ku(dst++) = ku(src) + ku(src + 1); src += 2; }
@@ -223,7 +223,7 @@ struct PtexKernel {
         uw = dst;
         ulog2--;
     }
-    SELAS_D void downresV() {
+    __device__ __noinline__ void downresV() {
         int src = 0, dst = 0;
         if (v & 1) { dst++; src++; vw--; }
         for (int i = vw / 2; i > 0; i--) { kv(dst++) = kv(src) + kv(src + 1); src += 2; }
@@ -232,17 +232,17 @@ struct PtexKernel {
         vw = dst;
         vlog2--;
     }
-    SELAS_D void upresU() {  // :369-379 (only reached with uw <= 5: the result fits the buffer)
+    __device__ __noinline__ void upresU() {  // :369-379 (only reached with uw <= 5: the result fits the buffer)
         compactU();
         for (int i = uw - 1; i >= 0; --i) { float h = kub[i] / 2; kub[2 * i] = h; kub[2 * i + 1] = h; }
         uw *= 2; u *= 2; ulog2++;
     }
-    SELAS_D void upresV() {
+    __device__ __noinline__ void upresV() {
         compactV();
         for (int i = vw - 1; i >= 0; --i) { float h = kvb[i] / 2; kvb[2 * i] = h; kvb[2 * i + 1] = h; }
         vw *= 2; v *= 2; vlog2++;
     }
-    SELAS_D bool adjustMainToSubface(int eid) {  // :272-303
+    __device__ __noinline__ bool adjustMainToSubface(int eid) {  // :272-303
         if (ulog2 == 0) upresU();
         if (vlog2 == 0) upresV();
         if (ulog2 > 0) ulog2--;
@@ -266,7 +266,7 @@ struct PtexKernel {
         }
         ulog2++; vlog2++;
     }
-    SELAS_D float makeSymmetric(float initialWeight) {  // :397-455
+    __device__ __noinline__ float makeSymmetric(float initialWeight) {  // :397-455
         if (ulog2 > vlog2) { do { downresU(); } while (ulog2 > vlog2); }
         else if (vlog2 > ulog2) { do { downresV(); } while (vlog2 > ulog2); }
         uw = vw = (uw < vw ? uw : vw);
@@ -311,7 +311,7 @@ SELAS_D void ptexApplyConst(const PtexGpu& tx, PtexEvalState& st, const uint8_t*
 }
 
 // PtexSeparableFilter::apply, :348-401
-SELAS_D void ptexApply(const PtexGpu& tx, PtexEvalState& st, PtexKernel& k, int faceid, const PtexFace& f) {
+static __device__ __noinline__ void ptexApply(const PtexGpu& tx, PtexEvalState& st, PtexKernel& k, int faceid, const PtexFace& f) {
     if (k.uw <= 0 || k.vw <= 0) return;
     while (k.ulog2 > f.ulog2) k.downresU();
     while (k.vlog2 > f.vlog2) k.downresV();
@@ -364,7 +364,7 @@ SELAS_D float ptexBlur(float x) {  // PtexFilters.cpp:133-139
 }
 
 // PtexWidth4Filter::buildKernelAxis with options.lerp == false (PtexFilters.cpp:141-248)
-SELAS_D void ptexBuildKernelAxis(int& kReslog2, int& kU, int& kUw, float* ku, float u, float uw, int fReslog2) {
+static __device__ __noinline__ void ptexBuildKernelAxis(int& kReslog2, int& kU, int& kUw, float* ku, float u, float uw, int fReslog2) {
     float minw = __uint_as_float((uint32_t)(127 - fReslog2) << 23);  // reciprocalPow2
     uw = uw > minw ? uw : minw;                                       // PtexUtils::max(uw, 1/res)
     kReslog2 = 127 - (int)((__float_as_uint(uw) >> 23) & 0xff);      // calcResFromWidth
@@ -438,7 +438,7 @@ struct PtexWorkList {
 };
 
 // PtexSeparableFilter::applyToCornerFace, :333-345
-SELAS_D void ptexApplyToCornerFace(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, const PtexFace& f, int eid,
+static __device__ __noinline__ void ptexApplyToCornerFace(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, const PtexFace& f, int eid,
                                    int cfid, const PtexFace& cf, int ceid) {
     bool fIsSubface = f.isSubface(), cfIsSubface = cf.isSubface();
     if (fIsSubface != cfIsSubface) {
@@ -451,7 +451,7 @@ SELAS_D void ptexApplyToCornerFace(const PtexGpu& tx, PtexEvalState& st, PtexWor
 }
 
 // PtexSeparableFilter::applyToCorner, :257-330
-SELAS_D void ptexApplyToCorner(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f,
+static __device__ __noinline__ void ptexApplyToCorner(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f,
                                int eid) {
     int afid = faceid, aeid = eid;
     PtexFace af = f;
@@ -505,7 +505,7 @@ SELAS_D void ptexApplyToCorner(const PtexGpu& tx, PtexEvalState& st, PtexWorkLis
 }
 
 // PtexSeparableFilter::applyAcrossEdge, :215-255
-SELAS_D void ptexApplyAcrossEdge(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f,
+static __device__ __noinline__ void ptexApplyAcrossEdge(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f,
                                  int eid) {
     int afid = f.adjface(eid), aeid = f.adjedge(eid);
     PtexFace af = ptexLoadFace(tx, afid);
@@ -533,7 +533,7 @@ SELAS_D void ptexApplyAcrossEdge(const PtexGpu& tx, PtexEvalState& st, PtexWorkL
 }
 
 // PtexSeparableFilter::splitAndApply, :135-213 (noedgeblend = false)
-SELAS_D void ptexSplitAndApply(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f) {
+static __device__ __noinline__ void ptexSplitAndApply(const PtexGpu& tx, PtexEvalState& st, PtexWorkList& wl, PtexKernel& k, int faceid, const PtexFace& f) {
     bool splitR = (k.u + k.uw > k.resu()), splitL = (k.u < 0);
     bool splitT = (k.v + k.vw > k.resv()), splitB = (k.v < 0);
     if (splitR || splitL || splitT || splitB) {

@@ -373,9 +373,8 @@ def ptex_quad_grid(nu=1581, nv=1581, ptex=None, seed=4):
     pos = np.stack([X, Z, Y], axis=-1).astype(np.float32).reshape(-1, 3)
     jj, ii = np.meshgrid(np.arange(nv), np.arange(nu), indexing="ij")
     v0 = (jj * (nu + 1) + ii).astype(np.uint32)
-    # (u along +x = i, v along +z = j); CCW seen from +y is v0, v0+row, v0+row+1, v0+1 -> but ptex u must run along
-    # edge 0 (v0->v1).  Keep u = i direction: v0 -> v0+1 -> v0+row+1 -> v0+row faces -y, so the camera looks from below
-    # ... simpler: keep u along i and accept the face normal; shading uses abs/cos of either side for diffuse.
+    # Ptex u runs along edge 0 (v0 -> v1) = +x = i, v along +z = j, so (u, v) of a hit and the face id j*nu + i line up with
+    # the grid adjacency of the .ptx; with this winding the geometric normal is -y: camera and light sit below the sheet.
     quads = np.stack([v0, v0 + np.uint32(1), v0 + np.uint32(nu + 2), v0 + np.uint32(nu + 1)], axis=-1).reshape(-1, 4)
     mats = np.array([material(shaderName="DisneySolid", baseColor=[0.6, 0.6, 0.6], metallic=0.0, roughness=0.8,
                               usesPtex=ptex is not None)])
