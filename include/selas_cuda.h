@@ -191,7 +191,9 @@ typedef struct SelasSceneDesc {
 
 /* Compile-time macros of the reference integrator made runtime (PathTracer.cpp:42-46, :248). */
 /* SelasRenderSettings.flags */
-enum { SELAS_RENDER_COUNT_TRAVERSAL = 1 /* use the counting build of the trace kernels and fill the node/triangle totals */ };
+enum { SELAS_RENDER_COUNT_TRAVERSAL = 1, /* use the counting build of the trace kernels and fill the node/triangle totals */
+       SELAS_RENDER_SKIP_NONFINITE = 2   /* drop NaN/Inf radiance contributions instead of adding them to the film; off = reference behaviour
+                                            (the reference checks for NaNs only in debug builds, BasicTypes.h:28) */ };
 
 typedef struct SelasRenderSettings {
     uint32_t width, height;

@@ -23,7 +23,8 @@ from tests import oracle_binding  # noqa: E402
 
 
 def relmse(a, b):
-    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+    ok = np.isfinite(a).all(axis=2) & np.isfinite(b).all(axis=2)  # the reference adds NaN/Inf samples to the film like any other
+    return float(np.mean((a[ok] - b[ok]) ** 2 / (b[ok] ** 2 + 1e-2)))
 
 
 def config1(ctx):
@@ -54,6 +55,7 @@ def config1(ctx):
                    "ray_cast": "oracle scalar SAH-BVH2 (Embree absent)"},
            "image_parity": {"relMSE_gpu_vs_cpu_same_seed": relmse(g, c), "mean_ratio_gpu_over_cpu": float(g.mean() / c.mean()),
                             "relMSE_gpu_vs_1024spp": relmse(g, ref_hi), "relMSE_cpu_vs_1024spp": relmse(c, ref_hi),
+                            "nonfinite_pixels_gpu_cpu_1024spp": [int((~np.isfinite(x).all(axis=2)).sum()) for x in (g, c, ref_hi)],
                             "fraction_pixels_within_1e-3": float(np.isclose(g, c, rtol=1e-3, atol=1e-4).all(axis=2).mean())}}
     sc.close()
     return out
@@ -94,7 +96,8 @@ def config4(ctx, grid, spp):
     out = {"quads": grid * grid, "triangles": data.triangle_count(), "ptex_file_mb": tmp.stat().st_size / 1e6, "ptex_write_s": write_s,
            "ptex_load_s": load_s, "spp": passes * 4, "paths": paths, "gpu_device_ms": tot_ms, "gpu_samples_per_s": paths / (tot_ms * 1e-3),
            "gpu_e2e_samples_per_s": paths / e2e_s, "gpu_rays": int(rays), "shade_ms_per_4spp_pass": shade_ms / passes,
-           "mean_radiance": float(film[0].mean() / 4.0),
+           "mean_radiance_finite_pixels": float(film[0][np.isfinite(film[0]).all(axis=2)].mean() / 4.0),
+           "nonfinite_pixels_last_pass": int((~np.isfinite(film[0]).all(axis=2)).sum()),
            "without_ptex": {"gpu_device_ms_per_4spp_pass": st2.renderMs, "shade_ms_per_4spp_pass": st2.shadeMs,
                             "gpu_samples_per_s": st2.pathSamples / (st2.renderMs * 1e-3)},
            "cpu": "Ptex lookups/s of the reference's PtexFilter are in scripts/bench_rows.py (ptex_lookup.cpu); the tier-B CPU integrator "

@@ -417,6 +417,7 @@ class Scene:
 
 
 RENDER_COUNT_TRAVERSAL = 1
+RENDER_SKIP_NONFINITE = 2
 
 
 def render_settings(width, height, spp, max_path_length=8, rr_start=8, layers=1, seed=1, first_sample=0, mis_mode=0,

@@ -360,15 +360,22 @@ struct Loader {
     }
 };
 
-__global__ void ptexEvalKernel(const PtexGpu* __restrict__ tex, size_t n, const int32_t* __restrict__ faceid, const float* __restrict__ u,
-                               const float* __restrict__ v, float* __restrict__ rgb) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float out[3];
-    ptexEvalBspline(tex, faceid[i], u[i], v[i], out);
-    rgb[3 * i] = out[0];
-    rgb[3 * i + 1] = out[1];
-    rgb[3 * i + 2] = out[2];
+__global__ void __launch_bounds__(128) ptexEvalKernel(const PtexGpu* __restrict__ tex, size_t n, const int32_t* __restrict__ faceid,
+                                                      const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ rgb) {
+    ptexTileEval<128, 8>(
+        n,
+        [&](size_t i, const PtexGpu*& t, int& f, float& uu, float& vv) {
+            t = tex;
+            f = faceid[i];
+            uu = u[i];
+            vv = v[i];
+            return true;
+        },
+        [&](size_t i, const float* c) {
+            rgb[3 * i] = c[0];
+            rgb[3 * i + 1] = c[1];
+            rgb[3 * i + 2] = c[2];
+        });
 }
 
 template <typename T>
@@ -598,7 +605,8 @@ int selas_cuda_ptex_eval_device(SelasPtex* tex, size_t n, const int32_t* d_facei
         return SELAS_ERR_ARGUMENT;
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    ptexEvalKernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(tex->d_self, n, d_faceid, d_u, d_v, d_rgb3);
+    unsigned grid = (unsigned)std::min<size_t>((n + 1023) / 1024, (size_t)ctx->smCount * 8);
+    ptexEvalKernel<<<grid, 128, 0, st>>>(tex->d_self, n, d_faceid, d_u, d_v, d_rgb3);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }

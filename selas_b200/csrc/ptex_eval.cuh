@@ -578,27 +578,214 @@ static __device__ __noinline__ void ptexSplitAndApply(const PtexGpu& tx, PtexEva
     ptexApply(tx, st, k, faceid, f);
 }
 
-// PtexSeparableFilter::eval, :47-132, with firstChan 0, nChannels 3, all widths 0, width 1, blur 0.
-// Channels the texture does not have are returned as 0 (the reference leaves them uninitialised).
-static __device__ __noinline__ void ptexEvalBspline(const PtexGpu* texPtr, int faceid, float u, float v, float* rgb) {
-    const PtexGpu tx = *texPtr;
-    rgb[0] = rgb[1] = rgb[2] = 0.f;
-    if (faceid < 0 || faceid >= tx.numFaces) return;
-    PtexEvalState st;
-    st.nchan = tx.nchan < 3 ? tx.nchan : 3;
-    st.result[0] = st.result[1] = st.result[2] = 0.f;
-    const float oneValueInv = tx.dataType == 0 ? 1.f / 255.f : (tx.dataType == 1 ? 1.f / 65535.f : 1.f);
-    const float oneValue = tx.dataType == 0 ? 255.f : (tx.dataType == 1 ? 65535.f : 1.f);
-    PtexFace f = ptexLoadFace(tx, faceid);
-    if (f.flags & kPtexFlagNbConstant) {  // :62-69, ConvertToFloat of the face's constant pixel
+
+// ---------------------------------------------------------------------------------------------------------------
+// Register-resident fast path.  The general evaluator above keeps its kernels in local memory (dynamic indexing of the
+// weight windows); measured at 1.1 G lookups/s it is far from the 104-B/lookup roofline.  The overwhelmingly common
+// cases -- a 4x4 kernel that stays inside its face, or crosses exactly one edge onto an ordinary neighbour of matching
+// resolution (or onto the mesh border) -- are handled here with compile-time indexed 4-element arrays.  Every sum is
+// formed in the same order as the general path, so the two agree bit for bit; anything else (corners, subfaces,
+// resolution mismatch, faces below 8 texels, kernels that are not 4 wide) returns false and takes the general path.
+// ---------------------------------------------------------------------------------------------------------------
+struct PtexPiece {  // a (sub)kernel: window origin, extent and weights compacted to index 0
+    int u, v, uw, vw;
+    float ku[4], kv[4];
+};
+
+SELAS_D void ptexReverse4(float* k, int n) {
+    if (n == 2) { float t = k[0]; k[0] = k[1]; k[1] = t; }
+    else if (n == 3) { float t = k[0]; k[0] = k[2]; k[2] = t; }
+    else if (n == 4) { float t = k[0]; k[0] = k[3]; k[3] = t; t = k[1]; k[1] = k[2]; k[2] = t; }
+}
+// PtexSeparableKernel::rotate on a piece (resu/resv = resolution the piece currently lives in)
+SELAS_D void ptexRotatePiece(PtexPiece& p, int rot, int& ulog2, int& vlog2) {
+    rot &= 3;
+    if (rot == 0) return;
+    if (rot == 1 || rot == 2) {  // flipU
+        p.u = (1 << ulog2) - p.u - p.uw;
+        ptexReverse4(p.ku, p.uw);
+    }
+    if (rot == 2 || rot == 3) {  // flipV
+        p.v = (1 << vlog2) - p.v - p.vw;
+        ptexReverse4(p.kv, p.vw);
+    }
+    if (rot == 1 || rot == 3) {  // swapUV
+        int t = ulog2; ulog2 = vlog2; vlog2 = t;
+        t = p.u; p.u = p.v; p.v = t;
+        t = p.uw; p.uw = p.vw; p.vw = t;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float w = p.ku[i]; p.ku[i] = p.kv[i]; p.kv[i] = w; }
+    }
+}
+SELAS_D float ptexPick4(const float* k, int i) { return i == 0 ? k[0] : (i == 1 ? k[1] : (i == 2 ? k[2] : k[3])); }
+// k'[i] = k[i + w] (0 past the end): the "ku += w" of the library on a register array
+SELAS_D void ptexShift4(float* k, int w) {
+    float t0 = ptexPick4(k, w), t1 = w + 1 < 4 ? ptexPick4(k, w + 1) : 0.f, t2 = w + 2 < 4 ? ptexPick4(k, w + 2) : 0.f;
+    float t3 = w + 3 < 4 ? ptexPick4(k, w + 3) : 0.f;
+    k[0] = t0; k[1] = t1; k[2] = t2; k[3] = t3;
+}
+SELAS_D float ptexSum4(const float* k, int n) {  // accumulate(): sequential from 0
+    float r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (i < n) r += k[i];
+    return r;
+}
+// PtexSeparableKernel::Apply on native-resolution data of a face (or applyConst for a constant face)
+SELAS_D void ptexApplyPiece(const PtexGpu& tx, const PtexFace& f, int faceid, const PtexPiece& p, int nchan, float* result) {
+    if (p.uw <= 0 || p.vw <= 0) return;
+    if (f.isConstant()) {
+        float w = ptexSum4(p.ku, p.uw) * ptexSum4(p.kv, p.vw);
         const uint8_t* px = tx.constData + (size_t)faceid * tx.pixelSize;
-        for (int c = 0; c < st.nchan; ++c) {
+        for (int c = 0; c < nchan; ++c) result[c] += ptexTexel(px, tx.dataType, c) * w;
+        return;
+    }
+    const uint8_t* data = tx.texels + (size_t)f.dataOffset16 * 16;
+    const int resu = 1 << f.ulog2, nt = tx.nchan;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+        if (y < p.vw) {
+            float row[3] = {0.f, 0.f, 0.f};
+            size_t rowBase = ((size_t)(p.v + y) * resu + p.u) * nt;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                if (x < p.uw) {
+                    float w = p.ku[x];
+                    for (int c = 0; c < nchan; ++c) {
+                        float t = ptexTexel(data, tx.dataType, rowBase + (size_t)x * nt + c);
+                        row[c] = (x == 0) ? t * w : row[c] + t * w;
+                    }
+                }
+            }
+            float wv = p.kv[y];
+            for (int c = 0; c < nchan; ++c) result[c] += row[c] * wv;
+        }
+    }
+}
+
+// One axis of the kernel for a face of >= 8 texels at filter width 0: four b-spline weights starting at texel k0.
+SELAS_D bool ptexFastAxis(float u, int reslog2, int& k0, int& kw, float* k) {
+    const float uw = __uint_as_float((uint32_t)(127 - reslog2) << 23);
+    const float resf = (float)(1 << reslog2);
+    float upix = u * resf - 0.5f;
+    float uwpix = uw * resf;  // == 1
+    float dupix = 2.0f * uwpix;
+    int u1 = (int)ceilf(upix - dupix), u2 = (int)ceilf(upix + dupix);
+    if (u2 - u1 != 4) return false;
+    float x1 = ((float)u1 - upix) / uwpix, step = 1.0f / uwpix;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[i] = ptexBsplineFn(x1 + (float)i * step);
+    // stripZeros
+    int a = 0, b = 3;
+    if (k[0] == 0) { a = 1; if (k[1] == 0) return false; }
+    if (k[3] == 0) { b = 2; if (k[2] == 0) return false; }
+    if (a == 1) { k[0] = k[1]; k[1] = k[2]; k[2] = k[3]; k[3] = 0.f; }
+    k0 = u1 + a;
+    kw = b - a + 1;
+    return true;
+}
+
+SELAS_D bool ptexEvalFast(const PtexGpu& tx, const PtexFace& f, int faceid, float u, float v, int nchan, float oneValue, float* rgb) {
+    if (f.isSubface() || f.isConstant() || f.ulog2 < 3 || f.vlog2 < 3) return false;
+    PtexPiece k;
+    if (!ptexFastAxis(u, f.ulog2, k.u, k.uw, k.ku) || !ptexFastAxis(v, f.vlog2, k.v, k.vw, k.kv)) return false;
+    const int resu = 1 << f.ulog2, resv = 1 << f.vlog2;
+    const bool splitR = (k.u + k.uw > resu), splitL = (k.u < 0), splitT = (k.v + k.vw > resv), splitB = (k.v < 0);
+    const int nsplit = (int)splitR + (int)splitL + (int)splitT + (int)splitB;
+    if (nsplit > 1) return false;  // corner: general path
+    const float weight = ptexSum4(k.ku, k.uw) * ptexSum4(k.kv, k.vw);
+    float result[3] = {0.f, 0.f, 0.f};
+    if (nsplit == 1) {
+        const int eid = splitB ? kEdgeBottom : splitR ? kEdgeRight : splitT ? kEdgeTop : kEdgeLeft;
+        const int afid = f.adjface(eid);
+        // overhang width and the piece that leaves the face (splitL/R/B/T, PtexSeparableKernel.h:149-237)
+        PtexPiece ka = k;
+        const bool uAxis = splitL || splitR, lowSide = splitL || splitB;
+        // the split axis is handled on a copy so that every array index stays a compile-time constant
+        float kk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kk[i] = uAxis ? k.ku[i] : k.kv[i];
+        const int kn = uAxis ? k.uw : k.vw, k0 = uAxis ? k.u : k.v, res = uAxis ? resu : resv;
+        const int w = lowSide ? -k0 : k0 + kn - res;  // overhang width (splitL/R/B/T, PtexSeparableKernel.h:149-237)
+        float ko[4];  // weights of the piece that leaves the face
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ko[i] = kk[i];
+        if (!lowSide) ptexShift4(ko, kn - w);
+        const int o0 = lowSide ? res - w : 0;
+        if (uAxis) { ka.u = o0; ka.uw = w; }
+        else { ka.v = o0; ka.vw = w; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (uAxis) ka.ku[i] = ko[i];
+            else ka.kv[i] = ko[i];
+        }
+        int newK0 = k0, newKn = kn - w;
+        if (afid >= 0) {
+            PtexFace af = ptexLoadFace(tx, afid);
+            if (af.isSubface()) return false;
+            int ul = f.ulog2, vl = f.vlog2;
+            ptexRotatePiece(ka, eid - f.adjedge(eid) + 2, ul, vl);
+            if (ul != af.ulog2 || vl != af.vlog2) return false;  // needs downres / reduced data: general path
+            ptexApplyPiece(tx, af, afid, ka, nchan, result);
+            if (lowSide) { ptexShift4(kk, w); newK0 = 0; }  // the part that stays
+        } else {
+            // mesh border: mergeL/R/B/T fold the overhang onto the edge texel (border mode black drops it)
+            const int mode = uAxis ? tx.uMode : tx.vMode;
+            if (lowSide) {
+                float acc = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < w) acc += kk[i];
+                float edge = ptexPick4(kk, w);
+                if (mode != 1) edge += acc;
+                ptexShift4(kk, w);
+                kk[0] = edge;
+                newK0 = 0;
+            } else {
+                float acc = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i >= newKn && i < kn) acc += kk[i];
+                if (mode != 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (i == newKn - 1) kk[i] += acc;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (uAxis) k.ku[i] = kk[i];
+            else k.kv[i] = kk[i];
+        }
+        if (uAxis) { k.u = newK0; k.uw = newKn; }
+        else { k.v = newK0; k.vw = newKn; }
+    }
+    ptexApplyPiece(tx, f, faceid, k, nchan, result);
+    float scale = 1.0f / (weight * oneValue);
+    for (int c = 0; c < nchan; ++c) rgb[c] = result[c] * scale;
+    return true;
+}
+
+// PtexSeparableFilter::eval, :47-132, with firstChan 0, nChannels 3, all widths 0, width 1, blur 0, split in three steps:
+//   ptexPrologue   early outs (bad face id, constant neighbourhood, border modes); returns true when a filter is needed
+//   ptexEvalFast   register-resident common cases (above)
+//   ptexGeneral    everything else (the library's full splitAndApply logic)
+// Channels the texture does not have are returned as 0 (the reference leaves them uninitialised).
+SELAS_D bool ptexPrologue(const PtexGpu& tx, int faceid, float& u, float& v, PtexFace& f, float* rgb) {
+    rgb[0] = rgb[1] = rgb[2] = 0.f;
+    if (faceid < 0 || faceid >= tx.numFaces) return false;
+    const int nchan = tx.nchan < 3 ? tx.nchan : 3;
+    f = ptexLoadFace(tx, faceid);
+    if (f.flags & kPtexFlagNbConstant) {  // :62-69, ConvertToFloat of the face's constant pixel
+        const float oneValueInv = tx.dataType == 0 ? 1.f / 255.f : (tx.dataType == 1 ? 1.f / 65535.f : 1.f);
+        const uint8_t* px = tx.constData + (size_t)faceid * tx.pixelSize;
+        for (int c = 0; c < nchan; ++c) {
             float t = ptexTexel(px, tx.dataType, c);
             rgb[c] = tx.dataType == 3 ? t : t * oneValueInv;
         }
-        return;
+        return false;
     }
-    float uw = 0.f, vw = 0.f;
     bool black = false;
     switch (tx.uMode) {
         case 0: u = clampf_(u, 0.0f, 1.0f); break;
@@ -610,8 +797,17 @@ static __device__ __noinline__ void ptexEvalBspline(const PtexGpu* texPtr, int f
         case 2: v = v - floorf(v); break;
         case 1: if (v <= -1.0f || v >= 2.0f) black = true; break;
     }
-    if (black) return;
+    return !black;
+}
 
+static __device__ __noinline__ void ptexGeneral(const PtexGpu* texPtr, int faceid, float u, float v, float* rgb) {
+    const PtexGpu tx = *texPtr;
+    PtexEvalState st;
+    st.nchan = tx.nchan < 3 ? tx.nchan : 3;
+    st.result[0] = st.result[1] = st.result[2] = 0.f;
+    const float oneValue = tx.dataType == 0 ? 255.f : (tx.dataType == 1 ? 65535.f : 1.f);
+    PtexFace f = ptexLoadFace(tx, faceid);
+    float uw = 0.f, vw = 0.f;
     PtexWorkList wl;
     wl.count = 0;
     PtexKernel k;
@@ -643,7 +839,62 @@ static __device__ __noinline__ void ptexEvalBspline(const PtexGpu* texPtr, int f
         ptexSplitAndApply(tx, st, wl, kk, fid, ff);
     }
     float scale = 1.0f / (st.weight * oneValue);
+    rgb[0] = rgb[1] = rgb[2] = 0.f;
     for (int c = 0; c < st.nchan; ++c) rgb[c] = st.result[c] * scale;
+}
+
+// Tile-cooperative lookups: a CTA of BLOCK threads walks tiles of BLOCK * PER_THREAD lookups.  Phase 1 runs the early
+// outs and the register-resident fast path for every lookup of the tile; the ones it cannot take (corners, subfaces, mixed
+// resolutions: ~14 % on 8x8 faces) are queued in shared memory.  Phase 2 spreads the queue over all threads, so the long
+// general path runs in dense warps and its latency is amortised over the whole tile instead of being paid once per warp.
+//   fetch(i, tex, faceid, u, v) -> bool   describes lookup i (false: nothing to do for i)
+//   store(i, rgb)                         receives the result
+template <int BLOCK, int PER_THREAD, typename Fetch, typename Store>
+SELAS_D void ptexTileEval(size_t n, Fetch fetch, Store store) {
+    struct Item {
+        const PtexGpu* tex;
+        uint32_t index;
+        int faceid;
+        float u, v;
+    };
+    constexpr int TILE = BLOCK * PER_THREAD;
+    __shared__ int failCount;
+    __shared__ Item failItem[TILE];
+    for (size_t base = (size_t)blockIdx.x * TILE; base < n; base += (size_t)gridDim.x * TILE) {
+        if (threadIdx.x == 0) failCount = 0;
+        __syncthreads();
+#pragma unroll 1
+        for (int k = 0; k < PER_THREAD; ++k) {
+            size_t i = base + (size_t)k * BLOCK + threadIdx.x;
+            if (i >= n) continue;
+            const PtexGpu* texPtr;
+            int faceid;
+            float u, v;
+            if (!fetch(i, texPtr, faceid, u, v)) continue;
+            const PtexGpu tx = *texPtr;
+            PtexFace f;
+            float rgb[3];
+            bool done = true;
+            if (ptexPrologue(tx, faceid, u, v, f, rgb)) {
+                const float oneValue = tx.dataType == 0 ? 255.f : (tx.dataType == 1 ? 65535.f : 1.f);
+                if (!ptexEvalFast(tx, f, faceid, u, v, tx.nchan < 3 ? tx.nchan : 3, oneValue, rgb)) {
+                    int slot = atomicAdd(&failCount, 1);
+                    failItem[slot] = Item{texPtr, (uint32_t)(i - base), faceid, u, v};
+                    done = false;
+                }
+            }
+            if (done) store(i, rgb);
+        }
+        __syncthreads();
+        const int nf = failCount;
+        for (int j = threadIdx.x; j < nf; j += BLOCK) {
+            Item it = failItem[j];
+            float rgb[3];
+            ptexGeneral(it.tex, it.faceid, it.u, it.v, rgb);
+            store(base + it.index, rgb);
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace selas

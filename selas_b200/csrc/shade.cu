@@ -105,9 +105,9 @@ __global__ void cameraRaysKernel(SelasCamera cam, size_t n, const float* __restr
     o[1] = make_float4(d.x, d.y, d.z, SELAS_FLOAT_MAX);
 }
 
-template <bool PTEX>
-__global__ void surfaceParamsKernel(SceneGpu sc, size_t n, const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
-                                    SelasSurface* __restrict__ out) {
+__global__ void __launch_bounds__(128) surfaceParamsKernel(SceneGpu sc, size_t n, const SelasRay* __restrict__ rays,
+                                                           const SelasHit* __restrict__ hits, const float* __restrict__ ptexRgb,
+                                                           SelasSurface* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     SelasHit h = hits[i];
@@ -116,7 +116,8 @@ __global__ void surfaceParamsKernel(SceneGpu sc, size_t n, const SelasRay* __res
     if (h.geomID != SELAS_INVALID_ID) {
         SelasRay r = rays[i];
         Surface s;
-        surfaceFromHit<PTEX>(sc, v3(r.ox, r.oy, r.oz), v3(r.dx, r.dy, r.dz), h.t, h.u, h.v, h.primID, h.geomID, h.instID0, s);
+        surfaceFromHit(sc, v3(r.ox, r.oy, r.oz), v3(r.dx, r.dy, r.dz), h.t, h.u, h.v, h.primID, h.geomID, h.instID0,
+                       ptexRgb ? ptexRgb + 3 * i : nullptr, s);
         storeSurface(s, v3(-r.dx, -r.dy, -r.dz), o);
     }
     out[i] = o;
@@ -162,10 +163,17 @@ int launchCameraRays(SelasContext* ctx, const SelasCamera& cam, size_t n, const 
 }
 int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, const SelasHit* d_hits, SelasSurface* d_out) {
     if (!n) return SELAS_OK;
-    if (scene->usesPtex)
-        surfaceParamsKernel<true><<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_out);
-    else
-        surfaceParamsKernel<false><<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_out);
+    float* d_rgb = nullptr;
+    if (scene->usesPtex) {
+        SELAS_CUDA_CHECK(scene->ctx, cudaMalloc((void**)&d_rgb, sizeof(float) * 3 * n));
+        unsigned grid = (unsigned)std::min<size_t>((n + 1023) / 1024, (size_t)scene->ctx->smCount * 8);
+        ptexStageKernel<<<grid, 128, 0, scene->ctx->stream>>>(scene->gpu, (uint32_t)n, d_hits, d_rgb);
+    }
+    surfaceParamsKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_rgb, d_out);
+    if (d_rgb) {
+        cudaStreamSynchronize(scene->ctx->stream);
+        cudaFree(d_rgb);
+    }
     SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -192,6 +200,7 @@ struct WavefrontBuffers {
     float4* medium[2] = {nullptr, nullptr};
     SelasRay* shadowRays = nullptr;
     float4* shadowPayload = nullptr;
+    float* ptexRgb = nullptr;      // Ptex stage output, 3 floats per path (scenes with Ptex materials only)
     uint32_t* order = nullptr;     // material-sorted visiting order of the hit queue
     uint32_t* bins = nullptr;      // per iteration: 64 counts + 64 cursors
     uint32_t* counters = nullptr;  // 4 per iteration: nextPaths, shadowRays, closestFetch, shadowFetch
@@ -214,6 +223,7 @@ void freeWavefront(SelasScene* scene) {
     cudaFree(w->shadowPayload);
     cudaFree(w->counters);
     cudaFree(w->order);
+    cudaFree(w->ptexRgb);
     cudaFree(w->bins);
     if (w->h_counts) cudaFreeHost(w->h_counts);
     if (w->ev0) cudaEventDestroy(w->ev0);
@@ -243,6 +253,7 @@ static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterat
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity));
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->counters, sizeof(uint32_t) * slots));
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->order, sizeof(uint32_t) * (size_t)capacity));
+    if (scene->usesPtex) SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->ptexRgb, sizeof(float) * 3 * (size_t)capacity));
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->bins, sizeof(uint32_t) * 2 * kBinCount * (size_t)(iterations + 2)));
     SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4));
     SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev0));
@@ -338,10 +349,9 @@ __global__ void __launch_bounds__(256) binScatterKernel(SceneGpu sc, uint32_t n,
 }
 
 struct ShadeParams {
-    uint32_t maxPathLength, rrStartBounce, layerCount, pixels, misMode;
+    uint32_t maxPathLength, rrStartBounce, layerCount, pixels, misMode, skipNonFinite;
 };
 
-template <bool PTEX>
 __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ order, uint32_t nMax,
                                                    const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                                    const float4* __restrict__ thrPix, const uint2* __restrict__ rngFlags,
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
                                                    float4* __restrict__ thrPixOut, uint2* __restrict__ rngFlagsOut,
                                                    float4* __restrict__ mediumOut, SelasRay* __restrict__ shadowRays,
                                                    float4* __restrict__ shadowPayload, uint32_t* __restrict__ counters,
-                                                   float* __restrict__ film) {
+                                                   float* __restrict__ film, const float* __restrict__ ptexRgb) {
     const uint32_t n = nMax;
     const uint32_t slotIndex = blockIdx.x * blockDim.x + threadIdx.x;
     // material-sorted visiting order (binScatterKernel): lanes of a warp share a material, hence code path
@@ -391,7 +401,8 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
 
         Surface s;
         if (isHit) {
-            surfaceFromHit<PTEX>(sc, o, d, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, geomID, h1.y, s);
+            surfaceFromHit(sc, o, d, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, geomID, h1.y,
+                           ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, s);
             rayDistance = length(s.position - o);  // :165-167
         }
         thr = thr * transmission(medium, rayDistance);  // :168-169
@@ -423,7 +434,7 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
                     shRay.ox = so.x; shRay.oy = so.y; shRay.oz = so.z; shRay.tnear = s.error;
                     shRay.dx = ls.direction.x; shRay.dy = ls.direction.y; shRay.dz = ls.direction.z; shRay.tfar = ls.distance;
                     shPayload = make_float4(c.x, c.y, c.z, __uint_as_float(pixel));
-                    wantShadow = true;
+                    wantShadow = !(prm.skipNonFinite && !(isfinite(c.x) && isfinite(c.y) && isfinite(c.z)));
                 }
             }
             // ---- BSDF sampling, :197-226 ----
@@ -461,6 +472,7 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
             alive = true;
         } else {  // escaped: background, :234-243 (no IBL: both background variants are the constant)
             V3 c = v3(sc.background[0], sc.background[1], sc.background[2]) * thr;
+            if (prm.skipNonFinite && !(isfinite(c.x) && isfinite(c.y) && isfinite(c.z))) c = v3(0.0f);
             atomicAdd(filmRadiance + 3 * (size_t)pixel, c.x);
             atomicAdd(filmRadiance + 3 * (size_t)pixel + 1, c.y);
             atomicAdd(filmRadiance + 3 * (size_t)pixel + 2, c.z);
@@ -583,7 +595,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     int rc = ensureWavefront(scene, capacity, rs.maxPathLength);
     if (rc) return rc;
     WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
-    ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels, rs.misMode};
+    ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels, rs.misMode, (rs.flags & SELAS_RENDER_SKIP_NONFINITE) ? 1u : 0u};
     const bool counting = (rs.flags & SELAS_RENDER_COUNT_TRAVERSAL) != 0;
     unsigned long long* d_totals = nullptr;
     if (counting) {
@@ -625,16 +637,15 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 order = w->order;
                 st.kernelLaunches += 3;
             }
-            if (scene->usesPtex)
-                shadeKernel<true><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur],
-                                                                      w->rngFlags[cur], w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1],
-                                                                      w->rngFlags[cur ^ 1], w->medium[cur ^ 1], w->shadowRays, w->shadowPayload,
-                                                                      ctr, d_film);
-            else
-                shadeKernel<false><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur],
-                                                                       w->rngFlags[cur], w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1],
-                                                                       w->rngFlags[cur ^ 1], w->medium[cur ^ 1], w->shadowRays, w->shadowPayload,
-                                                                       ctr, d_film);
+            if (scene->usesPtex) {  // Ptex stage: base-colour lookups for the whole hit queue
+                unsigned grid = (unsigned)std::min<uint32_t>(divUp(n, 1024), (uint32_t)ctx->smCount * 8);
+                ptexStageKernel<<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
+                ++st.kernelLaunches;
+            }
+            shadeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
+                                                            w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
+                                                            w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film,
+                                                            scene->usesPtex ? w->ptexRgb : nullptr);
             timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));

@@ -22,10 +22,9 @@ SELAS_D float interpAttr(const float* a, const uint32_t* ix, uint32_t ipf, int c
     return (1.0f - v) * ((1.0f - u) * t0 + u * t1) + v * ((1.0f - u) * t3 + u * t2);
 }
 
-// PTEX = false compiles the Ptex lookup out (scenes without Ptex materials keep the leaner kernel).
-template <bool PTEX>
+// ptexRgb: this hit's Ptex lookup, made by the Ptex stage kernel (ptexStageKernel) before shading, or null.
 SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, float v, uint32_t primID, uint32_t geomID,
-                            uint32_t instID, Surface& s) {
+                            uint32_t instID, const float* ptexRgb, Surface& s) {
     const MeshGpu mesh = sc.meshes[geomID];
     const InstanceGpu* inst = sc.instances + instID;
     const SelasMaterial* mat = sc.materials + mesh.materialIndex;
@@ -70,11 +69,10 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
     }
 
     V3 base;
-    if (PTEX && (mat->flags & SELAS_MAT_USES_PTEX) && mesh.ptex) {
-        // SurfaceParameters.cpp:196-208: filter->eval(faceid = primId, u, v, widths 0), then pow 2.2 only
-        float rgb[3];
-        ptexEvalBspline((const PtexGpu*)mesh.ptex, (int)primID, u, v, rgb);
-        base = v3(rgb[0], rgb[1], rgb[2]);
+    if (ptexRgb && (mat->flags & SELAS_MAT_USES_PTEX) && mesh.ptex) {
+        // SurfaceParameters.cpp:196-208: filter->eval(faceid = primId, u, v, widths 0), then pow 2.2 only.  The lookup itself
+        // was done by the Ptex stage that runs between the closest-hit and the shade kernels.
+        base = v3(ptexRgb[0], ptexRgb[1], ptexRgb[2]);
     } else {
         base = v3(mat->baseColor);  // non-Ptex textures: SURVEY.md 8(f)4, not in this round
     }
@@ -109,6 +107,30 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
     s.shader = mat->shader;
     V3 view = v3(-d.x, -d.y, -d.z);
     s.relativeIOR = ((mat->flags & SELAS_MAT_TRANSPARENT) && dot(view, n) < 0.0f) ? s.ior : 1.0f / s.ior;
+}
+
+// Ptex stage of the wavefront: base-colour lookups for every hit of the queue whose material uses Ptex
+// (SurfaceParameters.cpp:196-208), written as 3 floats per path for the shade kernel.
+__global__ void __launch_bounds__(128) ptexStageKernel(SceneGpu sc, uint32_t n, const SelasHit* __restrict__ hits, float* __restrict__ rgbOut) {
+    ptexTileEval<128, 8>(
+        n,
+        [&](size_t i, const PtexGpu*& t, int& f, float& uu, float& vv) {
+            const uint4* hp = reinterpret_cast<const uint4*>(hits + i);
+            uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+            if (h1.x == SELAS_INVALID_ID) return false;
+            const MeshGpu& mesh = sc.meshes[h1.x];
+            if (!((sc.materials[mesh.materialIndex].flags & SELAS_MAT_USES_PTEX) && mesh.ptex)) return false;
+            t = (const PtexGpu*)mesh.ptex;
+            f = (int)h0.w;
+            uu = __uint_as_float(h0.y);
+            vv = __uint_as_float(h0.z);
+            return true;
+        },
+        [&](size_t i, const float* c) {
+            rgbOut[3 * i] = c[0];
+            rgbOut[3 * i + 1] = c[1];
+            rgbOut[3 * i + 2] = c[2];
+        });
 }
 
 SELAS_D void storeSurface(const Surface& s, V3 view, SelasSurface& o) {
