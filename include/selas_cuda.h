@@ -206,7 +206,9 @@ typedef struct SelasRenderSettings {
     uint32_t misMode;         /* 0 = reference (weight 1.0, PathTracer.cpp:215); 1 = balance heuristic */
     uint32_t flags;           /* SELAS_RENDER_* */
     uint32_t pixelStride;     /* 0/1 = every pixel; k = only pixels p with p % k == 0 (bounded samples of a workload) */
-    uint32_t reserved;
+    uint32_t pixelSampler;    /* 0 = two uniforms from the path's stream (PathTracer, Camera.cpp:63-74); (m | n << 16) = correlated
+                                 multi-jitter over an m x n grid with s = sample index, p = pixel index (the DeferredPathTracer's
+                                 primary rays, DeferredPathTracer.cpp:349-380 / Camera.cpp:77-86) */
 } SelasRenderSettings;
 
 typedef struct SelasRenderStats {
@@ -275,6 +277,9 @@ int selas_cuda_camera_init(const SelasCameraSettings* settings, uint32_t width, 
 /* rays[i] from pixel (px[i] + jitter[2i], py[i] + jitter[2i+1]); jitter NULL => pixel centre +0.5 */
 int selas_cuda_camera_rays(SelasContext* ctx, const SelasCamera* camera, size_t n, const float* px,
                            const float* py, const float* jitter, SelasRay* rays);
+
+/* CorrelatedMultiJitter (MathLib/CorrelatedMultiJitter.cpp:52-62): out2[2i..] = sample s[i] of pattern p[i] on an m x n grid */
+int selas_cuda_cmj(SelasContext* ctx, size_t count, const int32_t* s, int32_t m, int32_t n, const int32_t* p, float* out2);
 
 /* ---- BSDF operators: SurfaceScattering.h:15-16 ----------------------------------------------------
  * EvaluateBsdf (SurfaceScattering.cpp:41): f*|cos| in rgb[3n], forward/reverse pdf.

@@ -548,7 +548,10 @@ int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
                 uint32_t y = (uint32_t)(p / rs->width), x = (uint32_t)(p - (size_t)y * rs->width);
                 for (uint32_t k = 0; k < rs->samplesPerPixel; ++k) {
                     g_src = DrawSource{nullptr, 0, 0, mix32(rs->seed ^ mix32((uint32_t)p ^ mix32(rs->firstSample + k + 0x9e3779b9u))), true};
-                    Ray ray = JitteredCameraRay(&rc, &ctx->sampler, (float)x, (float)y);
+                    Ray ray = rs->pixelSampler == 0
+                                  ? JitteredCameraRay(&rc, &ctx->sampler, (float)x, (float)y)
+                                  : JitteredCameraRay(&rc, (int32)x, (int32)y, (int32)(rs->firstSample + k), (int32)(rs->pixelSampler & 0xffffu),
+                                                      (int32)(rs->pixelSampler >> 16), (int32)p);
                     // ---- EvaluatePath, PathTracer.cpp:142-258 ----
                     float3 Ld[2] = {float3::Zero_, float3::Zero_};
                     float3 throughput = float3::One_;

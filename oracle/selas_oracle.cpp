@@ -242,8 +242,16 @@ static void evaluatePath(const Scene& sc, const SelasCamera& cam, const SelasRen
     PathRng rng;
     rng.init(rs.seed, py * rs.width + px, sample);
     // JitteredCameraRay, Camera.cpp:63-74
-    float vx = (float)px + rng.next();
-    float vy = (float)py + rng.next();
+    float vx, vy;
+    if (rs.pixelSampler == 0) {
+        vx = (float)px + rng.next();
+        vy = (float)py + rng.next();
+    } else {  // JitteredCameraRay, CMJ overload: Camera.cpp:77-86 (s = sample index, p = pixel index)
+        float j[2];
+        cmj((int32_t)sample, (int32_t)(rs.pixelSampler & 0xffffu), (int32_t)(rs.pixelSampler >> 16), (int32_t)(py * rs.width + px), j);
+        vx = (float)px + j[0];
+        vy = (float)py + j[1];
+    }
     SelasRay ray;
     V3 dir = imageToWorldDirection(cam, vx, vy);
     ray.ox = cam.position[0]; ray.oy = cam.position[1]; ray.oz = cam.position[2];

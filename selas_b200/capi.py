@@ -71,7 +71,7 @@ class SceneDesc(C.Structure):
 class RenderSettings(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("samplesPerPixel", u32), ("maxPathLength", u32),
                 ("rrStartBounce", u32), ("layerCount", u32), ("seed", u32), ("firstSample", u32), ("misMode", u32),
-                ("flags", u32), ("pixelStride", u32), ("reserved", u32)]
+                ("flags", u32), ("pixelStride", u32), ("pixelSampler", u32)]
 
 
 class RenderStats(C.Structure):
@@ -114,7 +114,7 @@ EXPORTS = [
     "selas_cuda_context_create", "selas_cuda_context_destroy", "selas_cuda_last_error", "selas_cuda_device_count",
     "selas_cuda_version", "selas_cuda_scene_create", "selas_cuda_scene_destroy", "selas_cuda_scene_bvh_stats",
     "selas_cuda_intersect", "selas_cuda_occluded", "selas_cuda_intersect_device", "selas_cuda_occluded_device",
-    "selas_cuda_intersect_counted", "selas_cuda_camera_init", "selas_cuda_camera_rays", "selas_cuda_bsdf_eval",
+    "selas_cuda_intersect_counted", "selas_cuda_camera_init", "selas_cuda_camera_rays", "selas_cuda_cmj", "selas_cuda_bsdf_eval",
     "selas_cuda_bsdf_sample", "selas_cuda_light_sample", "selas_cuda_light_pdf", "selas_cuda_surface_params",
     "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_film_scale_device",
     "selas_cuda_hashgrid_build", "selas_cuda_hashgrid_destroy", "selas_cuda_hashgrid_read",
@@ -206,6 +206,13 @@ class Context:
         self.check(self.lib.selas_cuda_camera_rays(self.handle, C.byref(camera), C.c_size_t(n), _ptr(px), _ptr(py),
                                                    _ptr(jit), _ptr(rays)))
         return rays
+
+    def cmj(self, s, m, n, p):
+        s = np.ascontiguousarray(s, dtype=np.int32)
+        p = np.ascontiguousarray(p, dtype=np.int32)
+        out = np.zeros((s.size, 2), np.float32)
+        self.check(self.lib.selas_cuda_cmj(self.handle, C.c_size_t(s.size), _ptr(s), C.c_int32(m), C.c_int32(n), _ptr(p), _ptr(out)))
+        return out
 
     def bsdf_eval(self, surfaces, v, l):
         surfaces = np.ascontiguousarray(surfaces, dtype=SURFACE_DTYPE)
@@ -421,9 +428,10 @@ RENDER_SKIP_NONFINITE = 2
 
 
 def render_settings(width, height, spp, max_path_length=8, rr_start=8, layers=1, seed=1, first_sample=0, mis_mode=0,
-                    flags=0, pixel_stride=0):
+                    flags=0, pixel_stride=0, cmj=None):
     rs = RenderSettings()
     rs.flags, rs.pixelStride = flags, pixel_stride
+    rs.pixelSampler = 0 if cmj is None else (cmj[0] | (cmj[1] << 16))
     rs.width, rs.height, rs.samplesPerPixel = width, height, spp
     rs.maxPathLength, rs.rrStartBounce, rs.layerCount = max_path_length, rr_start, layers
     rs.seed, rs.firstSample, rs.misMode = seed, first_sample, mis_mode

@@ -277,6 +277,7 @@ int selas_cuda_scene_destroy(SelasScene* scene) {
         cudaStreamSynchronize(scene->ctx->stream);
     }
     freeWavefront(scene);
+    cudaFree(scene->d_filmCache);
     for (void* p : scene->allocations) cudaFree(p);
     delete scene;
     return SELAS_OK;
@@ -456,6 +457,25 @@ int selas_cuda_camera_rays(SelasContext* ctx, const SelasCamera* camera, size_t 
     return SELAS_OK;
 }
 
+int selas_cuda_cmj(SelasContext* ctx, size_t count, const int32_t* sIdx, int32_t m, int32_t n, const int32_t* p, float* out2) {
+    SELAS_TRY(bind(ctx));
+    if (count == 0) return SELAS_OK;
+    if (!sIdx || !p || !out2 || m <= 0 || n <= 0) {
+        setError(ctx, "selas_cuda_cmj: bad argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    int32_t *d_s, *d_p;
+    float* d_o;
+    SELAS_TRY(s.upload(&d_s, sIdx, count));
+    SELAS_TRY(s.upload(&d_p, p, count));
+    SELAS_TRY(s.alloc(&d_o, 2 * count));
+    SELAS_TRY(launchCmj(ctx, count, d_s, m, n, d_p, d_o));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(out2, d_o, 2 * count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
 // ---- BSDF / light / surface operators ----------------------------------------------------------------------------
 int selas_cuda_bsdf_eval(SelasContext* ctx, size_t n, const SelasSurface* surfaces, const float* v3in, const float* l3in, float* rgb3,
                          float* forwardPdfW, float* reversePdfW) {
@@ -611,9 +631,14 @@ int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera, c
         return SELAS_ERR_ARGUMENT;
     }
     const size_t plane = (size_t)settings->width * settings->height * 3;
-    Scratch s(ctx);
-    float* d_film;
-    SELAS_TRY(s.alloc(&d_film, plane * settings->layerCount));
+    if (scene->filmCacheFloats < plane * settings->layerCount) {
+        cudaFree(scene->d_filmCache);
+        scene->d_filmCache = nullptr;
+        scene->filmCacheFloats = 0;
+        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&scene->d_filmCache, plane * settings->layerCount * sizeof(float)));
+        scene->filmCacheFloats = plane * settings->layerCount;
+    }
+    float* d_film = scene->d_filmCache;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_film, 0, plane * settings->layerCount * sizeof(float), ctx->stream));
     SELAS_TRY(renderPathTracer(scene, *camera, *settings, d_film, stats, ctx->stream));
     for (uint32_t l = 0; l < settings->layerCount; ++l)

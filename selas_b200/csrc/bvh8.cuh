@@ -29,7 +29,9 @@ struct Bvh8 {
     uint32_t nodeCount, triCount;
 };
 
+#ifndef SELAS_STACK_SIZE
 #define SELAS_STACK_SIZE 48
+#endif
 
 SELAS_D uint32_t extractByte(uint32_t x, uint32_t i) { return (x >> (i * 8)) & 0xff; }
 SELAS_D uint32_t signExtendS8x4(uint32_t x) {

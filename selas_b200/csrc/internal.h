@@ -71,6 +71,9 @@ struct SelasScene {
     bool usesPtex = false;  // any mesh carries a Ptex texture: selects the shade kernel built with the lookup
     // wavefront scratch, grown on demand
     void* wf = nullptr;
+    // device film of the host-buffer render entry point, kept between calls
+    float* d_filmCache = nullptr;
+    size_t filmCacheFloats = 0;
 };
 
 namespace selas {
@@ -113,6 +116,7 @@ int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, con
 int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
                      cudaStream_t stream);
 int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream);
+int launchCmj(SelasContext* ctx, size_t count, const int32_t* d_s, int32_t m, int32_t n, const int32_t* d_p, float* d_out2);
 void freeWavefront(SelasScene* scene);
 
 // ptex.cu

@@ -230,4 +230,43 @@ SELAS_HD V3 imageToWorldDirection(const SelasCamera& cam, float x, float y) {
     return normalize(lightF3(cam.cameraZ) - cx * lightF3(cam.cameraX) + cy * lightF3(cam.cameraY));
 }
 
+// ---- correlated multi-jitter (MathLib/CorrelatedMultiJitter.cpp:12-62; Kensler 2013) ---------------------------------
+SELAS_HD float cmjFloat(uint32_t i, uint32_t p) {
+    i ^= p;
+    i ^= i >> 17;
+    i ^= i >> 10; i *= 0xb36534e5u;
+    i ^= i >> 12;
+    i ^= i >> 21; i *= 0x93fc4795u;
+    i ^= 0xdf6e307fu;
+    i ^= i >> 17; i *= 1u | p >> 18;
+    return i * (1.0f / 4294967808.0f);
+}
+SELAS_HD uint32_t cmjPermute(uint32_t i, uint32_t l, uint32_t p) {
+    uint32_t w = l - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        i ^= p; i *= 0xe170893du;
+        i ^= p >> 16;
+        i ^= (i & w) >> 4;
+        i ^= p >> 8; i *= 0x0929eb3fu;
+        i ^= p >> 23;
+        i ^= (i & w) >> 1; i *= 1u | p >> 27;
+        i *= 0x6935fa69u;
+        i ^= (i & w) >> 11; i *= 0x74dcb303u;
+        i ^= (i & w) >> 2; i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2; i *= 0xc860a3dfu;
+        i &= w;
+        i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+SELAS_HD void correlatedMultiJitter(int32_t s, int32_t m, int32_t n, int32_t p, float& jx, float& jy) {
+    int sx = (int)cmjPermute((uint32_t)(s % m), (uint32_t)m, (uint32_t)p * 0xa511e9b3u);
+    int sy = (int)cmjPermute((uint32_t)(s / m), (uint32_t)n, (uint32_t)p * 0x63d83595u);
+    float fx = cmjFloat((uint32_t)s, (uint32_t)p * 0xa399d265u);
+    float fy = cmjFloat((uint32_t)s, (uint32_t)p * 0x711ad6a5u);
+    jx = (s % m + (sy + fx) / n) / m;
+    jy = (s / m + (sx + fy) / m) / n;
+}
+
 }  // namespace selas

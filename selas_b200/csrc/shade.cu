@@ -105,6 +105,15 @@ __global__ void cameraRaysKernel(SelasCamera cam, size_t n, const float* __restr
     o[1] = make_float4(d.x, d.y, d.z, SELAS_FLOAT_MAX);
 }
 
+__global__ void cmjKernel(size_t count, const int32_t* __restrict__ sIdx, int32_t m, int32_t n, const int32_t* __restrict__ p, float* __restrict__ out2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float jx, jy;
+    correlatedMultiJitter(sIdx[i], m, n, p[i], jx, jy);
+    out2[2 * i] = jx;
+    out2[2 * i + 1] = jy;
+}
+
 __global__ void __launch_bounds__(128) surfaceParamsKernel(SceneGpu sc, size_t n, const SelasRay* __restrict__ rays,
                                                            const SelasHit* __restrict__ hits, const float* __restrict__ ptexRgb,
                                                            SelasSurface* __restrict__ out) {
@@ -177,6 +186,12 @@ int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, con
     SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
     return SELAS_OK;
 }
+int launchCmj(SelasContext* ctx, size_t count, const int32_t* d_s, int32_t m, int32_t n, const int32_t* d_p, float* d_out2) {
+    if (!count) return SELAS_OK;
+    cmjKernel<<<divUp(count, 256), 256, 0, ctx->stream>>>(count, d_s, m, n, d_p, d_out2);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
 int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream) {
     if (!n) return SELAS_OK;
     scaleKernel<<<divUp(n, 256), 256, 0, stream>>>(d, n, s);
@@ -190,6 +205,47 @@ int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t str
 constexpr uint32_t kBinCount = 64;  // material bins of the pre-shade counting sort (63 materials + miss)
 #define FLAG_DELTA_ONLY (1u << 16)
 #define FLAG_IN_MEDIUM (1u << 17)
+
+// CUDA events around every launch of the loop: per-kernel device time for the roofline report (SURVEY.md 8(d)).
+struct KernelTimers {
+    std::vector<cudaEvent_t> pool;
+    struct Span { int kind; size_t a, b; };
+    std::vector<Span> spans;
+    size_t used = 0;
+    cudaEvent_t get() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    size_t begin(cudaStream_t st) {
+        cudaEvent_t e = get();
+        cudaEventRecord(e, st);
+        return used - 1;
+    }
+    void end(int kind, size_t a, cudaStream_t st) {
+        cudaEvent_t e = get();
+        cudaEventRecord(e, st);
+        spans.push_back({kind, a, used - 1});
+    }
+    void collect(SelasRenderStats& st) {
+        for (const Span& sp : spans) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pool[sp.a], pool[sp.b]);
+            if (sp.kind == 0) st.generateMs += ms;
+            else if (sp.kind == 1) { st.closestMs += ms; ++st.closestLaunches; }
+            else if (sp.kind == 2) { st.shadeMs += ms; ++st.shadeLaunches; }
+            else { st.shadowMs += ms; ++st.shadowLaunches; }
+        }
+        spans.clear();
+        used = 0;
+    }
+    ~KernelTimers() {
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    }
+};
 
 struct WavefrontBuffers {
     uint32_t capacity = 0;
@@ -207,6 +263,7 @@ struct WavefrontBuffers {
     uint32_t counterSlots = 0;
     uint32_t* h_counts = nullptr;  // pinned readback
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    KernelTimers timers;  // event pool reused across calls
 };
 
 void freeWavefront(SelasScene* scene) {
@@ -263,7 +320,7 @@ static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterat
 
 // JitteredCameraRay (Camera.cpp:63-74) for path ids [first, first+count): pixel = id % pixels, sample = id / pixels.
 __global__ void generateKernel(SelasCamera cam, uint32_t width, uint32_t height, uint32_t seed, uint32_t firstSample, uint64_t firstPath,
-                               uint32_t count, uint32_t activePixels, uint32_t pixelStride, SelasRay* __restrict__ rays,
+                               uint32_t count, uint32_t activePixels, uint32_t pixelStride, uint32_t pixelSampler, SelasRay* __restrict__ rays,
                                float4* __restrict__ thrPix, uint2* __restrict__ rngFlags) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -272,8 +329,16 @@ __global__ void generateKernel(SelasCamera cam, uint32_t width, uint32_t height,
     uint32_t y = pixel / width, x = pixel - y * width;
     PathRng rng;
     rng.init(seed, pixel, sample);
-    float vx = (float)x + rng.next();
-    float vy = (float)y + rng.next();
+    float vx, vy;
+    if (pixelSampler == 0) {  // JitteredCameraRay with the sampler, Camera.cpp:63-74
+        vx = (float)x + rng.next();
+        vy = (float)y + rng.next();
+    } else {  // JitteredCameraRay with correlated multi-jitter, Camera.cpp:77-86 (s = sample, p = pixel index)
+        float jx, jy;
+        correlatedMultiJitter((int32_t)sample, (int32_t)(pixelSampler & 0xffffu), (int32_t)(pixelSampler >> 16), (int32_t)pixel, jx, jy);
+        vx = (float)x + jx;
+        vy = (float)y + jy;
+    }
     V3 d = imageToWorldDirection(cam, vx, vy);
     float4* o = reinterpret_cast<float4*>(rays + i);
     o[0] = make_float4(cam.position[0], cam.position[1], cam.position[2], 0.0f);
@@ -526,47 +591,6 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
     }
 }
 
-// CUDA events around every launch of the loop: per-kernel device time for the roofline report (SURVEY.md 8(d)).
-struct KernelTimers {
-    std::vector<cudaEvent_t> pool;
-    struct Span { int kind; size_t a, b; };
-    std::vector<Span> spans;
-    size_t used = 0;
-    cudaEvent_t get() {
-        if (used == pool.size()) {
-            cudaEvent_t e;
-            cudaEventCreate(&e);
-            pool.push_back(e);
-        }
-        return pool[used++];
-    }
-    size_t begin(cudaStream_t st) {
-        cudaEvent_t e = get();
-        cudaEventRecord(e, st);
-        return used - 1;
-    }
-    void end(int kind, size_t a, cudaStream_t st) {
-        cudaEvent_t e = get();
-        cudaEventRecord(e, st);
-        spans.push_back({kind, a, used - 1});
-    }
-    void collect(SelasRenderStats& st) {
-        for (const Span& sp : spans) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, pool[sp.a], pool[sp.b]);
-            if (sp.kind == 0) st.generateMs += ms;
-            else if (sp.kind == 1) { st.closestMs += ms; ++st.closestLaunches; }
-            else if (sp.kind == 2) { st.shadeMs += ms; ++st.shadeLaunches; }
-            else { st.shadowMs += ms; ++st.shadowLaunches; }
-        }
-        spans.clear();
-        used = 0;
-    }
-    ~KernelTimers() {
-        for (cudaEvent_t e : pool) cudaEventDestroy(e);
-    }
-};
-
 int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
                      cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
@@ -574,6 +598,13 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         (uint64_t)rs.width * rs.height > 0x7fffffffull) {
         setError(ctx, "render settings out of range (width/height > 0, layerCount 1..2, maxPathLength <= 65535)");
         return SELAS_ERR_ARGUMENT;
+    }
+    if (rs.pixelSampler != 0) {
+        const uint32_t m = rs.pixelSampler & 0xffffu, n = rs.pixelSampler >> 16;
+        if (m == 0 || n == 0 || (uint64_t)rs.firstSample + rs.samplesPerPixel > (uint64_t)m * n) {
+            setError(ctx, "pixelSampler: correlated multi-jitter needs an m x n grid (m, n > 0) holding firstSample + samplesPerPixel samples");
+            return SELAS_ERR_ARGUMENT;
+        }
     }
     if (rs.misMode > 1) {
         setError(ctx, "misMode %u unknown (0 = reference weighting, 1 = balance heuristic)", rs.misMode);
@@ -602,7 +633,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&d_totals, 4 * sizeof(unsigned long long)));
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_totals, 0, 4 * sizeof(unsigned long long), stream));
     }
-    KernelTimers timers;
+    KernelTimers& timers = w->timers;
     // tuning knob: first bounce whose hit queue is sorted by material before shading (SELAS_SORT_FROM_BOUNCE, default 0)
     static const uint32_t sortFromBounce = getenv("SELAS_SORT_FROM_BOUNCE") ? (uint32_t)atoi(getenv("SELAS_SORT_FROM_BOUNCE")) : 0u;
 
@@ -613,7 +644,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->bins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)(rs.maxPathLength + 2), stream));
         size_t t0 = timers.begin(stream);
         generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, activePixels,
-                                                              stride, w->rays[0], w->thrPix[0], w->rngFlags[0]);
+                                                              stride, rs.pixelSampler, w->rays[0], w->thrPix[0], w->rngFlags[0]);
         timers.end(0, t0, stream);
         ++st.kernelLaunches;
         uint32_t n = count;

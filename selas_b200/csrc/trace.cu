@@ -193,7 +193,7 @@ static Bvh8 bvhOf(const SelasScene* s) {
     return b;
 }
 
-static int traceGrid(const SelasContext* ctx) { return ctx->smCount * 8; }
+static int traceGrid(const SelasContext* ctx) { return ctx->smCount * SELAS_TRACE_CTAS_PER_SM; }
 
 int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_ng4, uint32_t* d_counts,
                     uint32_t* d_rayCounter, cudaStream_t stream) {

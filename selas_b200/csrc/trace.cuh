@@ -10,8 +10,15 @@
 
 namespace selas {
 
+#ifndef SELAS_TRACE_THREADS
 #define SELAS_TRACE_THREADS 128
+#endif
+#ifndef SELAS_REFILL_THRESHOLD
 #define SELAS_REFILL_THRESHOLD 20
+#endif
+#ifndef SELAS_TRACE_CTAS_PER_SM
+#define SELAS_TRACE_CTAS_PER_SM 8
+#endif
 
 // MODE 0: closest hit -> hits (+Ng); 1: any hit -> occluded byte; 2: any hit -> film[pixel] += payload.rgb when
 // unoccluded (the NEE shadow ray of PathTracer.cpp:186-191 fused with FramebufferWriter_Write).

@@ -15,6 +15,10 @@ from tests import inputs
 
 pytestmark = pytest.mark.gpu
 
+
+def _relmse(a, b):
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
 REL_BSDF = 1e-5
 N = 200_000
 
@@ -107,6 +111,28 @@ def test_camera_parity(ctx, oracle):
         np.testing.assert_array_equal(g["ox"], o["ox"])
         g, o = ctx.camera_rays(cam, px, py), oracle.camera_rays(cam, px, py)
         np.testing.assert_allclose(g["dz"], o["dz"], rtol=0, atol=2e-7)
+
+
+def test_cmj_bit_exact_and_cmj_render(ctx, oracle):
+    """CorrelatedMultiJitter (integer hashing + a few float ops) is bit-exact; a render with the DeferredPathTracer's 4x4 CMJ
+    pixel sampling (DeferredPathTracer.cpp:349-380) matches the oracle like the uniformly jittered one."""
+    rng = np.random.default_rng(26)
+    for (m, n) in ((4, 4), (5, 3), (1, 1)):
+        s = rng.integers(0, m * n, size=50000).astype(np.int32)
+        p = rng.integers(0, 1 << 26, size=50000).astype(np.int32)
+        g, o = ctx.cmj(s, m, n, p), oracle.cmj(s, m, n, p)
+        np.testing.assert_array_equal(g.view(np.uint32), o.view(np.uint32))
+    data = inputs.small_scene()
+    cam = capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 64, 48)
+    rs = capi.render_settings(64, 48, 16, max_path_length=5, rr_start=8, layers=1, seed=6, cmj=(4, 4))
+    sc, hs = capi.Scene(ctx, data), oracle.scene_create(data)
+    g = sc.render(cam, rs)[0][0] / 16.0
+    o = oracle.render(hs, cam, rs, nthreads=8)[0][0] / 16.0
+    assert abs(g.mean() / o.mean() - 1.0) < 2e-3 and _relmse(g, o) < 2e-3
+    with pytest.raises(capi.SelasError):
+        sc.render(cam, capi.render_settings(8, 8, 17, cmj=(4, 4)))  # 17 samples do not fit a 4x4 pattern
+    oracle.scene_destroy(hs)
+    sc.close()
 
 
 # ---- (a) ray cast ----------------------------------------------------------------------------------------------
@@ -248,10 +274,6 @@ def test_surface_params_parity(ctx, oracle, instances):
 
 
 # ---- (d) integrator ---------------------------------------------------------------------------------------------
-def _relmse(a, b):
-    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
-
-
 def test_render_small_scene_matches_oracle(ctx, oracle):
     """Same scene, camera, settings and per-path RNG streams through the wavefront kernels and the oracle's
     EvaluatePath restatement: the two images differ only where float noise flips a discrete decision."""

@@ -135,3 +135,17 @@ def test_tier_b_integrator_matches_restatement(oracle, ref):
     for l in range(2):
         np.testing.assert_allclose(fa[l], fb[l], rtol=1e-5, atol=1e-6)
     assert fa[1].sum() > 0
+
+
+def test_tier_b_integrator_cmj_pixel_sampling(oracle, ref):
+    """Correlated multi-jitter primary rays (the reference's own JitteredCameraRay CMJ overload vs the restatement)."""
+    data = inputs.small_scene(with_attrs=False)
+    cam = capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 40, 30)
+    rs = capi.render_settings(40, 30, 16, max_path_length=4, rr_start=8, layers=1, seed=2, cmj=(4, 4))
+    ha, hb = oracle.scene_create(data), ref.scene_create(data)
+    fa, sa = oracle.render(ha, cam, rs, nthreads=2)
+    fb, sb = ref.render(hb, cam, rs, nthreads=2)
+    oracle.scene_destroy(ha)
+    ref.scene_destroy(hb)
+    assert sa.closestRays == sb.closestRays
+    np.testing.assert_allclose(fa[0], fb[0], rtol=1e-5, atol=1e-6)
