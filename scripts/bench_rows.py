@@ -183,11 +183,28 @@ def row_hashgrid(ctx, torch, dev, stream, n, m):
     idx = np.zeros(n, np.uint32)
     ctx.check(lib.selas_cuda_hashgrid_read(handle, ends.ctypes.data_as(capi.C.c_void_p), idx.ctypes.data_as(capi.C.c_void_p), None))
     occ = np.diff(np.concatenate([[0], ends.astype(np.int64)]))
-    # candidates visited per query are not reported by the kernel; the accepted count is
+    aabb = np.zeros(6, np.float32)
+    ctx.check(lib.selas_cuda_hashgrid_read(handle, None, None, aabb.ctypes.data_as(capi.C.c_void_p)))
+    # candidates actually visited = sum of the eight cell-range lengths per query (host restatement of the addressing,
+    # used only to account the bytes: 64-bit hash as VCMHashGrid.cpp:15-22)
+    inv = np.float32(1.0) / (np.float32(2.0) * radius)
+    cp = (inv * (q - aabb[None, :3])).astype(np.float32)
+    fl = np.floor(cp)
+    basec = fl.astype(np.int64) - ((cp - fl) < np.float32(0.5))
+    inside = np.all(q >= aabb[None, :3], axis=1) & np.all(q <= aabb[None, 3:], axis=1)
+    cand = np.zeros(m, np.int64)
+    for c8 in range(8):
+        xyz = basec + np.array([c8 & 1, (c8 >> 1) & 1, c8 >> 2], np.int64)[None, :]
+        h = (xyz[:, 0].astype(np.uint64) * np.uint64(73856093)) ^ (xyz[:, 1].astype(np.uint64) * np.uint64(19349663)) ^ \
+            (xyz[:, 2].astype(np.uint64) * np.uint64(83492791))
+        cell = (h % np.uint64(cells)).astype(np.int64)
+        cand += occ[cell]
+    cand[~inside] = 0
     accepted = float(counts.mean())
     build_bytes = 36.0 * n + 8.0 * cells
-    query_bytes = (64.0 + 12.0 + 4.0) * m + 16.0 * float(occ.mean()) * 8 * m + 4.0 * np.minimum(counts, kmax).sum()
+    query_bytes = (64.0 + 12.0 + 4.0) * m + 16.0 * float(cand.sum()) + 4.0 * np.minimum(counts, kmax).sum()
     out = {"points": n, "queries": m, "cells": cells, "radius": float(radius), "max_cell_occupancy": int(occ.max()), "mean_accepted_per_query": accepted,
+           "mean_candidates_per_query": float(cand.mean()),
            "build": {"ms": build_ms, "mpoints_per_s": n / build_ms / 1e3, "algorithmic_bytes": build_bytes,
                      "achieved_gbs": build_bytes / (build_ms * 1e-3) / 1e9, "frac_of_measured_hbm": build_bytes / (build_ms * 1e-3) / 1e9 / peak()},
            "query": {"ms": query_ms, "mqueries_per_s": m / query_ms / 1e3, "algorithmic_bytes": query_bytes,

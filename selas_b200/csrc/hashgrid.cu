@@ -21,6 +21,8 @@
 // (the d2 <= r2 accept test is otherwise not reproducible at the boundary).
 //
 // Algorithmic bytes: build 36 B/point + 8 B/cell; query 64 B + 16 B/candidate.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -313,6 +315,94 @@ __global__ void __launch_bounds__(128) queryKernel(const uint32_t* __restrict__ 
     counts[i] = found;
 }
 
+// SearchHashGrid, warp-cooperative form.  Every lane first prepares one query (AABB test, the eight cell ranges); the
+// warp then walks the 32 queries one after the other, all lanes testing 32 consecutive candidates of the query's
+// flattened candidate list (cell 0 .. cell 7, slots in order) per step.  Candidate loads are coalesced 16-byte reads,
+// all lanes stay busy even when the cell occupancy is heavy-tailed, and the ballot prefix keeps the accepted indices in
+// the reference's visiting order.
+constexpr int kQueryWarps = 4;
+__global__ void __launch_bounds__(kQueryWarps * 32) queryWarpKernel(const uint32_t* __restrict__ bounds, float inv, float r2, uint32_t cellCount,
+                                                                    const uint32_t* __restrict__ ends, const float4* __restrict__ cellPoints,
+                                                                    size_t m, const float* __restrict__ q, uint32_t* __restrict__ counts,
+                                                                    uint32_t* __restrict__ indices, uint32_t maxPerQuery) {
+    __shared__ float sPos[kQueryWarps][32][3];
+    __shared__ uint32_t sBegin[kQueryWarps][32][8];
+    __shared__ uint32_t sCum[kQueryWarps][32][8];  // inclusive prefix of the eight range lengths
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const size_t warpCount = (size_t)gridDim.x * kQueryWarps;
+    const float minx = floatFromOrdered(bounds[0]), miny = floatFromOrdered(bounds[1]), minz = floatFromOrdered(bounds[2]);
+    const float maxx = floatFromOrdered(bounds[3]), maxy = floatFromOrdered(bounds[4]), maxz = floatFromOrdered(bounds[5]);
+    for (size_t base = ((size_t)blockIdx.x * kQueryWarps + wib) * 32; base < m; base += warpCount * 32) {
+        // ---- phase 1: one query per lane ----
+        const size_t qi = base + lane;
+        uint32_t total = 0;
+        if (qi < m) {
+            float px = __ldg(q + 3 * qi), py = __ldg(q + 3 * qi + 1), pz = __ldg(q + 3 * qi + 2);
+            sPos[wib][lane][0] = px; sPos[wib][lane][1] = py; sPos[wib][lane][2] = pz;
+            float dminx = px - minx, dminy = py - miny, dminz = pz - minz;
+            float dmaxx = maxx - px, dmaxy = maxy - py, dmaxz = maxz - pz;
+            bool outside = (dminx < 0.0f || dminy < 0.0f || dminz < 0.0f) || (dmaxx < 0.0f || dmaxy < 0.0f || dmaxz < 0.0f);
+            if (!outside) {
+                float cx = inv * dminx, cy = inv * dminy, cz = inv * dminz;
+                float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+                int32_t bx = (int32_t)fx, by = (int32_t)fy, bz = (int32_t)fz;
+                if (cx - fx < 0.5f) --bx;
+                if (cy - fy < 0.5f) --by;
+                if (cz - fz < 0.5f) --bz;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    uint32_t cell = cellHash(bx + (c8 & 1), by + ((c8 >> 1) & 1), bz + (c8 >> 2), cellCount);
+                    uint32_t b = cell ? __ldg(ends + cell - 1) : 0u, e = __ldg(ends + cell);
+                    total += e - b;
+                    sBegin[wib][lane][c8] = b;
+                    sCum[wib][lane][c8] = total;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: the warp serves its 32 queries in turn ----
+        uint32_t pending = __ballot_sync(0xffffffffu, total != 0u);
+        uint32_t myCount = 0;  // lane L ends up holding the count of query L
+        while (pending) {
+            const uint32_t L = __ffs(pending) - 1u;
+            pending &= pending - 1u;
+            const float px = sPos[wib][L][0], py = sPos[wib][L][1], pz = sPos[wib][L][2];
+            uint32_t cum[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cum[k] = sCum[wib][L][k];
+            const uint32_t T = cum[7];
+            uint32_t* out = indices ? indices + (base + L) * (size_t)maxPerQuery : nullptr;
+            uint32_t found = 0;
+            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                bool accept = false;
+                uint32_t index = 0;
+                if (i < T) {
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) c += (i >= cum[k]) ? 1u : 0u;
+                    const uint32_t before = c ? sCum[wib][L][c - 1] : 0u;
+                    const float4 p = __ldg(cellPoints + sBegin[wib][L][c] + (i - before));
+                    float dx = px - p.x, dy = py - p.y, dz = pz - p.z;
+                    float d2 = (dx * dx) + (dy * dy) + (dz * dz);
+                    accept = d2 <= r2;
+                    index = __float_as_uint(p.w);
+                }
+                const uint32_t mask = __ballot_sync(0xffffffffu, accept);
+                if (accept && out) {
+                    uint32_t pos = found + __popc(mask & ltMask);
+                    if (pos < maxPerQuery) out[pos] = index;
+                }
+                found += __popc(mask);
+            }
+            if (lane == L) myCount = found;
+        }
+        if (qi < m) counts[qi] = myCount;
+        __syncwarp();
+    }
+}
+
 inline uint32_t divUp(size_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
 
 void releaseBuffers(SelasHashGrid* g) {
@@ -479,8 +569,15 @@ int selas_cuda_hashgrid_query_device(const SelasHashGrid* g, size_t m, const flo
         return SELAS_ERR_ARGUMENT;
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    queryKernel<<<divUp(m, 128), 128, 0, st>>>(g->d_bounds, g->inverseCellSize, g->radiusSq, g->cellCount, g->d_cellEnds, g->d_cellPoints, m,
-                                               d_queries3, d_counts, d_indices, maxPerQuery);
+    static const bool perThread = getenv("SELAS_HASHGRID_PER_THREAD_QUERY") != nullptr;  // tuning knob: the first version of the kernel
+    if (perThread)
+        queryKernel<<<divUp(m, 128), 128, 0, st>>>(g->d_bounds, g->inverseCellSize, g->radiusSq, g->cellCount, g->d_cellEnds, g->d_cellPoints, m,
+                                                   d_queries3, d_counts, d_indices, maxPerQuery);
+    else {
+        uint32_t grid = (uint32_t)std::min<size_t>((m + kQueryWarps * 32 - 1) / (kQueryWarps * 32), (size_t)ctx->smCount * 16);
+        queryWarpKernel<<<grid, kQueryWarps * 32, 0, st>>>(g->d_bounds, g->inverseCellSize, g->radiusSq, g->cellCount, g->d_cellEnds,
+                                                           g->d_cellPoints, m, d_queries3, d_counts, d_indices, maxPerQuery);
+    }
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
