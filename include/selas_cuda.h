@@ -175,6 +175,20 @@ typedef struct SelasInstanceDesc {
     float    localToWorld[16];
 } SelasInstanceDesc;
 
+/* ImageBasedLightResourceData, Source/Core/SceneLib/ImageBasedLightResource.h:16-35: lat-long environment with the marginal /
+ * conditional CDFs the bake step computes (BuildCommon/BuildImageBasedLight.cpp:44-105) and the separate "miss" image shown to
+ * paths that have only seen delta events (PathTracer.cpp:236-239). */
+typedef struct SelasIblDesc {
+    uint32_t     width, height;          /* of lightData and the density functions */
+    const float* marginalDensityFunction;     /* height entries, inclusive CDF over rows */
+    const float* conditionalDensityFunctions; /* width*height entries, inclusive CDF per row */
+    const float* lightData;              /* float3 per texel */
+    uint32_t     missWidth, missHeight;
+    const float* missData;               /* float3 per texel */
+    float        rotationRadians;
+    float        exposureScale;          /* 2^exposure */
+} SelasIblDesc;
+
 typedef struct SelasSceneDesc {
     const SelasMeshDesc*      meshes;
     uint32_t                  meshCount;
@@ -187,6 +201,7 @@ typedef struct SelasSceneDesc {
     const SelasLightSetRange* lightSets;
     uint32_t                  lightSetCount;
     float                     backgroundIntensity[4]; /* SceneResourceData::backgroundIntensity */
+    const SelasIblDesc*       ibl;           /* SceneResource::iblResource, or NULL: constant background (AreaLighting.cpp:415-437) */
 } SelasSceneDesc;
 
 /* Compile-time macros of the reference integrator made runtime (PathTracer.cpp:42-46, :248). */
@@ -298,6 +313,12 @@ int selas_cuda_light_sample(SelasContext* ctx, size_t n, const SelasLight* light
                             SelasLightSample* out);
 int selas_cuda_light_pdf(SelasContext* ctx, size_t n, const SelasLight* lights, uint32_t lightCount,
                          const uint32_t* lightIndex, const float* position3, const float* wi3, float* pdf);
+
+/* ---- image based light: ImageBasedLightResource.cpp:118-262 (the scene must have been created with an IBL) -------------
+ * lookup: SampleIbl(ibl, wi, pdf) -> rgb3/pdf and SampleIblMiss(ibl, wi, pdf) -> missRgb3 (any output may be NULL);
+ * sample: Ibl(ibl, r0, r1, theta, phi, x, y, pdf): u2 = 2 uniforms per sample; thetaPhiPdf3 = 3 floats, xy2 = 2 uint32 per sample */
+int selas_cuda_ibl_lookup(SelasScene* scene, size_t n, const float* wi3, float* rgb3, float* pdf, float* missRgb3);
+int selas_cuda_ibl_sample(SelasScene* scene, size_t n, const float* u2, float* thetaPhiPdf3, uint32_t* xy2);
 
 /* ---- surface: CalculateSurfaceParams SurfaceParameters.cpp:144-247 over a batch of hits ---------- */
 int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays, const SelasHit* hits,

@@ -786,6 +786,85 @@ static inline V3 uniformSphere(Stream& rng) {  // MathLib/Sampler.cpp:44-54
     return v3(norm * cosf(theta), u, norm * sinf(theta));
 }
 
+// ---- image based light: SceneLib/ImageBasedLightResource.cpp:81-262 ------------------------------------------------
+struct Ibl {  // host copy of SelasIblDesc
+    uint32_t width = 0, height = 0, missWidth = 0, missHeight = 0;
+    const float *marginal = nullptr, *conditional = nullptr, *light = nullptr, *miss = nullptr;
+    float rotation = 0.f, exposureScale = 1.f;
+};
+static inline void sampleDistribution(const float* dist, int64_t count, float random01, uint32_t& index, float& pdf) {  // :81-103
+    index = 0xFFFFFFFFu;
+    int64_t low = 0, high = count - 1;
+    while (low <= high) {
+        int64_t mid = (low + high) / 2;
+        if (dist[mid] >= random01) {
+            index = (uint32_t)mid;
+            pdf = (mid > 0) ? dist[mid] - dist[mid - 1] : dist[mid];
+            high = mid - 1;
+        } else {
+            low = mid + 1;
+        }
+    }
+}
+static inline void iblSample(const Ibl& ibl, float r0, float r1, float& theta, float& phi, uint32_t& x, uint32_t& y, float& pdf) {  // :118-151
+    float widthf = (float)ibl.width, heightf = (float)ibl.height;
+    float mdf = 0.f, cdf = 0.f;
+    sampleDistribution(ibl.marginal, ibl.height, r0, y, mdf);
+    if (y == 0xFFFFFFFFu) y = ibl.height - 1;  // r0 above the last CDF entry cannot happen (it is forced to 1); guard anyway
+    sampleDistribution(ibl.conditional + (size_t)y * ibl.width, ibl.width, r1, x, cdf);
+    if (x == 0xFFFFFFFFu) x = ibl.width - 1;
+    theta = (y + 0.5f) * kPi / heightf;
+    phi = fmodf(((x + 0.5f) * kTwoPi / widthf) + ibl.rotation, kTwoPi) - kPi;
+    float invJacobian = (widthf * heightf) / kTwoPi;
+    float sinTheta = sinf(theta);
+    pdf = (sinTheta > 0) ? mdf * cdf * invJacobian / sinTheta : 0.0f;
+}
+// texel addressing shared by SampleIbl / SampleIblMiss / SampleIBlPdf (:160-169).  QUIRK (appendix B #23): Clamp(.., 0, width)
+// lets x reach width (the first texel of the next row) and y reach height; the linear index is clamped to the last texel here,
+// as the CUDA path does, where the reference would read past the image.
+static inline void iblTexel(V3 wi, float rotation, uint32_t width, uint32_t height, int32_t& x, int32_t& y, float& theta) {
+    float widthf = (float)(int32_t)width, heightf = (float)(int32_t)height;
+    theta = acosf(wi.y);                 // NormalizedCartesianToSpherical, MathLib/Projection.cpp:109-113
+    float phi = atan2f(wi.z, wi.x);
+    phi = fmodf(phi + kPi + rotation, kTwoPi);
+    x = (int32_t)(phi * widthf / kTwoPi - 0.5f);
+    y = (int32_t)(theta * heightf / kPi - 0.5f);
+    x = x < 0 ? 0 : (x > (int32_t)width ? (int32_t)width : x);
+    y = y < 0 ? 0 : (y > (int32_t)height ? (int32_t)height : y);
+}
+static inline size_t iblIndex(int32_t x, int32_t y, uint32_t width, uint32_t height) {
+    size_t i = (size_t)y * width + (size_t)x, last = (size_t)width * height - 1;
+    return i > last ? last : i;
+}
+static inline float iblPdf(const Ibl& ibl, V3 wi) {  // SampleIBlPdf, :221-262
+    int32_t x, y;
+    float theta;
+    iblTexel(wi, ibl.rotation, ibl.width, ibl.height, x, y, theta);
+    float widthf = (float)(int32_t)ibl.width, heightf = (float)(int32_t)ibl.height;
+    if (y > (int32_t)ibl.height - 1) y = (int32_t)ibl.height - 1;  // unreachable for theta in [0, pi]; keeps the reads in range
+    if (x > (int32_t)ibl.width - 1) x = (int32_t)ibl.width - 1;
+    float mdf = (y > 0) ? ibl.marginal[y] - ibl.marginal[y - 1] : ibl.marginal[y];
+    size_t i = iblIndex(x, y, ibl.width, ibl.height);
+    float cdf = (x > 0) ? ibl.conditional[i] - ibl.conditional[i - 1] : ibl.conditional[i];
+    float invJacobian = (widthf * heightf) / kTwoPi;
+    float sinTheta = sinf(theta);
+    return (sinTheta > 0) ? mdf * cdf * invJacobian / sinTheta : 0.0f;
+}
+static inline V3 iblLookup(const Ibl& ibl, V3 wi, float& pdf) {  // SampleIbl(ibl, wi, pdf), :154-195
+    pdf = iblPdf(ibl, wi);
+    int32_t x, y;
+    float theta;
+    iblTexel(wi, ibl.rotation, ibl.width, ibl.height, x, y, theta);
+    return ibl.exposureScale * v3(ibl.light + 3 * iblIndex(x, y, ibl.width, ibl.height));
+}
+static inline V3 iblLookupMiss(const Ibl& ibl, V3 wi, float& pdf) {  // SampleIblMiss, :198-218 (no exposure scale there)
+    pdf = iblPdf(ibl, wi);
+    int32_t x, y;
+    float theta;
+    iblTexel(wi, ibl.rotation, ibl.missWidth, ibl.missHeight, x, y, theta);
+    return v3(ibl.miss + 3 * iblIndex(x, y, ibl.missWidth, ibl.missHeight));
+}
+
 // ---- camera: GeometryLib/Camera.cpp:56-60, :89-115 -------------------------------------------------------
 static inline void initCamera(const SelasCameraSettings& st, uint32_t width, uint32_t height, SelasCamera& cam) {
     float widthf = (float)width, heightf = (float)height;

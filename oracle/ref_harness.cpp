@@ -27,6 +27,7 @@
 #include "Shading/VolumetricScattering.h"
 #include "Shading/Scattering.h"
 #include "SceneLib/SceneResource.h"
+#include "SceneLib/ImageBasedLightResource.h"
 #include "GeometryLib/Camera.h"
 #include "GeometryLib/Ray.h"
 #include "GeometryLib/CoordinateSystem.h"
@@ -148,6 +149,15 @@ struct FakeContext {
     alignas(16) unsigned char dataBytes[sizeof(SceneResourceData)];
     std::vector<SceneLight> lights;
     std::vector<SceneLightSet> sets;
+    alignas(16) unsigned char iblResBytes[sizeof(ImageBasedLightResource)];
+    ImageBasedLightResourceData iblData;
+    void setIbl(const ImageBasedLightResourceData* src) {  // borrowed arrays; the resource struct is never destructed
+        if (!src) return;
+        iblData = *src;
+        ImageBasedLightResource* res = reinterpret_cast<ImageBasedLightResource*>(iblResBytes);
+        res->data = &iblData;
+        scene()->iblResource = res;
+    }
     GIIntegratorContext* ctx() { return reinterpret_cast<GIIntegratorContext*>(ctxBytes); }
     SceneResource* scene() { return reinterpret_cast<SceneResource*>(sceneBytes); }
     SceneResourceData* data() { return reinterpret_cast<SceneResourceData*>(dataBytes); }
@@ -395,8 +405,49 @@ int ref_vcm_iteration_constants(uint32_t vmCount, uint32_t vcCount, float baseRa
     return 0;
 }
 
+// ImageBasedLightResource.cpp: SampleIbl / SampleIblMiss / Ibl on a scene created with an IBL (ref_scene_create)
+int ref_ibl_lookup(void* s, size_t n, const float* wi3, float* rgb3, float* pdf, float* miss3);
+int ref_ibl_sample(void* s, size_t n, const float* u2, float* thetaPhiPdf3, uint32_t* xy2);
+
 // ---- tier-B CPU integrator: reference shading + restated ray cast --------------------------------------------
+struct RefIbl {
+    std::vector<float> marginal, conditional, light, miss;
+    ImageBasedLightResourceData data;
+    bool present = false;
+    void set(const SelasIblDesc* I) {
+        if (!I) return;
+        marginal.assign(I->marginalDensityFunction, I->marginalDensityFunction + I->height);
+        conditional.assign(I->conditionalDensityFunctions, I->conditionalDensityFunctions + (size_t)I->width * I->height);
+        // the reference clamps texel coordinates to [0, width] / [0, height] (appendix B #23) and can read one row past the image;
+        // pad one row (a copy of the last texel, which is what the restatement and the CUDA path read) so that stays defined
+        light.assign(I->lightData, I->lightData + 3 * (size_t)I->width * I->height);
+        miss.assign(I->missData, I->missData + 3 * (size_t)I->missWidth * I->missHeight);
+        auto pad = [](std::vector<float>& img, size_t w) {
+            float last[3] = {img[img.size() - 3], img[img.size() - 2], img[img.size() - 1]};
+            for (size_t i = 0; i < w + 1; ++i) img.insert(img.end(), last, last + 3);
+        };
+        pad(light, I->width);
+        pad(miss, I->missWidth);
+        float lastC = conditional.back();
+        conditional.resize(conditional.size() + I->width + 1, lastC);
+        marginal.push_back(marginal.back());
+        memset(&data, 0, sizeof(data));
+        data.densityfunctions.width = I->width;
+        data.densityfunctions.height = I->height;
+        data.densityfunctions.marginalDensityFunction = marginal.data();
+        data.densityfunctions.conditionalDensityFunctions = conditional.data();
+        data.missWidth = I->missWidth;
+        data.missHeight = I->missHeight;
+        data.rotationRadians = I->rotationRadians;
+        data.exposureScale = I->exposureScale;
+        data.lightData = reinterpret_cast<float3*>(light.data());
+        data.missData = reinterpret_cast<float3*>(miss.data());
+        present = true;
+    }
+};
+
 struct RefScene {
+    RefIbl ibl;
     struct Mesh {
         std::vector<float> positions, normals, tangents;
         std::vector<uint32_t> indices;
@@ -445,6 +496,7 @@ int ref_scene_create(const SelasSceneDesc* d, void** out) {
     sc->lights.assign(d->lights, d->lights + d->lightCount);
     sc->sets.assign(d->lightSets, d->lightSets + d->lightSetCount);
     memcpy(sc->background, d->backgroundIntensity, sizeof(sc->background));
+    sc->ibl.set(d->ibl);
     sc->bvh.build();
     *out = sc;
     return 0;
@@ -535,6 +587,7 @@ int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
         setFtz();
         FakeContext fc;
         fc.init(sc.lights.data(), (uint32_t)sc.lights.size(), sc.sets.data(), (uint32_t)sc.sets.size(), sc.background);
+        if (sc.ibl.present) fc.setIbl(&sc.ibl.data);
         GIIntegratorContext* ctx = fc.ctx();
         ctx->camera = &rc;
         ctx->maxPathLength = rs->maxPathLength;
@@ -646,6 +699,33 @@ int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
         stats->closestRays = closest;
         stats->occlusionRays = shadow;
         stats->pathSamples = ((pixels + stride - 1) / stride) * rs->samplesPerPixel;
+    }
+    return 0;
+}
+
+int ref_ibl_lookup(void* s, size_t n, const float* wi3, float* rgb3, float* pdf, float* miss3) {
+    setFtz();
+    const RefScene& sc = *(RefScene*)s;
+    if (!sc.ibl.present) return 2;
+    for (size_t i = 0; i < n; ++i) {
+        float p = 0.f;
+        float3 c = SampleIbl(&sc.ibl.data, f3(wi3 + 3 * i), p);
+        if (rgb3) st3(rgb3 + 3 * i, c);
+        if (pdf) pdf[i] = p;
+        if (miss3) st3(miss3 + 3 * i, SampleIblMiss(&sc.ibl.data, f3(wi3 + 3 * i), p));
+    }
+    return 0;
+}
+int ref_ibl_sample(void* s, size_t n, const float* u2, float* thetaPhiPdf3, uint32_t* xy2) {
+    setFtz();
+    const RefScene& sc = *(RefScene*)s;
+    if (!sc.ibl.present) return 2;
+    for (size_t i = 0; i < n; ++i) {
+        float theta, phi, pdf;
+        Selas::uint x, y;
+        Ibl(&sc.ibl.data, u2[2 * i], u2[2 * i + 1], theta, phi, x, y, pdf);
+        thetaPhiPdf3[3 * i] = theta; thetaPhiPdf3[3 * i + 1] = phi; thetaPhiPdf3[3 * i + 2] = pdf;
+        xy2[2 * i] = (uint32_t)x; xy2[2 * i + 1] = (uint32_t)y;
     }
     return 0;
 }

@@ -43,6 +43,9 @@ struct Scene {
     std::vector<SelasLight> lights;
     std::vector<SelasLightSetRange> lightSets;
     float background[4];
+    bool hasIbl = false;
+    Ibl ibl;
+    std::vector<float> iblMarginal, iblConditional, iblLight, iblMiss;
     Bvh bvh;
 };
 
@@ -339,8 +342,13 @@ static void evaluatePath(const Scene& sc, const SelasCamera& cam, const SelasRen
             ray.ox = org.x; ray.oy = org.y; ray.oz = org.z;
             ray.dx = nd.x; ray.dy = nd.y; ray.dz = nd.z;
         } else {
-            (void)isDeltaOnly;  // no IBL: EvaluateBackground == EvaluateBackgroundMiss, AreaLighting.cpp:415-437
-            Ld[1] = Ld[1] + background * throughput;
+            V3 smp = background;  // EvaluateBackground / EvaluateBackgroundMiss, AreaLighting.cpp:415-437
+            if (sc.hasIbl) {
+                float pdf;
+                V3 dirv = v3(ray.dx, ray.dy, ray.dz);
+                smp = isDeltaOnly ? iblLookupMiss(sc.ibl, dirv, pdf) : iblLookup(sc.ibl, dirv, pdf);
+            }
+            Ld[1] = Ld[1] + smp * throughput;
             break;
         }
         ++bounce;
@@ -388,6 +396,18 @@ int orc_scene_create(const SelasSceneDesc* d, void** out) {
     sc->lights.assign(d->lights, d->lights + d->lightCount);
     sc->lightSets.assign(d->lightSets, d->lightSets + d->lightSetCount);
     memcpy(sc->background, d->backgroundIntensity, sizeof(sc->background));
+    if (d->ibl) {
+        const SelasIblDesc& I = *d->ibl;
+        sc->iblMarginal.assign(I.marginalDensityFunction, I.marginalDensityFunction + I.height);
+        sc->iblConditional.assign(I.conditionalDensityFunctions, I.conditionalDensityFunctions + (size_t)I.width * I.height);
+        sc->iblLight.assign(I.lightData, I.lightData + 3 * (size_t)I.width * I.height);
+        sc->iblMiss.assign(I.missData, I.missData + 3 * (size_t)I.missWidth * I.missHeight);
+        sc->ibl.width = I.width; sc->ibl.height = I.height; sc->ibl.missWidth = I.missWidth; sc->ibl.missHeight = I.missHeight;
+        sc->ibl.marginal = sc->iblMarginal.data(); sc->ibl.conditional = sc->iblConditional.data();
+        sc->ibl.light = sc->iblLight.data(); sc->ibl.miss = sc->iblMiss.data();
+        sc->ibl.rotation = I.rotationRadians; sc->ibl.exposureScale = I.exposureScale;
+        sc->hasIbl = true;
+    }
     for (uint32_t ii = 0; ii < sc->instances.size(); ++ii) {
         const Instance& in = sc->instances[ii];
         for (uint32_t m = 0; m < sc->meshes.size(); ++m) {
@@ -558,6 +578,32 @@ int orc_surface_params(void* s, size_t n, const SelasRay* rays, const SelasHit* 
     for (size_t i = 0; i < n; ++i) {
         memset(&out[i], 0, sizeof(SelasSurface));
         if (hits[i].geomID != SELAS_INVALID_ID) surfaceParams(sc, rays[i], hits[i], out[i]);
+    }
+    return 0;
+}
+int orc_ibl_lookup(void* s, size_t n, const float* wi3, float* rgb3, float* pdf, float* miss3) {
+    setFtz();
+    const Scene& sc = *(Scene*)s;
+    if (!sc.hasIbl) return 2;
+    for (size_t i = 0; i < n; ++i) {
+        float p = 0.f;
+        V3 c = iblLookup(sc.ibl, v3(wi3 + 3 * i), p);
+        if (rgb3) store(rgb3 + 3 * i, c);
+        if (pdf) pdf[i] = p;
+        if (miss3) store(miss3 + 3 * i, iblLookupMiss(sc.ibl, v3(wi3 + 3 * i), p));
+    }
+    return 0;
+}
+int orc_ibl_sample(void* s, size_t n, const float* u2, float* thetaPhiPdf3, uint32_t* xy2) {
+    setFtz();
+    const Scene& sc = *(Scene*)s;
+    if (!sc.hasIbl) return 2;
+    for (size_t i = 0; i < n; ++i) {
+        float theta, phi, pdf;
+        uint32_t x, y;
+        iblSample(sc.ibl, u2[2 * i], u2[2 * i + 1], theta, phi, x, y, pdf);
+        thetaPhiPdf3[3 * i] = theta; thetaPhiPdf3[3 * i + 1] = phi; thetaPhiPdf3[3 * i + 2] = pdf;
+        xy2[2 * i] = x; xy2[2 * i + 1] = y;
     }
     return 0;
 }

@@ -61,11 +61,17 @@ class InstanceDesc(C.Structure):
     _fields_ = [("meshIndex", u32), ("localToWorld", f32 * 16)]
 
 
+class IblDesc(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("marginalDensityFunction", C.c_void_p), ("conditionalDensityFunctions", C.c_void_p),
+                ("lightData", C.c_void_p), ("missWidth", u32), ("missHeight", u32), ("missData", C.c_void_p),
+                ("rotationRadians", f32), ("exposureScale", f32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("meshes", C.POINTER(MeshDesc)), ("meshCount", u32), ("instances", C.POINTER(InstanceDesc)),
                 ("instanceCount", u32), ("materials", C.POINTER(Material)), ("materialCount", u32),
                 ("lights", C.POINTER(Light)), ("lightCount", u32), ("lightSets", C.POINTER(LightSetRange)),
-                ("lightSetCount", u32), ("backgroundIntensity", f32 * 4)]
+                ("lightSetCount", u32), ("backgroundIntensity", f32 * 4), ("ibl", C.POINTER(IblDesc))]
 
 
 class RenderSettings(C.Structure):
@@ -116,6 +122,7 @@ EXPORTS = [
     "selas_cuda_intersect", "selas_cuda_occluded", "selas_cuda_intersect_device", "selas_cuda_occluded_device",
     "selas_cuda_intersect_counted", "selas_cuda_camera_init", "selas_cuda_camera_rays", "selas_cuda_cmj", "selas_cuda_bsdf_eval",
     "selas_cuda_bsdf_sample", "selas_cuda_light_sample", "selas_cuda_light_pdf", "selas_cuda_surface_params",
+    "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample",
     "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_film_scale_device",
     "selas_cuda_hashgrid_build", "selas_cuda_hashgrid_destroy", "selas_cuda_hashgrid_read",
     "selas_cuda_hashgrid_query", "selas_cuda_hashgrid_build_device", "selas_cuda_hashgrid_query_device",
@@ -277,7 +284,8 @@ class SceneData:
     meshes: list of dicts {positions (V,3) f32, indices (F,3|4) u32, normals?, tangents?, uvs?, material, lightSet, ptex?}
     """
 
-    def __init__(self, meshes, materials, lights=None, light_sets=None, background=(0, 0, 0, 0), instances=None):
+    def __init__(self, meshes, materials, lights=None, light_sets=None, background=(0, 0, 0, 0), instances=None, ibl=None):
+        self.ibl = ibl  # dict: light (H,W,3), marginal (H,), conditional (H,W), miss (h,w,3), rotation, exposure_scale -- see scenes.build_ibl
         self.meshes = []
         for m in meshes:
             mm = dict(m)
@@ -337,6 +345,21 @@ class SceneData:
         desc.lightSets = C.cast(self.light_sets.ctypes.data, C.POINTER(LightSetRange))
         desc.lightSetCount = self.light_sets.shape[0]
         desc.backgroundIntensity[:] = self.background
+        if self.ibl is not None:
+            i = self.ibl
+            for k in ("light", "marginal", "conditional", "miss"):
+                i[k] = np.ascontiguousarray(i[k], dtype=np.float32)
+            d = IblDesc()
+            d.height, d.width = i["light"].shape[0], i["light"].shape[1]
+            d.marginalDensityFunction = i["marginal"].ctypes.data
+            d.conditionalDensityFunctions = i["conditional"].ctypes.data
+            d.lightData = i["light"].ctypes.data
+            d.missHeight, d.missWidth = i["miss"].shape[0], i["miss"].shape[1]
+            d.missData = i["miss"].ctypes.data
+            d.rotationRadians = i.get("rotation", 0.0)
+            d.exposureScale = i.get("exposure_scale", 1.0)
+            desc.ibl = C.pointer(d)
+            keep.append(d)
         keep.append(md)
         return desc, keep
 
@@ -397,6 +420,20 @@ class Scene:
         out = np.zeros(rays.size, dtype=SURFACE_DTYPE)
         self.ctx.check(self.lib.selas_cuda_surface_params(self.handle, C.c_size_t(rays.size), _ptr(rays), _ptr(hits), _ptr(out)))
         return out
+
+    def ibl_lookup(self, wi):
+        wi = _f32(wi).reshape(-1, 3)
+        n = wi.shape[0]
+        rgb, pdf, miss = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        self.ctx.check(self.lib.selas_cuda_ibl_lookup(self.handle, C.c_size_t(n), _ptr(wi), _ptr(rgb), _ptr(pdf), _ptr(miss)))
+        return rgb, pdf, miss
+
+    def ibl_sample(self, u2):
+        u2 = _f32(u2).reshape(-1, 2)
+        n = u2.shape[0]
+        tpp, xy = np.zeros((n, 3), np.float32), np.zeros((n, 2), np.uint32)
+        self.ctx.check(self.lib.selas_cuda_ibl_sample(self.handle, C.c_size_t(n), _ptr(u2), _ptr(tpp), _ptr(xy)))
+        return tpp, xy
 
     def render(self, camera: Camera, settings: RenderSettings):
         """PathTracer::GenerateImage (PathTracer.cpp:301-350) with host film buffers; returns (layers, stats).

@@ -254,6 +254,23 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
     g.lightCount = d->lightCount;
     g.lightSetCount = d->lightSetCount;
     memcpy(g.background, d->backgroundIntensity, sizeof(g.background));
+    memset(&g.ibl, 0, sizeof(g.ibl));
+    if (d->ibl) {
+        const SelasIblDesc& I = *d->ibl;
+        if (!I.width || !I.height || !I.missWidth || !I.missHeight || !I.marginalDensityFunction || !I.conditionalDensityFunctions ||
+            !I.lightData || !I.missData) {
+            setError(ctx, "ibl: width/height and all four arrays are required");
+            return SELAS_ERR_ARGUMENT;
+        }
+        SELAS_TRY(sceneUpload(scene, &g.ibl.marginal, I.marginalDensityFunction, I.height));
+        SELAS_TRY(sceneUpload(scene, &g.ibl.conditional, I.conditionalDensityFunctions, (size_t)I.width * I.height));
+        SELAS_TRY(sceneUpload(scene, &g.ibl.light, I.lightData, 3 * (size_t)I.width * I.height));
+        SELAS_TRY(sceneUpload(scene, &g.ibl.miss, I.missData, 3 * (size_t)I.missWidth * I.missHeight));
+        g.ibl.width = I.width; g.ibl.height = I.height; g.ibl.missWidth = I.missWidth; g.ibl.missHeight = I.missHeight;
+        g.ibl.rotation = I.rotationRadians;
+        g.ibl.exposureScale = I.exposureScale;
+        g.ibl.present = 1;
+    }
 
     SELAS_TRY(buildBvh(scene, meshes, inst, g.instances));
     uint64_t attrBytes = 0;
@@ -453,6 +470,59 @@ int selas_cuda_camera_rays(SelasContext* ctx, const SelasCamera* camera, size_t 
     SELAS_TRY(s.alloc(&d_rays, n));
     SELAS_TRY(launchCameraRays(ctx, *camera, n, d_px, d_py, d_j, d_rays));
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(rays, d_rays, n * sizeof(SelasRay), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_ibl_lookup(SelasScene* scene, size_t n, const float* wi3, float* rgb3, float* pdf, float* missRgb3) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (!scene->gpu.ibl.present) {
+        setError(ctx, "selas_cuda_ibl_lookup: the scene has no image based light");
+        return SELAS_ERR_ARGUMENT;
+    }
+    if (n == 0) return SELAS_OK;
+    if (!wi3) {
+        setError(ctx, "selas_cuda_ibl_lookup: wi3 is null");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    float *d_wi, *d_rgb = nullptr, *d_pdf = nullptr, *d_miss = nullptr;
+    SELAS_TRY(s.upload(&d_wi, wi3, 3 * n));
+    if (rgb3) SELAS_TRY(s.alloc(&d_rgb, 3 * n));
+    if (pdf) SELAS_TRY(s.alloc(&d_pdf, n));
+    if (missRgb3) SELAS_TRY(s.alloc(&d_miss, 3 * n));
+    SELAS_TRY(launchIblLookup(scene, n, d_wi, d_rgb, d_pdf, d_miss));
+    if (rgb3) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(rgb3, d_rgb, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pdf) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(pdf, d_pdf, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (missRgb3) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(missRgb3, d_miss, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_ibl_sample(SelasScene* scene, size_t n, const float* u2, float* thetaPhiPdf3, uint32_t* xy2) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (!scene->gpu.ibl.present) {
+        setError(ctx, "selas_cuda_ibl_sample: the scene has no image based light");
+        return SELAS_ERR_ARGUMENT;
+    }
+    if (n == 0) return SELAS_OK;
+    if (!u2 || !thetaPhiPdf3 || !xy2) {
+        setError(ctx, "selas_cuda_ibl_sample: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    Scratch s(ctx);
+    float *d_u, *d_t;
+    uint32_t* d_xy;
+    SELAS_TRY(s.upload(&d_u, u2, 2 * n));
+    SELAS_TRY(s.alloc(&d_t, 3 * n));
+    SELAS_TRY(s.alloc(&d_xy, 2 * n));
+    SELAS_TRY(launchIblSample(scene, n, d_u, d_t, d_xy));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(thetaPhiPdf3, d_t, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(xy2, d_xy, 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return SELAS_OK;
 }

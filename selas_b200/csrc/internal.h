@@ -34,6 +34,17 @@ struct InstanceGpu {
     uint32_t pad[2];
 };
 
+// ImageBasedLightResourceData on the device (ImageBasedLightResource.h:16-35)
+struct IblGpu {
+    const float* marginal;     // height
+    const float* conditional;  // width*height
+    const float* light;        // float3 per texel
+    const float* miss;         // float3 per texel
+    uint32_t width, height, missWidth, missHeight;
+    float rotation, exposureScale;
+    uint32_t present, pad;
+};
+
 // Everything the shade kernel needs, passed by value.
 struct SceneGpu {
     const float4* nodes;
@@ -46,6 +57,7 @@ struct SceneGpu {
     const SelasLightSetRange* lightSets;
     uint32_t meshCount, instanceCount, materialCount, lightCount, lightSetCount;
     float background[4];
+    IblGpu ibl;
 };
 
 struct DeviceBuffer {
@@ -116,6 +128,8 @@ int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, con
 int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
                      cudaStream_t stream);
 int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream);
+int launchIblLookup(SelasScene* scene, size_t n, const float* d_wi3, float* d_rgb3, float* d_pdf, float* d_miss3);
+int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp3, uint32_t* d_xy2);
 int launchCmj(SelasContext* ctx, size_t count, const int32_t* d_s, int32_t m, int32_t n, const int32_t* d_p, float* d_out2);
 void freeWavefront(SelasScene* scene);
 

@@ -9,6 +9,7 @@
 //   ImageToWorldDirection / JitteredCameraRay              GeometryLib/Camera.cpp:56-74
 #pragma once
 #include "../../include/selas_cuda.h"
+#include "internal.h"
 #include "vec.cuh"
 
 namespace selas {
@@ -228,6 +229,74 @@ SELAS_HD V3 imageToWorldDirection(const SelasCamera& cam, float x, float y) {
     float cx = ((x / (uint32_t)cam.width) * 2.0f - 1.0f);
     float cy = 1.0f - 2.0f * y / (uint32_t)cam.height;
     return normalize(lightF3(cam.cameraZ) - cx * lightF3(cam.cameraX) + cy * lightF3(cam.cameraY));
+}
+
+// ---- image based light: SceneLib/ImageBasedLightResource.cpp:81-262 ------------------------------------------------------
+SELAS_D void iblSampleDistribution(const float* __restrict__ dist, int count, float random01, uint32_t& index, float& pdf) {  // :81-103
+    index = 0xFFFFFFFFu;
+    int low = 0, high = count - 1;
+    while (low <= high) {
+        int mid = (low + high) / 2;
+        float d = __ldg(dist + mid);
+        if (d >= random01) {
+            index = (uint32_t)mid;
+            pdf = (mid > 0) ? d - __ldg(dist + mid - 1) : d;
+            high = mid - 1;
+        } else {
+            low = mid + 1;
+        }
+    }
+}
+SELAS_D void iblSample(const IblGpu& ibl, float r0, float r1, float& theta, float& phi, uint32_t& x, uint32_t& y, float& pdf) {  // Ibl(), :118-151
+    float widthf = (float)ibl.width, heightf = (float)ibl.height;
+    float mdf = 0.f, cdf = 0.f;
+    iblSampleDistribution(ibl.marginal, (int)ibl.height, r0, y, mdf);
+    if (y == 0xFFFFFFFFu) y = ibl.height - 1;
+    iblSampleDistribution(ibl.conditional + (size_t)y * ibl.width, (int)ibl.width, r1, x, cdf);
+    if (x == 0xFFFFFFFFu) x = ibl.width - 1;
+    theta = (y + 0.5f) * SELAS_PI / heightf;
+    phi = fmodf(((x + 0.5f) * SELAS_TWO_PI / widthf) + ibl.rotation, SELAS_TWO_PI) - SELAS_PI;
+    float invJacobian = (widthf * heightf) / SELAS_TWO_PI;
+    float sinTheta = sinf(theta);
+    pdf = (sinTheta > 0) ? mdf * cdf * invJacobian / sinTheta : 0.0f;
+}
+// Texel addressing of SampleIbl / SampleIblMiss / SampleIBlPdf (:160-169).  QUIRK: the reference clamps to [0, width] / [0, height]
+// (one past the image); those values cannot be reached for a unit direction, and the reads are kept in range here.
+SELAS_D void iblTexel(V3 wi, float rotation, uint32_t width, uint32_t height, int& x, int& y, float& theta) {
+    float widthf = (float)(int)width, heightf = (float)(int)height;
+    theta = acosf(wi.y);  // NormalizedCartesianToSpherical, MathLib/Projection.cpp:109-113
+    float phi = atan2f(wi.z, wi.x);
+    phi = fmodf(phi + SELAS_PI + rotation, SELAS_TWO_PI);
+    x = (int)(phi * widthf / SELAS_TWO_PI - 0.5f);
+    y = (int)(theta * heightf / SELAS_PI - 0.5f);
+    x = x < 0 ? 0 : (x > (int)width - 1 ? (int)width - 1 : x);
+    y = y < 0 ? 0 : (y > (int)height - 1 ? (int)height - 1 : y);
+}
+SELAS_D float iblPdf(const IblGpu& ibl, V3 wi) {  // SampleIBlPdf, :221-262
+    int x, y;
+    float theta;
+    iblTexel(wi, ibl.rotation, ibl.width, ibl.height, x, y, theta);
+    float widthf = (float)(int)ibl.width, heightf = (float)(int)ibl.height;
+    float mdf = (y > 0) ? __ldg(ibl.marginal + y) - __ldg(ibl.marginal + y - 1) : __ldg(ibl.marginal + y);
+    const float* row = ibl.conditional + (size_t)y * ibl.width;
+    float cdf = (x > 0) ? __ldg(row + x) - __ldg(row + x - 1) : __ldg(row + x);
+    float invJacobian = (widthf * heightf) / SELAS_TWO_PI;
+    float sinTheta = sinf(theta);
+    return (sinTheta > 0) ? mdf * cdf * invJacobian / sinTheta : 0.0f;
+}
+SELAS_D V3 iblLookup(const IblGpu& ibl, V3 wi) {  // SampleIbl(ibl, wi, pdf) without the pdf, :154-195
+    int x, y;
+    float theta;
+    iblTexel(wi, ibl.rotation, ibl.width, ibl.height, x, y, theta);
+    const float* t = ibl.light + 3 * ((size_t)y * ibl.width + x);
+    return ibl.exposureScale * v3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
+}
+SELAS_D V3 iblLookupMiss(const IblGpu& ibl, V3 wi) {  // SampleIblMiss, :198-218 (no exposure scale there)
+    int x, y;
+    float theta;
+    iblTexel(wi, ibl.rotation, ibl.missWidth, ibl.missHeight, x, y, theta);
+    const float* t = ibl.miss + 3 * ((size_t)y * ibl.missWidth + x);
+    return v3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
 }
 
 // ---- correlated multi-jitter (MathLib/CorrelatedMultiJitter.cpp:12-62; Kensler 2013) ---------------------------------

@@ -105,6 +105,25 @@ __global__ void cameraRaysKernel(SelasCamera cam, size_t n, const float* __restr
     o[1] = make_float4(d.x, d.y, d.z, SELAS_FLOAT_MAX);
 }
 
+__global__ void iblLookupKernel(IblGpu ibl, size_t n, const float* __restrict__ wi3, float* __restrict__ rgb3, float* __restrict__ pdf,
+                                float* __restrict__ miss3) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 wi = v3(wi3 + 3 * i);
+    if (rgb3) store3(rgb3 + 3 * i, iblLookup(ibl, wi));
+    if (pdf) pdf[i] = iblPdf(ibl, wi);
+    if (miss3) store3(miss3 + 3 * i, iblLookupMiss(ibl, wi));
+}
+__global__ void iblSampleKernel(IblGpu ibl, size_t n, const float* __restrict__ u2, float* __restrict__ tpp3, uint32_t* __restrict__ xy2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float theta, phi, pdf;
+    uint32_t x, y;
+    iblSample(ibl, u2[2 * i], u2[2 * i + 1], theta, phi, x, y, pdf);
+    tpp3[3 * i] = theta; tpp3[3 * i + 1] = phi; tpp3[3 * i + 2] = pdf;
+    xy2[2 * i] = x; xy2[2 * i + 1] = y;
+}
+
 __global__ void cmjKernel(size_t count, const int32_t* __restrict__ sIdx, int32_t m, int32_t n, const int32_t* __restrict__ p, float* __restrict__ out2) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -183,6 +202,18 @@ int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, con
         cudaStreamSynchronize(scene->ctx->stream);
         cudaFree(d_rgb);
     }
+    SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchIblLookup(SelasScene* scene, size_t n, const float* d_wi3, float* d_rgb3, float* d_pdf, float* d_miss3) {
+    if (!n) return SELAS_OK;
+    iblLookupKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu.ibl, n, d_wi3, d_rgb3, d_pdf, d_miss3);
+    SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp3, uint32_t* d_xy2) {
+    if (!n) return SELAS_OK;
+    iblSampleKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu.ibl, n, d_u2, d_tpp3, d_xy2);
     SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -535,8 +566,12 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
             o = o + rayDistance * d;
             d = uniformSphere(rng);
             alive = true;
-        } else {  // escaped: background, :234-243 (no IBL: both background variants are the constant)
-            V3 c = v3(sc.background[0], sc.background[1], sc.background[2]) * thr;
+        } else {  // escaped: background, :234-243
+            // EvaluateBackground / EvaluateBackgroundMiss, AreaLighting.cpp:415-437: the IBL when the scene has one (the
+            // "miss" image for paths that only saw delta events), else the constant background
+            V3 bg = v3(sc.background[0], sc.background[1], sc.background[2]);
+            if (sc.ibl.present) bg = deltaOnly ? iblLookupMiss(sc.ibl, d) : iblLookup(sc.ibl, d);
+            V3 c = bg * thr;
             if (prm.skipNonFinite && !(isfinite(c.x) && isfinite(c.y) && isfinite(c.z))) c = v3(0.0f);
             atomicAdd(filmRadiance + 3 * (size_t)pixel, c.x);
             atomicAdd(filmRadiance + 3 * (size_t)pixel + 1, c.y);

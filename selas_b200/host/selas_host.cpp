@@ -318,6 +318,7 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
     desc.lightSets = scene->lightSets.data();
     desc.lightSetCount = (uint32_t)scene->lightSets.size();
     memcpy(desc.backgroundIntensity, scene->backgroundIntensity, sizeof(desc.backgroundIntensity));
+    desc.ibl = scene->ibl;
     if (selas_cuda_scene_create(scene->gpu, &desc, &scene->gpuScene) != SELAS_OK) {
         Error e = Error_("%s", selas_cuda_last_error(scene->gpu));
         ShutdownSceneResource(scene);

@@ -93,6 +93,7 @@ struct SceneResource {
     std::vector<SelasLight> lights;
     std::vector<SelasLightSetRange> lightSets;
     float backgroundIntensity[4] = {0, 0, 0, 0};
+    const SelasIblDesc* ibl = nullptr;  // SceneResource::iblResource (borrowed), or null: constant background
     // device side
     SelasContext* gpu = nullptr;
     SelasScene* gpuScene = nullptr;

@@ -385,3 +385,35 @@ def ptex_quad_grid(nu=1581, nv=1581, ptex=None, seed=4):
 
 def ptex_grid_camera(width=1920, height=1080):
     return capi.camera_init((0.0, -9.0, -14.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 55.0, width, height)
+
+
+# ---- image based light (config 5 and the background of any scene) ----------------------------------------------------
+def build_ibl(light, miss=None, rotation=0.0, exposure=0.0):
+    """The bake step's density functions for a lat-long environment image (BuildCommon/BuildImageBasedLight.cpp:24-105):
+    intensity = sin(theta) * CIE luma, per-row inclusive CDFs normalised to 1, marginal inclusive CDF over the row sums."""
+    light = np.ascontiguousarray(light, dtype=np.float32)
+    h, w = light.shape[:2]
+    theta = ((np.arange(h, dtype=np.float32) + np.float32(0.5)) * np.float32(math.pi) / np.float32(h)).astype(np.float32)
+    luma = light[..., 0] * np.float32(0.299) + light[..., 1] * np.float32(0.587) + light[..., 2] * np.float32(0.114)
+    inten = (np.sin(theta).astype(np.float32)[:, None] * luma).astype(np.float32)
+    rows = np.cumsum(inten, axis=1, dtype=np.float32)
+    row_sum = rows[:, -1].copy()
+    cond = np.zeros((h, w), np.float32)
+    nz = row_sum > 0
+    cond[nz] = np.cumsum((np.float32(1.0) / row_sum[nz])[:, None] * inten[nz], axis=1, dtype=np.float32)
+    cond[:, -1] = 1.0
+    total = np.cumsum(row_sum, dtype=np.float32)[-1]
+    marg = np.cumsum(row_sum * (np.float32(1.0) / total), dtype=np.float32) if total > 0 else row_sum.copy()
+    marg[-1] = 1.0
+    return dict(light=light, marginal=marg.astype(np.float32), conditional=cond, miss=light if miss is None else np.ascontiguousarray(miss, np.float32),
+                rotation=float(rotation), exposure_scale=float(2.0 ** exposure))
+
+
+def sun_sky_ibl(width=1024, height=512, sun_theta_deg=40.0, sun_nits=5000.0, sky=0.2):
+    """sky of constant radiance with a 16x16-texel sun at theta = 40 degrees; a dimmer copy as the miss image."""
+    img = np.full((height, width, 3), sky, np.float32)
+    y0 = int(sun_theta_deg / 180.0 * height) - 8
+    x0 = width // 3
+    img[y0:y0 + 16, x0:x0 + 16] = sun_nits
+    miss = np.full((height // 4, width // 4, 3), sky * 0.5, np.float32)
+    return build_ibl(img, miss=miss, rotation=0.3, exposure=0.0)

@@ -124,6 +124,22 @@ class ShadingOracle(_Lib):
     def scene_destroy(self, h):
         self.fn("scene_destroy")(h)
 
+    def ibl_lookup(self, h, wi):
+        wi = _f32(wi).reshape(-1, 3)
+        n = wi.shape[0]
+        rgb, pdf, miss = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32)
+        rc = self.fn("ibl_lookup")(h, C.c_size_t(n), _ptr(wi), _ptr(rgb), _ptr(pdf), _ptr(miss))
+        assert rc == 0, rc
+        return rgb, pdf, miss
+
+    def ibl_sample(self, h, u2):
+        u2 = _f32(u2).reshape(-1, 2)
+        n = u2.shape[0]
+        tpp, xy = np.zeros((n, 3), np.float32), np.zeros((n, 2), np.uint32)
+        rc = self.fn("ibl_sample")(h, C.c_size_t(n), _ptr(u2), _ptr(tpp), _ptr(xy))
+        assert rc == 0, rc
+        return tpp, xy
+
     def render(self, h, camera, settings, nthreads=8):
         w, hgt, layers = settings.width, settings.height, settings.layerCount
         film = [np.zeros((hgt, w, 3), np.float32) for _ in range(layers)]

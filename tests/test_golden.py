@@ -63,4 +63,4 @@ def test_ptex_fixtures_match_reference(ptexref):
 
 def test_record_layouts():
     assert capi.C.sizeof(capi.RenderSettings) == 48 and capi.C.sizeof(capi.RenderStats) == 96
-    assert capi.C.sizeof(capi.MeshDesc) == 72 and capi.C.sizeof(capi.SceneDesc) == 96
+    assert capi.C.sizeof(capi.MeshDesc) == 72 and capi.C.sizeof(capi.SceneDesc) == 104 and capi.C.sizeof(capi.IblDesc) == 56

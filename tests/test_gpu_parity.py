@@ -373,3 +373,42 @@ def test_hashgrid_bit_exact(ctx, oracle, n, cells, radius, scale):
         c, _ = grid.query(np.zeros((10, 3), np.float32))
         assert not c.any()
     grid.close()
+
+
+# ---- image based light ---------------------------------------------------------------------------------------------
+def test_ibl_parity_and_background(ctx, oracle):
+    """SampleIbl / SampleIblMiss / SampleIBlPdf / Ibl (ImageBasedLightResource.cpp:118-262) and a render whose misses read the
+    environment (EvaluateBackground / EvaluateBackgroundMiss, AreaLighting.cpp:415-437)."""
+    data = inputs.small_scene(with_attrs=False)
+    rng = np.random.default_rng(51)
+    img = (rng.uniform(0, 1, size=(64, 128, 3)) ** 6 * 40.0).astype(np.float32)
+    img[9:13, 30:36] = 900.0
+    img[40] = 0.0
+    data.ibl = scenes.build_ibl(img, miss=rng.uniform(0, 2, size=(16, 32, 3)).astype(np.float32), rotation=0.7, exposure=1.0)
+    sc, hs = capi.Scene(ctx, data), oracle.scene_create(data)
+    wi = inputs.unit_vectors(rng, 100_000)
+    wi[:6] = [[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1]]
+    g, o = sc.ibl_lookup(wi), oracle.ibl_lookup(hs, wi)
+    # the texel index is floor(angle * size): a direction within float noise of a texel border may land next door
+    same = (g[0] == o[0]).all(axis=1)
+    assert same.mean() > 0.9995
+    assert ((g[2] == o[2]).all(axis=1)).mean() > 0.9995
+    _assert_rel(g[1][same], o[1][same], 1e-4, "ibl pdf", floor=1e-6, allow_frac=1e-3)
+    u2 = inputs.uniforms(52, 100_000, 2)
+    u2[:4] = [[0, 0], [1, 1], [0, 1], [1, 0]]
+    (gt, gx), (ot, ox) = sc.ibl_sample(u2), oracle.ibl_sample(hs, u2)
+    np.testing.assert_array_equal(gx, ox)  # binary search over the CDFs: index work, bit-exact
+    np.testing.assert_allclose(gt[:, :2], ot[:, :2], rtol=0, atol=1e-6)
+    _assert_rel(gt[:, 2], ot[:, 2], 1e-5, "ibl sample pdf", floor=1e-6)
+    cam = capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 64, 48)
+    rs = capi.render_settings(64, 48, 16, max_path_length=5, rr_start=8, layers=1, seed=8)
+    gi = sc.render(cam, rs)[0][0] / 16.0
+    oi = oracle.render(hs, cam, rs, nthreads=8)[0][0] / 16.0
+    assert abs(gi.mean() / oi.mean() - 1.0) < 3e-3 and _relmse(gi, oi) < 3e-3
+    plain = inputs.small_scene(with_attrs=False)
+    sc2 = capi.Scene(ctx, plain)
+    with pytest.raises(capi.SelasError):
+        sc2.ibl_lookup(wi[:4])
+    sc2.close()
+    oracle.scene_destroy(hs)
+    sc.close()
