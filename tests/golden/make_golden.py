@@ -5,7 +5,7 @@
     for the expected lookups).
 The reference ships no test vectors of its own, so these are the pins.  Run from the repo root:
     python tests/golden/make_golden.py
-Outputs: tests/golden/shading.npz, tests/golden/hashgrid.npz, tests/golden/ptex_*.ptx, tests/golden/ptex_lookups.npz
+Outputs: tests/golden/shading.npz, tests/golden/ibl.npz, tests/golden/hashgrid.npz, tests/golden/ptex_*.ptx, tests/golden/ptex_lookups.npz
 """
 import sys
 from pathlib import Path
@@ -77,6 +77,24 @@ def main():
     md = rng.uniform(0, 50, size=1024).astype(np.float32)
     msamp, mtrans = ref.medium(ext, mu, md)
     vcm = np.stack([ref.vcm_iteration_constants(2073600, 1, 0.05, 0.75, float(i)) for i in range(1, 9)])
+    # image based light (ImageBasedLightResource.cpp) on a small synthetic environment
+    from selas_b200 import scenes
+    irng = np.random.default_rng(105)
+    img = (irng.uniform(0, 1, size=(32, 64, 3)) ** 6 * 40.0).astype(np.float32)
+    img[5:8, 10:14] = 900.0
+    img[20] = 0.0
+    ibl = scenes.build_ibl(img, miss=irng.uniform(0, 2, size=(8, 16, 3)).astype(np.float32), rotation=0.7, exposure=1.0)
+    idata = inputs.small_scene(with_attrs=False)
+    idata.ibl = ibl
+    hs = ref.scene_create(idata)
+    iwi = inputs.unit_vectors(irng, n)
+    iu2 = inputs.uniforms(105, n, 2)
+    irgb, ipdf, imiss = ref.ibl_lookup(hs, iwi)
+    itpp, ixy = ref.ibl_sample(hs, iu2)
+    ref.scene_destroy(hs)
+    np.savez_compressed(OUT / "ibl.npz", light=ibl["light"], marginal=ibl["marginal"], conditional=ibl["conditional"], miss=ibl["miss"],
+                        rotation=np.float32(ibl["rotation"]), exposure_scale=np.float32(ibl["exposure_scale"]), wi=iwi, u2=iu2,
+                        rgb=irgb, pdf=ipdf, miss_rgb=imiss, theta_phi_pdf=itpp, xy=ixy)
     np.savez_compressed(OUT / "shading.npz", surfaces=s, v=v, l=l, u=u, eval_rgb=rgb, eval_fwd=fwd, eval_rev=rev, sample=smp,
                         lights=lights, light_pos=pos, light_nrm=ln, light_u3=u3, light_sample=ls, light_pdf=lpdf,
                         camera=np.frombuffer(bytes(cam), np.uint8), cam_px=px, cam_py=py, cam_jitter=jit, cam_rays=rays,

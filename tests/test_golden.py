@@ -39,6 +39,24 @@ def test_camera_cmj_medium_golden(oracle):
     np.testing.assert_array_equal(_bits(trans), _bits(z["med_trans"]))
 
 
+def test_ibl_golden(oracle):
+    from tests import inputs
+
+    z = np.load(G / "ibl.npz")
+    data = inputs.small_scene(with_attrs=False)
+    data.ibl = dict(light=z["light"], marginal=z["marginal"], conditional=z["conditional"], miss=z["miss"], rotation=float(z["rotation"]),
+                    exposure_scale=float(z["exposure_scale"]))
+    hs = oracle.scene_create(data)
+    rgb, pdf, miss = oracle.ibl_lookup(hs, z["wi"])
+    tpp, xy = oracle.ibl_sample(hs, z["u2"])
+    oracle.scene_destroy(hs)
+    np.testing.assert_array_equal(_bits(rgb), _bits(z["rgb"]))
+    np.testing.assert_array_equal(_bits(pdf), _bits(z["pdf"]))
+    np.testing.assert_array_equal(_bits(miss), _bits(z["miss_rgb"]))
+    np.testing.assert_array_equal(_bits(tpp), _bits(z["theta_phi_pdf"]))
+    np.testing.assert_array_equal(xy, z["xy"])
+
+
 def test_hashgrid_golden(oracle):
     z = np.load(G / "hashgrid.npz")
     ends, idx, aabb = oracle.hashgrid_build(z["positions"], float(z["radius"]), int(z["cells"]))
