@@ -165,8 +165,28 @@ def run_cpu_arm(data, camera, args, steps, warmup, which="auto"):
             "ray_cast": "oracle scalar SAH-BVH2 (Embree 3.2.0 absent: headers only in the reference tree)"}
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, for one) also write to fd 1, so everything is
+    sent to stderr and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,7 +210,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ray_cast")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     import torch
@@ -360,7 +380,7 @@ def main():
             "bvh": {"build_ms": bvh.buildMs, "nodes": bvh.nodeCount, "triangles": bvh.triangleCount, "device_gb": bvh.deviceBytes / 1e9,
                     "upload_plus_build_s": upload_s},
             "mean_radiance": mean_radiance, "nonfinite_film_values": nonfinite_values}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
