@@ -251,6 +251,56 @@ typedef struct SelasBvhStats {
     uint64_t deviceBytes;
 } SelasBvhStats;
 
+/* ---- VCM (vertex connection and merging) ---------------------------------------------------------------------------
+ * Compile-time macros of the reference's VCM integrator made runtime (Applications/Selas/Source/VCM.cpp:28-35, :716-735,
+ * :765-779).  One "iteration" = vmCount = width*height light paths, the hash grid over their vertices, then one camera
+ * path per pixel (VertexConnectionAndMerging, VCM.cpp:664-697); vcCount = 1.  The reference only emits from the IBL
+ * (VCMCommon.cpp:37-63), so the scene must have been created with one. */
+enum { SELAS_VCM_NO_LIGHT_TRACING = 1, /* skip ConnectLightPathToCamera  (VCM.cpp:186-239) */
+       SELAS_VCM_NO_DIRECT        = 2, /* skip ConnectCameraPathToLight  (VCM.cpp:242-292) */
+       SELAS_VCM_NO_CONNECTIONS   = 4, /* skip ConnectPathVertices       (VCM.cpp:295-359) */
+       SELAS_VCM_NO_MERGING       = 8, /* skip SearchHashGrid/MergeVertices (VCM.cpp:362-409) */
+       SELAS_VCM_NO_SKY           = 16,/* skip ConnectToSkyLight         (VCM.cpp:168-183) */
+       SELAS_VCM_SKIP_NONFINITE   = 32 /* drop NaN/Inf contributions instead of adding them to the film */ };
+
+typedef struct SelasVcmSettings {
+    uint32_t width, height;
+    uint32_t iterations;      /* passes rendered by this call */
+    uint32_t firstIteration;  /* iteration shard: this call renders passes [firstIteration, firstIteration + iterations);
+                                 a pass's iterationIndex is pass + 1 (VCM.cpp:727-728) and its RNG streams are keyed by the pass */
+    uint32_t maxPathLength;   /* MaxBounceCount_ (VCM.cpp:28: 10); at most 31 (PathStatePathLengthBitCount_, VCMCommon.h:17) */
+    uint32_t seed;
+    float    radiusFactor;    /* VcmRadiusFactor_ 0.0025: base radius = radiusFactor * boundingSphere.w (VCM.cpp:778) */
+    float    radiusAlpha;     /* VcmRadiusAlpha_ 0.75 */
+    float    boundingSphere[4]; /* SceneResource::boundingSphere (centre xyz, radius) */
+    uint32_t flags;           /* SELAS_VCM_* */
+    uint32_t reserved;
+} SelasVcmSettings;
+
+/* VCMVertex (VCMCommon.h:33-42) as the device stores it: HitParameters is kept as the ray + hit record it is recomputed
+ * from (RayPick, VCM.cpp:123-166). */
+typedef struct SelasVcmVertex {
+    float    throughput[3];
+    uint32_t indexAndLength;  /* index : 26, pathLength : 5 (VCMCommon.h:36-37), bit 31 = material is eTransparent */
+    float    dVCM, dVC, dVM;
+    float    continuationProbability; /* ContinuationProbability(lightSurface), SurfaceParameters.cpp:420-424 */
+    SelasRay ray;
+    SelasHit hit;
+} SelasVcmVertex;
+
+typedef struct SelasVcmStats {
+    uint64_t lightPaths, cameraPaths;
+    uint64_t lightVertices;       /* stored over all iterations */
+    uint64_t closestRays, occlusionRays;
+    uint64_t mergeCandidates;     /* hash-grid candidates distance-tested */
+    uint64_t mergesAccepted;      /* MergeVertices calls (dist^2 <= r^2) */
+    uint64_t connections;         /* ConnectPathVertices evaluations */
+    uint64_t kernelLaunches;
+    float    renderMs;            /* device time of all iterations */
+    float    lightPassMs, gridBuildMs, cameraPassMs, mergeMs, connectMs;
+    float    lastRadius;          /* vmSearchRadius of the last iteration */
+} SelasVcmStats;
+
 typedef struct SelasContext  SelasContext;
 typedef struct SelasScene    SelasScene;
 typedef struct SelasHashGrid SelasHashGrid;
@@ -336,6 +386,23 @@ int selas_cuda_render_pathtracer_device(SelasScene* scene, const SelasCamera* ca
                                         SelasRenderStats* stats, void* stream);
 /* FrameBuffer_Scale Framebuffer.cpp:62-70 on a device film. */
 int selas_cuda_film_scale_device(SelasContext* ctx, float* d_film, size_t floatCount, float scale, void* stream);
+
+/* ---- VCM integrator: VCM::GenerateImage VCM.cpp:738-807 (iterations instead of IntegrationSeconds_) --------------------
+ * film: width*height float3, receives the SUM over this call's iterations (FrameBuffer_Normalize by 1/iterations,
+ * VCM.cpp:801, is the caller's job: selas_cuda_film_scale_device).  Iterations are independent given the scene, so N GPUs
+ * render disjoint [firstIteration, ...) shards and reduce the films. */
+int selas_cuda_render_vcm(SelasScene* scene, const SelasCamera* camera, const SelasVcmSettings* settings, float* film,
+                          SelasVcmStats* stats);
+int selas_cuda_render_vcm_device(SelasScene* scene, const SelasCamera* camera, const SelasVcmSettings* settings, float* d_film,
+                                 SelasVcmStats* stats, void* stream);
+/* Light pass of iteration `settings->firstIteration` only (GenerateLightSamples + EvaluateLightPaths, VCM.cpp:492-561), for
+ * inspection: lightVertices in the reference's order (path by path), pathEnds[vmCount] (LightPathSet, VCM.cpp:57-62).
+ * vertices may be NULL (count only); at most maxVertices are written; *vertexCount receives the total. */
+int selas_cuda_vcm_light_pass(SelasScene* scene, const SelasCamera* camera, const SelasVcmSettings* settings,
+                              SelasVcmVertex* vertices, size_t maxVertices, uint32_t* pathEnds, size_t* vertexCount);
+/* CalculateIterationConstants, VCMCommon.cpp:97-112: out5 = {vmSearchRadius, vmSearchRadiusSqr, vmNormalization, vmWeight, vcWeight} */
+int selas_cuda_vcm_iteration_constants(uint32_t vmCount, uint32_t vcCount, float baseRadius, float radiusAlpha, float iterationIndex,
+                                       float* out5);
 
 /* ---- VCM hash grid: BuildHashGrid VCMHashGrid.cpp:48-97, SearchHashGrid :107-155 ------------------
  * positions: float3 per vertex.  Query returns, per query point, the indices of vertices with

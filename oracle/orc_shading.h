@@ -947,4 +947,130 @@ static inline void cmj(int32_t s, int32_t m, int32_t n, int32_t p, float out[2])
     out[1] = (s / m + (sx + jy) / m) / n;
 }
 
+
+// ---- VCM building blocks ------------------------------------------------------------------------------------------
+// MathLib/Projection.cpp:132-146
+static inline V3 sphericalToCartesian(float theta, float phi) {
+    float sintheta = sinf(theta), costheta = cosf(theta), sinphi = sinf(phi), cosphi = cosf(phi);
+    return v3(sintheta * cosphi, costheta, sintheta * sinphi);
+}
+// GeometryLib/CoordinateSystem.h:14-21
+static inline void makeOrthogonalCoordinateSystem(V3 v1, V3& v2, V3& v3out) {
+    if (absf(v1.x) > absf(v1.y))
+        v2 = v3(-v1.z, 0, v1.x) * (1.0f / sqrtf(v1.x * v1.x + v1.z * v1.z));
+    else
+        v2 = v3(0, v1.z, -v1.y) * (1.0f / sqrtf(v1.y * v1.y + v1.z * v1.z));
+    v3out = cross(v1, v2);
+}
+// GeometryLib/Disc.cpp:13-56 (Shirley-Chiu concentric map)
+static inline void sampleConcentricDisc(float r0, float r1, float& dx, float& dy) {
+    float phi, r;
+    float a = 2.0f * r0 - 1.0f, b = 2.0f * r1 - 1.0f;
+    if (a > -b) {
+        if (a > b) { r = a; phi = (kPi / 4.0f) * (b / a); }
+        else { r = b; phi = (kPi / 4.0f) * (2.0f - (a / b)); }
+    } else {
+        if (a < b) { r = -a; phi = (kPi / 4.0f) * (4.0f + (b / a)); }
+        else {
+            r = -b;
+            if (absf(b) > 0.0f) phi = (kPi / 4.0f) * (6.0f - (a / b));
+            else phi = 0;
+        }
+    }
+    dx = r * cosf(phi);
+    dy = r * sinf(phi);
+}
+struct LightEmission {  // LightEmissionSample, Shading/AreaLighting.h:33-45
+    V3 position, direction, radiance;
+    float emissionPdfW, directionPdfA, cosThetaLight;
+};
+// EmitIblLightSample, Shading/AreaLighting.cpp:246-290 (four uniforms r0..r3)
+static inline void emitIblLightSample(Stream& rng, const Ibl& ibl, const float sphere[4], LightEmission& o) {
+    float r0 = rng.next(), r1 = rng.next(), r2 = rng.next(), r3 = rng.next();
+    uint32_t x, y;
+    float dirPhi, dirTheta;
+    iblSample(ibl, r0, r1, dirTheta, dirPhi, x, y, o.directionPdfA);
+    V3 toIbl = sphericalToCartesian(dirTheta, dirPhi);
+    V3 radiance = ibl.exposureScale * v3(ibl.light + 3 * ((size_t)y * ibl.width + x));  // SampleIbl(ibl, x, y), ImageBasedLightResource.cpp:264-267
+    V3 dX, dZ;
+    makeOrthogonalCoordinateSystem(toIbl, dX, dZ);
+    float R = sphere[3];
+    V3 center = v3(sphere);
+    float sx, sy;
+    sampleConcentricDisc(r2, r3, sx, sy);
+    float discPdf = kInvPi;
+    o.position = center + R * (toIbl + sx * dX + sy * dZ);
+    float pdfPosition = discPdf * (1.0f / (R * R));
+    float pdfDirection = o.directionPdfA;
+    o.direction = -toIbl;
+    o.radiance = radiance;
+    o.emissionPdfW = pdfPosition * pdfDirection;
+    o.cosThetaLight = 1.0f;
+}
+// DirectIblLightSample, Shading/AreaLighting.cpp:293-314 (two uniforms)
+static inline void directIblLightSample(Stream& rng, const Ibl& ibl, SelasLightSample& o) {
+    float r0 = rng.next(), r1 = rng.next();
+    uint32_t x, y;
+    float dirPhi, dirTheta;
+    iblSample(ibl, r0, r1, dirTheta, dirPhi, x, y, o.pdfW);
+    V3 toIbl = sphericalToCartesian(dirTheta, dirPhi);
+    o.index = 0;
+    o.distance = 1e36f;
+    store(o.direction, toIbl);
+    store(o.radiance, ibl.exposureScale * v3(ibl.light + 3 * ((size_t)y * ibl.width + x)));
+}
+// IblCalculateRadiance, Shading/AreaLighting.cpp:317-331
+static inline V3 iblCalculateRadiance(const Ibl& ibl, const float sphere[4], V3 direction, float& directPdfA, float& emissionPdfW) {
+    float iblPdfA;
+    V3 radiance = iblLookup(ibl, direction, iblPdfA);
+    float R = sphere[3];
+    float pdfPosition = kInvPi * (1.0f / (R * R));
+    directPdfA = iblPdfA;
+    emissionPdfW = pdfPosition * iblPdfA;
+    return radiance;
+}
+// ContinuationProbability, Shading/SurfaceParameters.cpp:420-424
+static inline float continuationProbability(const SelasSurface& s) {
+    return saturate(maxf(maxf(s.baseColor[0], s.baseColor[1]), s.baseColor[2]));
+}
+// OffsetRayOrigin with the signed bias distance, Shading/SurfaceParameters.cpp:411-417
+static inline V3 offsetRayOriginBias(const SelasSurface& s, V3 direction, float biasScale, float& signedBiasDistance) {
+    V3 n = geometricNormal(s);
+    float dirOffset = dot(direction, n) < 0.0f ? -1.0f : 1.0f;
+    signedBiasDistance = dirOffset * s.error * biasScale;
+    V3 offset = signedBiasDistance * n;
+    return v3(s.position) + offset;
+}
+// VCMCommon::SearchRadius / CalculateIterationConstants, Applications/Selas/Source/VCMCommon.cpp:91-112
+struct VcmConstants {
+    uint32_t vmCount, vcCount;
+    float vmSearchRadius, vmSearchRadiusSqr, vmNormalization, vmWeight, vcWeight;
+};
+static inline VcmConstants vcmIterationConstants(uint32_t vmCount, uint32_t vcCount, float baseRadius, float radiusAlpha, float iterationIndex) {
+    float r = baseRadius / powf(iterationIndex, 0.5f * (1.0f - radiusAlpha));
+    VcmConstants c;
+    c.vmCount = vmCount;
+    c.vcCount = vcCount;
+    c.vmSearchRadius = r;
+    c.vmSearchRadiusSqr = r * r;
+    c.vmNormalization = 1.0f / (kPi * c.vmSearchRadiusSqr * vmCount);
+    c.vmWeight = kPi * c.vmSearchRadiusSqr * vmCount / vcCount;
+    c.vcWeight = vcCount / (kPi * c.vmSearchRadiusSqr * vmCount);
+    return c;
+}
+// WorldToImage: the reference's VCM calls it (VCM.cpp:199) but the function no longer exists in GeometryLib/Camera.cpp; it is
+// restated as the inverse of ImageToWorldDirection (Camera.cpp:56-60): dir ~ Z - cx X + cy Y with X, Y, Z mutually orthogonal
+// (InitializeRayCastCamera, Camera.cpp:89-115), x = (cx + 1) w / 2, y = (1 - cy) h / 2, truncated toward -inf.
+static inline void worldToImage(const SelasCamera& cam, V3 p, int32_t& ix, int32_t& iy) {
+    V3 to = p - v3(cam.position);
+    V3 X = v3(cam.cameraX), Y = v3(cam.cameraY), Z = v3(cam.cameraZ);
+    float z = dot(to, Z) / dot(Z, Z);
+    float cx = -(dot(to, X) / dot(X, X)) / z;
+    float cy = (dot(to, Y) / dot(Y, Y)) / z;
+    float x = (cx + 1.0f) * 0.5f * (float)(uint32_t)cam.width;
+    float y = (1.0f - cy) * 0.5f * (float)(uint32_t)cam.height;
+    ix = (int32_t)floorf(x);
+    iy = (int32_t)floorf(y);
+}
+
 }  // namespace orc

@@ -730,4 +730,115 @@ int ref_ibl_sample(void* s, size_t n, const float* u2, float* thetaPhiPdf3, uint
     return 0;
 }
 
+// ---- VCM building blocks that are still live code in the reference ---------------------------------------------------
+// EmitIblLightSample / DirectIblLightSample / IblCalculateRadiance (Shading/AreaLighting.cpp:246-331) and
+// VCMCommon::GenerateLightSample / GenerateCameraSample (VCMCommon.cpp:37-88), driven with a scripted CSampler.
+namespace {
+struct VcmContext {
+    // SceneResource / ImageBasedLightResource have out-of-line constructors in translation units that are not linked
+    // (they need Embree and the asset IO); raw zeroed storage of the right size stands in for them.
+    alignas(16) unsigned char sceneStorage[sizeof(SceneResource)];
+    alignas(16) unsigned char iblStorage[sizeof(ImageBasedLightResource)];
+    alignas(16) unsigned char ctxStorage[sizeof(GIIntegratorContext)];
+    GIIntegratorContext* ctx;
+    VcmContext(const RefScene& sc, const float* sphere4, const RayCastCameraSettings* cam) {
+        memset(sceneStorage, 0, sizeof(sceneStorage));
+        memset(iblStorage, 0, sizeof(iblStorage));
+        memset(ctxStorage, 0, sizeof(ctxStorage));
+        SceneResource* scene = reinterpret_cast<SceneResource*>(sceneStorage);
+        ImageBasedLightResource* ibl = reinterpret_cast<ImageBasedLightResource*>(iblStorage);
+        ibl->data = const_cast<ImageBasedLightResourceData*>(&sc.ibl.data);
+        scene->iblResource = ibl;
+        if (sphere4) scene->boundingSphere = float4(sphere4[0], sphere4[1], sphere4[2], sphere4[3]);
+        ctx = reinterpret_cast<GIIntegratorContext*>(ctxStorage);
+        ctx->scene = scene;
+        ctx->camera = cam;
+    }
+};
+}  // namespace
+
+int ref_ibl_emit(void* s, const float* sphere4, size_t n, const float* u4, float* posDirRad9, float* pdfs3) {
+    setFtz();
+    const RefScene& sc = *(RefScene*)s;
+    if (!sc.ibl.present) return 2;
+    VcmContext vc(sc, sphere4, nullptr);
+    for (size_t i = 0; i < n; ++i) {
+        g_src = DrawSource{u4 + 4 * i, 0, 4, 0, false};
+        LightEmissionSample e;
+        EmitIblLightSample(vc.ctx, e);
+        st3(posDirRad9 + 9 * i, e.position);
+        st3(posDirRad9 + 9 * i + 3, e.direction);
+        st3(posDirRad9 + 9 * i + 6, e.radiance);
+        pdfs3[3 * i] = e.emissionPdfW; pdfs3[3 * i + 1] = e.directionPdfA; pdfs3[3 * i + 2] = e.cosThetaLight;
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+int ref_ibl_direct(void* s, size_t n, const float* u2, SelasLightSample* out) {
+    setFtz();
+    const RefScene& sc = *(RefScene*)s;
+    if (!sc.ibl.present) return 2;
+    VcmContext vc(sc, nullptr, nullptr);
+    for (size_t i = 0; i < n; ++i) {
+        g_src = DrawSource{u2 + 2 * i, 0, 2, 0, false};
+        LightDirectSample d;
+        d.index = 0;
+        DirectIblLightSample(vc.ctx, d);
+        out[i].index = 0;
+        st3(out[i].direction, d.direction);
+        st3(out[i].radiance, d.radiance);
+        out[i].distance = d.distance;
+        out[i].pdfW = d.pdfW;
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+int ref_ibl_radiance(void* s, const float* sphere4, size_t n, const float* dir3, float* rgb3, float* pdfs2) {
+    setFtz();
+    const RefScene& sc = *(RefScene*)s;
+    if (!sc.ibl.present) return 2;
+    VcmContext vc(sc, sphere4, nullptr);
+    for (size_t i = 0; i < n; ++i) {
+        float a = 0.f, b = 0.f;
+        st3(rgb3 + 3 * i, IblCalculateRadiance(vc.ctx, f3(dir3 + 3 * i), a, b));
+        pdfs2[2 * i] = a; pdfs2[2 * i + 1] = b;
+    }
+    return 0;
+}
+// out13 per sample: position, direction, throughput, dVCM, dVC, dVM, (pathLength | isAreaMeasure << 8 as float)
+static void storeState(const PathState& st, float* o) {
+    st3(o, st.position); st3(o + 3, st.direction); st3(o + 6, st.throughput);
+    o[9] = st.dVCM; o[10] = st.dVC; o[11] = st.dVM;
+    o[12] = (float)(st.pathLength | (st.isAreaMeasure << 8));
+}
+int ref_vcm_generate_light(void* s, const float* sphere4, float vcWeight, size_t n, const float* u4, float* out13) {
+    setFtz();
+    const RefScene& sc = *(RefScene*)s;
+    if (!sc.ibl.present) return 2;
+    VcmContext vc(sc, sphere4, nullptr);
+    for (size_t i = 0; i < n; ++i) {
+        g_src = DrawSource{u4 + 4 * i, 0, 4, 0, false};
+        PathState st;
+        VCMCommon::GenerateLightSample(vc.ctx, vcWeight, (Selas::uint)i, st);
+        storeState(st, out13 + 13 * i);
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+int ref_vcm_generate_camera(const SelasCamera* cam, float lightPathCount, size_t n, const uint32_t* xy2, const float* u2, float* out13,
+                            uint32_t* index) {
+    setFtz();
+    RefScene dummy;
+    VcmContext vc(dummy, nullptr, reinterpret_cast<const RayCastCameraSettings*>(cam));
+    for (size_t i = 0; i < n; ++i) {
+        g_src = DrawSource{u2 + 2 * i, 0, 2, 0, false};
+        PathState st;
+        VCMCommon::GenerateCameraSample(vc.ctx, xy2[2 * i], xy2[2 * i + 1], lightPathCount, st);
+        storeState(st, out13 + 13 * i);
+        index[i] = st.index;
+    }
+    g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+
 }  // extern "C"

@@ -11,9 +11,13 @@
 //   * EvaluatePath / PathTracerKernel   Applications/Selas/Source/PathTracer.cpp:142-299
 //   * BuildHashGrid / SearchHashGrid    Applications/Selas/Source/VCMHashGrid.cpp:15-155
 //   * FramebufferWriter_Write           Core/TextureLib/Framebuffer.cpp:104-135 (film[y*w+x] += sample)
+//   * VCM::GenerateImage and callees    Applications/Selas/Source/VCM.cpp (orc_vcm.h)
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -748,3 +752,6 @@ int orc_rng(uint32_t seed, uint32_t pixel, uint32_t sample, size_t n, float* out
 }
 
 }  // extern "C"
+
+// ---- VCM integrator (Applications/Selas/Source/VCM.cpp) -----------------------------------------------------------
+#include "orc_vcm.h"

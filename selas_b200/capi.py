@@ -87,6 +87,19 @@ class RenderStats(C.Structure):
                 ("closestNodes", u64), ("closestTris", u64), ("shadowNodes", u64), ("shadowTris", u64)]
 
 
+class VcmSettings(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("iterations", u32), ("firstIteration", u32), ("maxPathLength", u32),
+                ("seed", u32), ("radiusFactor", f32), ("radiusAlpha", f32), ("boundingSphere", f32 * 4), ("flags", u32),
+                ("reserved", u32)]
+
+
+class VcmStats(C.Structure):
+    _fields_ = [("lightPaths", u64), ("cameraPaths", u64), ("lightVertices", u64), ("closestRays", u64), ("occlusionRays", u64),
+                ("mergeCandidates", u64), ("mergesAccepted", u64), ("connections", u64), ("kernelLaunches", u64),
+                ("renderMs", f32), ("lightPassMs", f32), ("gridBuildMs", f32), ("cameraPassMs", f32), ("mergeMs", f32),
+                ("connectMs", f32), ("lastRadius", f32)]
+
+
 class BvhStats(C.Structure):
     _fields_ = [("triangleCount", u32), ("nodeCount", u32), ("maxDepth", u32), ("reserved", u32), ("buildMs", f32),
                 ("sahCost", f32), ("deviceBytes", u64)]
@@ -110,6 +123,9 @@ LIGHT_SAMPLE_DTYPE = np.dtype([("index", "u4"), ("direction", "f4", 3), ("radian
                                ("pdfW", "f4")])
 LIGHT_DTYPE = np.dtype([("type", "u4"), ("position", "f4", 3), ("direction", "f4", 3), ("x", "f4", 3), ("z", "f4", 3),
                         ("radiance", "f4", 3)])
+VCM_VERTEX_DTYPE = np.dtype([("throughput", "f4", 3), ("indexAndLength", "u4"), ("dVCM", "f4"), ("dVC", "f4"), ("dVM", "f4"),
+                             ("continuationProbability", "f4"), ("ray", RAY_DTYPE), ("hit", HIT_DTYPE)])
+assert VCM_VERTEX_DTYPE.itemsize == 96
 MATERIAL_DTYPE = np.dtype([("shader", "u4"), ("flags", "u4"), ("baseColor", "f4", 3), ("transmittanceColor", "f4", 3),
                            ("scalars", "f4", SCALAR_COUNT)])
 assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 32 and SURFACE_DTYPE.itemsize == 156
@@ -124,6 +140,7 @@ EXPORTS = [
     "selas_cuda_bsdf_sample", "selas_cuda_light_sample", "selas_cuda_light_pdf", "selas_cuda_surface_params",
     "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample",
     "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_film_scale_device",
+    "selas_cuda_render_vcm", "selas_cuda_render_vcm_device", "selas_cuda_vcm_light_pass", "selas_cuda_vcm_iteration_constants",
     "selas_cuda_hashgrid_build", "selas_cuda_hashgrid_destroy", "selas_cuda_hashgrid_read",
     "selas_cuda_hashgrid_query", "selas_cuda_hashgrid_build_device", "selas_cuda_hashgrid_query_device",
     "selas_cuda_ptex_load", "selas_cuda_ptex_load_memory", "selas_cuda_ptex_destroy", "selas_cuda_ptex_eval",
@@ -451,6 +468,32 @@ class Scene:
                                                                     C.c_void_p(d_film_ptr), C.byref(stats), C.c_void_p(stream)))
         return stats
 
+    def render_vcm(self, camera: Camera, settings: VcmSettings):
+        """VCM::GenerateImage (VCM.cpp:738-807) with a host film; returns ((H, W, 3) SUM over iterations, stats)."""
+        film = np.zeros((settings.height, settings.width, 3), np.float32)
+        stats = VcmStats()
+        self.ctx.check(self.lib.selas_cuda_render_vcm(self.handle, C.byref(camera), C.byref(settings), _ptr(film), C.byref(stats)))
+        return film, stats
+
+    def render_vcm_device(self, camera: Camera, settings: VcmSettings, d_film_ptr: int, stream: int = 0):
+        stats = VcmStats()
+        self.ctx.check(self.lib.selas_cuda_render_vcm_device(self.handle, C.byref(camera), C.byref(settings), C.c_void_p(d_film_ptr),
+                                                             C.byref(stats), C.c_void_p(stream)))
+        return stats
+
+    def vcm_light_pass(self, camera: Camera, settings: VcmSettings):
+        """Light pass of iteration settings.firstIteration: (vertices in the reference's order, pathEnds)."""
+        vm_count = settings.width * settings.height
+        total = C.c_size_t(0)
+        ends = np.zeros(vm_count, np.uint32)
+        self.ctx.check(self.lib.selas_cuda_vcm_light_pass(self.handle, C.byref(camera), C.byref(settings), None, C.c_size_t(0), _ptr(ends),
+                                                          C.byref(total)))
+        verts = np.zeros(total.value, dtype=VCM_VERTEX_DTYPE)
+        if total.value:
+            self.ctx.check(self.lib.selas_cuda_vcm_light_pass(self.handle, C.byref(camera), C.byref(settings), _ptr(verts),
+                                                              C.c_size_t(total.value), _ptr(ends), C.byref(total)))
+        return verts, ends
+
     def intersect_device(self, n, d_rays, d_hits, d_ng=0, stream=0):
         self.ctx.check(self.lib.selas_cuda_intersect_device(self.handle, C.c_size_t(n), C.c_void_p(d_rays), C.c_void_p(d_hits),
                                                             C.c_void_p(d_ng) if d_ng else None, C.c_void_p(stream)))
@@ -473,6 +516,27 @@ def render_settings(width, height, spp, max_path_length=8, rr_start=8, layers=1,
     rs.maxPathLength, rs.rrStartBounce, rs.layerCount = max_path_length, rr_start, layers
     rs.seed, rs.firstSample, rs.misMode = seed, first_sample, mis_mode
     return rs
+
+
+(VCM_NO_LIGHT_TRACING, VCM_NO_DIRECT, VCM_NO_CONNECTIONS, VCM_NO_MERGING, VCM_NO_SKY, VCM_SKIP_NONFINITE) = 1, 2, 4, 8, 16, 32
+
+
+def vcm_settings(width, height, iterations, bounding_sphere, first_iteration=0, max_path_length=10, seed=1, radius_factor=0.0025,
+                 radius_alpha=0.75, flags=0):
+    """Defaults are the reference's macros: MaxBounceCount_ 10, VcmRadiusFactor_ 0.0025, VcmRadiusAlpha_ 0.75 (VCM.cpp:28-35)."""
+    vs = VcmSettings()
+    vs.width, vs.height, vs.iterations, vs.firstIteration = width, height, iterations, first_iteration
+    vs.maxPathLength, vs.seed, vs.radiusFactor, vs.radiusAlpha, vs.flags = max_path_length, seed, radius_factor, radius_alpha, flags
+    vs.boundingSphere[:] = [float(x) for x in bounding_sphere]
+    return vs
+
+
+def vcm_iteration_constants(vm_count, vc_count, base_radius, alpha, iteration):
+    out = np.zeros(5, np.float32)
+    rc = load_library().selas_cuda_vcm_iteration_constants(u32(vm_count), u32(vc_count), f32(base_radius), f32(alpha), f32(iteration), _ptr(out))
+    if rc:
+        raise SelasError(rc, "selas_cuda_vcm_iteration_constants")
+    return out
 
 
 class HashGrid:

@@ -294,6 +294,7 @@ int selas_cuda_scene_destroy(SelasScene* scene) {
         cudaStreamSynchronize(scene->ctx->stream);
     }
     freeWavefront(scene);
+    freeVcm(scene);
     cudaFree(scene->d_filmCache);
     for (void* p : scene->allocations) cudaFree(p);
     delete scene;
@@ -715,6 +716,55 @@ int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera, c
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(filmLayers[l], d_film + plane * l, plane * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return SELAS_OK;
+}
+
+// ---- VCM integrator: VCM::GenerateImage, VCM.cpp:738-807 ---------------------------------------------------------------
+int selas_cuda_render_vcm_device(SelasScene* scene, const SelasCamera* camera, const SelasVcmSettings* settings, float* d_film,
+                                 SelasVcmStats* stats, void* stream) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (!camera || !settings || !d_film) {
+        setError(ctx, "selas_cuda_render_vcm_device: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    return renderVcm(scene, *camera, *settings, d_film, stats, stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+int selas_cuda_render_vcm(SelasScene* scene, const SelasCamera* camera, const SelasVcmSettings* settings, float* film, SelasVcmStats* stats) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (!camera || !settings || !film) {
+        setError(ctx, "selas_cuda_render_vcm: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    const size_t plane = (size_t)settings->width * settings->height * 3;
+    if (scene->filmCacheFloats < plane) {
+        cudaFree(scene->d_filmCache);
+        scene->d_filmCache = nullptr;
+        scene->filmCacheFloats = 0;
+        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&scene->d_filmCache, plane * sizeof(float)));
+        scene->filmCacheFloats = plane;
+    }
+    float* d_film = scene->d_filmCache;
+    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_film, 0, plane * sizeof(float), ctx->stream));
+    SELAS_TRY(renderVcm(scene, *camera, *settings, d_film, stats, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(film, d_film, plane * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
+int selas_cuda_vcm_light_pass(SelasScene* scene, const SelasCamera* camera, const SelasVcmSettings* settings, SelasVcmVertex* vertices,
+                              size_t maxVertices, uint32_t* pathEnds, size_t* vertexCount) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SelasContext* ctx = scene->ctx;
+    SELAS_TRY(bind(ctx));
+    if (!camera || !settings) {
+        setError(ctx, "selas_cuda_vcm_light_pass: null argument");
+        return SELAS_ERR_ARGUMENT;
+    }
+    return vcmLightPassInspect(scene, *camera, *settings, vertices, maxVertices, pathEnds, vertexCount);
 }
 
 int selas_cuda_film_scale_device(SelasContext* ctx, float* d_film, size_t floatCount, float scale, void* stream) {

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <new>
 
+#include "hashgrid.cuh"
 #include "internal.h"
 #include "vec.cuh"
 
@@ -53,32 +54,11 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;  // per thread
 constexpr int kScanTile = kScanThreads * kScanItems;
 
-SELAS_D uint32_t orderedFromFloat(float f) {
-    uint32_t u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-SELAS_HD float floatFromOrdered(uint32_t u) {
-    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-#ifdef __CUDA_ARCH__
-    return __uint_as_float(u);
-#else
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-#endif
-}
-
 struct GridParams {
     float minx, miny, minz, maxx, maxy, maxz;
     float inv, r2;
     uint32_t cellCount;
 };
-
-SELAS_D uint32_t cellHash(int32_t x, int32_t y, int32_t z, uint32_t cellCount) {
-    uint64_t ux = (uint64_t)(int64_t)x, uy = (uint64_t)(int64_t)y, uz = (uint64_t)(int64_t)z;
-    uint64_t h = (ux * 73856093ull) ^ (uy * 19349663ull) ^ (uz * 83492791ull);
-    return (uint32_t)(h % (uint64_t)cellCount);
-}
 
 __global__ void boundsKernel(const float* __restrict__ pos, size_t n, uint32_t* __restrict__ bounds) {
     float lo[3] = {SELAS_FLOAT_MAX, SELAS_FLOAT_MAX, SELAS_FLOAT_MAX}, hi[3] = {-SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX};
@@ -474,6 +454,30 @@ int buildOnDevice(SelasHashGrid* g, size_t n, const float* d_pos, float radius, 
 }
 
 }  // namespace
+
+// for vcm.cu: a by-value view of a built grid, and the 3-kernel inclusive/exclusive scan (sums: n / 2048 + 1 words of scratch)
+HashGridView hashGridView(const SelasHashGrid* g) {
+    HashGridView v;
+    v.bounds = g->d_bounds;
+    v.cellEnds = g->d_cellEnds;
+    v.cellPoints = g->d_cellPoints;
+    v.inverseCellSize = g->inverseCellSize;
+    v.radiusSq = g->radiusSq;
+    v.cellCount = g->cellCount;
+    v.n = (uint32_t)g->n;
+    return v;
+}
+uint32_t scanScratchWords(uint32_t n) { return divUp(n, kScanTile) + 1; }
+int launchScanU32(SelasContext* ctx, const uint32_t* d_in, uint32_t n, uint32_t* d_sums, uint32_t* d_inclusive, uint32_t* d_exclusive,
+                  cudaStream_t st) {
+    if (!n) return SELAS_OK;
+    uint32_t blocks = divUp(n, kScanTile);
+    scanTileSums<<<blocks, kScanThreads, 0, st>>>(d_in, n, d_sums);
+    scanSums<<<1, 1024, 0, st>>>(d_sums, blocks);
+    scanTiles<<<blocks, kScanThreads, 0, st>>>(d_in, n, d_sums, d_inclusive, d_exclusive);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
 }  // namespace selas
 
 using namespace selas;

@@ -83,6 +83,7 @@ struct SelasScene {
     bool usesPtex = false;  // any mesh carries a Ptex texture: selects the shade kernel built with the lookup
     // wavefront scratch, grown on demand
     void* wf = nullptr;
+    void* vcm = nullptr;  // VCM scratch (vcm.cu), grown on demand
     // device film of the host-buffer render entry point, kept between calls
     float* d_filmCache = nullptr;
     size_t filmCacheFloats = 0;
@@ -132,6 +133,19 @@ int launchIblLookup(SelasScene* scene, size_t n, const float* d_wi3, float* d_rg
 int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp3, uint32_t* d_xy2);
 int launchCmj(SelasContext* ctx, size_t count, const int32_t* d_s, int32_t m, int32_t n, const int32_t* d_p, float* d_out2);
 void freeWavefront(SelasScene* scene);
+
+// hashgrid.cu
+struct HashGridView;
+HashGridView hashGridView(const SelasHashGrid* grid);
+uint32_t scanScratchWords(uint32_t n);
+int launchScanU32(SelasContext* ctx, const uint32_t* d_in, uint32_t n, uint32_t* d_sums, uint32_t* d_inclusive, uint32_t* d_exclusive,
+                  cudaStream_t stream);
+
+// vcm.cu
+int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings& vs, float* d_film, SelasVcmStats* stats, cudaStream_t stream);
+int vcmLightPassInspect(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings& vs, SelasVcmVertex* vertices, size_t maxVertices,
+                        uint32_t* pathEnds, size_t* vertexCount);
+void freeVcm(SelasScene* scene);
 
 // ptex.cu
 const void* ptexDevicePointer(SelasPtex* tex);

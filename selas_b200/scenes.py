@@ -417,3 +417,63 @@ def sun_sky_ibl(width=1024, height=512, sun_theta_deg=40.0, sun_nits=5000.0, sky
     img[y0:y0 + 16, x0:x0 + 16] = sun_nits
     miss = np.full((height // 4, width // 4, 3), sky * 0.5, np.float32)
     return build_ibl(img, miss=miss, rotation=0.3, exposure=0.0)
+
+
+# ---- C5: caustic scene for the VCM integrator ----------------------------------------------------------------------
+def _uv_sphere(center, radius, n_theta, n_phi, material_index):
+    th = np.linspace(0.0, math.pi, n_theta + 1, dtype=np.float64)
+    ph = np.linspace(0.0, 2.0 * math.pi, n_phi + 1, dtype=np.float64)[:-1]
+    T, P = np.meshgrid(th, ph, indexing="ij")
+    vid = np.arange(T.size, dtype=np.uint32).reshape(T.shape)
+    n = np.stack([np.sin(T) * np.cos(P), np.cos(T), np.sin(T) * np.sin(P)], axis=-1)
+    pos = (np.asarray(center, np.float64)[None, None, :] + radius * n).astype(np.float32)
+    i0, i1 = vid[:-1, :], vid[1:, :]
+    quads = np.stack([i0, np.roll(i0, -1, axis=1), np.roll(i1, -1, axis=1), i1], axis=-1).reshape(-1, 4).astype(np.uint32)
+    return dict(positions=pos.reshape(-1, 3), normals=n.astype(np.float32).reshape(-1, 3), indices=quads, material=material_index, lightSet=0)
+
+
+def caustic_scene(sphere_res=(96, 192), floor_cells=64, ibl_size=(1024, 512)):
+    """Config 5: floor + glass sphere (Content/Materials/BSDF.json: specTrans 1, ior 1.7, roughness 0.01) +
+    diffuse box, lit only by a synthetic sun-and-sky IBL (the reference's VCM emits from the IBL alone, VCMCommon.cpp:37-63).
+    No quad lights: the light-set range is empty."""
+    g = floor_cells
+    xs = np.linspace(-6.0, 6.0, g + 1)
+    X, Z = np.meshgrid(xs, xs, indexing="ij")
+    fpos = np.stack([X, np.zeros_like(X), Z], axis=-1).astype(np.float32).reshape(-1, 3)
+    ci, cj = np.meshgrid(np.arange(g), np.arange(g), indexing="ij")
+    v00 = (ci * (g + 1) + cj).astype(np.uint32)
+    # CCW seen from +y
+    fquads = np.stack([v00, v00 + np.uint32(1), v00 + np.uint32(g + 2), v00 + np.uint32(g + 1)], axis=-1).reshape(-1, 4)
+    floor = dict(positions=fpos, indices=fquads, material=0, lightSet=0)
+    sphere = _uv_sphere((0.0, 1.2, 0.0), 1.2, sphere_res[0], sphere_res[1], 1)
+
+    def box(lo, hi):
+        x0, y0, z0 = lo
+        x1, y1, z1 = hi
+        v = [(x0, y0, z0), (x1, y0, z0), (x1, y0, z1), (x0, y0, z1), (x0, y1, z0), (x1, y1, z0), (x1, y1, z1), (x0, y1, z1)]
+        quads = [_quad(v[4], v[7], v[6], v[5]), _quad(v[0], v[4], v[5], v[1]), _quad(v[1], v[5], v[6], v[2]),
+                 _quad(v[2], v[6], v[7], v[3]), _quad(v[3], v[7], v[4], v[0])]
+        pos = np.array([p for q in quads for p in q], dtype=np.float32)
+        return dict(positions=pos, indices=np.arange(20, dtype=np.uint32).reshape(-1, 4), material=2, lightSet=0)
+
+    rough = dict(REFERENCE_MATERIALS["RoughDiffuse"])
+    mats = np.array([
+        material(**{**rough, "baseColor": [0.8, 0.8, 0.78]}),
+        material(**REFERENCE_MATERIALS["BSDF"]),
+        material(**rough),
+    ])
+    ibl = sun_sky_ibl(ibl_size[0], ibl_size[1])
+    return capi.SceneData([floor, sphere, box((2.2, 0.0, -1.0), (3.6, 1.6, 0.6))], mats, None, None, background=(0, 0, 0, 0), ibl=ibl)
+
+
+def caustic_camera(width=1920, height=1080):
+    return capi.camera_init((0.0, 4.5, -9.0), (0.4, 0.6, 0.0), (0.0, 1.0, 0.0), 45.0, width, height)
+
+
+def bounding_sphere(data):
+    """SceneResource::boundingSphere as {centre of the scene's AABB, half its diagonal} (the reference declares the field,
+    SceneResource.h:78, and reads it in AreaLighting.cpp:274-275 / VCM.cpp:778; the baker's value is not in the tree)."""
+    lo = np.min([m["positions"].min(axis=0) for m in data.meshes], axis=0).astype(np.float64)
+    hi = np.max([m["positions"].max(axis=0) for m in data.meshes], axis=0).astype(np.float64)
+    c = 0.5 * (lo + hi)
+    return (float(c[0]), float(c[1]), float(c[2]), float(0.5 * np.linalg.norm(hi - lo)))

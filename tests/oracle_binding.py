@@ -140,6 +140,38 @@ class ShadingOracle(_Lib):
         assert rc == 0, rc
         return tpp, xy
 
+    # VCM building blocks (live code in the reference: AreaLighting.cpp:246-331, VCMCommon.cpp:37-112) ------------------
+    def ibl_emit(self, h, sphere4, u4):
+        u4 = _f32(u4).reshape(-1, 4)
+        n = u4.shape[0]
+        sphere4 = _f32(sphere4, (4,))
+        pdr, pdfs = np.zeros((n, 9), np.float32), np.zeros((n, 3), np.float32)
+        rc = self.fn("ibl_emit")(h, _ptr(sphere4), C.c_size_t(n), _ptr(u4), _ptr(pdr), _ptr(pdfs))
+        assert rc == 0, rc
+        return pdr, pdfs
+
+    def ibl_direct(self, h, u2):
+        u2 = _f32(u2).reshape(-1, 2)
+        out = np.zeros(u2.shape[0], dtype=capi.LIGHT_SAMPLE_DTYPE)
+        rc = self.fn("ibl_direct")(h, C.c_size_t(u2.shape[0]), _ptr(u2), _ptr(out))
+        assert rc == 0, rc
+        return out
+
+    def ibl_radiance(self, h, sphere4, dirs):
+        dirs = _f32(dirs).reshape(-1, 3)
+        n = dirs.shape[0]
+        sphere4 = _f32(sphere4, (4,))
+        rgb, pdfs = np.zeros((n, 3), np.float32), np.zeros((n, 2), np.float32)
+        rc = self.fn("ibl_radiance")(h, _ptr(sphere4), C.c_size_t(n), _ptr(dirs), _ptr(rgb), _ptr(pdfs))
+        assert rc == 0, rc
+        return rgb, pdfs
+
+    def vcm_iteration_constants(self, vm_count, vc_count, base_radius, alpha, iteration):
+        out = np.zeros(5, np.float32)
+        self.fn("vcm_iteration_constants")(C.c_uint32(vm_count), C.c_uint32(vc_count), C.c_float(base_radius), C.c_float(alpha),
+                                           C.c_float(iteration), _ptr(out))
+        return out
+
     def render(self, h, camera, settings, nthreads=8):
         w, hgt, layers = settings.width, settings.height, settings.layerCount
         film = [np.zeros((hgt, w, 3), np.float32) for _ in range(layers)]
@@ -202,6 +234,32 @@ class Oracle(ShadingOracle):
                                   _ptr(idx), _ptr(aabb), C.c_size_t(m), _ptr(queries), _ptr(counts), _ptr(indices), C.c_uint32(max_per_query))
         return counts, indices
 
+    def world_to_image(self, camera, points):
+        points = _f32(points).reshape(-1, 3)
+        out = np.zeros((points.shape[0], 2), np.int32)
+        self.fn("world_to_image")(C.byref(camera), C.c_size_t(points.shape[0]), _ptr(points), _ptr(out))
+        return out
+
+    def vcm_light_pass(self, h, camera, settings, nthreads=8, film=None):
+        vm_count = settings.width * settings.height
+        total = C.c_size_t(0)
+        ends = np.zeros(vm_count, np.uint32)
+        cap = vm_count * max(1, settings.maxPathLength)
+        verts = np.zeros(cap, dtype=capi.VCM_VERTEX_DTYPE)
+        rc = self.fn("vcm_light_pass")(h, C.byref(camera), C.byref(settings), _ptr(verts), C.c_size_t(cap), _ptr(ends), C.byref(total),
+                                       _ptr(film), C.c_int(nthreads))
+        if rc:
+            raise RuntimeError(f"orc_vcm_light_pass failed: {rc}")
+        return verts[:total.value].copy(), ends
+
+    def render_vcm(self, h, camera, settings, nthreads=8):
+        film = np.zeros((settings.height, settings.width, 3), np.float32)
+        stats = capi.VcmStats()
+        rc = self.fn("render_vcm")(h, C.byref(camera), C.byref(settings), _ptr(film), C.byref(stats), C.c_int(nthreads))
+        if rc:
+            raise RuntimeError(f"orc_render_vcm failed: {rc}")
+        return film, stats
+
     def rng(self, seed, pixel, sample, n):
         out = np.zeros(n, np.float32)
         self.fn("rng")(C.c_uint32(seed), C.c_uint32(pixel), C.c_uint32(sample), C.c_size_t(n), _ptr(out))
@@ -232,11 +290,23 @@ class Ref(ShadingOracle):
                                   _ptr(queries), _ptr(counts), _ptr(indices), C.c_uint32(max_per_query))
         return counts, indices
 
-    def vcm_iteration_constants(self, vm_count, vc_count, base_radius, alpha, iteration):
-        out = np.zeros(5, np.float32)
-        self.fn("vcm_iteration_constants")(C.c_uint32(vm_count), C.c_uint32(vc_count), C.c_float(base_radius), C.c_float(alpha),
-                                           C.c_float(iteration), _ptr(out))
+    def vcm_generate_light(self, h, sphere4, vc_weight, u4):
+        """VCMCommon::GenerateLightSample: rows of 13 floats (position, direction, throughput, dVCM, dVC, dVM, length|area<<8)."""
+        u4 = _f32(u4).reshape(-1, 4)
+        sphere4 = _f32(sphere4, (4,))
+        out = np.zeros((u4.shape[0], 13), np.float32)
+        rc = self.fn("vcm_generate_light")(h, _ptr(sphere4), C.c_float(vc_weight), C.c_size_t(u4.shape[0]), _ptr(u4), _ptr(out))
+        assert rc == 0, rc
         return out
+
+    def vcm_generate_camera(self, camera, light_path_count, xy, u2):
+        xy = np.ascontiguousarray(xy, dtype=np.uint32).reshape(-1, 2)
+        u2 = _f32(u2).reshape(-1, 2)
+        out, index = np.zeros((xy.shape[0], 13), np.float32), np.zeros(xy.shape[0], np.uint32)
+        rc = self.fn("vcm_generate_camera")(C.byref(camera), C.c_float(light_path_count), C.c_size_t(xy.shape[0]), _ptr(xy), _ptr(u2),
+                                            _ptr(out), _ptr(index))
+        assert rc == 0, rc
+        return out, index
 
 
 class PtexRef(_Lib):

@@ -188,3 +188,89 @@ def test_ibl_bit_exact(oracle, ref):
     np.testing.assert_allclose(fa[0], fb[0], rtol=1e-5, atol=1e-6)
     oracle.scene_destroy(ha)
     ref.scene_destroy(hb)
+
+
+# ---- VCM building blocks that are live code in the reference ---------------------------------------------------------------
+SPHERE = (0.25, 0.5, -0.75, 6.5)
+
+
+def test_vcm_ibl_emission_bit_exact(oracle, ref):
+    """EmitIblLightSample / DirectIblLightSample / IblCalculateRadiance (Shading/AreaLighting.cpp:246-331): restatement vs the
+    reference objects, same scripted uniforms."""
+    data = _ibl_scene()
+    ha, hb = oracle.scene_create(data), ref.scene_create(data)
+    u4 = inputs.uniforms(41, N, 4)
+    u4[:6] = [[0, 0, 0, 0], [1, 1, 1, 1], [0.5, 0.5, 0.5, 0.5], [0.2, 0.9, 0.5, 0.25], [0.3, 0.3, 0.0, 1.0], [0.7, 0.1, 1.0, 0.0]]
+    (pa, fa), (pb, fb) = oracle.ibl_emit(ha, SPHERE, u4), ref.ibl_emit(hb, SPHERE, u4)
+    np.testing.assert_array_equal(pa.view(np.uint32), pb.view(np.uint32))
+    np.testing.assert_array_equal(fa.view(np.uint32), fb.view(np.uint32))
+    assert (fa[:, 0] > 0).mean() > 0.9 and np.all(fa[:, 2] == 1.0)
+    u2 = inputs.uniforms(42, N, 2)
+    da, db = oracle.ibl_direct(ha, u2), ref.ibl_direct(hb, u2)
+    for f in ("direction", "radiance", "distance", "pdfW"):
+        np.testing.assert_array_equal(da[f].view(np.uint32), db[f].view(np.uint32), err_msg=f)
+    assert np.all(da["distance"] == np.float32(1e36))
+    rng = np.random.default_rng(43)
+    wi = inputs.unit_vectors(rng, N)
+    (ra, qa), (rb, qb) = oracle.ibl_radiance(ha, SPHERE, wi), ref.ibl_radiance(hb, SPHERE, wi)
+    np.testing.assert_array_equal(ra.view(np.uint32), rb.view(np.uint32))
+    np.testing.assert_array_equal(qa.view(np.uint32), qb.view(np.uint32))
+    oracle.scene_destroy(ha)
+    ref.scene_destroy(hb)
+
+
+def test_vcm_generate_samples_match_reference(oracle, ref):
+    """VCMCommon::GenerateLightSample / GenerateCameraSample (VCMCommon.cpp:37-88) from the reference objects against the
+    formulas the restatement uses (orc_vcm.h), evaluated in float32 on the restatement's own emission / camera outputs."""
+    f32 = np.float32
+    data = _ibl_scene()
+    ha, hb = oracle.scene_create(data), ref.scene_create(data)
+    u4 = inputs.uniforms(44, 5000, 4)
+    vc_weight = f32(0.37)
+    st = ref.vcm_generate_light(hb, SPHERE, vc_weight, u4)
+    pdr, pdfs = oracle.ibl_emit(ha, SPHERE, u4)
+    ok = pdfs[:, 0] > 0
+    emission, direction_pdf, cos_light = pdfs[:, 0], pdfs[:, 1], pdfs[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        thr = pdr[:, 6:9] * (f32(1.0) / emission)[:, None]
+        dvcm, dvc = direction_pdf / emission, cos_light / emission
+        dvm = cos_light / emission * vc_weight
+    np.testing.assert_array_equal(st[ok, 0:6].view(np.uint32), pdr[ok, 0:6].view(np.uint32))
+    np.testing.assert_array_equal(st[ok, 6:9].view(np.uint32), thr[ok].view(np.uint32))
+    for col, want in ((9, dvcm), (10, dvc), (11, dvm)):
+        np.testing.assert_array_equal(st[ok, col].view(np.uint32), want[ok].astype(f32).view(np.uint32))
+    assert np.all(st[:, 12] == 1.0)  # pathLength 1, isAreaMeasure 0
+
+    w, h = 64, 36
+    cam = capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, w, h)
+    rng = np.random.default_rng(45)
+    xy = np.stack([rng.integers(0, w, 4000), rng.integers(0, h, 4000)], axis=1).astype(np.uint32)
+    u2 = inputs.uniforms(46, 4000, 2)
+    cs, index = ref.vcm_generate_camera(cam, float(w * h), xy, u2)
+    rays = oracle.camera_rays(cam, xy[:, 0].astype(f32), xy[:, 1].astype(f32), u2)
+    d = np.stack([rays["dx"], rays["dy"], rays["dz"]], axis=1)
+    fwd = np.array(cam.forward[:], f32)
+    cos_cam = (fwd[0] * d[:, 0] + fwd[1] * d[:, 1]) + fwd[2] * d[:, 2]
+    dist = f32(cam.virtualImagePlaneDistance) / cos_cam
+    inv_solid = dist * dist / cos_cam
+    dvcm = f32(w * h) * (f32(1.0) / inv_solid)
+    np.testing.assert_array_equal(cs[:, 3:6].view(np.uint32), d.view(np.uint32))
+    np.testing.assert_array_equal(cs[:, 9].view(np.uint32), dvcm.astype(f32).view(np.uint32))
+    assert np.all(cs[:, 6:9] == 1.0) and np.all(cs[:, 10:12] == 0.0) and np.all(cs[:, 12] == 257.0)
+    np.testing.assert_array_equal(index, xy[:, 1] * w + xy[:, 0])
+    # WorldToImage (restated: the reference no longer has it) inverts ImageToWorldDirection
+    t = rng.uniform(0.5, 30.0, size=4000).astype(f32)
+    p = np.array(cam.position[:], f32)[None, :] + d * t[:, None]
+    frac = u2 - 0.5
+    inner = (np.abs(frac) < 0.49).all(axis=1)  # away from pixel borders, where float rounding may pick the neighbour
+    got = oracle.world_to_image(cam, p)
+    np.testing.assert_array_equal(got[inner], xy[inner].astype(np.int32))
+    oracle.scene_destroy(ha)
+    ref.scene_destroy(hb)
+
+
+def test_vcm_iteration_constants_bit_exact(oracle, ref):
+    for vm, it in ((2073600, 1.0), (2073600, 7.0), (4096, 100.0), (640 * 360, 3.0)):
+        a = oracle.vcm_iteration_constants(vm, 1, 0.0214, 0.75, it)
+        b = ref.vcm_iteration_constants(vm, 1, 0.0214, 0.75, it)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
