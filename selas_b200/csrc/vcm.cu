@@ -2,8 +2,8 @@
 //
 // Device restatement of Source/Applications/Selas/Source/VCM.cpp (VertexConnectionAndMerging, :664-697) and
 // VCMCommon.cpp.  VCM.cpp is commented out in the reference tree (it predates the current LightDirectSample /
-// CalculateSurfaceParams signatures); the fill-ins for the symbols that no longer exist are listed in DESIGN.md and
-// oracle/orc_vcm.h, and are the same here as in the oracle.  Compiled with -fmad=false -ftz=true -prec-div=true
+// CalculateSurfaceParams signatures); the fill-ins for the symbols that no longer exist are listed in DESIGN.md
+// (section 4, VCM) and are the same here as in the CPU checker.  Compiled with -fmad=false -ftz=true -prec-div=true
 // -prec-sqrt=true like shade.cu.
 //
 // One iteration (pass p, iterationIndex p + 1):
@@ -85,7 +85,8 @@ SELAS_D void sampleConcentricDisc(float r0, float r1, float& dx, float& dy) {
 }
 // ContinuationProbability, Shading/SurfaceParameters.cpp:420-424
 SELAS_D float continuationProbability(const Surface& s) { return saturate_(maxf_(maxf_(s.baseColor.x, s.baseColor.y), s.baseColor.z)); }
-// WorldToImage: inverse of ImageToWorldDirection (GeometryLib/Camera.cpp:56-60); see oracle/orc_shading.h
+// WorldToImage (called at VCM.cpp:199, no longer present in GeometryLib/Camera.cpp): inverse of ImageToWorldDirection
+// (Camera.cpp:56-60): dir ~ Z - cx X + cy Y with X, Y, Z mutually orthogonal; x = (cx + 1) w / 2, y = (1 - cy) h / 2, floor
 SELAS_D void worldToImage(const SelasCamera& cam, V3 p, int32_t& ix, int32_t& iy) {
     V3 to = p - lightF3(cam.position);
     V3 X = lightF3(cam.cameraX), Y = lightF3(cam.cameraY), Z = lightF3(cam.cameraZ);
