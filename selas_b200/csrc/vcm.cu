@@ -1010,7 +1010,8 @@ int vcmLightPassInspect(SelasScene* scene, const SelasCamera& cam, const SelasVc
         SelasVcmVertex* d_out = nullptr;
         SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&d_out, sizeof(SelasVcmVertex) * nOut));
         vcmPackVerticesKernel<<<divUp(nOut, 256), 256, 0, stream>>>(nOut, w->lvA, w->lvB, w->lvRay, w->lvHit, d_out);
-        cudaError_t e = cudaMemcpy(vertices, d_out, sizeof(SelasVcmVertex) * nOut, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpyAsync(vertices, d_out, sizeof(SelasVcmVertex) * nOut, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         cudaFree(d_out);
         SELAS_CUDA_CHECK(ctx, e);
     }
