@@ -3,6 +3,10 @@
   C1  Cornell box (Disney diffuse + copper), 512x512, 64 spp, depth 8: GPU vs the reference CPU path, plus image parity
   C4  Ptex-textured quad grid (default 1581^2 = 2,499,561 quads ~ 5M triangles, 8x8 uint8 faces written with the reference's
       PtexWriter), 1920x1080, depth 8, Ptex lookups inside the shading loop
+  C5  VCM (light paths + vertex connection + hash-grid merging) on the caustic scene (floor + glass sphere + box under a sun-and-sky
+      IBL), 1920x1080, vmCount = width*height light paths per iteration, path length <= 10: GPU iterations/s and paths/s with the
+      per-stage device times, against the CPU restatement of VCM.cpp on a reduced frame (VCM.cpp is dead code in the reference, so
+      there is no reference binary to time; kind = "port")
 One JSON document on stdout.  (C2 and the C5 hash-grid microbench are in scripts/bench_rows.py.)
 """
 import argparse
@@ -109,9 +113,58 @@ def config4(ctx, grid, spp):
     return out
 
 
+def config5(ctx, iterations, cpu_width):
+    data = scenes.caustic_scene()
+    sphere = scenes.bounding_sphere(data)
+    w, h = 1920, 1080
+    cam = scenes.caustic_camera(w, h)
+    sc = capi.Scene(ctx, data)
+    sc.render_vcm(cam, capi.vcm_settings(w, h, 1, sphere, seed=1))  # warm-up: allocations, first-launch costs
+    t0 = time.perf_counter()
+    film, st = sc.render_vcm(cam, capi.vcm_settings(w, h, iterations, sphere, seed=1, first_iteration=1))
+    e2e_s = time.perf_counter() - t0
+    paths = int(st.lightPaths + st.cameraPaths)
+    out = {"triangles": data.triangle_count(), "iterations": iterations, "vmCount": w * h, "max_path_length": 10,
+           "gpu_device_ms": st.renderMs, "gpu_ms_per_iteration": st.renderMs / iterations,
+           "gpu_paths_per_s": paths / (st.renderMs * 1e-3), "gpu_e2e_paths_per_s": paths / e2e_s,
+           "stage_ms_per_iteration": {"light_pass": st.lightPassMs / iterations, "grid_build": st.gridBuildMs / iterations,
+                                      "camera_pass_total": st.cameraPassMs / iterations, "of_which_merge": st.mergeMs / iterations,
+                                      "of_which_connect": st.connectMs / iterations},
+           "per_iteration": {"light_vertices": st.lightVertices / iterations, "closest_rays": st.closestRays / iterations,
+                             "occlusion_rays": st.occlusionRays / iterations, "merge_candidates": st.mergeCandidates / iterations,
+                             "merges_accepted": st.mergesAccepted / iterations, "connections": st.connections / iterations},
+           "merge_candidates_per_s": st.mergeCandidates / max(st.mergeMs * 1e-3, 1e-9),
+           "connections_per_s": st.connections / max(st.connectMs * 1e-3, 1e-9),
+           "kernel_launches": int(st.kernelLaunches), "last_radius": st.lastRadius,
+           "mean_radiance": float(film[np.isfinite(film).all(axis=2)].mean() / iterations),
+           "nonfinite_pixels": int((~np.isfinite(film).all(axis=2)).sum())}
+    # CPU restatement on a reduced frame (same scene, same settings otherwise): paths/s scale with vmCount
+    cw, ch = cpu_width, cpu_width * 9 // 16
+    orc = oracle_binding.load_oracle()
+    threads = len(os.sched_getaffinity(0))
+    hs = orc.scene_create(data)
+    ccam = scenes.caustic_camera(cw, ch)
+    t0 = time.perf_counter()
+    cfilm, cst = orc.render_vcm(hs, ccam, capi.vcm_settings(cw, ch, 1, sphere, seed=1, first_iteration=1), nthreads=threads)
+    cpu_s = time.perf_counter() - t0
+    orc.scene_destroy(hs)
+    gfilm, _ = sc.render_vcm(ccam, capi.vcm_settings(cw, ch, 1, sphere, seed=1, first_iteration=1))
+    ok = np.isfinite(gfilm).all(axis=2) & np.isfinite(cfilm).all(axis=2)
+    out["cpu"] = {"kind": "port", "cores": threads, "frame": [cw, ch], "seconds": cpu_s,
+                  "paths_per_s": float(cst.lightPaths + cst.cameraPaths) / cpu_s,
+                  "note": "oracle/orc_vcm.h over the oracle's scalar SAH-BVH2; VCM.cpp is commented out in the reference"}
+    out["image_parity_reduced_frame"] = {"mean_ratio_gpu_over_cpu": float(gfilm[ok].mean() / cfilm[ok].mean()),
+                                         "relMSE_2x2_binned": relmse(gfilm.reshape(ch // 2, 2, cw // 2, 2, 3).mean(axis=(1, 3)),
+                                                                     cfilm.reshape(ch // 2, 2, cw // 2, 2, 3).mean(axis=(1, 3)))}
+    sc.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="1,4")
+    ap.add_argument("--configs", default="1,4,5")
+    ap.add_argument("--c5-iterations", type=int, default=8)
+    ap.add_argument("--c5-cpu-width", type=int, default=1920)
     ap.add_argument("--c4-grid", type=int, default=1581)
     ap.add_argument("--c4-spp", type=int, default=128)
     args = ap.parse_args()
@@ -121,6 +174,8 @@ def main():
         doc["config1_cornell_512x512_64spp_depth8"] = config1(ctx)
     if "4" in args.configs.split(","):
         doc["config4_ptex_1080p_depth8"] = config4(ctx, args.c4_grid, args.c4_spp)
+    if "5" in args.configs.split(","):
+        doc["config5_vcm_1080p"] = config5(ctx, args.c5_iterations, args.c5_cpu_width)
     print(json.dumps(doc, indent=1))
 
 

@@ -25,6 +25,7 @@
 //   shadow queue   ray 32 B + payload 16 B {contribution, pixel}
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "disney.cuh"
@@ -665,6 +666,162 @@ __global__ void __launch_bounds__(128) vcmMergeKernel(SceneGpu sc, VcmParams prm
     if (merges) atomicAdd(statCounters + 1, (unsigned long long)merges);
 }
 
+// ---- merging in two phases (the default) ------------------------------------------------------------------------------
+// vcmMergeKernel above keeps the reference's serial order per camera vertex, but its per-thread candidate loops are badly
+// balanced: the caustic concentrates light vertices, so a few lanes walk hundreds of candidates and evaluate hundreds of BSDFs
+// while the rest of the warp idles (ncu, profiles/r1_vcm_*: 77 % of an iteration, 12 of 32 lanes active).  The two-phase form:
+//   gather  warp-cooperative SearchHashGrid: each lane prepares one camera vertex (position, AABB test, eight cell ranges), then
+//           the warp serves its 32 vertices in turn, 32 consecutive candidates per step (coalesced 16-byte reads); accepted
+//           (camera vertex, light vertex) pairs are appended to a dense pair list.
+//   eval    one thread per pair: MergeVertices; contributions of the same camera vertex are contiguous in the list, so a
+//           segmented warp reduction leaves one film atomic per run.
+// The per-vertex sum is then accumulated in a different order than on the CPU (fp32 reassociation only).
+constexpr int kGatherWarps = 4;
+__global__ void __launch_bounds__(kGatherWarps * 32) vcmMergeGatherKernel(HashGridView grid, uint32_t n, const SelasRay* __restrict__ rays,
+                                                                          const SelasHit* __restrict__ hits, uint2* __restrict__ pairs,
+                                                                          uint32_t pairCapacity, uint32_t* __restrict__ pairCounter,
+                                                                          unsigned long long* __restrict__ statCounters) {
+    __shared__ float sPos[kGatherWarps][32][3];
+    __shared__ uint32_t sBegin[kGatherWarps][32][8];
+    __shared__ uint32_t sCum[kGatherWarps][32][8];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t warpCount = gridDim.x * kGatherWarps;
+    const float minx = floatFromOrdered(__ldg(grid.bounds + 0)), miny = floatFromOrdered(__ldg(grid.bounds + 1)),
+                minz = floatFromOrdered(__ldg(grid.bounds + 2));
+    const float maxx = floatFromOrdered(__ldg(grid.bounds + 3)), maxy = floatFromOrdered(__ldg(grid.bounds + 4)),
+                maxz = floatFromOrdered(__ldg(grid.bounds + 5));
+    const float inv = grid.inverseCellSize, r2 = grid.radiusSq;
+    unsigned long long candidates = 0;
+    for (uint32_t base = (blockIdx.x * kGatherWarps + wib) * 32u; base < n; base += warpCount * 32u) {
+        const uint32_t qi = base + lane;
+        uint32_t total = 0;
+        if (qi < n) {
+            const uint4* hp = reinterpret_cast<const uint4*>(hits + qi);
+            uint4 h0 = __ldg(hp), h1 = __ldg(hp + 1);
+            if (h1.x != SELAS_INVALID_ID) {
+                const float4* rp = reinterpret_cast<const float4*>(rays + qi);
+                float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                float t = __uint_as_float(h0.x);
+                float px = r0.x + t * r1.x, py = r0.y + t * r1.y, pz = r0.z + t * r1.z;  // surface.position, RayPick
+                sPos[wib][lane][0] = px; sPos[wib][lane][1] = py; sPos[wib][lane][2] = pz;
+                float dminx = px - minx, dminy = py - miny, dminz = pz - minz;
+                float dmaxx = maxx - px, dmaxy = maxy - py, dmaxz = maxz - pz;
+                bool outside = (dminx < 0.0f || dminy < 0.0f || dminz < 0.0f) || (dmaxx < 0.0f || dmaxy < 0.0f || dmaxz < 0.0f);
+                if (!outside) {
+                    float cx = inv * dminx, cy = inv * dminy, cz = inv * dminz;
+                    float fx = floorf(cx), fy = floorf(cy), fz = floorf(cz);
+                    int32_t bx = (int32_t)fx, by = (int32_t)fy, bz = (int32_t)fz;
+                    if (cx - fx < 0.5f) --bx;
+                    if (cy - fy < 0.5f) --by;
+                    if (cz - fz < 0.5f) --bz;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        uint32_t cell = cellHash(bx + (c8 & 1), by + ((c8 >> 1) & 1), bz + (c8 >> 2), grid.cellCount);
+                        uint32_t b = cell ? __ldg(grid.cellEnds + cell - 1) : 0u, e = __ldg(grid.cellEnds + cell);
+                        total += e - b;
+                        sBegin[wib][lane][c8] = b;
+                        sCum[wib][lane][c8] = total;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        uint32_t pending = __ballot_sync(0xffffffffu, total != 0u);
+        while (pending) {
+            const uint32_t L = __ffs(pending) - 1u;
+            pending &= pending - 1u;
+            const float px = sPos[wib][L][0], py = sPos[wib][L][1], pz = sPos[wib][L][2];
+            uint32_t cum[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cum[k] = sCum[wib][L][k];
+            const uint32_t T = cum[7];
+            if (lane == 0) candidates += T;
+            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                bool accept = false;
+                uint32_t index = 0;
+                if (i < T) {
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) c += (i >= cum[k]) ? 1u : 0u;
+                    const uint32_t before = c ? sCum[wib][L][c - 1] : 0u;
+                    const float4 p = __ldg(grid.cellPoints + sBegin[wib][L][c] + (i - before));
+                    float dx = px - p.x, dy = py - p.y, dz = pz - p.z;
+                    float d2 = (dx * dx) + (dy * dy) + (dz * dz);
+                    accept = d2 <= r2;
+                    index = __float_as_uint(p.w);
+                }
+                const uint32_t mask = __ballot_sync(0xffffffffu, accept);
+                if (mask) {
+                    uint32_t slot = 0;
+                    if (lane == 0) slot = atomicAdd(pairCounter, (uint32_t)__popc(mask));
+                    slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(mask & ltMask);
+                    if (accept && slot < pairCapacity) pairs[slot] = make_uint2(base + L, index);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && candidates) atomicAdd(statCounters + 0, candidates);
+}
+
+__global__ void __launch_bounds__(128) vcmMergeEvalKernel(SceneGpu sc, VcmParams prm, uint32_t pairCount, const uint2* __restrict__ pairs,
+                                                          const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
+                                                          const float4* __restrict__ thrIdx, const float4* __restrict__ vertexMis,
+                                                          const float* __restrict__ ptexRgb, const float4* __restrict__ lvA,
+                                                          const float4* __restrict__ lvB, const SelasRay* __restrict__ lvRay,
+                                                          float* __restrict__ film) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    V3 c = v3(0.0f);
+    uint32_t key = 0xFFFFFFFFu;  // film pixel of this pair's camera vertex
+    if (p < pairCount) {
+        const uint2 pr = __ldg(pairs + p);
+        const uint32_t i = pr.x, pi = pr.y;
+        key = __float_as_uint(__ldg(thrIdx + i).w) & kIndexMask;
+        float4 a = __ldg(lvA + pi);
+        uint32_t bits = __float_as_uint(a.w);
+        uint32_t lvLength = (bits >> 26) & 31u;
+        uint32_t cameraLength = __float_as_uint(__ldg(vertexMis + i).w);
+        if (cameraLength + lvLength <= prm.maxPathLength) {  // VCM.cpp:371-373
+            CameraVertex cv;
+            loadCameraVertex(sc, i, rays, hits, thrIdx, vertexMis, ptexRgb, cv);
+            if (((cv.s.materialFlags & SELAS_MAT_TRANSPARENT) != 0) == ((bits & 0x80000000u) != 0)) {  // :380-383
+                float4 lb = __ldg(lvB + pi);
+                float4 ld = __ldg(reinterpret_cast<const float4*>(lvRay + pi) + 1);
+                V3 lightView = v3(-ld.x, -ld.y, -ld.z);
+                float fwd = 0.f, rev = 0.f;
+                V3 bsdf = evaluateBsdf(cv.s, cv.frame, cv.view, lightView, fwd, rev);
+                if (!isZero3(bsdf)) {
+                    fwd *= continuationProbability(cv.s);
+                    rev *= lb.w;
+                    float lightWeight = lb.x * prm.vcWeight + lb.z * fwd;
+                    float cameraWeight = cv.dVCM * prm.vcWeight + cv.dVM * rev;
+                    float misWeight = 1.0f / (lightWeight + 1.0f + cameraWeight);
+                    c = cv.throughput * prm.vmNormalization * (misWeight * bsdf * v3(a.x, a.y, a.z));
+                    if ((prm.flags & SELAS_VCM_SKIP_NONFINITE) && !finite3(c)) c = v3(0.0f);
+                }
+            }
+        }
+    }
+    // segmented reduction over runs of equal pixel (pairs of one camera vertex are mostly contiguous), one atomic per run.  Runs are
+    // numbered by their head so that the same pixel appearing in two separate runs of a warp is not merged across the gap.
+    uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || prev != key;
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const uint32_t run = __popc(heads & ((2u << lane) - 1u));
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float tx = __shfl_down_sync(0xffffffffu, c.x, o), ty = __shfl_down_sync(0xffffffffu, c.y, o), tz = __shfl_down_sync(0xffffffffu, c.z, o);
+        uint32_t r = __shfl_down_sync(0xffffffffu, run, o);
+        if (lane + o < 32 && r == run) {
+            c.x += tx; c.y += ty; c.z += tz;
+        }
+    }
+    if (head && key != 0xFFFFFFFFu && !isZero3(c)) filmAdd(film, key, c);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------------
 struct VcmBuffers {
     uint32_t capacity = 0, stride = 0;
@@ -684,6 +841,9 @@ struct VcmBuffers {
     uint32_t* counters = nullptr;  // 4 per launch slot: next paths, shadow rays, closest fetch, shadow fetch
     uint32_t counterSlots = 0;
     unsigned long long* statCounters = nullptr;  // merge candidates, merges, connections
+    uint2* pairs = nullptr;  // (camera vertex, light vertex) pairs accepted by the range query
+    uint32_t pairCapacity = 0;
+    uint32_t* pairCounter = nullptr;
     uint32_t* h_counts = nullptr;
     SelasHashGrid* grid = nullptr;
     std::vector<cudaEvent_t> events;
@@ -739,7 +899,10 @@ int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     VCM_TRY(vcmAlloc(ctx, w, &w->shadowPayload, n + nv));
     if (scene->usesPtex) VCM_TRY(vcmAlloc(ctx, w, &w->ptexRgb, 3 * n));
     VCM_TRY(vcmAlloc(ctx, w, &w->counters, (size_t)slots));
-    VCM_TRY(vcmAlloc(ctx, w, &w->statCounters, (size_t)4));
+    VCM_TRY(vcmAlloc(ctx, w, &w->statCounters, (size_t)8));
+    w->pairCapacity = (uint32_t)std::min<size_t>(std::max<size_t>(n * 8, (size_t)1 << 20), (size_t)1 << 28);
+    VCM_TRY(vcmAlloc(ctx, w, &w->pairs, (size_t)w->pairCapacity));
+    VCM_TRY(vcmAlloc(ctx, w, &w->pairCounter, (size_t)1));
 #undef VCM_TRY
     SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4));
     return SELAS_OK;
@@ -893,8 +1056,11 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
     rc = ensureVcm(scene, vmCount, vs.maxPathLength);
     if (rc) return rc;
     VcmBuffers* w = (VcmBuffers*)scene->vcm;
-    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->statCounters, 0, 4 * sizeof(unsigned long long), stream));
+    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->statCounters, 0, 8 * sizeof(unsigned long long), stream));
     EventSpans ev{w, stream};
+    // SELAS_VCM_SERIAL_MERGE=1: one thread per camera vertex, candidates in the reference's order (A/B and parity of the summation order)
+    static const bool serialMerge = getenv("SELAS_VCM_SERIAL_MERGE") && atoi(getenv("SELAS_VCM_SERIAL_MERGE")) != 0;
+    unsigned long long pairsAccepted = 0;
     const size_t tAll = ev.mark();
     for (uint32_t itn = 0; itn < vs.iterations; ++itn) {
         const uint32_t pass = vs.firstIteration + itn;
@@ -949,17 +1115,43 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
                 ev.span(4, tc);
                 ++st.kernelLaunches;
             }
-            if (merging) {
+            if (merging && serialMerge) {
                 size_t tm = ev.mark();
                 vcmMergeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, hashGridView(w->grid), n, w->rays[cur], w->hits, w->thrIdx[cur],
                                                                    w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, d_film, w->statCounters);
                 ev.span(3, tm);
                 ++st.kernelLaunches;
+            } else if (merging) {
+                size_t tm = ev.mark();
+                SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->pairCounter, 0, sizeof(uint32_t), stream));
+                unsigned grid = (unsigned)std::min<uint32_t>(divUp(n, kGatherWarps * 32), (uint32_t)ctx->smCount * 16);
+                vcmMergeGatherKernel<<<grid, kGatherWarps * 32, 0, stream>>>(hashGridView(w->grid), n, w->rays[cur], w->hits, w->pairs, w->pairCapacity,
+                                                                             w->pairCounter, w->statCounters);
+                ev.span(3, tm);
+                ++st.kernelLaunches;
             }
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            if (merging && !serialMerge)
+                SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts + 2, w->pairCounter, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
             SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
             uint32_t nNext = w->h_counts[0], nShadow = w->h_counts[1];
+            if (merging && !serialMerge) {
+                const uint32_t pairCount = w->h_counts[2];
+                size_t tm = ev.mark();
+                if (pairCount > w->pairCapacity) {
+                    // more accepted pairs than the list holds: this bounce falls back to the serial kernel (its candidate count is
+                    // added a second time; the gather's pairs are dropped)
+                    vcmMergeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, hashGridView(w->grid), n, w->rays[cur], w->hits, w->thrIdx[cur],
+                                                                       w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, d_film, w->statCounters + 4);
+                } else if (pairCount) {
+                    vcmMergeEvalKernel<<<divUp(pairCount, 128), 128, 0, stream>>>(scene->gpu, prm, pairCount, w->pairs, w->rays[cur], w->hits, w->thrIdx[cur],
+                                                                                   w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, d_film);
+                }
+                pairsAccepted += pairCount;
+                ev.span(3, tm);
+                ++st.kernelLaunches;
+            }
             if (nShadow) {
                 rc = launchShadowAccumulate(scene, nullptr, nShadow, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream);
                 if (rc) return rc;
@@ -978,7 +1170,7 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
     SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
     ev.collect(st);
     st.mergeCandidates = h[0];
-    st.mergesAccepted = h[1];
+    st.mergesAccepted = serialMerge ? h[1] : pairsAccepted;
     st.connections = h[2];
     if (stats) *stats = st;
     return SELAS_OK;
