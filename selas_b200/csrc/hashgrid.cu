@@ -467,6 +467,17 @@ HashGridView hashGridView(const SelasHashGrid* g) {
     v.n = (uint32_t)g->n;
     return v;
 }
+// a grid whose buffers hold up to n points / cellCount cells, so that per-iteration rebuilds never allocate
+int hashGridReserve(SelasContext* ctx, SelasHashGrid** inout, size_t n, uint32_t cellCount) {
+    SelasHashGrid* g = *inout;
+    if (!g) {
+        g = new (std::nothrow) SelasHashGrid();
+        if (!g) return SELAS_ERR_MEMORY;
+        g->ctx = ctx;
+        *inout = g;
+    }
+    return reserve(g, n, cellCount);
+}
 uint32_t scanScratchWords(uint32_t n) { return divUp(n, kScanTile) + 1; }
 int launchScanU32(SelasContext* ctx, const uint32_t* d_in, uint32_t n, uint32_t* d_sums, uint32_t* d_inclusive, uint32_t* d_exclusive,
                   cudaStream_t st) {

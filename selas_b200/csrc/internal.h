@@ -137,6 +137,7 @@ void freeWavefront(SelasScene* scene);
 // hashgrid.cu
 struct HashGridView;
 HashGridView hashGridView(const SelasHashGrid* grid);
+int hashGridReserve(SelasContext* ctx, SelasHashGrid** inout, size_t n, uint32_t cellCount);
 uint32_t scanScratchWords(uint32_t n);
 int launchScanU32(SelasContext* ctx, const uint32_t* d_in, uint32_t n, uint32_t* d_sums, uint32_t* d_inclusive, uint32_t* d_exclusive,
                   cudaStream_t stream);

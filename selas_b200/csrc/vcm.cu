@@ -508,30 +508,59 @@ SELAS_D bool loadCameraVertex(const SceneGpu& sc, uint32_t i, const SelasRay* ra
     return true;
 }
 
-// ConnectPathVertices (VCM.cpp:295-359): one thread per (camera vertex, k-th vertex of light path vcIndex = index; vcCount = 1)
-__global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams prm, uint32_t n, const SelasRay* __restrict__ rays,
+// Pairs for ConnectPathVertices: camera vertex i connects to the vertices of light path vcIndex = index (vcCount = 1, VCM.cpp:617-631).
+// The path's vertices have pathLength 1, 2, ...: vertex k has length k + 1, so the reference's `break` at the first vertex that is too
+// long (:624-626) bounds k by maxPathLength - 2 - cameraLength.  One thread per camera vertex, warp-scanned append of (i, li) pairs.
+__global__ void __launch_bounds__(256) vcmConnectGatherKernel(VcmParams prm, uint32_t n, const SelasHit* __restrict__ hits,
+                                                              const float4* __restrict__ thrIdx, const float4* __restrict__ vertexMis,
+                                                              const uint32_t* __restrict__ pathStarts, const uint32_t* __restrict__ pathEnds,
+                                                              uint2* __restrict__ pairs, uint32_t* __restrict__ pairCounter) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t count = 0, start = 0;
+    if (i < n && __ldg(reinterpret_cast<const uint32_t*>(hits + i) + 4) != SELAS_INVALID_ID) {
+        uint32_t index = __float_as_uint(__ldg(thrIdx + i).w) & kIndexMask;
+        uint32_t cameraLength = __float_as_uint(__ldg(vertexMis + i).w);
+        start = __ldg(pathStarts + index);
+        count = __ldg(pathEnds + index) - start;
+        uint32_t allowed = prm.maxPathLength > cameraLength + 1 ? prm.maxPathLength - 1 - cameraLength : 0u;
+        count = count < allowed ? count : allowed;
+    }
+    uint32_t incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += y;
+    }
+    uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(pairCounter, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - count;
+    for (uint32_t k = 0; k < count; ++k) pairs[base + k] = make_uint2(i, start + k);
+}
+
+// ConnectPathVertices (VCM.cpp:295-359): one thread per gathered (camera vertex, light vertex) pair; the pair count lives in device memory
+__global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams prm, const uint32_t* __restrict__ pairCountPtr,
+                                                        const uint2* __restrict__ pairs, const SelasRay* __restrict__ rays,
                                                         const SelasHit* __restrict__ hits, const float4* __restrict__ thrIdx,
                                                         const float4* __restrict__ vertexMis, const float* __restrict__ ptexRgb,
-                                                        const uint32_t* __restrict__ pathStarts, const uint32_t* __restrict__ pathEnds,
                                                         const float4* __restrict__ lvA, const float4* __restrict__ lvB,
                                                         const SelasRay* __restrict__ lvRay, const SelasHit* __restrict__ lvHit,
                                                         SelasRay* __restrict__ shadowRays, float4* __restrict__ shadowPayload,
-                                                        uint32_t* __restrict__ counters, unsigned long long* __restrict__ statCounters) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                        uint32_t* __restrict__ counters) {
+    const uint32_t pairCount = __ldg(pairCountPtr);
+    // whole warps iterate together (the appends are warp-collective)
+    for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < pairCount; t0 += gridDim.x * blockDim.x) {
+    const uint32_t t = t0 + threadIdx.x;
     bool wantShadow = false;
     V3 shO = v3(0.f), shD = v3(0.f);
     float shNear = 0.f, shFar = 0.f;
     float4 shPayload = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < (size_t)n * prm.stride) {
-        const uint32_t i = (uint32_t)(t / prm.stride), k = (uint32_t)(t - (size_t)i * prm.stride);
-        const uint4* hp = reinterpret_cast<const uint4*>(hits + i);
-        if (__ldg(reinterpret_cast<const uint32_t*>(hp) + 4) != SELAS_INVALID_ID) {
-            uint32_t index = __float_as_uint(__ldg(thrIdx + i).w) & kIndexMask;
-            uint32_t cameraLength = __float_as_uint(__ldg(vertexMis + i).w);
-            uint32_t li = __ldg(pathStarts + index) + k;
-            // the path's vertices have pathLength 1, 2, ...: vertex k has length k + 1, so the reference's `break` at the first
-            // vertex that is too long (VCM.cpp:624-626) is the same as skipping every such vertex
-            if (li < __ldg(pathEnds + index) && (k + 1) + 1 + cameraLength <= prm.maxPathLength) {
+    if (t < pairCount) {
+        const uint2 pr = __ldg(pairs + t);
+        const uint32_t i = pr.x, li = pr.y;
+        {
+            {
                 CameraVertex cv;
                 loadCameraVertex(sc, i, rays, hits, thrIdx, vertexMis, ptexRgb, cv);
                 float4 a = __ldg(lvA + li), b = __ldg(lvB + li);
@@ -542,7 +571,6 @@ __global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams p
                 Surface ls;  // CalculateSurfaceParams(context, &lightVertex.hit, lightSurface), :314-317
                 V3 lo = v3(lr0.x, lr0.y, lr0.z), ld = v3(lr1.x, lr1.y, lr1.z);
                 surfaceFromHit(sc, lo, ld, __uint_as_float(lh0.x), __uint_as_float(lh0.y), __uint_as_float(lh0.z), lh0.w, lh1.x, lh1.y, nullptr, ls);
-                atomicAdd(statCounters + 2, 1ull);
                 V3 direction = ls.position - cv.s.position;
                 float distanceSquared = dot(direction, direction);
                 float distance = sqrtf(distanceSquared);
@@ -597,6 +625,7 @@ __global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams p
     if (wantShadow) {
         storeRay(shadowRays, slotS, shO, shNear, shD, shFar);
         shadowPayload[slotS] = shPayload;
+    }
     }
 }
 
@@ -766,14 +795,18 @@ __global__ void __launch_bounds__(kGatherWarps * 32) vcmMergeGatherKernel(HashGr
     if (lane == 0 && candidates) atomicAdd(statCounters + 0, candidates);
 }
 
-__global__ void __launch_bounds__(128) vcmMergeEvalKernel(SceneGpu sc, VcmParams prm, uint32_t pairCount, const uint2* __restrict__ pairs,
+__global__ void __launch_bounds__(128) vcmMergeEvalKernel(SceneGpu sc, VcmParams prm, const uint32_t* __restrict__ pairCountPtr, uint32_t pairCapacity,
+                                                          const uint2* __restrict__ pairs,
                                                           const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                                           const float4* __restrict__ thrIdx, const float4* __restrict__ vertexMis,
                                                           const float* __restrict__ ptexRgb, const float4* __restrict__ lvA,
                                                           const float4* __restrict__ lvB, const SelasRay* __restrict__ lvRay,
                                                           float* __restrict__ film) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pairCount = __ldg(pairCountPtr);
+    if (pairCount > pairCapacity) return;  // the list overflowed: the host runs the serial kernel for this bounce instead
     const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t p0 = blockIdx.x * blockDim.x; p0 < pairCount; p0 += gridDim.x * blockDim.x) {
+    const uint32_t p = p0 + threadIdx.x;
     V3 c = v3(0.0f);
     uint32_t key = 0xFFFFFFFFu;  // film pixel of this pair's camera vertex
     if (p < pairCount) {
@@ -820,6 +853,7 @@ __global__ void __launch_bounds__(128) vcmMergeEvalKernel(SceneGpu sc, VcmParams
         }
     }
     if (head && key != 0xFFFFFFFFu && !isZero3(c)) filmAdd(film, key, c);
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -837,13 +871,15 @@ struct VcmBuffers {
     uint32_t *lvCount = nullptr, *pathEnds = nullptr, *pathStarts = nullptr, *scanSums = nullptr;
     SelasRay* shadowRays = nullptr;
     float4* shadowPayload = nullptr;
+    uint32_t shadowCapacity = 0;
     float* ptexRgb = nullptr;
     uint32_t* counters = nullptr;  // 4 per launch slot: next paths, shadow rays, closest fetch, shadow fetch
     uint32_t counterSlots = 0;
     unsigned long long* statCounters = nullptr;  // merge candidates, merges, connections
     uint2* pairs = nullptr;  // (camera vertex, light vertex) pairs accepted by the range query
     uint32_t pairCapacity = 0;
-    uint32_t* pairCounter = nullptr;
+    uint32_t* pairCounter = nullptr;  // 2 per bounce: merge pairs, connect pairs
+    uint2* connPairs = nullptr;
     uint32_t* h_counts = nullptr;
     SelasHashGrid* grid = nullptr;
     std::vector<cudaEvent_t> events;
@@ -862,7 +898,7 @@ int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     VcmBuffers* w = (VcmBuffers*)scene->vcm;
     const uint32_t stride = maxPathLength > 3 ? maxPathLength - 3 : 0;  // light vertices have pathLength 1 .. max-3 (VCM.cpp:509)
     const uint32_t slots = 4 * (2 * maxPathLength + 4);
-    if (w && w->capacity >= vmCount && w->stride >= stride && w->counterSlots >= slots) return SELAS_OK;
+    if (w && w->capacity == vmCount && w->stride == stride && w->counterSlots == slots) return SELAS_OK;
     if (w) freeVcm(scene);
     w = new VcmBuffers();
     scene->vcm = w;
@@ -897,15 +933,18 @@ int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     VCM_TRY(vcmAlloc(ctx, w, &w->scanSums, (size_t)scanScratchWords(vmCount)));
     VCM_TRY(vcmAlloc(ctx, w, &w->shadowRays, n + nv));       // one direct connection + up to `stride` vertex connections per vertex
     VCM_TRY(vcmAlloc(ctx, w, &w->shadowPayload, n + nv));
+    w->shadowCapacity = (uint32_t)std::min<size_t>(n + nv, 0xFFFFFFFFull);
     if (scene->usesPtex) VCM_TRY(vcmAlloc(ctx, w, &w->ptexRgb, 3 * n));
     VCM_TRY(vcmAlloc(ctx, w, &w->counters, (size_t)slots));
     VCM_TRY(vcmAlloc(ctx, w, &w->statCounters, (size_t)8));
     w->pairCapacity = (uint32_t)std::min<size_t>(std::max<size_t>(n * 8, (size_t)1 << 20), (size_t)1 << 28);
     VCM_TRY(vcmAlloc(ctx, w, &w->pairs, (size_t)w->pairCapacity));
-    VCM_TRY(vcmAlloc(ctx, w, &w->pairCounter, (size_t)1));
+    VCM_TRY(vcmAlloc(ctx, w, &w->pairCounter, (size_t)(2 * maxPathLength + 2)));
+    VCM_TRY(vcmAlloc(ctx, w, &w->connPairs, nv));
 #undef VCM_TRY
-    SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4));
-    return SELAS_OK;
+    SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 8));
+    // the hash grid is rebuilt every iteration over a varying number of vertices: size it once for the worst case
+    return hashGridReserve(ctx, &w->grid, nv, vmCount);
 }
 
 struct EventSpans {
@@ -1060,7 +1099,7 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
     EventSpans ev{w, stream};
     // SELAS_VCM_SERIAL_MERGE=1: one thread per camera vertex, candidates in the reference's order (A/B and parity of the summation order)
     static const bool serialMerge = getenv("SELAS_VCM_SERIAL_MERGE") && atoi(getenv("SELAS_VCM_SERIAL_MERGE")) != 0;
-    unsigned long long pairsAccepted = 0;
+    unsigned long long pairsAccepted = 0, connectionsMade = 0;
     const size_t tAll = ev.mark();
     for (uint32_t itn = 0; itn < vs.iterations; ++itn) {
         const uint32_t pass = vs.firstIteration + itn;
@@ -1086,6 +1125,7 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
         // ---- camera paths ----
         t0 = ev.mark();
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
+        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->pairCounter, 0, sizeof(uint32_t) * (2 * (size_t)vs.maxPathLength + 2), stream));
         vcmGenerateCameraKernel<<<divUp(vmCount, 256), 256, 0, stream>>>(cam, prm, vmCount, w->rays[0], w->thrIdx[0], w->mis[0]);
         ++st.kernelLaunches;
         uint32_t n = vmCount;
@@ -1106,14 +1146,20 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
                                                                      w->vertexMis, w->rays[cur ^ 1], w->thrIdx[cur ^ 1], w->mis[cur ^ 1],
                                                                      w->shadowRays, w->shadowPayload, ctr, d_film);
             st.kernelLaunches += 2;
-            if (!(vs.flags & SELAS_VCM_NO_CONNECTIONS) && prm.stride && total > 0) {
+            // Everything below is enqueued before the one host synchronisation of the bounce; the pair and shadow-ray counts stay
+            // in device memory (grid-stride kernels, the persistent trace kernel reads its ray count through a pointer).
+            uint32_t* pairCtr = w->pairCounter + 2 * (size_t)it;  // [0] merge pairs, [1] connect pairs (zeroed with the queue counters)
+            const bool connecting = !(vs.flags & SELAS_VCM_NO_CONNECTIONS) && prm.stride && total > 0;
+            const unsigned evalGrid = (unsigned)ctx->smCount * 8;
+            if (connecting) {
                 size_t tc = ev.mark();
-                vcmConnectKernel<<<divUp((size_t)n * prm.stride, 128), 128, 0, stream>>>(scene->gpu, prm, n, w->rays[cur], w->hits, w->thrIdx[cur],
-                                                                                          w->vertexMis, ptexRgb, w->pathStarts, w->pathEnds, w->lvA, w->lvB,
-                                                                                          w->lvRay, w->lvHit, w->shadowRays, w->shadowPayload, ctr,
-                                                                                          w->statCounters);
+                vcmConnectGatherKernel<<<divUp(n, 256), 256, 0, stream>>>(prm, n, w->hits, w->thrIdx[cur], w->vertexMis, w->pathStarts, w->pathEnds,
+                                                                          w->connPairs, pairCtr + 1);
+                vcmConnectKernel<<<evalGrid, 128, 0, stream>>>(scene->gpu, prm, pairCtr + 1, w->connPairs, w->rays[cur], w->hits, w->thrIdx[cur],
+                                                                w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, w->lvHit, w->shadowRays,
+                                                                w->shadowPayload, ctr);
                 ev.span(4, tc);
-                ++st.kernelLaunches;
+                st.kernelLaunches += 2;
             }
             if (merging && serialMerge) {
                 size_t tm = ev.mark();
@@ -1123,40 +1169,37 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
                 ++st.kernelLaunches;
             } else if (merging) {
                 size_t tm = ev.mark();
-                SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->pairCounter, 0, sizeof(uint32_t), stream));
                 unsigned grid = (unsigned)std::min<uint32_t>(divUp(n, kGatherWarps * 32), (uint32_t)ctx->smCount * 16);
                 vcmMergeGatherKernel<<<grid, kGatherWarps * 32, 0, stream>>>(hashGridView(w->grid), n, w->rays[cur], w->hits, w->pairs, w->pairCapacity,
-                                                                             w->pairCounter, w->statCounters);
+                                                                             pairCtr, w->statCounters);
+                vcmMergeEvalKernel<<<evalGrid, 128, 0, stream>>>(scene->gpu, prm, pairCtr, w->pairCapacity, w->pairs, w->rays[cur], w->hits,
+                                                                  w->thrIdx[cur], w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, d_film);
                 ev.span(3, tm);
-                ++st.kernelLaunches;
+                st.kernelLaunches += 2;
             }
+            // shadow rays of the direct connection and of the vertex connections: count read on the device
+            rc = launchShadowAccumulate(scene, ctr + 1, w->shadowCapacity, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream);
+            if (rc) return rc;
+            ++st.kernelLaunches;
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            if (merging && !serialMerge)
-                SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts + 2, w->pairCounter, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts + 2, pairCtr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
             SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
-            uint32_t nNext = w->h_counts[0], nShadow = w->h_counts[1];
+            const uint32_t nNext = w->h_counts[0];
+            st.occlusionRays += w->h_counts[1];
+            connectionsMade += w->h_counts[3];
             if (merging && !serialMerge) {
                 const uint32_t pairCount = w->h_counts[2];
-                size_t tm = ev.mark();
                 if (pairCount > w->pairCapacity) {
-                    // more accepted pairs than the list holds: this bounce falls back to the serial kernel (its candidate count is
-                    // added a second time; the gather's pairs are dropped)
+                    // more accepted pairs than the list holds (the eval kernel then did nothing): this bounce is merged by the serial
+                    // kernel instead, before the queue buffers are reused
+                    size_t tm = ev.mark();
                     vcmMergeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, hashGridView(w->grid), n, w->rays[cur], w->hits, w->thrIdx[cur],
                                                                        w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, d_film, w->statCounters + 4);
-                } else if (pairCount) {
-                    vcmMergeEvalKernel<<<divUp(pairCount, 128), 128, 0, stream>>>(scene->gpu, prm, pairCount, w->pairs, w->rays[cur], w->hits, w->thrIdx[cur],
-                                                                                   w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, d_film);
+                    ev.span(3, tm);
+                    ++st.kernelLaunches;
                 }
                 pairsAccepted += pairCount;
-                ev.span(3, tm);
-                ++st.kernelLaunches;
-            }
-            if (nShadow) {
-                rc = launchShadowAccumulate(scene, nullptr, nShadow, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream);
-                if (rc) return rc;
-                st.occlusionRays += nShadow;
-                ++st.kernelLaunches;
             }
             n = nNext;
             cur ^= 1;
@@ -1171,7 +1214,7 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
     ev.collect(st);
     st.mergeCandidates = h[0];
     st.mergesAccepted = serialMerge ? h[1] : pairsAccepted;
-    st.connections = h[2];
+    st.connections = connectionsMade;
     if (stats) *stats = st;
     return SELAS_OK;
 }
