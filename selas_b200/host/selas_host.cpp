@@ -6,6 +6,7 @@
 #include <cctype>
 #include <cmath>
 #include <cstdarg>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -305,6 +306,23 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
         d.lightSetIndex = m.lightSetIndex;
         d.ptex = m.ptex;
     }
+    // SceneResource::aaBox / boundingSphere (SceneResource.h:77-78): the instances' boxes in the reference (SceneResource.cpp:196-201);
+    // here the vertices of the identity-instanced meshes
+    float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (const SceneMesh& m : scene->meshes)
+        for (size_t v = 0; v + 2 < m.positions.size(); v += 3)
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = std::min(lo[k], m.positions[v + k]);
+                hi[k] = std::max(hi[k], m.positions[v + k]);
+            }
+    double diag2 = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        scene->aaBox[k] = lo[k];
+        scene->aaBox[3 + k] = hi[k];
+        scene->boundingSphere[k] = (float)(0.5 * ((double)lo[k] + (double)hi[k]));
+        diag2 += ((double)hi[k] - (double)lo[k]) * ((double)hi[k] - (double)lo[k]);
+    }
+    scene->boundingSphere[3] = (float)(0.5 * sqrt(diag2));
     SelasSceneDesc desc;
     memset(&desc, 0, sizeof(desc));
     desc.meshes = meshes.data();
@@ -449,6 +467,181 @@ Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, c
     return Success_;
 }
 }  // namespace PathTracer
+
+// ---- image based light + config 5 scene -------------------------------------------------------------------------------
+void ImageBasedLight::BuildDensityFunctions() {
+    const float pi = 3.141592653589793f;
+    marginal.assign(height, 0.f);
+    conditional.assign((size_t)width * height, 0.f);
+    std::vector<float> rowSum(height, 0.f);
+    std::vector<float> inten(width);
+    for (uint32_t y = 0; y < height; ++y) {
+        float theta = ((float)y + 0.5f) * pi / (float)height;
+        float st = sinf(theta);
+        float run = 0.f;
+        for (uint32_t x = 0; x < width; ++x) {
+            const float* t = &lightData[3 * ((size_t)y * width + x)];
+            float luma = t[0] * 0.299f + t[1] * 0.587f + t[2] * 0.114f;
+            inten[x] = st * luma;
+            run += inten[x];
+        }
+        rowSum[y] = run;
+        if (run > 0.f) {
+            float inv = 1.0f / run, c = 0.f;
+            for (uint32_t x = 0; x < width; ++x) {
+                c += inv * inten[x];
+                conditional[(size_t)y * width + x] = c;
+            }
+        }
+        conditional[(size_t)y * width + width - 1] = 1.0f;
+    }
+    float total = 0.f;
+    for (uint32_t y = 0; y < height; ++y) total += rowSum[y];
+    float c = 0.f;
+    for (uint32_t y = 0; y < height; ++y) {
+        c += total > 0.f ? rowSum[y] * (1.0f / total) : 0.f;
+        marginal[y] = c;
+    }
+    marginal[height - 1] = 1.0f;
+    memset(&desc, 0, sizeof(desc));
+    desc.width = width;
+    desc.height = height;
+    desc.marginalDensityFunction = marginal.data();
+    desc.conditionalDensityFunctions = conditional.data();
+    desc.lightData = lightData.data();
+    desc.missWidth = missWidth;
+    desc.missHeight = missHeight;
+    desc.missData = missData.data();
+    desc.rotationRadians = rotationRadians;
+    desc.exposureScale = exposureScale;
+}
+
+// identical to selas_b200/scenes.py:caustic_scene / sun_sky_ibl
+void MakeCausticScene(SceneResource* scene, ImageBasedLight* ibl, uint32_t sphereTheta, uint32_t spherePhi, uint32_t floorCells) {
+    const double pi = 3.14159265358979323846;
+    scene->meshes.assign(3, SceneMesh());
+    for (auto& m : scene->meshes) m.indicesPerFace = 4;
+    SceneMesh& floor = scene->meshes[0];
+    const uint32_t g = floorCells;
+    for (uint32_t i = 0; i <= g; ++i)
+        for (uint32_t j = 0; j <= g; ++j) {
+            floor.positions.push_back((float)(-6.0 + 12.0 * i / g));
+            floor.positions.push_back(0.0f);
+            floor.positions.push_back((float)(-6.0 + 12.0 * j / g));
+        }
+    for (uint32_t i = 0; i < g; ++i)
+        for (uint32_t j = 0; j < g; ++j) {
+            uint32_t v00 = i * (g + 1) + j;
+            uint32_t q[4] = {v00, v00 + 1, v00 + g + 2, v00 + g + 1};  // CCW seen from +y
+            floor.indices.insert(floor.indices.end(), q, q + 4);
+        }
+    floor.materialIndex = 0;
+    SceneMesh& sphere = scene->meshes[1];
+    const double cx = 0.0, cy = 1.2, cz = 0.0, R = 1.2;
+    for (uint32_t t = 0; t <= sphereTheta; ++t)
+        for (uint32_t p = 0; p < spherePhi; ++p) {
+            double th = pi * t / sphereTheta, ph = 2.0 * pi * p / spherePhi;
+            double nx = sin(th) * cos(ph), ny = cos(th), nz = sin(th) * sin(ph);
+            sphere.positions.push_back((float)(cx + R * nx));
+            sphere.positions.push_back((float)(cy + R * ny));
+            sphere.positions.push_back((float)(cz + R * nz));
+            sphere.normals.push_back((float)nx);
+            sphere.normals.push_back((float)ny);
+            sphere.normals.push_back((float)nz);
+        }
+    for (uint32_t t = 0; t < sphereTheta; ++t)
+        for (uint32_t p = 0; p < spherePhi; ++p) {
+            uint32_t pn = (p + 1) % spherePhi;
+            uint32_t q[4] = {t * spherePhi + p, t * spherePhi + pn, (t + 1) * spherePhi + pn, (t + 1) * spherePhi + p};
+            sphere.indices.insert(sphere.indices.end(), q, q + 4);
+        }
+    sphere.materialIndex = 1;
+    SceneMesh& box = scene->meshes[2];
+    {
+        const float x0 = 2.2f, y0 = 0.0f, z0 = -1.0f, x1 = 3.6f, y1 = 1.6f, z1 = 0.6f;
+        float v[8][3] = {{x0, y0, z0}, {x1, y0, z0}, {x1, y0, z1}, {x0, y0, z1}, {x0, y1, z0}, {x1, y1, z0}, {x1, y1, z1}, {x0, y1, z1}};
+        addQuad(box, v[4], v[7], v[6], v[5]);
+        addQuad(box, v[0], v[4], v[5], v[1]);
+        addQuad(box, v[1], v[5], v[6], v[2]);
+        addQuad(box, v[2], v[6], v[7], v[3]);
+        addQuad(box, v[3], v[7], v[4], v[0]);
+    }
+    box.materialIndex = 2;
+    const char* rough = "{\"shaderName\":\"DisneySolid\",\"baseColor\":[%s],\"ior\":1.2,\"metallic\":0.0,\"specularTint\":0.0,\"roughness\":0.8,"
+                        "\"anisotropic\":0.0,\"sheen\":0.0,\"sheenTint\":0.0,\"clearcoat\":0.0,\"clearcoatGloss\":0.0,\"specTrans\":0.0,"
+                        "\"diffTrans\":0.0,\"flatness\":0.5}";
+    const char* glass = "{\"shaderName\":\"DisneySolid\",\"baseColor\":[0.9,1.0,0.9],\"transmittanceColor\":[0.4519,1.0,0.7054],\"ior\":1.7,"
+                        "\"metallic\":0.0,\"specularTint\":0.0,\"roughness\":0.01,\"anisotropic\":0.0,\"sheen\":0.0,\"sheenTint\":0.0,"
+                        "\"clearcoat\":0.0,\"clearcoatGloss\":0.0,\"specTrans\":1.0,\"diffTrans\":0.0,\"flatness\":0.0,\"scatterDistance\":15.0}";
+    scene->materials.assign(3, SelasMaterial());
+    char buf[1024];
+    ImportedMaterialData imp;
+    snprintf(buf, sizeof(buf), rough, "0.8,0.8,0.78");
+    ImportMaterialFromString(buf, &imp);
+    BuildMaterial(imp, scene->materials[0]);
+    ImportMaterialFromString(glass, &imp);
+    BuildMaterial(imp, scene->materials[1]);
+    snprintf(buf, sizeof(buf), rough, "0.82,0.39,0.37");
+    ImportMaterialFromString(buf, &imp);
+    BuildMaterial(imp, scene->materials[2]);
+    scene->lights.clear();
+    scene->lightSets.clear();
+    memset(scene->backgroundIntensity, 0, sizeof(scene->backgroundIntensity));
+    // sun_sky_ibl: 0.2 sky with a 16x16-texel 5000-nit sun at theta = 40 degrees; a dimmer quarter-size miss image
+    ibl->width = 1024;
+    ibl->height = 512;
+    ibl->lightData.assign((size_t)3 * ibl->width * ibl->height, 0.2f);
+    const uint32_t y0 = (uint32_t)(40.0 / 180.0 * ibl->height) - 8, x0 = ibl->width / 3;
+    for (uint32_t y = y0; y < y0 + 16; ++y)
+        for (uint32_t x = x0; x < x0 + 16; ++x)
+            for (int c = 0; c < 3; ++c) ibl->lightData[3 * ((size_t)y * ibl->width + x) + c] = 5000.0f;
+    ibl->missWidth = ibl->width / 4;
+    ibl->missHeight = ibl->height / 4;
+    ibl->missData.assign((size_t)3 * ibl->missWidth * ibl->missHeight, 0.1f);
+    ibl->rotationRadians = 0.3f;
+    ibl->exposureScale = 1.0f;
+    ibl->BuildDensityFunctions();
+    scene->ibl = &ibl->desc;
+}
+
+void SetupCausticCamera(uint32_t width, uint32_t height, RayCastCameraSettings& camera) {
+    CameraSettings s;
+    s.position[0] = 0.0f; s.position[1] = 4.5f; s.position[2] = -9.0f;
+    s.lookAt[0] = 0.4f; s.lookAt[1] = 0.6f; s.lookAt[2] = 0.0f;
+    s.up[0] = 0.0f; s.up[1] = 1.0f; s.up[2] = 0.0f;
+    s.fovDegrees = 45.0f;
+    s.znear = 0.1f;
+    s.zfar = 10000.0f;
+    InitializeRayCastCamera(s, width, height, camera);
+}
+
+namespace VCM {
+Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, const char* imageName, const VCMSettings& settings,
+                    SelasVcmStats* stats, Framebuffer* keep) {
+    if (!scene->gpuScene) return Error_("VCM::GenerateImage: scene is not initialised on a GPU (there is no CPU fallback)");
+    if (settings.iterations == 0) return Error_("VCM::GenerateImage: iterations must be > 0");
+    const uint32_t width = (uint32_t)camera.width, height = (uint32_t)camera.height;
+    Framebuffer frame;
+    FrameBuffer_Initialize(&frame, width, height, 1);  // VCM.cpp:741
+    SelasVcmSettings vs;
+    memset(&vs, 0, sizeof(vs));
+    vs.width = width;
+    vs.height = height;
+    vs.iterations = settings.iterations;
+    vs.maxPathLength = settings.maxBounceCount;
+    vs.seed = settings.seed;
+    vs.radiusFactor = settings.vcmRadiusFactor;  // sharedData.vcmRadius = VcmRadiusFactor_ * scene->boundingSphere.w, VCM.cpp:778
+    vs.radiusAlpha = settings.vcmRadiusAlpha;
+    memcpy(vs.boundingSphere, scene->boundingSphere, sizeof(vs.boundingSphere));
+    if (selas_cuda_render_vcm(scene->gpuScene, &camera, &vs, &frame.buffers[0][0].x, stats) != SELAS_OK)
+        return Error_("%s", selas_cuda_last_error(scene->gpu));
+    FrameBuffer_Scale(&frame, 1.0f / (float)settings.iterations);  // FrameBuffer_Normalize(&frame, 1 / iterationsPerPixel), VCM.cpp:801
+    ReturnError_(FrameBuffer_Save(&frame, imageName));
+    if (keep) *keep = frame;
+    FrameBuffer_Shutdown(&frame);
+    return Success_;
+}
+}  // namespace VCM
 
 }  // namespace Selas
 

@@ -7,6 +7,8 @@
 //   Framebuffer, FrameBuffer_* / FramebufferWriter    Source/Core/TextureLib/Framebuffer.h:17-48, Framebuffer.cpp:18-138
 //   RayCastCameraSettings / InitializeRayCastCamera   Source/Core/GeometryLib/Camera.h:17-47, Camera.cpp:89-115
 //   PathTracer::GenerateImage                         Source/Applications/Selas/Source/PathTracer.h:20-21, PathTracer.cpp:301-350
+//   VCM::GenerateImage                                Source/Applications/Selas/Source/VCM.h:18, VCM.cpp:738-807
+//   BuildImageBasedLight density functions            Source/Core/BuildCommon/BuildImageBasedLight.cpp:24-105
 #pragma once
 #include <cstdint>
 #include <string>
@@ -94,6 +96,8 @@ struct SceneResource {
     std::vector<SelasLightSetRange> lightSets;
     float backgroundIntensity[4] = {0, 0, 0, 0};
     const SelasIblDesc* ibl = nullptr;  // SceneResource::iblResource (borrowed), or null: constant background
+    float aaBox[6] = {0, 0, 0, 0, 0, 0};          // SceneResource::aaBox (min xyz, max xyz), filled by InitializeSceneResource
+    float boundingSphere[4] = {0, 0, 0, 0};       // SceneResource::boundingSphere: centre of aaBox, half its diagonal
     // device side
     SelasContext* gpu = nullptr;
     SelasScene* gpuScene = nullptr;
@@ -102,6 +106,20 @@ Error InitializeSceneResource(SceneResource* scene, int device);  // context + u
 void ShutdownSceneResource(SceneResource* scene);
 void MakeCornellBoxScene(SceneResource* scene, float copperRoughness);  // BASELINE config 1
 void SetupCornellCamera(uint32_t width, uint32_t height, RayCastCameraSettings& camera);
+
+// ---- image based light ----------------------------------------------------------------------------------------------
+// Owns the arrays a SelasIblDesc points at.  BuildDensityFunctions is the bake step's CDF construction
+// (BuildImageBasedLight.cpp:24-105): intensity = sin(theta) * luma, per-row inclusive CDFs, marginal inclusive CDF of the row sums.
+struct ImageBasedLight {
+    uint32_t width = 0, height = 0, missWidth = 0, missHeight = 0;
+    std::vector<float> lightData, missData, marginal, conditional;
+    float rotationRadians = 0.f, exposureScale = 1.f;
+    SelasIblDesc desc;
+    void BuildDensityFunctions();
+};
+// BASELINE config 5: floor + glass sphere (Content/Materials/BSDF.json) + diffuse box under a sun-and-sky IBL.
+void MakeCausticScene(SceneResource* scene, ImageBasedLight* ibl, uint32_t sphereTheta = 96, uint32_t spherePhi = 192, uint32_t floorCells = 64);
+void SetupCausticCamera(uint32_t width, uint32_t height, RayCastCameraSettings& camera);
 
 // ---- integrator -----------------------------------------------------------------------------------------------------
 // The reference's compile-time macros (PathTracer.cpp:42-46, :248) as runtime settings; defaults = reference values.
@@ -117,6 +135,20 @@ namespace PathTracer {
 Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, const char* imageName,
                     const PathTracerSettings& settings = PathTracerSettings(), SelasRenderStats* stats = nullptr, Framebuffer* keep = nullptr);
 }  // namespace PathTracer
+
+// The reference's VCM macros (VCM.cpp:28-35) as runtime settings; IntegrationSeconds_ becomes an iteration count.
+struct VCMSettings {
+    uint32_t maxBounceCount = 10;    // MaxBounceCount_
+    uint32_t iterations = 16;
+    float vcmRadiusFactor = 0.0025f; // VcmRadiusFactor_
+    float vcmRadiusAlpha = 0.75f;    // VcmRadiusAlpha_
+    uint32_t seed = 0;
+};
+namespace VCM {
+// Renders `iterations` passes, normalises by 1/iterations (FrameBuffer_Normalize, VCM.cpp:801) and writes _Images/<imageName>_0.hdr.
+Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, const char* imageName, const VCMSettings& settings = VCMSettings(),
+                    SelasVcmStats* stats = nullptr, Framebuffer* keep = nullptr);
+}  // namespace VCM
 
 }  // namespace Selas
 

@@ -1,6 +1,7 @@
 // selas_render.cpp -- the reference's main() (Source/Applications/Selas/Source/main.cpp:82-135) for the synthetic Cornell
 // scene: initialise the scene on the GPU, set up the camera, PathTracer::GenerateImage, report the render time.
 //   selas_render [--width W] [--height H] [--spp N] [--depth D] [--layers L] [--roughness R] [--device I] [--name NAME]
+//   selas_render --integrator vcm [--width W] [--height H] [--iterations N] [--depth D] ...   (config 5 caustic scene, VCM::GenerateImage)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,9 +28,14 @@ int main(int argc, char** argv) {
     float roughness = 0.01f;
     int device = 0;
     const char* name = "cornell";
+    const char* integrator = "pathtracer";
+    VCMSettings vcm;
+    bool sizeGiven = false;
     for (int i = 1; i + 1 < argc; i += 2) {
-        if (!strcmp(argv[i], "--width")) width = (uint32_t)atoi(argv[i + 1]);
-        else if (!strcmp(argv[i], "--height")) height = (uint32_t)atoi(argv[i + 1]);
+        if (!strcmp(argv[i], "--width")) { width = (uint32_t)atoi(argv[i + 1]); sizeGiven = true; }
+        else if (!strcmp(argv[i], "--height")) { height = (uint32_t)atoi(argv[i + 1]); sizeGiven = true; }
+        else if (!strcmp(argv[i], "--integrator")) integrator = argv[i + 1];
+        else if (!strcmp(argv[i], "--iterations")) vcm.iterations = (uint32_t)atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--spp")) settings.pathsPerPixel = (uint32_t)atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--depth")) settings.maxBounceCount = (uint32_t)atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--layers")) settings.layerCount = (uint32_t)atoi(argv[i + 1]);
@@ -41,6 +47,33 @@ int main(int argc, char** argv) {
             fprintf(stderr, "unknown option %s\n", argv[i]);
             return 2;
         }
+    }
+    if (!strcmp(integrator, "vcm")) {
+        if (!sizeGiven) { width = 960; height = 540; }
+        if (!strcmp(name, "cornell")) name = "caustic";
+        if (settings.maxBounceCount != 8) vcm.maxBounceCount = settings.maxBounceCount;
+        vcm.seed = settings.seed;
+        auto t0 = std::chrono::steady_clock::now();
+        SceneResource scene;
+        ImageBasedLight ibl;
+        MakeCausticScene(&scene, &ibl);
+        ExitMainOnError_(InitializeSceneResource(&scene, device));
+        auto t1 = std::chrono::steady_clock::now();
+        printf("Scene load time %fms\n", std::chrono::duration<double, std::milli>(t1 - t0).count());
+        RayCastCameraSettings camera;
+        SetupCausticCamera(width, height, camera);
+        SelasVcmStats vst;
+        ExitMainOnError_(VCM::GenerateImage(&scene, camera, name, vcm, &vst));
+        auto t2 = std::chrono::steady_clock::now();
+        printf("Scene render time %fms\n", std::chrono::duration<double, std::milli>(t2 - t1).count());
+        printf("Vcm integration performed with %u iterations\n", vcm.iterations);  // VCM.cpp:799
+        printf("{\"iterations\": %u, \"light_vertices\": %llu, \"closest_rays\": %llu, \"occlusion_rays\": %llu, \"merges\": %llu, "
+               "\"connections\": %llu, \"kernel_launches\": %llu, \"device_ms\": %.3f, \"paths_per_s\": %.1f}\n",
+               vcm.iterations, (unsigned long long)vst.lightVertices, (unsigned long long)vst.closestRays, (unsigned long long)vst.occlusionRays,
+               (unsigned long long)vst.mergesAccepted, (unsigned long long)vst.connections, (unsigned long long)vst.kernelLaunches, vst.renderMs,
+               vst.renderMs > 0 ? (vst.lightPaths + vst.cameraPaths) / (vst.renderMs * 1e-3) : 0.0);
+        ShutdownSceneResource(&scene);
+        return 0;
     }
     auto t0 = std::chrono::steady_clock::now();
     SceneResource scene;

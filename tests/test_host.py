@@ -80,3 +80,28 @@ def test_selas_render_cornell(ctx, host, tmp_path):
         close = np.abs(got - want) <= m / 100.0 + 1e-4
         assert close.mean() > 0.995  # RGBE quantisation + atomic float accumulation order
     sc.close()
+
+
+@pytest.mark.gpu
+def test_selas_render_vcm(ctx, host, tmp_path):
+    """VCM::GenerateImage through the C++ host on its own C++ copy of the config 5 scene (MakeCausticScene, the IBL density
+    functions of ImageBasedLight::BuildDensityFunctions) against the Python-built scene rendered through the C ABI."""
+    exe = LIB / "selas_render"
+    w, h, its = 128, 72, 3
+    out = subprocess.run([str(exe), "--integrator", "vcm", "--width", str(w), "--height", str(h), "--iterations", str(its), "--seed", "4",
+                          "--name", "v"], cwd=tmp_path, capture_output=True, text=True, check=True).stdout
+    assert f"Vcm integration performed with {its} iterations" in out
+    stats = json.loads(out.strip().splitlines()[-1])
+    assert stats["iterations"] == its and stats["light_vertices"] > 0 and stats["merges"] > 0 and stats["connections"] > 0
+    got = read_hdr(tmp_path / "_Images" / "v_0.hdr")
+    data = scenes.caustic_scene()
+    sc = capi.Scene(ctx, data)
+    film, st = sc.render_vcm(scenes.caustic_camera(w, h), capi.vcm_settings(w, h, its, scenes.bounding_sphere(data), seed=4))
+    want = film / its
+    assert abs(int(st.lightVertices) - stats["light_vertices"]) <= 0.01 * st.lightVertices
+    # same streams, but the two scene builders round vertex positions and CDFs independently: compare as pictures
+    assert abs(got.mean() / want.mean() - 1.0) < 0.02
+    gb = got.reshape(h // 4, 4, w // 4, 4, 3).mean(axis=(1, 3))
+    wb = want.reshape(h // 4, 4, w // 4, 4, 3).mean(axis=(1, 3))
+    assert float(np.mean((gb - wb) ** 2 / (wb ** 2 + 1e-2))) < 0.02
+    sc.close()
