@@ -16,6 +16,12 @@ def shard_samples(total_spp: int, rank: int, world: int):
     return first, count
 
 
+def shard_iterations(total_iterations: int, rank: int, world: int):
+    """VCM shards whole iterations (each pass has its own light paths, hash grid and radius; SelasVcmSettings.firstIteration):
+    returns (first_iteration, count) with the same contiguous split as shard_samples."""
+    return shard_samples(total_iterations, rank, world)
+
+
 def reduce_film(film, dst: int = 0):
     """Sum the per-rank accumulation buffers onto rank `dst` (the path's only collective); no-op without a process group."""
     import torch.distributed as dist
