@@ -57,7 +57,7 @@ def workload_config(args, n_gpus, tris):
                     f"{tris} triangles, 1920x1080, depth 16, RR after 8, 4 quad lights, constant background",
         "triangles": int(tris), "width": WIDTH, "height": HEIGHT, "max_depth": MAX_DEPTH,
         "spp_per_step_per_gpu": args.spp_per_step, "paths_per_step": WIDTH * HEIGHT * args.spp_per_step * n_gpus,
-        "sharding": f"sample passes over {n_gpus} GPU(s), scene replicated, one NCCL reduce of the film",
+        "sharding": f"sample passes over {n_gpus} GPU(s), scene replicated, one ncclReduce of the film (selas_cuda_reduce_film)",
         "mis": "reference (weight 1.0, PathTracer.cpp:215)",
         "l2": "no explicit flush: BVH+triangles (~1 GB) and the wavefront queues (~1 GB) exceed the 126 MB L2",
     }
@@ -256,9 +256,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    reducer = None
+    if world > 1:
+        from selas_b200 import distributed
+        reducer = distributed.FilmReducer(ctx, rank, world)  # raw ncclComm_t for selas_cuda_reduce_film
+
     # ---- device-resident arm: value ---------------------------------------------------------------------------
     for i in range(args.warmup):
         scene.render_device(camera, settings(i), film.data_ptr(), stream.cuda_stream)
+    if reducer is not None:  # warm the communicator up (first collective sets up the NVLink channels)
+        reducer.reduce(film, dst=0, stream=stream.cuda_stream)
     film.zero_()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -276,8 +283,8 @@ def main():
         agg["occlusionRays"] += st.occlusionRays
         agg["launches"] += st.kernelLaunches
         agg["closestLaunches"] += st.closestLaunches
-    if world > 1:
-        dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)  # the path's only collective
+    if world > 1:  # the path's only collective: one ncclReduce of the film, through the C ABI
+        reducer.reduce(film, dst=0, stream=stream.cuda_stream)
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

@@ -384,6 +384,11 @@ int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera,
 int selas_cuda_render_pathtracer_device(SelasScene* scene, const SelasCamera* camera,
                                         const SelasRenderSettings* settings, float* d_film,
                                         SelasRenderStats* stats, void* stream);
+/* The path's only collective: ncclReduce(accum, accum, count, ncclFloat32, ncclSum, root, comm, stream) of the
+ * per-GPU accumulation buffers after the last pass.  `ncclComm` is the caller's ncclComm_t (one process per GPU); NCCL is bound
+ * at run time (dlopen of libnccl.so.2), so the library loads on hosts without it and this call then fails with
+ * SELAS_ERR_UNSUPPORTED.  Does not synchronise. */
+int selas_cuda_reduce_film(SelasContext* ctx, void* ncclComm, float* d_accum, size_t count, int root, void* stream);
 /* FrameBuffer_Scale Framebuffer.cpp:62-70 on a device film. */
 int selas_cuda_film_scale_device(SelasContext* ctx, float* d_film, size_t floatCount, float scale, void* stream);
 

@@ -57,8 +57,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    reducer = distributed.FilmReducer(ctx, rank, world) if world > 1 else None
     for i in range(args.warmup):
         scene.render_vcm_device(cam, settings(i), film.data_ptr(), stream.cuda_stream)
+    if reducer is not None:
+        reducer.reduce(film, dst=0, stream=stream.cuda_stream)
     film.zero_()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -73,7 +76,7 @@ def main():
         for k in agg:
             agg[k] += getattr(st, k)
     if world > 1:
-        dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+        reducer.reduce(film, dst=0, stream=stream.cuda_stream)
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

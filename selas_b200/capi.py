@@ -140,7 +140,7 @@ EXPORTS = [
     "selas_cuda_bsdf_sample", "selas_cuda_light_sample", "selas_cuda_light_pdf", "selas_cuda_surface_params",
     "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample",
     "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_film_scale_device",
-    "selas_cuda_render_vcm", "selas_cuda_render_vcm_device", "selas_cuda_vcm_light_pass", "selas_cuda_vcm_iteration_constants",
+    "selas_cuda_reduce_film", "selas_cuda_render_vcm", "selas_cuda_render_vcm_device", "selas_cuda_vcm_light_pass", "selas_cuda_vcm_iteration_constants",
     "selas_cuda_hashgrid_build", "selas_cuda_hashgrid_destroy", "selas_cuda_hashgrid_read",
     "selas_cuda_hashgrid_query", "selas_cuda_hashgrid_build_device", "selas_cuda_hashgrid_query_device",
     "selas_cuda_ptex_load", "selas_cuda_ptex_load_memory", "selas_cuda_ptex_destroy", "selas_cuda_ptex_eval",

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <new>
 
 #include "internal.h"
@@ -765,6 +766,52 @@ int selas_cuda_vcm_light_pass(SelasScene* scene, const SelasCamera* camera, cons
         return SELAS_ERR_ARGUMENT;
     }
     return vcmLightPassInspect(scene, *camera, *settings, vertices, maxVertices, pathEnds, vertexCount);
+}
+
+// ---- the film reduce over NCCL, bound at run time -----------------------------------------------------------------------
+namespace {
+typedef int (*NcclReduceFn)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+typedef const char* (*NcclErrorFn)(int);
+struct NcclApi {
+    void* handle = nullptr;
+    NcclReduceFn reduce = nullptr;
+    NcclErrorFn errorString = nullptr;
+    bool tried = false;
+};
+NcclApi& ncclApi() {
+    static NcclApi api;
+    if (!api.tried) {
+        api.tried = true;
+        // RTLD_NOLOAD first: reuse the NCCL the process already has (e.g. the one torch.distributed loaded)
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!api.handle) api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) {
+            api.reduce = (NcclReduceFn)dlsym(api.handle, "ncclReduce");
+            api.errorString = (NcclErrorFn)dlsym(api.handle, "ncclGetErrorString");
+        }
+    }
+    return api;
+}
+}  // namespace
+
+int selas_cuda_reduce_film(SelasContext* ctx, void* ncclComm, float* d_accum, size_t count, int root, void* stream) {
+    SELAS_TRY(bind(ctx));
+    if (!ncclComm || (!d_accum && count)) {
+        setError(ctx, "selas_cuda_reduce_film: null communicator or buffer");
+        return SELAS_ERR_ARGUMENT;
+    }
+    NcclApi& api = ncclApi();
+    if (!api.reduce) {
+        setError(ctx, "selas_cuda_reduce_film: libnccl.so.2 (ncclReduce) is not available on this host");
+        return SELAS_ERR_UNSUPPORTED;
+    }
+    const int ncclFloat32 = 7, ncclSum = 0;  // nccl.h: ncclDataType_t / ncclRedOp_t
+    int rc = api.reduce(d_accum, d_accum, count, ncclFloat32, ncclSum, root, ncclComm, stream ? (cudaStream_t)stream : ctx->stream);
+    if (rc != 0) {
+        setError(ctx, "ncclReduce failed: %s", api.errorString ? api.errorString(rc) : "unknown NCCL error");
+        return SELAS_ERR_CUDA;
+    }
+    return SELAS_OK;
 }
 
 int selas_cuda_film_scale_device(SelasContext* ctx, float* d_film, size_t floatCount, float scale, void* stream) {
