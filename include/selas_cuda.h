@@ -224,7 +224,13 @@ typedef struct SelasRenderSettings {
     uint32_t pixelSampler;    /* 0 = two uniforms from the path's stream (PathTracer, Camera.cpp:63-74); (m | n << 16) = correlated
                                  multi-jitter over an m x n grid with s = sample index, p = pixel index (the DeferredPathTracer's
                                  primary rays, DeferredPathTracer.cpp:349-380 / Camera.cpp:77-86) */
+    uint32_t integrator;      /* SELAS_INTEGRATOR_*: 0 = PathTracer::EvaluatePath (PathTracer.cpp:142-258); 1 = the DeferredPathTracer's
+                                 ShadeHitPosition (DeferredPathTracer.cpp:61-148): area-light NEE + sky/IBL NEE with balance-heuristic MIS,
+                                 BSDF sampling MIS-weighted against the sky pdf, Russian roulette (u >= p terminates) once 7 bounces are
+                                 tracked, no media, shadow rays from tnear 0, one layer; rrStartBounce / misMode are ignored and
+                                 maxPathLength is only a safety bound (the reference has none) */
 } SelasRenderSettings;
+enum { SELAS_INTEGRATOR_PATHTRACER = 0, SELAS_INTEGRATOR_DEFERRED = 1 };
 
 typedef struct SelasRenderStats {
     uint64_t closestRays;

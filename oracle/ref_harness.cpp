@@ -34,6 +34,7 @@
 #include "MathLib/Sampler.h"
 #include "MathLib/CorrelatedMultiJitter.h"
 #include "MathLib/FloatFuncs.h"
+#include "MathLib/ImportanceSampling.h"
 #include "IoLib/File.h"
 #include "Assets/AssetFileUtils.h"
 #include "VCMHashGrid.h"
@@ -605,6 +606,77 @@ int ref_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
                                   ? JitteredCameraRay(&rc, &ctx->sampler, (float)x, (float)y)
                                   : JitteredCameraRay(&rc, (int32)x, (int32)y, (int32)(rs->firstSample + k), (int32)(rs->pixelSampler & 0xffffu),
                                                       (int32)(rs->pixelSampler >> 16), (int32)p);
+                    if (rs->integrator == SELAS_INTEGRATOR_DEFERRED) {
+                        // ---- DeferredPathTracer.cpp:61-148, :151-290 walked path by path, with the reference's own NextEventEstimation,
+                        // SampleBackground, BackgroundLightingPdf, BalanceHeuristic, EvaluateBackground[Miss], EvaluateBsdf, SampleBsdfFunction
+                        float3 L = float3::Zero_;
+                        float3 throughput = float3::One_;
+                        bool diracScatterOnly = true;
+                        uint32_t trackedBounces = 0, bounce = 0;
+                        auto occludedFrom = [&](const SurfaceParameters& surface, float3 dir, float distance) {
+                            float3 org = OffsetRayOrigin(surface, dir, 0.1f);
+                            float so[3] = {org.x, org.y, org.z}, sd[3] = {dir.x, dir.y, dir.z};
+                            orc::RayHit shh;
+                            ++sh;
+                            return sc.bvh.trace<float>(so, sd, 0.0f, distance, true, shh);
+                        };
+                        while (bounce < ctx->maxPathLength) {
+                            orc::RayHit rh;
+                            float o[3] = {ray.origin.x, ray.origin.y, ray.origin.z}, d[3] = {ray.direction.x, ray.direction.y, ray.direction.z};
+                            bool hit = sc.bvh.trace<float>(o, d, 0.0f, FloatMax_, false, rh);
+                            ++c;
+                            if (!hit) {
+                                float3 smp = diracScatterOnly ? EvaluateBackgroundMiss(ctx, ray.direction) : EvaluateBackground(ctx, ray.direction);
+                                L += smp * throughput;
+                                break;
+                            }
+                            SurfaceParameters surface;
+                            const orc::Tri& T = sc.bvh.tris[rh.tri];
+                            float hu = T.second ? (float)(1.0 - rh.u) : (float)rh.u, hv = T.second ? (float)(1.0 - rh.v) : (float)rh.v;
+                            refSurface(sc, ray, (float)rh.t, hu, hv, T.geomID, T.primID, surface);
+                            float3 view = -ray.direction;
+                            LightDirectSample lightSample;
+                            memset(&lightSample, 0, sizeof(lightSample));
+                            NextEventEstimation(ctx, surface.lightSetIndex, surface.position, GeometricNormal(surface), lightSample);
+                            if (Dot(lightSample.radiance, float3::One_) > 0) {
+                                float fw = 0, rv = 0;
+                                float3 reflectance = EvaluateBsdf(surface, view, lightSample.direction, fw, rv);
+                                float weight = 1.0f;
+                                float3 smp = weight * reflectance * lightSample.radiance * (1.0f / lightSample.pdfW);
+                                if (Dot(smp, float3::One_) > 0 && !occludedFrom(surface, lightSample.direction, lightSample.distance)) L += smp * throughput;
+                            }
+                            LightDirectSample skySample;
+                            memset(&skySample, 0, sizeof(skySample));
+                            SampleBackground(ctx, skySample);
+                            if (Dot(skySample.radiance, float3::One_) > 0) {
+                                float fw = 0, rv = 0;
+                                float3 reflectance = EvaluateBsdf(surface, view, skySample.direction, fw, rv);
+                                float misWeight = ImportanceSampling::BalanceHeuristic(1, skySample.pdfW, 1, fw);
+                                float3 smp = misWeight * reflectance * skySample.radiance * (1.0f / skySample.pdfW);
+                                if (Dot(smp, float3::One_) > 0 && !occludedFrom(surface, skySample.direction, skySample.distance)) L += smp * throughput;
+                            }
+                            BsdfSample bsdfSample;
+                            bsdfSample.flags = eScatterEvent;
+                            if (SampleBsdfFunction(&ctx->sampler, surface, view, bsdfSample) == false) break;
+                            float skyPdfW = BackgroundLightingPdf(ctx, bsdfSample.wi);
+                            float misWeight = ImportanceSampling::BalanceHeuristic(1, bsdfSample.forwardPdfW, 1, skyPdfW);
+                            throughput = misWeight * throughput * bsdfSample.reflectance;
+                            if (LengthSquared(throughput) == 0.0f) break;
+                            if (trackedBounces >= MaxTrackedBounces_) {
+                                float continuationProb = Max<float>(Max<float>(throughput.x, throughput.y), throughput.z);
+                                if (ctx->sampler.UniformFloat() >= continuationProb) break;
+                                throughput = throughput * (1.0f / continuationProb);
+                            }
+                            float3 offsetOrigin = OffsetRayOrigin(surface, bsdfSample.wi, 1.0f);
+                            ray = MakeRay(offsetOrigin, bsdfSample.wi);
+                            diracScatterOnly = diracScatterOnly && (bsdfSample.flags & SurfaceEventFlags::eDiracEvent);
+                            trackedBounces = Min<uint32>(MaxTrackedBounces_, trackedBounces + 1);
+                            ++bounce;
+                        }
+                        float* out = film[rs->layerCount == 2 ? 1 : 0];
+                        out[3 * p] += L.x; out[3 * p + 1] += L.y; out[3 * p + 2] += L.z;
+                        continue;
+                    }
                     // ---- EvaluatePath, PathTracer.cpp:142-258 ----
                     float3 Ld[2] = {float3::Zero_, float3::Zero_};
                     float3 throughput = float3::One_;

@@ -364,6 +364,123 @@ static void evaluatePath(const Scene& sc, const SelasCamera& cam, const SelasRen
     }
 }
 
+// DeferredPathTracer: GeneratePrimaryRays + TraceRayBatch + ShadeHitPosition + TraceOcclusionBatch
+// (Applications/Selas/Source/DeferredPathTracer.cpp:61-148, :151-229, :232-290, :349-380) for one path.  The reference queues rays
+// and hits in batches (PathTracingBatcher); paths are independent, so walking one path to its end is the same computation.
+static void evaluatePathDeferred(const Scene& sc, const SelasCamera& cam, const SelasRenderSettings& rs, uint32_t px, uint32_t py,
+                                 uint32_t sample, V3& Ld, uint64_t& closest, uint64_t& shadow) {
+    PathRng rng;
+    rng.init(rs.seed, py * rs.width + px, sample);
+    float vx, vy;
+    if (rs.pixelSampler == 0) {
+        vx = (float)px + rng.next();
+        vy = (float)py + rng.next();
+    } else {  // JitteredCameraRay(camera, x, y, scan, SamplesPerPixelX_, SamplesPerPixelY_, index), :365-366
+        float j[2];
+        cmj((int32_t)sample, (int32_t)(rs.pixelSampler & 0xffffu), (int32_t)(rs.pixelSampler >> 16), (int32_t)(py * rs.width + px), j);
+        vx = (float)px + j[0];
+        vy = (float)py + j[1];
+    }
+    SelasRay ray;
+    V3 dir = imageToWorldDirection(cam, vx, vy);
+    ray.ox = cam.position[0]; ray.oy = cam.position[1]; ray.oz = cam.position[2];
+    ray.dx = dir.x; ray.dy = dir.y; ray.dz = dir.z;
+    Ld = v3(0.0f);
+    V3 throughput = v3(1.0f);
+    bool diracScatterOnly = true;
+    uint32_t trackedBounces = 0, bounce = 0;
+    const uint32_t kMaxTracked = 7;  // MaxTrackedBounces_, IntegratorContexts.h:43
+    auto occluded = [&](const SelasSurface& surf, V3 d, float distance) {
+        V3 org = offsetRayOrigin(surf, d, 0.1f);
+        float so[3] = {org.x, org.y, org.z}, sd[3] = {d.x, d.y, d.z};
+        RayHit sh;
+        ++shadow;
+        return sc.bvh.trace<float>(so, sd, 0.0f, distance, true, sh);  // ray.tnear = 0, :262
+    };
+    while (bounce < rs.maxPathLength) {
+        ray.tnear = 0.0f;
+        ray.tfar = kFloatMax;
+        RayHit rh;
+        float o[3] = {ray.ox, ray.oy, ray.oz}, d[3] = {ray.dx, ray.dy, ray.dz};
+        bool hit = sc.bvh.trace<float>(o, d, 0.0f, kFloatMax, false, rh);
+        ++closest;
+        if (!hit) {  // :198-207
+            V3 smp = v3(sc.background);
+            if (sc.hasIbl) {
+                float pdf;
+                V3 dirv = v3(ray.dx, ray.dy, ray.dz);
+                smp = diracScatterOnly ? iblLookupMiss(sc.ibl, dirv, pdf) : iblLookup(sc.ibl, dirv, pdf);
+            }
+            Ld = Ld + smp * throughput;
+            break;
+        }
+        SelasHit h;
+        hitToRecord(sc, rh, ray, h, nullptr);
+        SelasSurface surf;
+        surfaceParams(sc, ray, h, surf);
+        V3 view = v3(-ray.dx, -ray.dy, -ray.dz);
+        // ---- area lights, :68-89 (weight 1) ----
+        SelasLightSample ls;
+        memset(&ls, 0, sizeof(ls));
+        uint32_t lightCount = 0;
+        const SelasLight* lights = nullptr;
+        if (surf.lightSetIndex < sc.lightSets.size()) {
+            lightCount = sc.lightSets[surf.lightSetIndex].count;
+            lights = sc.lights.data() + sc.lightSets[surf.lightSetIndex].start;
+        }
+        if (lightCount > 0)
+            withStream(rng, [&](Stream& st) { nextEventEstimation(st, lights, lightCount, v3(surf.position), geometricNormal(surf), ls); });
+        if (dot(v3(ls.radiance), v3(1.0f)) > 0) {
+            float f = 0, r = 0;
+            V3 refl = evaluateBsdf(surf, view, v3(ls.direction), f, r);
+            float weight = 1.0f;
+            V3 smp = weight * refl * v3(ls.radiance) * (1.0f / ls.pdfW);
+            if (dot(smp, v3(1.0f)) > 0 && !occluded(surf, v3(ls.direction), ls.distance)) Ld = Ld + smp * throughput;
+        }
+        // ---- sky, :91-111: SampleBackground (AreaLighting.cpp:392-400) + balance heuristic ----
+        SelasLightSample sky;
+        memset(&sky, 0, sizeof(sky));
+        withStream(rng, [&](Stream& st) {
+            if (sc.hasIbl) {
+                directIblLightSample(st, sc.ibl, sky);
+            } else {  // BackgroundLightSample, AreaLighting.cpp:334-350
+                V3 dd = uniformSphere(st);
+                sky.distance = 1e36f;
+                store(sky.direction, dd);
+                store(sky.radiance, v3(sc.background));
+                sky.pdfW = 1.0f;
+            }
+        });
+        if (dot(v3(sky.radiance), v3(1.0f)) > 0) {
+            float f = 0, r = 0;
+            V3 refl = evaluateBsdf(surf, view, v3(sky.direction), f, r);
+            float misWeight = (1 * sky.pdfW) / (1 * sky.pdfW + 1 * f);  // BalanceHeuristic, ImportanceSampling.cpp:19-22
+            V3 smp = misWeight * refl * v3(sky.radiance) * (1.0f / sky.pdfW);
+            if (dot(smp, v3(1.0f)) > 0 && !occluded(surf, v3(sky.direction), sky.distance)) Ld = Ld + smp * throughput;
+        }
+        // ---- BSDF sample, :113-146 ----
+        SelasBsdfSample bs;
+        bool ok;
+        withStream(rng, [&](Stream& st) { ok = sampleBsdf(st, surf, view, bs); });
+        if (!ok) break;
+        float skyPdfW = sc.hasIbl ? iblPdf(sc.ibl, v3(bs.wi)) : kInv4Pi;  // BackgroundLightingPdf, AreaLighting.cpp:403-411
+        float misWeight = (1 * bs.forwardPdfW) / (1 * bs.forwardPdfW + 1 * skyPdfW);
+        throughput = misWeight * throughput * v3(bs.reflectance);
+        if (dot(throughput, throughput) == 0.0f) break;
+        if (trackedBounces >= kMaxTracked) {
+            float p = maxf(maxf(throughput.x, throughput.y), throughput.z);
+            if (rng.next() >= p) break;
+            throughput = throughput * (1.0f / p);
+        }
+        V3 org = offsetRayOrigin(surf, v3(bs.wi), 1.0f);
+        ray.ox = org.x; ray.oy = org.y; ray.oz = org.z;
+        ray.dx = bs.wi[0]; ray.dy = bs.wi[1]; ray.dz = bs.wi[2];
+        diracScatterOnly = diracScatterOnly && (bs.flags & SELAS_EVENT_DIRAC);
+        trackedBounces = trackedBounces + 1 < kMaxTracked ? trackedBounces + 1 : kMaxTracked;
+        ++bounce;
+    }
+}
+
 extern "C" {
 
 int orc_scene_create(const SelasSceneDesc* d, void** out) {
@@ -641,6 +758,10 @@ int orc_render_pathtracer(void* s, const SelasCamera* cam, const SelasRenderSett
             uint32_t py = (uint32_t)(p / rs->width), px = (uint32_t)(p - (size_t)py * rs->width);
             for (uint32_t k = 0; k < rs->samplesPerPixel; ++k) {
                 V3 Ld[2];
+                if (rs->integrator == SELAS_INTEGRATOR_DEFERRED) {
+                    Ld[0] = v3(0.0f);
+                    evaluatePathDeferred(sc, *cam, *rs, px, py, rs->firstSample + k, Ld[1], c, sh);
+                } else
                 evaluatePath(sc, *cam, *rs, px, py, rs->firstSample + k, Ld, c, sh);
                 if (rs->layerCount == 1) {
                     film[0][3 * p] += Ld[1].x; film[0][3 * p + 1] += Ld[1].y; film[0][3 * p + 2] += Ld[1].z;

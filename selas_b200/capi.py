@@ -77,7 +77,7 @@ class SceneDesc(C.Structure):
 class RenderSettings(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("samplesPerPixel", u32), ("maxPathLength", u32),
                 ("rrStartBounce", u32), ("layerCount", u32), ("seed", u32), ("firstSample", u32), ("misMode", u32),
-                ("flags", u32), ("pixelStride", u32), ("pixelSampler", u32)]
+                ("flags", u32), ("pixelStride", u32), ("pixelSampler", u32), ("integrator", u32)]
 
 
 class RenderStats(C.Structure):
@@ -507,9 +507,13 @@ RENDER_COUNT_TRAVERSAL = 1
 RENDER_SKIP_NONFINITE = 2
 
 
+INTEGRATOR_PATHTRACER, INTEGRATOR_DEFERRED = 0, 1
+
+
 def render_settings(width, height, spp, max_path_length=8, rr_start=8, layers=1, seed=1, first_sample=0, mis_mode=0,
-                    flags=0, pixel_stride=0, cmj=None):
+                    flags=0, pixel_stride=0, cmj=None, integrator=0):
     rs = RenderSettings()
+    rs.integrator = integrator
     rs.flags, rs.pixelStride = flags, pixel_stride
     rs.pixelSampler = 0 if cmj is None else (cmj[0] | (cmj[1] << 16))
     rs.width, rs.height, rs.samplesPerPixel = width, height, spp

@@ -292,6 +292,7 @@ struct WavefrontBuffers {
     uint32_t* bins = nullptr;      // per iteration: 64 counts + 64 cursors
     uint32_t* counters = nullptr;  // 4 per iteration: nextPaths, shadowRays, closestFetch, shadowFetch
     uint32_t counterSlots = 0;
+    uint32_t shadowPerPath = 1;    // shadow-ray slots per queued path (2 for the deferred integrator: area light + sky)
     uint32_t* h_counts = nullptr;  // pinned readback
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     KernelTimers timers;  // event pool reused across calls
@@ -320,16 +321,17 @@ void freeWavefront(SelasScene* scene) {
     scene->wf = nullptr;
 }
 
-static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterations) {
+static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterations, uint32_t shadowPerPath) {
     SelasContext* ctx = scene->ctx;
     WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
     uint32_t slots = (iterations + 2) * 4;
-    if (w && w->capacity >= capacity && w->counterSlots >= slots) return SELAS_OK;
+    if (w && w->capacity >= capacity && w->counterSlots >= slots && w->shadowPerPath >= shadowPerPath) return SELAS_OK;
     if (w) freeWavefront(scene);
     w = new WavefrontBuffers();
     scene->wf = w;
     w->capacity = capacity;
     w->counterSlots = slots;
+    w->shadowPerPath = shadowPerPath;
     for (int k = 0; k < 2; ++k) {
         SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->rays[k], sizeof(SelasRay) * (size_t)capacity));
         SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->thrPix[k], sizeof(float4) * (size_t)capacity));
@@ -337,8 +339,8 @@ static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterat
         SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->medium[k], sizeof(float4) * (size_t)capacity));
     }
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->hits, sizeof(SelasHit) * (size_t)capacity));
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowRays, sizeof(SelasRay) * (size_t)capacity));
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity));
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowRays, sizeof(SelasRay) * (size_t)capacity * shadowPerPath));
+    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity * shadowPerPath));
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->counters, sizeof(uint32_t) * slots));
     SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->order, sizeof(uint32_t) * (size_t)capacity));
     if (scene->usesPtex) SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->ptexRgb, sizeof(float) * 3 * (size_t)capacity));
@@ -448,6 +450,10 @@ struct ShadeParams {
     uint32_t maxPathLength, rrStartBounce, layerCount, pixels, misMode, skipNonFinite;
 };
 
+// INTEGRATOR 0: PathTracer::EvaluatePath (PathTracer.cpp:142-258).  INTEGRATOR 1: the DeferredPathTracer's ShadeHitPosition
+// (DeferredPathTracer.cpp:61-148) -- a second NEE sample towards the sky / IBL with balance-heuristic MIS, the BSDF sample weighted
+// against the sky pdf, Russian roulette (u >= p) once MaxTrackedBounces_ = 7 bounces are tracked, no media, shadow rays from tnear 0.
+template <int INTEGRATOR>
 __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ order, uint32_t nMax,
                                                    const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                                    const float4* __restrict__ thrPix, const uint2* __restrict__ rngFlags,
@@ -462,13 +468,13 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
     const uint32_t i = (order && slotIndex < n) ? __ldg(order + slotIndex) : slotIndex;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ltMask = (1u << lane) - 1u;
-    bool alive = false, wantShadow = false;
+    bool alive = false, wantShadow = false, wantShadow2 = false;
     SelasRay outRay;
     float4 outThrPix = make_float4(0.f, 0.f, 0.f, 0.f);
     uint2 outRngFlags = make_uint2(0u, 0u);
     float4 outMedium = make_float4(0.f, 0.f, 0.f, 0.f);
-    SelasRay shRay;
-    float4 shPayload = make_float4(0.f, 0.f, 0.f, 0.f);
+    SelasRay shRay, shRay2;
+    float4 shPayload = make_float4(0.f, 0.f, 0.f, 0.f), shPayload2 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     if (slotIndex < n) {
         const float4* rp = reinterpret_cast<const float4*>(rays + i);
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
         uint32_t bounce = rf.y & 0xffffu;
         bool deltaOnly = (rf.y & FLAG_DELTA_ONLY) != 0;
         Medium medium{SELAS_MEDIUM_VACUUM, v3(0.0f)};
-        if (rf.y & FLAG_IN_MEDIUM) {
+        if (INTEGRATOR == 0 && (rf.y & FLAG_IN_MEDIUM)) {
             float4 m = __ldg(mediumIn + i);
             medium.phase = SELAS_MEDIUM_ISOTROPIC;
             medium.extinction = v3(m.x, m.y, m.z);
@@ -522,20 +528,72 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
             if (dot(ls.radiance, v3(1.0f)) > 0) {
                 float fp, rpdf;
                 V3 refl = evaluateBsdf(s, frame, view, ls.direction, fp, rpdf);
-                if (dot(refl, v3(1.0f)) > 0) {
+                // PathTracer.cpp:184 tests the reflectance, DeferredPathTracer.cpp:78 the finished sample (weight 1 in both)
+                V3 smp = INTEGRATOR == 1 ? 1.0f * refl * ls.radiance * (1.0f / ls.pdfW) : refl * ls.radiance * (1.0f / ls.pdfW);
+                if (dot(INTEGRATOR == 1 ? smp : refl, v3(1.0f)) > 0) {
                     // OcclusionRay, :71-92: origin offset 0.1*error along +-N, tnear = error, tfar = light distance
+                    // (the deferred tracer's occlusion batch starts at tnear = 0, DeferredPathTracer.cpp:262)
                     V3 so = offsetRayOrigin(s, ls.direction, 0.1f);
-                    V3 smp = refl * ls.radiance * (1.0f / ls.pdfW);
                     V3 c = smp * thr;
-                    shRay.ox = so.x; shRay.oy = so.y; shRay.oz = so.z; shRay.tnear = s.error;
+                    shRay.ox = so.x; shRay.oy = so.y; shRay.oz = so.z; shRay.tnear = INTEGRATOR == 1 ? 0.0f : s.error;
                     shRay.dx = ls.direction.x; shRay.dy = ls.direction.y; shRay.dz = ls.direction.z; shRay.tfar = ls.distance;
                     shPayload = make_float4(c.x, c.y, c.z, __uint_as_float(pixel));
                     wantShadow = !(prm.skipNonFinite && !(isfinite(c.x) && isfinite(c.y) && isfinite(c.z)));
                 }
             }
+            if (INTEGRATOR == 1) {
+                // ---- sky sample, DeferredPathTracer.cpp:91-111: SampleBackground (AreaLighting.cpp:392-400) + balance heuristic ----
+                V3 skyDir, skyRadiance;
+                float skyPdf;
+                if (sc.ibl.present) {  // DirectIblLightSample, AreaLighting.cpp:293-314
+                    float r0 = rng.next(), r1 = rng.next();
+                    uint32_t x, y;
+                    float dirPhi, dirTheta;
+                    iblSample(sc.ibl, r0, r1, dirTheta, dirPhi, x, y, skyPdf);
+                    float st = sinf(dirTheta), ct = cosf(dirTheta), sp = sinf(dirPhi), cp = cosf(dirPhi);
+                    skyDir = v3(st * cp, ct, st * sp);  // Math::SphericalToCartesian, Projection.cpp:132-146
+                    const float* t = sc.ibl.light + 3 * ((size_t)y * sc.ibl.width + x);
+                    skyRadiance = sc.ibl.exposureScale * v3(__ldg(t), __ldg(t + 1), __ldg(t + 2));
+                } else {  // BackgroundLightSample, AreaLighting.cpp:334-350; QUIRK: pdfW = 1, not 1/(4 pi)
+                    skyDir = uniformSphere(rng);
+                    skyRadiance = v3(sc.background[0], sc.background[1], sc.background[2]);
+                    skyPdf = 1.0f;
+                }
+                if (dot(skyRadiance, v3(1.0f)) > 0) {
+                    float fp = 0.f, rpdf = 0.f;
+                    V3 refl = evaluateBsdf(s, frame, view, skyDir, fp, rpdf);
+                    float misWeight = (1 * skyPdf) / (1 * skyPdf + 1 * fp);  // BalanceHeuristic, ImportanceSampling.cpp:19-22
+                    V3 smp = misWeight * refl * skyRadiance * (1.0f / skyPdf);
+                    if (dot(smp, v3(1.0f)) > 0) {
+                        V3 so = offsetRayOrigin(s, skyDir, 0.1f);
+                        V3 c = smp * thr;
+                        shRay2.ox = so.x; shRay2.oy = so.y; shRay2.oz = so.z; shRay2.tnear = 0.0f;
+                        shRay2.dx = skyDir.x; shRay2.dy = skyDir.y; shRay2.dz = skyDir.z; shRay2.tfar = 1e36f;
+                        shPayload2 = make_float4(c.x, c.y, c.z, __uint_as_float(pixel));
+                        wantShadow2 = !(prm.skipNonFinite && !(isfinite(c.x) && isfinite(c.y) && isfinite(c.z)));
+                    }
+                }
+            }
             // ---- BSDF sampling, :197-226 ----
             BsdfResult bs;
-            if (sampleBsdf(rng, s, frame, view, bs)) {
+            if (INTEGRATOR == 1) {  // DeferredPathTracer.cpp:113-146
+                if (sampleBsdf(rng, s, frame, view, bs)) {
+                    float skyPdfW = sc.ibl.present ? iblPdf(sc.ibl, bs.wi) : SELAS_INV_4PI;  // BackgroundLightingPdf, AreaLighting.cpp:403-411
+                    float misWeight = (1 * bs.forwardPdfW) / (1 * bs.forwardPdfW + 1 * skyPdfW);
+                    thr = misWeight * thr * bs.reflectance;
+                    if (dot(thr, thr) != 0.0f) {
+                        alive = true;
+                        if (bounce >= 7u) {  // hit.trackedBounces >= MaxTrackedBounces_ (IntegratorContexts.h:43); tracked = min(7, bounces)
+                            float p = maxf_(maxf_(thr.x, thr.y), thr.z);
+                            if (rng.next() >= p) alive = false;
+                            thr = thr * (1.0f / p);
+                        }
+                        deltaOnly = deltaOnly && (bs.flags & SELAS_EVENT_DIRAC);
+                        o = offsetRayOrigin(s, bs.wi, 1.0f);
+                        d = bs.wi;
+                    }
+                }
+            } else if (sampleBsdf(rng, s, frame, view, bs)) {
                 deltaOnly = deltaOnly && (bs.flags & SELAS_EVENT_DIRAC);
                 if (bs.flags == SELAS_EVENT_TRANSMISSION) {  // exact equality, :206
                     if (medium.phase == SELAS_MEDIUM_VACUUM) {
@@ -580,7 +638,7 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
 
         if (alive) {
             ++bounce;
-            if (bounce > prm.rrStartBounce) {  // Russian roulette, :248-254; QUIRK: p is not clamped to 1
+            if (INTEGRATOR == 0 && bounce > prm.rrStartBounce) {  // Russian roulette, :248-254; QUIRK: p is not clamped to 1
                 float p = maxf_(maxf_(thr.x, thr.y), thr.z);
                 if (rng.next() > p) alive = false;
                 thr = thr * (1.0f / p);
@@ -624,6 +682,19 @@ __global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm,
         so[1] = make_float4(shRay.dx, shRay.dy, shRay.dz, shRay.tfar);
         shadowPayload[slot] = shPayload;
     }
+    if (INTEGRATOR == 1) {  // the sky shadow ray
+        uint32_t mask2 = __ballot_sync(0xffffffffu, wantShadow2);
+        uint32_t base2 = 0;
+        if (lane == 0 && mask2) base2 = atomicAdd(counters + 1, (uint32_t)__popc(mask2));
+        base2 = __shfl_sync(0xffffffffu, base2, 0);
+        if (wantShadow2) {
+            uint32_t slot = base2 + __popc(mask2 & ltMask);
+            float4* so = reinterpret_cast<float4*>(shadowRays + slot);
+            so[0] = make_float4(shRay2.ox, shRay2.oy, shRay2.oz, shRay2.tnear);
+            so[1] = make_float4(shRay2.dx, shRay2.dy, shRay2.dz, shRay2.tfar);
+            shadowPayload[slot] = shPayload2;
+        }
+    }
 }
 
 int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
@@ -640,6 +711,10 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             setError(ctx, "pixelSampler: correlated multi-jitter needs an m x n grid (m, n > 0) holding firstSample + samplesPerPixel samples");
             return SELAS_ERR_ARGUMENT;
         }
+    }
+    if (rs.integrator > SELAS_INTEGRATOR_DEFERRED || (rs.integrator == SELAS_INTEGRATOR_DEFERRED && rs.layerCount != 1)) {
+        setError(ctx, "integrator %u unknown, or the deferred integrator asked for %u layers (it has one, OutputLayers_)", rs.integrator, rs.layerCount);
+        return SELAS_ERR_ARGUMENT;
     }
     if (rs.misMode > 1) {
         setError(ctx, "misMode %u unknown (0 = reference weighting, 1 = balance heuristic)", rs.misMode);
@@ -658,7 +733,8 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         if (stats) *stats = st;
         return SELAS_OK;
     }
-    int rc = ensureWavefront(scene, capacity, rs.maxPathLength);
+    const bool deferred = rs.integrator == SELAS_INTEGRATOR_DEFERRED;
+    int rc = ensureWavefront(scene, capacity, rs.maxPathLength, deferred ? 2u : 1u);
     if (rc) return rc;
     WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
     ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels, rs.misMode, (rs.flags & SELAS_RENDER_SKIP_NONFINITE) ? 1u : 0u};
@@ -708,10 +784,16 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 ptexStageKernel<<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
                 ++st.kernelLaunches;
             }
-            shadeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
-                                                            w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
-                                                            w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film,
-                                                            scene->usesPtex ? w->ptexRgb : nullptr);
+            if (deferred)
+                shadeKernel<1><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
+                                                                   w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
+                                                                   w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film,
+                                                                   scene->usesPtex ? w->ptexRgb : nullptr);
+            else
+                shadeKernel<0><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
+                                                                   w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
+                                                                   w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film,
+                                                                   scene->usesPtex ? w->ptexRgb : nullptr);
             timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));

@@ -315,6 +315,38 @@ def test_render_mis_balance_mode(ctx, oracle):
     sc.close()
 
 
+@pytest.mark.parametrize("with_ibl", [False, True])
+def test_render_deferred_integrator(ctx, oracle, with_ibl):
+    """SelasRenderSettings.integrator = 1: the DeferredPathTracer's ShadeHitPosition (area NEE + sky NEE with balance-heuristic MIS,
+    BSDF sample weighted against the sky pdf, RR after 7 tracked bounces, CMJ 4x4 primary rays) against the oracle on the same streams."""
+    data = inputs.small_scene()
+    if with_ibl:
+        rng = np.random.default_rng(31)
+        img = (rng.uniform(0, 1, size=(32, 64, 3)) ** 6 * 40.0).astype(np.float32)
+        img[5:8, 10:14] = 900.0
+        data.ibl = scenes.build_ibl(img, miss=rng.uniform(0, 2, size=(8, 16, 3)).astype(np.float32), rotation=0.7, exposure=1.0)
+    cam = capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 96, 64)
+    rs = capi.render_settings(96, 64, 16, max_path_length=48, layers=1, seed=9, cmj=(4, 4), integrator=capi.INTEGRATOR_DEFERRED)
+    sc, hs = capi.Scene(ctx, data), oracle.scene_create(data)
+    gf, gs = sc.render(cam, rs)
+    of, os_ = oracle.render(hs, cam, rs, nthreads=8)
+    assert gs.pathSamples == 96 * 64 * 16
+    assert abs(int(gs.closestRays) - int(os_.closestRays)) <= 0.003 * os_.closestRays
+    assert abs(int(gs.occlusionRays) - int(os_.occlusionRays)) <= 0.003 * os_.occlusionRays
+    a, b = gf[0] / 16.0, of[0] / 16.0
+    fin = np.isfinite(b).all(axis=2) & np.isfinite(a).all(axis=2)
+    assert fin.mean() > 0.995
+    assert abs(a[fin].mean() / b[fin].mean() - 1.0) < 3e-3, (a[fin].mean(), b[fin].mean())
+    assert _relmse(a[fin], b[fin]) < 3e-3
+    assert np.isclose(a[fin], b[fin], rtol=1e-3, atol=1e-4).all(axis=1).mean() > 0.97
+    with pytest.raises(capi.SelasError):  # one output layer (OutputLayers_)
+        sc.render(cam, capi.render_settings(8, 8, 1, layers=2, integrator=capi.INTEGRATOR_DEFERRED))
+    with pytest.raises(capi.SelasError):
+        sc.render(cam, capi.render_settings(8, 8, 1, integrator=5))
+    oracle.scene_destroy(hs)
+    sc.close()
+
+
 def test_render_cornell_config1_reduced(ctx, oracle):
     """Config 1 (Cornell, Disney diffuse + copper) at 128x128, 16 spp, depth 8 against the oracle, plus the noise-floor
     criterion of SURVEY.md 8(d): relMSE(gpu, ref-hi) <= 1.5 x relMSE(oracle, ref-hi) with an independent seed."""
