@@ -154,6 +154,16 @@ typedef struct SelasHit {
     uint32_t pad;
 } SelasHit;
 
+/* TextureResourceData (TextureLib/TextureResource.h:15-39), level 0 only: the path samples mip 0 with the bilinear "Triangle" filter
+ * (ForceNoMips_, SurfaceParameters.cpp:21; TextureFiltering::Triangle(data, 0, uvs, ...), TextureFiltering.h:77-104, Repeat wrap). */
+enum { SELAS_TEXTURE_FLOAT = 0, SELAS_TEXTURE_FLOAT2 = 1, SELAS_TEXTURE_FLOAT3 = 2, SELAS_TEXTURE_FLOAT4 = 3 }; /* TextureDataType */
+typedef struct SelasTextureDesc {
+    uint32_t     width, height;   /* mipWidths[0], mipHeights[0] */
+    uint32_t     format;          /* SELAS_TEXTURE_*: floats per texel = format + 1 */
+    uint32_t     reserved;
+    const float* texels;          /* row-major, texel (s, t) at [t * width + s] */
+} SelasTextureDesc;
+
 /* One triangle/quad mesh = one Embree geometry (ModelResource.cpp:164-200, :236-297). */
 typedef struct SelasMeshDesc {
     const float*    positions;      /* float3, stride 12 */
@@ -167,6 +177,9 @@ typedef struct SelasMeshDesc {
     uint32_t        materialIndex;
     uint32_t        lightSetIndex;
     void*           ptex;           /* SelasPtex* for SELAS_MAT_USES_PTEX materials, else NULL */
+    const SelasTextureDesc* baseColorTexture; /* ModelGeometryUserData::baseColorTextureHandle for non-Ptex materials, or NULL: the
+                                                 material's constant baseColor (SurfaceParameters.cpp:209-214); sampled at the
+                                                 interpolated uvs (0,0 without a uv buffer), sRGB -> linear, then pow 2.2 */
 } SelasMeshDesc;
 
 /* Instance of a mesh; localToWorld is a row-major row-vector 4x4 (translation in row 3). */
@@ -375,6 +388,10 @@ int selas_cuda_light_pdf(SelasContext* ctx, size_t n, const SelasLight* lights, 
  * sample: Ibl(ibl, r0, r1, theta, phi, x, y, pdf): u2 = 2 uniforms per sample; thetaPhiPdf3 = 3 floats, xy2 = 2 uint32 per sample */
 int selas_cuda_ibl_lookup(SelasScene* scene, size_t n, const float* wi3, float* rgb3, float* pdf, float* missRgb3);
 int selas_cuda_ibl_sample(SelasScene* scene, size_t n, const float* u2, float* thetaPhiPdf3, uint32_t* xy2);
+
+/* ---- textures: SampleTextureFloat3(texture, uvs, sRGB, default) (SurfaceParameters.cpp:97-118) over a batch of uvs ------------------
+ * = TextureFiltering::Triangle at level 0 (+ Math::SrgbToLinearPrecise when sRGB != 0), for parity checks of the lookup itself. */
+int selas_cuda_texture_sample(SelasContext* ctx, const SelasTextureDesc* texture, size_t n, const float* uv2, int sRGB, float* rgb3);
 
 /* ---- surface: CalculateSurfaceParams SurfaceParameters.cpp:144-247 over a batch of hits ---------- */
 int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays, const SelasHit* hits,

@@ -1073,4 +1073,38 @@ static inline void worldToImage(const SelasCamera& cam, V3 p, int32_t& ix, int32
     iy = (int32_t)floorf(y);
 }
 
+
+// ---- non-Ptex base colour textures ------------------------------------------------------------------------------------
+struct Texture {  // TextureResourceData level 0 (TextureLib/TextureResource.h:15-39)
+    const float* texels = nullptr;
+    uint32_t width = 0, height = 0, format = 0;
+};
+// TextureFiltering::Sample, WrapMode::Repeat (TextureFiltering.h:35-52): `s % w` with int32 s and uint32 w is an unsigned modulo
+static inline size_t textureTexel(const Texture& t, int32_t s, int32_t tt) {
+    uint32_t ss = (uint32_t)s % t.width, ts = (uint32_t)tt % t.height;
+    return (size_t)ts * t.width + ss;
+}
+static inline float srgbToLinearPrecise(float x) {  // MathLib/ColorSpace.cpp:16-23
+    if (x <= 0.04045f) return x / 12.92f;
+    return powf((x + 0.055f) / (1.0f + 0.055f), 2.4f);
+}
+// SampleTextureFloat3 (Shading/SurfaceParameters.cpp:97-118) over TextureFiltering::Triangle at level 0 (TextureFiltering.h:77-104)
+static inline V3 sampleTextureFloat3(const Texture& tex, float u, float v, bool sRGB) {
+    if (tex.format == SELAS_TEXTURE_FLOAT2) return v3(0.0f);
+    float s = u * tex.width - 0.5f, t = v * tex.height - 0.5f;
+    int32_t s0 = (int32_t)floorf(s), t0 = (int32_t)floorf(t);
+    float ds = s - s0, dt = t - t0;
+    const float w00 = (1 - ds) * (1 - dt), w01 = (1 - ds) * dt, w10 = ds * (1 - dt), w11 = ds * dt;
+    const uint32_t comps = tex.format + 1u;
+    const size_t i00 = textureTexel(tex, s0, t0) * comps, i01 = textureTexel(tex, s0, t0 + 1) * comps,
+                 i10 = textureTexel(tex, s0 + 1, t0) * comps, i11 = textureTexel(tex, s0 + 1, t0 + 1) * comps;
+    float r[3] = {0, 0, 0};
+    const uint32_t used = comps == 1 ? 1u : 3u;
+    for (uint32_t c = 0; c < used; ++c) {
+        float x = w00 * tex.texels[i00 + c] + w01 * tex.texels[i01 + c] + w10 * tex.texels[i10 + c] + w11 * tex.texels[i11 + c];
+        r[c] = sRGB ? srgbToLinearPrecise(x) : x;
+    }
+    return comps == 1 ? v3(r[0]) : v3(r[0], r[1], r[2]);
+}
+
 }  // namespace orc

@@ -34,6 +34,9 @@
 #include "MathLib/Sampler.h"
 #include "MathLib/CorrelatedMultiJitter.h"
 #include "MathLib/FloatFuncs.h"
+#include "MathLib/ColorSpace.h"
+#include "TextureLib/TextureFiltering.h"
+#include "TextureLib/TextureResource.h"
 #include "MathLib/ImportanceSampling.h"
 #include "IoLib/File.h"
 #include "Assets/AssetFileUtils.h"
@@ -464,6 +467,8 @@ struct RefScene {
 
 int ref_scene_create(const SelasSceneDesc* d, void** out) {
     if (d->instanceCount) return 5;  // the tier-B integrator handles the identity single-instance scenes only
+    for (uint32_t m = 0; m < d->meshCount; ++m)
+        if (d->meshes[m].baseColorTexture) return 5;  // refSurface has no texture fetch (the lookup itself is pinned by ref_texture_sample)
     RefScene* sc = new RefScene();
     sc->meshes.resize(d->meshCount);
     for (uint32_t m = 0; m < d->meshCount; ++m) {
@@ -910,6 +915,43 @@ int ref_vcm_generate_camera(const SelasCamera* cam, float lightPathCount, size_t
         index[i] = st.index;
     }
     g_src = DrawSource{nullptr, 0, 0, 0, false};
+    return 0;
+}
+
+// SampleTextureFloat3(texture, uvs, sRGB, default) of Shading/SurfaceParameters.cpp:97-118 (static there, and that translation unit
+// is not linked): the reference's own TextureFiltering::Triangle template (TextureLib/TextureFiltering.h:77-104) and
+// Math::SrgbToLinearPrecise (MathLib/ColorSpace.cpp) under the same format dispatch.
+int ref_texture_sample(const SelasTextureDesc* t, size_t n, const float* uv2, int sRGB, float* rgb3) {
+    setFtz();
+    TextureResourceData data;
+    memset(&data, 0, sizeof(data));
+    data.mipCount = 1;
+    data.mipWidths[0] = t->width;
+    data.mipHeights[0] = t->height;
+    data.mipOffsets[0] = 0;
+    data.format = (TextureResourceData::TextureDataType)t->format;
+    data.texture = reinterpret_cast<uint8*>(const_cast<float*>(t->texels));
+    for (size_t i = 0; i < n; ++i) {
+        float2 uvs(uv2[2 * i], uv2[2 * i + 1]);
+        float3 out = float3::Zero_;
+        if (data.format == TextureResourceData::Float) {
+            float v;
+            TextureFiltering::Triangle(&data, 0, uvs, v);
+            if (sRGB) v = Math::SrgbToLinearPrecise(v);
+            out = float3(v, v, v);
+        } else if (data.format == TextureResourceData::Float3) {
+            float3 v;
+            TextureFiltering::Triangle(&data, 0, uvs, v);
+            if (sRGB) v = Math::SrgbToLinearPrecise(v);
+            out = v;
+        } else if (data.format == TextureResourceData::Float4) {
+            float4 v;
+            TextureFiltering::Triangle(&data, 0, uvs, v);
+            if (sRGB) v = Math::SrgbToLinearPrecise(v);
+            out = v.XYZ();
+        }
+        st3(rgb3 + 3 * i, out);
+    }
     return 0;
 }
 

@@ -32,7 +32,8 @@ using namespace orc;
 namespace {
 
 struct Mesh {
-    std::vector<float> positions, normals, tangents, uvs;
+    std::vector<float> positions, normals, tangents, uvs, texels;
+    Texture texture;  // base colour texture (texels above), or texels == nullptr
     std::vector<uint32_t> indices;
     uint32_t faceCount, indicesPerFace, materialIndex, lightSetIndex;
 };
@@ -194,6 +195,11 @@ static void surfaceParams(const Scene& sc, const SelasRay& r, const SelasHit& h,
         b = cross(n, t);
     }
     V3 base = v3(mat.baseColor);
+    if (mesh.texture.texels) {  // SurfaceParameters.cpp:186-190, :209-214
+        float uv[2] = {0.0f, 0.0f};
+        if (!mesh.uvs.empty()) interp3(mesh.uvs, 2, uv);
+        base = sampleTextureFloat3(mesh.texture, uv[0], uv[1], true);
+    }
     base = v3(powf(base.x, 2.2f), powf(base.y, 2.2f), powf(base.z, 2.2f));
     store(s.baseColor, base);
 
@@ -493,6 +499,13 @@ int orc_scene_create(const SelasSceneDesc* d, void** out) {
         if (md.normals) M.normals.assign(md.normals, md.normals + 3 * (size_t)md.vertexCount);
         if (md.tangents) M.tangents.assign(md.tangents, md.tangents + 4 * (size_t)md.vertexCount);
         if (md.uvs) M.uvs.assign(md.uvs, md.uvs + 2 * (size_t)md.vertexCount);
+        if (md.baseColorTexture) {
+            const SelasTextureDesc& t = *md.baseColorTexture;
+            M.texels.assign(t.texels, t.texels + (size_t)t.width * t.height * (t.format + 1));
+            M.texture.width = t.width;
+            M.texture.height = t.height;
+            M.texture.format = t.format;
+        }
         M.indices.assign(md.indices, md.indices + (size_t)md.faceCount * md.indicesPerFace);
         M.faceCount = md.faceCount;
         M.indicesPerFace = md.indicesPerFace;
@@ -559,10 +572,20 @@ int orc_scene_create(const SelasSceneDesc* d, void** out) {
             }
         }
     }
+    for (Mesh& M : sc->meshes)  // the meshes vector no longer moves: point the textures at their texel copies
+        if (!M.texels.empty()) M.texture.texels = M.texels.data();
     sc->bvh.build();
     *out = sc;
     return 0;
 }
+int orc_texture_sample(const SelasTextureDesc* t, size_t n, const float* uv2, int sRGB, float* rgb3) {
+    setFtz();
+    Texture tex;
+    tex.texels = t->texels; tex.width = t->width; tex.height = t->height; tex.format = t->format;
+    for (size_t i = 0; i < n; ++i) store(rgb3 + 3 * i, sampleTextureFloat3(tex, uv2[2 * i], uv2[2 * i + 1], sRGB != 0));
+    return 0;
+}
+
 int orc_scene_destroy(void* s) {
     delete (Scene*)s;
     return 0;

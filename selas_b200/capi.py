@@ -51,10 +51,14 @@ class CameraSettings(C.Structure):
                 ("zfar", f32)]
 
 
+class TextureDesc(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("format", u32), ("reserved", u32), ("texels", C.c_void_p)]
+
+
 class MeshDesc(C.Structure):
     _fields_ = [("positions", C.c_void_p), ("vertexCount", u32), ("indices", C.c_void_p), ("faceCount", u32),
                 ("indicesPerFace", u32), ("normals", C.c_void_p), ("tangents", C.c_void_p), ("uvs", C.c_void_p),
-                ("materialIndex", u32), ("lightSetIndex", u32), ("ptex", C.c_void_p)]
+                ("materialIndex", u32), ("lightSetIndex", u32), ("ptex", C.c_void_p), ("baseColorTexture", C.POINTER(TextureDesc))]
 
 
 class InstanceDesc(C.Structure):
@@ -138,7 +142,7 @@ EXPORTS = [
     "selas_cuda_intersect", "selas_cuda_occluded", "selas_cuda_intersect_device", "selas_cuda_occluded_device",
     "selas_cuda_intersect_counted", "selas_cuda_camera_init", "selas_cuda_camera_rays", "selas_cuda_cmj", "selas_cuda_bsdf_eval",
     "selas_cuda_bsdf_sample", "selas_cuda_light_sample", "selas_cuda_light_pdf", "selas_cuda_surface_params",
-    "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample",
+    "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample", "selas_cuda_texture_sample",
     "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_film_scale_device",
     "selas_cuda_reduce_film", "selas_cuda_render_vcm", "selas_cuda_render_vcm_device", "selas_cuda_vcm_light_pass", "selas_cuda_vcm_iteration_constants",
     "selas_cuda_hashgrid_build", "selas_cuda_hashgrid_destroy", "selas_cuda_hashgrid_read",
@@ -258,6 +262,16 @@ class Context:
                                                    _ptr(out)))
         return out
 
+    def texture_sample(self, texture, uv, srgb=True):
+        """SampleTextureFloat3 (SurfaceParameters.cpp:97-118) = Triangle filter at level 0 (+ sRGB -> linear) over a batch of uvs."""
+        a = texture_array(texture)
+        td = texture_desc(a)
+        uv = _f32(uv).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3), np.float32)
+        self.check(self.lib.selas_cuda_texture_sample(self.handle, C.byref(td), C.c_size_t(uv.shape[0]), _ptr(uv), C.c_int(1 if srgb else 0),
+                                                      _ptr(out)))
+        return out
+
     def light_sample(self, lights, position, normal, u3):
         lights = np.ascontiguousarray(lights, dtype=LIGHT_DTYPE)
         position = _f32(position).reshape(-1, 3)
@@ -295,6 +309,22 @@ def camera_init(position, look_at, up, fov_degrees, width, height, znear=0.1, zf
     return cam
 
 
+def texture_array(tex):
+    a = np.ascontiguousarray(tex, dtype=np.float32)
+    if a.ndim == 2:
+        a = a[..., None]
+    assert a.ndim == 3 and 1 <= a.shape[2] <= 4
+    return np.ascontiguousarray(a)
+
+
+def texture_desc(a):
+    """SelasTextureDesc over a texture_array (the array must outlive the descriptor's use)."""
+    td = TextureDesc()
+    td.width, td.height, td.format, td.reserved = a.shape[1], a.shape[0], a.shape[2] - 1, 0
+    td.texels = a.ctypes.data
+    return td
+
+
 class SceneData:
     """Host-side scene description (numpy) from which both the CUDA scene and the oracle scene are created.
 
@@ -315,6 +345,8 @@ class SceneData:
             mm.setdefault("material", 0)
             mm.setdefault("lightSet", 0)
             mm.setdefault("ptex", None)
+            tex = m.get("texture")  # (H, W) or (H, W, 1|2|3|4) float32: base colour texture, level 0 (SelasTextureDesc)
+            mm["texture"] = None if tex is None else texture_array(tex)
             self.meshes.append(mm)
         self.materials = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
         self.lights = np.zeros(0, LIGHT_DTYPE) if lights is None else np.ascontiguousarray(lights, dtype=LIGHT_DTYPE)
@@ -342,6 +374,10 @@ class SceneData:
             md[i].uvs = None if m["uvs"] is None else m["uvs"].ctypes.data
             md[i].materialIndex = m["material"]
             md[i].lightSetIndex = m["lightSet"]
+            if m["texture"] is not None:
+                td = texture_desc(m["texture"])
+                keep.append(td)
+                md[i].baseColorTexture = C.pointer(td)
             ptex = m["ptex"]
             md[i].ptex = None if ptex is None else (ptex.handle if hasattr(ptex, "handle") else ptex)
         desc = SceneDesc()

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libselas_cuda.so (include/selas_cuda.h): contexts, scene upload + BVH build, and
 // the host-buffer entry points (copy in, launch, copy out, synchronise).  No CPU fallback anywhere: every
 // entry point either runs its CUDA kernels or fails with SELAS_ERR_CUDA.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -181,6 +182,13 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
             setError(ctx, "mesh %u: materialIndex %u out of range (%u materials)", m, md.materialIndex, d->materialCount);
             return SELAS_ERR_ARGUMENT;
         }
+        if (md.baseColorTexture) {
+            const SelasTextureDesc& t = *md.baseColorTexture;
+            if (t.width == 0 || t.height == 0 || t.format > SELAS_TEXTURE_FLOAT4 || !t.texels) {
+                setError(ctx, "mesh %u: baseColorTexture needs width, height > 0, a TextureDataType format and texels", m);
+                return SELAS_ERR_ARGUMENT;
+            }
+        }
         const size_t nidx = (size_t)md.faceCount * md.indicesPerFace;
         for (size_t k = 0; k < nidx; ++k)
             if (md.indices[k] >= md.vertexCount) {
@@ -209,6 +217,24 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
         }
     } guard{scene};
 
+    // base colour textures: one device copy per distinct descriptor
+    std::vector<const SelasTextureDesc*> texDescs;
+    std::vector<TextureGpu> texGpu;
+    for (uint32_t m = 0; m < d->meshCount; ++m) {
+        const SelasTextureDesc* t = d->meshes[m].baseColorTexture;
+        if (!t || std::find(texDescs.begin(), texDescs.end(), t) != texDescs.end()) continue;
+        TextureGpu g;
+        memset(&g, 0, sizeof(g));
+        SELAS_TRY(sceneUpload(scene, &g.texels, t->texels, (size_t)t->width * t->height * (t->format + 1)));
+        g.width = t->width;
+        g.height = t->height;
+        g.format = t->format;
+        texDescs.push_back(t);
+        texGpu.push_back(g);
+    }
+    const TextureGpu* d_textures = nullptr;
+    if (!texGpu.empty()) SELAS_TRY(sceneUpload(scene, &d_textures, texGpu.data(), texGpu.size()));
+
     std::vector<MeshGpu> meshes(d->meshCount);
     for (uint32_t m = 0; m < d->meshCount; ++m) {
         const SelasMeshDesc& md = d->meshes[m];
@@ -221,6 +247,8 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
         if (md.uvs) SELAS_TRY(sceneUpload(scene, &g.uvs, md.uvs, 2 * (size_t)md.vertexCount));
         g.ptex = md.ptex ? ptexDevicePointer((SelasPtex*)md.ptex) : nullptr;
         if (g.ptex) scene->usesPtex = true;
+        if (md.baseColorTexture)
+            g.texture = d_textures + (std::find(texDescs.begin(), texDescs.end(), md.baseColorTexture) - texDescs.begin());
         g.faceCount = md.faceCount;
         g.indicesPerFace = md.indicesPerFace;
         g.materialIndex = md.materialIndex;
@@ -674,6 +702,41 @@ int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays,
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(SelasSurface), cudaMemcpyDeviceToHost, ctx->stream));
     SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return SELAS_OK;
+}
+
+// ---- textures ------------------------------------------------------------------------------------------------------
+int selas_cuda_texture_sample(SelasContext* ctx, const SelasTextureDesc* t, size_t n, const float* uv2, int sRGB, float* rgb3) {
+    SELAS_TRY(bind(ctx));
+    if (!t || t->width == 0 || t->height == 0 || t->format > SELAS_TEXTURE_FLOAT4 || !t->texels || (n && (!uv2 || !rgb3))) {
+        setError(ctx, "selas_cuda_texture_sample: bad texture descriptor or null buffers");
+        return SELAS_ERR_ARGUMENT;
+    }
+    if (!n) return SELAS_OK;
+    const size_t floats = (size_t)t->width * t->height * (t->format + 1);
+    float *d_tex = nullptr, *d_uv = nullptr, *d_out = nullptr;
+    int rc = SELAS_OK;
+    auto fail = [&](cudaError_t e, const char* what) {
+        if (e != cudaSuccess && !rc) {
+            setError(ctx, "%s failed: %s", what, cudaGetErrorString(e));
+            rc = SELAS_ERR_CUDA;
+        }
+    };
+    fail(cudaMalloc((void**)&d_tex, sizeof(float) * floats), "cudaMalloc(texels)");
+    fail(cudaMalloc((void**)&d_uv, sizeof(float) * 2 * n), "cudaMalloc(uvs)");
+    fail(cudaMalloc((void**)&d_out, sizeof(float) * 3 * n), "cudaMalloc(out)");
+    if (!rc) fail(cudaMemcpyAsync(d_tex, t->texels, sizeof(float) * floats, cudaMemcpyHostToDevice, ctx->stream), "upload texels");
+    if (!rc) fail(cudaMemcpyAsync(d_uv, uv2, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, ctx->stream), "upload uvs");
+    if (!rc) {
+        TextureGpu g;
+        g.texels = d_tex; g.width = t->width; g.height = t->height; g.format = t->format; g.pad = 0;
+        rc = launchTextureSample(ctx, g, n, d_uv, sRGB, d_out);
+    }
+    if (!rc) fail(cudaMemcpyAsync(rgb3, d_out, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream), "download");
+    if (!rc) fail(cudaStreamSynchronize(ctx->stream), "synchronize");
+    cudaFree(d_tex);
+    cudaFree(d_uv);
+    cudaFree(d_out);
+    return rc;
 }
 
 // ---- integrator ------------------------------------------------------------------------------------------------

@@ -14,6 +14,12 @@ struct Bvh8;
 
 // Device view of one mesh (= one Embree geometry: ModelGeometryUserData + its shared buffers,
 // ModelResource.h:97-105, ModelResource.cpp:164-200).
+// TextureResourceData level 0 on the device
+struct TextureGpu {
+    const float* texels;
+    uint32_t width, height, format, pad;
+};
+
 struct MeshGpu {
     const float* positions;
     const uint32_t* indices;
@@ -21,6 +27,7 @@ struct MeshGpu {
     const float* tangents;  // float4 or null
     const float* uvs;       // float2 or null
     const void* ptex;       // device PtexGpu* or null
+    const TextureGpu* texture;  // base colour texture (non-Ptex materials) or null
     uint32_t faceCount;
     uint32_t indicesPerFace;
     uint32_t materialIndex;
@@ -131,6 +138,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
 int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream);
 int launchIblLookup(SelasScene* scene, size_t n, const float* d_wi3, float* d_rgb3, float* d_pdf, float* d_miss3);
 int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp3, uint32_t* d_xy2);
+int launchTextureSample(SelasContext* ctx, const TextureGpu& tex, size_t n, const float* d_uv2, int sRGB, float* d_rgb3);
 int launchCmj(SelasContext* ctx, size_t count, const int32_t* d_s, int32_t m, int32_t n, const int32_t* d_p, float* d_out2);
 void freeWavefront(SelasScene* scene);
 

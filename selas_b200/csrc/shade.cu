@@ -151,6 +151,12 @@ __global__ void __launch_bounds__(128) surfaceParamsKernel(SceneGpu sc, size_t n
     out[i] = o;
 }
 
+__global__ void textureSampleKernel(TextureGpu tex, size_t n, const float* __restrict__ uv2, int sRGB, float* __restrict__ rgb3) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    store3(rgb3 + 3 * i, sampleTextureFloat3(tex, uv2[2 * i], uv2[2 * i + 1], sRGB != 0));
+}
+
 __global__ void scaleKernel(float* __restrict__ d, size_t n, float s) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] *= s;
@@ -215,6 +221,12 @@ int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp
     if (!n) return SELAS_OK;
     iblSampleKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu.ibl, n, d_u2, d_tpp3, d_xy2);
     SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchTextureSample(SelasContext* ctx, const TextureGpu& tex, size_t n, const float* d_uv2, int sRGB, float* d_rgb3) {
+    if (!n) return SELAS_OK;
+    textureSampleKernel<<<divUp(n, 256), 256, 0, ctx->stream>>>(tex, n, d_uv2, sRGB, d_rgb3);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
 int launchCmj(SelasContext* ctx, size_t count, const int32_t* d_s, int32_t m, int32_t n, const int32_t* d_p, float* d_out2) {

@@ -22,6 +22,39 @@ SELAS_D float interpAttr(const float* a, const uint32_t* ix, uint32_t ipf, int c
     return (1.0f - v) * ((1.0f - u) * t0 + u * t1) + v * ((1.0f - u) * t3 + u * t2);
 }
 
+// ---- non-Ptex base colour textures ----------------------------------------------------------------------------------------
+// TextureFiltering::Sample with WrapMode::Repeat (TextureFiltering.h:35-52).  QUIRK: `s % w` mixes int32 and uint32, so a negative
+// coordinate is reduced as a 32-bit unsigned number: -1 wraps to w - 1 only when w is a power of two.
+SELAS_D size_t textureTexel(const TextureGpu& tex, int32_t s, int32_t t) {
+    uint32_t ss = (uint32_t)s % tex.width, tt = (uint32_t)t % tex.height;
+    return (size_t)tt * tex.width + ss;
+}
+// Math::SrgbToLinearPrecise, MathLib/ColorSpace.cpp:16-23
+SELAS_D float srgbToLinearPrecise(float x) {
+    if (x <= 0.04045f) return x / 12.92f;
+    return powf((x + 0.055f) / (1.0f + 0.055f), 2.4f);
+}
+// SampleTextureFloat3(texture, uvs, sRGB, default) (SurfaceParameters.cpp:97-118) over TextureFiltering::Triangle at level 0
+// (TextureFiltering.h:77-104): four taps weighted (1-ds)(1-dt), (1-ds)dt, ds(1-dt), ds dt, summed in that order.
+SELAS_D V3 sampleTextureFloat3(const TextureGpu& tex, float u, float v, bool sRGB) {
+    if (tex.format == SELAS_TEXTURE_FLOAT2) return v3(0.0f);  // Assert_(false) branch, :116-117
+    float s = u * tex.width - 0.5f, t = v * tex.height - 0.5f;
+    int32_t s0 = (int32_t)floorf(s), t0 = (int32_t)floorf(t);
+    float ds = s - s0, dt = t - t0;
+    const float w00 = (1 - ds) * (1 - dt), w01 = (1 - ds) * dt, w10 = ds * (1 - dt), w11 = ds * dt;
+    const uint32_t comps = tex.format + 1u;
+    const size_t i00 = textureTexel(tex, s0, t0) * comps, i01 = textureTexel(tex, s0, t0 + 1) * comps,
+                 i10 = textureTexel(tex, s0 + 1, t0) * comps, i11 = textureTexel(tex, s0 + 1, t0 + 1) * comps;
+    float r[3];
+    const uint32_t used = comps == 1 ? 1u : 3u;
+    for (uint32_t c = 0; c < used; ++c) {
+        float x = w00 * __ldg(tex.texels + i00 + c) + w01 * __ldg(tex.texels + i01 + c) + w10 * __ldg(tex.texels + i10 + c) +
+                  w11 * __ldg(tex.texels + i11 + c);
+        r[c] = sRGB ? srgbToLinearPrecise(x) : x;
+    }
+    return comps == 1 ? v3(r[0]) : v3(r[0], r[1], r[2]);
+}
+
 // ptexRgb: this hit's Ptex lookup, made by the Ptex stage kernel (ptexStageKernel) before shading, or null.
 SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, float v, uint32_t primID, uint32_t geomID,
                             uint32_t instID, const float* ptexRgb, Surface& s) {
@@ -73,8 +106,17 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
         // SurfaceParameters.cpp:196-208: filter->eval(faceid = primId, u, v, widths 0), then pow 2.2 only.  The lookup itself
         // was done by the Ptex stage that runs between the closest-hit and the shade kernels.
         base = v3(ptexRgb[0], ptexRgb[1], ptexRgb[2]);
+    } else if (mesh.texture) {
+        // SurfaceParameters.cpp:209-214: SampleTextureFloat3(baseColorTexture, uvs, sRGB = true, material baseColor); uvs = (0, 0)
+        // without a uv buffer (:186-190)
+        float tu = 0.0f, tv = 0.0f;
+        if (mesh.uvs) {
+            tu = interpAttr(mesh.uvs, ix, mesh.indicesPerFace, 2, 0, u, v);
+            tv = interpAttr(mesh.uvs, ix, mesh.indicesPerFace, 2, 1, u, v);
+        }
+        base = sampleTextureFloat3(*mesh.texture, tu, tv, true);
     } else {
-        base = v3(mat->baseColor);  // non-Ptex textures: SURVEY.md 8(f)4, not in this round
+        base = v3(mat->baseColor);
     }
     // QUIRK SurfaceParameters.cpp:204,:211-212: pow(x, 2.2) applied on top of everything
     s.baseColor = v3(powf(base.x, 2.2f), powf(base.y, 2.2f), powf(base.z, 2.2f));

@@ -140,6 +140,15 @@ class ShadingOracle(_Lib):
         assert rc == 0, rc
         return tpp, xy
 
+    def texture_sample(self, texture, uv, srgb=True):
+        a = capi.texture_array(texture)
+        td = capi.texture_desc(a)
+        uv = _f32(uv).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3), np.float32)
+        rc = self.fn("texture_sample")(C.byref(td), C.c_size_t(uv.shape[0]), _ptr(uv), C.c_int(1 if srgb else 0), _ptr(out))
+        assert rc == 0, rc
+        return out
+
     # VCM building blocks (live code in the reference: AreaLighting.cpp:246-331, VCMCommon.cpp:37-112) ------------------
     def ibl_emit(self, h, sphere4, u4):
         u4 = _f32(u4).reshape(-1, 4)

@@ -315,6 +315,49 @@ def test_render_mis_balance_mode(ctx, oracle):
     sc.close()
 
 
+@pytest.mark.parametrize("shape", [(16, 32, 3), (7, 13, 3), (9, 5, 1), (8, 8, 4)])
+def test_texture_lookup_parity(ctx, oracle, shape):
+    """SampleTextureFloat3: same taps and weights in the same order as the CPU (the unit is compiled -fmad=false), so only powf of the
+    sRGB curve can differ; the linear path is bit-exact."""
+    rng = np.random.default_rng(61 + shape[0])
+    tex = rng.uniform(0, 1, size=shape).astype(np.float32)
+    uv = rng.uniform(-2.5, 3.5, size=(N, 2)).astype(np.float32)
+    np.testing.assert_array_equal(ctx.texture_sample(tex, uv, srgb=False).view(np.uint32), oracle.texture_sample(tex, uv, False).view(np.uint32))
+    _assert_rel(ctx.texture_sample(tex, uv, srgb=True), oracle.texture_sample(tex, uv, True), 1e-6, "srgb lookup", floor=1e-6)
+
+
+def test_render_textured_base_colour(ctx, oracle):
+    """A base colour texture on the floor and on the uv-less sphere (uvs default to (0,0), SurfaceParameters.cpp:186): surface
+    parameters and the rendered image against the oracle; the texture must actually change the picture."""
+    data = inputs.small_scene()
+    rng = np.random.default_rng(5)
+    checker = ((np.add.outer(np.arange(16), np.arange(16)) % 2) * 0.8 + 0.1).astype(np.float32)
+    tex = np.stack([checker, checker[::-1], rng.uniform(0, 1, size=(16, 16)).astype(np.float32)], axis=2)
+    data.meshes[2]["uvs"] = np.array([[0, 0], [0, 3], [3, 3], [3, 0]], np.float32)  # the floor quad, repeated 3x3
+    data.meshes[2]["texture"] = tex
+    data.meshes[1]["texture"] = np.full((4, 4, 1), 0.6, np.float32)  # no uv buffer on this mesh
+    sc, hs = capi.Scene(ctx, data), oracle.scene_create(data)
+    rays = inputs.scene_rays(3, 20000)
+    hits = sc.intersect(rays)
+    ok = hits["geomID"] != capi.SELAS_INVALID_ID
+    gs, os_ = sc.surface_params(rays[ok], hits[ok]), oracle.surface_params(hs, rays[ok], hits[ok])
+    _assert_rel(gs["baseColor"], os_["baseColor"], 1e-5, "textured baseColor", floor=1e-6)
+    on_floor = hits[ok]["geomID"] == 2
+    assert on_floor.sum() > 100 and np.unique(np.round(os_["baseColor"][on_floor], 3), axis=0).shape[0] > 20
+    cam = capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 96, 64)
+    rs = capi.render_settings(96, 64, 16, max_path_length=6, rr_start=8, layers=2, seed=2)
+    g, o = sc.render(cam, rs)[0], oracle.render(hs, cam, rs, nthreads=8)[0]
+    for l in range(2):
+        a, b = g[l] / 16.0, o[l] / 16.0
+        assert abs(a.mean() / b.mean() - 1.0) < 2e-3 and _relmse(a, b) < 2e-3
+    plain = capi.Scene(ctx, inputs.small_scene())
+    p = plain.render(cam, rs)[0][0] / 16.0
+    assert _relmse(p, g[0] / 16.0) > 1e-2
+    plain.close()
+    oracle.scene_destroy(hs)
+    sc.close()
+
+
 @pytest.mark.parametrize("with_ibl", [False, True])
 def test_render_deferred_integrator(ctx, oracle, with_ibl):
     """SelasRenderSettings.integrator = 1: the DeferredPathTracer's ShadeHitPosition (area NEE + sky NEE with balance-heuristic MIS,

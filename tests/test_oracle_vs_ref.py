@@ -304,3 +304,17 @@ def oracle_render_plain(oracle, data, cam):
     f, s = oracle.render(h, cam, capi.render_settings(40, 30, 16, max_path_length=64, layers=1, seed=8, cmj=(4, 4)), nthreads=2)
     oracle.scene_destroy(h)
     return f[0], s
+
+
+@pytest.mark.parametrize("shape", [(16, 32, 3), (7, 13, 3), (9, 5, 1), (8, 8, 4), (1, 1, 3)])
+def test_texture_lookup_bit_exact(oracle, ref, shape):
+    """SampleTextureFloat3 (SurfaceParameters.cpp:97-118): the reference's TextureFiltering::Triangle template and SrgbToLinearPrecise
+    against the restatement, incl. non-power-of-two sizes where the int32 % uint32 Repeat wrap of negative coordinates is not w - 1."""
+    rng = np.random.default_rng(51 + shape[0])
+    tex = rng.uniform(0, 1, size=shape).astype(np.float32)
+    uv = rng.uniform(-2.5, 3.5, size=(N, 2)).astype(np.float32)
+    uv[:8] = [[0, 0], [1, 1], [0.5, 0.5], [-0.01, 0.99], [1e-4, -1e-4], [0.999, 0.001], [2.0, -1.0], [0.25, 0.75]]
+    for srgb in (True, False):
+        a, b = oracle.texture_sample(tex, uv, srgb), ref.texture_sample(tex, uv, srgb)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert a.max() > 0
