@@ -19,6 +19,16 @@ namespace selas {
 #ifndef SELAS_TRACE_CTAS_PER_SM
 #define SELAS_TRACE_CTAS_PER_SM 8
 #endif
+// Triangle postponing (after Ylitie, Karras, Laine 2017, section 4.3).  ncu (profiles/r1_trace_*): tested right after the node that
+// produced them, leaf triangles took 28 % of the kernel's issue slots at 3 of 32 lanes.  Instead a lane parks the triangle group of
+// its last node in a register pair and the warp votes every iteration: the parked groups are tested together once at least
+// 1/SELAS_TRI_POSTPONE_DIV of the traversing lanes have one (or a lane has nothing else left, or needs the slot for a new group).
+// 0 disables -- and is the default: measured on configs[2] (scripts/ab_trace.sh, DIV = 0/2/3/5/8) the closest-hit time stayed within
+// noise (9.47-9.68 ms per step) while instructions went UP 6 % (2.32 -> 2.45 G warp instructions, lanes/instr 18.8 -> 19.6): leaf
+// triangles are met at the end of a ray's traversal, when the lane has nothing else left, so most parked groups are tested alone anyway.
+#ifndef SELAS_TRI_POSTPONE_DIV
+#define SELAS_TRI_POSTPONE_DIV 0
+#endif
 
 // MODE 0: closest hit -> hits (+Ng); 1: any hit -> occluded byte; 2: any hit -> film[pixel] += payload.rgb when
 // unoccluded (the NEE shadow ray of PathTracer.cpp:186-191 fused with FramebufferWriter_Write).
@@ -40,6 +50,9 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
     uint2 stack[SELAS_STACK_SIZE];
     int sp = 0;
     uint2 group = make_uint2(0u, 0u);
+#if SELAS_TRI_POSTPONE_DIV
+    uint2 pendTri = make_uint2(0u, 0u);
+#endif
     V3 o = v3(0.f), d = v3(0.f), idir = v3(0.f);
     float tnear = 0.f, tfar = 0.f, tmax = 0.f;
     bool negx = false, negy = false, negz = false;
@@ -86,6 +99,9 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                     group = make_uint2(0u, (bvh.nodeCount && valid) ? 0x80000000u : 0u);
                     rayIdx = idx;
                     nNodes = 0; nTris = 0;
+#if SELAS_TRI_POSTPONE_DIV
+                    pendTri = make_uint2(0u, 0u);
+#endif
                     active = true;
                 }
             }
@@ -96,6 +112,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
         while (active) {
             bool finished = false;
             uint2 triGroup;
+
             if (group.y & 0xff000000u) {
                 uint32_t hitsImask = group.y;
                 uint32_t childBit = 31u - __clz(hitsImask);
@@ -115,6 +132,22 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                 triGroup = group;
                 group = make_uint2(0u, 0u);
             }
+#if SELAS_TRI_POSTPONE_DIV
+            {
+                if (triGroup.y != 0u) {  // new leaf triangles: park them; if the slot is taken, the older group is tested now
+                    uint2 older = pendTri;
+                    pendTri = triGroup;
+                    triGroup = older;
+                }
+                const uint32_t amask = __activemask();
+                const uint32_t parked = __ballot_sync(amask, pendTri.y != 0u);
+                const bool nothingElse = (group.y & 0xff000000u) == 0u && sp == 0;
+                if (triGroup.y == 0u && pendTri.y != 0u && (__popc(parked) * SELAS_TRI_POSTPONE_DIV >= __popc(amask) || nothingElse)) {
+                    triGroup = pendTri;
+                    pendTri = make_uint2(0u, 0u);
+                }
+            }
+#endif
             while (triGroup.y != 0u) {
                 uint32_t bit = 31u - __clz(triGroup.y);
                 triGroup.y &= ~(1u << bit);
@@ -130,7 +163,14 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                 }
             }
             if (!finished && (group.y & 0xff000000u) == 0u) {
+#if SELAS_TRI_POSTPONE_DIV
+                if (sp == 0) {  // parked triangles are tested next iteration (nothingElse); the spent group must not be read as one
+                    group = make_uint2(0u, 0u);
+                    finished = pendTri.y == 0u;
+                }
+#else
                 if (sp == 0) finished = true;
+#endif
                 else group = stack[--sp];
             }
             if (finished) {
