@@ -468,6 +468,37 @@ Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, c
 }
 }  // namespace PathTracer
 
+namespace DeferredPathTracer {
+Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, const char* imageName, const DeferredPathTracerSettings& settings,
+                    SelasRenderStats* stats, Framebuffer* keep) {
+    if (!scene->gpuScene) return Error_("DeferredPathTracer::GenerateImage: scene is not initialised on a GPU (there is no CPU fallback)");
+    const uint32_t width = (uint32_t)camera.width, height = (uint32_t)camera.height;
+    const uint32_t spp = settings.samplesPerPixelX * settings.samplesPerPixelY;
+    if (spp == 0 || settings.samplesPerPixelX > 0xffffu || settings.samplesPerPixelY > 0xffffu)
+        return Error_("DeferredPathTracer::GenerateImage: SamplesPerPixelX_/Y_ out of range");
+    Framebuffer frame;
+    FrameBuffer_Initialize(&frame, width, height, 1);  // OutputLayers_, :42
+    SelasRenderSettings rs;
+    memset(&rs, 0, sizeof(rs));
+    rs.width = width;
+    rs.height = height;
+    rs.samplesPerPixel = spp;
+    rs.maxPathLength = settings.maxBounceCount;
+    rs.layerCount = 1;
+    rs.seed = settings.seed;
+    rs.pixelSampler = settings.samplesPerPixelX | (settings.samplesPerPixelY << 16);  // JitteredCameraRay(..., scan, X, Y, index), :365-366
+    rs.integrator = SELAS_INTEGRATOR_DEFERRED;
+    float* layers[1] = {&frame.buffers[0][0].x};
+    if (selas_cuda_render_pathtracer(scene->gpuScene, &camera, &rs, layers, stats) != SELAS_OK)
+        return Error_("%s", selas_cuda_last_error(scene->gpu));
+    FrameBuffer_Scale(&frame, 1.0f / (float)spp);  // :467
+    ReturnError_(FrameBuffer_Save(&frame, imageName));
+    if (keep) *keep = frame;
+    FrameBuffer_Shutdown(&frame);
+    return Success_;
+}
+}  // namespace DeferredPathTracer
+
 // ---- image based light + config 5 scene -------------------------------------------------------------------------------
 void ImageBasedLight::BuildDensityFunctions() {
     const float pi = 3.141592653589793f;

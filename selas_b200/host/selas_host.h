@@ -136,6 +136,19 @@ Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, c
                     const PathTracerSettings& settings = PathTracerSettings(), SelasRenderStats* stats = nullptr, Framebuffer* keep = nullptr);
 }  // namespace PathTracer
 
+// DeferredPathTracer::GenerateImage (DeferredPathTracer.cpp:421-470): SamplesPerPixelX_ x SamplesPerPixelY_ correlated multi-jittered
+// primary rays per pixel, one output layer, the ShadeHitPosition estimator (SelasRenderSettings.integrator = 1).
+struct DeferredPathTracerSettings {
+    uint32_t samplesPerPixelX = 4, samplesPerPixelY = 4;  // :40-41
+    uint32_t maxBounceCount = 2048;                       // safety bound only: the reference terminates paths by Russian roulette
+    uint32_t seed = 0;
+};
+namespace DeferredPathTracer {
+Error GenerateImage(SceneResource* scene, const RayCastCameraSettings& camera, const char* imageName,
+                    const DeferredPathTracerSettings& settings = DeferredPathTracerSettings(), SelasRenderStats* stats = nullptr,
+                    Framebuffer* keep = nullptr);
+}  // namespace DeferredPathTracer
+
 // The reference's VCM macros (VCM.cpp:28-35) as runtime settings; IntegrationSeconds_ becomes an iteration count.
 struct VCMSettings {
     uint32_t maxBounceCount = 10;    // MaxBounceCount_

@@ -1,6 +1,7 @@
 // selas_render.cpp -- the reference's main() (Source/Applications/Selas/Source/main.cpp:82-135) for the synthetic Cornell
 // scene: initialise the scene on the GPU, set up the camera, PathTracer::GenerateImage, report the render time.
 //   selas_render [--width W] [--height H] [--spp N] [--depth D] [--layers L] [--roughness R] [--device I] [--name NAME]
+//   selas_render --integrator deferred [...]                      (DeferredPathTracer::GenerateImage, 4 x 4 CMJ samples per pixel)
 //   selas_render --integrator vcm [--width W] [--height H] [--iterations N] [--depth D] ...   (config 5 caustic scene, VCM::GenerateImage)
 #include <chrono>
 #include <cstdio>
@@ -75,6 +76,11 @@ int main(int argc, char** argv) {
         ShutdownSceneResource(&scene);
         return 0;
     }
+    const bool deferred = !strcmp(integrator, "deferred");
+    if (strcmp(integrator, "pathtracer") && !deferred) {
+        fprintf(stderr, "unknown integrator %s (pathtracer | deferred | vcm)\n", integrator);
+        return 2;
+    }
     auto t0 = std::chrono::steady_clock::now();
     SceneResource scene;
     MakeCornellBoxScene(&scene, roughness);
@@ -85,7 +91,13 @@ int main(int argc, char** argv) {
     RayCastCameraSettings camera;
     SetupCornellCamera(width, height, camera);
     SelasRenderStats stats;
-    ExitMainOnError_(PathTracer::GenerateImage(&scene, camera, name, settings, &stats));
+    if (deferred) {
+        DeferredPathTracerSettings ds;
+        ds.seed = settings.seed;
+        if (settings.maxBounceCount != 8) ds.maxBounceCount = settings.maxBounceCount;
+        ExitMainOnError_(DeferredPathTracer::GenerateImage(&scene, camera, name, ds, &stats));
+    } else
+        ExitMainOnError_(PathTracer::GenerateImage(&scene, camera, name, settings, &stats));
     auto t2 = std::chrono::steady_clock::now();
     printf("Scene render time %fms\n", std::chrono::duration<double, std::milli>(t2 - t1).count());  // main.cpp:124-125
     printf("{\"paths\": %llu, \"closest_rays\": %llu, \"occlusion_rays\": %llu, \"kernel_launches\": %llu, \"device_ms\": %.3f, "

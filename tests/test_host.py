@@ -105,3 +105,21 @@ def test_selas_render_vcm(ctx, host, tmp_path):
     wb = want.reshape(h // 4, 4, w // 4, 4, 3).mean(axis=(1, 3))
     assert float(np.mean((gb - wb) ** 2 / (wb ** 2 + 1e-2))) < 0.02
     sc.close()
+
+
+@pytest.mark.gpu
+def test_selas_render_deferred(ctx, host, tmp_path):
+    """DeferredPathTracer::GenerateImage through the C++ host equals the same settings through the C ABI."""
+    exe = LIB / "selas_render"
+    out = subprocess.run([str(exe), "--integrator", "deferred", "--width", "80", "--height", "80", "--roughness", "0.1", "--seed", "2", "--depth", "32",
+                          "--name", "d"], cwd=tmp_path, capture_output=True, text=True, check=True).stdout
+    stats = json.loads(out.strip().splitlines()[-1])
+    assert stats["paths"] == 80 * 80 * 16 and stats["occlusion_rays"] > stats["paths"]  # two NEE samples per vertex
+    got = read_hdr(tmp_path / "_Images" / "d_0.hdr")
+    sc = capi.Scene(ctx, scenes.cornell_box(copper_roughness=0.1))
+    film, _ = sc.render(scenes.cornell_camera(80, 80), capi.render_settings(80, 80, 16, max_path_length=32, layers=1, seed=2, cmj=(4, 4),
+                                                                             integrator=capi.INTEGRATOR_DEFERRED))
+    want = film[0] / 16.0
+    m = want.max(axis=2, keepdims=True)
+    assert (np.abs(got - want) <= m / 100.0 + 1e-4).mean() > 0.995
+    sc.close()
