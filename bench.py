@@ -111,6 +111,21 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def captured_traffic_per_ray():
+    """DRAM bytes per closest-hit ray from the committed `ncu --set full` capture of traceKernel<0> on this workload
+    (profiles/r1_trace_kernel_metrics.csv, bounce-0 launch of 8,294,400 rays): dram__bytes_read.sum + dram__bytes_write.sum."""
+    p = ROOT / "profiles" / "r1_trace_kernel_metrics.csv"
+    try:
+        import csv
+        rows = list(csv.reader(l for l in p.read_text().splitlines() if not l.startswith("#")))
+        hdr, first = rows[0], rows[1]
+        rd = float(first[hdr.index("dram__bytes_read.sum [Gbyte]")]) * 1e9
+        wr = float(first[hdr.index("dram__bytes_write.sum [Mbyte]")]) * 1e6
+        return (rd + wr) / (WIDTH * HEIGHT * 4), str(p.relative_to(ROOT))
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -351,8 +366,15 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = bytes_per_ray * agg["closestRays"] / (agg["closestMs"] * 1e-3) / 1e9 if agg["closestMs"] > 0 else 0.0
     kernel_ms = agg["closestMs"] + agg["shadeMs"] + agg["shadowMs"] + agg["generateMs"]
+    rays_per_launch = agg["closestRays"] / max(1, agg["closestLaunches"])
+    dram_per_ray, traffic_src = captured_traffic_per_ray()
     roofline = {"bound": "hbm", "kernel": "traceKernel<0> (BVH8 closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src, "traffic": None,
+                "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
+                # bytes per launch: DRAM bytes per ray of the committed ncu capture x this run's average rays per launch
+                "traffic": dram_per_ray * rays_per_launch if dram_per_ray else None,
+                "traffic_source": f"{traffic_src}: {dram_per_ray:.1f} DRAM B/ray (algorithmic {bytes_per_ray:.0f} B/ray: the tree top is served by L1/L2)"
+                if dram_per_ray else None,
+                "algorithmic_bytes_per_launch": bytes_per_ray * rays_per_launch,
                 "algorithmic_bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "tris_per_ray": n_tri,
                 "rays_per_launch": agg["closestRays"] / max(1, agg["closestLaunches"]),
                 "avg_launch_ms": agg["closestMs"] / max(1, agg["closestLaunches"]),

@@ -11,6 +11,7 @@
 //     CPU BVH, because Embree (the reference's ray caster) is not available.  This is BASELINE.md's tier B
 //     "reference shading + restated ray cast".
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <random>
@@ -37,8 +38,11 @@
 #include "MathLib/ColorSpace.h"
 #include "TextureLib/TextureFiltering.h"
 #include "TextureLib/TextureResource.h"
+#include "TextureLib/StbImage.h"
+#include "IoLib/Directory.h"
 #include "MathLib/ImportanceSampling.h"
 #include "IoLib/File.h"
+#include "IoLib/BinaryStreamSerializer.h"
 #include "Assets/AssetFileUtils.h"
 #include "VCMHashGrid.h"
 #include "VCMCommon.h"
@@ -96,6 +100,11 @@ void AssetFilePath(cpointer, uint64, cpointer, FilePathString& filepath) { filep
 namespace File {
 Error ReadWholeFile(cpointer, void**, uint64*) { return Error_("oracle harness: no file IO"); }
 }
+// TextureLib/TextureResource.cpp is linked for its Serialize(TextureResourceData&); its debug image dump is never called here
+namespace Directory {
+void EnsureDirectoryExists(const char*) {}
+}
+Error StbImageWrite(cpointer, uint, uint, uint, StbImageFormats, void*) { return Error_("oracle harness: no image IO"); }
 // Shading/SurfaceParameters.cpp is not linked (it needs Embree + the caches); these two accessors are the
 // only symbols of it the BSDF code uses.  They read column 1 of worldToTangent (SurfaceParameters.cpp:391).
 float3 GeometricNormal(const SurfaceParameters& surface) {
@@ -952,6 +961,59 @@ int ref_texture_sample(const SelasTextureDesc* t, size_t n, const float* uv2, in
         }
         st3(rgb3 + 3 * i, out);
     }
+    return 0;
+}
+
+// ---- baked blobs written by the reference's own serializer (IoLib/BinaryStreamSerializer.h: SerializeToBinary) -----------------
+// The product's host library reads these files (selas_b200/host: ReadImageBasedLightResource / ReadTextureResource); the baker itself
+// (BuildCore) is not buildable here, so the blobs are produced from in-memory resource data by the same Serialize() functions it calls.
+static int writeFile(const char* path, const uint8* data, uint64 size) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return 1;
+    size_t n = fwrite(data, 1, size, f);
+    fclose(f);
+    return n == size ? 0 : 1;
+}
+int ref_write_ibl_blob(const SelasIblDesc* I, const char* path) {
+    ImageBasedLightResourceData data;
+    memset(&data, 0, sizeof(data));
+    data.densityfunctions.width = I->width;
+    data.densityfunctions.height = I->height;
+    data.densityfunctions.marginalDensityFunction = const_cast<float*>(I->marginalDensityFunction);
+    data.densityfunctions.conditionalDensityFunctions = const_cast<float*>(I->conditionalDensityFunctions);
+    data.missWidth = I->missWidth;
+    data.missHeight = I->missHeight;
+    data.rotationRadians = I->rotationRadians;
+    data.exposureScale = I->exposureScale;
+    data.lightData = reinterpret_cast<float3*>(const_cast<float*>(I->lightData));
+    data.missData = reinterpret_cast<float3*>(const_cast<float*>(I->missData));
+    uint8* blob = nullptr;
+    Selas::uint blobSize = 0;
+    SerializeToBinary(data, blob, blobSize);
+    int rc = writeFile(path, blob, blobSize);
+    SelasAlignedFree(blob);
+    return rc;
+}
+int ref_write_texture_blob(const SelasTextureDesc* t, const char* path) {
+    TextureResourceData data;
+    memset(&data, 0, sizeof(data));
+    data.mipCount = 1;
+    data.dataSize = (uint32)(sizeof(float) * (t->format + 1) * t->width * t->height);
+    data.mipWidths[0] = t->width;
+    data.mipHeights[0] = t->height;
+    data.mipOffsets[0] = 0;
+    data.format = (TextureResourceData::TextureDataType)t->format;
+    data.texture = reinterpret_cast<uint8*>(const_cast<float*>(t->texels));
+    uint8* blob = nullptr;
+    Selas::uint blobSize = 0;
+    SerializeToBinary(data, blob, blobSize);
+    int rc = writeFile(path, blob, blobSize);
+    SelasAlignedFree(blob);
+    return rc;
+}
+unsigned long long ref_asset_version(const char* type) {
+    if (!strcmp(type, "IBL")) return ImageBasedLightResource::kDataVersion;
+    if (!strcmp(type, "Textures")) return TextureResource::kDataVersion;
     return 0;
 }
 

@@ -547,6 +547,103 @@ void ImageBasedLight::BuildDensityFunctions() {
     desc.exposureScale = exposureScale;
 }
 
+// ---- baked assets ---------------------------------------------------------------------------------------------------------
+std::string AssetFilePath(const char* root, const char* type, uint64_t version, const char* name) {
+    char buf[1024];
+    snprintf(buf, sizeof(buf), "%s_Assets/%s/%llu/%s.bin", root, type, (unsigned long long)version, name);
+    return std::string(buf);
+}
+
+namespace {
+Error readWholeFile(const char* filepath, std::vector<uint8_t>& data) {  // File::ReadWholeFile, IoLib/File.cpp
+    FILE* f = fopen(filepath, "rb");
+    if (!f) return Error_("Failed to open file: %s", filepath);
+    fseek(f, 0, SEEK_END);
+    long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    data.resize(size > 0 ? (size_t)size : 0);
+    size_t got = data.empty() ? 0 : fread(data.data(), 1, data.size(), f);
+    fclose(f);
+    if (got != data.size()) return Error_("Failed to read file: %s", filepath);
+    return Success_;
+}
+// a pointer field of an attached blob: the 8 bytes at `fieldOffset` hold the file offset of `size` bytes of data
+Error blobPointer(const std::vector<uint8_t>& blob, size_t fieldOffset, uint64_t size, const uint8_t** out, const char* what) {
+    uint64_t off = 0;
+    memcpy(&off, blob.data() + fieldOffset, 8);
+    if (off > blob.size() || size > blob.size() - off) return Error_("baked blob: %s lies outside the file (offset %llu, %llu bytes, file %zu)", what,
+                                                                      (unsigned long long)off, (unsigned long long)size, blob.size());
+    *out = blob.data() + off;
+    return Success_;
+}
+}  // namespace
+
+// ImageBasedLightResourceData as serialized (the struct itself, pointers = offsets; `uint` is 64 bits wide):
+//   0 width u64 | 8 height u64 | 16 marginal* | 24 conditional* | 32 missWidth u64 | 40 missHeight u64 | 48 rotation f32 | 52 exposure f32
+//   56 lightData* | 64 missData*                                                  (ImageBasedLightResource.h:16-35, .cpp:23-44)
+Error ReadImageBasedLightResource(const char* filepath, ImageBasedLight* ibl) {
+    std::vector<uint8_t> blob;
+    ReturnError_(readWholeFile(filepath, blob));
+    if (blob.size() < 72) return Error_("baked IBL blob %s: %zu bytes is shorter than the 72-byte resource header", filepath, blob.size());
+    uint64_t w, h, mw, mh;
+    memcpy(&w, blob.data() + 0, 8);
+    memcpy(&h, blob.data() + 8, 8);
+    memcpy(&mw, blob.data() + 32, 8);
+    memcpy(&mh, blob.data() + 40, 8);
+    if (w == 0 || h == 0 || w > 65536 || h > 65536 || mw > 65536 || mh > 65536) return Error_("baked IBL blob %s: implausible dimensions", filepath);
+    memcpy(&ibl->rotationRadians, blob.data() + 48, 4);
+    memcpy(&ibl->exposureScale, blob.data() + 52, 4);
+    const uint8_t *pm = nullptr, *pc = nullptr, *pl = nullptr, *ps = nullptr;
+    ReturnError_(blobPointer(blob, 16, 4 * h, &pm, "marginalDensityFunction"));
+    ReturnError_(blobPointer(blob, 24, 4 * w * h, &pc, "conditionalDensityFunctions"));
+    ReturnError_(blobPointer(blob, 56, 12 * w * h, &pl, "lightData"));
+    ReturnError_(blobPointer(blob, 64, 12 * mw * mh, &ps, "missData"));
+    ibl->width = (uint32_t)w; ibl->height = (uint32_t)h; ibl->missWidth = (uint32_t)mw; ibl->missHeight = (uint32_t)mh;
+    ibl->marginal.assign((const float*)pm, (const float*)pm + h);
+    ibl->conditional.assign((const float*)pc, (const float*)pc + w * h);
+    ibl->lightData.assign((const float*)pl, (const float*)pl + 3 * w * h);
+    ibl->missData.assign((const float*)ps, (const float*)ps + 3 * mw * mh);
+    memset(&ibl->desc, 0, sizeof(ibl->desc));
+    ibl->desc.width = ibl->width;
+    ibl->desc.height = ibl->height;
+    ibl->desc.marginalDensityFunction = ibl->marginal.data();
+    ibl->desc.conditionalDensityFunctions = ibl->conditional.data();
+    ibl->desc.lightData = ibl->lightData.data();
+    ibl->desc.missWidth = ibl->missWidth;
+    ibl->desc.missHeight = ibl->missHeight;
+    ibl->desc.missData = ibl->missData.data();
+    ibl->desc.rotationRadians = ibl->rotationRadians;
+    ibl->desc.exposureScale = ibl->exposureScale;
+    return Success_;
+}
+
+// TextureResourceData as serialized: 0 mipCount u32 | 4 dataSize u32 | 8 mipWidths[16] u32 | 72 mipHeights[16] u32 | 136 mipOffsets[16] u64
+//   264 format u32 | 268 pad u32 | 272 texture*                                   (TextureResource.h:15-39, .cpp:23-42)
+Error ReadTextureResource(const char* filepath, TextureResource* tex) {
+    std::vector<uint8_t> blob;
+    ReturnError_(readWholeFile(filepath, blob));
+    if (blob.size() < 280) return Error_("baked texture blob %s: %zu bytes is shorter than the 280-byte resource header", filepath, blob.size());
+    uint32_t dataSize;
+    memcpy(&tex->mipCount, blob.data() + 0, 4);
+    memcpy(&dataSize, blob.data() + 4, 4);
+    memcpy(tex->mipWidths, blob.data() + 8, 64);
+    memcpy(tex->mipHeights, blob.data() + 72, 64);
+    memcpy(tex->mipOffsets, blob.data() + 136, 128);
+    memcpy(&tex->format, blob.data() + 264, 4);
+    if (tex->mipCount == 0 || tex->mipCount > 16 || tex->format > SELAS_TEXTURE_FLOAT4) return Error_("baked texture blob %s: bad mipCount / format", filepath);
+    const uint8_t* pt = nullptr;
+    ReturnError_(blobPointer(blob, 272, dataSize, &pt, "texture"));
+    const uint64_t level0 = (uint64_t)tex->mipWidths[0] * tex->mipHeights[0] * (tex->format + 1) * 4;
+    if (tex->mipOffsets[0] > dataSize || level0 > dataSize - tex->mipOffsets[0]) return Error_("baked texture blob %s: level 0 lies outside the data", filepath);
+    tex->texture.assign(pt, pt + dataSize);
+    tex->desc.width = tex->mipWidths[0];
+    tex->desc.height = tex->mipHeights[0];
+    tex->desc.format = tex->format;
+    tex->desc.reserved = 0;
+    tex->desc.texels = reinterpret_cast<const float*>(tex->texture.data() + tex->mipOffsets[0]);
+    return Success_;
+}
+
 // identical to selas_b200/scenes.py:caustic_scene / sun_sky_ibl
 void MakeCausticScene(SceneResource* scene, ImageBasedLight* ibl, uint32_t sphereTheta, uint32_t spherePhi, uint32_t floorCells) {
     const double pi = 3.14159265358979323846;
@@ -685,6 +782,33 @@ int selas_host_import_material_json(const char* json, SelasMaterial* out, char* 
         return SELAS_ERR_FORMAT;
     }
     Selas::BuildMaterial(imp, *out);
+    return SELAS_OK;
+}
+int selas_host_read_ibl_blob(const char* path, uint32_t* info4, float* params2, float* marginal, float* conditional, float* light, float* miss,
+                             char* errorOut, int errorCapacity) {
+    Selas::ImageBasedLight ibl;
+    Selas::Error e = Selas::ReadImageBasedLightResource(path, &ibl);
+    if (e.Failed()) {
+        if (errorOut && errorCapacity > 0) snprintf(errorOut, errorCapacity, "%s", e.Message());
+        return SELAS_ERR_FORMAT;
+    }
+    if (info4) { info4[0] = ibl.width; info4[1] = ibl.height; info4[2] = ibl.missWidth; info4[3] = ibl.missHeight; }
+    if (params2) { params2[0] = ibl.rotationRadians; params2[1] = ibl.exposureScale; }
+    if (marginal) memcpy(marginal, ibl.marginal.data(), ibl.marginal.size() * 4);
+    if (conditional) memcpy(conditional, ibl.conditional.data(), ibl.conditional.size() * 4);
+    if (light) memcpy(light, ibl.lightData.data(), ibl.lightData.size() * 4);
+    if (miss) memcpy(miss, ibl.missData.data(), ibl.missData.size() * 4);
+    return SELAS_OK;
+}
+int selas_host_read_texture_blob(const char* path, uint32_t* info4, float* texels0, char* errorOut, int errorCapacity) {
+    Selas::TextureResource tex;
+    Selas::Error e = Selas::ReadTextureResource(path, &tex);
+    if (e.Failed()) {
+        if (errorOut && errorCapacity > 0) snprintf(errorOut, errorCapacity, "%s", e.Message());
+        return SELAS_ERR_FORMAT;
+    }
+    if (info4) { info4[0] = tex.mipCount; info4[1] = tex.format; info4[2] = tex.desc.width; info4[3] = tex.desc.height; }
+    if (texels0) memcpy(texels0, tex.desc.texels, (size_t)tex.desc.width * tex.desc.height * (tex.format + 1) * 4);
     return SELAS_OK;
 }
 int selas_host_write_hdr(const char* path, uint32_t width, uint32_t height, const float* rgb) {

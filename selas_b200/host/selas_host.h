@@ -117,6 +117,26 @@ struct ImageBasedLight {
     SelasIblDesc desc;
     void BuildDensityFunctions();
 };
+// ---- baked assets -----------------------------------------------------------------------------------
+// The reference's bake step writes every resource with SerializeToBinary (IoLib/BinaryStreamSerializer.h:14-32): the resource-data
+// struct with each pointer field replaced by the file offset of its data, followed by the pointed-to data; the run time attaches the
+// file in place (AttachToBinary, :34-44; CBinaryAttachSerializer, BinarySerializers.cpp:118-139).  These readers take such a file.
+// _Assets/<type>/<version>/<name>.bin  (AssetFileUtils::AssetFilePath, Assets/AssetFileUtils.cpp:128-135)
+std::string AssetFilePath(const char* root, const char* type, uint64_t version, const char* name);
+static const uint64_t kIblDataVersion = 1538087123ull;      // ImageBasedLightResource::kDataVersion, type "IBL"
+static const uint64_t kTextureDataVersion = 1534887410ull;  // TextureResource::kDataVersion, type "Textures"
+// ImageBasedLightResourceData blob (Serialize, SceneLib/ImageBasedLightResource.cpp:23-44) -> ImageBasedLight incl. its SelasIblDesc
+Error ReadImageBasedLightResource(const char* filepath, ImageBasedLight* ibl);
+// TextureResourceData blob (Serialize, TextureLib/TextureResource.cpp:23-42): every mip level is kept, `desc` describes level 0
+struct TextureResource {
+    uint32_t mipCount = 0, format = 0;
+    uint32_t mipWidths[16] = {0}, mipHeights[16] = {0};
+    uint64_t mipOffsets[16] = {0};
+    std::vector<uint8_t> texture;  // all levels, as in the file
+    SelasTextureDesc desc;         // level 0 (what the path samples: ForceNoMips_, SurfaceParameters.cpp:21)
+};
+Error ReadTextureResource(const char* filepath, TextureResource* texture);
+
 // BASELINE config 5: floor + glass sphere (Content/Materials/BSDF.json) + diffuse box under a sun-and-sky IBL.
 void MakeCausticScene(SceneResource* scene, ImageBasedLight* ibl, uint32_t sphereTheta = 96, uint32_t spherePhi = 192, uint32_t floorCells = 64);
 void SetupCausticCamera(uint32_t width, uint32_t height, RayCastCameraSettings& camera);
@@ -169,4 +189,9 @@ extern "C" {
 // C handles for tests (ctypes): material JSON -> 88-byte payload; Radiance writer.
 int selas_host_import_material_json(const char* json, SelasMaterial* out, char* errorOut, int errorCapacity);
 int selas_host_write_hdr(const char* path, uint32_t width, uint32_t height, const float* rgb);
+// Baked-asset readers for tests: info = {width, height, missWidth, missHeight}, params = {rotationRadians, exposureScale}; any array may be null.
+int selas_host_read_ibl_blob(const char* path, uint32_t* info4, float* params2, float* marginal, float* conditional, float* light, float* miss,
+                             char* errorOut, int errorCapacity);
+// info = {mipCount, format, width0, height0}; texels0 receives level 0 (width0 * height0 * (format + 1) floats) when not null
+int selas_host_read_texture_blob(const char* path, uint32_t* info4, float* texels0, char* errorOut, int errorCapacity);
 }

@@ -44,7 +44,51 @@ def ptex_lookups(rng, nfaces, n):
     return face, u, v
 
 
+def extra():
+    """Round-1 additions: VCM emission building blocks, texture lookups, a deferred-integrator image and two baked blobs, all from the
+    reference objects.  `python tests/golden/make_golden.py extra` writes only these."""
+    from selas_b200 import scenes
+    ref = oracle_binding.load_ref()
+    assert ref is not None, "build oracle/_ref first (make -C oracle) with /root/reference mounted"
+    rng = np.random.default_rng(301)
+    img = (rng.uniform(0, 1, size=(32, 64, 3)) ** 6 * 40.0).astype(np.float32)
+    img[5:8, 10:14] = 900.0
+    ibl = scenes.build_ibl(img, miss=rng.uniform(0, 2, size=(8, 16, 3)).astype(np.float32), rotation=0.7, exposure=1.0)
+    data = inputs.small_scene(with_attrs=False)
+    data.ibl = ibl
+    hs = ref.scene_create(data)
+    n = 2048
+    sphere = np.array([0.25, 0.5, -0.75, 6.5], np.float32)
+    u4, u2 = inputs.uniforms(302, n, 4), inputs.uniforms(303, n, 2)
+    wi = inputs.unit_vectors(rng, n)
+    emit_pdr, emit_pdfs = ref.ibl_emit(hs, sphere, u4)
+    direct = ref.ibl_direct(hs, u2)
+    rad_rgb, rad_pdfs = ref.ibl_radiance(hs, sphere, wi)
+    light_state = ref.vcm_generate_light(hs, sphere, 0.37, u4)
+    cam = ref.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 40, 30)
+    rs = capi.render_settings(40, 30, 16, max_path_length=64, layers=1, seed=8, cmj=(4, 4), integrator=capi.INTEGRATOR_DEFERRED)
+    deferred_film, dst = ref.render(hs, cam, rs, nthreads=1)
+    ref.scene_destroy(hs)
+    tex = rng.uniform(0, 1, size=(7, 13, 3)).astype(np.float32)
+    tex_uv = rng.uniform(-2.5, 3.5, size=(n, 2)).astype(np.float32)
+    np.savez_compressed(OUT / "vcm_texture.npz", light=ibl["light"], marginal=ibl["marginal"], conditional=ibl["conditional"], miss=ibl["miss"],
+                        rotation=np.float32(ibl["rotation"]), exposure_scale=np.float32(ibl["exposure_scale"]), sphere=sphere, u4=u4, u2=u2,
+                        wi=wi, emit_pdr=emit_pdr, emit_pdfs=emit_pdfs, direct=direct, rad_rgb=rad_rgb, rad_pdfs=rad_pdfs,
+                        light_state=light_state, deferred_film=deferred_film[0], deferred_rays=np.array([dst.closestRays, dst.occlusionRays]),
+                        tex=tex, tex_uv=tex_uv, tex_srgb=ref.texture_sample(tex, tex_uv, True), tex_linear=ref.texture_sample(tex, tex_uv, False))
+    # baked blobs (tests/test_host.py::_golden_assets)
+    brng = np.random.default_rng(71)
+    bimg = (brng.uniform(0, 1, size=(12, 24, 3)) ** 4 * 30.0).astype(np.float32)
+    bibl = scenes.build_ibl(bimg, miss=brng.uniform(0, 2, size=(3, 6, 3)).astype(np.float32), rotation=0.7, exposure=1.0)
+    btex = brng.uniform(0, 1, size=(5, 7, 3)).astype(np.float32)
+    ref.write_ibl_blob(bibl, OUT / "baked_ibl.bin")
+    ref.write_texture_blob(btex, OUT / "baked_texture.bin")
+    print("extra golden vectors written")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        return extra()
     ref = oracle_binding.load_ref()
     ptex = oracle_binding.load_ptexref()
     assert ref is not None and ptex is not None, "build oracle/_ref first (make -C oracle) with /root/reference mounted"
@@ -123,6 +167,7 @@ def main():
         look[f"{name}_rgb"] = ptex.eval(path, face, uu, vv)[:, :min(3, nchan)]
         print(name, path.stat().st_size, "bytes", ptex.info(path))
     np.savez_compressed(OUT / "ptex_lookups.npz", **look)
+    extra()
 
 
 if __name__ == "__main__":

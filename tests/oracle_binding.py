@@ -299,6 +299,29 @@ class Ref(ShadingOracle):
                                   _ptr(queries), _ptr(counts), _ptr(indices), C.c_uint32(max_per_query))
         return counts, indices
 
+    # baked blobs written by the reference's own SerializeToBinary (IoLib/BinaryStreamSerializer.h)
+    def write_ibl_blob(self, ibl, path):
+        desc = capi.IblDesc()
+        keep = [np.ascontiguousarray(ibl[k], np.float32) for k in ("marginal", "conditional", "light", "miss")]
+        desc.height, desc.width = keep[2].shape[:2]
+        desc.missHeight, desc.missWidth = keep[3].shape[:2]
+        desc.marginalDensityFunction, desc.conditionalDensityFunctions = keep[0].ctypes.data, keep[1].ctypes.data
+        desc.lightData, desc.missData = keep[2].ctypes.data, keep[3].ctypes.data
+        desc.rotationRadians, desc.exposureScale = ibl["rotation"], ibl["exposure_scale"]
+        rc = self.fn("write_ibl_blob")(C.byref(desc), str(path).encode())
+        assert rc == 0, rc
+
+    def write_texture_blob(self, texture, path):
+        a = capi.texture_array(texture)
+        td = capi.texture_desc(a)
+        rc = self.fn("write_texture_blob")(C.byref(td), str(path).encode())
+        assert rc == 0, rc
+
+    def asset_version(self, type_name):
+        f = self.lib.ref_asset_version
+        f.restype = C.c_ulonglong
+        return int(f(type_name.encode()))
+
     def vcm_generate_light(self, h, sphere4, vc_weight, u4):
         """VCMCommon::GenerateLightSample: rows of 13 floats (position, direction, throughput, dVCM, dVC, dVM, length|area<<8)."""
         u4 = _f32(u4).reshape(-1, 4)

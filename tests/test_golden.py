@@ -83,3 +83,31 @@ def test_record_layouts():
     assert capi.C.sizeof(capi.RenderSettings) == 52 and capi.C.sizeof(capi.RenderStats) == 96
     assert capi.C.sizeof(capi.VcmSettings) == 56 and capi.C.sizeof(capi.VcmStats) == 104 and capi.VCM_VERTEX_DTYPE.itemsize == 96
     assert capi.C.sizeof(capi.MeshDesc) == 80 and capi.C.sizeof(capi.TextureDesc) == 24 and capi.C.sizeof(capi.SceneDesc) == 104 and capi.C.sizeof(capi.IblDesc) == 56
+
+
+def test_vcm_texture_deferred_golden(oracle):
+    """Round-1 additions (make_golden.py extra): EmitIblLightSample / DirectIblLightSample / IblCalculateRadiance, the texture lookup
+    and a DeferredPathTracer image, all produced by the reference objects."""
+    from tests import inputs
+
+    z = np.load(G / "vcm_texture.npz")
+    data = inputs.small_scene(with_attrs=False)
+    data.ibl = dict(light=z["light"], marginal=z["marginal"], conditional=z["conditional"], miss=z["miss"], rotation=float(z["rotation"]),
+                    exposure_scale=float(z["exposure_scale"]))
+    hs = oracle.scene_create(data)
+    pdr, pdfs = oracle.ibl_emit(hs, z["sphere"], z["u4"])
+    np.testing.assert_array_equal(_bits(pdr), _bits(z["emit_pdr"]))
+    np.testing.assert_array_equal(_bits(pdfs), _bits(z["emit_pdfs"]))
+    assert oracle.ibl_direct(hs, z["u2"]).tobytes() == z["direct"].tobytes()
+    rgb, rp = oracle.ibl_radiance(hs, z["sphere"], z["wi"])
+    np.testing.assert_array_equal(_bits(rgb), _bits(z["rad_rgb"]))
+    np.testing.assert_array_equal(_bits(rp), _bits(z["rad_pdfs"]))
+    cam = oracle.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 40, 30)
+    rs = capi.render_settings(40, 30, 16, max_path_length=64, layers=1, seed=8, cmj=(4, 4), integrator=capi.INTEGRATOR_DEFERRED)
+    film, st = oracle.render(hs, cam, rs, nthreads=1)
+    oracle.scene_destroy(hs)
+    assert [st.closestRays, st.occlusionRays] == list(z["deferred_rays"])
+    fin = np.isfinite(z["deferred_film"]).all(axis=2)
+    np.testing.assert_allclose(film[0][fin], z["deferred_film"][fin], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(_bits(oracle.texture_sample(z["tex"], z["tex_uv"], True)), _bits(z["tex_srgb"]))
+    np.testing.assert_array_equal(_bits(oracle.texture_sample(z["tex"], z["tex_uv"], False)), _bits(z["tex_linear"]))

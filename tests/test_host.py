@@ -123,3 +123,71 @@ def test_selas_render_deferred(ctx, host, tmp_path):
     m = want.max(axis=2, keepdims=True)
     assert (np.abs(got - want) <= m / 100.0 + 1e-4).mean() > 0.995
     sc.close()
+
+
+# ---- baked assets: blobs written by the reference's own serializer, read by the host library -------------------
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def _read_ibl(host, path):
+    info, params = (C.c_uint32 * 4)(), (C.c_float * 2)()
+    err = C.create_string_buffer(256)
+    assert host.selas_host_read_ibl_blob(str(path).encode(), info, params, None, None, None, None, err, 256) == 0, err.value
+    w, h, mw, mh = list(info)
+    marg, cond = np.zeros(h, np.float32), np.zeros((h, w), np.float32)
+    light, miss = np.zeros((h, w, 3), np.float32), np.zeros((mh, mw, 3), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert host.selas_host_read_ibl_blob(str(path).encode(), info, params, p(marg), p(cond), p(light), p(miss), err, 256) == 0, err.value
+    return dict(marginal=marg, conditional=cond, light=light, miss=miss, rotation=params[0], exposure_scale=params[1])
+
+
+def _read_texture(host, path):
+    info = (C.c_uint32 * 4)()
+    err = C.create_string_buffer(256)
+    assert host.selas_host_read_texture_blob(str(path).encode(), info, None, err, 256) == 0, err.value
+    mips, fmt, w, h = list(info)
+    tex = np.zeros((h, w, fmt + 1), np.float32)
+    assert host.selas_host_read_texture_blob(str(path).encode(), info, tex.ctypes.data_as(C.c_void_p), err, 256) == 0
+    return mips, tex
+
+
+def _golden_assets():
+    rng = np.random.default_rng(71)
+    img = (rng.uniform(0, 1, size=(12, 24, 3)) ** 4 * 30.0).astype(np.float32)
+    ibl = scenes.build_ibl(img, miss=rng.uniform(0, 2, size=(3, 6, 3)).astype(np.float32), rotation=0.7, exposure=1.0)
+    tex = rng.uniform(0, 1, size=(5, 7, 3)).astype(np.float32)
+    return ibl, tex
+
+
+def test_baked_blobs_from_the_reference_serializer(host, ref, tmp_path):
+    """Written here by the reference's SerializeToBinary, read back by ReadImageBasedLightResource / ReadTextureResource."""
+    ibl, tex = _golden_assets()
+    ref.write_ibl_blob(ibl, tmp_path / "ibl.bin")
+    ref.write_texture_blob(tex, tmp_path / "tex.bin")
+    got = _read_ibl(host, tmp_path / "ibl.bin")
+    for k in ("marginal", "conditional", "light", "miss"):
+        np.testing.assert_array_equal(got[k], ibl[k], err_msg=k)
+    assert got["rotation"] == np.float32(ibl["rotation"]) and got["exposure_scale"] == np.float32(ibl["exposure_scale"])
+    mips, t = _read_texture(host, tmp_path / "tex.bin")
+    assert mips == 1
+    np.testing.assert_array_equal(t, tex)
+    # the committed golden blobs are these very files
+    assert (tmp_path / "ibl.bin").read_bytes() == (GOLDEN / "baked_ibl.bin").read_bytes()
+    assert (tmp_path / "tex.bin").read_bytes() == (GOLDEN / "baked_texture.bin").read_bytes()
+    assert ref.asset_version("IBL") == 1538087123 and ref.asset_version("Textures") == 1534887410
+
+
+def test_baked_blobs_golden(host, tmp_path):
+    """The committed blobs (made by tests/golden/make_golden.py from the reference serializer) without the reference at hand."""
+    ibl, tex = _golden_assets()
+    got = _read_ibl(host, GOLDEN / "baked_ibl.bin")
+    for k in ("marginal", "conditional", "light", "miss"):
+        np.testing.assert_array_equal(got[k], ibl[k], err_msg=k)
+    mips, t = _read_texture(host, GOLDEN / "baked_texture.bin")
+    np.testing.assert_array_equal(t, tex)
+    # malformed files are reported, not read
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes((GOLDEN / "baked_ibl.bin").read_bytes()[:100])
+    err = C.create_string_buffer(256)
+    assert host.selas_host_read_ibl_blob(str(bad).encode(), None, None, None, None, None, None, err, 256) == 4 and b"outside the file" in err.value
+    assert host.selas_host_read_texture_blob(str(tmp_path / "missing.bin").encode(), None, None, err, 256) == 4 and b"Failed to open" in err.value
