@@ -539,7 +539,70 @@ __global__ void __launch_bounds__(256) vcmConnectGatherKernel(VcmParams prm, uin
     for (uint32_t k = 0; k < count; ++k) pairs[base + k] = make_uint2(i, start + k);
 }
 
-// ConnectPathVertices (VCM.cpp:295-359): one thread per gathered (camera vertex, light vertex) pair; the pair count lives in device memory
+// ConnectPathVertices (VCM.cpp:295-359) for camera vertex i and light vertex li.  Returns false when the connection carries nothing;
+// otherwise fills the shadow ray (VcOcclusionRay, VCM.cpp:95-120) and its payload {contribution, pixel}.
+struct ShadowOut {
+    V3 o, d;
+    float tnear, tfar;
+    float4 payload;
+};
+SELAS_D bool connectPathVertices(const SceneGpu& sc, const VcmParams& prm, uint32_t i, uint32_t li, const SelasRay* rays, const SelasHit* hits,
+                                 const float4* thrIdx, const float4* vertexMis, const float* ptexRgb, const float4* lvA, const float4* lvB,
+                                 const SelasRay* lvRay, const SelasHit* lvHit, ShadowOut& out) {
+    CameraVertex cv;
+    loadCameraVertex(sc, i, rays, hits, thrIdx, vertexMis, ptexRgb, cv);
+    float4 a = __ldg(lvA + li), b = __ldg(lvB + li);
+    const float4* lrp = reinterpret_cast<const float4*>(lvRay + li);
+    float4 lr0 = __ldg(lrp), lr1 = __ldg(lrp + 1);
+    const uint4* lhp = reinterpret_cast<const uint4*>(lvHit + li);
+    uint4 lh0 = __ldg(lhp), lh1 = __ldg(lhp + 1);
+    Surface ls;  // CalculateSurfaceParams(context, &lightVertex.hit, lightSurface), :314-317
+    V3 lo = v3(lr0.x, lr0.y, lr0.z), ld = v3(lr1.x, lr1.y, lr1.z);
+    surfaceFromHit(sc, lo, ld, __uint_as_float(lh0.x), __uint_as_float(lh0.y), __uint_as_float(lh0.z), lh0.w, lh1.x, lh1.y, nullptr, ls);
+    V3 direction = ls.position - cv.s.position;
+    float distanceSquared = dot(direction, direction);
+    float distance = sqrtf(distanceSquared);
+    direction = (1.0f / distance) * direction;
+    float cFwd = 0.f, cRev = 0.f;
+    V3 cameraBsdf = evaluateBsdf(cv.s, cv.frame, cv.view, direction, cFwd, cRev);
+    if (isZero3(cameraBsdf)) return false;
+    DisneyFrame lframe;
+    makeDisneyFrame(ls, ls.shader == SELAS_SHADER_DISNEY_THIN, lframe);
+    float lFwd = 0.f, lRev = 0.f;
+    V3 lightView = -ld;
+    V3 lightBsdf = evaluateBsdf(ls, lframe, -direction, lightView, lFwd, lRev);
+    if (isZero3(lightBsdf)) return false;
+    float cosThetaCamera = fabsf(dot(direction, shadingNormal(cv.s)));
+    float cosThetaLight = fabsf(dot(-direction, shadingNormal(ls)));
+    float geometryTerm = cosThetaLight * cosThetaCamera / distanceSquared;
+    if (geometryTerm < 0.0f) return false;
+    float cameraContProb = continuationProbability(cv.s);
+    cFwd *= cameraContProb;
+    cRev *= cameraContProb;
+    float lightContProb = continuationProbability(ls);
+    lFwd *= lightContProb;
+    lRev *= lightContProb;
+    float cameraBsdfPdfA = cFwd * fabsf(cosThetaLight) / distanceSquared;
+    float lightBsdfPdfA = lFwd * fabsf(cosThetaCamera) / distanceSquared;
+    float lightWeight = cameraBsdfPdfA * (prm.vmWeight + b.x + b.y * lRev);
+    float cameraWeight = lightBsdfPdfA * (prm.vmWeight + cv.dVCM + cv.dVC * cRev);
+    float misWeight = 1.0f / (lightWeight + 1.0f + cameraWeight);
+    V3 pc = misWeight * geometryTerm * cameraBsdf * lightBsdf;
+    if (isZero3(pc)) return false;
+    V3 c = cv.throughput * v3(a.x, a.y, a.z) * pc;  // :628-629
+    if ((prm.flags & SELAS_VCM_SKIP_NONFINITE) && !finite3(c)) return false;
+    V3 nrm = shadingNormal(cv.s);
+    float directionOffset = dot(direction, nrm) < 0.0f ? -1.0f : 1.0f;
+    float biasDistance = directionOffset * cv.s.error * 0.1f;
+    out.o = cv.s.position + biasDistance * nrm;
+    out.d = direction;
+    out.tnear = cv.s.error;
+    out.tfar = distance - 16.0f * fabsf(biasDistance);
+    out.payload = make_float4(c.x, c.y, c.z, __uint_as_float(cv.index));
+    return true;
+}
+
+// One thread per gathered (camera vertex, light vertex) pair; the pair count lives in device memory, the grid strides over it.
 __global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams prm, const uint32_t* __restrict__ pairCountPtr,
                                                         const uint2* __restrict__ pairs, const SelasRay* __restrict__ rays,
                                                         const SelasHit* __restrict__ hits, const float4* __restrict__ thrIdx,
@@ -549,83 +612,20 @@ __global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams p
                                                         SelasRay* __restrict__ shadowRays, float4* __restrict__ shadowPayload,
                                                         uint32_t* __restrict__ counters) {
     const uint32_t pairCount = __ldg(pairCountPtr);
-    // whole warps iterate together (the appends are warp-collective)
+    // whole warps iterate together: the queue append is warp-collective
     for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < pairCount; t0 += gridDim.x * blockDim.x) {
-    const uint32_t t = t0 + threadIdx.x;
-    bool wantShadow = false;
-    V3 shO = v3(0.f), shD = v3(0.f);
-    float shNear = 0.f, shFar = 0.f;
-    float4 shPayload = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < pairCount) {
-        const uint2 pr = __ldg(pairs + t);
-        const uint32_t i = pr.x, li = pr.y;
-        {
-            {
-                CameraVertex cv;
-                loadCameraVertex(sc, i, rays, hits, thrIdx, vertexMis, ptexRgb, cv);
-                float4 a = __ldg(lvA + li), b = __ldg(lvB + li);
-                const float4* lrp = reinterpret_cast<const float4*>(lvRay + li);
-                float4 lr0 = __ldg(lrp), lr1 = __ldg(lrp + 1);
-                const uint4* lhp = reinterpret_cast<const uint4*>(lvHit + li);
-                uint4 lh0 = __ldg(lhp), lh1 = __ldg(lhp + 1);
-                Surface ls;  // CalculateSurfaceParams(context, &lightVertex.hit, lightSurface), :314-317
-                V3 lo = v3(lr0.x, lr0.y, lr0.z), ld = v3(lr1.x, lr1.y, lr1.z);
-                surfaceFromHit(sc, lo, ld, __uint_as_float(lh0.x), __uint_as_float(lh0.y), __uint_as_float(lh0.z), lh0.w, lh1.x, lh1.y, nullptr, ls);
-                V3 direction = ls.position - cv.s.position;
-                float distanceSquared = dot(direction, direction);
-                float distance = sqrtf(distanceSquared);
-                direction = (1.0f / distance) * direction;
-                float cFwd = 0.f, cRev = 0.f;
-                V3 cameraBsdf = evaluateBsdf(cv.s, cv.frame, cv.view, direction, cFwd, cRev);
-                if (!isZero3(cameraBsdf)) {
-                    DisneyFrame lframe;
-                    makeDisneyFrame(ls, ls.shader == SELAS_SHADER_DISNEY_THIN, lframe);
-                    float lFwd = 0.f, lRev = 0.f;
-                    V3 lightView = -ld;
-                    V3 lightBsdf = evaluateBsdf(ls, lframe, -direction, lightView, lFwd, lRev);
-                    if (!isZero3(lightBsdf)) {
-                        float cosThetaCamera = fabsf(dot(direction, shadingNormal(cv.s)));
-                        float cosThetaLight = fabsf(dot(-direction, shadingNormal(ls)));
-                        float geometryTerm = cosThetaLight * cosThetaCamera / distanceSquared;
-                        if (!(geometryTerm < 0.0f)) {
-                            float cameraContProb = continuationProbability(cv.s);
-                            cFwd *= cameraContProb;
-                            cRev *= cameraContProb;
-                            float lightContProb = continuationProbability(ls);
-                            lFwd *= lightContProb;
-                            lRev *= lightContProb;
-                            float cameraBsdfPdfA = cFwd * fabsf(cosThetaLight) / distanceSquared;
-                            float lightBsdfPdfA = lFwd * fabsf(cosThetaCamera) / distanceSquared;
-                            float lightWeight = cameraBsdfPdfA * (prm.vmWeight + b.x + b.y * lRev);
-                            float cameraWeight = lightBsdfPdfA * (prm.vmWeight + cv.dVCM + cv.dVC * cRev);
-                            float misWeight = 1.0f / (lightWeight + 1.0f + cameraWeight);
-                            V3 pc = misWeight * geometryTerm * cameraBsdf * lightBsdf;
-                            if (!isZero3(pc)) {
-                                V3 c = cv.throughput * v3(a.x, a.y, a.z) * pc;  // :628-629
-                                if (!((prm.flags & SELAS_VCM_SKIP_NONFINITE) && !finite3(c))) {
-                                    // VcOcclusionRay, VCM.cpp:95-120
-                                    V3 nrm = shadingNormal(cv.s);
-                                    float directionOffset = dot(direction, nrm) < 0.0f ? -1.0f : 1.0f;
-                                    float biasDistance = directionOffset * cv.s.error * 0.1f;
-                                    shO = cv.s.position + biasDistance * nrm;
-                                    shD = direction;
-                                    shNear = cv.s.error;
-                                    shFar = distance - 16.0f * fabsf(biasDistance);
-                                    shPayload = make_float4(c.x, c.y, c.z, __uint_as_float(cv.index));
-                                    wantShadow = true;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
+        const uint32_t t = t0 + threadIdx.x;
+        ShadowOut sh;
+        bool wantShadow = false;
+        if (t < pairCount) {
+            const uint2 pr = __ldg(pairs + t);
+            wantShadow = connectPathVertices(sc, prm, pr.x, pr.y, rays, hits, thrIdx, vertexMis, ptexRgb, lvA, lvB, lvRay, lvHit, sh);
         }
-    }
-    uint32_t slotS = warpAppend(wantShadow, counters + 1);
-    if (wantShadow) {
-        storeRay(shadowRays, slotS, shO, shNear, shD, shFar);
-        shadowPayload[slotS] = shPayload;
-    }
+        uint32_t slotS = warpAppend(wantShadow, counters + 1);
+        if (wantShadow) {
+            storeRay(shadowRays, slotS, sh.o, sh.tnear, sh.d, sh.tfar);
+            shadowPayload[slotS] = sh.payload;
+        }
     }
 }
 
@@ -795,64 +795,68 @@ __global__ void __launch_bounds__(kGatherWarps * 32) vcmMergeGatherKernel(HashGr
     if (lane == 0 && candidates) atomicAdd(statCounters + 0, candidates);
 }
 
+// MergeVertices (VCM.cpp:362-409) for one accepted (camera vertex i, light vertex pi) pair: the film contribution
+// throughput * vmNormalization * misWeight * bsdf * lightVertex.throughput (:405, :649-650), or zero.
+SELAS_D V3 mergeVertices(const SceneGpu& sc, const VcmParams& prm, uint32_t i, uint32_t pi, const SelasRay* rays, const SelasHit* hits,
+                         const float4* thrIdx, const float4* vertexMis, const float* ptexRgb, const float4* lvA, const float4* lvB,
+                         const SelasRay* lvRay) {
+    float4 a = __ldg(lvA + pi);
+    uint32_t bits = __float_as_uint(a.w);
+    uint32_t lvLength = (bits >> 26) & 31u;
+    uint32_t cameraLength = __float_as_uint(__ldg(vertexMis + i).w);
+    if (cameraLength + lvLength > prm.maxPathLength) return v3(0.0f);  // :371-373
+    CameraVertex cv;
+    loadCameraVertex(sc, i, rays, hits, thrIdx, vertexMis, ptexRgb, cv);
+    if (((cv.s.materialFlags & SELAS_MAT_TRANSPARENT) != 0) != ((bits & 0x80000000u) != 0)) return v3(0.0f);  // :380-383
+    float4 lb = __ldg(lvB + pi);
+    float4 ld = __ldg(reinterpret_cast<const float4*>(lvRay + pi) + 1);
+    V3 lightView = v3(-ld.x, -ld.y, -ld.z);
+    float fwd = 0.f, rev = 0.f;
+    V3 bsdf = evaluateBsdf(cv.s, cv.frame, cv.view, lightView, fwd, rev);
+    if (isZero3(bsdf)) return v3(0.0f);
+    fwd *= continuationProbability(cv.s);
+    rev *= lb.w;
+    float lightWeight = lb.x * prm.vcWeight + lb.z * fwd;
+    float cameraWeight = cv.dVCM * prm.vcWeight + cv.dVM * rev;
+    float misWeight = 1.0f / (lightWeight + 1.0f + cameraWeight);
+    V3 c = cv.throughput * prm.vmNormalization * (misWeight * bsdf * v3(a.x, a.y, a.z));
+    if ((prm.flags & SELAS_VCM_SKIP_NONFINITE) && !finite3(c)) return v3(0.0f);
+    return c;
+}
+
 __global__ void __launch_bounds__(128) vcmMergeEvalKernel(SceneGpu sc, VcmParams prm, const uint32_t* __restrict__ pairCountPtr, uint32_t pairCapacity,
-                                                          const uint2* __restrict__ pairs,
-                                                          const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
-                                                          const float4* __restrict__ thrIdx, const float4* __restrict__ vertexMis,
-                                                          const float* __restrict__ ptexRgb, const float4* __restrict__ lvA,
-                                                          const float4* __restrict__ lvB, const SelasRay* __restrict__ lvRay,
-                                                          float* __restrict__ film) {
+                                                          const uint2* __restrict__ pairs, const SelasRay* __restrict__ rays,
+                                                          const SelasHit* __restrict__ hits, const float4* __restrict__ thrIdx,
+                                                          const float4* __restrict__ vertexMis, const float* __restrict__ ptexRgb,
+                                                          const float4* __restrict__ lvA, const float4* __restrict__ lvB,
+                                                          const SelasRay* __restrict__ lvRay, float* __restrict__ film) {
     const uint32_t pairCount = __ldg(pairCountPtr);
     if (pairCount > pairCapacity) return;  // the list overflowed: the host runs the serial kernel for this bounce instead
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t p0 = blockIdx.x * blockDim.x; p0 < pairCount; p0 += gridDim.x * blockDim.x) {
-    const uint32_t p = p0 + threadIdx.x;
-    V3 c = v3(0.0f);
-    uint32_t key = 0xFFFFFFFFu;  // film pixel of this pair's camera vertex
-    if (p < pairCount) {
-        const uint2 pr = __ldg(pairs + p);
-        const uint32_t i = pr.x, pi = pr.y;
-        key = __float_as_uint(__ldg(thrIdx + i).w) & kIndexMask;
-        float4 a = __ldg(lvA + pi);
-        uint32_t bits = __float_as_uint(a.w);
-        uint32_t lvLength = (bits >> 26) & 31u;
-        uint32_t cameraLength = __float_as_uint(__ldg(vertexMis + i).w);
-        if (cameraLength + lvLength <= prm.maxPathLength) {  // VCM.cpp:371-373
-            CameraVertex cv;
-            loadCameraVertex(sc, i, rays, hits, thrIdx, vertexMis, ptexRgb, cv);
-            if (((cv.s.materialFlags & SELAS_MAT_TRANSPARENT) != 0) == ((bits & 0x80000000u) != 0)) {  // :380-383
-                float4 lb = __ldg(lvB + pi);
-                float4 ld = __ldg(reinterpret_cast<const float4*>(lvRay + pi) + 1);
-                V3 lightView = v3(-ld.x, -ld.y, -ld.z);
-                float fwd = 0.f, rev = 0.f;
-                V3 bsdf = evaluateBsdf(cv.s, cv.frame, cv.view, lightView, fwd, rev);
-                if (!isZero3(bsdf)) {
-                    fwd *= continuationProbability(cv.s);
-                    rev *= lb.w;
-                    float lightWeight = lb.x * prm.vcWeight + lb.z * fwd;
-                    float cameraWeight = cv.dVCM * prm.vcWeight + cv.dVM * rev;
-                    float misWeight = 1.0f / (lightWeight + 1.0f + cameraWeight);
-                    c = cv.throughput * prm.vmNormalization * (misWeight * bsdf * v3(a.x, a.y, a.z));
-                    if ((prm.flags & SELAS_VCM_SKIP_NONFINITE) && !finite3(c)) c = v3(0.0f);
-                }
+        const uint32_t p = p0 + threadIdx.x;
+        V3 c = v3(0.0f);
+        uint32_t key = 0xFFFFFFFFu;  // film pixel of this pair's camera vertex
+        if (p < pairCount) {
+            const uint2 pr = __ldg(pairs + p);
+            key = __float_as_uint(__ldg(thrIdx + pr.x).w) & kIndexMask;
+            c = mergeVertices(sc, prm, pr.x, pr.y, rays, hits, thrIdx, vertexMis, ptexRgb, lvA, lvB, lvRay);
+        }
+        // segmented reduction over runs of equal pixel (pairs of one camera vertex are mostly contiguous), one atomic per run.  Runs
+        // are numbered by their head so that the same pixel appearing in two separate runs of a warp is not merged across the gap.
+        uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = lane == 0 || prev != key;
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const uint32_t run = __popc(heads & ((2u << lane) - 1u));
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            float tx = __shfl_down_sync(0xffffffffu, c.x, o), ty = __shfl_down_sync(0xffffffffu, c.y, o), tz = __shfl_down_sync(0xffffffffu, c.z, o);
+            uint32_t r = __shfl_down_sync(0xffffffffu, run, o);
+            if (lane + o < 32 && r == run) {
+                c.x += tx; c.y += ty; c.z += tz;
             }
         }
-    }
-    // segmented reduction over runs of equal pixel (pairs of one camera vertex are mostly contiguous), one atomic per run.  Runs are
-    // numbered by their head so that the same pixel appearing in two separate runs of a warp is not merged across the gap.
-    uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || prev != key;
-    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    const uint32_t run = __popc(heads & ((2u << lane) - 1u));
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        float tx = __shfl_down_sync(0xffffffffu, c.x, o), ty = __shfl_down_sync(0xffffffffu, c.y, o), tz = __shfl_down_sync(0xffffffffu, c.z, o);
-        uint32_t r = __shfl_down_sync(0xffffffffu, run, o);
-        if (lane + o < 32 && r == run) {
-            c.x += tx; c.y += ty; c.z += tz;
-        }
-    }
-    if (head && key != 0xFFFFFFFFu && !isZero3(c)) filmAdd(film, key, c);
+        if (head && key != 0xFFFFFFFFu && !isZero3(c)) filmAdd(film, key, c);
     }
 }
 
