@@ -154,3 +154,35 @@ def test_vcm_errors(ctx):
     f, st = scene.render_vcm(cam, capi.vcm_settings(32, 32, 1, scenes.bounding_sphere(data), max_path_length=3))
     assert st.lightVertices == 0 and np.isfinite(f).all() and f.sum() > 0
     scene.close()
+
+
+def test_vcm_degenerate_inputs(ctx, oracle):
+    """No geometry at all (every path escapes: the image is the IBL seen through ConnectToSkyLight with pathLength 1), a 1x1 and a
+    ragged 33x7 frame (queue sizes that are not multiples of the warp / tile sizes), zero iterations."""
+    ibl = scenes.sun_sky_ibl(64, 32)
+    empty = capi.SceneData([], np.array([scenes.material()]), None, None, background=(0, 0, 0, 0), ibl=ibl)
+    sc, hs = capi.Scene(ctx, empty), oracle.scene_create(empty)
+    cam = scenes.caustic_camera(33, 7)
+    vs = capi.vcm_settings(33, 7, 2, (0.0, 0.0, 0.0, 5.0), seed=2)
+    g, gst = sc.render_vcm(cam, vs)
+    o, ost = oracle.render_vcm(hs, cam, vs, nthreads=2)
+    assert gst.lightVertices == ost.lightVertices == 0 and gst.occlusionRays == 0 and gst.mergesAccepted == 0
+    np.testing.assert_allclose(g, o, rtol=1e-6, atol=1e-7)
+    assert g.min() > 0  # sky everywhere
+    oracle.scene_destroy(hs)
+    sc.close()
+    data = scenes.caustic_scene(sphere_res=(8, 16), floor_cells=2, ibl_size=(64, 32))
+    sc, hs = capi.Scene(ctx, data), oracle.scene_create(data)
+    sphere = scenes.bounding_sphere(data)
+    for w, h in ((1, 1), (33, 7)):
+        cam = scenes.caustic_camera(w, h)
+        vs = capi.vcm_settings(w, h, 3, sphere, seed=5)
+        g, gst = sc.render_vcm(cam, vs)
+        o, ost = oracle.render_vcm(hs, cam, vs, nthreads=1)
+        assert np.isfinite(g).all() and gst.lightPaths == 3 * w * h
+        assert abs(int(gst.lightVertices) - int(ost.lightVertices)) <= 1
+        np.testing.assert_allclose(g.sum(), o.sum(), rtol=2e-2, atol=1e-3)
+    z, zst = sc.render_vcm(scenes.caustic_camera(8, 8), capi.vcm_settings(8, 8, 0, sphere))
+    assert not z.any() and zst.lightPaths == 0
+    oracle.scene_destroy(hs)
+    sc.close()
