@@ -28,6 +28,8 @@
 #include "Shading/VolumetricScattering.h"
 #include "Shading/Scattering.h"
 #include "SceneLib/SceneResource.h"
+#include "SceneLib/SubsceneResource.h"
+#include "SceneLib/ModelResource.h"
 #include "SceneLib/ImageBasedLightResource.h"
 #include "GeometryLib/Camera.h"
 #include "GeometryLib/Ray.h"
@@ -1014,7 +1016,114 @@ int ref_write_texture_blob(const SelasTextureDesc* t, const char* path) {
 unsigned long long ref_asset_version(const char* type) {
     if (!strcmp(type, "IBL")) return ImageBasedLightResource::kDataVersion;
     if (!strcmp(type, "Textures")) return TextureResource::kDataVersion;
+    if (!strcmp(type, "SceneResource")) return SceneResource::kDataVersion;
+    if (!strcmp(type, "SubsceneResource")) return SubsceneResource::kDataVersion;
+    if (!strcmp(type, "ModelResource") || !strcmp(type, "ModelGeometryResource")) return ModelResource::kDataVersion;
     return 0;
+}
+
+// ---- baked scene / subscene / model blobs -----------------------------------------------------------------------------------
+// Inputs are raw arrays in the reference's own element layouts (MeshMetaData 92 B, MaterialResourceData 600 B, Instance 72 B,
+// CameraSettings 176 B, SceneLight 64 B, SceneLightSetRange 8 B, FilePathString 512 B); they are copied into the reference's CArrays and
+// written with SerializeToBinary through the reference's Serialize(SceneResourceData&) / (SubsceneResourceData&) / (ModelResourceData&)
+// / (ModelGeometryData&) (SceneLib/*.cpp, linked unmodified).
+}  // extern "C"
+template <typename T>
+static void fillArray(CArray<T>& a, const void* src, uint64 count) {
+    a.Resize(count);
+    if (count) memcpy(a.DataPointer(), src, count * sizeof(T));
+}
+template <int N>
+static void copyFixed(FixedString<N>& dst, const char* src) {  // FixedString::Copy goes through StringUtil, which is not built here
+    memset(dst.str, 0, N);
+    strncpy(dst.str, src, N - 1);
+}
+template <typename T>
+static int writeBlob(T& data, const char* path) {
+    uint8* blob = nullptr;
+    Selas::uint blobSize = 0;
+    SerializeToBinary(data, blob, blobSize);
+    int rc = writeFile(path, blob, blobSize);
+    SelasAlignedFree(blob);
+    return rc;
+}
+static_assert(sizeof(MeshMetaData) == 92 && sizeof(MaterialResourceData) == 600 && sizeof(Instance) == 72 && sizeof(CameraSettings) == 176,
+              "reference element layouts");
+extern "C" {
+
+int ref_write_model_blobs(const char* dataPath, const char* geomPath, const float* aabb6, uint32_t totalVertexCount, const uint32_t* indices,
+                          uint64_t indexCount, const float* positions, const float* normals, const float* tangents, const float* uvs,
+                          const void* meshes92, uint32_t meshCount, const void* materials600, const uint32_t* materialHashes,
+                          uint32_t materialCount) {
+    ModelResourceData* data = new ModelResourceData();
+    memset(&data->aaBox, 0, sizeof(data->aaBox));
+    data->aaBox.min = float3(aabb6[0], aabb6[1], aabb6[2]);
+    data->aaBox.max = float3(aabb6[3], aabb6[4], aabb6[5]);
+    data->totalVertexCount = totalVertexCount;
+    data->totalCurveVertexCount = 0;
+    data->curveModelName = 0;
+    data->pad = 0;
+    data->indexSize = indexCount * sizeof(uint32);
+    data->faceIndexSize = 0;
+    data->positionSize = (uint64)totalVertexCount * sizeof(float3);
+    data->normalsSize = normals ? (uint64)totalVertexCount * sizeof(float3) : 0;
+    data->tangentsSize = tangents ? (uint64)totalVertexCount * sizeof(float4) : 0;
+    data->uvsSize = uvs ? (uint64)totalVertexCount * sizeof(float2) : 0;
+    data->curveIndexSize = 0;
+    data->curveVertexSize = 0;
+    fillArray(data->materials, materials600, materialCount);
+    fillArray(data->materialHashes, materialHashes, materialCount);
+    fillArray(data->meshes, meshes92, meshCount);
+    int rc = writeBlob(*data, dataPath);
+    data->materials.Shutdown(); data->materialHashes.Shutdown(); data->meshes.Shutdown();
+    delete data;
+    ModelGeometryData geom;
+    memset(&geom, 0, sizeof(geom));
+    geom.indexSize = indexCount * sizeof(uint32);
+    geom.positionSize = (uint64)totalVertexCount * sizeof(float3);
+    geom.normalsSize = normals ? (uint64)totalVertexCount * sizeof(float3) : 0;
+    geom.tangentsSize = tangents ? (uint64)totalVertexCount * sizeof(float4) : 0;
+    geom.uvsSize = uvs ? (uint64)totalVertexCount * sizeof(float2) : 0;
+    geom.indices = const_cast<uint32*>(indices);
+    geom.positions = reinterpret_cast<float3*>(const_cast<float*>(positions));
+    geom.normals = reinterpret_cast<float3*>(const_cast<float*>(normals));
+    geom.tangents = reinterpret_cast<float4*>(const_cast<float*>(tangents));
+    geom.uvs = reinterpret_cast<float2*>(const_cast<float*>(uvs));
+    if (!rc) rc = writeBlob(geom, geomPath);
+    return rc;
+}
+int ref_write_subscene_blob(const char* path, const char* name, uint64_t lightSetIndex, const void* modelNames512, uint32_t modelCount,
+                            const void* instances72, uint32_t instanceCount, const uint32_t* sceneMaterialHashes, const void* sceneMaterials600,
+                            uint32_t sceneMaterialCount) {
+    SubsceneResourceData* data = new SubsceneResourceData();
+    copyFixed(data->name, name);
+    data->lightSetIndex = lightSetIndex;
+    fillArray(data->modelNames, modelNames512, modelCount);
+    fillArray(data->modelInstances, instances72, instanceCount);
+    fillArray(data->sceneMaterialNames, sceneMaterialHashes, sceneMaterialCount);
+    fillArray(data->sceneMaterials, sceneMaterials600, sceneMaterialCount);
+    int rc = writeBlob(*data, path);
+    data->modelNames.Shutdown(); data->modelInstances.Shutdown(); data->sceneMaterialNames.Shutdown(); data->sceneMaterials.Shutdown();
+    delete data;
+    return rc;
+}
+int ref_write_scene_blob(const char* path, const char* name, const char* iblName, const float* background4, const void* subsceneNames512,
+                         uint32_t subsceneCount, const void* instances72, uint32_t instanceCount, const void* lights64, uint32_t lightCount,
+                         const void* lightSets8, uint32_t lightSetCount, const void* cameras176, uint32_t cameraCount) {
+    SceneResourceData* data = new SceneResourceData();
+    copyFixed(data->name, name);
+    copyFixed(data->iblName, iblName ? iblName : "");
+    data->backgroundIntensity = float4(background4[0], background4[1], background4[2], background4[3]);
+    fillArray(data->subsceneNames, subsceneNames512, subsceneCount);
+    fillArray(data->subsceneInstances, instances72, instanceCount);
+    fillArray(data->lights, lights64, lightCount);
+    fillArray(data->lightSetRanges, lightSets8, lightSetCount);
+    fillArray(data->cameras, cameras176, cameraCount);
+    int rc = writeBlob(*data, path);
+    data->subsceneNames.Shutdown(); data->subsceneInstances.Shutdown(); data->lights.Shutdown(); data->lightSetRanges.Shutdown();
+    data->cameras.Shutdown();
+    delete data;
+    return rc;
 }
 
 }  // extern "C"

@@ -644,6 +644,239 @@ Error ReadTextureResource(const char* filepath, TextureResource* tex) {
     return Success_;
 }
 
+// ---- scene / subscene / model blobs ---------------------------------------------------------------------------------------------
+namespace {
+std::string fixedString(const uint8_t* p, size_t n) {
+    size_t len = 0;
+    while (len < n && p[len]) ++len;
+    return std::string((const char*)p, len);
+}
+// CArray header at `fieldOffset`: {flags u32, padding u32, count u64, capacity u64, data offset u64}; returns the element data
+Error blobArray(const std::vector<uint8_t>& blob, size_t fieldOffset, size_t elementSize, uint64_t* count, const uint8_t** data, const char* what) {
+    if (fieldOffset + 32 > blob.size()) return Error_("baked blob: array header %s lies outside the file", what);
+    memcpy(count, blob.data() + fieldOffset + 8, 8);
+    if (*count > blob.size()) return Error_("baked blob: array %s has an implausible count", what);
+    return blobPointer(blob, fieldOffset + 24, *count * elementSize, data, what);
+}
+void readMaterial(const uint8_t* p, BakedMaterial& m) {  // MaterialResourceData: 0 texture[512] | 512 shader | 516 flags | 520 baseColor | 532 transmittance | 544 scalars[14]
+    m.baseColorTexture = fixedString(p, 512);
+    memcpy(&m.material.shader, p + 512, 4);
+    memcpy(&m.material.flags, p + 516, 4);
+    memcpy(m.material.baseColor, p + 520, 12);
+    memcpy(m.material.transmittanceColor, p + 532, 12);
+    memcpy(m.material.scalars, p + 544, 4 * SELAS_SCALAR_COUNT);
+}
+void multiply44(const float* a, const float* b, float* c) {  // MatrixMultiply, MathLib/FloatFuncs.cpp (row-major, row vectors)
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) c[4 * i + j] = a[4 * i] * b[j] + a[4 * i + 1] * b[4 + j] + a[4 * i + 2] * b[8 + j] + a[4 * i + 3] * b[12 + j];
+}
+}  // namespace
+
+// ModelResourceData: 0 aaBox | 24 totalVertexCount | 28 totalCurveVertexCount | 32 curveModelName | 36 pad | 40..103 eight u64 sizes |
+//   104 cameras | 136 textureResourceNames | 168 materials | 200 materialHashes | 232 meshes | 264 curves          (296 bytes)
+// ModelGeometryData: 0..63 the same eight sizes | 64 indices* | 72 faceIndexCounts* | 80 positions* | 88 normals* | 96 tangents* |
+//   104 uvs* | 112 curveIndices* | 120 curveVertices*                                                              (128 bytes)
+Error ReadModelResource(const char* dataPath, const char* geometryPath, BakedModel* model) {
+    std::vector<uint8_t> blob;
+    ReturnError_(readWholeFile(dataPath, blob));
+    if (blob.size() < 296) return Error_("baked model blob %s: shorter than the 296-byte resource header", dataPath);
+    memcpy(model->aaBox, blob.data(), 24);
+    memcpy(&model->totalVertexCount, blob.data() + 24, 4);
+    memcpy(&model->totalCurveVertexCount, blob.data() + 28, 4);
+    uint64_t n = 0;
+    const uint8_t* p = nullptr;
+    ReturnError_(blobArray(blob, 168, 600, &n, &p, "materials"));
+    model->materials.resize(n);
+    for (uint64_t i = 0; i < n; ++i) readMaterial(p + 600 * i, model->materials[i]);
+    ReturnError_(blobArray(blob, 200, 4, &n, &p, "materialHashes"));
+    model->materialHashes.assign((const uint32_t*)p, (const uint32_t*)p + n);
+    ReturnError_(blobArray(blob, 232, 92, &n, &p, "meshes"));
+    model->meshes.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint8_t* m = p + 92 * i;
+        BakedMesh& bm = model->meshes[i];
+        memcpy(&bm.indexCount, m, 4); memcpy(&bm.indexOffset, m + 4, 4); memcpy(&bm.vertexCount, m + 8, 4); memcpy(&bm.vertexOffset, m + 12, 4);
+        memcpy(&bm.materialHash, m + 16, 4); memcpy(&bm.indicesPerFace, m + 20, 4); memcpy(&bm.nameHash, m + 24, 4);
+        bm.name = fixedString(m + 28, 64);
+    }
+    ReturnError_(blobArray(blob, 264, 8, &model->curveCount, &p, "curves"));
+
+    std::vector<uint8_t> geo;
+    ReturnError_(readWholeFile(geometryPath, geo));
+    if (geo.size() < 128) return Error_("baked geometry blob %s: shorter than the 128-byte header", geometryPath);
+    uint64_t sizes[8];
+    memcpy(sizes, geo.data(), 64);
+    const uint8_t *pi = nullptr, *pp = nullptr, *pn = nullptr, *pt = nullptr, *pu = nullptr;
+    ReturnError_(blobPointer(geo, 64, sizes[0], &pi, "indices"));
+    ReturnError_(blobPointer(geo, 80, sizes[2], &pp, "positions"));
+    ReturnError_(blobPointer(geo, 88, sizes[3], &pn, "normals"));
+    ReturnError_(blobPointer(geo, 96, sizes[4], &pt, "tangents"));
+    ReturnError_(blobPointer(geo, 104, sizes[5], &pu, "uvs"));
+    if (sizes[2] != 12ull * model->totalVertexCount) return Error_("baked geometry blob %s: positionSize does not match totalVertexCount", geometryPath);
+    model->indices.assign((const uint32_t*)pi, (const uint32_t*)pi + sizes[0] / 4);
+    model->positions.assign((const float*)pp, (const float*)pp + sizes[2] / 4);
+    model->normals.assign((const float*)pn, (const float*)pn + sizes[3] / 4);
+    model->tangents.assign((const float*)pt, (const float*)pt + sizes[4] / 4);
+    model->uvs.assign((const float*)pu, (const float*)pu + sizes[5] / 4);
+    return Success_;
+}
+
+// SubsceneResourceData: 0 name[512] | 512 lightSetIndex u64 | 520 modelNames | 552 modelInstances | 584 sceneMaterialNames | 616 sceneMaterials
+Error ReadSubsceneResource(const char* filepath, BakedSubscene* sub) {
+    std::vector<uint8_t> blob;
+    ReturnError_(readWholeFile(filepath, blob));
+    if (blob.size() < 648) return Error_("baked subscene blob %s: shorter than the 648-byte resource header", filepath);
+    sub->name = fixedString(blob.data(), 512);
+    memcpy(&sub->lightSetIndex, blob.data() + 512, 8);
+    uint64_t n = 0;
+    const uint8_t* p = nullptr;
+    ReturnError_(blobArray(blob, 520, 512, &n, &p, "modelNames"));
+    sub->modelNames.resize(n);
+    for (uint64_t i = 0; i < n; ++i) sub->modelNames[i] = fixedString(p + 512 * i, 512);
+    ReturnError_(blobArray(blob, 552, 72, &n, &p, "modelInstances"));
+    sub->modelInstances.resize(n);
+    for (uint64_t i = 0; i < n; ++i) memcpy(&sub->modelInstances[i], p + 72 * i, 72);
+    ReturnError_(blobArray(blob, 584, 4, &n, &p, "sceneMaterialNames"));
+    sub->sceneMaterialNames.assign((const uint32_t*)p, (const uint32_t*)p + n);
+    ReturnError_(blobArray(blob, 616, 600, &n, &p, "sceneMaterials"));
+    sub->sceneMaterials.resize(n);
+    for (uint64_t i = 0; i < n; ++i) readMaterial(p + 600 * i, sub->sceneMaterials[i]);
+    return Success_;
+}
+
+// SceneResourceData: 0 name[512] | 512 iblName[512] | 1024 backgroundIntensity | 1040 subsceneNames | 1072 subsceneInstances | 1104 lights |
+//   1136 lightSetRanges | 1168 cameras                                                                            (1200 bytes)
+Error ReadSceneResource(const char* filepath, BakedScene* scene) {
+    std::vector<uint8_t> blob;
+    ReturnError_(readWholeFile(filepath, blob));
+    if (blob.size() < 1200) return Error_("baked scene blob %s: shorter than the 1200-byte resource header", filepath);
+    scene->name = fixedString(blob.data(), 512);
+    scene->iblName = fixedString(blob.data() + 512, 512);
+    memcpy(scene->backgroundIntensity, blob.data() + 1024, 16);
+    uint64_t n = 0;
+    const uint8_t* p = nullptr;
+    ReturnError_(blobArray(blob, 1040, 512, &n, &p, "subsceneNames"));
+    scene->subsceneNames.resize(n);
+    for (uint64_t i = 0; i < n; ++i) scene->subsceneNames[i] = fixedString(p + 512 * i, 512);
+    ReturnError_(blobArray(blob, 1072, 72, &n, &p, "subsceneInstances"));
+    scene->subsceneInstances.resize(n);
+    for (uint64_t i = 0; i < n; ++i) memcpy(&scene->subsceneInstances[i], p + 72 * i, 72);
+    ReturnError_(blobArray(blob, 1104, 64, &n, &p, "lights"));
+    scene->lights.resize(n);
+    if (n) memcpy(scene->lights.data(), p, 64 * n);
+    ReturnError_(blobArray(blob, 1136, 8, &n, &p, "lightSetRanges"));
+    scene->lightSetRanges.resize(n);
+    if (n) memcpy(scene->lightSetRanges.data(), p, 8 * n);
+    ReturnError_(blobArray(blob, 1168, 176, &n, &p, "cameras"));
+    scene->cameras.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        scene->cameras[i].name = fixedString(p + 176 * i, 128);
+        memcpy(&scene->cameras[i].settings, p + 176 * i + 128, 48);  // position, fov, lookAt, znear, up, zfar
+    }
+    return Success_;
+}
+
+Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* scene, ImageBasedLight* ibl, std::vector<BakedCamera>* cameras) {
+    BakedScene bs;
+    ReturnError_(ReadSceneResource(AssetFilePath(root, "SceneResource", kSceneDataVersion, sceneName).c_str(), &bs));
+    scene->meshes.clear();
+    scene->instances.clear();
+    scene->materials.clear();
+    scene->lights = bs.lights;
+    scene->lightSets = bs.lightSetRanges;
+    memcpy(scene->backgroundIntensity, bs.backgroundIntensity, 16);
+    scene->ibl = nullptr;
+    if (!bs.iblName.empty()) {
+        if (!ibl) return Error_("LoadBakedScene: scene %s names an IBL (%s) but no ImageBasedLight was passed", sceneName, bs.iblName.c_str());
+        ReturnError_(ReadImageBasedLightResource(AssetFilePath(root, "IBL", kIblDataVersion, bs.iblName.c_str()).c_str(), ibl));
+        scene->ibl = &ibl->desc;
+    }
+    if (cameras) *cameras = bs.cameras;
+    // the default material of CreateDefaultMaterial (ModelResource.cpp:203-211), appended on first use
+    int defaultMaterial = -1;
+    // subscenes -> models -> meshes; meshRange[subscene][model] = first global mesh index, mesh count
+    struct ModelMeshes { uint32_t first, count; };
+    std::vector<std::vector<ModelMeshes>> meshRange(bs.subsceneNames.size());
+    std::vector<BakedSubscene> subs(bs.subsceneNames.size());
+    for (size_t s = 0; s < bs.subsceneNames.size(); ++s) {
+        BakedSubscene& sub = subs[s];
+        ReturnError_(ReadSubsceneResource(AssetFilePath(root, "SubsceneResource", kSubsceneDataVersion, bs.subsceneNames[s].c_str()).c_str(), &sub));
+        const uint32_t sceneMaterialBase = (uint32_t)scene->materials.size();
+        for (const BakedMaterial& m : sub.sceneMaterials) scene->materials.push_back(m.material);
+        for (const std::string& modelName : sub.modelNames) {
+            BakedModel model;
+            ReturnError_(ReadModelResource(AssetFilePath(root, "ModelResource", kModelDataVersion, modelName.c_str()).c_str(),
+                                           AssetFilePath(root, "ModelGeometryResource", kModelDataVersion, modelName.c_str()).c_str(), &model));
+            if (model.curveCount) return Error_("LoadBakedScene: model %s has %llu curves (ROUND_BSPLINE_CURVE geometry is not supported)", modelName.c_str(),
+                                                (unsigned long long)model.curveCount);
+            const uint32_t modelMaterialBase = (uint32_t)scene->materials.size();
+            for (const BakedMaterial& m : model.materials) scene->materials.push_back(m.material);
+            ModelMeshes range{(uint32_t)scene->meshes.size(), (uint32_t)model.meshes.size()};
+            for (const BakedMesh& bm : model.meshes) {
+                if (bm.indicesPerFace != 3 && bm.indicesPerFace != 4) return Error_("LoadBakedScene: mesh %s has %u indices per face", bm.name.c_str(), bm.indicesPerFace);
+                if ((uint64_t)bm.indexOffset + bm.indexCount > model.indices.size()) return Error_("LoadBakedScene: mesh %s indexes outside the model's index buffer", bm.name.c_str());
+                SceneMesh mesh;
+                mesh.indicesPerFace = bm.indicesPerFace;
+                mesh.lightSetIndex = (uint32_t)sub.lightSetIndex;
+                // FindMeshMaterial: the model's own materials (sorted hashes), then the subscene's, then the default
+                int material = -1;
+                auto it = std::lower_bound(model.materialHashes.begin(), model.materialHashes.end(), bm.materialHash);
+                if (it != model.materialHashes.end() && *it == bm.materialHash) material = (int)(modelMaterialBase + (it - model.materialHashes.begin()));
+                for (size_t k = 0; material < 0 && k < sub.sceneMaterialNames.size(); ++k)
+                    if (sub.sceneMaterialNames[k] == bm.materialHash) material = (int)(sceneMaterialBase + k);
+                if (material < 0) {
+                    if (defaultMaterial < 0) {
+                        SelasMaterial dm;
+                        memset(&dm, 0, sizeof(dm));
+                        dm.shader = SELAS_SHADER_DISNEY_SOLID;
+                        dm.baseColor[0] = dm.baseColor[1] = dm.baseColor[2] = 0.6f;
+                        dm.scalars[SELAS_IOR] = 1.5f;
+                        defaultMaterial = (int)scene->materials.size();
+                        scene->materials.push_back(dm);
+                    }
+                    material = defaultMaterial;
+                }
+                mesh.materialIndex = (uint32_t)material;
+                if (scene->materials[material].flags & SELAS_MAT_DISPLACEMENT)
+                    return Error_("LoadBakedScene: mesh %s uses a displaced subdivision surface, which is not supported", bm.name.c_str());
+                // the mesh's vertices: indices are absolute into the model-wide arrays (SetMeshVertexAttributes, ModelResource.cpp:164-199);
+                // take the span they touch and rebase
+                const uint32_t* ix = model.indices.data() + bm.indexOffset;
+                uint32_t lo = 0xFFFFFFFFu, hi = 0;
+                for (uint32_t k = 0; k < bm.indexCount; ++k) { lo = std::min(lo, ix[k]); hi = std::max(hi, ix[k]); }
+                if (bm.indexCount == 0) { lo = 0; hi = 0; }
+                if (hi >= model.totalVertexCount) return Error_("LoadBakedScene: mesh %s references vertex %u of %u", bm.name.c_str(), hi, model.totalVertexCount);
+                const uint32_t nv = bm.indexCount ? hi - lo + 1 : 0;
+                mesh.indices.resize(bm.indexCount);
+                for (uint32_t k = 0; k < bm.indexCount; ++k) mesh.indices[k] = ix[k] - lo;
+                mesh.positions.assign(model.positions.begin() + 3 * (size_t)lo, model.positions.begin() + 3 * (size_t)(lo + nv));
+                if (!model.normals.empty()) mesh.normals.assign(model.normals.begin() + 3 * (size_t)lo, model.normals.begin() + 3 * (size_t)(lo + nv));
+                if (!model.tangents.empty()) mesh.tangents.assign(model.tangents.begin() + 4 * (size_t)lo, model.tangents.begin() + 4 * (size_t)(lo + nv));
+                if (!model.uvs.empty()) mesh.uvs.assign(model.uvs.begin() + 2 * (size_t)lo, model.uvs.begin() + 2 * (size_t)(lo + nv));
+                scene->meshes.push_back(std::move(mesh));
+            }
+            meshRange[s].push_back(range);
+        }
+    }
+    // flatten the two instancing levels (InitializeModelInstances, SubsceneResource.cpp:63-79; scene level, SceneResource.cpp:218-249)
+    for (const BakedInstance& si : bs.subsceneInstances) {
+        if (si.index >= subs.size()) return Error_("LoadBakedScene: subscene instance refers to subscene %llu of %zu", (unsigned long long)si.index, subs.size());
+        const BakedSubscene& sub = subs[si.index];
+        for (const BakedInstance& mi : sub.modelInstances) {
+            if (mi.index >= meshRange[si.index].size()) return Error_("LoadBakedScene: model instance refers to model %llu of %zu", (unsigned long long)mi.index,
+                                                                      meshRange[si.index].size());
+            const ModelMeshes& range = meshRange[si.index][mi.index];
+            SelasInstanceDesc inst;
+            multiply44(mi.localToWorld, si.localToWorld, inst.localToWorld);
+            for (uint32_t m = 0; m < range.count; ++m) {
+                inst.meshIndex = range.first + m;
+                scene->instances.push_back(inst);
+            }
+        }
+    }
+    return Success_;
+}
+
 // identical to selas_b200/scenes.py:caustic_scene / sun_sky_ibl
 void MakeCausticScene(SceneResource* scene, ImageBasedLight* ibl, uint32_t sphereTheta, uint32_t spherePhi, uint32_t floorCells) {
     const double pi = 3.14159265358979323846;
@@ -782,6 +1015,53 @@ int selas_host_import_material_json(const char* json, SelasMaterial* out, char* 
         return SELAS_ERR_FORMAT;
     }
     Selas::BuildMaterial(imp, *out);
+    return SELAS_OK;
+}
+int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_t* counts8, float* instanceMatrices, uint32_t* instanceMesh,
+                                void* materials, char* errorOut, int errorCapacity) {
+    Selas::SceneResource scene;
+    Selas::ImageBasedLight ibl;
+    std::vector<Selas::BakedCamera> cameras;
+    Selas::Error e = Selas::LoadBakedScene(root, sceneName, &scene, &ibl, &cameras);
+    if (e.Failed()) {
+        if (errorOut && errorCapacity > 0) snprintf(errorOut, errorCapacity, "%s", e.Message());
+        return SELAS_ERR_FORMAT;
+    }
+    if (counts8) {
+        uint64_t tris = 0;
+        for (const SelasInstanceDesc& in : scene.instances) {
+            const Selas::SceneMesh& m = scene.meshes[in.meshIndex];
+            tris += m.indices.size() / m.indicesPerFace * (m.indicesPerFace == 4 ? 2 : 1);
+        }
+        uint64_t c[8] = {scene.meshes.size(), scene.instances.size(), scene.materials.size(), scene.lights.size(), scene.lightSets.size(),
+                         cameras.size(), tris, scene.ibl ? 1ull : 0ull};
+        memcpy(counts8, c, sizeof(c));
+    }
+    for (size_t i = 0; i < scene.instances.size(); ++i) {
+        if (instanceMatrices) memcpy(instanceMatrices + 16 * i, scene.instances[i].localToWorld, 64);
+        if (instanceMesh) instanceMesh[i] = scene.instances[i].meshIndex;
+    }
+    if (materials && !scene.materials.empty()) memcpy(materials, scene.materials.data(), scene.materials.size() * sizeof(SelasMaterial));
+    return SELAS_OK;
+}
+int selas_host_render_baked_scene(const char* root, const char* sceneName, int device, const SelasCamera* camera, const SelasRenderSettings* settings,
+                                  float* film, char* errorOut, int errorCapacity) {
+    Selas::SceneResource scene;
+    Selas::ImageBasedLight ibl;
+    Selas::Error e = Selas::LoadBakedScene(root, sceneName, &scene, &ibl, nullptr);
+    if (!e.Failed()) e = Selas::InitializeSceneResource(&scene, device);
+    if (!e.Failed()) {
+        const size_t plane = (size_t)settings->width * settings->height * 3;
+        std::vector<float*> layers(settings->layerCount);
+        for (uint32_t l = 0; l < settings->layerCount; ++l) layers[l] = film + plane * l;
+        if (selas_cuda_render_pathtracer(scene.gpuScene, camera, settings, layers.data(), nullptr) != SELAS_OK)
+            e = Selas::MakeError("%s", selas_cuda_last_error(scene.gpu));
+        Selas::ShutdownSceneResource(&scene);
+    }
+    if (e.Failed()) {
+        if (errorOut && errorCapacity > 0) snprintf(errorOut, errorCapacity, "%s", e.Message());
+        return SELAS_ERR_FORMAT;
+    }
     return SELAS_OK;
 }
 int selas_host_read_ibl_blob(const char* path, uint32_t* info4, float* params2, float* marginal, float* conditional, float* light, float* miss,

@@ -137,6 +137,64 @@ struct TextureResource {
 };
 Error ReadTextureResource(const char* filepath, TextureResource* texture);
 
+// Scene / subscene / model blobs.  Raw region = the resource-data struct (strings are FixedString<512>, arrays are CArray headers
+// {flags u32, pad u32, count u64, capacity u64, data*} whose data is the raw element array, ContainersLib/CArray.h:239-250).
+static const uint64_t kSceneDataVersion = 1539147471ull;     // SceneResource::kDataVersion, type "SceneResource"
+static const uint64_t kSubsceneDataVersion = 1539551841ull;  // SubsceneResource::kDataVersion, type "SubsceneResource"
+static const uint64_t kModelDataVersion = 1539636447ull;     // ModelResource::kDataVersion, types "ModelResource" / "ModelGeometryResource"
+struct BakedInstance {  // Instance, SubsceneResource.h:28-38 (72 bytes)
+    uint64_t index;
+    float localToWorld[16];
+};
+struct BakedMaterial {  // MaterialResourceData, ModelResource.h:68-88 (600 bytes)
+    std::string baseColorTexture;
+    SelasMaterial material;
+};
+struct BakedMesh {  // MeshMetaData, ModelResource.h:113-123 (92 bytes)
+    uint32_t indexCount, indexOffset, vertexCount, vertexOffset, materialHash, indicesPerFace, nameHash;
+    std::string name;
+};
+struct BakedModel {  // ModelResourceData + ModelGeometryData, ModelResource.h:125-170
+    float aaBox[6];
+    uint32_t totalVertexCount = 0, totalCurveVertexCount = 0;
+    uint64_t curveCount = 0;
+    std::vector<BakedMaterial> materials;
+    std::vector<uint32_t> materialHashes;
+    std::vector<BakedMesh> meshes;
+    std::vector<uint32_t> indices;
+    std::vector<float> positions, normals, tangents, uvs;
+};
+struct BakedSubscene {  // SubsceneResourceData, SubsceneResource.h:41-49
+    std::string name;
+    uint64_t lightSetIndex = 0;
+    std::vector<std::string> modelNames;
+    std::vector<BakedInstance> modelInstances;
+    std::vector<uint32_t> sceneMaterialNames;
+    std::vector<BakedMaterial> sceneMaterials;
+};
+struct BakedCamera {  // CameraSettings, Camera.h:17-26 (176 bytes with its 128-byte name)
+    std::string name;
+    CameraSettings settings;
+};
+struct BakedScene {  // SceneResourceData, SceneResource.h:49-59
+    std::string name, iblName;
+    float backgroundIntensity[4];
+    std::vector<std::string> subsceneNames;
+    std::vector<BakedInstance> subsceneInstances;
+    std::vector<SelasLight> lights;
+    std::vector<SelasLightSetRange> lightSetRanges;
+    std::vector<BakedCamera> cameras;
+};
+Error ReadModelResource(const char* dataPath, const char* geometryPath, BakedModel* model);
+Error ReadSubsceneResource(const char* filepath, BakedSubscene* subscene);
+Error ReadSceneResource(const char* filepath, BakedScene* scene);
+// ReadSceneResource + InitializeSceneResource of the reference (SceneResource.cpp:266-330) for `<root>_Assets/...`: the scene blob, its
+// subscenes, their models and the IBL.  The two instancing levels are flattened: every (subscene instance, model instance, mesh)
+// becomes one SelasInstanceDesc with localToWorld = model.localToWorld * subscene.localToWorld (ModelDataFromRayIds,
+// SceneResource.cpp:362-378); materials are resolved like FindMeshMaterial (ModelResource.cpp:214-235).  Curves and displaced
+// subdivision meshes are reported as unsupported.  `scene` is left ready for InitializeSceneResource(scene, device).
+Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* scene, ImageBasedLight* ibl, std::vector<BakedCamera>* cameras);
+
 // BASELINE config 5: floor + glass sphere (Content/Materials/BSDF.json) + diffuse box under a sun-and-sky IBL.
 void MakeCausticScene(SceneResource* scene, ImageBasedLight* ibl, uint32_t sphereTheta = 96, uint32_t spherePhi = 192, uint32_t floorCells = 64);
 void SetupCausticCamera(uint32_t width, uint32_t height, RayCastCameraSettings& camera);
@@ -192,6 +250,13 @@ int selas_host_write_hdr(const char* path, uint32_t width, uint32_t height, cons
 // Baked-asset readers for tests: info = {width, height, missWidth, missHeight}, params = {rotationRadians, exposureScale}; any array may be null.
 int selas_host_read_ibl_blob(const char* path, uint32_t* info4, float* params2, float* marginal, float* conditional, float* light, float* miss,
                              char* errorOut, int errorCapacity);
+// LoadBakedScene summary for tests: counts8 = {meshes, instances, materials, lights, lightSets, cameras, triangles, hasIbl}; when not null,
+// instanceMatrices receives 16 floats per instance, instanceMesh one uint32 per instance, materials 88 bytes per material
+int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_t* counts8, float* instanceMatrices, uint32_t* instanceMesh,
+                                void* materials, char* errorOut, int errorCapacity);
+// Loads the baked scene, builds it on `device` and renders with PathTracer settings through the C ABI; film = layerCount planes of w*h*3
+int selas_host_render_baked_scene(const char* root, const char* sceneName, int device, const SelasCamera* camera, const SelasRenderSettings* settings,
+                                  float* film, char* errorOut, int errorCapacity);
 // info = {mipCount, format, width0, height0}; texels0 receives level 0 (width0 * height0 * (format + 1) floats) when not null
 int selas_host_read_texture_blob(const char* path, uint32_t* info4, float* texels0, char* errorOut, int errorCapacity);
 }

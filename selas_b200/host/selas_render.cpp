@@ -2,6 +2,7 @@
 // scene: initialise the scene on the GPU, set up the camera, PathTracer::GenerateImage, report the render time.
 //   selas_render [--width W] [--height H] [--spp N] [--depth D] [--layers L] [--roughness R] [--device I] [--name NAME]
 //   selas_render --integrator deferred [...]                      (DeferredPathTracer::GenerateImage, 4 x 4 CMJ samples per pixel)
+//   selas_render --scene NAME --assets ROOT [...]                 (a scene baked by the reference: ROOT_Assets/SceneResource/<version>/NAME.bin)
 //   selas_render --integrator vcm [--width W] [--height H] [--iterations N] [--depth D] ...   (config 5 caustic scene, VCM::GenerateImage)
 #include <chrono>
 #include <cstdio>
@@ -30,12 +31,16 @@ int main(int argc, char** argv) {
     int device = 0;
     const char* name = "cornell";
     const char* integrator = "pathtracer";
+    const char* bakedScene = nullptr;
+    const char* assetRoot = "";
     VCMSettings vcm;
     bool sizeGiven = false;
     for (int i = 1; i + 1 < argc; i += 2) {
         if (!strcmp(argv[i], "--width")) { width = (uint32_t)atoi(argv[i + 1]); sizeGiven = true; }
         else if (!strcmp(argv[i], "--height")) { height = (uint32_t)atoi(argv[i + 1]); sizeGiven = true; }
         else if (!strcmp(argv[i], "--integrator")) integrator = argv[i + 1];
+        else if (!strcmp(argv[i], "--scene")) bakedScene = argv[i + 1];
+        else if (!strcmp(argv[i], "--assets")) assetRoot = argv[i + 1];
         else if (!strcmp(argv[i], "--iterations")) vcm.iterations = (uint32_t)atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--spp")) settings.pathsPerPixel = (uint32_t)atoi(argv[i + 1]);
         else if (!strcmp(argv[i], "--depth")) settings.maxBounceCount = (uint32_t)atoi(argv[i + 1]);
@@ -83,13 +88,21 @@ int main(int argc, char** argv) {
     }
     auto t0 = std::chrono::steady_clock::now();
     SceneResource scene;
-    MakeCornellBoxScene(&scene, roughness);
+    ImageBasedLight bakedIbl;
+    std::vector<BakedCamera> bakedCameras;
+    if (bakedScene)  // ReadSceneResource + InitializeSceneResource, main.cpp:104-113
+        ExitMainOnError_(LoadBakedScene(assetRoot, bakedScene, &scene, &bakedIbl, &bakedCameras));
+    else
+        MakeCornellBoxScene(&scene, roughness);
     ExitMainOnError_(InitializeSceneResource(&scene, device));
     auto t1 = std::chrono::steady_clock::now();
     printf("Scene load time %fms\n", std::chrono::duration<double, std::milli>(t1 - t0).count());  // main.cpp:106-107
 
     RayCastCameraSettings camera;
-    SetupCornellCamera(width, height, camera);
+    if (bakedScene && !bakedCameras.empty())  // SetupSceneCamera(scene, 0, width, height, camera), main.cpp:116-117
+        InitializeRayCastCamera(bakedCameras[0].settings, width, height, camera);
+    else
+        SetupCornellCamera(width, height, camera);
     SelasRenderStats stats;
     if (deferred) {
         DeferredPathTracerSettings ds;

@@ -83,6 +83,11 @@ def extra():
     btex = brng.uniform(0, 1, size=(5, 7, 3)).astype(np.float32)
     ref.write_ibl_blob(bibl, OUT / "baked_ibl.bin")
     ref.write_texture_blob(btex, OUT / "baked_texture.bin")
+    # a whole baked scene (scene / subscene / two models + geometry / IBL), tests/baked.py
+    import shutil
+    from tests import baked
+    shutil.rmtree(OUT / "baked_scene", ignore_errors=True)
+    baked.write_baked(ref, OUT / "baked_scene", baked.small_two_level_scene())
     print("extra golden vectors written")
 
 

@@ -191,3 +191,78 @@ def test_baked_blobs_golden(host, tmp_path):
     err = C.create_string_buffer(256)
     assert host.selas_host_read_ibl_blob(str(bad).encode(), None, None, None, None, None, None, err, 256) == 4 and b"outside the file" in err.value
     assert host.selas_host_read_texture_blob(str(tmp_path / "missing.bin").encode(), None, None, err, 256) == 4 and b"Failed to open" in err.value
+
+
+def _load_baked(host, root, name):
+    counts = (C.c_uint64 * 8)()
+    err = C.create_string_buffer(512)
+    rc = host.selas_host_load_baked_scene(str(root).encode() + b"/", name.encode(), counts, None, None, None, err, 512)
+    assert rc == 0, err.value
+    n_mesh, n_inst, n_mat = counts[0], counts[1], counts[2]
+    mats, mesh = np.zeros((n_inst, 4, 4), np.float32), np.zeros(n_inst, np.uint32)
+    materials = np.zeros(n_mat, capi.MATERIAL_DTYPE)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert host.selas_host_load_baked_scene(str(root).encode() + b"/", name.encode(), counts, p(mats), p(mesh), p(materials), err, 512) == 0
+    return list(counts), mats, mesh, materials
+
+
+def test_baked_scene_from_the_reference_serializer(host, ref, tmp_path):
+    """Scene / subscene / model / geometry / IBL blobs written by the reference's Serialize() functions (oracle/_ref) and read by
+    LoadBakedScene: counts, FindMeshMaterial resolution and the flattened two-level instance transforms."""
+    from tests import baked
+
+    scene = baked.small_two_level_scene()
+    baked.write_baked(ref, tmp_path, scene)
+    want = baked.expected_flat_scene(scene)
+    counts, mats, mesh, materials = _load_baked(host, tmp_path, scene["name"])
+    assert counts[0] == len(want.meshes) == 4 and counts[1] == len(want.instances) == 12 and counts[3] == 3 and counts[4] == 1 and counts[5] == 1
+    assert counts[6] == sum(want.meshes[i]["indices"].shape[0] * (2 if want.meshes[i]["indices"].shape[1] == 4 else 1) for i, _ in want.instances)
+    assert counts[7] == 1
+    np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])
+    np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))  # bit-exact: same float32 summation order
+    assert materials.tobytes() == want.materials.tobytes()
+    for t in ("SceneResource", "SubsceneResource", "ModelResource", "ModelGeometryResource"):
+        assert ref.asset_version(t) == baked.VERSIONS[t]
+    # a missing subscene blob is an error, not an empty scene
+    (baked.asset_path(tmp_path, "SubsceneResource", "sub0")).unlink()
+    err = C.create_string_buffer(512)
+    assert host.selas_host_load_baked_scene(str(tmp_path).encode() + b"/", b"twolevel", None, None, None, None, err, 512) == 4
+    assert b"Failed to open" in err.value
+
+
+@pytest.mark.gpu
+def test_baked_scene_renders_like_the_flat_description(ctx, host, ref, tmp_path):
+    """The baked two-level scene rendered through the host loader equals the flat SceneData rendered through the C ABI."""
+    from tests import baked
+
+    scene = baked.small_two_level_scene()
+    baked.write_baked(ref, tmp_path, scene)
+    want = baked.expected_flat_scene(scene)
+    w, h, spp = 96, 64, 8
+    c = scene["cameras"][0]
+    cam = capi.camera_init(c["position"], c["lookAt"], c["up"], c["fovDegrees"], w, h, c["znear"], c["zfar"])
+    rs = capi.render_settings(w, h, spp, max_path_length=6, rr_start=8, layers=1, seed=3)
+    film = np.zeros((h, w, 3), np.float32)
+    err = C.create_string_buffer(512)
+    rc = host.selas_host_render_baked_scene(str(tmp_path).encode() + b"/", b"twolevel", 0, C.byref(cam), C.byref(rs), film.ctypes.data_as(C.c_void_p), err, 512)
+    assert rc == 0, err.value
+    sc = capi.Scene(ctx, want)
+    ref_film = sc.render(cam, rs)[0][0]
+    sc.close()
+    assert ref_film.sum() > 0
+    fin = np.isfinite(ref_film).all(axis=2) & np.isfinite(film).all(axis=2)
+    np.testing.assert_allclose(film[fin], ref_film[fin], rtol=2e-3, atol=2e-3)  # identical inputs: only the float atomics' order differs
+
+
+def test_baked_scene_golden(host):
+    """The committed baked scene (tests/golden/baked_scene, written by make_golden.py with the reference serializer) without the
+    reference at hand."""
+    from tests import baked
+
+    scene = baked.small_two_level_scene()
+    want = baked.expected_flat_scene(scene)
+    counts, mats, mesh, materials = _load_baked(host, GOLDEN / "baked_scene", scene["name"])
+    assert counts[:6] == [4, 12, len(want.materials), 3, 1, 1] and counts[7] == 1
+    np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])
+    np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))
+    assert materials.tobytes() == want.materials.tobytes()
