@@ -305,6 +305,7 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
         d.materialIndex = m.materialIndex;
         d.lightSetIndex = m.lightSetIndex;
         d.ptex = m.ptex;
+        d.baseColorTexture = m.baseColorTexture;
     }
     // SceneResource::aaBox / boundingSphere (SceneResource.h:77-78): the instances' boxes in the reference (SceneResource.cpp:196-201);
     // here the vertices of the identity-instanced meshes
@@ -346,6 +347,9 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
 }
 
 void ShutdownSceneResource(SceneResource* scene) {
+    for (TextureResource* t : scene->textures) delete t;
+    scene->textures.clear();
+    scene->textureNames.clear();
     if (scene->gpuScene) selas_cuda_scene_destroy(scene->gpuScene);
     if (scene->gpu) selas_cuda_context_destroy(scene->gpu);
     scene->gpuScene = nullptr;
@@ -794,6 +798,26 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
     if (cameras) *cameras = bs.cameras;
     // the default material of CreateDefaultMaterial (ModelResource.cpp:203-211), appended on first use
     int defaultMaterial = -1;
+    std::vector<std::string> materialTexture;  // baseColorTexture name of scene->materials[i]
+    auto textureFor = [&](const std::string& name, const SelasTextureDesc** out) -> Error {  // TextureCache::LoadTextureResource
+        *out = nullptr;
+        if (name.empty()) return Success_;
+        for (size_t k = 0; k < scene->textureNames.size(); ++k)
+            if (scene->textureNames[k] == name) {
+                *out = &scene->textures[k]->desc;
+                return Success_;
+            }
+        TextureResource* t = new TextureResource();
+        Error e = ReadTextureResource(AssetFilePath(root, "Textures", kTextureDataVersion, name.c_str()).c_str(), t);
+        if (e.Failed()) {
+            delete t;
+            return e;
+        }
+        scene->textures.push_back(t);
+        scene->textureNames.push_back(name);
+        *out = &t->desc;
+        return Success_;
+    };
     // subscenes -> models -> meshes; meshRange[subscene][model] = first global mesh index, mesh count
     struct ModelMeshes { uint32_t first, count; };
     std::vector<std::vector<ModelMeshes>> meshRange(bs.subsceneNames.size());
@@ -802,7 +826,10 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
         BakedSubscene& sub = subs[s];
         ReturnError_(ReadSubsceneResource(AssetFilePath(root, "SubsceneResource", kSubsceneDataVersion, bs.subsceneNames[s].c_str()).c_str(), &sub));
         const uint32_t sceneMaterialBase = (uint32_t)scene->materials.size();
-        for (const BakedMaterial& m : sub.sceneMaterials) scene->materials.push_back(m.material);
+        for (const BakedMaterial& m : sub.sceneMaterials) {
+            scene->materials.push_back(m.material);
+            materialTexture.push_back(m.baseColorTexture);
+        }
         for (const std::string& modelName : sub.modelNames) {
             BakedModel model;
             ReturnError_(ReadModelResource(AssetFilePath(root, "ModelResource", kModelDataVersion, modelName.c_str()).c_str(),
@@ -810,7 +837,10 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
             if (model.curveCount) return Error_("LoadBakedScene: model %s has %llu curves (ROUND_BSPLINE_CURVE geometry is not supported)", modelName.c_str(),
                                                 (unsigned long long)model.curveCount);
             const uint32_t modelMaterialBase = (uint32_t)scene->materials.size();
-            for (const BakedMaterial& m : model.materials) scene->materials.push_back(m.material);
+            for (const BakedMaterial& m : model.materials) {
+                scene->materials.push_back(m.material);
+                materialTexture.push_back(m.baseColorTexture);
+            }
             ModelMeshes range{(uint32_t)scene->meshes.size(), (uint32_t)model.meshes.size()};
             for (const BakedMesh& bm : model.meshes) {
                 if (bm.indicesPerFace != 3 && bm.indicesPerFace != 4) return Error_("LoadBakedScene: mesh %s has %u indices per face", bm.name.c_str(), bm.indicesPerFace);
@@ -833,10 +863,15 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
                         dm.scalars[SELAS_IOR] = 1.5f;
                         defaultMaterial = (int)scene->materials.size();
                         scene->materials.push_back(dm);
+                        materialTexture.push_back(std::string());
                     }
                     material = defaultMaterial;
                 }
                 mesh.materialIndex = (uint32_t)material;
+                if (scene->materials[material].flags & SELAS_MAT_USES_PTEX)  // <texture dir>/<mesh name>.ptx under the content root, ModelResource.cpp:361-368
+                    return Error_("LoadBakedScene: mesh %s uses a Ptex base colour (%s/%s.ptx): pass it through SceneMesh::ptex", bm.name.c_str(),
+                                  materialTexture[material].c_str(), bm.name.c_str());
+                ReturnError_(textureFor(materialTexture[material], &mesh.baseColorTexture));
                 if (scene->materials[material].flags & SELAS_MAT_DISPLACEMENT)
                     return Error_("LoadBakedScene: mesh %s uses a displaced subdivision surface, which is not supported", bm.name.c_str());
                 // the mesh's vertices: indices are absolute into the model-wide arrays (SetMeshVertexAttributes, ModelResource.cpp:164-199);
@@ -1028,13 +1063,14 @@ int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_
         return SELAS_ERR_FORMAT;
     }
     if (counts8) {
-        uint64_t tris = 0;
+        uint64_t tris = 0, texturedMeshes = 0;
+        for (const Selas::SceneMesh& m : scene.meshes) texturedMeshes += m.baseColorTexture ? 1 : 0;
         for (const SelasInstanceDesc& in : scene.instances) {
             const Selas::SceneMesh& m = scene.meshes[in.meshIndex];
             tris += m.indices.size() / m.indicesPerFace * (m.indicesPerFace == 4 ? 2 : 1);
         }
         uint64_t c[8] = {scene.meshes.size(), scene.instances.size(), scene.materials.size(), scene.lights.size(), scene.lightSets.size(),
-                         cameras.size(), tris, scene.ibl ? 1ull : 0ull};
+                         cameras.size(), tris, (scene.ibl ? 1ull : 0ull) | ((uint64_t)scene.textures.size() << 8) | (texturedMeshes << 32)};
         memcpy(counts8, c, sizeof(c));
     }
     for (size_t i = 0; i < scene.instances.size(); ++i) {
@@ -1042,6 +1078,7 @@ int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_
         if (instanceMesh) instanceMesh[i] = scene.instances[i].meshIndex;
     }
     if (materials && !scene.materials.empty()) memcpy(materials, scene.materials.data(), scene.materials.size() * sizeof(SelasMaterial));
+    Selas::ShutdownSceneResource(&scene);
     return SELAS_OK;
 }
 int selas_host_render_baked_scene(const char* root, const char* sceneName, int device, const SelasCamera* camera, const SelasRenderSettings* settings,

@@ -87,6 +87,7 @@ struct SceneMesh {
     std::vector<uint32_t> indices;
     uint32_t indicesPerFace = 3, materialIndex = 0, lightSetIndex = 0;
     SelasPtex* ptex = nullptr;
+    const SelasTextureDesc* baseColorTexture = nullptr;  // borrowed (e.g. from SceneResource::textures)
 };
 struct SceneResource {
     std::vector<SceneMesh> meshes;
@@ -96,6 +97,8 @@ struct SceneResource {
     std::vector<SelasLightSetRange> lightSets;
     float backgroundIntensity[4] = {0, 0, 0, 0};
     const SelasIblDesc* ibl = nullptr;  // SceneResource::iblResource (borrowed), or null: constant background
+    std::vector<struct TextureResource*> textures;  // base colour textures loaded by LoadBakedScene (owned; freed by ShutdownSceneResource)
+    std::vector<std::string> textureNames;
     float aaBox[6] = {0, 0, 0, 0, 0, 0};          // SceneResource::aaBox (min xyz, max xyz), filled by InitializeSceneResource
     float boundingSphere[4] = {0, 0, 0, 0};       // SceneResource::boundingSphere: centre of aaBox, half its diagonal
     // device side
@@ -192,7 +195,9 @@ Error ReadSceneResource(const char* filepath, BakedScene* scene);
 // subscenes, their models and the IBL.  The two instancing levels are flattened: every (subscene instance, model instance, mesh)
 // becomes one SelasInstanceDesc with localToWorld = model.localToWorld * subscene.localToWorld (ModelDataFromRayIds,
 // SceneResource.cpp:362-378); materials are resolved like FindMeshMaterial (ModelResource.cpp:214-235).  Curves and displaced
-// subdivision meshes are reported as unsupported.  `scene` is left ready for InitializeSceneResource(scene, device).
+// subdivision meshes are reported as unsupported.  Base colour textures of non-Ptex materials are loaded from their "Textures" blobs
+// (TextureCache::LoadTextureResource, TextureCache.cpp:68-96: one copy per name; an empty name means the constant colour).
+// `scene` is left ready for InitializeSceneResource(scene, device).
 Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* scene, ImageBasedLight* ibl, std::vector<BakedCamera>* cameras);
 
 // BASELINE config 5: floor + glass sphere (Content/Materials/BSDF.json) + diffuse box under a sun-and-sky IBL.
@@ -250,7 +255,8 @@ int selas_host_write_hdr(const char* path, uint32_t width, uint32_t height, cons
 // Baked-asset readers for tests: info = {width, height, missWidth, missHeight}, params = {rotationRadians, exposureScale}; any array may be null.
 int selas_host_read_ibl_blob(const char* path, uint32_t* info4, float* params2, float* marginal, float* conditional, float* light, float* miss,
                              char* errorOut, int errorCapacity);
-// LoadBakedScene summary for tests: counts8 = {meshes, instances, materials, lights, lightSets, cameras, triangles, hasIbl}; when not null,
+// LoadBakedScene summary for tests: counts8 = {meshes, instances, materials, lights, lightSets, cameras, triangles,
+// hasIbl | distinct textures << 8 | textured meshes << 32}; when not null,
 // instanceMatrices receives 16 floats per instance, instanceMesh one uint32 per instance, materials 88 bytes per material
 int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_t* counts8, float* instanceMatrices, uint32_t* instanceMesh,
                                 void* materials, char* errorOut, int errorCapacity);

@@ -18,7 +18,7 @@ CAMERA_DTYPE = np.dtype([("name", "S128"), ("position", "f4", 3), ("fovDegrees",
                          ("zfar", "f4")])
 assert MESH_META_DTYPE.itemsize == 92 and MATERIAL_RES_DTYPE.itemsize == 600 and INSTANCE_DTYPE.itemsize == 72 and CAMERA_DTYPE.itemsize == 176
 
-VERSIONS = {"SceneResource": 1539147471, "SubsceneResource": 1539551841, "ModelResource": 1539636447, "ModelGeometryResource": 1539636447,
+VERSIONS = {"Textures": 1534887410, "SceneResource": 1539147471, "SubsceneResource": 1539551841, "ModelResource": 1539636447, "ModelGeometryResource": 1539636447,
             "IBL": 1538087123}
 
 
@@ -52,10 +52,12 @@ def _names(strings, width=512):
     return a
 
 
-def _material_res(materials):
+def _material_res(materials, names=None):
     a = np.zeros(len(materials), MATERIAL_RES_DTYPE)
     for i, m in enumerate(materials):
         a[i]["payload"] = m
+        if names and names[i]:
+            a[i]["baseColorTexture"] = names[i].encode()
     return a
 
 
@@ -71,7 +73,9 @@ def small_two_level_scene():
     rng = np.random.default_rng(9)
     uvs = rng.uniform(0, 1, size=(sph["positions"].shape[0], 2)).astype(np.float32)
     half = sph["indices"].shape[0] // 2
-    model_a = dict(name="modelA", meshes=[dict(name="capTop", material=0xA1, indices=sph["indices"][:half]),
+    checker = ((np.add.outer(np.arange(8), np.arange(8)) % 2) * 0.7 + 0.2).astype(np.float32)
+    texture = np.stack([checker, checker[::-1], np.full((8, 8), 0.5, np.float32)], axis=2)
+    model_a = dict(name="modelA", textures={0xA1: "checker"}, meshes=[dict(name="capTop", material=0xA1, indices=sph["indices"][:half]),
                                           dict(name="capBottom", material=0xB7, indices=sph["indices"][half:])],
                    positions=sph["positions"], normals=sph["normals"], tangents=sph["tangents"], uvs=uvs,
                    materials={0xA1: base.materials[0]})  # 0xB7 is only in the subscene's material list
@@ -82,7 +86,7 @@ def small_two_level_scene():
                instances=[(0, np.eye(4, dtype=np.float32)), (1, np.eye(4, dtype=np.float32)), (0, xform(-2.5, 0.4, 0.5, 0.6, 0.7))])
     ibl_img = (rng.uniform(0, 1, size=(16, 32, 3)) ** 4 * 6.0).astype(np.float32)
     ibl = scenes.build_ibl(ibl_img, miss=rng.uniform(0, 1, size=(4, 8, 3)).astype(np.float32), rotation=0.4, exposure=0.0)
-    scene = dict(name="twolevel", ibl_name="sky", ibl=ibl, background=(0.2, 0.3, 0.4, 0.0), subscenes=[sub],
+    scene = dict(name="twolevel", ibl_name="sky", ibl=ibl, textures={"checker": texture}, background=(0.2, 0.3, 0.4, 0.0), subscenes=[sub],
                  instances=[(0, np.eye(4, dtype=np.float32)), (0, xform(1.0, 2.6, 1.5, 0.5, -0.4))], lights=base.lights, light_sets=[(0, 3)],
                  cameras=[dict(name="main", position=(0.0, 1.0, -6.0), lookAt=(0.3, 0.2, 0.0), up=(0.0, 1.0, 0.0), fovDegrees=45.0, znear=0.1, zfar=500.0)])
     return scene
@@ -92,6 +96,8 @@ def write_baked(ref, root, scene):
     """All blobs of `scene` under root/_Assets/... through the reference serializer."""
     lib = ref.lib
     ref.write_ibl_blob(scene["ibl"], asset_path(root, "IBL", scene["ibl_name"]))
+    for name, tex in scene.get("textures", {}).items():
+        ref.write_texture_blob(tex, asset_path(root, "Textures", name))
     for sub in scene["subscenes"]:
         for model in sub["models"]:
             meshes = model["meshes"]
@@ -116,7 +122,7 @@ def write_baked(ref, root, scene):
             tan = None if model["tangents"] is None else np.ascontiguousarray(model["tangents"], np.float32)
             uvs = None if model["uvs"] is None else np.ascontiguousarray(model["uvs"], np.float32)
             hashes = np.array(sorted(model["materials"]), np.uint32)
-            mats = _material_res([model["materials"][h] for h in hashes])
+            mats = _material_res([model["materials"][h] for h in hashes], [model.get("textures", {}).get(int(h)) for h in hashes])
             aabb = np.concatenate([positions.min(axis=0), positions.max(axis=0)]).astype(np.float32)
             rc = lib.ref_write_model_blobs(str(asset_path(root, "ModelResource", model["name"])).encode(),
                                            str(asset_path(root, "ModelGeometryResource", model["name"])).encode(), _p(aabb),
@@ -174,6 +180,9 @@ def expected_flat_scene(scene):
                     d = dict(positions=m["positions"], indices=ind)
                 if m["material"] in model["materials"]:
                     d["material"] = model_base + hashes.index(m["material"])
+                    tname = model.get("textures", {}).get(m["material"])
+                    if tname:
+                        d["texture"] = scene["textures"][tname]
                 elif m["material"] in sub["scene_materials"]:
                     d["material"] = scene_base + sm_hashes.index(m["material"])
                 else:

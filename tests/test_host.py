@@ -217,7 +217,7 @@ def test_baked_scene_from_the_reference_serializer(host, ref, tmp_path):
     counts, mats, mesh, materials = _load_baked(host, tmp_path, scene["name"])
     assert counts[0] == len(want.meshes) == 4 and counts[1] == len(want.instances) == 12 and counts[3] == 3 and counts[4] == 1 and counts[5] == 1
     assert counts[6] == sum(want.meshes[i]["indices"].shape[0] * (2 if want.meshes[i]["indices"].shape[1] == 4 else 1) for i, _ in want.instances)
-    assert counts[7] == 1
+    assert counts[7] == (1 | (1 << 8) | (1 << 32))  # IBL, one distinct texture ("checker"), one textured mesh
     np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])
     np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))  # bit-exact: same float32 summation order
     assert materials.tobytes() == want.materials.tobytes()
@@ -262,7 +262,7 @@ def test_baked_scene_golden(host):
     scene = baked.small_two_level_scene()
     want = baked.expected_flat_scene(scene)
     counts, mats, mesh, materials = _load_baked(host, GOLDEN / "baked_scene", scene["name"])
-    assert counts[:6] == [4, 12, len(want.materials), 3, 1, 1] and counts[7] == 1
+    assert counts[:6] == [4, 12, len(want.materials), 3, 1, 1] and counts[7] == (1 | (1 << 8) | (1 << 32))
     np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])
     np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))
     assert materials.tobytes() == want.materials.tobytes()
