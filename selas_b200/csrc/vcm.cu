@@ -1154,12 +1154,21 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
             // in device memory (grid-stride kernels, the persistent trace kernel reads its ray count through a pointer).
             uint32_t* pairCtr = w->pairCounter + 2 * (size_t)it;  // [0] merge pairs, [1] connect pairs (zeroed with the queue counters)
             const bool connecting = !(vs.flags & SELAS_VCM_NO_CONNECTIONS) && prm.stride && total > 0;
-            const unsigned evalGrid = (unsigned)ctx->smCount * 8;
+            // persistent grids sized to what is actually resident (a grid of 8 CTAs per SM ran in two uneven waves for the 78-register
+            // merge kernel: 2.39 instead of 1.40 ms on the first bounce, profiles/r1_vcm_launches_summary.csv)
+            static int connectCtas = 0, mergeCtas = 0;
+            if (!connectCtas) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&connectCtas, vcmConnectKernel, 128, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mergeCtas, vcmMergeEvalKernel, 128, 0);
+                connectCtas = std::max(1, connectCtas);
+                mergeCtas = std::max(1, mergeCtas);
+            }
+            const unsigned connectGrid = (unsigned)(ctx->smCount * connectCtas), mergeGrid = (unsigned)(ctx->smCount * mergeCtas);
             if (connecting) {
                 size_t tc = ev.mark();
                 vcmConnectGatherKernel<<<divUp(n, 256), 256, 0, stream>>>(prm, n, w->hits, w->thrIdx[cur], w->vertexMis, w->pathStarts, w->pathEnds,
                                                                           w->connPairs, pairCtr + 1);
-                vcmConnectKernel<<<evalGrid, 128, 0, stream>>>(scene->gpu, prm, pairCtr + 1, w->connPairs, w->rays[cur], w->hits, w->thrIdx[cur],
+                vcmConnectKernel<<<connectGrid, 128, 0, stream>>>(scene->gpu, prm, pairCtr + 1, w->connPairs, w->rays[cur], w->hits, w->thrIdx[cur],
                                                                 w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, w->lvHit, w->shadowRays,
                                                                 w->shadowPayload, ctr);
                 ev.span(4, tc);
@@ -1176,7 +1185,7 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
                 unsigned grid = (unsigned)std::min<uint32_t>(divUp(n, kGatherWarps * 32), (uint32_t)ctx->smCount * 16);
                 vcmMergeGatherKernel<<<grid, kGatherWarps * 32, 0, stream>>>(hashGridView(w->grid), n, w->rays[cur], w->hits, w->pairs, w->pairCapacity,
                                                                              pairCtr, w->statCounters);
-                vcmMergeEvalKernel<<<evalGrid, 128, 0, stream>>>(scene->gpu, prm, pairCtr, w->pairCapacity, w->pairs, w->rays[cur], w->hits,
+                vcmMergeEvalKernel<<<mergeGrid, 128, 0, stream>>>(scene->gpu, prm, pairCtr, w->pairCapacity, w->pairs, w->rays[cur], w->hits,
                                                                   w->thrIdx[cur], w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, d_film);
                 ev.span(3, tm);
                 st.kernelLaunches += 2;
