@@ -465,8 +465,11 @@ struct ShadeParams {
 // INTEGRATOR 0: PathTracer::EvaluatePath (PathTracer.cpp:142-258).  INTEGRATOR 1: the DeferredPathTracer's ShadeHitPosition
 // (DeferredPathTracer.cpp:61-148) -- a second NEE sample towards the sky / IBL with balance-heuristic MIS, the BSDF sample weighted
 // against the sky pdf, Russian roulette (u >= p) once MaxTrackedBounces_ = 7 bounces are tracked, no media, shadow rays from tnear 0.
+#ifndef SELAS_SHADE_MIN_CTAS
+#define SELAS_SHADE_MIN_CTAS 4
+#endif
 template <int INTEGRATOR>
-__global__ void __launch_bounds__(128) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ order, uint32_t nMax,
+__global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ order, uint32_t nMax,
                                                    const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                                    const float4* __restrict__ thrPix, const uint2* __restrict__ rngFlags,
                                                    const float4* __restrict__ mediumIn, SelasRay* __restrict__ raysOut,
