@@ -306,7 +306,7 @@ struct WavefrontBuffers {
     uint32_t counterSlots = 0;
     uint32_t shadowPerPath = 1;    // shadow-ray slots per queued path (2 for the deferred integrator: area light + sky)
     uint32_t* h_counts = nullptr;  // pinned readback
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evCounts = nullptr;
     KernelTimers timers;  // event pool reused across calls
 };
 
@@ -329,6 +329,7 @@ void freeWavefront(SelasScene* scene) {
     if (w->h_counts) cudaFreeHost(w->h_counts);
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
+    if (w->evCounts) cudaEventDestroy(w->evCounts);
     delete w;
     scene->wf = nullptr;
 }
@@ -360,6 +361,7 @@ static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterat
     SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4));
     SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev0));
     SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev1));
+    SELAS_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&w->evCounts, cudaEventDisableTiming));
     return SELAS_OK;
 }
 
@@ -811,20 +813,24 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                                                                    scene->usesPtex ? w->ptexRgb : nullptr);
             timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+            // The queue lengths go back to the host for the next bounce's launch shapes, but the shadow launch does not wait for them:
+            // the persistent any-hit kernel reads its ray count from device memory, and is enqueued before the host blocks, so the GPU
+            // traces shadow rays while the host wakes up and enqueues the next bounce (no idle gap between bounces).
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
-            uint32_t nNext = w->h_counts[0], nShadow = w->h_counts[1];
+            SELAS_CUDA_CHECK(ctx, cudaEventRecord(w->evCounts, stream));
             st.kernelLaunches += 2;
-            if (nShadow) {
+            {
                 float* filmRadiance = d_film + (rs.layerCount == 2 ? 3 * (size_t)pixels : 0);
                 t0 = timers.begin(stream);
-                rc = launchShadowAccumulate(scene, nullptr, nShadow, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
+                rc = launchShadowAccumulate(scene, ctr + 1, n * w->shadowPerPath, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
                                             d_totals ? d_totals + 2 : nullptr, stream);
                 if (rc) return rc;
                 timers.end(3, t0, stream);
-                st.occlusionRays += nShadow;
                 ++st.kernelLaunches;
             }
+            SELAS_CUDA_CHECK(ctx, cudaEventSynchronize(w->evCounts));
+            uint32_t nNext = w->h_counts[0], nShadow = w->h_counts[1];
+            st.occlusionRays += nShadow;
             n = nNext;
             cur ^= 1;
         }

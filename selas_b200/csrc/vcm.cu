@@ -887,6 +887,7 @@ struct VcmBuffers {
     uint32_t* h_counts = nullptr;
     SelasHashGrid* grid = nullptr;
     std::vector<cudaEvent_t> events;
+    cudaEvent_t evCounts = nullptr;
     std::vector<void*> owned;
 };
 
@@ -947,6 +948,7 @@ int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     VCM_TRY(vcmAlloc(ctx, w, &w->connPairs, nv));
 #undef VCM_TRY
     SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 8));
+    SELAS_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&w->evCounts, cudaEventDisableTiming));
     // the hash grid is rebuilt every iteration over a varying number of vertices: size it once for the worst case
     return hashGridReserve(ctx, &w->grid, nv, vmCount);
 }
@@ -1046,16 +1048,19 @@ int lightPass(SelasScene* scene, const SelasCamera& cam, const VcmParams& prm, f
                                                                 w->lvCount, w->rays[cur ^ 1], w->thrIdx[cur ^ 1], w->mis[cur ^ 1], w->shadowRays,
                                                                 w->shadowPayload, ctr);
         SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+        // counts go back for the next bounce's launch shapes; the shadow launch reads its count on the device and is enqueued before
+        // the host blocks, so the GPU stays busy while the host wakes up
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
-        uint32_t nNext = w->h_counts[0], nShadow = w->h_counts[1];
+        SELAS_CUDA_CHECK(ctx, cudaEventRecord(w->evCounts, stream));
         st.kernelLaunches += 2;
-        if (nShadow) {
-            rc = launchShadowAccumulate(scene, nullptr, nShadow, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream);
+        if (!(prm.flags & SELAS_VCM_NO_LIGHT_TRACING)) {
+            rc = launchShadowAccumulate(scene, ctr + 1, n, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream);
             if (rc) return rc;
-            st.occlusionRays += nShadow;
             ++st.kernelLaunches;
         }
+        SELAS_CUDA_CHECK(ctx, cudaEventSynchronize(w->evCounts));
+        uint32_t nNext = w->h_counts[0];
+        st.occlusionRays += w->h_counts[1];
         n = nNext;
         cur ^= 1;
     }
@@ -1085,6 +1090,7 @@ void freeVcm(SelasScene* scene) {
     for (void* p : w->owned) cudaFree(p);
     if (w->h_counts) cudaFreeHost(w->h_counts);
     for (cudaEvent_t e : w->events) cudaEventDestroy(e);
+    if (w->evCounts) cudaEventDestroy(w->evCounts);
     if (w->grid) selas_cuda_hashgrid_destroy(w->grid);
     delete w;
     scene->vcm = nullptr;
