@@ -28,7 +28,8 @@ def short_name(name):
     if "cub::" in s:
         s = "cub::" + re.search(r"cub::(?:\w+::)*(\w+)", s).group(1)
     if "at::" in s:
-        s = "torch " + re.search(r"at::(?:native::)?(\w+)", s).group(1)
+        m = re.search(r"at::(?:native::)?(\w+)", s)
+        s = "torch " + (m.group(1) if m else s[:40])
     return s
 
 
