@@ -215,7 +215,15 @@ typedef struct SelasSceneDesc {
     uint32_t                  lightSetCount;
     float                     backgroundIntensity[4]; /* SceneResourceData::backgroundIntensity */
     const SelasIblDesc*       ibl;           /* SceneResource::iblResource, or NULL: constant background (AreaLighting.cpp:415-437) */
+    uint32_t                  flags;         /* SELAS_SCENE_* */
+    uint32_t                  reserved;
 } SelasSceneDesc;
+/* SelasSceneDesc.flags.  SELAS_SCENE_TWO_LEVEL_BVH: keep instanced geometry once -- one object-space BVH8 per mesh under a top-level BVH8
+ * over the instances, rays transformed into object space on entry (what the reference gets from Embree instance geometries and its
+ * subscene-instance callbacks, SubsceneResource.cpp:63-79, SceneResource.cpp:87-187) -- instead of flattening every instance into
+ * world-space triangles.  Same hits and ids as the flattened form up to float rounding of the ray transform; without an instance list
+ * one identity instance per mesh is implied (instID0 = mesh index). */
+enum { SELAS_SCENE_TWO_LEVEL_BVH = 1 };
 
 /* Compile-time macros of the reference integrator made runtime (PathTracer.cpp:42-46, :248). */
 /* SelasRenderSettings.flags */

@@ -75,7 +75,7 @@ class SceneDesc(C.Structure):
     _fields_ = [("meshes", C.POINTER(MeshDesc)), ("meshCount", u32), ("instances", C.POINTER(InstanceDesc)),
                 ("instanceCount", u32), ("materials", C.POINTER(Material)), ("materialCount", u32),
                 ("lights", C.POINTER(Light)), ("lightCount", u32), ("lightSets", C.POINTER(LightSetRange)),
-                ("lightSetCount", u32), ("backgroundIntensity", f32 * 4), ("ibl", C.POINTER(IblDesc))]
+                ("lightSetCount", u32), ("backgroundIntensity", f32 * 4), ("ibl", C.POINTER(IblDesc)), ("flags", u32), ("reserved", u32)]
 
 
 class RenderSettings(C.Structure):
@@ -309,6 +309,9 @@ def camera_init(position, look_at, up, fov_degrees, width, height, znear=0.1, zf
     return cam
 
 
+SCENE_TWO_LEVEL_BVH = 1
+
+
 def texture_array(tex):
     a = np.ascontiguousarray(tex, dtype=np.float32)
     if a.ndim == 2:
@@ -331,7 +334,8 @@ class SceneData:
     meshes: list of dicts {positions (V,3) f32, indices (F,3|4) u32, normals?, tangents?, uvs?, material, lightSet, ptex?}
     """
 
-    def __init__(self, meshes, materials, lights=None, light_sets=None, background=(0, 0, 0, 0), instances=None, ibl=None):
+    def __init__(self, meshes, materials, lights=None, light_sets=None, background=(0, 0, 0, 0), instances=None, ibl=None, two_level=False):
+        self.two_level = two_level  # SELAS_SCENE_TWO_LEVEL_BVH: per-mesh object-space trees under a top-level tree over the instances
         self.ibl = ibl  # dict: light (H,W,3), marginal (H,), conditional (H,W), miss (h,w,3), rotation, exposure_scale -- see scenes.build_ibl
         self.meshes = []
         for m in meshes:
@@ -398,6 +402,7 @@ class SceneData:
         desc.lightSets = C.cast(self.light_sets.ctypes.data, C.POINTER(LightSetRange))
         desc.lightSetCount = self.light_sets.shape[0]
         desc.backgroundIntensity[:] = self.background
+        desc.flags = SCENE_TWO_LEVEL_BVH if getattr(self, "two_level", False) else 0
         if self.ibl is not None:
             i = self.ibl
             for k in ("light", "marginal", "conditional", "miss"):

@@ -264,6 +264,14 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
             inst[i].identity = memcmp(inst[i].m, I, sizeof(I)) == 0 ? 1u : 0u;
             inst[i].pad[0] = inst[i].pad[1] = 0;
         }
+    } else if (d->flags & SELAS_SCENE_TWO_LEVEL_BVH) {  // one identity instance per mesh, instID0 = mesh index
+        inst.resize(d->meshCount ? d->meshCount : 1);
+        for (uint32_t i = 0; i < inst.size(); ++i) {
+            memset(&inst[i], 0, sizeof(InstanceGpu));
+            inst[i].m[0] = inst[i].m[5] = inst[i].m[10] = inst[i].m[15] = 1.0f;
+            inst[i].mesh = d->meshCount ? i : 0xFFFFFFFFu;
+            inst[i].identity = 1;
+        }
     } else {  // every mesh once, identity, instID0 = 0
         inst.resize(1);
         memset(&inst[0], 0, sizeof(InstanceGpu));
@@ -301,7 +309,10 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
         g.ibl.present = 1;
     }
 
-    SELAS_TRY(buildBvh(scene, meshes, inst, g.instances));
+    if ((d->flags & SELAS_SCENE_TWO_LEVEL_BVH) && d->meshCount)
+        SELAS_TRY(buildBvhTwoLevel(scene, meshes, inst));
+    else
+        SELAS_TRY(buildBvh(scene, meshes, inst, g.instances));
     uint64_t attrBytes = 0;
     for (uint32_t m = 0; m < d->meshCount; ++m) {
         const SelasMeshDesc& md = d->meshes[m];

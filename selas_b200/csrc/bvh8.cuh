@@ -23,10 +23,15 @@
 
 namespace selas {
 
+struct InstanceTrace;  // internal.h
+
 struct Bvh8 {
     const float4* nodes;  // 5 per node
     const float4* tris;   // 3 per triangle
     uint32_t nodeCount, triCount;
+    // two-level form: the top-level tree's leaves are instance references (triangle records whose a.w is the flat instance index) and
+    // every mesh has its own object-space tree elsewhere in the same arrays (internal.h: InstanceTrace); null for the flattened form
+    const InstanceTrace* instances;
 };
 
 #ifndef SELAS_STACK_SIZE
@@ -44,7 +49,8 @@ SELAS_D float fminMin(float a, float b, float c) { return fminf(fminf(a, b), c);
 
 struct TraceResult {
     float t, u, v;
-    uint32_t tri;  // index into tris, 0xFFFFFFFF = none
+    uint32_t tri;   // index into tris, 0xFFFFFFFF = none
+    uint32_t inst;  // two-level form: flat instance index of the hit (the triangle record's own instID is 0 there)
 };
 
 // Quantised plane byte -> float without the conversion (XU) pipe.  The first version used (float)byte = I2F.U8, 48 per
@@ -207,6 +213,7 @@ SELAS_D void traceRay(const Bvh8& bvh, V3 o, V3 d, float tnear, float tfar, Trac
 
 // Fill the 32-byte hit record (and optional Ng) from a trace result.  The ids travel as integers: bit-casting a
 // small id to float and masking it lets the compiler emit abs.ftz.f32, which flushes the (denormal) pattern to 0.
+template <bool INST = false>
 SELAS_D void writeHit(const Bvh8& bvh, const TraceResult& r, float tfar, SelasHit* out, float4* ng) {
     uint4 h0, h1;
     if (r.tri == 0xFFFFFFFFu) {
@@ -219,7 +226,7 @@ SELAS_D void writeHit(const Bvh8& bvh, const TraceResult& r, float tfar, SelasHi
         bool second = (c.w >> 31) != 0;
         float u = second ? 1.0f - r.u : r.u, v = second ? 1.0f - r.v : r.v;
         h0 = make_uint4(__float_as_uint(r.t), __float_as_uint(u), __float_as_uint(v), a.w);
-        h1 = make_uint4(b.w, c.w & 0x7fffffffu, 0u, 0u);
+        h1 = make_uint4(b.w, INST ? r.inst : (c.w & 0x7fffffffu), 0u, 0u);
         if (ng) {
             V3 n = cross(v3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)),
                          v3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z)));

@@ -52,11 +52,20 @@ struct IblGpu {
     uint32_t present, pad;
 };
 
+// Two-level BVH (SELAS_SCENE_TWO_LEVEL_BVH): per flat instance, the world -> object transform the ray goes through when it enters the
+// instance (SceneInstanceIntersectFunction, SceneResource.cpp:87-142: MatrixMultiplyPoint / MatrixMultiplyVector with worldToLocal) and
+// where its mesh's BVH8 lives in the shared node / triangle arrays.
+struct InstanceTrace {
+    float w2l[12];  // row-vector affine: p_local = p_world * M, rows 0-2 linear part, row 3 translation
+    uint32_t nodeBase, triBase, mesh, pad;
+};
+
 // Everything the shade kernel needs, passed by value.
 struct SceneGpu {
     const float4* nodes;
     const float4* tris;
     uint32_t nodeCount, triCount;
+    const InstanceTrace* traceInstances;  // null: one flattened world-space BVH8
     const MeshGpu* meshes;
     const InstanceGpu* instances;
     const SelasMaterial* materials;
@@ -112,6 +121,7 @@ void setError(SelasContext* ctx, const char* fmt, ...);
 // trace.cu
 int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::vector<InstanceGpu>& hostInstances,
              const InstanceGpu* d_instances);
+int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::vector<InstanceGpu>& hostInstances);
 int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_ng4, uint32_t* d_counts,
                     uint32_t* d_rayCounter, cudaStream_t stream);
 int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_t* d_occ, uint32_t* d_counts, uint32_t* d_rayCounter,

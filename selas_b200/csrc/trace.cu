@@ -1,4 +1,6 @@
 // trace.cu -- BVH8 build driver and ray-cast launchers (translation unit compiled with FMA contraction on).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -34,39 +36,17 @@ inline uint32_t divUp(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 }  // namespace
 
-int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::vector<InstanceGpu>& inst, const InstanceGpu* d_instances) {
+// One BVH8 over n BuildTri records (Morton sort -> Karras radix tree -> refit -> per-level collapse).  out.nodes / out.tris are
+// plain cudaMalloc allocations owned by the caller; node and triangle indices inside them are relative to their own start.
+struct TreeOut {
+    float4* nodes = nullptr;
+    float4* tris = nullptr;
+    uint32_t nodeCount = 0, triCount = 0, levels = 0;
+};
+
+static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* d_bounds, uint32_t n, TreeOut& out) {
     SelasContext* ctx = scene->ctx;
     cudaStream_t st = ctx->stream;
-    cudaEvent_t ev0, ev1;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
-    cudaEventRecord(ev0, st);
-
-    // ---- count triangles per draw ----
-    struct Draw { uint32_t mesh, inst, base, tris; };
-    std::vector<Draw> draws;
-    uint64_t total = 0;
-    for (uint32_t ii = 0; ii < inst.size(); ++ii)
-        for (uint32_t m = 0; m < meshes.size(); ++m) {
-            if (inst[ii].mesh != 0xFFFFFFFFu && inst[ii].mesh != m) continue;
-            uint32_t t = meshes[m].faceCount * (meshes[m].indicesPerFace == 4 ? 2u : 1u);
-            if (t == 0) continue;
-            draws.push_back({m, ii, (uint32_t)total, t});
-            total += t;
-        }
-    if (total >= 0x7fffffffull) {
-        setError(ctx, "scene has %llu triangles; the builder is limited to 2^31-1", (unsigned long long)total);
-        return SELAS_ERR_UNSUPPORTED;
-    }
-    const uint32_t n = (uint32_t)total;
-    scene->stats = SelasBvhStats{};
-    scene->stats.triangleCount = n;
-    scene->gpu.nodes = nullptr;
-    scene->gpu.tris = nullptr;
-    scene->gpu.nodeCount = 0;
-    scene->gpu.triCount = 0;
-    if (n == 0) return SELAS_OK;
-
     TempFree tmp;
     auto tempAlloc = [&](void** p, size_t bytes) -> int {
         cudaError_t e = cudaMalloc(p, bytes + 16);
@@ -77,26 +57,13 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
         tmp.ptrs.push_back(*p);
         return SELAS_OK;
     };
-
-    BuildTri* d_tris;
-    uint32_t* d_bounds;
     uint64_t *d_keys, *d_keysAlt;
     uint32_t *d_vals, *d_valsAlt;
     int rc;
-    if ((rc = tempAlloc((void**)&d_tris, sizeof(BuildTri) * (size_t)n))) return rc;
-    if ((rc = tempAlloc((void**)&d_bounds, 6 * sizeof(uint32_t)))) return rc;
     if ((rc = tempAlloc((void**)&d_keys, sizeof(uint64_t) * (size_t)n))) return rc;
     if ((rc = tempAlloc((void**)&d_keysAlt, sizeof(uint64_t) * (size_t)n))) return rc;
     if ((rc = tempAlloc((void**)&d_vals, sizeof(uint32_t) * (size_t)n))) return rc;
     if ((rc = tempAlloc((void**)&d_valsAlt, sizeof(uint32_t) * (size_t)n))) return rc;
-
-    uint32_t boundsInit[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
-    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, st));
-    for (const Draw& d : draws) {
-        MeshDev md{meshes[d.mesh].positions, meshes[d.mesh].indices, meshes[d.mesh].faceCount, meshes[d.mesh].indicesPerFace};
-        gatherTrianglesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, d_instances[d.inst].m, inst[d.inst].identity != 0, d.mesh, d.inst,
-                                                                         d_tris, d.base, d_bounds);
-    }
     mortonKernel<<<divUp(n, 256), 256, 0, st>>>(d_tris, n, d_bounds, d_keys, d_vals);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
 
@@ -133,9 +100,15 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     // branching nodes B < L; chain nodes (one inner child) own >= 7 direct triangles: 4L + 7C <= n.  So the node
     // count is < 2L + C <= n/2.  The final triangle array has exactly n entries.
     const size_t maxNodes = (size_t)n / 2 + 2;
-    float4 *d_nodes, *d_outTris;
-    if ((rc = devAlloc(scene, &d_nodes, maxNodes * 5, true))) return rc;
-    if ((rc = devAlloc(scene, &d_outTris, (size_t)n * 3, true))) return rc;
+    float4 *d_nodes = nullptr, *d_outTris = nullptr;
+    if (cudaMalloc((void**)&d_nodes, maxNodes * 5 * sizeof(float4) + 16) != cudaSuccess ||
+        cudaMalloc((void**)&d_outTris, (size_t)n * 3 * sizeof(float4) + 16) != cudaSuccess) {
+        cudaFree(d_nodes);
+        setError(ctx, "cudaMalloc failed for the BVH8 arrays (%u primitives)", n);
+        return SELAS_ERR_MEMORY;
+    }
+    out.nodes = d_nodes;
+    out.tris = d_outTris;
     CollapseTask *d_tasksA, *d_tasksB;
     uint32_t* d_ctr;  // [0]=nodeCounter [1]=triCounter [2..]=per-level next counts
     if ((rc = tempAlloc((void**)&d_tasksA, sizeof(CollapseTask) * maxNodes))) return rc;
@@ -145,7 +118,7 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     ctrInit[0] = 1;  // root occupies node 0
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_ctr, ctrInit.data(), sizeof(uint32_t) * 260, cudaMemcpyHostToDevice, st));
     CollapseTask root;
-    root.bvh2 = (n == 1) ? 0u : 0u;  // internal node 0, or the only leaf (id n-1+0 = 0)
+    root.bvh2 = 0u;  // internal node 0, or the only leaf (id n-1+0 = 0)
     root.node = 0;
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_tasksA, &root, sizeof(root), cudaMemcpyHostToDevice, st));
     uint32_t taskCount = 1, level = 0;
@@ -163,24 +136,296 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     }
     uint32_t finalCtr[2];
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(finalCtr, d_ctr, sizeof(finalCtr), cudaMemcpyDeviceToHost, st));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    if (finalCtr[1] != n) {
+        setError(ctx, "BVH collapse emitted %u of %u triangles", finalCtr[1], n);
+        return SELAS_ERR_CUDA;
+    }
+    out.nodeCount = finalCtr[0];
+    out.triCount = n;
+    out.levels = level;
+    return SELAS_OK;
+}
+
+int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::vector<InstanceGpu>& inst, const InstanceGpu* d_instances) {
+    SelasContext* ctx = scene->ctx;
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+
+    // ---- count triangles per draw ----
+    struct Draw { uint32_t mesh, inst, base, tris; };
+    std::vector<Draw> draws;
+    uint64_t total = 0;
+    for (uint32_t ii = 0; ii < inst.size(); ++ii)
+        for (uint32_t m = 0; m < meshes.size(); ++m) {
+            if (inst[ii].mesh != 0xFFFFFFFFu && inst[ii].mesh != m) continue;
+            uint32_t t = meshes[m].faceCount * (meshes[m].indicesPerFace == 4 ? 2u : 1u);
+            if (t == 0) continue;
+            draws.push_back({m, ii, (uint32_t)total, t});
+            total += t;
+        }
+    if (total >= 0x7fffffffull) {
+        setError(ctx, "scene has %llu triangles; the builder is limited to 2^31-1", (unsigned long long)total);
+        return SELAS_ERR_UNSUPPORTED;
+    }
+    const uint32_t n = (uint32_t)total;
+    scene->stats = SelasBvhStats{};
+    scene->stats.triangleCount = n;
+    scene->gpu.nodes = nullptr;
+    scene->gpu.tris = nullptr;
+    scene->gpu.nodeCount = 0;
+    scene->gpu.triCount = 0;
+    scene->gpu.traceInstances = nullptr;
+    if (n == 0) return SELAS_OK;
+
+    TempFree tmp;
+    BuildTri* d_tris = nullptr;
+    uint32_t* d_bounds = nullptr;
+    if (cudaMalloc((void**)&d_tris, sizeof(BuildTri) * (size_t)n + 16) != cudaSuccess || cudaMalloc((void**)&d_bounds, 6 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaFree(d_tris);
+        setError(ctx, "cudaMalloc failed during BVH build (%u triangles)", n);
+        return SELAS_ERR_MEMORY;
+    }
+    tmp.ptrs.push_back(d_tris);
+    tmp.ptrs.push_back(d_bounds);
+    uint32_t boundsInit[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, st));
+    for (const Draw& d : draws) {
+        MeshDev md{meshes[d.mesh].positions, meshes[d.mesh].indices, meshes[d.mesh].faceCount, meshes[d.mesh].indicesPerFace};
+        gatherTrianglesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, d_instances[d.inst].m, inst[d.inst].identity != 0, d.mesh, d.inst,
+                                                                         d_tris, d.base, d_bounds);
+    }
+    TreeOut tree;
+    int rc = buildTree(scene, d_tris, d_bounds, n, tree);
+    if (tree.nodes) scene->allocations.push_back(tree.nodes);
+    if (tree.tris) scene->allocations.push_back(tree.tris);
+    if (rc) return rc;
     cudaEventRecord(ev1, st);
     SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
-    if (finalCtr[1] != n) {
-        setError(ctx, "BVH collapse emitted %u of %u triangles", finalCtr[1], n);
-        return SELAS_ERR_CUDA;
-    }
-    scene->gpu.nodes = d_nodes;
-    scene->gpu.tris = d_outTris;
-    scene->gpu.nodeCount = finalCtr[0];
+    scene->gpu.nodes = tree.nodes;
+    scene->gpu.tris = tree.tris;
+    scene->gpu.nodeCount = tree.nodeCount;
     scene->gpu.triCount = n;
-    scene->stats.nodeCount = finalCtr[0];
-    scene->stats.maxDepth = level;
+    scene->stats.nodeCount = tree.nodeCount;
+    scene->stats.maxDepth = tree.levels;
     scene->stats.buildMs = ms;
-    scene->stats.deviceBytes = (uint64_t)finalCtr[0] * 80ull + (uint64_t)n * 48ull;
+    scene->stats.deviceBytes = (uint64_t)tree.nodeCount * 80ull + (uint64_t)n * 48ull;
+    return SELAS_OK;
+}
+
+// ---- two-level build (SELAS_SCENE_TWO_LEVEL_BVH) -------------------------------------------------------------------------------
+// One object-space BVH8 per mesh that some instance uses, and a top-level BVH8 over the instances' world-space boxes, all in one node
+// array and one triangle array: [top level][mesh 0][mesh 1]...  Geometry is stored once however many instances refer to it -- what the
+// reference gets from rtcNewGeometry(RTC_GEOMETRY_TYPE_INSTANCE) / its user-geometry subscene instances (SubsceneResource.cpp:63-79,
+// SceneResource.cpp:218-249).  The top level reuses the triangle builder: instance i is fed as a degenerate "triangle" (lo, hi, lo)
+// whose bounds are the instance's box and whose primID is i.
+static uint32_t hostFloatFlip(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::vector<InstanceGpu>& inst) {
+    SelasContext* ctx = scene->ctx;
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+    scene->stats = SelasBvhStats{};
+    scene->gpu.nodes = nullptr;
+    scene->gpu.tris = nullptr;
+    scene->gpu.nodeCount = 0;
+    scene->gpu.triCount = 0;
+    scene->gpu.traceInstances = nullptr;
+
+    struct Blas {
+        TreeOut tree;
+        float lo[3], hi[3];
+        uint32_t nodeBase = 0, triBase = 0;
+        bool used = false;
+    };
+    std::vector<Blas> blas(meshes.size());
+    TreeOut top;
+    struct TreeGuard {  // the per-tree arrays are temporaries: everything is copied into the two shared arrays
+        std::vector<Blas>& b;
+        TreeOut& top;
+        ~TreeGuard() {
+            for (Blas& x : b) {
+                cudaFree(x.tree.nodes);
+                cudaFree(x.tree.tris);
+            }
+            cudaFree(top.nodes);
+            cudaFree(top.tris);
+        }
+    } guard{blas, top};
+    for (const InstanceGpu& in : inst) {
+        if (in.mesh >= meshes.size()) {
+            setError(ctx, "two-level BVH: every instance must name its mesh");
+            return SELAS_ERR_ARGUMENT;
+        }
+        blas[in.mesh].used = true;
+    }
+    uint64_t uniqueTris = 0, instancedTris = 0;
+    for (uint32_t m = 0; m < meshes.size(); ++m) {
+        const uint32_t t = meshes[m].faceCount * (meshes[m].indicesPerFace == 4 ? 2u : 1u);
+        if (!blas[m].used || t == 0) {
+            blas[m].used = false;
+            continue;
+        }
+        TempFree tmp;
+        BuildTri* d_tris = nullptr;
+        uint32_t* d_bounds = nullptr;
+        if (cudaMalloc((void**)&d_tris, sizeof(BuildTri) * (size_t)t + 16) != cudaSuccess || cudaMalloc((void**)&d_bounds, 6 * sizeof(uint32_t)) != cudaSuccess) {
+            cudaFree(d_tris);
+            setError(ctx, "cudaMalloc failed during the BVH build of mesh %u (%u triangles)", m, t);
+            return SELAS_ERR_MEMORY;
+        }
+        tmp.ptrs.push_back(d_tris);
+        tmp.ptrs.push_back(d_bounds);
+        uint32_t boundsInit[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, st));
+        MeshDev md{meshes[m].positions, meshes[m].indices, meshes[m].faceCount, meshes[m].indicesPerFace};
+        gatherTrianglesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, nullptr, true, m, 0u, d_tris, 0u, d_bounds);
+        int rc = buildTree(scene, d_tris, d_bounds, t, blas[m].tree);
+        if (rc) return rc;
+        uint32_t hb[6];
+        SELAS_CUDA_CHECK(ctx, cudaMemcpy(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 3; ++k) {
+            blas[m].lo[k] = floatUnflip(hb[k]);
+            blas[m].hi[k] = floatUnflip(hb[3 + k]);
+        }
+        uniqueTris += t;
+    }
+    // top level: one degenerate triangle per instance whose mesh has geometry
+    std::vector<BuildTri> fake;
+    float tlo[3] = {SELAS_FLOAT_MAX, SELAS_FLOAT_MAX, SELAS_FLOAT_MAX}, thi[3] = {-SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX};
+    for (uint32_t i = 0; i < inst.size(); ++i) {
+        const Blas& b = blas[inst[i].mesh];
+        if (!b.used) continue;
+        float lo[3] = {SELAS_FLOAT_MAX, SELAS_FLOAT_MAX, SELAS_FLOAT_MAX}, hi[3] = {-SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX};
+        for (int c = 0; c < 8; ++c) {
+            V3 p = v3((c & 1) ? b.hi[0] : b.lo[0], (c & 2) ? b.hi[1] : b.lo[1], (c & 4) ? b.hi[2] : b.lo[2]);
+            V3 q = mulPoint44(p, inst[i].m);
+            const float qq[3] = {q.x, q.y, q.z};
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = std::min(lo[k], qq[k]);
+                hi[k] = std::max(hi[k], qq[k]);
+            }
+        }
+        for (int k = 0; k < 3; ++k) {  // the object-space walk rounds differently from this box: keep a relative margin
+            const float pad = 1e-5f * (std::max(std::fabs(lo[k]), std::fabs(hi[k])) + (hi[k] - lo[k])) + 1e-30f;
+            lo[k] -= pad;
+            hi[k] += pad;
+            tlo[k] = std::min(tlo[k], lo[k]);
+            thi[k] = std::max(thi[k], hi[k]);
+        }
+        BuildTri t;
+        t.a = make_float4(lo[0], lo[1], lo[2], 0.f);
+        t.b = make_float4(hi[0], hi[1], hi[2], 0.f);
+        t.c = t.a;
+        memcpy(&t.a.w, &i, 4);             // primID = flat instance index
+        memcpy(&t.b.w, &inst[i].mesh, 4);  // geomID = mesh
+        memcpy(&t.c.w, &i, 4);
+        fake.push_back(t);
+        instancedTris += meshes[inst[i].mesh].faceCount * (meshes[inst[i].mesh].indicesPerFace == 4 ? 2u : 1u);
+    }
+    scene->stats.triangleCount = (uint32_t)std::min<uint64_t>(uniqueTris, 0xFFFFFFFFull);
+    if (fake.empty()) return SELAS_OK;
+    {
+        TempFree tmp;
+        BuildTri* d_fake = nullptr;
+        uint32_t* d_bounds = nullptr;
+        if (cudaMalloc((void**)&d_fake, sizeof(BuildTri) * fake.size() + 16) != cudaSuccess || cudaMalloc((void**)&d_bounds, 6 * sizeof(uint32_t)) != cudaSuccess) {
+            cudaFree(d_fake);
+            setError(ctx, "cudaMalloc failed during the top-level BVH build (%zu instances)", fake.size());
+            return SELAS_ERR_MEMORY;
+        }
+        tmp.ptrs.push_back(d_fake);
+        tmp.ptrs.push_back(d_bounds);
+        uint32_t hb[6] = {hostFloatFlip(tlo[0]), hostFloatFlip(tlo[1]), hostFloatFlip(tlo[2]), hostFloatFlip(thi[0]), hostFloatFlip(thi[1]), hostFloatFlip(thi[2])};
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, st));
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_fake, fake.data(), sizeof(BuildTri) * fake.size(), cudaMemcpyHostToDevice, st));
+        int rc = buildTree(scene, d_fake, d_bounds, (uint32_t)fake.size(), top);
+        if (rc) return rc;
+    }
+    // one node array, one triangle array: [top level][mesh 0][mesh 1]...
+    uint64_t totalNodes = top.nodeCount, totalTris = top.triCount;
+    for (Blas& b : blas)
+        if (b.used) {
+            b.nodeBase = (uint32_t)totalNodes;
+            b.triBase = (uint32_t)totalTris;
+            totalNodes += b.tree.nodeCount;
+            totalTris += b.tree.triCount;
+        }
+    if (totalNodes >= 0x7fffffffull || totalTris >= 0x7fffffffull) {
+        setError(ctx, "two-level BVH: %llu nodes / %llu triangles exceed the 2^31-1 index range", (unsigned long long)totalNodes, (unsigned long long)totalTris);
+        return SELAS_ERR_UNSUPPORTED;
+    }
+    float4 *d_nodes, *d_tris;
+    int rc;
+    if ((rc = devAlloc(scene, &d_nodes, (size_t)totalNodes * 5, true))) return rc;
+    if ((rc = devAlloc(scene, &d_tris, (size_t)totalTris * 3, true))) return rc;
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_nodes, top.nodes, sizeof(float4) * 5 * (size_t)top.nodeCount, cudaMemcpyDeviceToDevice, st));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_tris, top.tris, sizeof(float4) * 3 * (size_t)top.triCount, cudaMemcpyDeviceToDevice, st));
+    for (const Blas& b : blas)
+        if (b.used) {
+            SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_nodes + (size_t)b.nodeBase * 5, b.tree.nodes, sizeof(float4) * 5 * (size_t)b.tree.nodeCount,
+                                                  cudaMemcpyDeviceToDevice, st));
+            SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_tris + (size_t)b.triBase * 3, b.tree.tris, sizeof(float4) * 3 * (size_t)b.tree.triCount,
+                                                  cudaMemcpyDeviceToDevice, st));
+        }
+    // per instance: world -> object (inverse of the affine localToWorld, in double) and where its mesh's tree starts
+    std::vector<InstanceTrace> table(inst.size());
+    for (uint32_t i = 0; i < inst.size(); ++i) {
+        InstanceTrace& t = table[i];
+        memset(&t, 0, sizeof(t));
+        const float* m = inst[i].m;
+        const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], k = m[10];
+        const double det = a * (e * k - f * h) - b * (d * k - f * g) + c * (d * h - e * g);
+        if (blas[inst[i].mesh].used && !(std::fabs(det) > 0.0)) {
+            setError(ctx, "two-level BVH: instance %u has a singular localToWorld", i);
+            return SELAS_ERR_ARGUMENT;
+        }
+        const double id = det != 0.0 ? 1.0 / det : 0.0;
+        const double w[9] = {(e * k - f * h) * id, (c * h - b * k) * id, (b * f - c * e) * id,
+                             (f * g - d * k) * id, (a * k - c * g) * id, (c * d - a * f) * id,
+                             (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id};
+        for (int r = 0; r < 9; ++r) t.w2l[r] = (float)w[r];
+        const double tx = m[12], ty = m[13], tz = m[14];
+        t.w2l[9] = (float)-(tx * w[0] + ty * w[3] + tz * w[6]);
+        t.w2l[10] = (float)-(tx * w[1] + ty * w[4] + tz * w[7]);
+        t.w2l[11] = (float)-(tx * w[2] + ty * w[5] + tz * w[8]);
+        t.nodeBase = blas[inst[i].mesh].nodeBase;
+        t.triBase = blas[inst[i].mesh].triBase;
+        t.mesh = inst[i].mesh;
+    }
+    InstanceTrace* d_table;
+    if ((rc = devAlloc(scene, &d_table, table.size(), true))) return rc;
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_table, table.data(), sizeof(InstanceTrace) * table.size(), cudaMemcpyHostToDevice, st));
+    cudaEventRecord(ev1, st);
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    scene->gpu.nodes = d_nodes;
+    scene->gpu.tris = d_tris;
+    scene->gpu.nodeCount = (uint32_t)totalNodes;
+    scene->gpu.triCount = (uint32_t)totalTris;
+    scene->gpu.traceInstances = d_table;
+    scene->stats.nodeCount = (uint32_t)totalNodes;
+    scene->stats.maxDepth = top.levels;
+    scene->stats.buildMs = ms;
+    scene->stats.reserved = (uint32_t)std::min<uint64_t>(instancedTris, 0xFFFFFFFFull);  // triangles a flattened build would have stored
+    scene->stats.deviceBytes = totalNodes * 80ull + totalTris * 48ull + table.size() * sizeof(InstanceTrace);
     return SELAS_OK;
 }
 
@@ -190,8 +435,12 @@ static Bvh8 bvhOf(const SelasScene* s) {
     b.tris = s->gpu.tris;
     b.nodeCount = s->gpu.nodeCount;
     b.triCount = s->gpu.triCount;
+    b.instances = s->gpu.traceInstances;
     return b;
 }
+
+// the two-level variant of the kernel only when the scene was built that way: the flattened form keeps its register budget
+#define SELAS_TRACE_LAUNCH(MODE, COUNT) (scene->gpu.traceInstances ? traceKernel<MODE, COUNT, true> : traceKernel<MODE, COUNT, false>)
 
 static int traceGrid(const SelasContext* ctx) { return ctx->smCount * SELAS_TRACE_CTAS_PER_SM; }
 
@@ -202,10 +451,10 @@ int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, Selas
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
     int grid = traceGrid(ctx);
     if (d_counts)
-        traceKernel<0, true><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts,
+        SELAS_TRACE_LAUNCH(0, true)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts,
                                                                         nullptr, nullptr, d_rayCounter, nullptr);
     else
-        traceKernel<0, false><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, nullptr,
+        SELAS_TRACE_LAUNCH(0, false)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, nullptr,
                                                                          nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
@@ -218,10 +467,10 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
     int grid = traceGrid(ctx);
     if (d_counts)
-        traceKernel<1, true><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr,
+        SELAS_TRACE_LAUNCH(1, true)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr,
                                                                         nullptr, d_rayCounter, nullptr);
     else
-        traceKernel<1, false><<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, nullptr, nullptr,
+        SELAS_TRACE_LAUNCH(1, false)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, nullptr, nullptr,
                                                                          nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
@@ -233,10 +482,10 @@ int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t max
                             uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
     if (d_totals)
-        traceKernel<0, true><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
+        SELAS_TRACE_LAUNCH(0, true)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
                                                                                   nullptr, nullptr, d_rayCounter, d_totals);
     else
-        traceKernel<0, false><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
+        SELAS_TRACE_LAUNCH(0, false)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
                                                                                    nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
@@ -246,10 +495,10 @@ int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN
                            float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
     if (d_totals)
-        traceKernel<2, true><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
+        SELAS_TRACE_LAUNCH(2, true)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
                                                                                   d_payload, d_film, d_rayCounter, d_totals);
     else
-        traceKernel<2, false><<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
+        SELAS_TRACE_LAUNCH(2, false)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
                                                                                    d_payload, d_film, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;

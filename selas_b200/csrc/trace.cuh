@@ -7,6 +7,7 @@
 // moved as two 16-byte vectors.
 #pragma once
 #include "bvh8.cuh"
+#include "internal.h"
 
 namespace selas {
 
@@ -33,7 +34,20 @@ namespace selas {
 // MODE 0: closest hit -> hits (+Ng); 1: any hit -> occluded byte; 2: any hit -> film[pixel] += payload.rgb when
 // unoccluded (the NEE shadow ray of PathTracer.cpp:186-191 fused with FramebufferWriter_Write).
 // nPtr != null: the ray count is read from device memory (wavefront queues), n is then only an upper bound.
-template <int MODE, bool COUNT>
+// INST: two-level traversal (SceneInstanceIntersectFunction / InstanceOccludedFunction, SceneResource.cpp:87-187): a top-level leaf is an
+// instance; the lane keeps what is left of the top-level node on its stack, maps the ray into the instance's object space
+// (MatrixMultiplyPoint / MatrixMultiplyVector with worldToLocal -- the direction is not renormalised, so t means the same in both
+// spaces, as in the reference), walks the mesh's tree with the same stack, and restores the world ray when the stack is back at the mark.
+SELAS_D void setupRayDirection(V3 d, V3& idir, bool& negx, bool& negy, bool& negz, uint32_t& octInv4) {
+    const float tiny = 1e-30f;
+    idir = v3(1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)), 1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
+              1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
+    negx = d.x < 0.0f; negy = d.y < 0.0f; negz = d.z < 0.0f;
+    uint32_t oct = (negx ? 4u : 0u) | (negy ? 2u : 0u) | (negz ? 1u : 0u);
+    octInv4 = (7u - oct) * 0x01010101u;
+}
+
+template <int MODE, bool COUNT, bool INST = false>
 __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n,
                                                                    const uint32_t* __restrict__ nPtr,
                                                                    SelasHit* __restrict__ hits, uint8_t* __restrict__ occluded,
@@ -42,6 +56,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                                                                    uint32_t* __restrict__ nextRay,
                                                                    unsigned long long* __restrict__ totals) {
     constexpr bool ANY = MODE != 0;
+    static_assert(!(INST && SELAS_TRI_POSTPONE_DIV), "parked triangle groups are not carried across instance boundaries");
     if (nPtr) n = min(n, *nPtr);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ltMask = (1u << lane) - 1u;
@@ -58,7 +73,12 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
     bool negx = false, negy = false, negz = false;
     uint32_t octInv4 = 0;
     TraceResult res;
-    res.t = 0.f; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
+    res.t = 0.f; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu; res.inst = 0u;
+    // two-level state (INST only): world ray while inside an instance, stack mark, the instance's node / triangle bases
+    V3 ow = v3(0.f), dw = v3(0.f);
+    int spMark = 0;
+    uint32_t nodeBase = 0u, triBase = 0u, curInst = 0u;
+    bool inBlas = false;
     uint32_t rayIdx = 0xFFFFFFFFu;
     uint32_t nNodes = 0, nTris = 0;
     unsigned long long sumNodes = 0, sumTris = 0;
@@ -83,15 +103,10 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                     tnear = r0.w;
                     tfar = r1.w;
                     tmax = tfar;
-                    const float tiny = 1e-30f;
-                    idir = v3(1.0f / (fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x)),
-                              1.0f / (fabsf(d.y) > tiny ? d.y : copysignf(tiny, d.y)),
-                              1.0f / (fabsf(d.z) > tiny ? d.z : copysignf(tiny, d.z)));
-                    negx = d.x < 0.0f; negy = d.y < 0.0f; negz = d.z < 0.0f;
-                    uint32_t oct = (negx ? 4u : 0u) | (negy ? 2u : 0u) | (negz ? 1u : 0u);
-                    octInv4 = (7u - oct) * 0x01010101u;
+                    setupRayDirection(d, idir, negx, negy, negz, octInv4);
                     res.t = tfar; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
                     sp = 0;
+                    if (INST) { inBlas = false; nodeBase = 0u; triBase = 0u; }
                     // A ray with a non-finite origin / direction would pass every slab test (NaN compares false both ways)
                     // and walk the whole tree; Embree reports such rays as misses, and so does this kernel, immediately.
                     const bool valid = isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z) &&
@@ -120,7 +135,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                 if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
                 uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
                 uint32_t rel = __popc(hitsImask & ~(0xffffffffu << slot));
-                const float4* np = bvh.nodes + (size_t)(group.x + rel) * 5;
+                const float4* np = bvh.nodes + (size_t)((INST ? nodeBase : 0u) + group.x + rel) * 5;
                 float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 if (COUNT) ++nNodes;
                 uint32_t hitMask = intersectNode(n0, n1, n2, n3, n4, o, idir, negx, negy, negz, octInv4, tnear, tmax);
@@ -152,6 +167,29 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                 uint32_t bit = 31u - __clz(triGroup.y);
                 triGroup.y &= ~(1u << bit);
                 uint32_t ti = triGroup.x + bit;
+                if (INST && !inBlas) {
+                    // top-level leaf: enter the instance.  What is left of this leaf group and of the current node goes on the stack
+                    // (below the mark), then the lane continues in object space from the root of the mesh's tree.
+                    const uint32_t ii = __float_as_uint(__ldg(bvh.tris + (size_t)ti * 3).w);
+                    if (triGroup.y != 0u && sp < SELAS_STACK_SIZE) stack[sp++] = triGroup;
+                    if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
+                    spMark = sp;
+                    ow = o; dw = d;
+                    const float4* ip = reinterpret_cast<const float4*>(bvh.instances + ii);
+                    float4 m0 = __ldg(ip), m1 = __ldg(ip + 1), m2 = __ldg(ip + 2);
+                    uint4 m3 = __ldg(reinterpret_cast<const uint4*>(ip + 3));
+                    // w2l rows: r0 = (m0.x, m0.y, m0.z), r1 = (m0.w, m1.x, m1.y), r2 = (m1.z, m1.w, m2.x), t = (m2.y, m2.z, m2.w)
+                    o = v3(ow.x * m0.x + ow.y * m0.w + ow.z * m1.z + m2.y, ow.x * m0.y + ow.y * m1.x + ow.z * m1.w + m2.z,
+                           ow.x * m0.z + ow.y * m1.y + ow.z * m2.x + m2.w);
+                    d = v3(dw.x * m0.x + dw.y * m0.w + dw.z * m1.z, dw.x * m0.y + dw.y * m1.x + dw.z * m1.w, dw.x * m0.z + dw.y * m1.y + dw.z * m2.x);
+                    setupRayDirection(d, idir, negx, negy, negz, octInv4);
+                    nodeBase = m3.x; triBase = m3.y; curInst = ii;
+                    inBlas = true;
+                    group = make_uint2(0u, 0x80000000u);
+                    triGroup = make_uint2(0u, 0u);
+                    break;
+                }
+                if (INST) ti += triBase;
                 const float4* tp = bvh.tris + (size_t)ti * 3;
                 float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 if (COUNT) ++nTris;
@@ -159,8 +197,16 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                 if (intersectTri(a, b, c, o, d, tnear, tmax, t, u, v)) {
                     tmax = t;
                     res.t = t; res.u = u; res.v = v; res.tri = ti;
+                    if (INST) res.inst = curInst;
                     if (ANY) { finished = true; break; }
                 }
+            }
+            if (INST && inBlas && !finished && (group.y & 0xff000000u) == 0u && sp == spMark) {
+                // the instance's tree is exhausted: back to world space and to what was left at the top level
+                o = ow; d = dw;
+                setupRayDirection(d, idir, negx, negy, negz, octInv4);
+                inBlas = false;
+                nodeBase = 0u; triBase = 0u;
             }
             if (!finished && (group.y & 0xff000000u) == 0u) {
 #if SELAS_TRI_POSTPONE_DIV
@@ -183,7 +229,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                         atomicAdd(px + 1, pl.y);
                         atomicAdd(px + 2, pl.z);
                     }
-                } else writeHit(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
+                } else writeHit<INST>(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
                 if (COUNT) {
                     if (counts) { counts[2 * (size_t)rayIdx] = nNodes; counts[2 * (size_t)rayIdx + 1] = nTris; }
                     sumNodes += nNodes;

@@ -338,6 +338,7 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
     desc.lightSetCount = (uint32_t)scene->lightSets.size();
     memcpy(desc.backgroundIntensity, scene->backgroundIntensity, sizeof(desc.backgroundIntensity));
     desc.ibl = scene->ibl;
+    desc.flags = scene->flags;
     if (selas_cuda_scene_create(scene->gpu, &desc, &scene->gpuScene) != SELAS_OK) {
         Error e = Error_("%s", selas_cuda_last_error(scene->gpu));
         ShutdownSceneResource(scene);
@@ -786,6 +787,7 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
     scene->meshes.clear();
     scene->instances.clear();
     scene->materials.clear();
+    scene->flags |= SELAS_SCENE_TWO_LEVEL_BVH;  // a baked scene is instances of models: keep each model's geometry once
     scene->lights = bs.lights;
     scene->lightSets = bs.lightSetRanges;
     memcpy(scene->backgroundIntensity, bs.backgroundIntensity, 16);

@@ -96,6 +96,7 @@ struct SceneResource {
     std::vector<SelasLight> lights;
     std::vector<SelasLightSetRange> lightSets;
     float backgroundIntensity[4] = {0, 0, 0, 0};
+    uint32_t flags = 0;  // SELAS_SCENE_*: LoadBakedScene sets SELAS_SCENE_TWO_LEVEL_BVH so instanced models are stored once
     const SelasIblDesc* ibl = nullptr;  // SceneResource::iblResource (borrowed), or null: constant background
     std::vector<struct TextureResource*> textures;  // base colour textures loaded by LoadBakedScene (owned; freed by ShutdownSceneResource)
     std::vector<std::string> textureNames;
