@@ -105,6 +105,44 @@ def row_raycast(ctx, torch, dev, stream, orc):
     return out
 
 
+def row_instancing(ctx, torch, dev, stream, n_inst=20000):
+    """Flattened vs two-level BVH (SELAS_SCENE_TWO_LEVEL_BVH) on a forest of instanced spheres: bytes on the device, build time and
+    primary closest-hit rate.  The flattened build stores every instance's triangles; the two-level one stores each mesh once."""
+    rng = np.random.default_rng(5)
+    sph = scenes.displaced_sphere(64, 128, as_quads=True)  # 16,384 triangles
+    floor = dict(positions=np.array([[-200, -2, -200], [-200, -2, 200], [200, -2, 200], [200, -2, -200]], np.float32),
+                 indices=np.array([[0, 1, 2, 3]], np.uint32), material=0, lightSet=0)
+    inst = [(1, np.eye(4, dtype=np.float32))]
+    for _ in range(n_inst):
+        a, s = rng.uniform(0, 2 * np.pi), rng.uniform(0.4, 1.6)
+        c, sn = np.cos(a), np.sin(a)
+        inst.append((0, np.array([[s * c, 0, -s * sn, 0], [0, s * rng.uniform(0.7, 1.3), 0, 0], [s * sn, 0, s * c, 0],
+                                  [rng.uniform(-180, 180), rng.uniform(-1, 8), rng.uniform(-180, 180), 1]], np.float32)))
+    mats = np.array([scenes.material(**scenes.REFERENCE_MATERIALS["RoughDiffuse"])])
+    cam = capi.camera_init((0.0, 60.0, -260.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 50.0, 1920, 1080)
+    rays = scenes.primary_rays(cam, 1920, 1080)
+    n = rays.size
+    d_r = to_dev(torch, dev, rays)
+    d_h = torch.empty(n * 32, dtype=torch.uint8, device=dev)
+    out = {"instances": n_inst, "triangles_per_instance": 64 * 128 * 2, "rays": int(n)}
+    hits = {}
+    for name, two in (("flattened", False), ("two_level", True)):
+        t0 = time.perf_counter()
+        sc = capi.Scene(ctx, capi.SceneData([sph, floor], mats, None, None, instances=inst, two_level=two))
+        create_s = time.perf_counter() - t0
+        st = sc.bvh_stats()
+        ms = median_ms(torch, stream, lambda: sc.intersect_device(n, d_r.data_ptr(), d_h.data_ptr(), 0, stream.cuda_stream))
+        hits[name] = sc.intersect(rays)
+        out[name] = {"scene_create_s": create_s, "bvh_build_ms": st.buildMs, "stored_triangles": int(st.triangleCount), "bvh_nodes": int(st.nodeCount),
+                     "device_mb": st.deviceBytes / 1e6, "primary_closest_ms": ms, "mrays_per_s": n / ms / 1e3}
+        sc.close()
+    a, b = hits["flattened"], hits["two_level"]
+    same = (a["geomID"] == b["geomID"]) & (a["primID"] == b["primID"]) & (a["instID0"] == b["instID0"])
+    out["id_agreement_two_level_vs_flattened"] = float(same.mean())
+    out["hit_fraction"] = float((a["geomID"] != capi.SELAS_INVALID_ID).mean())
+    return out
+
+
 def row_ptex(ctx, torch, dev, stream, grid, lookups):
     ptexref = oracle_binding.load_ptexref()
     if ptexref is None:
@@ -258,7 +296,7 @@ def main():
     ap.add_argument("--ptex-grid", type=int, default=800)
     ap.add_argument("--ptex-lookups", type=int, default=64_000_000)
     ap.add_argument("--grid-points", type=int, default=8_000_000)
-    ap.add_argument("--rows", default="raycast,ptex,hashgrid,bsdf")
+    ap.add_argument("--rows", default="raycast,ptex,hashgrid,bsdf,instancing")
     args = ap.parse_args()
     import torch
 
@@ -278,6 +316,8 @@ def main():
         doc["vcm_hashgrid"] = row_hashgrid(ctx, torch, dev, stream, args.grid_points, args.grid_points)
     if "bsdf" in rows:
         doc["disney_bsdf_operators"] = row_bsdf(ctx)
+    if "instancing" in rows:
+        doc["instancing_forest"] = row_instancing(ctx, torch, dev, stream)
     print(json.dumps(doc, indent=1))
 
 
