@@ -874,8 +874,9 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
                     return Error_("LoadBakedScene: mesh %s uses a Ptex base colour (%s/%s.ptx): pass it through SceneMesh::ptex", bm.name.c_str(),
                                   materialTexture[material].c_str(), bm.name.c_str());
                 ReturnError_(textureFor(materialTexture[material], &mesh.baseColorTexture));
-                if (scene->materials[material].flags & SELAS_MAT_DISPLACEMENT)
-                    return Error_("LoadBakedScene: mesh %s uses a displaced subdivision surface, which is not supported", bm.name.c_str());
+                // eDisplacementEnabled materials are plain triangle / quad meshes in the reference as built (EnableDisplacement_ 0,
+                // ModelResource.cpp:18,:251-252) and eAlphaTested ones pass every hit (CalculatePassesAlphaTest returns true,
+                // SurfaceParameters.cpp:344-347): nothing to do for either
                 // the mesh's vertices: indices are absolute into the model-wide arrays (SetMeshVertexAttributes, ModelResource.cpp:164-199);
                 // take the span they touch and rebase
                 const uint32_t* ix = model.indices.data() + bm.indexOffset;

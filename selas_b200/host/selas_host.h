@@ -195,8 +195,9 @@ Error ReadSceneResource(const char* filepath, BakedScene* scene);
 // ReadSceneResource + InitializeSceneResource of the reference (SceneResource.cpp:266-330) for `<root>_Assets/...`: the scene blob, its
 // subscenes, their models and the IBL.  The two instancing levels are flattened: every (subscene instance, model instance, mesh)
 // becomes one SelasInstanceDesc with localToWorld = model.localToWorld * subscene.localToWorld (ModelDataFromRayIds,
-// SceneResource.cpp:362-378); materials are resolved like FindMeshMaterial (ModelResource.cpp:214-235).  Curves and displaced
-// subdivision meshes are reported as unsupported.  Base colour textures of non-Ptex materials are loaded from their "Textures" blobs
+// SceneResource.cpp:362-378); materials are resolved like FindMeshMaterial (ModelResource.cpp:214-235).  Curves are reported as
+// unsupported; displacement and alpha testing are inert in the reference as built (EnableDisplacement_ 0; CalculatePassesAlphaTest
+// returns true) and are therefore loaded as plain meshes.  Base colour textures of non-Ptex materials are loaded from their "Textures" blobs
 // (TextureCache::LoadTextureResource, TextureCache.cpp:68-96: one copy per name; an empty name means the constant colour).
 // `scene` is left ready for InitializeSceneResource(scene, device).
 Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* scene, ImageBasedLight* ibl, std::vector<BakedCamera>* cameras);
