@@ -87,3 +87,37 @@ def test_config3_render_properties(ctx):
     assert st3.closestRays != st.closestRays
     assert abs(np.median(other[0].sum(axis=2)) / np.median(full[0].sum(axis=2)) - 1.0) < 0.03
     sc.close()
+
+
+def test_config5_hashgrid_properties(ctx, oracle):
+    """8M light vertices / 8M cells (the configs[4] microbench size): the arrays are a counting sort of the points by hashed cell --
+    checked as invariants in numpy -- and the range query of a vertex always returns the vertex itself; a slice of queries is compared
+    with the oracle's SearchHashGrid over the GPU-built arrays."""
+    n = cells = 8_000_000
+    rng = np.random.default_rng(4)
+    pos = np.empty((n, 3), np.float32)
+    pos[: n // 2] = np.stack([rng.uniform(-6, 6, n // 2), np.zeros(n // 2), rng.uniform(-6, 6, n // 2)], axis=1)  # the floor
+    d = rng.normal(size=(n - n // 2, 3))
+    pos[n // 2:] = (d / np.linalg.norm(d, axis=1, keepdims=True) * 1.2 + [0, 1.2, 0]).astype(np.float32)          # the sphere
+    radius = np.float32(0.0025 * 8.57)
+    grid = capi.HashGrid(ctx, pos, float(radius), cells)
+    ends, idx, aabb = grid.read()
+    np.testing.assert_array_equal(aabb, np.concatenate([pos.min(axis=0), pos.max(axis=0)]))
+    assert ends[-1] == n and np.all(np.diff(ends.astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(idx), np.arange(n, dtype=np.uint32))  # a permutation
+    # every point sits in the cell its position hashes to (GetCellIndex with the reference's 64-bit arithmetic), ascending inside a cell
+    inv = np.float32(1.0) / (np.float32(2.0) * radius)
+    c = np.floor(inv * (pos - aabb[:3])).astype(np.int64)
+    h = ((c[:, 0] * 73856093) ^ (c[:, 1] * 19349663) ^ (c[:, 2] * 83492791)).astype(np.uint64) % np.uint64(cells)
+    cell_of_slot = np.searchsorted(ends, np.arange(n), side="right")
+    np.testing.assert_array_equal(h[idx], cell_of_slot.astype(np.uint64))
+    same_cell = cell_of_slot[1:] == cell_of_slot[:-1]
+    assert np.all(idx[1:][same_cell] > idx[:-1][same_cell])
+    # a vertex is always within its own radius; compare a slice of queries with the oracle walking the GPU-built arrays
+    pick = rng.choice(n, size=20000, replace=False)
+    counts, found = grid.query(pos[pick], 64)
+    assert counts.min() >= 1 and np.all((found == pick[:, None].astype(np.uint32)).any(axis=1) | (counts > 64))
+    oc, of = oracle.hashgrid_query(pos, float(radius), cells, (ends, idx, aabb), pos[pick], 64)
+    np.testing.assert_array_equal(counts, oc)
+    np.testing.assert_array_equal(found, of)
+    grid.close()
