@@ -912,6 +912,9 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
             }
         }
     }
+    // geometry exists in the scene only through instances: without any, nothing is there to hit (an empty instance list would otherwise
+    // mean "every mesh once" to selas_cuda_scene_create)
+    if (scene->instances.empty()) scene->meshes.clear();
     return Success_;
 }
 
