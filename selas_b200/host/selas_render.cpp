@@ -98,25 +98,34 @@ int main(int argc, char** argv) {
     auto t1 = std::chrono::steady_clock::now();
     printf("Scene load time %fms\n", std::chrono::duration<double, std::milli>(t1 - t0).count());  // main.cpp:106-107
 
-    RayCastCameraSettings camera;
-    if (bakedScene && !bakedCameras.empty())  // SetupSceneCamera(scene, 0, width, height, camera), main.cpp:116-117
-        InitializeRayCastCamera(bakedCameras[0].settings, width, height, camera);
-    else
-        SetupCornellCamera(width, height, camera);
-    SelasRenderStats stats;
-    if (deferred) {
-        DeferredPathTracerSettings ds;
-        ds.seed = settings.seed;
-        if (settings.maxBounceCount != 8) ds.maxBounceCount = settings.maxBounceCount;
-        ExitMainOnError_(DeferredPathTracer::GenerateImage(&scene, camera, name, ds, &stats));
-    } else
-        ExitMainOnError_(PathTracer::GenerateImage(&scene, camera, name, settings, &stats));
-    auto t2 = std::chrono::steady_clock::now();
-    printf("Scene render time %fms\n", std::chrono::duration<double, std::milli>(t2 - t1).count());  // main.cpp:124-125
-    printf("{\"paths\": %llu, \"closest_rays\": %llu, \"occlusion_rays\": %llu, \"kernel_launches\": %llu, \"device_ms\": %.3f, "
-           "\"samples_per_s\": %.1f}\n",
-           (unsigned long long)stats.pathSamples, (unsigned long long)stats.closestRays, (unsigned long long)stats.occlusionRays,
-           (unsigned long long)stats.kernelLaunches, stats.renderMs, stats.renderMs > 0 ? stats.pathSamples / (stats.renderMs * 1e-3) : 0.0);
+    // main.cpp:115-126: one image per scene camera, named after the camera; the synthetic scene has one
+    const size_t cameraCount = (bakedScene && !bakedCameras.empty()) ? bakedCameras.size() : 1;
+    for (size_t scan = 0; scan < cameraCount; ++scan) {
+        RayCastCameraSettings camera;
+        const char* imageName = name;
+        if (bakedScene && !bakedCameras.empty()) {  // SetupSceneCamera(scene, scan, width, height, camera)
+            InitializeRayCastCamera(bakedCameras[scan].settings, width, height, camera);
+            if (!bakedCameras[scan].name.empty() && !strcmp(name, "cornell")) imageName = bakedCameras[scan].name.c_str();
+        } else {
+            SetupCornellCamera(width, height, camera);
+        }
+        auto tr0 = std::chrono::steady_clock::now();
+        SelasRenderStats stats;
+        if (deferred) {
+            DeferredPathTracerSettings ds;
+            ds.seed = settings.seed;
+            if (settings.maxBounceCount != 8) ds.maxBounceCount = settings.maxBounceCount;
+            ExitMainOnError_(DeferredPathTracer::GenerateImage(&scene, camera, imageName, ds, &stats));
+        } else {
+            ExitMainOnError_(PathTracer::GenerateImage(&scene, camera, imageName, settings, &stats));
+        }
+        auto tr1 = std::chrono::steady_clock::now();
+        printf("Scene render time %fms\n", std::chrono::duration<double, std::milli>(tr1 - tr0).count());  // main.cpp:124-125
+        printf("{\"image\": \"%s\", \"paths\": %llu, \"closest_rays\": %llu, \"occlusion_rays\": %llu, \"kernel_launches\": %llu, \"device_ms\": %.3f, "
+               "\"samples_per_s\": %.1f}\n",
+               imageName, (unsigned long long)stats.pathSamples, (unsigned long long)stats.closestRays, (unsigned long long)stats.occlusionRays,
+               (unsigned long long)stats.kernelLaunches, stats.renderMs, stats.renderMs > 0 ? stats.pathSamples / (stats.renderMs * 1e-3) : 0.0);
+    }
     ShutdownSceneResource(&scene);
     return 0;
 }

@@ -266,3 +266,17 @@ def test_baked_scene_golden(host):
     np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])
     np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))
     assert materials.tobytes() == want.materials.tobytes()
+
+
+@pytest.mark.gpu
+def test_selas_render_baked_scene(host, tmp_path):
+    """The reference's main() for a baked scene: selas_render --scene/--assets with the DeferredPathTracer (main.cpp:115-126), one image
+    per scene camera, named after the camera."""
+    exe = LIB / "selas_render"
+    root = str(GOLDEN / "baked_scene") + "/"
+    out = subprocess.run([str(exe), "--scene", "twolevel", "--assets", root, "--integrator", "deferred", "--width", "96", "--height", "64", "--depth", "24"],
+                         cwd=tmp_path, capture_output=True, text=True, check=True).stdout
+    stats = json.loads(out.strip().splitlines()[-1])
+    assert stats["image"] == "main" and stats["paths"] == 96 * 64 * 16 and stats["occlusion_rays"] > 0
+    img = read_hdr(tmp_path / "_Images" / "main_0.hdr")
+    assert img.shape == (64, 96, 3) and np.isfinite(img).all() and img.mean() > 0.01
