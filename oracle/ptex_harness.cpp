@@ -82,6 +82,39 @@ int ptexref_eval(const char* path, size_t n, const int32_t* faceid, const float*
     return 0;
 }
 
+// Persistent form for the CPU integrator's Ptex hook: one PtexCache + texture per handle (TextureCache.cpp:49-57, :99-126);
+// every lookup makes its own filter exactly as the reference's shading does (SurfaceParameters.cpp:199-206), which is also
+// what makes it callable from several threads at once.
+struct PtexRefHandle {
+    PtexCache* cache;
+    PtexTexture* tex;
+};
+
+void* ptexref_open(const char* path) {
+    Ptex::String err;
+    PtexCache* cache = PtexCache::create(128, (size_t)1 << 30, true, nullptr, nullptr);
+    PtexTexture* tex = cache->get(path, err);
+    if (!tex) { cache->release(); return nullptr; }
+    return new PtexRefHandle{cache, tex};
+}
+
+void ptexref_eval1(void* handle, int faceid, float u, float v, float* rgb3) {
+    PtexRefHandle* h = (PtexRefHandle*)handle;
+    PtexFilter::Options opts(PtexFilter::f_bspline);
+    PtexFilter* filter = PtexFilter::getFilter(h->tex, opts);
+    rgb3[0] = rgb3[1] = rgb3[2] = 0.0f;
+    filter->eval(rgb3, 0, 3, faceid, u, v, 0, 0, 0, 0);
+    filter->release();
+}
+
+void ptexref_close(void* handle) {
+    PtexRefHandle* h = (PtexRefHandle*)handle;
+    if (!h) return;
+    h->tex->release();
+    h->cache->release();
+    delete h;
+}
+
 int ptexref_info(const char* path, int* out8) {
     Ptex::String err;
     PtexTexture* tex = PtexTexture::open(path, err, true);

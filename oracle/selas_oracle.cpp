@@ -36,6 +36,10 @@ struct Mesh {
     Texture texture;  // base colour texture (texels above), or texels == nullptr
     std::vector<uint32_t> indices;
     uint32_t faceCount, indicesPerFace, materialIndex, lightSetIndex;
+    // Ptex base colour lookup of this mesh (orc_scene_set_ptex): the checker's stand-in for TextureCache + PtexFilter::eval,
+    // SurfaceParameters.cpp:196-208.  Tests bind it to the reference's own Ptex library (oracle/_ref/libptex_ref.so).
+    void (*ptexEval)(void* user, int faceid, float u, float v, float* rgb3) = nullptr;
+    void* ptexUser = nullptr;
 };
 struct Instance {
     uint32_t mesh;
@@ -195,7 +199,11 @@ static void surfaceParams(const Scene& sc, const SelasRay& r, const SelasHit& h,
         b = cross(n, t);
     }
     V3 base = v3(mat.baseColor);
-    if (mesh.texture.texels) {  // SurfaceParameters.cpp:186-190, :209-214
+    if (mesh.ptexEval && (mat.flags & SELAS_MAT_USES_PTEX)) {  // SurfaceParameters.cpp:196-208: eval(faceid = primId, u, v, widths 0)
+        float rgb[3] = {0.0f, 0.0f, 0.0f};
+        mesh.ptexEval(mesh.ptexUser, (int)h.primID, u, v, rgb);
+        base = v3(rgb);
+    } else if (mesh.texture.texels) {  // SurfaceParameters.cpp:186-190, :209-214
         float uv[2] = {0.0f, 0.0f};
         if (!mesh.uvs.empty()) interp3(mesh.uvs, 2, uv);
         base = sampleTextureFloat3(mesh.texture, uv[0], uv[1], true);
@@ -488,6 +496,15 @@ static void evaluatePathDeferred(const Scene& sc, const SelasCamera& cam, const 
 }
 
 extern "C" {
+
+// Attach a Ptex lookup to mesh `meshIndex` (used when its material has SELAS_MAT_USES_PTEX).
+int orc_scene_set_ptex(void* scene, uint32_t meshIndex, void (*fn)(void*, int, float, float, float*), void* user) {
+    Scene* sc = (Scene*)scene;
+    if (!sc || meshIndex >= sc->meshes.size()) return 1;
+    sc->meshes[meshIndex].ptexEval = fn;
+    sc->meshes[meshIndex].ptexUser = user;
+    return 0;
+}
 
 int orc_scene_create(const SelasSceneDesc* d, void** out) {
     Scene* sc = new Scene();

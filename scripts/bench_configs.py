@@ -92,6 +92,27 @@ def config4(ctx, grid, spp):
         paths += st.pathSamples
         rays += st.closestRays + st.occlusionRays
     e2e_s = time.perf_counter() - t0
+    # CPU leg: the restated integrator with its Ptex hook bound to the reference's own PtexFilter (oracle/_ref/libptex_ref.so), one
+    # 4 spp pass of the same frame on every host thread; the same pass on the GPU gives the image parity figure
+    orc = oracle_binding.load_oracle()
+    threads = len(os.sched_getaffinity(0))
+    rs.firstSample = 0
+    gfilm, _ = sc.render(cam, rs)
+    t0 = time.perf_counter()
+    hs = orc.scene_create(data)
+    th = ptexref.open(tmp)
+    orc.scene_set_ptex(hs, 0, ptexref, th)
+    cpu_build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cfilm, cst = orc.render(hs, cam, rs, nthreads=threads)
+    cpu_s = time.perf_counter() - t0
+    orc.scene_destroy(hs)
+    ptexref.close(th)
+    cpu = {"kind": "port (integrator) + reference Ptex library (lookups)", "cores": threads, "sample": "one 4 spp pass of the 1920x1080 frame",
+           "scene_build_s": cpu_build_s, "seconds": cpu_s, "samples_per_s": cst.pathSamples / cpu_s,
+           "relMSE_gpu_vs_cpu_same_seed": relmse(gfilm[0] / 4.0, cfilm[0] / 4.0),
+           "mean_ratio_gpu_over_cpu": float(np.nanmean(gfilm[0][np.isfinite(gfilm[0]).all(axis=2) & np.isfinite(cfilm[0]).all(axis=2)])
+                                            / np.nanmean(cfilm[0][np.isfinite(gfilm[0]).all(axis=2) & np.isfinite(cfilm[0]).all(axis=2)]))}
     # the same scene without the Ptex lookup (constant base colour) isolates the cost of the lookup inside shading
     plain = scenes.ptex_quad_grid(grid, grid, ptex=None)
     sc2 = capi.Scene(ctx, plain)
@@ -104,8 +125,7 @@ def config4(ctx, grid, spp):
            "nonfinite_pixels_last_pass": int((~np.isfinite(film[0]).all(axis=2)).sum()),
            "without_ptex": {"gpu_device_ms_per_4spp_pass": st2.renderMs, "shade_ms_per_4spp_pass": st2.shadeMs,
                             "gpu_samples_per_s": st2.pathSamples / (st2.renderMs * 1e-3)},
-           "cpu": "Ptex lookups/s of the reference's PtexFilter are in scripts/bench_rows.py (ptex_lookup.cpu); the tier-B CPU integrator "
-                  "has no Ptex hook, so no CPU samples/s is quoted for this config"}
+           "cpu": cpu}
     sc.close()
     sc2.close()
     tex.close()

@@ -124,6 +124,11 @@ class ShadingOracle(_Lib):
     def scene_destroy(self, h):
         self.fn("scene_destroy")(h)
 
+    def scene_set_ptex(self, h, mesh_index, ptexref, ptex_handle):
+        """Bind mesh `mesh_index`'s Ptex base colour to the reference Ptex library's lookup (PtexRef.open handle)."""
+        rc = self.fn("scene_set_ptex")(h, C.c_uint32(mesh_index), C.cast(ptexref.fn("eval1"), C.c_void_p), C.c_void_p(ptex_handle))
+        assert rc == 0, rc
+
     def ibl_lookup(self, h, wi):
         wi = _f32(wi).reshape(-1, 3)
         n = wi.shape[0]
@@ -359,6 +364,17 @@ class PtexRef(_Lib):
         if rc:
             raise RuntimeError(f"ptexref_eval failed: {rc}")
         return out
+
+    def open(self, path):
+        f = self.fn("open")
+        f.restype = C.c_void_p
+        h = f(str(path).encode())
+        if not h:
+            raise RuntimeError(f"ptexref_open failed: {path}")
+        return h
+
+    def close(self, handle):
+        self.fn("close")(C.c_void_p(handle))
 
     def info(self, path):
         out = (C.c_int * 8)()

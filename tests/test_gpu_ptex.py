@@ -84,3 +84,37 @@ def test_ptex_in_surface_params(ctx):
     assert np.abs(s["baseColor"] - want).max() <= 2e-4
     sc.close()
     tex.close()
+
+
+def test_ptex_render_matches_oracle(ctx, ptexref):
+    """End to end: the wavefront PathTracer with the Ptex stage between closest-hit and shade, against the CPU integrator whose
+    Ptex hook calls the reference's own PtexFilter (same RNG streams, so the images differ only by float rounding and the
+    1e-4 lookup tolerance)."""
+    orc = oracle_binding.load_oracle()
+    path = G / "ptex_jitter_u8.ptx"
+    nu, nv = 5, 4  # the fixture's face grid (tests/golden/make_golden.py)
+    assert ptexref.info(path)[0] == nu * nv
+    tex = capi.Ptex(ctx, path)
+    data = scenes.ptex_quad_grid(nu, nv, ptex=tex)
+    cam = scenes.ptex_grid_camera(96, 64)
+    rs = capi.render_settings(96, 64, 16, max_path_length=5, rr_start=8, layers=1, seed=5)
+    sc = capi.Scene(ctx, data)
+    film, st = sc.render(cam, rs)
+    hs = orc.scene_create(data)
+    th = ptexref.open(path)
+    orc.scene_set_ptex(hs, 0, ptexref, th)
+    ofilm, ost = orc.render(hs, cam, rs, nthreads=8)
+    flat = scenes.ptex_quad_grid(nu, nv, ptex=None)
+    hs2 = orc.scene_create(flat)
+    pfilm, _ = orc.render(hs2, cam, rs, nthreads=8)
+    orc.scene_destroy(hs)
+    orc.scene_destroy(hs2)
+    ptexref.close(th)
+    g, o, p = film[0] / 16.0, ofilm[0] / 16.0, pfilm[0] / 16.0
+    relmse = float(np.mean((g - o) ** 2 / (o ** 2 + 1e-2)))
+    textured = float(np.mean((p - o) ** 2 / (o ** 2 + 1e-2)))
+    assert st.closestRays == ost.closestRays or abs(int(st.closestRays) - int(ost.closestRays)) <= 1e-3 * ost.closestRays
+    assert abs(g.mean() / o.mean() - 1.0) < 5e-3 and relmse < 5e-3, (g.mean(), o.mean(), relmse)
+    assert textured > 20 * max(relmse, 1e-6), (textured, relmse)  # the texture is what the comparison is sensitive to
+    sc.close()
+    tex.close()

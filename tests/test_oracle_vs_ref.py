@@ -318,3 +318,29 @@ def test_texture_lookup_bit_exact(oracle, ref, shape):
         a, b = oracle.texture_sample(tex, uv, srgb), ref.texture_sample(tex, uv, srgb)
         np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
     assert a.max() > 0
+
+
+def test_oracle_ptex_hook_surface_params(oracle, ptexref):
+    """The CPU integrator's Ptex hook (orc_scene_set_ptex bound to the reference Ptex library): CalculateSurfaceParams gives
+    baseColor = pow(PtexFilter::eval(primId, u, v), 2.2) (SurfaceParameters.cpp:196-208), checked against the committed lookups."""
+    from pathlib import Path
+
+    from selas_b200 import scenes
+
+    G = Path(__file__).resolve().parent / "golden"
+    z = np.load(G / "ptex_lookups.npz")
+    data = scenes.ptex_quad_grid(6, 5, ptex=None)
+    data.materials["flags"] |= capi.MAT_USES_PTEX
+    hs = oracle.scene_create(data)
+    th = ptexref.open(G / "ptex_uniform_u8.ptx")
+    oracle.scene_set_ptex(hs, 0, ptexref, th)
+    face, u, v = z["ptex_uniform_u8_face"], z["ptex_uniform_u8_u"], z["ptex_uniform_u8_v"]
+    rays = np.zeros(face.size, dtype=capi.RAY_DTYPE)
+    rays["dy"] = 1.0
+    hits = np.zeros(face.size, dtype=capi.HIT_DTYPE)
+    hits["t"], hits["u"], hits["v"], hits["primID"] = 1.0, u, v, face.astype(np.uint32)
+    s = oracle.surface_params(hs, rays, hits)
+    want = np.power(z["ptex_uniform_u8_rgb"].astype(np.float32), np.float32(2.2))
+    assert np.abs(s["baseColor"] - want).max() <= 2e-6  # powf vs numpy's float32 power
+    oracle.scene_destroy(hs)
+    ptexref.close(th)
