@@ -631,13 +631,22 @@ SELAS_D float ptexSum4(const float* k, int n) {  // accumulate(): sequential fro
         if (i < n) r += k[i];
     return r;
 }
-// PtexSeparableKernel::Apply on native-resolution data of a face (or applyConst for a constant face)
+template <int DT>
+SELAS_D float ptexTexelT(const uint8_t* base, size_t idx) {
+    if (DT == 0) return (float)__ldg(base + idx);
+    if (DT == 1) return (float)__ldg(reinterpret_cast<const uint16_t*>(base) + idx);
+    if (DT == 2) return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const uint16_t*>(base) + idx)));
+    return __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+// PtexSeparableKernel::Apply on native-resolution data of a face (or applyConst for a constant face); the data type is a
+// template parameter so that the per-texel switch is decided once per lookup
+template <int DT>
 SELAS_D void ptexApplyPiece(const PtexGpu& tx, const PtexFace& f, int faceid, const PtexPiece& p, int nchan, float* result) {
     if (p.uw <= 0 || p.vw <= 0) return;
     if (f.isConstant()) {
         float w = ptexSum4(p.ku, p.uw) * ptexSum4(p.kv, p.vw);
         const uint8_t* px = tx.constData + (size_t)faceid * tx.pixelSize;
-        for (int c = 0; c < nchan; ++c) result[c] += ptexTexel(px, tx.dataType, c) * w;
+        for (int c = 0; c < nchan; ++c) result[c] += ptexTexelT<DT>(px, c) * w;
         return;
     }
     const uint8_t* data = tx.texels + (size_t)f.dataOffset16 * 16;
@@ -651,14 +660,19 @@ SELAS_D void ptexApplyPiece(const PtexGpu& tx, const PtexFace& f, int faceid, co
             for (int x = 0; x < 4; ++x) {
                 if (x < p.uw) {
                     float w = p.ku[x];
-                    for (int c = 0; c < nchan; ++c) {
-                        float t = ptexTexel(data, tx.dataType, rowBase + (size_t)x * nt + c);
-                        row[c] = (x == 0) ? t * w : row[c] + t * w;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (c < nchan) {
+                            float t = ptexTexelT<DT>(data, rowBase + (size_t)x * nt + c);
+                            row[c] = (x == 0) ? t * w : row[c] + t * w;
+                        }
                     }
                 }
             }
             float wv = p.kv[y];
-            for (int c = 0; c < nchan; ++c) result[c] += row[c] * wv;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                if (c < nchan) result[c] += row[c] * wv;
         }
     }
 }
@@ -685,86 +699,161 @@ SELAS_D bool ptexFastAxis(float u, int reslog2, int& k0, int& kw, float* k) {
     return true;
 }
 
-SELAS_D bool ptexEvalFast(const PtexGpu& tx, const PtexFace& f, int faceid, float u, float v, int nchan, float oneValue, float* rgb) {
-    if (f.isSubface() || f.isConstant() || f.ulog2 < 3 || f.vlog2 < 3) return false;
-    PtexPiece k;
-    if (!ptexFastAxis(u, f.ulog2, k.u, k.uw, k.ku) || !ptexFastAxis(v, f.vlog2, k.v, k.vw, k.kv)) return false;
-    const int resu = 1 << f.ulog2, resv = 1 << f.vlog2;
-    const bool splitR = (k.u + k.uw > resu), splitL = (k.u < 0), splitT = (k.v + k.vw > resv), splitB = (k.v < 0);
-    const int nsplit = (int)splitR + (int)splitL + (int)splitT + (int)splitB;
-    if (nsplit > 1) return false;  // corner: general path
-    const float weight = ptexSum4(k.ku, k.uw) * ptexSum4(k.kv, k.vw);
-    float result[3] = {0.f, 0.f, 0.f};
-    if (nsplit == 1) {
-        const int eid = splitB ? kEdgeBottom : splitR ? kEdgeRight : splitT ? kEdgeTop : kEdgeLeft;
-        const int afid = f.adjface(eid);
-        // overhang width and the piece that leaves the face (splitL/R/B/T, PtexSeparableKernel.h:149-237)
-        PtexPiece ka = k;
-        const bool uAxis = splitL || splitR, lowSide = splitL || splitB;
-        // the split axis is handled on a copy so that every array index stays a compile-time constant
-        float kk[4];
+// One axis of a piece, as (origin, extent, weights compacted to index 0).  The helpers below are the library's
+// splitL/R/B/T and mergeL/R/B/T (PtexSeparableKernel.h:149-237) on that representation, with every array index a
+// compile-time constant so the weights stay in registers.
+//   split: the w texels hanging over the low / high side leave as (o0, on, ko); the rest stays in (k0, kn, kk)
+SELAS_D void ptexSplitAxis(int& k0, int& kn, float* kk, int res, bool lowSide, int& o0, int& on, float* ko) {
+    const int w = lowSide ? -k0 : k0 + kn - res;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) kk[i] = uAxis ? k.ku[i] : k.kv[i];
-        const int kn = uAxis ? k.uw : k.vw, k0 = uAxis ? k.u : k.v, res = uAxis ? resu : resv;
-        const int w = lowSide ? -k0 : k0 + kn - res;  // overhang width (splitL/R/B/T, PtexSeparableKernel.h:149-237)
-        float ko[4];  // weights of the piece that leaves the face
+    for (int i = 0; i < 4; ++i) ko[i] = kk[i];
+    if (!lowSide) ptexShift4(ko, kn - w);
+    o0 = lowSide ? res - w : 0;
+    on = w;
+    if (lowSide) { ptexShift4(kk, w); k0 = 0; }
+    kn -= w;
+}
+//   merge (mesh border): the overhang folds onto the edge texel; border mode black (1) drops it
+SELAS_D void ptexMergeAxis(int& k0, int& kn, float* kk, int res, bool lowSide, int mode) {
+    const int w = lowSide ? -k0 : k0 + kn - res;
+    if (lowSide) {
+        float acc = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ko[i] = kk[i];
-        if (!lowSide) ptexShift4(ko, kn - w);
-        const int o0 = lowSide ? res - w : 0;
-        if (uAxis) { ka.u = o0; ka.uw = w; }
-        else { ka.v = o0; ka.vw = w; }
+        for (int i = 0; i < 4; ++i)
+            if (i < w) acc += kk[i];
+        float edge = ptexPick4(kk, w);
+        if (mode != 1) edge += acc;
+        ptexShift4(kk, w);
+        kk[0] = edge;
+        k0 = 0;
+        kn -= w;
+    } else {
+        const int newKn = kn - w;
+        float acc = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (uAxis) ka.ku[i] = ko[i];
-            else ka.kv[i] = ko[i];
+        for (int i = 0; i < 4; ++i)
+            if (i >= newKn && i < kn) acc += kk[i];
+        if (mode != 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i == newKn - 1) kk[i] += acc;
         }
-        int newK0 = k0, newKn = kn - w;
-        if (afid >= 0) {
-            PtexFace af = ptexLoadFace(tx, afid);
-            if (af.isSubface()) return false;
-            int ul = f.ulog2, vl = f.vlog2;
-            ptexRotatePiece(ka, eid - f.adjedge(eid) + 2, ul, vl);
-            if (ul != af.ulog2 || vl != af.vlog2) return false;  // needs downres / reduced data: general path
-            ptexApplyPiece(tx, af, afid, ka, nchan, result);
-            if (lowSide) { ptexShift4(kk, w); newK0 = 0; }  // the part that stays
-        } else {
-            // mesh border: mergeL/R/B/T fold the overhang onto the edge texel (border mode black drops it)
-            const int mode = uAxis ? tx.uMode : tx.vMode;
-            if (lowSide) {
-                float acc = 0;
+        kn = newKn;
+    }
+}
+
+// splitAndApply (PtexSeparableFilter.cpp:135-213) for a 4x4 kernel on an ordinary face of >= 8x8 texels.  The library applies up to
+// four pieces in a fixed order -- across the corner, across the u edge, across the v edge, the face itself -- and this walks the same
+// four slots in ONE loop: per axis a slot's piece is the part that leaves the face, the part that stays, the whole window, or (at a
+// mesh border) the window with the overhang merged onto the edge texel.  One copy of the code serves every slot, a warp holding
+// interior, edge and corner lookups stays converged (slots a lane does not need are predicated off), and the sums are formed in
+// the library's order, so the result matches the general path bit for bit.  Anything else -- subfaces, resolution mismatch,
+// valence 5+ corners, faces below 8 texels, kernels that are not 4 wide -- returns false and takes the general path.  Written
+// with status flags instead of early exits: with `return` in the middle the compiler moved the warp's reconvergence point to the
+// end of the lookup and the variants ran one after the other (measured 17.7 ms for 16 M mixed lookups).
+enum { kAxisWhole = 0, kAxisLeaving = 1, kAxisStaying = 2, kAxisMerged = 3 };
+SELAS_D void ptexDeriveAxis(int k0, int kn, const float* kk, int res, bool lowSide, int how, int mode, int& o0, int& on, float* ko) {
+    float t[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (i < w) acc += kk[i];
-                float edge = ptexPick4(kk, w);
-                if (mode != 1) edge += acc;
-                ptexShift4(kk, w);
-                kk[0] = edge;
-                newK0 = 0;
-            } else {
-                float acc = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (i >= newKn && i < kn) acc += kk[i];
-                if (mode != 1) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (i == newKn - 1) kk[i] += acc;
+    for (int i = 0; i < 4; ++i) { t[i] = kk[i]; ko[i] = kk[i]; }
+    o0 = k0;
+    on = kn;
+    if (how == kAxisLeaving) {
+        int tk0 = k0, tkn = kn;
+        ptexSplitAxis(tk0, tkn, t, res, lowSide, o0, on, ko);
+    } else if (how == kAxisStaying) {
+        int d0, dn;
+        ptexSplitAxis(o0, on, ko, res, lowSide, d0, dn, t);
+    } else if (how == kAxisMerged) {
+        ptexMergeAxis(o0, on, ko, res, lowSide, mode);
+    }
+}
+
+template <int DT>
+SELAS_D bool ptexEvalFastT(const PtexGpu& tx, const PtexFace& f, int faceid, float u, float v, int nchan, float oneValue, float* rgb) {
+    PtexPiece k;
+    bool ok = !(f.isSubface() || f.isConstant() || f.ulog2 < 3 || f.vlog2 < 3);
+    ok = ok && ptexFastAxis(u, f.ulog2, k.u, k.uw, k.ku);
+    ok = ok && ptexFastAxis(v, f.vlog2, k.v, k.vw, k.kv);
+    const int resu = 1 << f.ulog2, resv = 1 << f.vlog2;
+    const bool splitR = ok && (k.u + k.uw > resu), splitL = ok && (k.u < 0), splitT = ok && (k.v + k.vw > resv), splitB = ok && (k.v < 0);
+    ok = ok && !((splitR && splitL) || (splitT && splitB));
+    const bool splitU = splitR || splitL, splitV = splitT || splitB;
+    const int eU = splitR ? kEdgeRight : kEdgeLeft, eV = splitT ? kEdgeTop : kEdgeBottom;
+    const bool adjU = f.adjface(eU) >= 0, adjV = f.adjface(eV) >= 0;
+    float weight = ok ? ptexSum4(k.ku, k.uw) * ptexSum4(k.kv, k.vw) : 1.0f;
+    float result[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        const bool viaU = (s == 0 || s == 1), viaV = (s == 0 || s == 2);  // the slot's piece leaves through the u / v edge
+        const bool active = ok && (!viaU || (splitU && adjU)) && (!viaV || (splitV && adjV));
+        if (active) {
+            PtexPiece p;
+            const int howU = !splitU ? kAxisWhole : (adjU ? (viaU ? kAxisLeaving : kAxisStaying) : kAxisMerged);
+            const int howV = !splitV ? kAxisWhole : (adjV ? (viaV ? kAxisLeaving : kAxisStaying) : kAxisMerged);
+            ptexDeriveAxis(k.u, k.uw, k.ku, resu, splitL, howU, tx.uMode, p.u, p.uw, p.ku);
+            ptexDeriveAxis(k.v, k.vw, k.kv, resv, splitB, howV, tx.vMode, p.v, p.vw, p.kv);
+            int tfid = faceid, rot = 0;
+            PtexFace tf = f;
+            bool apply = true;
+            if (s == 0) {
+                // applyToCorner (:257-330) without subfaces: walk around the corner; an ordinary valence-4 corner applies the piece to
+                // the diagonal face, a walk that hits the mesh border or closes early (valence 2, 3) only takes the weight out
+                const int eid = splitR ? (splitT ? kEdgeTop : kEdgeRight) : (splitT ? kEdgeLeft : kEdgeBottom);
+                int afid = faceid, aeid = eid, numCorners = 0, state = 0;  // state: 0 walking, 1 finished, 2 general path
+                PtexFace af = f;
+#pragma unroll 1
+                for (int i = 0; i < 4; ++i) {
+                    if (state == 0) {
+                        const int next = af.adjface(aeid);
+                        aeid = (af.adjedge(aeid) + 1) & 3;
+                        afid = next;
+                        if (afid < 0 || (afid == faceid && aeid == eid)) {
+                            numCorners = i - 2;
+                            state = 1;
+                        } else if (i == 3) {
+                            state = 2;  // valence 5+
+                        } else {
+                            af = ptexLoadFace(tx, afid);
+                            if (af.isSubface()) state = 2;
+                            if (i == 1) { tfid = afid; tf = af; rot = eid - aeid + 2; }
+                        }
+                    }
                 }
+                ok = state == 1;
+                if (ok && numCorners != 1) {
+                    weight -= ptexSum4(p.ku, p.uw) * ptexSum4(p.kv, p.vw);
+                    apply = false;
+                }
+            } else if (s < 3) {
+                // applyAcrossEdge (:215-255) between two ordinary faces
+                const int e = s == 1 ? eU : eV;
+                tfid = f.adjface(e);
+                tf = ptexLoadFace(tx, tfid);
+                rot = e - f.adjedge(e) + 2;
+            }
+            if (ok && apply) {
+                int ul = f.ulog2, vl = f.vlog2;
+                ptexRotatePiece(p, rot, ul, vl);
+                ok = !tf.isSubface() && ul == tf.ulog2 && vl == tf.vlog2;  // else: downres / reduced data / subface logic
+                if (ok) ptexApplyPiece<DT>(tx, tf, tfid, p, nchan, result);
             }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (uAxis) k.ku[i] = kk[i];
-            else k.kv[i] = kk[i];
-        }
-        if (uAxis) { k.u = newK0; k.uw = newKn; }
-        else { k.v = newK0; k.vw = newKn; }
     }
-    ptexApplyPiece(tx, f, faceid, k, nchan, result);
-    float scale = 1.0f / (weight * oneValue);
-    for (int c = 0; c < nchan; ++c) rgb[c] = result[c] * scale;
-    return true;
+    if (ok) {
+        float scale = 1.0f / (weight * oneValue);
+        for (int c = 0; c < nchan; ++c) rgb[c] = result[c] * scale;
+    }
+    return ok;
+}
+
+SELAS_D bool ptexEvalFast(const PtexGpu& tx, const PtexFace& f, int faceid, float u, float v, int nchan, float oneValue, float* rgb) {
+    switch (tx.dataType) {
+        case 0: return ptexEvalFastT<0>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+        case 1: return ptexEvalFastT<1>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+        case 2: return ptexEvalFastT<2>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+        default: return ptexEvalFastT<3>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+    }
 }
 
 // PtexSeparableFilter::eval, :47-132, with firstChan 0, nChannels 3, all widths 0, width 1, blur 0, split in three steps:
@@ -866,21 +955,23 @@ SELAS_D void ptexTileEval(size_t n, Fetch fetch, Store store) {
 #pragma unroll 1
         for (int k = 0; k < PER_THREAD; ++k) {
             size_t i = base + (size_t)k * BLOCK + threadIdx.x;
-            if (i >= n) continue;
-            const PtexGpu* texPtr;
-            int faceid;
-            float u, v;
-            if (!fetch(i, texPtr, faceid, u, v)) continue;
-            const PtexGpu tx = *texPtr;
-            PtexFace f;
-            float rgb[3];
-            bool done = true;
-            if (ptexPrologue(tx, faceid, u, v, f, rgb)) {
-                const float oneValue = tx.dataType == 0 ? 255.f : (tx.dataType == 1 ? 65535.f : 1.f);
-                if (!ptexEvalFast(tx, f, faceid, u, v, tx.nchan < 3 ? tx.nchan : 3, oneValue, rgb)) {
-                    int slot = atomicAdd(&failCount, 1);
-                    failItem[slot] = Item{texPtr, (uint32_t)(i - base), faceid, u, v};
-                    done = false;
+            const PtexGpu* texPtr = nullptr;
+            int faceid = 0;
+            float u = 0.f, v = 0.f;
+            // flags instead of `continue`, so that the warp reconverges after every step
+            const bool live = i < n && fetch(i, texPtr, faceid, u, v);
+            float rgb[3] = {0.f, 0.f, 0.f};
+            bool done = live;
+            if (live) {
+                const PtexGpu tx = *texPtr;
+                PtexFace f;
+                if (ptexPrologue(tx, faceid, u, v, f, rgb)) {
+                    const float oneValue = tx.dataType == 0 ? 255.f : (tx.dataType == 1 ? 65535.f : 1.f);
+                    if (!ptexEvalFast(tx, f, faceid, u, v, tx.nchan < 3 ? tx.nchan : 3, oneValue, rgb)) {
+                        int slot = atomicAdd(&failCount, 1);
+                        failItem[slot] = Item{texPtr, (uint32_t)(i - base), faceid, u, v};
+                        done = false;
+                    }
                 }
             }
             if (done) store(i, rgb);
