@@ -20,12 +20,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=800)
     ap.add_argument("--lookups", type=int, default=16_000_000)
+    ap.add_argument("--ptx", default="", help="reuse / keep the authored .ptx at this path (A/B runs)")
     args = ap.parse_args()
     import torch
 
     ptexref = oracle_binding.load_ptexref()
-    tmp = Path(tempfile.mkdtemp()) / "c.ptx"
-    ptexref.write_grid(tmp, args.grid, args.grid, 3, 3, 0, 0, 3, 4, True, 0)
+    tmp = Path(args.ptx) if args.ptx else Path(tempfile.mkdtemp()) / "c.ptx"
+    if not tmp.exists():
+        ptexref.write_grid(tmp, args.grid, args.grid, 3, 3, 0, 0, 3, 4, True, 0)
     ctx = capi.Context(0)
     tex = capi.Ptex(ctx, tmp)
     dev = torch.device("cuda", 0)

@@ -360,7 +360,7 @@ struct Loader {
     }
 };
 
-__global__ void __launch_bounds__(128, 4) ptexEvalKernel(const PtexGpu* __restrict__ tex, size_t n, const int32_t* __restrict__ faceid,
+__global__ void __launch_bounds__(128, SELAS_PTEX_MIN_CTAS) ptexEvalKernel(const PtexGpu* __restrict__ tex, size_t n, const int32_t* __restrict__ faceid,
                                                       const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ rgb) {
     ptexTileEval<128, 8>(
         n,

@@ -932,6 +932,11 @@ static __device__ __noinline__ void ptexGeneral(const PtexGpu* texPtr, int facei
     for (int c = 0; c < st.nchan; ++c) rgb[c] = st.result[c] * scale;
 }
 
+// Resident CTAs per SM the lookup kernels are compiled for: 4 -> 128 registers (the four-slot loop wants 158 uncapped; 5 -> 96 spills).
+#ifndef SELAS_PTEX_MIN_CTAS
+#define SELAS_PTEX_MIN_CTAS 4
+#endif
+
 // Tile-cooperative lookups: a CTA of BLOCK threads walks tiles of BLOCK * PER_THREAD lookups.  Phase 1 runs the early
 // outs and the register-resident fast path for every lookup of the tile; the ones it cannot take (corners, subfaces, mixed
 // resolutions: ~14 % on 8x8 faces) are queued in shared memory.  Phase 2 spreads the queue over all threads, so the long
