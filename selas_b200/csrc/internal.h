@@ -133,6 +133,8 @@ int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t max
                             uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream);
 
 // shade.cu
+constexpr uint32_t kMaterialBinWords = 64;  // = kBinCount of the pre-shade counting sort
+int launchMaterialOrder(SelasScene* scene, uint32_t n, const SelasHit* d_hits, uint32_t* d_bins, uint32_t* d_order, cudaStream_t stream);
 int launchBsdfEval(SelasContext* ctx, size_t n, const SelasSurface* d_s, const float* d_v, const float* d_l, float* d_rgb, float* d_f,
                    float* d_r);
 int launchBsdfSample(SelasContext* ctx, size_t n, const SelasSurface* d_s, const float* d_v, const float* d_u, SelasBsdfSample* d_out);

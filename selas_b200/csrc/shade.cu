@@ -460,6 +460,18 @@ __global__ void __launch_bounds__(256) binScatterKernel(SceneGpu sc, uint32_t n,
     }
 }
 
+// Material-sorted visiting order of a hit queue for callers outside this file (the VCM light pass).  bins: 2 * kMaterialBinWords
+// zeroed words of scratch; order: n words.
+int launchMaterialOrder(SelasScene* scene, uint32_t n, const SelasHit* d_hits, uint32_t* d_bins, uint32_t* d_order, cudaStream_t stream) {
+    SelasContext* ctx = scene->ctx;
+    int grid = (int)std::min<uint32_t>(divUp(n, 2048), (uint32_t)ctx->smCount * 8);
+    binCountKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, d_hits, d_bins);
+    binScanKernel<<<1, 32, 0, stream>>>(d_bins, d_bins + kBinCount);
+    binScatterKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, d_hits, d_bins + kBinCount, d_order);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+
 struct ShadeParams {
     uint32_t maxPathLength, rrStartBounce, layerCount, pixels, misMode, skipNonFinite;
 };
