@@ -337,15 +337,15 @@ typedef struct SelasPtex     SelasPtex;
 /* rtcNewDevice / rtcReleaseDevice at Source/Applications/Selas/Source/main.cpp:99,:130 */
 int selas_cuda_context_create(int device, SelasContext** out);
 int selas_cuda_context_destroy(SelasContext* ctx);
-const char* selas_cuda_last_error(const SelasContext* ctx); /* ctx may be NULL: thread-local message */
-int selas_cuda_device_count(void);
+const char* selas_cuda_last_error(const SelasContext* ctx); /* Error::Message(), SystemLib/Error.h:33; ctx may be NULL: thread-local message */
+int selas_cuda_device_count(void);      /* no reference counterpart: the CPU renderer has one device */
 const char* selas_cuda_version(void);
 
 /* ---- scene: replaces the Embree scene construction ---------------------------------------------
  * rtcSetSharedGeometryBuffer/rtcCommitGeometry/rtcCommitScene at ModelResource.cpp:164-200,:461-468,
  * SubsceneResource.cpp:141-156, SceneResource.cpp:218-249.  Builds the compressed BVH8 on device. */
 int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* desc, SelasScene** out);
-int selas_cuda_scene_destroy(SelasScene* scene);
+int selas_cuda_scene_destroy(SelasScene* scene); /* ShutdownSceneResource, SceneResource.cpp:318 (rtcReleaseScene) */
 int selas_cuda_scene_bvh_stats(const SelasScene* scene, SelasBvhStats* out);
 
 /* ---- ray cast: replaces rtcIntersect1 / rtcOccluded1 ---------------------------------------------
