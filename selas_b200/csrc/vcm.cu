@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) vcmLightShadeKernel(SceneGpu sc, SelasCam
                                                            const SelasHit* __restrict__ hits, const float4* __restrict__ thrIdx,
                                                            const float4* __restrict__ mis, const float* __restrict__ ptexRgb,
                                                            float4* __restrict__ slotA, float4* __restrict__ slotB, SelasRay* __restrict__ slotRay,
-                                                           SelasHit* __restrict__ slotHit, uint32_t* __restrict__ lvCount,
+                                                           SelasHit* __restrict__ slotHit, float* __restrict__ slotPtex, uint32_t* __restrict__ lvCount,
                                                            SelasRay* __restrict__ raysOut, float4* __restrict__ thrIdxOut, float4* __restrict__ misOut,
                                                            SelasRay* __restrict__ shadowRays, float4* __restrict__ shadowPayload,
                                                            uint32_t* __restrict__ counters) {
@@ -249,6 +249,11 @@ __global__ void __launch_bounds__(128) vcmLightShadeKernel(SceneGpu sc, SelasCam
                 uint4* ho = reinterpret_cast<uint4*>(slotHit + slot);
                 ho[0] = h0;
                 ho[1] = h1;
+                if (slotPtex && ptexRgb) {  // the vertex keeps its Ptex base colour for ConnectPathVertices' CalculateSurfaceParams (VCM.cpp:314-317)
+                    slotPtex[3 * slot] = ptexRgb[3 * (size_t)i];
+                    slotPtex[3 * slot + 1] = ptexRgb[3 * (size_t)i + 1];
+                    slotPtex[3 * slot + 2] = ptexRgb[3 * (size_t)i + 2];
+                }
                 lvCount[st.index] = st.pathLength;
             }
             DisneyFrame frame;
@@ -307,7 +312,8 @@ __global__ void __launch_bounds__(256) vcmCompactKernel(uint32_t vmCount, uint32
                                                         const uint32_t* __restrict__ pathStarts, const float4* __restrict__ slotA,
                                                         const float4* __restrict__ slotB, const SelasRay* __restrict__ slotRay,
                                                         const SelasHit* __restrict__ slotHit, float4* __restrict__ lvA, float4* __restrict__ lvB,
-                                                        SelasRay* __restrict__ lvRay, SelasHit* __restrict__ lvHit, float* __restrict__ lvPos) {
+                                                        SelasRay* __restrict__ lvRay, SelasHit* __restrict__ lvHit, float* __restrict__ lvPos,
+                                                        const float* __restrict__ slotPtex, float* __restrict__ lvPtex) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)vmCount * stride) return;
     uint32_t path = (uint32_t)(t / stride), k = (uint32_t)(t - (size_t)path * stride);
@@ -329,6 +335,11 @@ __global__ void __launch_bounds__(256) vcmCompactKernel(uint32_t vmCount, uint32
     lvPos[3 * dst] = r0.x + tHit * r1.x;
     lvPos[3 * dst + 1] = r0.y + tHit * r1.y;
     lvPos[3 * dst + 2] = r0.z + tHit * r1.z;
+    if (slotPtex) {
+        lvPtex[3 * dst] = slotPtex[3 * t];
+        lvPtex[3 * dst + 1] = slotPtex[3 * t + 1];
+        lvPtex[3 * dst + 2] = slotPtex[3 * t + 2];
+    }
 }
 
 __global__ void vcmPackVerticesKernel(size_t n, const float4* __restrict__ lvA, const float4* __restrict__ lvB, const SelasRay* __restrict__ lvRay,
@@ -550,7 +561,7 @@ struct ShadowOut {
 };
 SELAS_D bool connectPathVertices(const SceneGpu& sc, const VcmParams& prm, uint32_t i, uint32_t li, const SelasRay* rays, const SelasHit* hits,
                                  const float4* thrIdx, const float4* vertexMis, const float* ptexRgb, const float4* lvA, const float4* lvB,
-                                 const SelasRay* lvRay, const SelasHit* lvHit, ShadowOut& out) {
+                                 const SelasRay* lvRay, const SelasHit* lvHit, const float* lvPtex, ShadowOut& out) {
     CameraVertex cv;
     loadCameraVertex(sc, i, rays, hits, thrIdx, vertexMis, ptexRgb, cv);
     float4 a = __ldg(lvA + li), b = __ldg(lvB + li);
@@ -560,7 +571,8 @@ SELAS_D bool connectPathVertices(const SceneGpu& sc, const VcmParams& prm, uint3
     uint4 lh0 = __ldg(lhp), lh1 = __ldg(lhp + 1);
     Surface ls;  // CalculateSurfaceParams(context, &lightVertex.hit, lightSurface), :314-317
     V3 lo = v3(lr0.x, lr0.y, lr0.z), ld = v3(lr1.x, lr1.y, lr1.z);
-    surfaceFromHit(sc, lo, ld, __uint_as_float(lh0.x), __uint_as_float(lh0.y), __uint_as_float(lh0.z), lh0.w, lh1.x, lh1.y, nullptr, ls);
+    surfaceFromHit(sc, lo, ld, __uint_as_float(lh0.x), __uint_as_float(lh0.y), __uint_as_float(lh0.z), lh0.w, lh1.x, lh1.y,
+                   lvPtex ? lvPtex + 3 * (size_t)li : nullptr, ls);
     V3 direction = ls.position - cv.s.position;
     float distanceSquared = dot(direction, direction);
     float distance = sqrtf(distanceSquared);
@@ -611,8 +623,8 @@ __global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams p
                                                         const float4* __restrict__ vertexMis, const float* __restrict__ ptexRgb,
                                                         const float4* __restrict__ lvA, const float4* __restrict__ lvB,
                                                         const SelasRay* __restrict__ lvRay, const SelasHit* __restrict__ lvHit,
-                                                        SelasRay* __restrict__ shadowRays, float4* __restrict__ shadowPayload,
-                                                        uint32_t* __restrict__ counters) {
+                                                        const float* __restrict__ lvPtex, SelasRay* __restrict__ shadowRays,
+                                                        float4* __restrict__ shadowPayload, uint32_t* __restrict__ counters) {
     const uint32_t pairCount = __ldg(pairCountPtr);
     // whole warps iterate together: the queue append is warp-collective
     for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < pairCount; t0 += gridDim.x * blockDim.x) {
@@ -621,7 +633,7 @@ __global__ void __launch_bounds__(128) vcmConnectKernel(SceneGpu sc, VcmParams p
         bool wantShadow = false;
         if (t < pairCount) {
             const uint2 pr = __ldg(pairs + t);
-            wantShadow = connectPathVertices(sc, prm, pr.x, pr.y, rays, hits, thrIdx, vertexMis, ptexRgb, lvA, lvB, lvRay, lvHit, sh);
+            wantShadow = connectPathVertices(sc, prm, pr.x, pr.y, rays, hits, thrIdx, vertexMis, ptexRgb, lvA, lvB, lvRay, lvHit, lvPtex, sh);
         }
         uint32_t slotS = warpAppend(wantShadow, counters + 1);
         if (wantShadow) {
@@ -895,6 +907,7 @@ struct VcmBuffers {
     float4* shadowPayload = nullptr;
     uint32_t shadowCapacity = 0;
     float* ptexRgb = nullptr;
+    float *slotPtex = nullptr, *lvPtex = nullptr;  // Ptex base colour of every light vertex (scenes with Ptex only)
     uint32_t* counters = nullptr;  // 4 per launch slot: next paths, shadow rays, closest fetch, shadow fetch
     uint32_t counterSlots = 0;
     uint32_t* order = nullptr;  // material-sorted visiting order of the light queue
@@ -959,7 +972,11 @@ int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     VCM_TRY(vcmAlloc(ctx, w, &w->shadowRays, n + nv));       // one direct connection + up to `stride` vertex connections per vertex
     VCM_TRY(vcmAlloc(ctx, w, &w->shadowPayload, n + nv));
     w->shadowCapacity = (uint32_t)std::min<size_t>(n + nv, 0xFFFFFFFFull);
-    if (scene->usesPtex) VCM_TRY(vcmAlloc(ctx, w, &w->ptexRgb, 3 * n));
+    if (scene->usesPtex) {
+        VCM_TRY(vcmAlloc(ctx, w, &w->ptexRgb, 3 * n));
+        VCM_TRY(vcmAlloc(ctx, w, &w->slotPtex, 3 * nv));
+        VCM_TRY(vcmAlloc(ctx, w, &w->lvPtex, 3 * nv));
+    }
     VCM_TRY(vcmAlloc(ctx, w, &w->counters, (size_t)slots));
     VCM_TRY(vcmAlloc(ctx, w, &w->order, n));
     VCM_TRY(vcmAlloc(ctx, w, &w->bins, (size_t)2 * kMaterialBinWords * std::max(1u, stride)));
@@ -1078,7 +1095,7 @@ int lightPass(SelasScene* scene, const SelasCamera& cam, const VcmParams& prm, f
         }
         vcmLightShadeKernel<<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, cam, prm, order, n, w->rays[cur], w->hits, w->thrIdx[cur], w->mis[cur],
                                                                 scene->usesPtex ? w->ptexRgb : nullptr, w->slotA, w->slotB, w->slotRay, w->slotHit,
-                                                                w->lvCount, w->rays[cur ^ 1], w->thrIdx[cur ^ 1], w->mis[cur ^ 1], w->shadowRays,
+                                                                w->slotPtex, w->lvCount, w->rays[cur ^ 1], w->thrIdx[cur ^ 1], w->mis[cur ^ 1], w->shadowRays,
                                                                 w->shadowPayload, ctr);
         SELAS_CUDA_CHECK(ctx, cudaGetLastError());
         // counts go back for the next bounce's launch shapes; the shadow launch reads its count on the device and is enqueued before
@@ -1105,7 +1122,7 @@ int lightPass(SelasScene* scene, const SelasCamera& cam, const VcmParams& prm, f
     if (prm.stride) {
         vcmCompactKernel<<<divUp((size_t)vmCount * prm.stride, 256), 256, 0, stream>>>(vmCount, prm.stride, w->lvCount, w->pathStarts, w->slotA, w->slotB,
                                                                                         w->slotRay, w->slotHit, w->lvA, w->lvB, w->lvRay, w->lvHit,
-                                                                                        w->lvPos);
+                                                                                        w->lvPos, w->slotPtex, w->lvPtex);
         ++st.kernelLaunches;
     }
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
@@ -1208,8 +1225,8 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
                 vcmConnectGatherKernel<<<divUp(n, 256), 256, 0, stream>>>(prm, n, w->hits, w->thrIdx[cur], w->vertexMis, w->pathStarts, w->pathEnds,
                                                                           w->connPairs, pairCtr + 1);
                 vcmConnectKernel<<<connectGrid, 128, 0, stream>>>(scene->gpu, prm, pairCtr + 1, w->connPairs, w->rays[cur], w->hits, w->thrIdx[cur],
-                                                                w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, w->lvHit, w->shadowRays,
-                                                                w->shadowPayload, ctr);
+                                                                w->vertexMis, ptexRgb, w->lvA, w->lvB, w->lvRay, w->lvHit, w->lvPtex,
+                                                                w->shadowRays, w->shadowPayload, ctr);
                 ev.span(4, tc);
                 st.kernelLaunches += 2;
             }

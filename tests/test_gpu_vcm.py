@@ -186,3 +186,53 @@ def test_vcm_degenerate_inputs(ctx, oracle):
     assert not z.any() and zst.lightPaths == 0
     oracle.scene_destroy(hs)
     sc.close()
+
+
+@pytest.mark.parametrize("name,flags", [("connections", ALL_OFF & ~capi.VCM_NO_CONNECTIONS), ("full", 0)])
+def test_vcm_with_ptex_matches_oracle(ctx, oracle, name, flags):
+    """Ptex base colours through VCM: the camera and light shade stages look them up, and a light vertex keeps its colour for the
+    surface ConnectPathVertices rebuilds (VCM.cpp:314-317).  The oracle's CalculateSurfaceParams calls the reference PtexFilter."""
+    from pathlib import Path
+
+    from tests import oracle_binding
+
+    ptexref = oracle_binding.load_ptexref()
+    if ptexref is None:
+        pytest.skip("oracle/_ref/libptex_ref.so not built")
+    path = Path(__file__).resolve().parent / "golden" / "ptex_jitter_u8.ptx"  # 5 x 4 faces
+    tex = capi.Ptex(ctx, path)
+    data = scenes.ptex_quad_grid(5, 4, ptex=tex)
+    # the sheet's geometric normal is -y and the camera sits below it: a sky whose bright patch is in the lower hemisphere
+    img = np.full((64, 128, 3), 0.2, np.float32)
+    img[44:52, 40:48] = 300.0
+    data.ibl = scenes.build_ibl(img, miss=np.full((16, 32, 3), 0.1, np.float32), rotation=0.3, exposure=0.0)
+    sphere = scenes.bounding_sphere(data)
+    w, h = 96, 64
+    cam = scenes.ptex_grid_camera(w, h)
+    sc = capi.Scene(ctx, data)
+    hs = oracle.scene_create(data)
+    th = ptexref.open(path)
+    oracle.scene_set_ptex(hs, 0, ptexref, th)
+    vs = capi.vcm_settings(w, h, 2, sphere, seed=11, flags=flags)
+    gf, gst = sc.render_vcm(cam, vs)
+    of, ost = oracle.render_vcm(hs, cam, vs, nthreads=8)
+    # the same render with the constant base colour must be clearly different, or the comparison proves nothing
+    plain = scenes.ptex_quad_grid(5, 4, ptex=None)
+    plain.ibl = data.ibl
+    hp = oracle.scene_create(plain)
+    pf, _ = oracle.render_vcm(hp, cam, vs, nthreads=8)
+    oracle.scene_destroy(hs)
+    oracle.scene_destroy(hp)
+    ptexref.close(th)
+    assert np.isfinite(gf).all() and of.mean() > 0
+    assert abs(int(gst.lightVertices) - int(ost.lightVertices)) <= 0.002 * ost.lightVertices + 2
+    assert abs(gf.mean() / of.mean() - 1.0) < 5e-3, (name, gf.mean(), of.mean())
+    scale = 1.0 / of.mean()  # connections alone are a small term on this nearly flat sheet: compare in units of the image mean
+    gb = gf.reshape(h // 2, 2, w // 2, 2, 3).mean(axis=(1, 3)) * scale
+    ob = of.reshape(h // 2, 2, w // 2, 2, 3).mean(axis=(1, 3)) * scale
+    pb = pf.reshape(h // 2, 2, w // 2, 2, 3).mean(axis=(1, 3)) * scale
+    assert _relmse(gb, ob) < 2e-3, (name, _relmse(gb, ob))
+    assert _relmse(pb, ob) > 20 * max(_relmse(gb, ob), 1e-4), (name, _relmse(pb, ob), _relmse(gb, ob))
+    assert abs(pf.mean() / of.mean() - 1.0) > 0.1
+    sc.close()
+    tex.close()
