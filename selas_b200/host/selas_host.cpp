@@ -289,6 +289,26 @@ void InitializeRayCastCamera(const CameraSettings& settings, uint32_t width, uin
 
 Error InitializeSceneResource(SceneResource* scene, int device) {
     if (selas_cuda_context_create(device, &scene->gpu) != SELAS_OK) return Error_("%s", selas_cuda_last_error(nullptr));
+    // TextureCache::LoadTexturePtex (TextureCache.cpp:99-126) for the meshes that name a Ptex file: one texture per distinct path
+    std::vector<std::pair<std::string, SelasPtex*>> loadedPtex;
+    std::vector<SelasPtex*> meshPtex(scene->meshes.size(), nullptr);
+    for (size_t i = 0; i < scene->meshes.size(); ++i) {
+        const SceneMesh& m = scene->meshes[i];
+        meshPtex[i] = m.ptex;
+        if (m.ptex || m.ptexPath.empty()) continue;
+        for (const auto& lp : loadedPtex)
+            if (lp.first == m.ptexPath) meshPtex[i] = lp.second;
+        if (meshPtex[i]) continue;
+        SelasPtex* tex = nullptr;
+        if (selas_cuda_ptex_load(scene->gpu, m.ptexPath.c_str(), &tex) != SELAS_OK) {
+            Error e = Error_("%s", selas_cuda_last_error(scene->gpu));
+            ShutdownSceneResource(scene);
+            return e;
+        }
+        scene->ownedPtex.push_back(tex);
+        loadedPtex.emplace_back(m.ptexPath, tex);
+        meshPtex[i] = tex;
+    }
     std::vector<SelasMeshDesc> meshes(scene->meshes.size());
     for (size_t i = 0; i < meshes.size(); ++i) {
         const SceneMesh& m = scene->meshes[i];
@@ -304,7 +324,7 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
         d.uvs = m.uvs.empty() ? nullptr : m.uvs.data();
         d.materialIndex = m.materialIndex;
         d.lightSetIndex = m.lightSetIndex;
-        d.ptex = m.ptex;
+        d.ptex = meshPtex[i];
         d.baseColorTexture = m.baseColorTexture;
     }
     // SceneResource::aaBox / boundingSphere (SceneResource.h:77-78): the instances' boxes in the reference (SceneResource.cpp:196-201);
@@ -352,6 +372,8 @@ void ShutdownSceneResource(SceneResource* scene) {
     scene->textures.clear();
     scene->textureNames.clear();
     if (scene->gpuScene) selas_cuda_scene_destroy(scene->gpuScene);
+    for (SelasPtex* t : scene->ownedPtex) selas_cuda_ptex_destroy(t);
+    scene->ownedPtex.clear();
     if (scene->gpu) selas_cuda_context_destroy(scene->gpu);
     scene->gpuScene = nullptr;
     scene->gpu = nullptr;
@@ -870,10 +892,18 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
                     material = defaultMaterial;
                 }
                 mesh.materialIndex = (uint32_t)material;
-                if (scene->materials[material].flags & SELAS_MAT_USES_PTEX)  // <texture dir>/<mesh name>.ptx under the content root, ModelResource.cpp:361-368
-                    return Error_("LoadBakedScene: mesh %s uses a Ptex base colour (%s/%s.ptx): pass it through SceneMesh::ptex", bm.name.c_str(),
-                                  materialTexture[material].c_str(), bm.name.c_str());
-                ReturnError_(textureFor(materialTexture[material], &mesh.baseColorTexture));
+                if (scene->materials[material].flags & SELAS_MAT_USES_PTEX) {
+                    // "<material.baseColorTexture>\\<mesh name>.ptx" under the content root (ModelResource.cpp:358-364, AssetFileUtils.cpp:85-92);
+                    // the file is opened when the scene goes to the device (InitializeSceneResource), its absence is reported here as
+                    // TextureCache::LoadTexturePtex does (TextureCache.cpp:105-108)
+                    mesh.ptexPath = std::string(root) + "Content/" + materialTexture[material] + "/" + bm.name + ".ptx";
+                    for (char& ch : mesh.ptexPath)
+                        if (ch == '\\') ch = '/';
+                    FILE* probe = fopen(mesh.ptexPath.c_str(), "rb");
+                    if (!probe) return Error_("Ptex file %s does not exist", mesh.ptexPath.c_str());
+                    fclose(probe);
+                }
+                if (mesh.ptexPath.empty()) ReturnError_(textureFor(materialTexture[material], &mesh.baseColorTexture));
                 // eDisplacementEnabled materials are plain triangle / quad meshes in the reference as built (EnableDisplacement_ 0,
                 // ModelResource.cpp:18,:251-252) and eAlphaTested ones pass every hit (CalculatePassesAlphaTest returns true,
                 // SurfaceParameters.cpp:344-347): nothing to do for either

@@ -86,7 +86,8 @@ struct SceneMesh {
     std::vector<float> positions, normals, tangents, uvs;
     std::vector<uint32_t> indices;
     uint32_t indicesPerFace = 3, materialIndex = 0, lightSetIndex = 0;
-    SelasPtex* ptex = nullptr;
+    SelasPtex* ptex = nullptr;  // borrowed; or leave null and name the file:
+    std::string ptexPath;       // Ptex base colour file, loaded (once per distinct path) by InitializeSceneResource and owned by the scene
     const SelasTextureDesc* baseColorTexture = nullptr;  // borrowed (e.g. from SceneResource::textures)
 };
 struct SceneResource {
@@ -100,6 +101,7 @@ struct SceneResource {
     const SelasIblDesc* ibl = nullptr;  // SceneResource::iblResource (borrowed), or null: constant background
     std::vector<struct TextureResource*> textures;  // base colour textures loaded by LoadBakedScene (owned; freed by ShutdownSceneResource)
     std::vector<std::string> textureNames;
+    std::vector<SelasPtex*> ownedPtex;        // Ptex textures InitializeSceneResource loaded from SceneMesh::ptexPath
     float aaBox[6] = {0, 0, 0, 0, 0, 0};          // SceneResource::aaBox (min xyz, max xyz), filled by InitializeSceneResource
     float boundingSphere[4] = {0, 0, 0, 0};       // SceneResource::boundingSphere: centre of aaBox, half its diagonal
     // device side
@@ -197,7 +199,8 @@ Error ReadSceneResource(const char* filepath, BakedScene* scene);
 // becomes one SelasInstanceDesc with localToWorld = model.localToWorld * subscene.localToWorld (ModelDataFromRayIds,
 // SceneResource.cpp:362-378); materials are resolved like FindMeshMaterial (ModelResource.cpp:214-235).  Curves are reported as
 // unsupported; displacement and alpha testing are inert in the reference as built (EnableDisplacement_ 0; CalculatePassesAlphaTest
-// returns true) and are therefore loaded as plain meshes.  Base colour textures of non-Ptex materials are loaded from their "Textures" blobs
+// returns true) and are therefore loaded as plain meshes.  A Ptex material's file is <root>Content/<baseColorTexture>/<mesh name>.ptx
+// (ModelResource.cpp:358-364; SceneMesh::ptexPath, opened by InitializeSceneResource).  Other base colour textures are loaded from their "Textures" blobs
 // (TextureCache::LoadTextureResource, TextureCache.cpp:68-96: one copy per name; an empty name means the constant colour).
 // `scene` is left ready for InitializeSceneResource(scene, device).
 Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* scene, ImageBasedLight* ibl, std::vector<BakedCamera>* cameras);

@@ -92,6 +92,22 @@ def small_two_level_scene():
     return scene
 
 
+def ptex_sheet_scene():
+    """One model with one quad mesh ("sheet", 5 x 4 quads = the faces of tests/golden/ptex_jitter_u8.ptx) whose material uses Ptex: the
+    loader must resolve Content/<material.baseColorTexture>/<mesh name>.ptx (ModelResource.cpp:358-364)."""
+    flat = scenes.ptex_quad_grid(5, 4, ptex=None)
+    sheet = flat.meshes[0]
+    mat = scenes.material(shaderName="DisneySolid", baseColor=[0.6, 0.6, 0.6], metallic=0.0, roughness=0.8, usesPtex=True)
+    model = dict(name="sheetModel", textures={0x51: "sheetTex"}, meshes=[dict(name="sheet", material=0x51, indices=sheet["indices"], positions=sheet["positions"])],
+                 normals=None, tangents=None, uvs=None, materials={0x51: mat})
+    sub = dict(name="sheetSub", light_set=0, models=[model], scene_materials={}, instances=[(0, np.eye(4, dtype=np.float32))])
+    rng = np.random.default_rng(3)
+    ibl = scenes.build_ibl((rng.uniform(0, 1, size=(8, 16, 3)) * 0.5).astype(np.float32), miss=np.full((2, 4, 3), 0.3, np.float32), rotation=0.0, exposure=0.0)
+    return dict(name="ptexsheet", ibl_name="dim", ibl=ibl, textures={}, background=(0.3, 0.35, 0.4, 0.0), subscenes=[sub],
+                instances=[(0, np.eye(4, dtype=np.float32))], lights=flat.lights, light_sets=[(0, 1)],
+                cameras=[dict(name="below", position=(0.0, -9.0, -14.0), lookAt=(0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0), fovDegrees=55.0, znear=0.1, zfar=500.0)])
+
+
 def write_baked(ref, root, scene):
     """All blobs of `scene` under root/_Assets/... through the reference serializer."""
     lib = ref.lib
@@ -181,7 +197,7 @@ def expected_flat_scene(scene):
                 if m["material"] in model["materials"]:
                     d["material"] = model_base + hashes.index(m["material"])
                     tname = model.get("textures", {}).get(m["material"])
-                    if tname:
+                    if tname and tname in scene["textures"]:  # a Ptex material names a directory of .ptx files instead
                         d["texture"] = scene["textures"][tname]
                 elif m["material"] in sub["scene_materials"]:
                     d["material"] = scene_base + sm_hashes.index(m["material"])

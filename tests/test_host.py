@@ -254,6 +254,68 @@ def test_baked_scene_renders_like_the_flat_description(ctx, host, ref, tmp_path)
     np.testing.assert_allclose(film[fin], ref_film[fin], rtol=2e-3, atol=2e-3)  # identical inputs: only the float atomics' order differs
 
 
+def _ptex_sheet(ref, tmp_path, with_file=True):
+    import shutil
+
+    from tests import baked
+
+    scene = baked.ptex_sheet_scene()
+    baked.write_baked(ref, tmp_path, scene)
+    if with_file:
+        d = tmp_path / "Content" / "sheetTex"
+        d.mkdir(parents=True)
+        shutil.copy(GOLDEN / "ptex_jitter_u8.ptx", d / "sheet.ptx")
+    return scene
+
+
+def test_baked_scene_resolves_ptex_files(host, ref, tmp_path):
+    """A mesh whose material uses Ptex names Content/<baseColorTexture>/<mesh name>.ptx (ModelResource.cpp:358-364); a missing file is
+    the reference's "Ptex file ... does not exist" (TextureCache.cpp:105-108)."""
+    from tests import baked
+
+    scene = _ptex_sheet(ref, tmp_path, with_file=False)
+    want = baked.expected_flat_scene(scene)
+    assert len(want.meshes) == 1 and want.meshes[0].get("texture") is None and want.to_desc() is not None
+    err = C.create_string_buffer(512)
+    assert host.selas_host_load_baked_scene(str(tmp_path).encode() + b"/", b"ptexsheet", None, None, None, None, err, 512) == 4
+    assert b"Ptex file" in err.value and b"Content/sheetTex/sheet.ptx does not exist" in err.value
+    d = tmp_path / "Content" / "sheetTex"
+    d.mkdir(parents=True)
+    (d / "sheet.ptx").write_bytes((GOLDEN / "ptex_jitter_u8.ptx").read_bytes())
+    counts, mats, mesh, materials = _load_baked(host, tmp_path, "ptexsheet")
+    assert counts[0] == 1 and counts[1] == 1 and materials[0]["flags"] & capi.MAT_USES_PTEX
+
+
+@pytest.mark.gpu
+def test_baked_scene_with_ptex_renders_like_the_flat_description(ctx, host, ref, tmp_path):
+    """The loader attaches the Ptex file itself: the baked sheet through the host equals the flat scene with the texture passed by hand."""
+    from tests import baked
+
+    scene = _ptex_sheet(ref, tmp_path)
+    want = baked.expected_flat_scene(scene)
+    tex = capi.Ptex(ctx, GOLDEN / "ptex_jitter_u8.ptx")
+    want.meshes[0]["ptex"] = tex
+    w, h, spp = 96, 64, 8
+    c = scene["cameras"][0]
+    cam = capi.camera_init(c["position"], c["lookAt"], c["up"], c["fovDegrees"], w, h, c["znear"], c["zfar"])
+    rs = capi.render_settings(w, h, spp, max_path_length=5, rr_start=8, layers=1, seed=4)
+    film = np.zeros((h, w, 3), np.float32)
+    err = C.create_string_buffer(512)
+    rc = host.selas_host_render_baked_scene(str(tmp_path).encode() + b"/", b"ptexsheet", 0, C.byref(cam), C.byref(rs), film.ctypes.data_as(C.c_void_p), err, 512)
+    assert rc == 0, err.value
+    sc = capi.Scene(ctx, want)
+    ref_film = sc.render(cam, rs)[0][0]
+    want.meshes[0]["ptex"] = None
+    plain = capi.Scene(ctx, want)
+    plain_film = plain.render(cam, rs)[0][0]
+    sc.close()
+    plain.close()
+    tex.close()
+    assert ref_film.sum() > 0
+    np.testing.assert_allclose(film, ref_film, rtol=2e-3, atol=2e-3)  # identical inputs: only the float atomics' order differs
+    assert np.abs(plain_film - ref_film).mean() > 0.05 * ref_film.mean()  # and the texture is what makes the picture
+
+
 def test_baked_scene_golden(host):
     """The committed baked scene (tests/golden/baked_scene, written by make_golden.py with the reference serializer) without the
     reference at hand."""
