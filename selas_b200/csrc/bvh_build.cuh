@@ -100,14 +100,21 @@ SELAS_D uint64_t expandBits21(uint32_t v) {
     return x;
 }
 
+// cube != 0: all three axes are quantised on the grid of the longest one (cubic cells), so the axes with a short extent do not
+// contribute their leading bits -- on a flat scene (terrain) per-axis normalisation splits by height every third level and the
+// resulting strata overlap over the whole ground plane.
 __global__ void mortonKernel(const BuildTri* __restrict__ tris, uint32_t n, const uint32_t* __restrict__ bounds,
-                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int cube) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float lo[3], ext[3];
     for (int k = 0; k < 3; ++k) {
         lo[k] = floatUnflip(bounds[k]);
         ext[k] = floatUnflip(bounds[3 + k]) - lo[k];
+    }
+    if (cube) {
+        const float longest = fmaxf(ext[0], fmaxf(ext[1], ext[2]));
+        ext[0] = ext[1] = ext[2] = longest;
     }
     BuildTri t = tris[i];
     float c[3] = {0.5f * (fminf(t.a.x, fminf(t.b.x, t.c.x)) + fmaxf(t.a.x, fmaxf(t.b.x, t.c.x))),

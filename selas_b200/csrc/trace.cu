@@ -64,7 +64,8 @@ static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* 
     if ((rc = tempAlloc((void**)&d_keysAlt, sizeof(uint64_t) * (size_t)n))) return rc;
     if ((rc = tempAlloc((void**)&d_vals, sizeof(uint32_t) * (size_t)n))) return rc;
     if ((rc = tempAlloc((void**)&d_valsAlt, sizeof(uint32_t) * (size_t)n))) return rc;
-    mortonKernel<<<divUp(n, 256), 256, 0, st>>>(d_tris, n, d_bounds, d_keys, d_vals);
+    static const int mortonCube = getenv("SELAS_MORTON_CUBE") ? atoi(getenv("SELAS_MORTON_CUBE")) : 1;  // A/B switch; cubic cells by default
+    mortonKernel<<<divUp(n, 256), 256, 0, st>>>(d_tris, n, d_bounds, d_keys, d_vals, mortonCube);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
 
     // library radix sort (load-time step, not on the measured path)
