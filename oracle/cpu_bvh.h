@@ -259,6 +259,147 @@ public:
         return out.tri != 0xFFFFFFFFu;
     }
 
+    // ---- tree-quality tooling (scripts/tree_quality.py): the same scene under different builders ---------------------------------
+    // LBVH: 63-bit Morton codes of the triangle-box centres (21 bits per axis, x most significant, as the product's device build),
+    // split top-down at the highest differing bit; cubic = all axes quantised on the grid of the longest one.  Leaves <= 4 triangles.
+    void buildLbvh(bool cubic) {
+        const size_t n = tris.size();
+        nodes.clear();
+        if (n == 0) return;
+        std::vector<float> blo(3 * n), bhi(3 * n);
+        float slo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, shi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                float a = tris[i].v0[k], b = tris[i].v1[k], c = tris[i].v2[k];
+                blo[3 * i + k] = std::min(a, std::min(b, c));
+                bhi[3 * i + k] = std::max(a, std::max(b, c));
+                slo[k] = std::min(slo[k], blo[3 * i + k]);
+                shi[k] = std::max(shi[k], bhi[3 * i + k]);
+            }
+        float ext[3] = {shi[0] - slo[0], shi[1] - slo[1], shi[2] - slo[2]};
+        if (cubic) ext[0] = ext[1] = ext[2] = std::max(ext[0], std::max(ext[1], ext[2]));
+        auto expand = [](uint64_t x) {
+            x &= 0x1fffffull;
+            x = (x | x << 32) & 0x1f00000000ffffull;
+            x = (x | x << 16) & 0x1f0000ff0000ffull;
+            x = (x | x << 8) & 0x100f00f00f00f00full;
+            x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+            x = (x | x << 2) & 0x1249249249249249ull;
+            return x;
+        };
+        std::vector<std::pair<uint64_t, uint32_t>> keyed(n);
+        for (size_t i = 0; i < n; ++i) {
+            uint64_t q[3];
+            for (int k = 0; k < 3; ++k) {
+                float c = 0.5f * (blo[3 * i + k] + bhi[3 * i + k]);
+                float nrm = ext[k] > 0.f ? (c - slo[k]) / ext[k] : 0.f;
+                q[k] = (uint64_t)std::min(std::max(nrm * 2097152.0f, 0.0f), 2097151.0f);
+            }
+            keyed[i] = {(expand(q[0]) << 2) | (expand(q[1]) << 1) | expand(q[2]), (uint32_t)i};
+        }
+        std::sort(keyed.begin(), keyed.end());
+        nodes.reserve(2 * n);
+        nodes.push_back(Node());
+        struct Job { uint32_t node, first, count; };
+        std::vector<Job> stack;
+        stack.push_back({0, 0, (uint32_t)n});
+        while (!stack.empty()) {
+            Job j = stack.back();
+            stack.pop_back();
+            Node nd;
+            for (int k = 0; k < 3; ++k) { nd.lo[k] = FLT_MAX; nd.hi[k] = -FLT_MAX; }
+            for (uint32_t i = j.first; i < j.first + j.count; ++i) {
+                uint32_t t = keyed[i].second;
+                for (int k = 0; k < 3; ++k) {
+                    nd.lo[k] = std::min(nd.lo[k], blo[3 * t + k]);
+                    nd.hi[k] = std::max(nd.hi[k], bhi[3 * t + k]);
+                }
+            }
+            if (j.count <= 4) {
+                nd.left = j.first;
+                nd.count = j.count;
+                nodes[j.node] = nd;
+                continue;
+            }
+            uint64_t a = keyed[j.first].first, b = keyed[j.first + j.count - 1].first;
+            uint32_t mid = j.first + j.count / 2;
+            if (a != b) {
+                int bit = 63 - __builtin_clzll(a ^ b);
+                uint64_t prefix = (b >> bit) << bit;  // first code with that bit set (codes below share the higher bits)
+                auto it = std::lower_bound(keyed.begin() + j.first, keyed.begin() + j.first + j.count, std::make_pair(prefix, (uint32_t)0));
+                mid = (uint32_t)(it - keyed.begin());
+            }
+            nd.count = 0;
+            nd.left = (uint32_t)nodes.size();
+            nodes[j.node] = nd;
+            nodes.push_back(Node());
+            nodes.push_back(Node());
+            stack.push_back({nd.left, j.first, mid - j.first});
+            stack.push_back({nd.left + 1, mid, j.first + j.count - mid});
+        }
+        std::vector<Tri> sorted(n);
+        for (size_t i = 0; i < n; ++i) sorted[i] = tris[keyed[i].second];
+        tris.swap(sorted);
+    }
+
+    // Surface-area-heuristic cost relative to the root: sum of inner-node areas, sum of leaf area x triangle count.
+    void sahCost(double& inner, double& leaf) const {
+        inner = leaf = 0.0;
+        if (nodes.empty()) return;
+        const double root = half_area(nodes[0].lo, nodes[0].hi);
+        for (const Node& nd : nodes) {
+            double a = half_area(nd.lo, nd.hi) / root;
+            if (nd.count) leaf += a * nd.count;
+            else inner += a;
+        }
+    }
+
+    // Closest hit with the near child visited first; counts box tests and triangle tests (what a tree costs a ray).
+    void traceCount(const float of[3], const float df[3], float tfar, uint64_t& boxTests, uint64_t& triTests) const {
+        if (nodes.empty()) return;
+        double o[3] = {of[0], of[1], of[2]}, d[3] = {df[0], df[1], df[2]}, inv[3];
+        for (int k = 0; k < 3; ++k) inv[k] = 1.0 / d[k];
+        double best = tfar;
+        uint32_t stack[128];
+        int sp = 0;
+        stack[sp++] = 0;
+        ++boxTests;
+        if (!slab(nodes[0], o, inv, 0.0, best)) return;
+        while (sp) {
+            const Node& nd = nodes[stack[--sp]];
+            if (nd.count) {
+                for (uint32_t i = nd.left; i < nd.left + nd.count; ++i) {
+                    double t, u, v;
+                    ++triTests;
+                    if (intersect_tri<double>(tris[i], o, d, 0.0, best, t, u, v)) best = t;
+                }
+                continue;
+            }
+            double tn[2];
+            bool hit[2];
+            for (int c = 0; c < 2; ++c) {
+                const Node& ch = nodes[nd.left + c];
+                ++boxTests;
+                double t0 = 0.0, t1 = best;
+                for (int k = 0; k < 3; ++k) {
+                    double x = ((double)ch.lo[k] - o[k]) * inv[k], y = ((double)ch.hi[k] - o[k]) * inv[k];
+                    if (x != x || y != y) continue;
+                    if (x > y) std::swap(x, y);
+                    t0 = std::max(t0, x);
+                    t1 = std::min(t1, y);
+                }
+                hit[c] = t0 <= t1;
+                tn[c] = t0;
+            }
+            if (hit[0] && hit[1]) {
+                int nearC = tn[0] <= tn[1] ? 0 : 1;
+                stack[sp++] = nd.left + (1 - nearC);
+                stack[sp++] = nd.left + nearC;
+            } else if (hit[0]) stack[sp++] = nd.left;
+            else if (hit[1]) stack[sp++] = nd.left + 1;
+        }
+    }
+
 private:
     std::vector<uint32_t> order_;
     static float half_area(const float lo[3], const float hi[3]) {

@@ -609,6 +609,41 @@ int orc_scene_destroy(void* s) {
 }
 size_t orc_scene_triangle_count(void* s) { return ((Scene*)s)->bvh.tris.size(); }
 
+// Tree-quality tooling (scripts/tree_quality.py): one triangle soup under three builders -- builder 0 = binned SAH (the oracle's own),
+// 1 = LBVH with per-axis Morton normalisation, 2 = LBVH on cubic cells (the product's device build) -- with the SAH cost of each tree and
+// the box / triangle tests a set of rays needs (closest hit, near child first).  out4 = {inner SAH, leaf SAH, box tests, tri tests} per ray.
+int orc_tree_quality(size_t ntri, const float* tri9, int builder, size_t nrays, const SelasRay* rays, int nthreads, double* out4) {
+    Bvh bvh;
+    bvh.tris.resize(ntri);
+    for (size_t i = 0; i < ntri; ++i) {
+        memset(&bvh.tris[i], 0, sizeof(Tri));
+        for (int k = 0; k < 3; ++k) {
+            bvh.tris[i].v0[k] = tri9[9 * i + k];
+            bvh.tris[i].v1[k] = tri9[9 * i + 3 + k];
+            bvh.tris[i].v2[k] = tri9[9 * i + 6 + k];
+        }
+    }
+    if (builder == 0) bvh.build();
+    else bvh.buildLbvh(builder == 2);
+    bvh.sahCost(out4[0], out4[1]);
+    std::vector<uint64_t> boxes(nthreads > 0 ? nthreads : 1, 0), tris(nthreads > 0 ? nthreads : 1, 0);
+    parallelFor(nrays, nthreads, [&](size_t b, size_t e, int t) {
+        uint64_t bx = 0, tr = 0;
+        for (size_t i = b; i < e; ++i) {
+            const SelasRay& r = rays[i];
+            float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
+            bvh.traceCount(o, d, r.tfar, bx, tr);
+        }
+        boxes[t] += bx;
+        tris[t] += tr;
+    });
+    uint64_t bx = 0, tr = 0;
+    for (size_t t = 0; t < boxes.size(); ++t) { bx += boxes[t]; tr += tris[t]; }
+    out4[2] = nrays ? (double)bx / (double)nrays : 0.0;
+    out4[3] = nrays ? (double)tr / (double)nrays : 0.0;
+    return 0;
+}
+
 // mode: 0 = float BVH (timed CPU baseline), 1 = double BVH (hit-ID oracle), 2 = double brute force
 int orc_intersect(void* s, size_t n, const SelasRay* rays, SelasHit* hits, float* Ng4, int mode, int nthreads) {
     const Scene& sc = *(Scene*)s;
