@@ -77,7 +77,9 @@ public:
     std::vector<Tri> tris;
     std::vector<Node> nodes;
 
-    void build() {
+    // lbvhBelow > 0 (tree-quality tooling): ranges of at most that many triangles are finished as an LBVH over cubic Morton codes, i.e. the
+    // binned SAH only shapes the top of the tree.
+    void build(uint32_t lbvhBelow = 0) {
         const size_t n = tris.size();
         nodes.clear();
         if (n == 0) return;
@@ -94,13 +96,34 @@ public:
                 cen[3 * i + k] = 0.5f * (lo + hi);
             }
         }
+        std::vector<uint64_t> codes;
+        if (lbvhBelow) {
+            float slo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, shi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (size_t i = 0; i < n; ++i)
+                for (int k = 0; k < 3; ++k) { slo[k] = std::min(slo[k], blo[3 * i + k]); shi[k] = std::max(shi[k], bhi[3 * i + k]); }
+            const float longest = std::max(shi[0] - slo[0], std::max(shi[1] - slo[1], shi[2] - slo[2]));
+            codes.resize(n);
+            for (size_t i = 0; i < n; ++i) {
+                uint64_t q[3];
+                for (int k = 0; k < 3; ++k) {
+                    float nrm = longest > 0.f ? (cen[3 * i + k] - slo[k]) / longest : 0.f;
+                    q[k] = (uint64_t)std::min(std::max(nrm * 2097152.0f, 0.0f), 2097151.0f);
+                }
+                codes[i] = (expandBits21(q[0]) << 2) | (expandBits21(q[1]) << 1) | expandBits21(q[2]);
+            }
+        }
         nodes.push_back(Node());
-        struct Job { uint32_t node, first, count; };
+        struct Job { uint32_t node, first, count; bool lbvh; };
         std::vector<Job> stack;
-        stack.push_back({0, 0, (uint32_t)n});
+        stack.push_back({0, 0, (uint32_t)n, false});
         while (!stack.empty()) {
             Job j = stack.back();
             stack.pop_back();
+            if (lbvhBelow && !j.lbvh && j.count <= lbvhBelow) {  // from here down: Morton order, highest-differing-bit splits
+                std::sort(order_.begin() + j.first, order_.begin() + j.first + j.count,
+                          [&](uint32_t a, uint32_t b) { return codes[a] < codes[b] || (codes[a] == codes[b] && a < b); });
+                j.lbvh = true;
+            }
             float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
             float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
             for (uint32_t i = j.first; i < j.first + j.count; ++i) {
@@ -123,6 +146,25 @@ public:
                 nd.left = j.first;
                 nd.count = j.count;
                 nodes[j.node] = nd;
+                continue;
+            }
+            if (j.lbvh) {
+                uint64_t a = codes[order_[j.first]], b = codes[order_[j.first + j.count - 1]];
+                uint32_t mid = j.first + j.count / 2;
+                if (a != b) {
+                    int bit = 63 - __builtin_clzll(a ^ b);
+                    uint64_t prefix = (b >> bit) << bit;
+                    auto it = std::lower_bound(order_.begin() + j.first, order_.begin() + j.first + j.count, prefix,
+                                               [&](uint32_t t, uint64_t key) { return codes[t] < key; });
+                    mid = (uint32_t)(it - order_.begin());
+                }
+                nd.count = 0;
+                nd.left = (uint32_t)nodes.size();
+                nodes[j.node] = nd;
+                nodes.push_back(Node());
+                nodes.push_back(Node());
+                stack.push_back({nd.left, j.first, mid - j.first, true});
+                stack.push_back({nd.left + 1, mid, j.first + j.count - mid, true});
                 continue;
             }
             // binned SAH, 16 bins per axis
@@ -185,8 +227,8 @@ public:
             nodes[j.node] = nd;
             nodes.push_back(Node());
             nodes.push_back(Node());
-            stack.push_back({nd.left, j.first, mid - j.first});
-            stack.push_back({nd.left + 1, mid, j.first + j.count - mid});
+            stack.push_back({nd.left, j.first, mid - j.first, false});
+            stack.push_back({nd.left + 1, mid, j.first + j.count - mid, false});
         }
         std::vector<Tri> sorted(n);
         for (size_t i = 0; i < n; ++i) sorted[i] = tris[order_[i]];
@@ -262,7 +304,9 @@ public:
     // ---- tree-quality tooling (scripts/tree_quality.py): the same scene under different builders ---------------------------------
     // LBVH: 63-bit Morton codes of the triangle-box centres (21 bits per axis, x most significant, as the product's device build),
     // split top-down at the highest differing bit; cubic = all axes quantised on the grid of the longest one.  Leaves <= 4 triangles.
-    void buildLbvh(bool cubic) {
+    // sweep = true keeps the Morton order of the triangles but places every split where the surface area heuristic is lowest along
+    // that order (a sweep over the node's range) instead of at the highest differing bit.
+    void buildLbvh(bool cubic, bool sweep = false) {
         const size_t n = tris.size();
         nodes.clear();
         if (n == 0) return;
@@ -278,15 +322,7 @@ public:
             }
         float ext[3] = {shi[0] - slo[0], shi[1] - slo[1], shi[2] - slo[2]};
         if (cubic) ext[0] = ext[1] = ext[2] = std::max(ext[0], std::max(ext[1], ext[2]));
-        auto expand = [](uint64_t x) {
-            x &= 0x1fffffull;
-            x = (x | x << 32) & 0x1f00000000ffffull;
-            x = (x | x << 16) & 0x1f0000ff0000ffull;
-            x = (x | x << 8) & 0x100f00f00f00f00full;
-            x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-            x = (x | x << 2) & 0x1249249249249249ull;
-            return x;
-        };
+        auto expand = [](uint64_t x) { return expandBits21(x); };
         std::vector<std::pair<uint64_t, uint32_t>> keyed(n);
         for (size_t i = 0; i < n; ++i) {
             uint64_t q[3];
@@ -323,7 +359,25 @@ public:
             }
             uint64_t a = keyed[j.first].first, b = keyed[j.first + j.count - 1].first;
             uint32_t mid = j.first + j.count / 2;
-            if (a != b) {
+            if (sweep) {
+                std::vector<float>& suffix = sweepScratch_;
+                suffix.resize(j.count + 1);
+                float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+                suffix[j.count] = 0.f;
+                for (uint32_t i = j.count; i-- > 0;) {
+                    uint32_t t = keyed[j.first + i].second;
+                    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], blo[3 * t + k]); hi[k] = std::max(hi[k], bhi[3 * t + k]); }
+                    suffix[i] = half_area(lo, hi);
+                }
+                for (int k = 0; k < 3; ++k) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+                float bestCost = FLT_MAX;
+                for (uint32_t i = 0; i + 1 < j.count; ++i) {
+                    uint32_t t = keyed[j.first + i].second;
+                    for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], blo[3 * t + k]); hi[k] = std::max(hi[k], bhi[3 * t + k]); }
+                    float cost = half_area(lo, hi) * (float)(i + 1) + suffix[i + 1] * (float)(j.count - i - 1);
+                    if (cost < bestCost) { bestCost = cost; mid = j.first + i + 1; }
+                }
+            } else if (a != b) {
                 int bit = 63 - __builtin_clzll(a ^ b);
                 uint64_t prefix = (b >> bit) << bit;  // first code with that bit set (codes below share the higher bits)
                 auto it = std::lower_bound(keyed.begin() + j.first, keyed.begin() + j.first + j.count, std::make_pair(prefix, (uint32_t)0));
@@ -401,7 +455,17 @@ public:
     }
 
 private:
+    static uint64_t expandBits21(uint64_t x) {
+        x &= 0x1fffffull;
+        x = (x | x << 32) & 0x1f00000000ffffull;
+        x = (x | x << 16) & 0x1f0000ff0000ffull;
+        x = (x | x << 8) & 0x100f00f00f00f00full;
+        x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+        x = (x | x << 2) & 0x1249249249249249ull;
+        return x;
+    }
     std::vector<uint32_t> order_;
+    std::vector<float> sweepScratch_;
     static float half_area(const float lo[3], const float hi[3]) {
         float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
         return x * y + y * z + z * x;

@@ -610,7 +610,8 @@ int orc_scene_destroy(void* s) {
 size_t orc_scene_triangle_count(void* s) { return ((Scene*)s)->bvh.tris.size(); }
 
 // Tree-quality tooling (scripts/tree_quality.py): one triangle soup under three builders -- builder 0 = binned SAH (the oracle's own),
-// 1 = LBVH with per-axis Morton normalisation, 2 = LBVH on cubic cells (the product's device build) -- with the SAH cost of each tree and
+// 1 = LBVH with per-axis Morton normalisation, 2 = LBVH on cubic cells (the product's device build), 3 = cubic Morton order with
+// SAH-swept split positions, >= 16 = binned SAH for the top of the tree and cubic LBVH for ranges of at most that many triangles -- with the SAH cost of each tree and
 // the box / triangle tests a set of rays needs (closest hit, near child first).  out4 = {inner SAH, leaf SAH, box tests, tri tests} per ray.
 int orc_tree_quality(size_t ntri, const float* tri9, int builder, size_t nrays, const SelasRay* rays, int nthreads, double* out4) {
     Bvh bvh;
@@ -624,7 +625,8 @@ int orc_tree_quality(size_t ntri, const float* tri9, int builder, size_t nrays, 
         }
     }
     if (builder == 0) bvh.build();
-    else bvh.buildLbvh(builder == 2);
+    else if (builder >= 16) bvh.build((uint32_t)builder);  // binned SAH above ranges of `builder` triangles, cubic LBVH below
+    else bvh.buildLbvh(builder >= 2, builder == 3);
     bvh.sahCost(out4[0], out4[1]);
     std::vector<uint64_t> boxes(nthreads > 0 ? nthreads : 1, 0), tris(nthreads > 0 ? nthreads : 1, 0);
     parallelFor(nrays, nthreads, [&](size_t b, size_t e, int t) {

@@ -55,7 +55,8 @@ def main():
     threads = len(os.sched_getaffinity(0))
     f = orc.fn("tree_quality")
     doc = {"triangles": int(tri.shape[0]), "rays_each": int(n), "builders": {}}
-    for name, b in (("binned_sah", 0), ("lbvh_per_axis", 1), ("lbvh_cubic", 2)):
+    for name, b in (("binned_sah", 0), ("lbvh_per_axis", 1), ("lbvh_cubic", 2), ("morton_order_sah_sweep", 3), ("sah_top_lbvh_below_65536", 65536),
+                    ("sah_top_lbvh_below_4096", 4096), ("sah_top_lbvh_below_256", 256)):
         row = {}
         for rname, rays in (("camera", primary), ("incoherent", inco)):
             out = (C.c_double * 4)()
