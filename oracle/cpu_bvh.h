@@ -79,7 +79,8 @@ public:
 
     // lbvhBelow > 0 (tree-quality tooling): ranges of at most that many triangles are finished as an LBVH over cubic Morton codes, i.e. the
     // binned SAH only shapes the top of the tree.
-    void build(uint32_t lbvhBelow = 0) {
+    // lbvhAbove > 0 is the opposite: Morton splits for ranges larger than that, binned SAH inside them.
+    void build(uint32_t lbvhBelow = 0, uint32_t lbvhAbove = 0) {
         const size_t n = tris.size();
         nodes.clear();
         if (n == 0) return;
@@ -97,7 +98,7 @@ public:
             }
         }
         std::vector<uint64_t> codes;
-        if (lbvhBelow) {
+        if (lbvhBelow || lbvhAbove) {
             float slo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, shi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
             for (size_t i = 0; i < n; ++i)
                 for (int k = 0; k < 3; ++k) { slo[k] = std::min(slo[k], blo[3 * i + k]); shi[k] = std::max(shi[k], bhi[3 * i + k]); }
@@ -115,10 +116,13 @@ public:
         nodes.push_back(Node());
         struct Job { uint32_t node, first, count; bool lbvh; };
         std::vector<Job> stack;
-        stack.push_back({0, 0, (uint32_t)n, false});
+        if (lbvhAbove)
+            std::sort(order_.begin(), order_.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b] || (codes[a] == codes[b] && a < b); });
+        stack.push_back({0, 0, (uint32_t)n, lbvhAbove && n > lbvhAbove});
         while (!stack.empty()) {
             Job j = stack.back();
             stack.pop_back();
+            if (lbvhAbove) j.lbvh = j.count > lbvhAbove;
             if (lbvhBelow && !j.lbvh && j.count <= lbvhBelow) {  // from here down: Morton order, highest-differing-bit splits
                 std::sort(order_.begin() + j.first, order_.begin() + j.first + j.count,
                           [&](uint32_t a, uint32_t b) { return codes[a] < codes[b] || (codes[a] == codes[b] && a < b); });
@@ -393,6 +397,122 @@ public:
         }
         std::vector<Tri> sorted(n);
         for (size_t i = 0; i < n; ++i) sorted[i] = tris[keyed[i].second];
+        tris.swap(sorted);
+    }
+
+    // PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) written serially: clusters start as the triangles in cubic Morton
+    // order; every round each cluster looks `radius` places to either side for the partner with the smallest merged surface area, mutual
+    // choices merge, the array is compacted.  Subtrees of at most 4 triangles become leaves.
+    void buildPloc(int radius) {
+        const size_t n = tris.size();
+        nodes.clear();
+        if (n == 0) return;
+        struct T { float lo[3], hi[3]; uint32_t left, right, count; };  // leaf: left = triangle id, right = 0xFFFFFFFF
+        std::vector<T> t;
+        t.reserve(2 * n);
+        float slo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, shi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (size_t i = 0; i < n; ++i) {
+            T leaf;
+            for (int k = 0; k < 3; ++k) {
+                float a = tris[i].v0[k], b = tris[i].v1[k], c = tris[i].v2[k];
+                leaf.lo[k] = std::min(a, std::min(b, c));
+                leaf.hi[k] = std::max(a, std::max(b, c));
+                slo[k] = std::min(slo[k], leaf.lo[k]);
+                shi[k] = std::max(shi[k], leaf.hi[k]);
+            }
+            leaf.left = (uint32_t)i;
+            leaf.right = 0xFFFFFFFFu;
+            leaf.count = 1;
+            t.push_back(leaf);
+        }
+        const float longest = std::max(shi[0] - slo[0], std::max(shi[1] - slo[1], shi[2] - slo[2]));
+        std::vector<std::pair<uint64_t, uint32_t>> keyed(n);
+        for (size_t i = 0; i < n; ++i) {
+            uint64_t q[3];
+            for (int k = 0; k < 3; ++k) {
+                float c = 0.5f * (t[i].lo[k] + t[i].hi[k]);
+                float nrm = longest > 0.f ? (c - slo[k]) / longest : 0.f;
+                q[k] = (uint64_t)std::min(std::max(nrm * 2097152.0f, 0.0f), 2097151.0f);
+            }
+            keyed[i] = {(expandBits21(q[0]) << 2) | (expandBits21(q[1]) << 1) | expandBits21(q[2]), (uint32_t)i};
+        }
+        std::sort(keyed.begin(), keyed.end());
+        std::vector<uint32_t> cur(n), next, nearest;
+        for (size_t i = 0; i < n; ++i) cur[i] = keyed[i].second;
+        auto mergedArea = [&](uint32_t a, uint32_t b) {
+            float lo[3], hi[3];
+            for (int k = 0; k < 3; ++k) { lo[k] = std::min(t[a].lo[k], t[b].lo[k]); hi[k] = std::max(t[a].hi[k], t[b].hi[k]); }
+            return half_area(lo, hi);
+        };
+        while (cur.size() > 1) {
+            const int m = (int)cur.size();
+            nearest.assign(m, 0);
+            for (int i = 0; i < m; ++i) {
+                float best = FLT_MAX;
+                int bj = i == 0 ? 1 : i - 1;
+                for (int j = std::max(0, i - radius); j <= std::min(m - 1, i + radius); ++j) {
+                    if (j == i) continue;
+                    float a = mergedArea(cur[i], cur[j]);
+                    if (a < best) { best = a; bj = j; }
+                }
+                nearest[i] = (uint32_t)bj;
+            }
+            next.clear();
+            for (int i = 0; i < m; ++i) {
+                int j = (int)nearest[i];
+                if ((int)nearest[j] == i) {
+                    if (i < j) {
+                        T nd;
+                        for (int k = 0; k < 3; ++k) { nd.lo[k] = std::min(t[cur[i]].lo[k], t[cur[j]].lo[k]); nd.hi[k] = std::max(t[cur[i]].hi[k], t[cur[j]].hi[k]); }
+                        nd.left = cur[i];
+                        nd.right = cur[j];
+                        nd.count = t[cur[i]].count + t[cur[j]].count;
+                        t.push_back(nd);
+                        next.push_back((uint32_t)t.size() - 1);
+                    }
+                } else {
+                    next.push_back(cur[i]);
+                }
+            }
+            cur.swap(next);
+        }
+        // lay the tree out in this class's format (inner: children adjacent; leaf: a contiguous triangle range)
+        std::vector<Tri> sorted;
+        sorted.reserve(n);
+        nodes.reserve(2 * n);
+        nodes.push_back(Node());
+        struct Job { uint32_t node, src; };
+        std::vector<Job> stack;
+        stack.push_back({0, cur[0]});
+        std::vector<uint32_t> walk;
+        while (!stack.empty()) {
+            Job j = stack.back();
+            stack.pop_back();
+            const T& src = t[j.src];
+            Node nd;
+            for (int k = 0; k < 3; ++k) { nd.lo[k] = src.lo[k]; nd.hi[k] = src.hi[k]; }
+            if (src.count <= 4) {
+                nd.left = (uint32_t)sorted.size();
+                nd.count = src.count;
+                walk.clear();
+                walk.push_back(j.src);
+                while (!walk.empty()) {
+                    uint32_t w = walk.back();
+                    walk.pop_back();
+                    if (t[w].right == 0xFFFFFFFFu) sorted.push_back(tris[t[w].left]);
+                    else { walk.push_back(t[w].right); walk.push_back(t[w].left); }
+                }
+                nodes[j.node] = nd;
+                continue;
+            }
+            nd.count = 0;
+            nd.left = (uint32_t)nodes.size();
+            nodes[j.node] = nd;
+            nodes.push_back(Node());
+            nodes.push_back(Node());
+            stack.push_back({nd.left, src.left});
+            stack.push_back({nd.left + 1, src.right});
+        }
         tris.swap(sorted);
     }
 

@@ -611,7 +611,7 @@ size_t orc_scene_triangle_count(void* s) { return ((Scene*)s)->bvh.tris.size(); 
 
 // Tree-quality tooling (scripts/tree_quality.py): one triangle soup under three builders -- builder 0 = binned SAH (the oracle's own),
 // 1 = LBVH with per-axis Morton normalisation, 2 = LBVH on cubic cells (the product's device build), 3 = cubic Morton order with
-// SAH-swept split positions, >= 16 = binned SAH for the top of the tree and cubic LBVH for ranges of at most that many triangles -- with the SAH cost of each tree and
+// SAH-swept split positions, >= 16 = binned SAH for the top of the tree and cubic LBVH for ranges of at most that many triangles, < 0 = PLOC with that search radius -- with the SAH cost of each tree and
 // the box / triangle tests a set of rays needs (closest hit, near child first).  out4 = {inner SAH, leaf SAH, box tests, tri tests} per ray.
 int orc_tree_quality(size_t ntri, const float* tri9, int builder, size_t nrays, const SelasRay* rays, int nthreads, double* out4) {
     Bvh bvh;
@@ -625,6 +625,8 @@ int orc_tree_quality(size_t ntri, const float* tri9, int builder, size_t nrays, 
         }
     }
     if (builder == 0) bvh.build();
+    else if (builder < 0) bvh.buildPloc(-builder);      // PLOC with search radius -builder over the cubic Morton order
+    else if (builder >= (1 << 24)) bvh.build(0, (uint32_t)(builder - (1 << 24)));  // cubic LBVH above ranges of that many triangles, binned SAH inside
     else if (builder >= 16) bvh.build((uint32_t)builder);  // binned SAH above ranges of `builder` triangles, cubic LBVH below
     else bvh.buildLbvh(builder >= 2, builder == 3);
     bvh.sahCost(out4[0], out4[1]);

@@ -56,7 +56,8 @@ def main():
     f = orc.fn("tree_quality")
     doc = {"triangles": int(tri.shape[0]), "rays_each": int(n), "builders": {}}
     for name, b in (("binned_sah", 0), ("lbvh_per_axis", 1), ("lbvh_cubic", 2), ("morton_order_sah_sweep", 3), ("sah_top_lbvh_below_65536", 65536),
-                    ("sah_top_lbvh_below_4096", 4096), ("sah_top_lbvh_below_256", 256)):
+                    ("sah_top_lbvh_below_4096", 4096), ("sah_top_lbvh_below_256", 256), ("ploc_radius_8", -8), ("ploc_radius_32", -32),
+                    ("lbvh_top_sah_inside_256", (1 << 24) + 256), ("lbvh_top_sah_inside_4096", (1 << 24) + 4096)):
         row = {}
         for rname, rays in (("camera", primary), ("incoherent", inco)):
             out = (C.c_double * 4)()
