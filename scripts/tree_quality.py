@@ -33,28 +33,40 @@ def soup(data):
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="configs2", choices=["configs2", "configs1", "configs3"],
+                    help="configs2 = heightfield + spheres (bench.py), configs1 = 1 M-triangle displaced sphere, configs3 = Ptex sheet")
     ap.add_argument("--grid", type=int, default=2236)
     ap.add_argument("--width", type=int, default=480)
     ap.add_argument("--height", type=int, default=270)
     args = ap.parse_args()
     orc = oracle_binding.load_oracle()
-    data = scenes.disney_heightfield(grid=args.grid)
+    if args.scene == "configs2":
+        data, cam = scenes.disney_heightfield(grid=args.grid), scenes.heightfield_camera(args.width, args.height)
+    elif args.scene == "configs1":
+        data, cam = scenes.raycast_scene(), scenes.raycast_camera(args.width, args.height)
+    else:
+        data, cam = scenes.ptex_quad_grid(), scenes.ptex_grid_camera(args.width, args.height)
     tri = soup(data)
-    cam = scenes.heightfield_camera(args.width, args.height)
     primary = scenes.primary_rays(cam, args.width, args.height)
     rng = np.random.default_rng(12)
     n = primary.size
     inco = np.zeros(n, dtype=capi.RAY_DTYPE)  # bounce-like rays: from points just above the terrain into the upper hemisphere and sideways
-    inco["ox"], inco["oz"] = rng.uniform(-9, 9, n), rng.uniform(-9, 9, n)
-    inco["oy"] = rng.uniform(-1.0, 1.5, n)
+    lo, hi = tri.reshape(-1, 3).min(axis=0), tri.reshape(-1, 3).max(axis=0)
     d = rng.normal(size=(n, 3))
-    d[:, 1] = np.abs(d[:, 1]) * 0.3 - 0.2
+    if args.scene == "configs2":
+        inco["ox"], inco["oz"] = rng.uniform(-9, 9, n), rng.uniform(-9, 9, n)
+        inco["oy"] = rng.uniform(-1.0, 1.5, n)
+        d[:, 1] = np.abs(d[:, 1]) * 0.3 - 0.2
+    else:  # random chords through the scene's box
+        a, b = rng.uniform(lo, hi, size=(n, 3)), rng.uniform(lo, hi, size=(n, 3))
+        inco["ox"], inco["oy"], inco["oz"] = a[:, 0], a[:, 1], a[:, 2]
+        d = b - a
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     inco["dx"], inco["dy"], inco["dz"] = d[:, 0], d[:, 1], d[:, 2]
     inco["tnear"], inco["tfar"] = 0.0, 3.0e38
     threads = len(os.sched_getaffinity(0))
     f = orc.fn("tree_quality")
-    doc = {"triangles": int(tri.shape[0]), "rays_each": int(n), "builders": {}}
+    doc = {"scene": args.scene, "triangles": int(tri.shape[0]), "rays_each": int(n), "builders": {}}
     for name, b in (("binned_sah", 0), ("lbvh_per_axis", 1), ("lbvh_cubic", 2), ("morton_order_sah_sweep", 3), ("sah_top_lbvh_below_65536", 65536),
                     ("sah_top_lbvh_below_4096", 4096), ("sah_top_lbvh_below_256", 256), ("ploc_radius_8", -8), ("ploc_radius_32", -32),
                     ("lbvh_top_sah_inside_256", (1 << 24) + 256), ("lbvh_top_sah_inside_4096", (1 << 24) + 4096)):
