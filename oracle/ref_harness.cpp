@@ -59,31 +59,10 @@ static_assert(sizeof(Selas::BsdfSample) == 52, "BsdfSample layout");
 static_assert(sizeof(Selas::LightDirectSample) == sizeof(SelasLightSample), "LightDirectSample layout");
 
 // ---- scripted uniform source ------------------------------------------------------------------------------
-namespace {
-struct DrawSource {
-    const float* script;  // scripted values (bsdf/light unit tests) ...
-    uint32_t pos, count;
-    uint32_t pcg;  // ... or the product's PCG stream (integrator)
-    bool usePcg;
-};
-thread_local DrawSource g_src = {nullptr, 0, 0, 0, false};
-thread_local std::mt19937* g_mt = nullptr;
-
-inline uint32_t mix32(uint32_t x) {
-    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-    return x;
-}
-inline float pcgNext(uint32_t& state) {
-    state = state * 747796405u + 2891336453u;
-    uint32_t w = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
-    w = (w >> 22u) ^ w;
-    return (float)(w >> 8) * (1.0f / 16777216.0f);
-}
-void setFtz() {
-    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
-    _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
-}
-}  // namespace
+#include "ref_harness.h"
+using namespace refh;
+thread_local refh::DrawSource refh::g_src = {nullptr, 0, 0, 0, false};
+thread_local std::mt19937* refh::g_mt = nullptr;
 
 namespace Selas {
 // platform shims -------------------------------------------------------------------------------------------
@@ -107,17 +86,6 @@ namespace Directory {
 void EnsureDirectoryExists(const char*) {}
 }
 Error StbImageWrite(cpointer, uint, uint, uint, StbImageFormats, void*) { return Error_("oracle harness: no image IO"); }
-// Shading/SurfaceParameters.cpp is not linked (it needs Embree + the caches); these two accessors are the
-// only symbols of it the BSDF code uses.  They read column 1 of worldToTangent (SurfaceParameters.cpp:391).
-float3 GeometricNormal(const SurfaceParameters& surface) {
-    return float3(surface.worldToTangent.r0.y, surface.worldToTangent.r1.y, surface.worldToTangent.r2.y);
-}
-float3 OffsetRayOrigin(const SurfaceParameters& surface, float3 direction, float biasScale) {
-    float directionOffset = Dot(direction, GeometricNormal(surface)) < 0.0f ? -1.0f : 1.0f;
-    float3 offset = directionOffset * surface.error * biasScale * GeometricNormal(surface);
-    return surface.position + offset;
-}
-
 // CSampler with a scriptable stream (MathLib/Sampler.cpp is not linked).
 void CSampler::Initialize(uint32 seed) {
     if (!g_mt) g_mt = new std::mt19937();
@@ -154,62 +122,6 @@ float CSampler::UniformSpherePdf() { return Math::Inv4Pi_; }
 using namespace Selas;
 
 namespace {
-
-// A GIIntegratorContext + SceneResource carved out of zeroed storage: their constructors live in TUs that
-// need Embree, and only `sampler`, `scene->lightSets`, `scene->data->backgroundIntensity`, `scene->iblResource`
-// are read by the functions called here.
-struct FakeContext {
-    alignas(16) unsigned char ctxBytes[sizeof(GIIntegratorContext)];
-    alignas(16) unsigned char sceneBytes[sizeof(SceneResource)];
-    alignas(16) unsigned char dataBytes[sizeof(SceneResourceData)];
-    std::vector<SceneLight> lights;
-    std::vector<SceneLightSet> sets;
-    alignas(16) unsigned char iblResBytes[sizeof(ImageBasedLightResource)];
-    ImageBasedLightResourceData iblData;
-    void setIbl(const ImageBasedLightResourceData* src) {  // borrowed arrays; the resource struct is never destructed
-        if (!src) return;
-        iblData = *src;
-        ImageBasedLightResource* res = reinterpret_cast<ImageBasedLightResource*>(iblResBytes);
-        res->data = &iblData;
-        scene()->iblResource = res;
-    }
-    GIIntegratorContext* ctx() { return reinterpret_cast<GIIntegratorContext*>(ctxBytes); }
-    SceneResource* scene() { return reinterpret_cast<SceneResource*>(sceneBytes); }
-    SceneResourceData* data() { return reinterpret_cast<SceneResourceData*>(dataBytes); }
-
-    void init(const SelasLight* L, uint32_t lightCount, const SelasLightSetRange* ranges, uint32_t setCount,
-              const float* background) {
-        memset(ctxBytes, 0, sizeof(ctxBytes));
-        memset(sceneBytes, 0, sizeof(sceneBytes));
-        memset(dataBytes, 0, sizeof(dataBytes));
-        lights.resize(lightCount);
-        if (lightCount) memcpy(lights.data(), L, sizeof(SceneLight) * lightCount);
-        sets.clear();
-        for (uint32_t i = 0; i < setCount; ++i) {
-            SceneLightSet s;
-            s.count = ranges[i].count;
-            s.lights = lights.data() + ranges[i].start;
-            sets.push_back(s);
-        }
-        // CArray<SceneLightSet> laid out as {flags,pad,count,capacity,data} (ContainersLib/CArray.h:57-62)
-        struct RawArray { uint32_t flags, pad; uint64_t count, capacity; void* data; };
-        static_assert(sizeof(RawArray) == sizeof(CArray<SceneLightSet>), "CArray layout");
-        RawArray raw = {0, 0, sets.size(), sets.size(), sets.data()};
-        memcpy(&scene()->lightSets, &raw, sizeof(raw));
-        if (background) data()->backgroundIntensity = float4(background[0], background[1], background[2], background[3]);
-        scene()->data = data();
-        scene()->iblResource = nullptr;
-        ctx()->scene = scene();
-    }
-    ~FakeContext() {
-        // make the borrowed CArray look empty so nothing is freed
-        memset(&scene()->lightSets, 0, sizeof(scene()->lightSets));
-    }
-};
-
-inline float3 f3(const float* p) { return float3(p[0], p[1], p[2]); }
-inline void st3(float* p, float3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
-
 void copySample(const BsdfSample& b, bool ok, uint32_t used, SelasBsdfSample& o) {
     o.flags = b.flags;
     o.mediumPhase = (uint32_t)b.medium.phaseFunction;
@@ -425,57 +337,6 @@ int ref_ibl_lookup(void* s, size_t n, const float* wi3, float* rgb3, float* pdf,
 int ref_ibl_sample(void* s, size_t n, const float* u2, float* thetaPhiPdf3, uint32_t* xy2);
 
 // ---- tier-B CPU integrator: reference shading + restated ray cast --------------------------------------------
-struct RefIbl {
-    std::vector<float> marginal, conditional, light, miss;
-    ImageBasedLightResourceData data;
-    bool present = false;
-    void set(const SelasIblDesc* I) {
-        if (!I) return;
-        marginal.assign(I->marginalDensityFunction, I->marginalDensityFunction + I->height);
-        conditional.assign(I->conditionalDensityFunctions, I->conditionalDensityFunctions + (size_t)I->width * I->height);
-        // the reference clamps texel coordinates to [0, width] / [0, height] (appendix B #23) and can read one row past the image;
-        // pad one row (a copy of the last texel, which is what the restatement and the CUDA path read) so that stays defined
-        light.assign(I->lightData, I->lightData + 3 * (size_t)I->width * I->height);
-        miss.assign(I->missData, I->missData + 3 * (size_t)I->missWidth * I->missHeight);
-        auto pad = [](std::vector<float>& img, size_t w) {
-            float last[3] = {img[img.size() - 3], img[img.size() - 2], img[img.size() - 1]};
-            for (size_t i = 0; i < w + 1; ++i) img.insert(img.end(), last, last + 3);
-        };
-        pad(light, I->width);
-        pad(miss, I->missWidth);
-        float lastC = conditional.back();
-        conditional.resize(conditional.size() + I->width + 1, lastC);
-        marginal.push_back(marginal.back());
-        memset(&data, 0, sizeof(data));
-        data.densityfunctions.width = I->width;
-        data.densityfunctions.height = I->height;
-        data.densityfunctions.marginalDensityFunction = marginal.data();
-        data.densityfunctions.conditionalDensityFunctions = conditional.data();
-        data.missWidth = I->missWidth;
-        data.missHeight = I->missHeight;
-        data.rotationRadians = I->rotationRadians;
-        data.exposureScale = I->exposureScale;
-        data.lightData = reinterpret_cast<float3*>(light.data());
-        data.missData = reinterpret_cast<float3*>(miss.data());
-        present = true;
-    }
-};
-
-struct RefScene {
-    RefIbl ibl;
-    struct Mesh {
-        std::vector<float> positions, normals, tangents;
-        std::vector<uint32_t> indices;
-        uint32_t indicesPerFace, materialIndex, lightSetIndex;
-    };
-    std::vector<Mesh> meshes;
-    std::vector<SelasMaterial> materials;
-    std::vector<SelasLight> lights;
-    std::vector<SelasLightSetRange> sets;
-    float background[4];
-    orc::Bvh bvh;
-};
-
 int ref_scene_create(const SelasSceneDesc* d, void** out) {
     if (d->instanceCount) return 5;  // the tier-B integrator handles the identity single-instance scenes only
     for (uint32_t m = 0; m < d->meshCount; ++m)
@@ -488,6 +349,7 @@ int ref_scene_create(const SelasSceneDesc* d, void** out) {
         M.positions.assign(md.positions, md.positions + 3 * (size_t)md.vertexCount);
         if (md.normals) M.normals.assign(md.normals, md.normals + 3 * (size_t)md.vertexCount);
         if (md.tangents) M.tangents.assign(md.tangents, md.tangents + 4 * (size_t)md.vertexCount);
+        if (md.uvs) M.uvs.assign(md.uvs, md.uvs + 2 * (size_t)md.vertexCount);
         M.indices.assign(md.indices, md.indices + (size_t)md.faceCount * md.indicesPerFace);
         M.indicesPerFace = md.indicesPerFace;
         M.materialIndex = md.materialIndex;

@@ -287,6 +287,27 @@ class Ref(ShadingOracle):
     def sizeof(self, name):
         return self.fn("sizeof")(name.encode())
 
+    def render_reference_loop(self, h, camera, settings, nthreads=8):
+        """The reference's own PathTracer.cpp EvaluatePath + SurfaceParameters.cpp CalculateSurfaceParams + Framebuffer.cpp writers,
+        compiled unmodified behind the Embree-API shim of oracle/ref_pathtracer.cpp (integrator 0, misMode 0, RR after bounce 8)."""
+        w, hgt, layers = settings.width, settings.height, settings.layerCount
+        film = [np.zeros((hgt, w, 3), np.float32) for _ in range(layers)]
+        ptrs = (C.c_void_p * layers)(*[f.ctypes.data for f in film])
+        stats = capi.RenderStats()
+        rc = self.lib.refpt_render(h, C.byref(camera), C.byref(settings), ptrs, C.byref(stats), C.c_int(nthreads))
+        if rc:
+            raise RuntimeError(f"refpt_render failed: {rc}")
+        return film, stats
+
+    def surface_params_reference(self, h, rays, hits):
+        """CalculateSurfaceParams (SurfaceParameters.cpp:144-247, unmodified) on a batch of hits."""
+        rays = np.ascontiguousarray(rays, dtype=capi.RAY_DTYPE)
+        hits = np.ascontiguousarray(hits, dtype=capi.HIT_DTYPE)
+        out = np.zeros(rays.size, dtype=capi.SURFACE_DTYPE)
+        rc = self.lib.refpt_surface_params(h, C.c_size_t(rays.size), _ptr(rays), _ptr(hits), _ptr(out))
+        assert rc == 0, rc
+        return out
+
     def hashgrid_build(self, positions, radius, cell_count):
         positions = _f32(positions).reshape(-1, 3)
         n = positions.shape[0]

@@ -344,3 +344,83 @@ def test_oracle_ptex_hook_surface_params(oracle, ptexref):
     assert np.abs(s["baseColor"] - want).max() <= 2e-6  # powf vs numpy's float32 power
     oracle.scene_destroy(hs)
     ptexref.close(th)
+
+
+# ---- the reference's own integrator loop (oracle/ref_pathtracer.cpp: PathTracer.cpp + SurfaceParameters.cpp + Framebuffer.cpp unmodified) ----
+def _loop_cases():
+    from selas_b200 import scenes
+
+    yield "cornell", scenes.cornell_box(copper_roughness=0.1), scenes.cornell_camera(48, 48), (48, 48), 8
+    # all eight materials of configs[2] (metal-aniso, clearcoat, sheen, solid glass with a medium, thin glass, thin diffTrans, diffuse, copper)
+    yield "disney_heightfield", scenes.disney_heightfield(grid=48), scenes.heightfield_camera(64, 36), (64, 36), 16
+    yield "small_scene_attrs", inputs.small_scene(with_attrs=True), capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 48, 32), (48, 32), 12
+    # IBL + miss image.  The clearcoat lobe is switched off here: SampleDisneyClearcoat never writes sample.flags (SURVEY appendix B
+    # #4) and EvaluatePath's BsdfSample is an uninitialised local (PathTracer.cpp:197), so after a clearcoat sample the unmodified loop
+    # reads whatever the stack slot held -- with an IBL that garbage decides between EvaluateBackground and EvaluateBackgroundMiss
+    # (17 of 1200 pixels with this compiler).  The restatement, the oracle and the CUDA path define it as eScatterEvent.
+    ibl = _ibl_scene()
+    ibl.materials["scalars"][:, capi.CLEARCOAT] = 0.0
+    yield "ibl", ibl, capi.camera_init((0.0, 1.0, -5.0), (0.3, 0.0, 0.0), (0.0, 1.0, 0.0), 45.0, 40, 30), (40, 30), 10
+
+
+@pytest.mark.parametrize("case", list(_loop_cases()), ids=lambda c: c[0])
+def test_restated_loop_is_bit_identical_to_reference_pathtracer_cpp(oracle, ref, case):
+    """Level (d) pin: PathTracer.cpp's EvaluatePath / RayPick / OcclusionRay, SurfaceParameters.cpp's CalculateSurfaceParams and
+    Framebuffer.cpp's writers, compiled UNMODIFIED behind the Embree-API shim, against (1) the restated loop over reference objects
+    (ref_render_pathtracer: bit for bit, both film layers, same ray counts) and (2) the plain-C++ oracle (float accumulation noise)."""
+    name, data, cam, (w, h), depth = case
+    hb = ref.scene_create(data)
+    ha = oracle.scene_create(data)
+    for layers in (1, 2):
+        rs = capi.render_settings(w, h, 6, max_path_length=depth, rr_start=8, layers=layers, seed=21)
+        loop, sl = ref.render_reference_loop(hb, cam, rs, nthreads=1)  # one thread: see the note on sample.flags in _loop_cases
+        rest, sr = ref.render(hb, cam, rs, nthreads=3)
+        assert sl.closestRays == sr.closestRays and sl.occlusionRays == sr.occlusionRays and sl.pathSamples == sr.pathSamples == w * h * 6
+        for l in range(layers):
+            np.testing.assert_array_equal(loop[l].view(np.uint32), rest[l].view(np.uint32), err_msg=f"{name} layer {l}")
+        assert np.nanmean(loop[-1]) > 0
+        orc, so = oracle.render(ha, cam, rs, nthreads=4)
+        assert so.closestRays == sl.closestRays and so.occlusionRays == sl.occlusionRays
+        fin = np.isfinite(loop[-1]).all(axis=2)
+        assert np.array_equal(fin, np.isfinite(orc[-1]).all(axis=2)) and fin.mean() > 0.99
+        np.testing.assert_allclose(orc[-1][fin], loop[-1][fin], rtol=2e-5, atol=1e-6)
+    # sample-pass shards add up exactly (per-pixel sums are sequential in sample order on both sides)
+    rs_a = capi.render_settings(w, h, 3, max_path_length=depth, rr_start=8, layers=1, seed=21)
+    rs_b = capi.render_settings(w, h, 3, max_path_length=depth, rr_start=8, layers=1, seed=21, first_sample=3)
+    fa, _ = ref.render_reference_loop(hb, cam, rs_a, nthreads=2)
+    fb, _ = ref.render_reference_loop(hb, cam, rs_b, nthreads=2)
+    full, _ = ref.render_reference_loop(hb, cam, capi.render_settings(w, h, 6, max_path_length=depth, rr_start=8, layers=1, seed=21), nthreads=2)
+    fin = np.isfinite(full[0]).all(axis=2)
+    np.testing.assert_allclose((fa[0] + fb[0])[fin], full[0][fin], rtol=1e-5, atol=1e-6)
+    oracle.scene_destroy(ha)
+    ref.scene_destroy(hb)
+
+
+def test_reference_loop_rejects_what_pathtracer_cpp_cannot_do(ref):
+    from selas_b200 import scenes
+
+    hb = ref.scene_create(scenes.cornell_box())
+    cam = scenes.cornell_camera(8, 8)
+    for kw in (dict(rr_start=3), dict(mis_mode=1), dict(integrator=capi.INTEGRATOR_DEFERRED), dict(cmj=(4, 4))):
+        args = dict(max_path_length=12, rr_start=8, layers=1, seed=1)
+        args.update(kw)
+        with pytest.raises(RuntimeError):
+            ref.render_reference_loop(hb, cam, capi.render_settings(8, 8, 2, **args), nthreads=1)
+    ref.scene_destroy(hb)
+
+
+def test_surface_params_bit_exact_vs_reference_calculate_surface_params(oracle, ref):
+    """CalculateSurfaceParams (SurfaceParameters.cpp:144-247, unmodified; ModelDataFromRayIds through the reference's own scene /
+    subscene / model tables; rtcInterpolate0 through the shim) against the restatement, on hits of a scene whose meshes do and do
+    not carry normals / tangents (triangles and quads)."""
+    data = inputs.small_scene(with_attrs=True)
+    ha, hb = oracle.scene_create(data), ref.scene_create(data)
+    rays = inputs.scene_rays(31, 20000)
+    hits = oracle.intersect(ha, rays, mode=0)
+    assert (hits["geomID"] != capi.SELAS_INVALID_ID).mean() > 0.3
+    a = oracle.surface_params(ha, rays, hits)
+    b = ref.surface_params_reference(hb, rays, hits)
+    for f in a.dtype.names:
+        np.testing.assert_array_equal(a[f].view(np.uint32), b[f].view(np.uint32), err_msg=f)
+    oracle.scene_destroy(ha)
+    ref.scene_destroy(hb)
