@@ -8,8 +8,12 @@
  *     message (mirrors Error::Message(), Source/Core/SystemLib/Error.h:33).
  *   - handles are opaque; host pointers are borrowed for the call; device memory is owned by a handle.
  *   - plain "host" entry points copy host buffers to the GPU, run, copy back and synchronise;
- *     "_device" entry points take device pointers (the caller's CUDA stream, 0 = default) and do
- *     not synchronise.
+ *     "_device" entry points take device pointers and a CUDA stream and do not synchronise: they
+ *     only enqueue.  stream = NULL means the context's own stream (created non-blocking: it is NOT
+ *     ordered against the legacy default stream -- pass your stream, or synchronise with
+ *     selas_cuda_context_synchronize, when producers / consumers run elsewhere).  A render call that
+ *     is handed a stats pointer has to wait for the device to fill it; pass NULL and collect later
+ *     (selas_cuda_render_collect_stats) to stay asynchronous.
  *   - there is NO CPU fallback: if no CUDA device is usable every call fails with SELAS_ERR_CUDA.
  *   - vectors are row vectors, matrices row-major with translation in row 3
  *     (Source/Core/MathLib/FloatFuncs.cpp:383-396); tangent space is y-up
@@ -276,6 +280,8 @@ typedef struct SelasBvhStats {
     float    buildMs;
     float    sahCost;
     uint64_t deviceBytes;
+    uint32_t sahClusters;    /* binned-SAH build: Morton clusters under the SAH top tree (0 = radix tree, SELAS_BVH_BUILD=lbvh) */
+    uint32_t sahGenerations; /* sahSplitKernel launches of the build */
 } SelasBvhStats;
 
 /* ---- VCM (vertex connection and merging) ---------------------------------------------------------------------------
@@ -337,6 +343,8 @@ typedef struct SelasPtex     SelasPtex;
 /* rtcNewDevice / rtcReleaseDevice at Source/Applications/Selas/Source/main.cpp:99,:130 */
 int selas_cuda_context_create(int device, SelasContext** out);
 int selas_cuda_context_destroy(SelasContext* ctx);
+/* Waits for everything enqueued on the context's own stream (what _device calls use when their stream argument is NULL). */
+int selas_cuda_context_synchronize(SelasContext* ctx);
 const char* selas_cuda_last_error(const SelasContext* ctx); /* Error::Message(), SystemLib/Error.h:33; ctx may be NULL: thread-local message */
 int selas_cuda_device_count(void);      /* no reference counterpart: the CPU renderer has one device */
 const char* selas_cuda_version(void);
@@ -411,10 +419,16 @@ int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays,
 int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera,
                                  const SelasRenderSettings* settings, float* const* filmLayers,
                                  SelasRenderStats* stats);
-/* Device-resident variant: d_film = layerCount consecutive width*height*3 float planes, accumulated into. */
+/* Device-resident variant: d_film = layerCount consecutive width*height*3 float planes, accumulated into.
+ * With stats == NULL the call only enqueues (queue lengths and launch shapes of every bounce stay on the device) and returns while
+ * the GPU works; with stats != NULL it waits and fills them (= render, then selas_cuda_render_collect_stats). */
 int selas_cuda_render_pathtracer_device(SelasScene* scene, const SelasCamera* camera,
                                         const SelasRenderSettings* settings, float* d_film,
                                         SelasRenderStats* stats, void* stream);
+/* Waits for the scene's enqueued renders and returns what was measured since the last collect, summed over those calls: per-kernel
+ * device times (CUDA events recorded around every launch), ray totals (summed on the device), path samples, launches; renderMs spans
+ * from the first launch to the last.  The reference has no counterpart (its integrators print a wall-clock time, PathTracer.cpp:344). */
+int selas_cuda_render_collect_stats(SelasScene* scene, SelasRenderStats* stats);
 /* The path's only collective: ncclReduce(accum, accum, count, ncclFloat32, ncclSum, root, comm, stream) of the
  * per-GPU accumulation buffers after the last pass.  `ncclComm` is the caller's ncclComm_t (one process per GPU); NCCL is bound
  * at run time (dlopen of libnccl.so.2), so the library loads on hosts without it and this call then fails with

@@ -106,7 +106,7 @@ class VcmStats(C.Structure):
 
 class BvhStats(C.Structure):
     _fields_ = [("triangleCount", u32), ("nodeCount", u32), ("maxDepth", u32), ("reserved", u32), ("buildMs", f32),
-                ("sahCost", f32), ("deviceBytes", u64)]
+                ("sahCost", f32), ("deviceBytes", u64), ("sahClusters", u32), ("sahGenerations", u32)]
 
 
 # numpy views of the plain-data records
@@ -137,13 +137,13 @@ assert BSDF_SAMPLE_DTYPE.itemsize == 60 and LIGHT_SAMPLE_DTYPE.itemsize == 36 an
 assert MATERIAL_DTYPE.itemsize == 88 == C.sizeof(Material) and C.sizeof(Camera) == 104
 
 EXPORTS = [
-    "selas_cuda_context_create", "selas_cuda_context_destroy", "selas_cuda_last_error", "selas_cuda_device_count",
+    "selas_cuda_context_create", "selas_cuda_context_destroy", "selas_cuda_context_synchronize", "selas_cuda_last_error", "selas_cuda_device_count",
     "selas_cuda_version", "selas_cuda_scene_create", "selas_cuda_scene_destroy", "selas_cuda_scene_bvh_stats",
     "selas_cuda_intersect", "selas_cuda_occluded", "selas_cuda_intersect_device", "selas_cuda_occluded_device",
     "selas_cuda_intersect_counted", "selas_cuda_camera_init", "selas_cuda_camera_rays", "selas_cuda_cmj", "selas_cuda_bsdf_eval",
     "selas_cuda_bsdf_sample", "selas_cuda_light_sample", "selas_cuda_light_pdf", "selas_cuda_surface_params",
     "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample", "selas_cuda_texture_sample",
-    "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_film_scale_device",
+    "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_render_collect_stats", "selas_cuda_film_scale_device",
     "selas_cuda_reduce_film", "selas_cuda_render_vcm", "selas_cuda_render_vcm_device", "selas_cuda_vcm_light_pass", "selas_cuda_vcm_iteration_constants",
     "selas_cuda_hashgrid_build", "selas_cuda_hashgrid_destroy", "selas_cuda_hashgrid_read",
     "selas_cuda_hashgrid_query", "selas_cuda_hashgrid_build_device", "selas_cuda_hashgrid_query_device",
@@ -503,10 +503,17 @@ class Scene:
         self.ctx.check(self.lib.selas_cuda_render_pathtracer(self.handle, C.byref(camera), C.byref(settings), ptrs, C.byref(stats)))
         return film, stats
 
-    def render_device(self, camera: Camera, settings: RenderSettings, d_film_ptr: int, stream: int = 0):
+    def render_device(self, camera: Camera, settings: RenderSettings, d_film_ptr: int, stream: int = 0, want_stats: bool = True):
+        """want_stats=False: the call only enqueues and returns while the GPU works (collect_stats() later)."""
+        stats = RenderStats() if want_stats else None
+        self.ctx.check(self.lib.selas_cuda_render_pathtracer_device(self.handle, C.byref(camera), C.byref(settings), C.c_void_p(d_film_ptr),
+                                                                    C.byref(stats) if want_stats else None, C.c_void_p(stream)))
+        return stats
+
+    def collect_stats(self) -> RenderStats:
+        """Waits for the enqueued renders; per-kernel times, ray totals and samples since the last collect."""
         stats = RenderStats()
-        self.ctx.check(self.lib.selas_cuda_render_pathtracer_device(self.handle, C.byref(camera), C.byref(settings),
-                                                                    C.c_void_p(d_film_ptr), C.byref(stats), C.c_void_p(stream)))
+        self.ctx.check(self.lib.selas_cuda_render_collect_stats(self.handle, C.byref(stats)))
         return stats
 
     def render_vcm(self, camera: Camera, settings: VcmSettings):

@@ -152,6 +152,9 @@ int selas_cuda_context_destroy(SelasContext* ctx) {
         cudaStreamDestroy(ctx->stream);
     }
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_rayStage);
+    for (cudaStream_t st : ctx->stageStream)
+        if (st) cudaStreamDestroy(st);
     delete ctx;
     return SELAS_OK;
 }
@@ -359,12 +362,20 @@ static int checkRayCount(SelasContext* ctx, size_t n) {
     return SELAS_OK;
 }
 
+static uint32_t* nextRayCounter(SelasContext* ctx) { return ctx->d_counters + (ctx->counterNext++ & 255u); }
+
+int selas_cuda_context_synchronize(SelasContext* ctx) {
+    SELAS_TRY(bind(ctx));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
 int selas_cuda_intersect_device(SelasScene* scene, size_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_Ng4, void* stream) {
     if (!scene) return SELAS_ERR_ARGUMENT;
     SELAS_TRY(bind(scene->ctx));
     SELAS_TRY(checkRayCount(scene->ctx, n));
     cudaStream_t st = stream ? (cudaStream_t)stream : scene->ctx->stream;
-    return launchIntersect(scene, (uint32_t)n, d_rays, d_hits, d_Ng4, nullptr, scene->ctx->d_counters, st);
+    return launchIntersect(scene, (uint32_t)n, d_rays, d_hits, d_Ng4, nullptr, nextRayCounter(scene->ctx), st);
 }
 
 int selas_cuda_occluded_device(SelasScene* scene, size_t n, const SelasRay* d_rays, uint8_t* d_occluded, void* stream) {
@@ -372,8 +383,68 @@ int selas_cuda_occluded_device(SelasScene* scene, size_t n, const SelasRay* d_ra
     SELAS_TRY(bind(scene->ctx));
     SELAS_TRY(checkRayCount(scene->ctx, n));
     cudaStream_t st = stream ? (cudaStream_t)stream : scene->ctx->stream;
-    return launchOccluded(scene, (uint32_t)n, d_rays, d_occluded, nullptr, scene->ctx->d_counters + 1, st);
+    return launchOccluded(scene, (uint32_t)n, d_rays, d_occluded, nullptr, nextRayCounter(scene->ctx), st);
 }
+
+// Host-buffer ray casts (the seam a maintainer binds first: RayPick / OcclusionRay over arrays).  Round 1 paid a cudaMalloc + cudaFree
+// and one monolithic pageable copy each way per call (50 Mrays/s, below the CPU on incoherent rays).  Now: device staging kept in the
+// context, the batch cut into chunks that alternate between two streams (upload -> trace -> download per chunk), so downloads overlap the
+// next upload; with pinned caller buffers the call is PCIe-bound, with pageable ones it is bound by the driver's staging copies.
+namespace {
+constexpr size_t kStageChunk = 1u << 19;        // rays per chunk (16 MB up, 16 MB down)
+constexpr size_t kStageMaxRays = 1u << 23;      // staging capacity: 8 M rays (about 0.7 GB); larger batches go through it in rounds
+constexpr size_t kStageBytesPerRay = sizeof(SelasRay) + sizeof(SelasHit) + 4 * sizeof(float) + 16;
+
+int ensureRayStage(SelasContext* ctx, size_t rays) {
+    for (cudaStream_t& st : ctx->stageStream)
+        if (!st) SELAS_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (ctx->rayStageCapacity >= rays) return SELAS_OK;
+    cudaFree(ctx->d_rayStage);
+    ctx->d_rayStage = nullptr;
+    ctx->rayStageCapacity = 0;
+    cudaError_t e = cudaMalloc(&ctx->d_rayStage, rays * kStageBytesPerRay);
+    if (e != cudaSuccess) {
+        setError(ctx, "cudaMalloc(%zu bytes) failed for the ray staging buffers: %s", rays * kStageBytesPerRay, cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? SELAS_ERR_MEMORY : SELAS_ERR_CUDA;
+    }
+    ctx->rayStageCapacity = rays;
+    return SELAS_OK;
+}
+
+// any == false: hits (+ Ng4) out; any == true: occluded bytes out
+int castHostRays(SelasScene* scene, size_t n, const SelasRay* rays, SelasHit* hits, float* Ng4, uint8_t* occluded, bool any) {
+    SelasContext* ctx = scene->ctx;
+    const size_t cap = std::min(n, kStageMaxRays);
+    SELAS_TRY(ensureRayStage(ctx, cap));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // order after what the caller enqueued on the context's stream (scene build)
+    char* base = (char*)ctx->d_rayStage;
+    SelasRay* d_rays = (SelasRay*)base;
+    SelasHit* d_hits = (SelasHit*)(base + ctx->rayStageCapacity * sizeof(SelasRay));
+    float* d_ng = (float*)(base + ctx->rayStageCapacity * (sizeof(SelasRay) + sizeof(SelasHit)));
+    uint8_t* d_occ = (uint8_t*)(base + ctx->rayStageCapacity * (sizeof(SelasRay) + sizeof(SelasHit) + 4 * sizeof(float)));
+    for (size_t round = 0; round < n; round += cap) {
+        const size_t m = std::min(cap, n - round);
+        int k = 0;
+        for (size_t off = 0; off < m; off += kStageChunk, k ^= 1) {
+            const size_t c = std::min(kStageChunk, m - off);
+            cudaStream_t st = ctx->stageStream[k];
+            SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_rays + off, rays + round + off, c * sizeof(SelasRay), cudaMemcpyHostToDevice, st));
+            if (any) {
+                SELAS_TRY(launchOccluded(scene, (uint32_t)c, d_rays + off, d_occ + off, nullptr, nextRayCounter(ctx), st));
+                SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(occluded + round + off, d_occ + off, c, cudaMemcpyDeviceToHost, st));
+            } else {
+                SELAS_TRY(launchIntersect(scene, (uint32_t)c, d_rays + off, d_hits + off, Ng4 ? d_ng + 4 * off : nullptr, nullptr, nextRayCounter(ctx), st));
+                SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(hits + round + off, d_hits + off, c * sizeof(SelasHit), cudaMemcpyDeviceToHost, st));
+                if (Ng4) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(Ng4 + 4 * (round + off), d_ng + 4 * off, 4 * c * sizeof(float), cudaMemcpyDeviceToHost, st));
+            }
+        }
+        SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stageStream[0]));
+        SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stageStream[1]));
+    }
+    return SELAS_OK;
+}
+}  // namespace
 
 int selas_cuda_intersect(SelasScene* scene, size_t n, const SelasRay* rays, SelasHit* hits, float* Ng4) {
     if (!scene) return SELAS_ERR_ARGUMENT;
@@ -385,18 +456,7 @@ int selas_cuda_intersect(SelasScene* scene, size_t n, const SelasRay* rays, Sela
         setError(ctx, "selas_cuda_intersect: null rays/hits");
         return SELAS_ERR_ARGUMENT;
     }
-    Scratch s(ctx);
-    SelasRay* d_rays;
-    SelasHit* d_hits;
-    float* d_ng = nullptr;
-    SELAS_TRY(s.upload(&d_rays, rays, n));
-    SELAS_TRY(s.alloc(&d_hits, n));
-    if (Ng4) SELAS_TRY(s.alloc(&d_ng, 4 * n));
-    SELAS_TRY(launchIntersect(scene, (uint32_t)n, d_rays, d_hits, d_ng, nullptr, ctx->d_counters, ctx->stream));
-    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(SelasHit), cudaMemcpyDeviceToHost, ctx->stream));
-    if (Ng4) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(Ng4, d_ng, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    return SELAS_OK;
+    return castHostRays(scene, n, rays, hits, Ng4, nullptr, false);
 }
 
 int selas_cuda_occluded(SelasScene* scene, size_t n, const SelasRay* rays, uint8_t* occluded) {
@@ -409,15 +469,7 @@ int selas_cuda_occluded(SelasScene* scene, size_t n, const SelasRay* rays, uint8
         setError(ctx, "selas_cuda_occluded: null rays/occluded");
         return SELAS_ERR_ARGUMENT;
     }
-    Scratch s(ctx);
-    SelasRay* d_rays;
-    uint8_t* d_occ;
-    SELAS_TRY(s.upload(&d_rays, rays, n));
-    SELAS_TRY(s.alloc(&d_occ, n));
-    SELAS_TRY(launchOccluded(scene, (uint32_t)n, d_rays, d_occ, nullptr, ctx->d_counters + 1, ctx->stream));
-    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(occluded, d_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
-    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    return SELAS_OK;
+    return castHostRays(scene, n, rays, nullptr, nullptr, occluded, true);
 }
 
 int selas_cuda_intersect_counted(SelasScene* scene, size_t n, const SelasRay* rays, SelasHit* hits, uint32_t* counts, int anyHit) {
@@ -441,7 +493,7 @@ int selas_cuda_intersect_counted(SelasScene* scene, size_t n, const SelasRay* ra
     SELAS_TRY(s.alloc(&d_counts, 2 * n));
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, 2 * n * sizeof(uint32_t), ctx->stream));
     if (anyHit) {
-        SELAS_TRY(launchOccluded(scene, (uint32_t)n, d_rays, d_occ, d_counts, ctx->d_counters + 1, ctx->stream));
+        SELAS_TRY(launchOccluded(scene, (uint32_t)n, d_rays, d_occ, d_counts, nextRayCounter(ctx), ctx->stream));
         if (hits) {  // any-hit mode reports only geomID != INVALID for occluded rays
             std::vector<uint8_t> occ(n);
             SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(occ.data(), d_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -453,7 +505,7 @@ int selas_cuda_intersect_counted(SelasScene* scene, size_t n, const SelasRay* ra
             }
         }
     } else {
-        SELAS_TRY(launchIntersect(scene, (uint32_t)n, d_rays, d_hits, nullptr, d_counts, ctx->d_counters, ctx->stream));
+        SELAS_TRY(launchIntersect(scene, (uint32_t)n, d_rays, d_hits, nullptr, d_counts, nextRayCounter(ctx), ctx->stream));
         if (hits) SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(hits, d_hits, n * sizeof(SelasHit), cudaMemcpyDeviceToHost, ctx->stream));
     }
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(counts, d_counts, 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -763,6 +815,12 @@ int selas_cuda_render_pathtracer_device(SelasScene* scene, const SelasCamera* ca
     return renderPathTracer(scene, *camera, *settings, d_film, stats, stream ? (cudaStream_t)stream : ctx->stream);
 }
 
+int selas_cuda_render_collect_stats(SelasScene* scene, SelasRenderStats* stats) {
+    if (!scene) return SELAS_ERR_ARGUMENT;
+    SELAS_TRY(bind(scene->ctx));
+    return collectRenderStats(scene, stats);
+}
+
 int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera, const SelasRenderSettings* settings,
                                  float* const* filmLayers, SelasRenderStats* stats) {
     if (!scene) return SELAS_ERR_ARGUMENT;
@@ -786,10 +844,12 @@ int selas_cuda_render_pathtracer(SelasScene* scene, const SelasCamera* camera, c
     }
     float* d_film = scene->d_filmCache;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_film, 0, plane * settings->layerCount * sizeof(float), ctx->stream));
-    SELAS_TRY(renderPathTracer(scene, *camera, *settings, d_film, stats, ctx->stream));
+    // everything is enqueued before the one wait: render, the film copies, and (when asked for) the stats readback
+    SELAS_TRY(renderPathTracer(scene, *camera, *settings, d_film, nullptr, ctx->stream));
     for (uint32_t l = 0; l < settings->layerCount; ++l)
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(filmLayers[l], d_film + plane * l, plane * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) SELAS_TRY(collectRenderStats(scene, stats));
+    else SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return SELAS_OK;
 }
 

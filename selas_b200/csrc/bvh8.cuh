@@ -32,6 +32,9 @@ struct Bvh8 {
     // two-level form: the top-level tree's leaves are instance references (triangle records whose a.w is the flat instance index) and
     // every mesh has its own object-space tree elsewhere in the same arrays (internal.h: InstanceTrace); null for the flattened form
     const InstanceTrace* instances;
+    // the first topCount nodes (whole levels of the tree, breadth first: the collapse numbers nodes level by level) are staged in
+    // shared memory by every CTA of the trace kernels; 0 = none
+    uint32_t topCount;
 };
 
 #ifndef SELAS_STACK_SIZE

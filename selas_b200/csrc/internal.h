@@ -88,7 +88,15 @@ struct SelasContext {
     cudaStream_t stream = nullptr;
     int smCount = 0;
     std::string lastError;
-    uint32_t* d_counters = nullptr;  // scratch counters (256 x u32)
+    // Ray-fetch counters of the persistent trace kernels: a ring of 256 words; every launch takes the next one and zeroes it on its own
+    // stream, so launches in flight on different streams (or scenes) never share a counter.
+    uint32_t* d_counters = nullptr;
+    uint32_t counterNext = 0;
+    // Staging of the host-buffer ray-cast entry points (selas_cuda_intersect / _occluded), kept between calls: no allocation per call,
+    // two streams so that a chunk's download overlaps the next chunk's upload and trace.
+    void* d_rayStage = nullptr;      // rays | hits | Ng | occluded for up to rayStageCapacity rays
+    size_t rayStageCapacity = 0;
+    cudaStream_t stageStream[2] = {nullptr, nullptr};
 };
 
 struct SelasScene {
@@ -97,6 +105,7 @@ struct SelasScene {
     std::vector<void*> allocations;  // everything cudaMalloc'ed for this scene
     SelasBvhStats stats{};
     bool usesPtex = false;  // any mesh carries a Ptex texture: selects the shade kernel built with the lookup
+    uint32_t topNodeCount = 0;  // leading BVH8 nodes (whole levels) the trace kernels stage in shared memory
     // wavefront scratch, grown on demand
     void* wf = nullptr;
     void* vcm = nullptr;  // VCM scratch (vcm.cu), grown on demand
@@ -147,6 +156,7 @@ int launchCameraRays(SelasContext* ctx, const SelasCamera& cam, size_t n, const 
 int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, const SelasHit* d_hits, SelasSurface* d_out);
 int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
                      cudaStream_t stream);
+int collectRenderStats(SelasScene* scene, SelasRenderStats* out);
 int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream);
 int launchIblLookup(SelasScene* scene, size_t n, const float* d_wi3, float* d_rgb3, float* d_pdf, float* d_miss3);
 int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp3, uint32_t* d_xy2);

@@ -302,16 +302,23 @@ struct WavefrontBuffers {
     float* ptexRgb = nullptr;      // Ptex stage output, 3 floats per path (scenes with Ptex materials only)
     uint32_t* order = nullptr;     // material-sorted visiting order of the hit queue
     uint32_t* bins = nullptr;      // per iteration: 64 counts + 64 cursors
-    uint32_t* counters = nullptr;  // 4 per iteration: nextPaths, shadowRays, closestFetch, shadowFetch
+    // 4 per iteration: [queue length of this iteration, shadow rays made by the previous one, closest-hit fetch counter, shadow fetch counter]
+    uint32_t* counters = nullptr;
     uint32_t counterSlots = 0;
     uint32_t shadowPerPath = 1;    // shadow-ray slots per queued path (2 for the deferred integrator: area light + sky)
-    uint32_t* h_counts = nullptr;  // pinned readback
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evCounts = nullptr;
+    bool hasPtex = false;
+    // totals since the last collect: closest rays, occlusion rays, then the counting build's nodes / triangles (closest, shadow)
+    unsigned long long* totals = nullptr;
+    unsigned long long* h_totals = nullptr;  // pinned readback
+    uint32_t* h_counts = nullptr;            // pinned readback of one queue length (long paths: periodic early-out check)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool spanOpen = false;         // ev0 recorded at the first launch since the last collect
+    uint64_t pendingSamples = 0, pendingLaunches = 0;
+    cudaStream_t lastStream = nullptr;
     KernelTimers timers;  // event pool reused across calls
 };
 
-void freeWavefront(SelasScene* scene) {
-    WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
+static void destroyWavefront(WavefrontBuffers* w) {
     if (!w) return;
     for (int k = 0; k < 2; ++k) {
         cudaFree(w->rays[k]);
@@ -326,51 +333,86 @@ void freeWavefront(SelasScene* scene) {
     cudaFree(w->order);
     cudaFree(w->ptexRgb);
     cudaFree(w->bins);
+    cudaFree(w->totals);
+    if (w->h_totals) cudaFreeHost(w->h_totals);
     if (w->h_counts) cudaFreeHost(w->h_counts);
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
-    if (w->evCounts) cudaEventDestroy(w->evCounts);
     delete w;
+}
+
+void freeWavefront(SelasScene* scene) {
+    destroyWavefront((WavefrontBuffers*)scene->wf);
     scene->wf = nullptr;
 }
 
-static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterations, uint32_t shadowPerPath) {
+// The buffer set is built aside and published to the scene only when every allocation succeeded: a failed cudaMalloc (8 M paths in
+// flight is 1.2 GB) must not leave a half-null set behind that the next call would take for "already large enough".
+static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterations, uint32_t shadowPerPath, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
-    WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
-    uint32_t slots = (iterations + 2) * 4;
-    if (w && w->capacity >= capacity && w->counterSlots >= slots && w->shadowPerPath >= shadowPerPath) return SELAS_OK;
-    if (w) freeWavefront(scene);
-    w = new WavefrontBuffers();
-    scene->wf = w;
-    w->capacity = capacity;
-    w->counterSlots = slots;
-    w->shadowPerPath = shadowPerPath;
-    for (int k = 0; k < 2; ++k) {
-        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->rays[k], sizeof(SelasRay) * (size_t)capacity));
-        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->thrPix[k], sizeof(float4) * (size_t)capacity));
-        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->rngFlags[k], sizeof(uint2) * (size_t)capacity));
-        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->medium[k], sizeof(float4) * (size_t)capacity));
+    WavefrontBuffers* old = (WavefrontBuffers*)scene->wf;
+    const uint32_t slots = (iterations + 2) * 4;
+    if (old && old->capacity >= capacity && old->counterSlots >= slots && old->shadowPerPath >= shadowPerPath && old->hasPtex == scene->usesPtex)
+        return SELAS_OK;
+    if (old) {  // work of earlier calls may still be running on the old buffers
+        if (old->lastStream) cudaStreamSynchronize(old->lastStream);
+        capacity = std::max(capacity, old->capacity);
+        shadowPerPath = std::max(shadowPerPath, old->shadowPerPath);
     }
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->hits, sizeof(SelasHit) * (size_t)capacity));
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowRays, sizeof(SelasRay) * (size_t)capacity * shadowPerPath));
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity * shadowPerPath));
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->counters, sizeof(uint32_t) * slots));
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->order, sizeof(uint32_t) * (size_t)capacity));
-    if (scene->usesPtex) SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->ptexRgb, sizeof(float) * 3 * (size_t)capacity));
-    SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&w->bins, sizeof(uint32_t) * 2 * kBinCount * (size_t)(iterations + 2)));
-    SELAS_CUDA_CHECK(ctx, cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4));
-    SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev0));
-    SELAS_CUDA_CHECK(ctx, cudaEventCreate(&w->ev1));
-    SELAS_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&w->evCounts, cudaEventDisableTiming));
+    WavefrontBuffers* w = new (std::nothrow) WavefrontBuffers();
+    if (!w) return SELAS_ERR_MEMORY;
+    w->capacity = capacity;
+    w->counterSlots = std::max(slots, old ? old->counterSlots : 0u);
+    w->shadowPerPath = shadowPerPath;
+    w->hasPtex = scene->usesPtex;
+    const uint32_t binSets = w->counterSlots / 4;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    };
+    for (int k = 0; k < 2; ++k) {
+        alloc((void**)&w->rays[k], sizeof(SelasRay) * (size_t)capacity);
+        alloc((void**)&w->thrPix[k], sizeof(float4) * (size_t)capacity);
+        alloc((void**)&w->rngFlags[k], sizeof(uint2) * (size_t)capacity);
+        alloc((void**)&w->medium[k], sizeof(float4) * (size_t)capacity);
+    }
+    alloc((void**)&w->hits, sizeof(SelasHit) * (size_t)capacity);
+    alloc((void**)&w->shadowRays, sizeof(SelasRay) * (size_t)capacity * shadowPerPath);
+    alloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity * shadowPerPath);
+    alloc((void**)&w->counters, sizeof(uint32_t) * w->counterSlots);
+    alloc((void**)&w->order, sizeof(uint32_t) * (size_t)capacity);
+    if (scene->usesPtex) alloc((void**)&w->ptexRgb, sizeof(float) * 3 * (size_t)capacity);
+    alloc((void**)&w->bins, sizeof(uint32_t) * 2 * kBinCount * (size_t)binSets);
+    alloc((void**)&w->totals, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_totals, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(w->totals, 0, sizeof(unsigned long long) * 8, stream);
+    if (e != cudaSuccess) {
+        setError(ctx, "wavefront buffers for %u paths in flight: %s", capacity, cudaGetErrorString(e));
+        destroyWavefront(w);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? SELAS_ERR_MEMORY : SELAS_ERR_CUDA;
+    }
+    if (old) {  // keep what has not been collected yet
+        w->pendingSamples = old->pendingSamples;
+        w->pendingLaunches = old->pendingLaunches;
+        if (old->totals) cudaMemcpyAsync(w->totals, old->totals, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToDevice, stream);
+        cudaStreamSynchronize(stream);
+        destroyWavefront(old);
+    }
+    scene->wf = w;
     return SELAS_OK;
 }
 
 // JitteredCameraRay (Camera.cpp:63-74) for path ids [first, first+count): pixel = id % pixels, sample = id / pixels.
 __global__ void generateKernel(SelasCamera cam, uint32_t width, uint32_t height, uint32_t seed, uint32_t firstSample, uint64_t firstPath,
                                uint32_t count, uint32_t activePixels, uint32_t pixelStride, uint32_t pixelSampler, SelasRay* __restrict__ rays,
-                               float4* __restrict__ thrPix, uint2* __restrict__ rngFlags) {
+                               float4* __restrict__ thrPix, uint2* __restrict__ rngFlags, uint32_t* __restrict__ queueLength) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
+    if (i == 0) *queueLength = count;  // every later launch of the pass reads its queue length from device memory
     uint64_t id = firstPath + i;
     uint32_t pixel = (uint32_t)(id % activePixels) * pixelStride, sample = firstSample + (uint32_t)(id / activePixels);
     uint32_t y = pixel / width, x = pixel - y * width;
@@ -406,8 +448,10 @@ SELAS_D uint32_t binOf(const SceneGpu& sc, const SelasHit* hits, uint32_t i) {
     return m < kBinCount - 1 ? m : kBinCount - 2;
 }
 
-__global__ void __launch_bounds__(256) binCountKernel(SceneGpu sc, uint32_t n, const SelasHit* __restrict__ hits, uint32_t* __restrict__ bins) {
+__global__ void __launch_bounds__(256) binCountKernel(SceneGpu sc, uint32_t n, const uint32_t* __restrict__ nPtr, const SelasHit* __restrict__ hits,
+                                                      uint32_t* __restrict__ bins) {
     __shared__ uint32_t local[kBinCount];
+    if (nPtr) n = min(n, *nPtr);
     if (threadIdx.x < kBinCount) local[threadIdx.x] = 0;
     __syncthreads();
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&local[binOf(sc, hits, i)], 1u);
@@ -429,8 +473,9 @@ __global__ void binScanKernel(const uint32_t* __restrict__ bins, uint32_t* __res
     cursor[lane + 32] = totalA + xb - b;
 }
 
-__global__ void __launch_bounds__(256) binScatterKernel(SceneGpu sc, uint32_t n, const SelasHit* __restrict__ hits, uint32_t* __restrict__ cursor,
-                                                        uint32_t* __restrict__ order) {
+__global__ void __launch_bounds__(256) binScatterKernel(SceneGpu sc, uint32_t n, const uint32_t* __restrict__ nPtr, const SelasHit* __restrict__ hits,
+                                                        uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    if (nPtr) n = min(n, *nPtr);
     // per-CTA: local histogram -> one global atomic per bin reserves a contiguous range -> ranks inside the CTA
     __shared__ uint32_t local[kBinCount];
     __shared__ uint32_t base[kBinCount];
@@ -465,9 +510,9 @@ __global__ void __launch_bounds__(256) binScatterKernel(SceneGpu sc, uint32_t n,
 int launchMaterialOrder(SelasScene* scene, uint32_t n, const SelasHit* d_hits, uint32_t* d_bins, uint32_t* d_order, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
     int grid = (int)std::min<uint32_t>(divUp(n, 2048), (uint32_t)ctx->smCount * 8);
-    binCountKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, d_hits, d_bins);
+    binCountKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, nullptr, d_hits, d_bins);
     binScanKernel<<<1, 32, 0, stream>>>(d_bins, d_bins + kBinCount);
-    binScatterKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, d_hits, d_bins + kBinCount, d_order);
+    binScatterKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, nullptr, d_hits, d_bins + kBinCount, d_order);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -490,9 +535,12 @@ __global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGp
                                                    float4* __restrict__ thrPixOut, uint2* __restrict__ rngFlagsOut,
                                                    float4* __restrict__ mediumOut, SelasRay* __restrict__ shadowRays,
                                                    float4* __restrict__ shadowPayload, uint32_t* __restrict__ counters,
-                                                   float* __restrict__ film, const float* __restrict__ ptexRgb) {
-    const uint32_t n = nMax;
-    const uint32_t slotIndex = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   float* __restrict__ film, const float* __restrict__ ptexRgb, const uint32_t* __restrict__ nPtr) {
+    // The queue length lives in device memory (nPtr; nMax is the launch's upper bound), so the host never waits for it: the grid is
+    // persistent and walks the queue with a CTA-uniform stride.
+    const uint32_t n = nPtr ? min(nMax, *nPtr) : nMax;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const uint32_t slotIndex = base + threadIdx.x;
     // material-sorted visiting order (binScatterKernel): lanes of a warp share a material, hence code path
     const uint32_t i = (order && slotIndex < n) ? __ldg(order + slotIndex) : slotIndex;
     const uint32_t lane = threadIdx.x & 31u;
@@ -724,8 +772,58 @@ __global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGp
             shadowPayload[slot] = shPayload2;
         }
     }
+  }
 }
 
+// Ray totals of one pass, summed on the device so that nothing has to be read back per bounce: closest-hit rays = sum of the queue lengths,
+// occlusion rays = sum of the shadow-queue lengths (counter layout: see renderPathTracer).
+__global__ void passTotalsKernel(const uint32_t* __restrict__ counters, uint32_t iterations, unsigned long long* __restrict__ totals) {
+    unsigned long long closest = 0, shadow = 0;
+    for (uint32_t it = threadIdx.x; it < iterations; it += 32) {
+        closest += counters[4 * it];
+        shadow += counters[4 * (it + 1) + 1];
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        closest += __shfl_xor_sync(0xffffffffu, closest, s);
+        shadow += __shfl_xor_sync(0xffffffffu, shadow, s);
+    }
+    if (threadIdx.x == 0) {
+        totals[0] += closest;
+        totals[1] += shadow;
+    }
+}
+
+// Sync with the render stream and hand out everything measured since the last collect: per-kernel event spans, ray totals summed on the
+// device, path samples.  (selas_cuda_render_collect_stats; also the tail of a render call that was given a stats pointer.)
+int collectRenderStats(SelasScene* scene, SelasRenderStats* out) {
+    SelasContext* ctx = scene->ctx;
+    SelasRenderStats st{};
+    WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
+    if (w) {
+        cudaStream_t stream = w->lastStream ? w->lastStream : ctx->stream;
+        if (w->spanOpen) cudaEventRecord(w->ev1, stream);
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_totals, w->totals, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, stream));
+        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->totals, 0, sizeof(unsigned long long) * 8, stream));
+        SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
+        if (w->spanOpen) cudaEventElapsedTime(&st.renderMs, w->ev0, w->ev1);
+        w->spanOpen = false;
+        w->timers.collect(st);
+        st.closestRays = w->h_totals[0];
+        st.occlusionRays = w->h_totals[1];
+        st.closestNodes = w->h_totals[2]; st.closestTris = w->h_totals[3]; st.shadowNodes = w->h_totals[4]; st.shadowTris = w->h_totals[5];
+        st.pathSamples = w->pendingSamples;
+        st.kernelLaunches = w->pendingLaunches;
+        w->pendingSamples = 0;
+        w->pendingLaunches = 0;
+    }
+    if (out) *out = st;
+    return SELAS_OK;
+}
+
+// Enqueues the whole render on `stream` and returns without waiting for the device: queue lengths, ray totals and the launch shapes of
+// every bounce stay on the device (persistent / grid-stride kernels that read their queue length from memory).  stats != null: the
+// call then collects (and so waits); stats == null: nothing is waited for -- selas_cuda_render_collect_stats picks the numbers up later.
+// Paths longer than 32 bounces (the reference's MaxBounceCount_ is 2048) look at the queue length every 16 bounces to stop early.
 int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRenderSettings& rs, float* d_film, SelasRenderStats* stats,
                      cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
@@ -756,109 +854,125 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     // paths in flight per pass: whole sample passes, about 8M
     uint32_t sppPerPass = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(rs.samplesPerPixel, (8u << 20) / std::max(1u, activePixels)));
     const uint32_t capacity = (uint32_t)std::min<uint64_t>(totalPaths, (uint64_t)activePixels * sppPerPass);
-    SelasRenderStats st{};
     if (capacity == 0 || rs.maxPathLength == 0) {
-        st.pathSamples = totalPaths;
-        if (stats) *stats = st;
+        if (stats) {
+            *stats = SelasRenderStats{};
+            stats->pathSamples = totalPaths;
+        }
         return SELAS_OK;
     }
     const bool deferred = rs.integrator == SELAS_INTEGRATOR_DEFERRED;
-    int rc = ensureWavefront(scene, capacity, rs.maxPathLength, deferred ? 2u : 1u);
+    // counter slots: a long path length only needs as many as are enqueued between two early-out checks
+    const uint32_t kCheckEvery = 16;
+    const bool longPaths = rs.maxPathLength > 32;
+    int rc = ensureWavefront(scene, capacity, longPaths ? kCheckEvery + 1 : rs.maxPathLength, deferred ? 2u : 1u, stream);
     if (rc) return rc;
     WavefrontBuffers* w = (WavefrontBuffers*)scene->wf;
+    if (w->lastStream && w->lastStream != stream) cudaStreamSynchronize(w->lastStream);  // one queue set: calls on another stream wait for the last
+    w->lastStream = stream;
     ShadeParams prm{rs.maxPathLength, rs.rrStartBounce, rs.layerCount, pixels, rs.misMode, (rs.flags & SELAS_RENDER_SKIP_NONFINITE) ? 1u : 0u};
     const bool counting = (rs.flags & SELAS_RENDER_COUNT_TRAVERSAL) != 0;
-    unsigned long long* d_totals = nullptr;
-    if (counting) {
-        SELAS_CUDA_CHECK(ctx, cudaMalloc((void**)&d_totals, 4 * sizeof(unsigned long long)));
-        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_totals, 0, 4 * sizeof(unsigned long long), stream));
-    }
+    unsigned long long* d_totals = counting ? w->totals + 2 : nullptr;
     KernelTimers& timers = w->timers;
     // tuning knob: first bounce whose hit queue is sorted by material before shading (SELAS_SORT_FROM_BOUNCE, default 0)
     static const uint32_t sortFromBounce = getenv("SELAS_SORT_FROM_BOUNCE") ? (uint32_t)atoi(getenv("SELAS_SORT_FROM_BOUNCE")) : 0u;
+    // persistent shade grid: what is resident, twice over (the queue is walked with a grid-wide stride, so every CTA sees every material)
+    static int shadeResident[2] = {0, 0};
+    if (!shadeResident[deferred ? 1 : 0]) {
+        int r = 0;
+        cudaError_t e = deferred ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, shadeKernel<1>, 128, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, shadeKernel<0>, 128, 0);
+        shadeResident[deferred ? 1 : 0] = (e == cudaSuccess && r > 0) ? r : 4;
+    }
+    static const int shadeWaves = getenv("SELAS_SHADE_WAVES") ? std::max(1, atoi(getenv("SELAS_SHADE_WAVES"))) : 2;
 
-    cudaEventRecord(w->ev0, stream);
+    if (!w->spanOpen) {
+        cudaEventRecord(w->ev0, stream);
+        w->spanOpen = true;
+    }
+    uint64_t launches = 0;
     for (uint64_t first = 0; first < totalPaths; first += capacity) {
-        uint32_t count = (uint32_t)std::min<uint64_t>(capacity, totalPaths - first);
+        const uint32_t count = (uint32_t)std::min<uint64_t>(capacity, totalPaths - first);
+        const uint32_t slotSets = w->counterSlots / 4;
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
-        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->bins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)(rs.maxPathLength + 2), stream));
+        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->bins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)slotSets, stream));
         size_t t0 = timers.begin(stream);
         generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, activePixels,
-                                                              stride, rs.pixelSampler, w->rays[0], w->thrPix[0], w->rngFlags[0]);
+                                                              stride, rs.pixelSampler, w->rays[0], w->thrPix[0], w->rngFlags[0], w->counters);
         timers.end(0, t0, stream);
-        ++st.kernelLaunches;
-        uint32_t n = count;
+        ++launches;
+        const int sortGrid = (int)std::min<uint32_t>(divUp(count, 2048), (uint32_t)ctx->smCount * 8);
+        const int shadeGrid = (int)std::min<uint32_t>(divUp(count, 128), (uint32_t)(ctx->smCount * shadeResident[deferred ? 1 : 0] * shadeWaves));
+        const unsigned ptexGrid = (unsigned)std::min<uint32_t>(divUp(count, 1024), (uint32_t)ctx->smCount * 8);
         int cur = 0;
-        for (uint32_t it = 0; it < rs.maxPathLength && n > 0; ++it) {
-            uint32_t* ctr = w->counters + 4 * (size_t)it;
+        uint32_t slot = 0;  // counter set of the current bounce
+        for (uint32_t it = 0; it < rs.maxPathLength; ++it, ++slot) {
+            if (longPaths && slot == kCheckEvery) {
+                // the sets in use are exhausted: fold them into the totals, look at the queue length, and start over at set 0
+                passTotalsKernel<<<1, 32, 0, stream>>>(w->counters, slot, w->totals);
+                SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, w->counters + 4 * (size_t)slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+                SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
+                const uint32_t alive = w->h_counts[0];
+                if (alive == 0) { slot = 0; break; }
+                SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
+                SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->counters, w->h_counts, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+                SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->bins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)slotSets, stream));
+                slot = 0;
+                ++launches;
+            }
+            uint32_t* ctr = w->counters + 4 * (size_t)slot;       // [0] = this bounce's queue length
+            uint32_t* next = ctr + 4;                              // [0] = next queue length, [1] = shadow rays of this bounce
             // closest hit over the dense path queue
             t0 = timers.begin(stream);
-            rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, d_totals, stream);
+            rc = launchIntersectIndirect(scene, ctr, count, w->rays[cur], w->hits, ctr + 2, d_totals, stream);
             if (rc) return rc;
             timers.end(1, t0, stream);
-            st.closestRays += n;
             t0 = timers.begin(stream);
             const uint32_t* order = nullptr;
-            if (it >= sortFromBounce && n >= 4096) {
-                uint32_t* bins = w->bins + 2 * kBinCount * (size_t)it;
-                int grid = (int)std::min<uint32_t>(divUp(n, 2048), (uint32_t)ctx->smCount * 8);
-                binCountKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, w->hits, bins);
+            if (it >= sortFromBounce) {
+                uint32_t* bins = w->bins + 2 * kBinCount * (size_t)slot;
+                binCountKernel<<<sortGrid, 256, 0, stream>>>(scene->gpu, count, ctr, w->hits, bins);
                 binScanKernel<<<1, 32, 0, stream>>>(bins, bins + kBinCount);
-                binScatterKernel<<<grid, 256, 0, stream>>>(scene->gpu, n, w->hits, bins + kBinCount, w->order);
+                binScatterKernel<<<sortGrid, 256, 0, stream>>>(scene->gpu, count, ctr, w->hits, bins + kBinCount, w->order);
                 order = w->order;
-                st.kernelLaunches += 3;
+                launches += 3;
             }
             if (scene->usesPtex) {  // Ptex stage: base-colour lookups for the whole hit queue
-                unsigned grid = (unsigned)std::min<uint32_t>(divUp(n, 1024), (uint32_t)ctx->smCount * 8);
-                ptexStageKernel<<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
-                ++st.kernelLaunches;
+                ptexStageKernel<<<ptexGrid, 128, 0, stream>>>(scene->gpu, count, w->hits, w->ptexRgb, ctr);
+                ++launches;
             }
             if (deferred)
-                shadeKernel<1><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
-                                                                   w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
-                                                                   w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film,
-                                                                   scene->usesPtex ? w->ptexRgb : nullptr);
+                shadeKernel<1><<<shadeGrid, 128, 0, stream>>>(scene->gpu, prm, order, count, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
+                                                              w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
+                                                              w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, next, d_film,
+                                                              scene->usesPtex ? w->ptexRgb : nullptr, ctr);
             else
-                shadeKernel<0><<<divUp(n, 128), 128, 0, stream>>>(scene->gpu, prm, order, n, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
-                                                                   w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
-                                                                   w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, ctr, d_film,
-                                                                   scene->usesPtex ? w->ptexRgb : nullptr);
+                shadeKernel<0><<<shadeGrid, 128, 0, stream>>>(scene->gpu, prm, order, count, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
+                                                              w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
+                                                              w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, next, d_film,
+                                                              scene->usesPtex ? w->ptexRgb : nullptr, ctr);
             timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
-            // The queue lengths go back to the host for the next bounce's launch shapes, but the shadow launch does not wait for them:
-            // the persistent any-hit kernel reads its ray count from device memory, and is enqueued before the host blocks, so the GPU
-            // traces shadow rays while the host wakes up and enqueues the next bounce (no idle gap between bounces).
-            SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, ctr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            SELAS_CUDA_CHECK(ctx, cudaEventRecord(w->evCounts, stream));
-            st.kernelLaunches += 2;
             {
                 float* filmRadiance = d_film + (rs.layerCount == 2 ? 3 * (size_t)pixels : 0);
                 t0 = timers.begin(stream);
-                rc = launchShadowAccumulate(scene, ctr + 1, n * w->shadowPerPath, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
+                rc = launchShadowAccumulate(scene, next + 1, count * w->shadowPerPath, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
                                             d_totals ? d_totals + 2 : nullptr, stream);
                 if (rc) return rc;
                 timers.end(3, t0, stream);
-                ++st.kernelLaunches;
             }
-            SELAS_CUDA_CHECK(ctx, cudaEventSynchronize(w->evCounts));
-            uint32_t nNext = w->h_counts[0], nShadow = w->h_counts[1];
-            st.occlusionRays += nShadow;
-            n = nNext;
+            launches += 3;
             cur ^= 1;
         }
+        if (slot) {
+            passTotalsKernel<<<1, 32, 0, stream>>>(w->counters, slot, w->totals);
+            ++launches;
+        }
     }
-    cudaEventRecord(w->ev1, stream);
-    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
-    cudaEventElapsedTime(&st.renderMs, w->ev0, w->ev1);
-    timers.collect(st);
-    if (counting) {
-        unsigned long long h[4];
-        SELAS_CUDA_CHECK(ctx, cudaMemcpy(h, d_totals, sizeof(h), cudaMemcpyDeviceToHost));
-        cudaFree(d_totals);
-        st.closestNodes = h[0]; st.closestTris = h[1]; st.shadowNodes = h[2]; st.shadowTris = h[3];
-    }
-    st.pathSamples = totalPaths;
-    if (stats) *stats = st;
+    w->pendingSamples += totalPaths;
+    w->pendingLaunches += launches;
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    if (stats) return collectRenderStats(scene, stats);
     return SELAS_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "bvh_build.cuh"
+#include "bvh_sah.cuh"
 #include "internal.h"
 #include "trace.cuh"
 
@@ -42,9 +43,147 @@ struct TreeOut {
     float4* nodes = nullptr;
     float4* tris = nullptr;
     uint32_t nodeCount = 0, triCount = 0, levels = 0;
+    std::vector<uint32_t> levelEnds;  // node count after each level: nodes [0, levelEnds[L]) are levels 0..L (breadth-first numbering)
 };
 
-static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* d_bounds, uint32_t n, TreeOut& out) {
+// ---- binned-SAH tree over the Morton clusters (bvh_sah.cuh) -------------------------------------------------------------------
+// Runs generations of sahSplitKernel until no segment is left.  items[0] holds the segments of generation 0; the buffers alternate.
+static int runSahGenerations(SelasContext* ctx, cudaStream_t st, SahItem* items[2], SahSeg* segs[2], uint32_t segCount, uint32_t* d_genCounts /* 256, zeroed */,
+                             const SahTree& tree, uint32_t* generations) {
+    uint32_t gen = 0;
+    while (segCount > 0) {
+        if (gen >= 255) {
+            setError(ctx, "SAH build exceeded 255 generations");
+            return SELAS_ERR_UNSUPPORTED;
+        }
+        sahSplitKernel<<<divUp(segCount, kSahWarpsPerCta), kSahWarpsPerCta * 32, 0, st>>>(items[gen & 1], items[(gen + 1) & 1], segs[gen & 1], segCount,
+                                                                                          segs[(gen + 1) & 1], d_genCounts + gen + 1, tree);
+        SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(&segCount, d_genCounts + gen + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+        ++gen;
+    }
+    if (generations) *generations = gen;
+    return SELAS_OK;
+}
+
+struct Bvh2Arrays {  // the binary tree the collapse consumes
+    const int2* children;
+    const uint2* range;
+    const float4* boxLo;
+    const float4* boxHi;
+    const uint32_t* sorted;
+    uint32_t root;
+};
+
+// radix-tree arrays in, SAH tree out (device arrays registered with `tmp`).  n >= 1.
+static int buildSahTree(SelasContext* ctx, cudaStream_t st, TempFree& tmp, const BuildTri* d_tris, uint32_t n, const uint32_t* d_sorted,
+                        const uint2* d_range, const uint32_t* d_parent, const float4* d_boxLo, const float4* d_boxHi, uint32_t clusterMax,
+                        Bvh2Arrays& out, SelasBvhStats* stats) {
+    auto tempAlloc = [&](void** p, size_t bytes) -> int {
+        cudaError_t e = cudaMalloc(p, bytes + 16);
+        if (e != cudaSuccess) {
+            setError(ctx, "cudaMalloc(%zu bytes) failed during the SAH build: %s", bytes, cudaGetErrorString(e));
+            return SELAS_ERR_MEMORY;
+        }
+        tmp.ptrs.push_back(*p);
+        return SELAS_OK;
+    };
+    int rc;
+    uint32_t* d_ctr;  // [0] cluster count, [1] seed count, [2] top root, [3] final root, [8..264) top generations, [264..520) bottom generations
+    if ((rc = tempAlloc((void**)&d_ctr, sizeof(uint32_t) * 520))) return rc;
+    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_ctr, 0, sizeof(uint32_t) * 520, st));
+    // ---- clusters: count, then fill ----
+    const uint32_t total = 2u * n - 1u;
+    sahClusterRootsKernel<<<divUp(total, 256), 256, 0, st>>>((int)n, clusterMax, d_range, d_parent, d_boxLo, d_boxHi, nullptr, nullptr, d_ctr, 0u);
+    uint32_t C = 0;
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(&C, d_ctr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    if (C == 0) {
+        setError(ctx, "SAH build found no clusters over %u primitives", n);
+        return SELAS_ERR_CUDA;
+    }
+    SahItem* topItems[2];
+    uint2* d_clusters;
+    if ((rc = tempAlloc((void**)&topItems[0], sizeof(SahItem) * (size_t)C))) return rc;
+    if ((rc = tempAlloc((void**)&topItems[1], sizeof(SahItem) * (size_t)C))) return rc;
+    if ((rc = tempAlloc((void**)&d_clusters, sizeof(uint2) * (size_t)C))) return rc;
+    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_ctr, 0, sizeof(uint32_t), st));
+    sahClusterRootsKernel<<<divUp(total, 256), 256, 0, st>>>((int)n, clusterMax, d_range, d_parent, d_boxLo, d_boxHi, topItems[0], d_clusters, d_ctr, C);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+
+    // ---- top tree over the clusters ----
+    SahTree top{};
+    uint32_t* d_topOrder;
+    if ((rc = tempAlloc((void**)&top.children, sizeof(int2) * (size_t)C))) return rc;
+    if ((rc = tempAlloc((void**)&top.range, sizeof(uint2) * (size_t)C))) return rc;
+    if ((rc = tempAlloc((void**)&top.boxLo, sizeof(float4) * 2 * (size_t)C))) return rc;
+    if ((rc = tempAlloc((void**)&top.boxHi, sizeof(float4) * 2 * (size_t)C))) return rc;
+    if ((rc = tempAlloc((void**)&d_topOrder, sizeof(uint32_t) * (size_t)C))) return rc;
+    top.order = d_topOrder;
+    top.leafBase = C - 1;
+    top.rootId = d_ctr + 2;
+    SahSeg* segs[2];
+    const size_t segCap = std::max<size_t>((size_t)n / 2 + 2, (size_t)C + 2);
+    if ((rc = tempAlloc((void**)&segs[0], sizeof(SahSeg) * segCap))) return rc;
+    if ((rc = tempAlloc((void**)&segs[1], sizeof(SahSeg) * segCap))) return rc;
+    uint32_t topGenerations = 0, bottomGenerations = 0;
+    if (C >= 2) {
+        const SahSeg rootSeg{0u, C, kSahNone, 0u};
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(segs[0], &rootSeg, sizeof(rootSeg), cudaMemcpyHostToDevice, st));
+        if ((rc = runSahGenerations(ctx, st, topItems, segs, 1u, d_ctr + 8, top, &topGenerations))) return rc;
+    } else {
+        const uint32_t zero = 0;
+        SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_topOrder, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    // ---- place the clusters in top-tree leaf order ----
+    uint32_t *d_counts, *d_excl, *d_incl, *d_sums;
+    if ((rc = tempAlloc((void**)&d_counts, sizeof(uint32_t) * ((size_t)C + 1)))) return rc;
+    if ((rc = tempAlloc((void**)&d_excl, sizeof(uint32_t) * ((size_t)C + 1)))) return rc;
+    if ((rc = tempAlloc((void**)&d_incl, sizeof(uint32_t) * ((size_t)C + 1)))) return rc;
+    if ((rc = tempAlloc((void**)&d_sums, sizeof(uint32_t) * (size_t)scanScratchWords(C + 1)))) return rc;
+    SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * ((size_t)C + 1), st));
+    sahOrderedCountsKernel<<<divUp(C, 256), 256, 0, st>>>(C, d_topOrder, d_clusters, d_counts);
+    if ((rc = launchScanU32(ctx, d_counts, C + 1, d_sums, d_incl, d_excl, st))) return rc;  // excl[C] = n: the graft reads excl[k + 1]
+    // ---- the final tree ----
+    SahItem* items[2];
+    if ((rc = tempAlloc((void**)&items[0], sizeof(SahItem) * (size_t)n))) return rc;
+    if ((rc = tempAlloc((void**)&items[1], sizeof(SahItem) * (size_t)n))) return rc;
+    SahTree fin{};
+    uint32_t* d_order;
+    if ((rc = tempAlloc((void**)&fin.children, sizeof(int2) * (size_t)n))) return rc;
+    if ((rc = tempAlloc((void**)&fin.range, sizeof(uint2) * (size_t)n))) return rc;
+    if ((rc = tempAlloc((void**)&fin.boxLo, sizeof(float4) * 2 * (size_t)n))) return rc;
+    if ((rc = tempAlloc((void**)&fin.boxHi, sizeof(float4) * 2 * (size_t)n))) return rc;
+    if ((rc = tempAlloc((void**)&d_order, sizeof(uint32_t) * (size_t)n))) return rc;
+    fin.order = d_order;
+    fin.leafBase = n - 1;
+    fin.rootId = d_ctr + 3;
+    sahSeedItemsKernel<<<divUp(n, 256), 256, 0, st>>>(n, C, d_topOrder, d_clusters, d_excl, d_sorted, d_tris, items[0]);
+    sahGraftTopKernel<<<divUp(std::max(C, 2u) - 1, 256), 256, 0, st>>>(n, C, top.children, top.range, top.boxLo, top.boxHi, d_excl, d_counts, items[0], fin,
+                                                                       segs[0], d_ctr + 1, d_ctr + 2);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    uint32_t seedCount = 0;
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(&seedCount, d_ctr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    if ((rc = runSahGenerations(ctx, st, items, segs, seedCount, d_ctr + 264, fin, &bottomGenerations))) return rc;
+    uint32_t root = 0;
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(&root, d_ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    out.children = fin.children;
+    out.range = fin.range;
+    out.boxLo = fin.boxLo;
+    out.boxHi = fin.boxHi;
+    out.sorted = d_order;
+    out.root = root;
+    if (stats) {
+        stats->sahClusters += C;
+        stats->sahGenerations += topGenerations + bottomGenerations;
+    }
+    return SELAS_OK;
+}
+
+static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* d_bounds, uint32_t n, TreeOut& out, bool topLevel = false) {
     SelasContext* ctx = scene->ctx;
     cudaStream_t st = ctx->stream;
     TempFree tmp;
@@ -96,6 +235,15 @@ static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* 
     fitBoxesKernel<<<divUp(n, 256), 256, 0, st>>>(d_tris, sorted, (int)n, d_children, d_parent, d_boxLo, d_boxHi, d_arrivals);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
 
+    // The binary tree to collapse: the radix tree itself (SELAS_BVH_BUILD=lbvh), or -- the default -- a binned-SAH tree whose top is built
+    // over the radix tree's clusters of <= SELAS_SAH_CLUSTER primitives and whose clusters are rebuilt by binned SAH (bvh_sah.cuh).
+    static const bool useSah = !(getenv("SELAS_BVH_BUILD") && !strcmp(getenv("SELAS_BVH_BUILD"), "lbvh"));
+    static const uint32_t clusterMax = getenv("SELAS_SAH_CLUSTER") ? (uint32_t)std::max(2, atoi(getenv("SELAS_SAH_CLUSTER"))) : 1024u;
+    Bvh2Arrays b2{d_children, d_range, d_boxLo, d_boxHi, sorted, 0u};
+    if (useSah && !topLevel) {
+        if ((rc = buildSahTree(ctx, st, tmp, d_tris, n, sorted, d_range, d_parent, d_boxLo, d_boxHi, clusterMax, b2, &scene->stats))) return rc;
+    }
+
     // ---- collapse ----
     // Wide nodes other than the root cover > 3 triangles.  Leaf wide nodes (no inner child) are disjoint: L <= n/4;
     // branching nodes B < L; chain nodes (one inner child) own >= 7 direct triangles: 4L + 7C <= n.  So the node
@@ -119,17 +267,19 @@ static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* 
     ctrInit[0] = 1;  // root occupies node 0
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_ctr, ctrInit.data(), sizeof(uint32_t) * 260, cudaMemcpyHostToDevice, st));
     CollapseTask root;
-    root.bvh2 = 0u;  // internal node 0, or the only leaf (id n-1+0 = 0)
+    root.bvh2 = b2.root;  // radix tree: internal node 0, or the only leaf (id n-1+0 = 0); SAH tree: the id its root segment reported
     root.node = 0;
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_tasksA, &root, sizeof(root), cudaMemcpyHostToDevice, st));
-    uint32_t taskCount = 1, level = 0;
+    uint32_t taskCount = 1, level = 0, nodesSoFar = 0;
     while (taskCount > 0) {
+        nodesSoFar += taskCount;
+        out.levelEnds.push_back(nodesSoFar);
         if (level >= 256) {
             setError(ctx, "BVH collapse exceeded 256 levels");
             return SELAS_ERR_UNSUPPORTED;
         }
-        collapseLevelKernel<<<divUp(taskCount, 128), 128, 0, st>>>(d_tasksA, taskCount, (int)n, d_children, d_range, d_boxLo, d_boxHi, d_tris,
-                                                                    sorted, d_nodes, d_outTris, d_ctr, d_ctr + 1, d_tasksB, d_ctr + 2 + level);
+        collapseLevelKernel<<<divUp(taskCount, 128), 128, 0, st>>>(d_tasksA, taskCount, (int)n, b2.children, b2.range, b2.boxLo, b2.boxHi, d_tris,
+                                                                    b2.sorted, d_nodes, d_outTris, d_ctr, d_ctr + 1, d_tasksB, d_ctr + 2 + level);
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(&taskCount, d_ctr + 2 + level, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
         std::swap(d_tasksA, d_tasksB);
@@ -148,6 +298,17 @@ static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* 
     return SELAS_OK;
 }
 
+// Whole levels of the tree (top-level tree for the two-level form) that fit the shared-memory budget of the trace kernels:
+// SELAS_TRACE_TOP_NODES nodes of 80 bytes per CTA (default 0 = no staging: see the measurement note in trace.cuh).
+static uint32_t chooseTopNodeCount(const std::vector<uint32_t>& levelEnds) {
+    static const uint32_t budget = getenv("SELAS_TRACE_TOP_NODES") ? (uint32_t)std::max(0, atoi(getenv("SELAS_TRACE_TOP_NODES"))) : 0u;
+    uint32_t m = 0;
+    for (uint32_t e : levelEnds)
+        if (e <= budget && e * 80u <= 200u * 1024u) m = e;
+    return m;
+}
+
+// (the two-level variant of the kernel runs only when the scene was built that way: the flattened form keeps its register budget)
 int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::vector<InstanceGpu>& inst, const InstanceGpu* d_instances) {
     SelasContext* ctx = scene->ctx;
     cudaStream_t st = ctx->stream;
@@ -180,6 +341,7 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     scene->gpu.nodeCount = 0;
     scene->gpu.triCount = 0;
     scene->gpu.traceInstances = nullptr;
+    scene->topNodeCount = 0;
     if (n == 0) return SELAS_OK;
 
     TempFree tmp;
@@ -216,6 +378,11 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     scene->gpu.triCount = n;
     scene->stats.nodeCount = tree.nodeCount;
     scene->stats.maxDepth = tree.levels;
+    scene->topNodeCount = chooseTopNodeCount(tree.levelEnds);
+    if (tree.levels > SELAS_STACK_SIZE) {  // one stack entry per level at most: a deeper tree would drop pushes silently
+        setError(ctx, "BVH8 has %u levels; the traversal stack holds %d", tree.levels, SELAS_STACK_SIZE);
+        return SELAS_ERR_UNSUPPORTED;
+    }
     scene->stats.buildMs = ms;
     scene->stats.deviceBytes = (uint64_t)tree.nodeCount * 80ull + (uint64_t)n * 48ull;
     return SELAS_OK;
@@ -246,6 +413,7 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
     scene->gpu.nodeCount = 0;
     scene->gpu.triCount = 0;
     scene->gpu.traceInstances = nullptr;
+    scene->topNodeCount = 0;
 
     struct Blas {
         TreeOut tree;
@@ -354,7 +522,7 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
         uint32_t hb[6] = {hostFloatFlip(tlo[0]), hostFloatFlip(tlo[1]), hostFloatFlip(tlo[2]), hostFloatFlip(thi[0]), hostFloatFlip(thi[1]), hostFloatFlip(thi[2])};
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, hb, sizeof(hb), cudaMemcpyHostToDevice, st));
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_fake, fake.data(), sizeof(BuildTri) * fake.size(), cudaMemcpyHostToDevice, st));
-        int rc = buildTree(scene, d_fake, d_bounds, (uint32_t)fake.size(), top);
+        int rc = buildTree(scene, d_fake, d_bounds, (uint32_t)fake.size(), top, true);  // instance boxes: the radix tree is kept
         if (rc) return rc;
     }
     // one node array, one triangle array: [top level][mesh 0][mesh 1]...
@@ -422,8 +590,18 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
     scene->gpu.nodeCount = (uint32_t)totalNodes;
     scene->gpu.triCount = (uint32_t)totalTris;
     scene->gpu.traceInstances = d_table;
+    scene->topNodeCount = chooseTopNodeCount(top.levelEnds);
     scene->stats.nodeCount = (uint32_t)totalNodes;
-    scene->stats.maxDepth = top.levels;
+    uint32_t deepestMesh = 0;
+    for (const Blas& b : blas)
+        if (b.used) deepestMesh = std::max(deepestMesh, b.tree.levels);
+    // the two-level walk shares one stack: top-level entries, the two entries parked on entering an instance, the mesh tree's entries
+    scene->stats.maxDepth = top.levels + 2 + deepestMesh;
+    if (scene->stats.maxDepth > SELAS_STACK_SIZE) {
+        setError(ctx, "two-level BVH8 needs %u stack entries (top %u + 2 + mesh %u); the traversal stack holds %d", scene->stats.maxDepth, top.levels,
+                 deepestMesh, SELAS_STACK_SIZE);
+        return SELAS_ERR_UNSUPPORTED;
+    }
     scene->stats.buildMs = ms;
     scene->stats.reserved = (uint32_t)std::min<uint64_t>(instancedTris, 0xFFFFFFFFull);  // triangles a flattened build would have stored
     scene->stats.deviceBytes = totalNodes * 80ull + totalTris * 48ull + table.size() * sizeof(InstanceTrace);
@@ -437,26 +615,54 @@ static Bvh8 bvhOf(const SelasScene* s) {
     b.nodeCount = s->gpu.nodeCount;
     b.triCount = s->gpu.triCount;
     b.instances = s->gpu.traceInstances;
+    b.topCount = s->topNodeCount;
     return b;
 }
 
-// the two-level variant of the kernel only when the scene was built that way: the flattened form keeps its register budget
-#define SELAS_TRACE_LAUNCH(MODE, COUNT) (scene->gpu.traceInstances ? traceKernel<MODE, COUNT, true> : traceKernel<MODE, COUNT, false>)
-
-static int traceGrid(const SelasContext* ctx) { return ctx->smCount * SELAS_TRACE_CTAS_PER_SM; }
+// Launch shape of a trace kernel: the staged top levels are dynamic shared memory; the grid is what is resident with that much of it.
+struct TraceLaunch {
+    int grid;
+    size_t smem;
+};
+template <typename K>
+static TraceLaunch traceLaunch(const SelasScene* scene, K kernel) {
+    TraceLaunch l;
+    l.smem = (size_t)scene->topNodeCount * 80u;
+    if (l.smem > 48u * 1024u) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
+    int perSm = SELAS_TRACE_CTAS_PER_SM;
+    if (l.smem) {
+        int resident = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, SELAS_TRACE_THREADS, l.smem) == cudaSuccess && resident > 0)
+            perSm = std::min(perSm, resident);
+    }
+    l.grid = scene->ctx->smCount * perSm;
+    return l;
+}
+// kernel variant by scene: two-level form only when the scene was built that way (the flattened form keeps its register budget), staged
+// top levels only when asked for
+#define SELAS_TRACE_GO2(MODE, COUNT, INST, TOP, ...)                                                              \
+    do {                                                                                                          \
+        TraceLaunch tl = traceLaunch(scene, traceKernel<MODE, COUNT, INST, TOP>);                                 \
+        traceKernel<MODE, COUNT, INST, TOP><<<tl.grid, SELAS_TRACE_THREADS, tl.smem, stream>>>(__VA_ARGS__);      \
+    } while (0)
+#define SELAS_TRACE_GO(MODE, COUNT, ...)                                                                           \
+    do {                                                                                                          \
+        const bool inst__ = scene->gpu.traceInstances != nullptr, top__ = scene->topNodeCount != 0;               \
+        if (inst__ && top__) SELAS_TRACE_GO2(MODE, COUNT, true, true, __VA_ARGS__);                               \
+        else if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, __VA_ARGS__);                                  \
+        else if (top__) SELAS_TRACE_GO2(MODE, COUNT, false, true, __VA_ARGS__);                                   \
+        else SELAS_TRACE_GO2(MODE, COUNT, false, false, __VA_ARGS__);                                             \
+    } while (0)
 
 int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_ng4, uint32_t* d_counts,
                     uint32_t* d_rayCounter, cudaStream_t stream) {
     if (n == 0) return SELAS_OK;
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
-    int grid = traceGrid(ctx);
     if (d_counts)
-        SELAS_TRACE_LAUNCH(0, true)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts,
-                                                                        nullptr, nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
-        SELAS_TRACE_LAUNCH(0, false)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, nullptr,
-                                                                         nullptr, nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(0, false, bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, nullptr, nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -466,13 +672,10 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
     if (n == 0) return SELAS_OK;
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
-    int grid = traceGrid(ctx);
     if (d_counts)
-        SELAS_TRACE_LAUNCH(1, true)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr,
-                                                                        nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(1, true, bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
-        SELAS_TRACE_LAUNCH(1, false)<<<grid, SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, nullptr, nullptr,
-                                                                         nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(1, false, bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, nullptr, nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -483,11 +686,9 @@ int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t max
                             uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
     if (d_totals)
-        SELAS_TRACE_LAUNCH(0, true)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
-                                                                                  nullptr, nullptr, d_rayCounter, d_totals);
+        SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, d_totals);
     else
-        SELAS_TRACE_LAUNCH(0, false)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr,
-                                                                                   nullptr, nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(0, false, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
@@ -496,11 +697,9 @@ int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN
                            float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
     SelasContext* ctx = scene->ctx;
     if (d_totals)
-        SELAS_TRACE_LAUNCH(2, true)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
-                                                                                  d_payload, d_film, d_rayCounter, d_totals);
+        SELAS_TRACE_GO(2, true, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, d_totals);
     else
-        SELAS_TRACE_LAUNCH(2, false)<<<traceGrid(ctx), SELAS_TRACE_THREADS, 0, stream>>>(bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr,
-                                                                                   d_payload, d_film, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(2, false, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }

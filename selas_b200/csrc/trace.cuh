@@ -47,8 +47,8 @@ SELAS_D void setupRayDirection(V3 d, V3& idir, bool& negx, bool& negy, bool& neg
     octInv4 = (7u - oct) * 0x01010101u;
 }
 
-template <int MODE, bool COUNT, bool INST = false>
-__global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n,
+template <int MODE, bool COUNT, bool INST = false, bool TOP = false>
+__global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT) ? 6 : SELAS_TRACE_CTAS_PER_SM) traceKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n,
                                                                    const uint32_t* __restrict__ nPtr,
                                                                    SelasHit* __restrict__ hits, uint8_t* __restrict__ occluded,
                                                                    float4* __restrict__ ng, uint32_t* __restrict__ counts,
@@ -57,6 +57,17 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                                                                    unsigned long long* __restrict__ totals) {
     constexpr bool ANY = MODE != 0;
     static_assert(!(INST && SELAS_TRI_POSTPONE_DIV), "parked triangle groups are not carried across instance boundaries");
+    // TOP: hot top levels in shared memory (north star (1)): every ray starts at the root and the first levels are visited by all of
+    // them; from shared memory 32 lanes on 32 different nodes are served bank-wise instead of one L1 tag lookup per line.  Measured on
+    // B200 (profiles/r2_ab_smem_top.jsonl) it does not pay: 9 / 73 / 585 / 1200 staged nodes at 128 / 256 / 512 threads per CTA are all
+    // 0.2 .. 2 % SLOWER than no staging on configs[2] and configs[1] (the top levels already hit in L1, the shared-memory carve-out
+    // shrinks that L1, and the select costs registers), so the variant is compiled but off by default (SELAS_TRACE_TOP_NODES=n enables).
+    extern __shared__ float4 sTopNodes[];
+    const uint32_t topCount = TOP ? bvh.topCount : 0u;
+    if constexpr (TOP) {
+        for (uint32_t i = threadIdx.x; i < bvh.topCount * 5u; i += blockDim.x) sTopNodes[i] = __ldg(bvh.nodes + i);
+        __syncthreads();
+    }
     if (nPtr) n = min(n, *nPtr);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ltMask = (1u << lane) - 1u;
@@ -135,8 +146,15 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS) traceKernel(Bvh8 bvh, con
                 if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
                 uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
                 uint32_t rel = __popc(hitsImask & ~(0xffffffffu << slot));
-                const float4* np = bvh.nodes + (size_t)((INST ? nodeBase : 0u) + group.x + rel) * 5;
-                float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                const uint32_t nodeIdx = (INST ? nodeBase : 0u) + group.x + rel;
+                float4 n0, n1, n2, n3, n4;
+                if (TOP && nodeIdx < topCount) {
+                    const float4* sp = sTopNodes + nodeIdx * 5u;
+                    n0 = sp[0]; n1 = sp[1]; n2 = sp[2]; n3 = sp[3]; n4 = sp[4];
+                } else {
+                    const float4* np = bvh.nodes + (size_t)nodeIdx * 5;
+                    n0 = __ldg(np); n1 = __ldg(np + 1); n2 = __ldg(np + 2); n3 = __ldg(np + 3); n4 = __ldg(np + 4);
+                }
                 if (COUNT) ++nNodes;
                 uint32_t hitMask = intersectNode(n0, n1, n2, n3, n4, o, idir, negx, negy, negz, octInv4, tnear, tmax);
                 group.x = __float_as_uint(n1.x);
