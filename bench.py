@@ -7,9 +7,12 @@
 
 A "step" is one pass of --spp-per-step samples per pixel over the whole 1080p frame on every GPU (weak scaling: per-GPU
 work is fixed, rank r renders its own sample indices).  `value` = paths/s with the scene, BVH and film resident in HBM
-(CUDA events on the render stream, max over ranks, one NCCL reduce of the film inside the timed region when N > 1);
-`e2e` = the same metric through the host-buffer C-ABI call selas_cuda_render_pathtracer (pinned host film buffers,
-device->host copy of the film every step).  One JSON line on stdout (rank 0).
+(the K steps are only ENQUEUED by the host -- selas_cuda_render_pathtracer_device with stats = NULL does not wait --, CUDA
+events on the render stream, max over ranks, one NCCL reduce of the film inside the timed region when N > 1).
+`e2e` = the same metric through the public C ABI with the result on the host every step: N = 1, selas_cuda_render_pathtracer
+(pinned host film, device->host copy inside the call); N > 1, render_pathtracer_device + selas_cuda_reduce_film + the
+device->host copy of the reduced film on rank 0, every step.  `job` = the whole configs[2] render (256 spp split over the N
+GPUs, the reduce, FrameBuffer_Scale, one device->host copy of the film): strong scaling.  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
@@ -30,6 +33,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "path_samples_per_s_1080p"
 UNIT = "samples/s"
 WIDTH, HEIGHT, MAX_DEPTH, RR_START = 1920, 1080, 16, 8
+PARITY_FIRST_SAMPLE = 7777  # sample index of the pass both arms render for the 1080p image comparison
 
 
 def log(*a):
@@ -48,6 +52,8 @@ def parse_args():
     ap.add_argument("--cpu-spp", type=int, default=1, help="samples per pixel of one CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-raycast", action="store_true", help="skip the config-2 Mrays/s side measurement")
+    ap.add_argument("--no-job", action="store_true", help="skip the whole-job (256 spp) strong-scaling measurement")
+    ap.add_argument("--job-spp", type=int, default=256, help="samples per pixel of the whole job (BASELINE configs[2]: 256)")
     return ap.parse_args()
 
 
@@ -143,11 +149,14 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def run_cpu_arm(data, camera, args, steps, warmup, which="auto"):
-    """The reference's CPU path for this workload: EvaluatePath over the reference's own Shading objects when
-    oracle/_ref was built here ("reference"), else over the restatement ("port"); ray casting by the oracle's
-    scalar SAH BVH in both (Embree is not available: BASELINE.md tier B).  Bounded sample: every cpu-stride-th pixel."""
-    from selas_b200 import capi
+def run_cpu_arm(data, args, steps, warmup, which="auto"):
+    """The reference's CPU path for this workload.  "reference": the reference's OWN integrator loop -- PathTracer.cpp's EvaluatePath /
+    RayPick / OcclusionRay, SurfaceParameters.cpp, Framebuffer.cpp and the Shading library compiled unmodified into oracle/_ref behind
+    the Embree-API shim (oracle/ref_pathtracer.cpp); "port": the plain-C++ restatement.  Ray casting by the oracle's scalar SAH BVH in
+    both (Embree is absent here and on the GPU box: BASELINE.md tier B, profiles/r2_gpu_box_probe.txt).  The camera is made by the
+    reference's InitializeRayCastCamera (ref_camera_init), not by the product.  Bounded sample: cpu-spp samples of every
+    cpu-stride-th pixel per step."""
+    from selas_b200 import capi, scenes
     from tests import oracle_binding
 
     lib, kind = None, "port"
@@ -157,15 +166,19 @@ def run_cpu_arm(data, camera, args, steps, warmup, which="auto"):
     if lib is None:
         lib, kind = oracle_binding.load_oracle(), "port"
     threads = cpu_threads()
+    c = scenes.HEIGHTFIELD_CAMERA
+    camera = lib.camera_init(c["position"], c["look_at"], c["up"], c["fov"], WIDTH, HEIGHT)
     t0 = time.perf_counter()
     h = lib.scene_create(data)
     build_s = time.perf_counter() - t0
     rs = capi.render_settings(WIDTH, HEIGHT, args.cpu_spp, MAX_DEPTH, RR_START, layers=1, seed=1, pixel_stride=args.cpu_stride)
+    render = lib.render_reference_loop if kind == "reference" else lib.render
     times, paths, rays = [], 0, 0
+    last_film = None
     for i in range(warmup + steps):
-        rs.firstSample = i * args.cpu_spp
+        rs.firstSample = PARITY_FIRST_SAMPLE if i == warmup + steps - 1 else i * args.cpu_spp
         t0 = time.perf_counter()
-        _, st = lib.render(h, camera, rs, nthreads=threads)
+        last_film, st = render(h, camera, rs, nthreads=threads)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
@@ -173,11 +186,14 @@ def run_cpu_arm(data, camera, args, steps, warmup, which="auto"):
             rays += st.closestRays + st.occlusionRays
     lib.scene_destroy(h)
     total = sum(times)
-    return {"value": paths / total, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"pixel stride {args.cpu_stride} over the 1080p frame, {args.cpu_spp} spp per step, {steps} steps "
+    return {"value": paths / total, "unit": UNIT, "cores": threads, "kind": kind, "last_film": last_film[0],
+            "sample": f"pixel stride {args.cpu_stride} over the 1080p frame, {args.cpu_spp} spp per step, {steps} steps after {warmup} warm-up "
                       f"({paths} paths, {total:.1f} s; CPU BVH build {build_s:.1f} s excluded)",
+            "integrator": "PathTracer.cpp EvaluatePath + SurfaceParameters.cpp + Framebuffer.cpp + Shading/*.cpp, unmodified (oracle/_ref)"
+                          if kind == "reference" else "oracle restatement (oracle/selas_oracle.cpp)",
             "mrays_per_s": rays / total / 1e6, "ms_per_step": 1e3 * total / max(1, len(times)), "paths_per_step": paths // max(1, len(times)),
-            "ray_cast": "oracle scalar SAH-BVH2 (Embree 3.2.0 absent: headers only in the reference tree)"}
+            "ray_cast": "oracle scalar SAH-BVH2 behind the Embree-API shim (Embree 3.2.0 absent: headers only in the reference tree, "
+                        "no libembree on the GPU box)"}
 
 
 _REAL_STDOUT = None
@@ -214,15 +230,17 @@ def main():
             return 0
         t0 = time.perf_counter()
         data = scenes.disney_heightfield(grid=args.grid)
-        camera = scenes.heightfield_camera(WIDTH, HEIGHT)
         log(f"[reference arm] scene generated in {time.perf_counter() - t0:.1f} s")
-        steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
-        r = run_cpu_arm(data, camera, args, steps, warmup)
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        r = run_cpu_arm(data, args, steps, warmup)
         cfg = workload_config(args, n_gpus, data.triangle_count())
+        # this arm's own step: the same workload, a bounded sample of it per step, on the host cores (no GPU, no sharding)
+        cfg.update({"spp_per_step_per_gpu": args.cpu_spp, "paths_per_step": r["paths_per_step"], "sharding": "none: one process, all host threads",
+                    "sample": r["sample"]})
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": cfg,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ray_cast")},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "integrator", "ray_cast")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -252,7 +270,7 @@ def main():
     bvh = scene.bvh_stats()
     if rank == 0:
         log(f"scene upload + BVH8 build: {upload_s:.2f} s (device build {bvh.buildMs:.1f} ms, {bvh.nodeCount} nodes, "
-            f"{bvh.deviceBytes / 1e9:.2f} GB)")
+            f"{bvh.deviceBytes / 1e9:.2f} GB, {bvh.sahClusters} SAH clusters)")
 
     S = args.spp_per_step
     pixels = WIDTH * HEIGHT
@@ -260,16 +278,21 @@ def main():
     stream = torch.cuda.Stream(dev)  # explicit stream: the library launches on it and the CUDA events below are recorded on it
     torch.cuda.set_stream(stream)
 
-    def settings(step_index, flags=0):
+    def settings(first_sample, spp=S, flags=0):
+        return capi.render_settings(WIDTH, HEIGHT, spp, MAX_DEPTH, RR_START, layers=1, seed=1, first_sample=first_sample, flags=flags)
+
+    def step_settings(step_index, flags=0):
         # rank r renders sample indices [(step*world + r) * S, +S): disjoint streams across ranks and steps
-        return capi.render_settings(WIDTH, HEIGHT, S, MAX_DEPTH, RR_START, layers=1, seed=1,
-                                    first_sample=(step_index * world + rank) * S, flags=flags)
+        return settings((step_index * world + rank) * S, flags=flags)
 
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+
+    def enqueue(rs):  # selas_cuda_render_pathtracer_device with stats = NULL: returns while the GPU works
+        scene.render_device(camera, rs, film.data_ptr(), stream.cuda_stream, want_stats=False)
 
     reducer = None
     if world > 1:
@@ -278,31 +301,32 @@ def main():
 
     # ---- device-resident arm: value ---------------------------------------------------------------------------
     for i in range(args.warmup):
-        scene.render_device(camera, settings(i), film.data_ptr(), stream.cuda_stream)
+        enqueue(step_settings(i))
     if reducer is not None:  # warm the communicator up (first collective sets up the NVLink channels)
         reducer.reduce(film, dst=0, stream=stream.cuda_stream)
+    scene.collect_stats()
     film.zero_()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    agg = {"closestMs": 0.0, "shadeMs": 0.0, "shadowMs": 0.0, "generateMs": 0.0, "closestRays": 0, "occlusionRays": 0, "launches": 0,
-           "closestLaunches": 0}
     e0.record(stream)
+    host_enqueue_ms = None
     for i in range(args.steps):
-        st = scene.render_device(camera, settings(args.warmup + i), film.data_ptr(), stream.cuda_stream)
-        for k in ("closestMs", "shadeMs", "shadowMs", "generateMs"):
-            agg[k] += getattr(st, k)
-        agg["closestRays"] += st.closestRays
-        agg["occlusionRays"] += st.occlusionRays
-        agg["launches"] += st.kernelLaunches
-        agg["closestLaunches"] += st.closestLaunches
+        t_host = time.perf_counter()
+        enqueue(step_settings(args.warmup + i))
+        if i == 0:  # host cost of enqueueing one step into an empty queue (later steps block on the driver's launch-queue depth)
+            host_enqueue_ms = (time.perf_counter() - t_host) * 1e3
     if world > 1:  # the path's only collective: one ncclReduce of the film, through the C ABI
         reducer.reduce(film, dst=0, stream=stream.cuda_stream)
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    st = scene.collect_stats()  # per-kernel CUDA-event spans and ray totals of exactly the timed steps
+    agg = {"closestMs": st.closestMs, "shadeMs": st.shadeMs, "shadowMs": st.shadowMs, "generateMs": st.generateMs,
+           "closestRays": int(st.closestRays), "occlusionRays": int(st.occlusionRays), "launches": int(st.kernelLaunches),
+           "closestLaunches": int(st.closestLaunches)}
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -310,6 +334,7 @@ def main():
     paths_total = pixels * S * args.steps * world
     value = paths_total / (total_ms * 1e-3)
     # FrameBuffer_Scale (Framebuffer.cpp:62-70) on the reduced film, outside the timed region like the reference's save path
+    mean_radiance, nonfinite_values = None, None
     if rank == 0:
         ctx.check(ctx.lib.selas_cuda_film_scale_device(ctx.handle, capi.C.c_void_p(film.data_ptr()), capi.C.c_size_t(film.numel()),
                                                        capi.f32(1.0 / (S * args.steps * world)), capi.C.c_void_p(stream.cuda_stream)))
@@ -321,17 +346,25 @@ def main():
         mean_radiance = float(film[finite].mean().item())
         assert mean_radiance > 0.0 and nonfinite_values < film.numel() // 1000, "film is empty or mostly not finite"
 
-    # ---- end-to-end arm through the host-buffer C ABI ---------------------------------------------------------------
+    # ---- end-to-end arm: the public C ABI with the step's result on the host, every step ------------------------------------------
     host_film = torch.zeros(pixels * 3, dtype=torch.float32).pin_memory()
     host_np = host_film.numpy()
     ptrs = (capi.C.c_void_p * 1)(host_np.ctypes.data)
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     stats = capi.RenderStats()
 
     def e2e_step(i):
-        rs = settings(1000 + i)
-        ctx.check(ctx.lib.selas_cuda_render_pathtracer(scene.handle, capi.C.byref(camera), capi.C.byref(rs), ptrs, capi.C.byref(stats)))
-        return float(host_np[::4099].sum())  # the step's result is read on the host
+        rs = step_settings(1000 + i)
+        if world == 1:  # PathTracer::GenerateImage's shape: host film out
+            ctx.check(ctx.lib.selas_cuda_render_pathtracer(scene.handle, capi.C.byref(camera), capi.C.byref(rs), ptrs, None))
+        else:  # N GPUs: render into the device film, reduce onto rank 0, rank 0 brings the reduced film to the host
+            film.zero_()
+            enqueue(rs)
+            reducer.reduce(film, dst=0, stream=stream.cuda_stream)
+            if rank == 0:
+                host_film.copy_(film, non_blocking=True)
+            stream.synchronize()
+        return float(host_np[::4099].sum()) if rank == 0 else 0.0  # the step's result is read on the host
 
     e2e_step(-1)
     barrier()
@@ -343,11 +376,51 @@ def main():
         e2e_each.append((time.perf_counter() - t1) * 1e3)
     barrier()
     if rank == 0:
-        log("e2e per-step ms:", [round(x, 2) for x in e2e_each], "device ms of last:", round(stats.renderMs, 2))
+        log("e2e per-step ms:", [round(x, 2) for x in e2e_each])
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = pixels * S * e2e_steps * world / float(e2e_s.item())
+    scene.collect_stats()
+
+    # ---- the whole configs[2] job: 256 spp over the N GPUs, reduce, scale, film to the host (strong scaling) ----------------------------
+    job = None
+    if not args.no_job:
+        from selas_b200 import distributed as D
+        JOB_SPP = args.job_spp
+        first, count = D.shard_samples(JOB_SPP, rank, world)
+        film.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        j0, j1, j2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        j0.record(stream)
+        done = 0
+        while done < count:  # whole sample passes of S spp, the library cuts them into <= 8 M paths in flight
+            k = min(S, count - done)
+            enqueue(settings(100000 + first + done, spp=k))
+            done += k
+        j1.record(stream)
+        if world > 1:
+            reducer.reduce(film, dst=0, stream=stream.cuda_stream)
+        j2.record(stream)
+        if rank == 0:
+            ctx.check(ctx.lib.selas_cuda_film_scale_device(ctx.handle, capi.C.c_void_p(film.data_ptr()), capi.C.c_size_t(film.numel()),
+                                                           capi.f32(1.0 / JOB_SPP), capi.C.c_void_p(stream.cuda_stream)))
+            host_film.copy_(film, non_blocking=True)
+        stream.synchronize()
+        barrier()
+        wall = torch.tensor([time.perf_counter() - t0, j0.elapsed_time(j1) * 1e-3, j1.elapsed_time(j2) * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        jst = scene.collect_stats()
+        if rank == 0:
+            fin = np.isfinite(host_np)
+            job = {"what": f"BASELINE configs[2] whole job: {JOB_SPP} spp at 1920x1080 split over {world} GPU(s) ({count} spp on rank 0), one "
+                           "ncclReduce of the film, FrameBuffer_Scale, one device->host copy of the film on rank 0",
+                   "spp": JOB_SPP, "paths": pixels * JOB_SPP, "seconds": float(wall[0].item()), "samples_per_s": pixels * JOB_SPP / float(wall[0].item()),
+                   "render_seconds_max_rank": float(wall[1].item()), "reduce_ms": float(wall[2].item()) * 1e3 if world > 1 else 0.0,
+                   "scaling": "strong", "mean_radiance": float(host_np[fin].mean()), "nonfinite_film_values": int((~fin).sum()),
+                   "rank0_closest_rays": int(jst.closestRays), "rank0_occlusion_rays": int(jst.occlusionRays)}
 
     if rank != 0:
         if world > 1:
@@ -356,7 +429,7 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel (closest-hit traversal) -------------------------------------------------------
-    cst = scene.render_device(camera, settings(2000, flags=capi.RENDER_COUNT_TRAVERSAL), film.data_ptr(), stream.cuda_stream)
+    cst = scene.render_device(camera, step_settings(2000, flags=capi.RENDER_COUNT_TRAVERSAL), film.data_ptr(), stream.cuda_stream)
     n_node = cst.closestNodes / max(1, cst.closestRays)
     n_tri = cst.closestTris / max(1, cst.closestRays)
     s_node = cst.shadowNodes / max(1, cst.occlusionRays)
@@ -370,7 +443,7 @@ def main():
     dram_per_ray, traffic_src = captured_traffic_per_ray()
     roofline = {"bound": "hbm", "kernel": "traceKernel<0> (BVH8 closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
-                # bytes per launch: DRAM bytes per ray of the committed ncu capture x this run's average rays per launch
+                # bytes per launch: DRAM bytes per ray of the committed ncu capture (all launches of a step) x this run's average rays per launch
                 "traffic": dram_per_ray * rays_per_launch if dram_per_ray else None,
                 "traffic_source": f"{traffic_src}: {dram_per_ray:.1f} DRAM B/ray (algorithmic {bytes_per_ray:.0f} B/ray: the tree top is served by L1/L2)"
                 if dram_per_ray else None,
@@ -380,8 +453,15 @@ def main():
                 "avg_launch_ms": agg["closestMs"] / max(1, agg["closestLaunches"]),
                 "kernel_share_of_step": {"closest": agg["closestMs"] / kernel_ms, "shade": agg["shadeMs"] / kernel_ms,
                                          "shadow": agg["shadowMs"] / kernel_ms, "generate": agg["generateMs"] / kernel_ms},
+                "kernel_ms_per_step": {"closest": agg["closestMs"] / args.steps, "shade_incl_material_sort": agg["shadeMs"] / args.steps,
+                                       "shadow": agg["shadowMs"] / args.steps, "generate": agg["generateMs"] / args.steps,
+                                       "step": total_ms / args.steps},
                 "shadow": {"algorithmic_bytes_per_ray": shadow_bytes_per_ray, "nodes_per_ray": s_node, "tris_per_ray": s_tri,
-                           "achieved": shadow_bytes_per_ray * agg["occlusionRays"] / (agg["shadowMs"] * 1e-3) / 1e9 if agg["shadowMs"] > 0 else 0.0}}
+                           "achieved": shadow_bytes_per_ray * agg["occlusionRays"] / (agg["shadowMs"] * 1e-3) / 1e9 if agg["shadowMs"] > 0 else 0.0,
+                           "frac": (shadow_bytes_per_ray * agg["occlusionRays"] / (agg["shadowMs"] * 1e-3) / 1e9 / peak) if agg["shadowMs"] > 0 else 0.0},
+                "shade": {"algorithmic_bytes_per_vertex": 388.0,
+                          "achieved": 388.0 * agg["closestRays"] / (agg["shadeMs"] * 1e-3) / 1e9 if agg["shadeMs"] > 0 else 0.0,
+                          "frac": (388.0 * agg["closestRays"] / (agg["shadeMs"] * 1e-3) / 1e9 / peak) if agg["shadeMs"] > 0 else 0.0}}
     mrays = {"closest": agg["closestRays"] / (agg["closestMs"] * 1e-3) / 1e6 if agg["closestMs"] > 0 else 0.0,
              "occlusion": agg["occlusionRays"] / (agg["shadowMs"] * 1e-3) / 1e6 if agg["shadowMs"] > 0 else 0.0,
              "whole_step": (agg["closestRays"] + agg["occlusionRays"]) * world / (total_ms * 1e-3) / 1e6}
@@ -393,20 +473,33 @@ def main():
         except Exception as ex:  # side measurement only: never hide the headline
             raycast = {"error": str(ex)}
 
-    cpu = None
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
+        # the pass the CPU arm renders last, through the CUDA path (same seed, same per-path streams), for the 1080p image comparison
+        prs = capi.render_settings(WIDTH, HEIGHT, args.cpu_spp, MAX_DEPTH, RR_START, layers=1, seed=1, first_sample=PARITY_FIRST_SAMPLE,
+                                   pixel_stride=args.cpu_stride)
+        gfilm, _ = scene.render(camera, prs)
         scene.close()
-        r = run_cpu_arm(data, camera, args, steps=6, warmup=0)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "ray_cast", "mrays_per_s")}
+        r = run_cpu_arm(data, args, steps=6, warmup=1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "integrator", "ray_cast", "mrays_per_s")}
+        parity = image_parity(gfilm[0], r["last_film"], f"configs[2] at 1920x1080, {args.cpu_spp} spp, depth 16: CUDA wavefront vs the CPU arm "
+                              f"({r['kind']}: {r['integrator']}) on the same per-path RNG streams")
 
+    if world == 1:
+        e2e_bytes = {"h2d_bytes_per_step": capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.RenderSettings), "d2h_bytes_per_step": pixels * 3 * 4,
+                     "api": "selas_cuda_render_pathtracer (pinned host film, scene resident as in the reference's GenerateImage)"}
+    else:
+        e2e_bytes = {"h2d_bytes_per_step": (capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.RenderSettings)) * world, "d2h_bytes_per_step": pixels * 3 * 4,
+                     "nccl_reduce_bytes_per_step_per_rank": pixels * 3 * 4,
+                     "api": "per rank selas_cuda_render_pathtracer_device + selas_cuda_reduce_film every step; rank 0 copies the reduced film to pinned host memory"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world, tris), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.RenderSettings),
-                    "d2h_bytes_per_step": pixels * 3 * 4, "steps": e2e_steps,
-                    "api": "selas_cuda_render_pathtracer (pinned host film, scene resident as in the reference's GenerateImage)"},
-            "gpu_launches": int(agg["launches"]), "roofline": roofline, "cpu_baseline": cpu, "mrays_per_s": mrays, "raycast_config2": raycast,
-            "bvh": {"build_ms": bvh.buildMs, "nodes": bvh.nodeCount, "triangles": bvh.triangleCount, "device_gb": bvh.deviceBytes / 1e9,
+            "e2e": dict({"value": e2e_value, "unit": UNIT, "steps": e2e_steps}, **e2e_bytes),
+            "gpu_launches": int(agg["launches"]), "host_enqueue_ms_per_step": host_enqueue_ms,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_1080p": parity, "job": job, "mrays_per_s": mrays, "raycast_config2": raycast,
+            "bvh": {"builder": "binned SAH over Morton clusters" if bvh.sahClusters else "LBVH", "build_ms": bvh.buildMs, "nodes": bvh.nodeCount,
+                    "triangles": bvh.triangleCount, "device_gb": bvh.deviceBytes / 1e9, "sah_clusters": bvh.sahClusters, "levels": bvh.maxDepth,
                     "upload_plus_build_s": upload_s},
             "mean_radiance": mean_radiance, "nonfinite_film_values": nonfinite_values}
     emit(line)
@@ -414,6 +507,20 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def image_parity(g, o, what):
+    """Same-stream image comparison (SURVEY 8(d)(v) metric, trimmed: the reference estimator has fireflies of 1e4 and a diverged path on
+    one of them would decide a plain mean): fraction of pixels within 1e-3, relMSE over the 99 % best pixels, ratio of the means."""
+    g, o = np.asarray(g, np.float64), np.asarray(o, np.float64)
+    fin = np.isfinite(g).all(axis=2) & np.isfinite(o).all(axis=2)
+    close = np.isclose(g, o, rtol=1e-3, atol=1e-4).all(axis=2)
+    with np.errstate(all="ignore"):
+        err = np.sort(((g - o) ** 2 / (o ** 2 + 1e-2)).mean(axis=2)[fin])
+    return {"what": what, "pixels": int(fin.size), "finite_both": float(fin.mean()),
+            "same_nonfinite_pixels": bool(np.array_equal(np.isfinite(g).all(axis=2), np.isfinite(o).all(axis=2))),
+            "pixels_within_1e-3": float(close.mean()), "relmse_99pct": float(err[: int(len(err) * 0.99)].mean()), "relmse_all": float(err.mean()),
+            "mean_ratio": float(g[fin].mean() / o[fin].mean())}
 
 
 def raycast_microbench(ctx, torch, dev, stream):

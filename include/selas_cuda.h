@@ -190,6 +190,13 @@ typedef struct SelasMeshDesc {
 typedef struct SelasInstanceDesc {
     uint32_t meshIndex;
     float    localToWorld[16];
+    /* The ids a hit on this instance reports, read only when SelasSceneDesc.flags has SELAS_SCENE_INSTANCE_IDS: the reference's two
+     * instancing levels (SceneResource.cpp:87-142, :362-378; SubsceneResource.cpp:186-195).  instID0 = index of the subscene instance in
+     * SceneResourceData::subsceneInstances, instID1 = index of the model instance in SubsceneResourceData::modelInstances, geomID = index
+     * of the mesh inside its model (ModelResource::userDatas), so that ModelDataFromRayIds(scene, hit.instId, hit.geomId, ...) of the
+     * reference resolves a hit of this library unchanged.  localToWorld is then model.localToWorld * subscene.localToWorld.
+     * Without the flag a hit reports instID0 = index of this record, instID1 = 0, geomID = meshIndex. */
+    uint32_t instID0, instID1, geomID;
 } SelasInstanceDesc;
 
 /* ImageBasedLightResourceData, Source/Core/SceneLib/ImageBasedLightResource.h:16-35: lat-long environment with the marginal /
@@ -227,7 +234,7 @@ typedef struct SelasSceneDesc {
  * subscene-instance callbacks, SubsceneResource.cpp:63-79, SceneResource.cpp:87-187) -- instead of flattening every instance into
  * world-space triangles.  Same hits and ids as the flattened form up to float rounding of the ray transform; without an instance list
  * one identity instance per mesh is implied (instID0 = mesh index). */
-enum { SELAS_SCENE_TWO_LEVEL_BVH = 1 };
+enum { SELAS_SCENE_TWO_LEVEL_BVH = 1, SELAS_SCENE_INSTANCE_IDS = 2 /* SelasInstanceDesc.instID0 / instID1 / geomID are what hits report */ };
 
 /* Compile-time macros of the reference integrator made runtime (PathTracer.cpp:42-46, :248). */
 /* SelasRenderSettings.flags */

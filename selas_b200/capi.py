@@ -62,7 +62,7 @@ class MeshDesc(C.Structure):
 
 
 class InstanceDesc(C.Structure):
-    _fields_ = [("meshIndex", u32), ("localToWorld", f32 * 16)]
+    _fields_ = [("meshIndex", u32), ("localToWorld", f32 * 16), ("instID0", u32), ("instID1", u32), ("geomID", u32)]
 
 
 class IblDesc(C.Structure):
@@ -310,6 +310,7 @@ def camera_init(position, look_at, up, fov_degrees, width, height, znear=0.1, zf
 
 
 SCENE_TWO_LEVEL_BVH = 1
+SCENE_INSTANCE_IDS = 2
 
 
 def texture_array(tex):
@@ -334,7 +335,8 @@ class SceneData:
     meshes: list of dicts {positions (V,3) f32, indices (F,3|4) u32, normals?, tangents?, uvs?, material, lightSet, ptex?}
     """
 
-    def __init__(self, meshes, materials, lights=None, light_sets=None, background=(0, 0, 0, 0), instances=None, ibl=None, two_level=False):
+    def __init__(self, meshes, materials, lights=None, light_sets=None, background=(0, 0, 0, 0), instances=None, ibl=None, two_level=False,
+                 instance_ids=None):
         self.two_level = two_level  # SELAS_SCENE_TWO_LEVEL_BVH: per-mesh object-space trees under a top-level tree over the instances
         self.ibl = ibl  # dict: light (H,W,3), marginal (H,), conditional (H,W), miss (h,w,3), rotation, exposure_scale -- see scenes.build_ibl
         self.meshes = []
@@ -359,6 +361,8 @@ class SceneData:
         self.light_sets = np.array(light_sets, dtype=np.uint32).reshape(-1, 2)
         self.background = tuple(float(x) for x in background)
         self.instances = instances  # list of (meshIndex, 4x4) or None
+        # per instance (instID0, instID1, geomID): the reference's two instancing levels as hits report them (SELAS_SCENE_INSTANCE_IDS), or None
+        self.instance_ids = instance_ids
 
     def triangle_count(self):
         return sum(m["indices"].shape[0] * (2 if m["indices"].shape[1] == 4 else 1) for m in self.meshes)
@@ -392,6 +396,8 @@ class SceneData:
             for i, (mi, mat) in enumerate(self.instances):
                 inst[i].meshIndex = mi
                 inst[i].localToWorld[:] = list(np.asarray(mat, dtype=np.float32).reshape(16))
+                ids = self.instance_ids[i] if self.instance_ids is not None else (i, 0, mi)
+                inst[i].instID0, inst[i].instID1, inst[i].geomID = (int(x) for x in ids)
             desc.instances = inst
             desc.instanceCount = len(self.instances)
             keep.append(inst)
@@ -402,7 +408,7 @@ class SceneData:
         desc.lightSets = C.cast(self.light_sets.ctypes.data, C.POINTER(LightSetRange))
         desc.lightSetCount = self.light_sets.shape[0]
         desc.backgroundIntensity[:] = self.background
-        desc.flags = SCENE_TWO_LEVEL_BVH if getattr(self, "two_level", False) else 0
+        desc.flags = (SCENE_TWO_LEVEL_BVH if getattr(self, "two_level", False) else 0) | (SCENE_INSTANCE_IDS if self.instance_ids is not None else 0)
         if self.ibl is not None:
             i = self.ibl
             for k in ("light", "marginal", "conditional", "miss"):

@@ -267,6 +267,18 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
             inst[i].identity = memcmp(inst[i].m, I, sizeof(I)) == 0 ? 1u : 0u;
             inst[i].pad[0] = inst[i].pad[1] = 0;
         }
+        if (d->flags & SELAS_SCENE_INSTANCE_IDS) {  // the reference's two instancing levels as the ids public hits report
+            std::vector<uint4> ids(d->instanceCount);
+            for (uint32_t i = 0; i < d->instanceCount; ++i) {
+                const SelasInstanceDesc& in = d->instances[i];
+                ids[i] = make_uint4(in.instID0, in.instID1, in.geomID, 0u);
+                if (!scene->instanceIdLookup.emplace(std::array<uint32_t, 3>{in.instID0, in.instID1, in.geomID}, i).second) {
+                    setError(ctx, "instance %u repeats the ids (instID0 %u, instID1 %u, geomID %u) of an earlier instance", i, in.instID0, in.instID1, in.geomID);
+                    return SELAS_ERR_ARGUMENT;  // (the guard above releases the scene)
+                }
+            }
+            SELAS_TRY(sceneUpload(scene, &scene->gpu.instanceIds, ids.data(), ids.size()));
+        }
     } else if (d->flags & SELAS_SCENE_TWO_LEVEL_BVH) {  // one identity instance per mesh, instID0 = mesh index
         inst.resize(d->meshCount ? d->meshCount : 1);
         for (uint32_t i = 0; i < inst.size(); ++i) {
@@ -746,10 +758,32 @@ int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays,
         setError(ctx, "selas_cuda_surface_params: null argument");
         return SELAS_ERR_ARGUMENT;
     }
-    for (size_t i = 0; i < n; ++i) {  // ModelDataFromRayIds asserts these in the reference (SceneResource.cpp:362-378)
+    // ModelDataFromRayIds (SceneResource.cpp:362-378): the hit's ids name the instance and the mesh.  A SELAS_SCENE_INSTANCE_IDS scene
+    // reports the reference's (instID[0], instID[1], geomID); they are resolved to the flat instance and its mesh here.
+    std::vector<SelasHit> resolved;
+    const bool publicIds = !scene->instanceIdLookup.empty();
+    if (publicIds) resolved.assign(hits, hits + n);
+    std::vector<uint32_t> meshOfInstance;
+    if (publicIds) {
+        meshOfInstance.resize(scene->gpu.instanceCount);
+        std::vector<InstanceGpu> tmp(scene->gpu.instanceCount);
+        SELAS_CUDA_CHECK(ctx, cudaMemcpy(tmp.data(), scene->gpu.instances, sizeof(InstanceGpu) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < tmp.size(); ++k) meshOfInstance[k] = tmp[k].mesh;
+    }
+    for (size_t i = 0; i < n; ++i) {
         const SelasHit& h = hits[i];
         if (h.geomID == SELAS_INVALID_ID) continue;
-        if (h.geomID >= scene->gpu.meshCount || h.instID0 >= scene->gpu.instanceCount) {
+        if (publicIds) {
+            auto it = scene->instanceIdLookup.find(std::array<uint32_t, 3>{h.instID0, h.instID1, h.geomID});
+            if (it == scene->instanceIdLookup.end()) {
+                setError(ctx, "selas_cuda_surface_params: hit %zu names (instID0 %u, instID1 %u, geomID %u), which no instance of the scene reports", i,
+                         h.instID0, h.instID1, h.geomID);
+                return SELAS_ERR_ARGUMENT;
+            }
+            resolved[i].instID0 = it->second;
+            resolved[i].instID1 = 0;
+            resolved[i].geomID = meshOfInstance[it->second];
+        } else if (h.geomID >= scene->gpu.meshCount || h.instID0 >= scene->gpu.instanceCount) {
             setError(ctx, "selas_cuda_surface_params: hit %zu names geomID %u / instID %u outside the scene", i, h.geomID, h.instID0);
             return SELAS_ERR_ARGUMENT;
         }
@@ -759,7 +793,7 @@ int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays,
     SelasHit* d_h;
     SelasSurface* d_o;
     SELAS_TRY(s.upload(&d_r, rays, n));
-    SELAS_TRY(s.upload(&d_h, hits, n));
+    SELAS_TRY(s.upload(&d_h, publicIds ? resolved.data() : hits, n));
     SELAS_TRY(s.alloc(&d_o, n));
     SELAS_TRY(launchSurfaceParams(scene, n, d_r, d_h, d_o));
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(SelasSurface), cudaMemcpyDeviceToHost, ctx->stream));

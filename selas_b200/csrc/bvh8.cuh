@@ -35,6 +35,9 @@ struct Bvh8 {
     // the first topCount nodes (whole levels of the tree, breadth first: the collapse numbers nodes level by level) are staged in
     // shared memory by every CTA of the trace kernels; 0 = none
     uint32_t topCount;
+    // public entry points of a SELAS_SCENE_INSTANCE_IDS scene: per flat instance the {instID0, instID1, geomID} a hit reports (the
+    // reference's two instancing levels); null inside the wavefront, whose queues keep {flat instance, mesh index}
+    const uint4* instanceIds;
 };
 
 #ifndef SELAS_STACK_SIZE
@@ -229,7 +232,12 @@ SELAS_D void writeHit(const Bvh8& bvh, const TraceResult& r, float tfar, SelasHi
         bool second = (c.w >> 31) != 0;
         float u = second ? 1.0f - r.u : r.u, v = second ? 1.0f - r.v : r.v;
         h0 = make_uint4(__float_as_uint(r.t), __float_as_uint(u), __float_as_uint(v), a.w);
-        h1 = make_uint4(b.w, INST ? r.inst : (c.w & 0x7fffffffu), 0u, 0u);
+        const uint32_t flat = INST ? r.inst : (c.w & 0x7fffffffu);
+        h1 = make_uint4(b.w, flat, 0u, 0u);
+        if (bvh.instanceIds) {  // SceneInstanceIntersectFunction: instID[0] = subscene instance, instID[1] = the subscene hit's instID[0]
+            const uint4 ids = __ldg(bvh.instanceIds + flat);
+            h1 = make_uint4(ids.z, ids.x, ids.y, 0u);
+        }
         if (ng) {
             V3 n = cross(v3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)),
                          v3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z)));

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <array>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -66,6 +68,7 @@ struct SceneGpu {
     const float4* tris;
     uint32_t nodeCount, triCount;
     const InstanceTrace* traceInstances;  // null: one flattened world-space BVH8
+    const uint4* instanceIds;             // SELAS_SCENE_INSTANCE_IDS: per flat instance {instID0, instID1, geomID, -} the public hits report
     const MeshGpu* meshes;
     const InstanceGpu* instances;
     const SelasMaterial* materials;
@@ -106,6 +109,8 @@ struct SelasScene {
     SelasBvhStats stats{};
     bool usesPtex = false;  // any mesh carries a Ptex texture: selects the shade kernel built with the lookup
     uint32_t topNodeCount = 0;  // leading BVH8 nodes (whole levels) the trace kernels stage in shared memory
+    // SELAS_SCENE_INSTANCE_IDS: reported (instID0, instID1, geomID) -> flat instance index, for hits handed back to selas_cuda_surface_params
+    std::map<std::array<uint32_t, 3>, uint32_t> instanceIdLookup;
     // wavefront scratch, grown on demand
     void* wf = nullptr;
     void* vcm = nullptr;  // VCM scratch (vcm.cu), grown on demand

@@ -608,8 +608,9 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
     return SELAS_OK;
 }
 
-static Bvh8 bvhOf(const SelasScene* s) {
+static Bvh8 bvhOf(const SelasScene* s, bool publicIds = false) {
     Bvh8 b;
+    b.instanceIds = publicIds ? s->gpu.instanceIds : nullptr;
     b.nodes = s->gpu.nodes;
     b.tris = s->gpu.tris;
     b.nodeCount = s->gpu.nodeCount;
@@ -660,9 +661,9 @@ int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, Selas
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
     if (d_counts)
-        SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(0, true, bvhOf(scene, true), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
-        SELAS_TRACE_GO(0, false, bvhOf(scene), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, nullptr, nullptr, nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(0, false, bvhOf(scene, true), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, nullptr, nullptr, nullptr, d_rayCounter, nullptr);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }

@@ -287,6 +287,67 @@ void InitializeRayCastCamera(const CameraSettings& settings, uint32_t width, uin
     selas_cuda_camera_init(&st, width, height, &camera);
 }
 
+// SceneResource::aaBox / boundingSphere from the meshes and the instance list (no device work).
+void CalculateSceneBoundingBox(SceneResource* scene) {
+    // SceneResource::aaBox / boundingSphere (SceneResource.h:77-78), CalculateSceneBoundingBox (SceneResource.cpp:194-203): every
+    // instance contributes the eight corners of its mesh's object-space box taken through localToWorld (IncludeBox,
+    // AxisAlignedBox.cpp:44-65: tmin + combinations of the transformed edge vectors).  Scenes without an instance list are one
+    // identity instance over all meshes: the raw vertices.
+    float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    std::vector<float> meshBox(scene->meshes.size() * 6);
+    for (size_t mi = 0; mi < scene->meshes.size(); ++mi) {
+        const SceneMesh& m = scene->meshes[mi];
+        float* b = &meshBox[mi * 6];
+        for (int k = 0; k < 3; ++k) { b[k] = 3.402823466e+38f; b[3 + k] = -3.402823466e+38f; }
+        for (size_t v = 0; v + 2 < m.positions.size(); v += 3)
+            for (int k = 0; k < 3; ++k) {
+                b[k] = std::min(b[k], m.positions[v + k]);
+                b[3 + k] = std::max(b[3 + k], m.positions[v + k]);
+            }
+    }
+    auto includePoint = [&](const float* p) {
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], p[k]);
+            hi[k] = std::max(hi[k], p[k]);
+        }
+    };
+    if (scene->instances.empty()) {
+        for (size_t mi = 0; mi < scene->meshes.size(); ++mi)
+            if (meshBox[mi * 6] <= meshBox[mi * 6 + 3]) {
+                includePoint(&meshBox[mi * 6]);
+                includePoint(&meshBox[mi * 6 + 3]);
+            }
+    } else {
+        for (const SelasInstanceDesc& inst : scene->instances) {
+            if (inst.meshIndex >= scene->meshes.size()) continue;
+            const float* b = &meshBox[(size_t)inst.meshIndex * 6];
+            if (!(b[0] <= b[3])) continue;  // empty mesh
+            const float* M = inst.localToWorld;  // row-major, row vectors, translation in row 3
+            float tmin[3], e[3][3];
+            for (int c = 0; c < 3; ++c) {
+                tmin[c] = b[0] * M[0 + c] + b[1] * M[4 + c] + b[2] * M[8 + c] + M[12 + c];
+                for (int a = 0; a < 3; ++a) e[a][c] = (b[3 + a] - b[a]) * M[4 * a + c];
+            }
+            for (int corner = 0; corner < 8; ++corner) {
+                float p[3];
+                for (int c = 0; c < 3; ++c)
+                    p[c] = tmin[c] + ((corner & 1) ? e[0][c] : 0.0f) + ((corner & 2) ? e[1][c] : 0.0f) + ((corner & 4) ? e[2][c] : 0.0f);
+                includePoint(p);
+            }
+        }
+    }
+    if (!(lo[0] <= hi[0]))
+        for (int k = 0; k < 3; ++k) lo[k] = hi[k] = 0.0f;
+    double diag2 = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        scene->aaBox[k] = lo[k];
+        scene->aaBox[3 + k] = hi[k];
+        scene->boundingSphere[k] = (float)(0.5 * ((double)lo[k] + (double)hi[k]));
+        diag2 += ((double)hi[k] - (double)lo[k]) * ((double)hi[k] - (double)lo[k]);
+    }
+    scene->boundingSphere[3] = (float)(0.5 * sqrt(diag2));
+}
+
 Error InitializeSceneResource(SceneResource* scene, int device) {
     if (selas_cuda_context_create(device, &scene->gpu) != SELAS_OK) return Error_("%s", selas_cuda_last_error(nullptr));
     // TextureCache::LoadTexturePtex (TextureCache.cpp:99-126) for the meshes that name a Ptex file: one texture per distinct path
@@ -327,23 +388,7 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
         d.ptex = meshPtex[i];
         d.baseColorTexture = m.baseColorTexture;
     }
-    // SceneResource::aaBox / boundingSphere (SceneResource.h:77-78): the instances' boxes in the reference (SceneResource.cpp:196-201);
-    // here the vertices of the identity-instanced meshes
-    float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-    for (const SceneMesh& m : scene->meshes)
-        for (size_t v = 0; v + 2 < m.positions.size(); v += 3)
-            for (int k = 0; k < 3; ++k) {
-                lo[k] = std::min(lo[k], m.positions[v + k]);
-                hi[k] = std::max(hi[k], m.positions[v + k]);
-            }
-    double diag2 = 0.0;
-    for (int k = 0; k < 3; ++k) {
-        scene->aaBox[k] = lo[k];
-        scene->aaBox[3 + k] = hi[k];
-        scene->boundingSphere[k] = (float)(0.5 * ((double)lo[k] + (double)hi[k]));
-        diag2 += ((double)hi[k] - (double)lo[k]) * ((double)hi[k] - (double)lo[k]);
-    }
-    scene->boundingSphere[3] = (float)(0.5 * sqrt(diag2));
+    CalculateSceneBoundingBox(scene);
     SelasSceneDesc desc;
     memset(&desc, 0, sizeof(desc));
     desc.meshes = meshes.data();
@@ -927,21 +972,29 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
         }
     }
     // flatten the two instancing levels (InitializeModelInstances, SubsceneResource.cpp:63-79; scene level, SceneResource.cpp:218-249)
-    for (const BakedInstance& si : bs.subsceneInstances) {
+    // Both levels stay visible in what a hit reports (SELAS_SCENE_INSTANCE_IDS): instID0 = subscene instance, instID1 = model instance
+    // inside the subscene, geomID = mesh inside the model -- the triple ModelDataFromRayIds takes (SceneResource.cpp:362-378).
+    for (size_t sIdx = 0; sIdx < bs.subsceneInstances.size(); ++sIdx) {
+        const BakedInstance& si = bs.subsceneInstances[sIdx];
         if (si.index >= subs.size()) return Error_("LoadBakedScene: subscene instance refers to subscene %llu of %zu", (unsigned long long)si.index, subs.size());
         const BakedSubscene& sub = subs[si.index];
-        for (const BakedInstance& mi : sub.modelInstances) {
+        for (size_t mIdx = 0; mIdx < sub.modelInstances.size(); ++mIdx) {
+            const BakedInstance& mi = sub.modelInstances[mIdx];
             if (mi.index >= meshRange[si.index].size()) return Error_("LoadBakedScene: model instance refers to model %llu of %zu", (unsigned long long)mi.index,
                                                                       meshRange[si.index].size());
             const ModelMeshes& range = meshRange[si.index][mi.index];
             SelasInstanceDesc inst;
             multiply44(mi.localToWorld, si.localToWorld, inst.localToWorld);
+            inst.instID0 = (uint32_t)sIdx;
+            inst.instID1 = (uint32_t)mIdx;
             for (uint32_t m = 0; m < range.count; ++m) {
                 inst.meshIndex = range.first + m;
+                inst.geomID = m;
                 scene->instances.push_back(inst);
             }
         }
     }
+    scene->flags |= SELAS_SCENE_INSTANCE_IDS;
     // geometry exists in the scene only through instances: without any, nothing is there to hit (an empty instance list would otherwise
     // mean "every mesh once" to selas_cuda_scene_create)
     if (scene->instances.empty()) scene->meshes.clear();
@@ -1113,7 +1166,38 @@ int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_
         if (instanceMatrices) memcpy(instanceMatrices + 16 * i, scene.instances[i].localToWorld, 64);
         if (instanceMesh) instanceMesh[i] = scene.instances[i].meshIndex;
     }
+    if (counts8) counts8[7] |= (uint64_t)((scene.flags & SELAS_SCENE_INSTANCE_IDS) ? 1 : 0) << 62;
     if (materials && !scene.materials.empty()) memcpy(materials, scene.materials.data(), scene.materials.size() * sizeof(SelasMaterial));
+    Selas::ShutdownSceneResource(&scene);
+    return SELAS_OK;
+}
+int selas_host_baked_scene_instance_ids(const char* root, const char* sceneName, uint32_t* ids3, uint64_t capacity, char* errorOut, int errorCapacity) {
+    Selas::SceneResource scene;
+    Selas::ImageBasedLight ibl;
+    Selas::Error e = Selas::LoadBakedScene(root, sceneName, &scene, &ibl, nullptr);
+    if (e.Failed()) {
+        if (errorOut && errorCapacity > 0) snprintf(errorOut, errorCapacity, "%s", e.Message());
+        return SELAS_ERR_FORMAT;
+    }
+    for (size_t i = 0; i < scene.instances.size() && i < capacity; ++i) {
+        ids3[3 * i] = scene.instances[i].instID0;
+        ids3[3 * i + 1] = scene.instances[i].instID1;
+        ids3[3 * i + 2] = scene.instances[i].geomID;
+    }
+    Selas::ShutdownSceneResource(&scene);
+    return SELAS_OK;
+}
+int selas_host_baked_scene_bounds(const char* root, const char* sceneName, float* aabb6, float* sphere4, char* errorOut, int errorCapacity) {
+    Selas::SceneResource scene;
+    Selas::ImageBasedLight ibl;
+    Selas::Error e = Selas::LoadBakedScene(root, sceneName, &scene, &ibl, nullptr);
+    if (e.Failed()) {
+        if (errorOut && errorCapacity > 0) snprintf(errorOut, errorCapacity, "%s", e.Message());
+        return SELAS_ERR_FORMAT;
+    }
+    Selas::CalculateSceneBoundingBox(&scene);
+    if (aabb6) memcpy(aabb6, scene.aaBox, sizeof(scene.aaBox));
+    if (sphere4) memcpy(sphere4, scene.boundingSphere, sizeof(scene.boundingSphere));
     Selas::ShutdownSceneResource(&scene);
     return SELAS_OK;
 }

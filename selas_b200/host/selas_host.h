@@ -108,6 +108,7 @@ struct SceneResource {
     SelasContext* gpu = nullptr;
     SelasScene* gpuScene = nullptr;
 };
+void CalculateSceneBoundingBox(SceneResource* scene);
 Error InitializeSceneResource(SceneResource* scene, int device);  // context + upload + BVH8 build
 void ShutdownSceneResource(SceneResource* scene);
 void MakeCornellBoxScene(SceneResource* scene, float copperRoughness);  // BASELINE config 1
@@ -266,6 +267,10 @@ int selas_host_read_ibl_blob(const char* path, uint32_t* info4, float* params2, 
 int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_t* counts8, float* instanceMatrices, uint32_t* instanceMesh,
                                 void* materials, char* errorOut, int errorCapacity);
 // Loads the baked scene, builds it on `device` and renders with PathTracer settings through the C ABI; film = layerCount planes of w*h*3
+/* SceneResource::aaBox / boundingSphere of a baked scene (CalculateSceneBoundingBox, SceneResource.cpp:194-203): no device needed. */
+/* (instID0, instID1, geomID) per flattened instance: the reference's two instancing levels as hits report them. */
+int selas_host_baked_scene_instance_ids(const char* root, const char* sceneName, uint32_t* ids3, uint64_t capacity, char* errorOut, int errorCapacity);
+int selas_host_baked_scene_bounds(const char* root, const char* sceneName, float* aabb6, float* sphere4, char* errorOut, int errorCapacity);
 int selas_host_render_baked_scene(const char* root, const char* sceneName, int device, const SelasCamera* camera, const SelasRenderSettings* settings,
                                   float* film, char* errorOut, int errorCapacity);
 // info = {mipCount, format, width0, height0}; texels0 receives level 0 (width0 * height0 * (format + 1) floats) when not null

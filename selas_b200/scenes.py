@@ -358,8 +358,12 @@ def disney_heightfield(grid=2236, patch=64, seed=3, spheres=9, sphere_res=(50, 1
     return capi.SceneData(meshes, mats, lights, [(0, 4)], background=(0.5, 0.7, 1.0, 0.0))
 
 
+HEIGHTFIELD_CAMERA = dict(position=(0.0, 7.0, -16.0), look_at=(0.0, -0.5, 0.0), up=(0.0, 1.0, 0.0), fov=50.0)
+
+
 def heightfield_camera(width=1920, height=1080):
-    return capi.camera_init((0.0, 7.0, -16.0), (0.0, -0.5, 0.0), (0.0, 1.0, 0.0), 50.0, width, height)
+    c = HEIGHTFIELD_CAMERA
+    return capi.camera_init(c["position"], c["look_at"], c["up"], c["fov"], width, height)
 
 
 # ---- C4: Ptex-textured quad grid ---------------------------------------------------------------------------------
@@ -473,7 +477,20 @@ def caustic_camera(width=1920, height=1080):
 def bounding_sphere(data):
     """SceneResource::boundingSphere as {centre of the scene's AABB, half its diagonal} (the reference declares the field,
     SceneResource.h:78, and reads it in AreaLighting.cpp:274-275 / VCM.cpp:778; the baker's value is not in the tree)."""
-    lo = np.min([m["positions"].min(axis=0) for m in data.meshes], axis=0).astype(np.float64)
-    hi = np.max([m["positions"].max(axis=0) for m in data.meshes], axis=0).astype(np.float64)
+    if getattr(data, "instances", None):
+        # CalculateSceneBoundingBox (SceneResource.cpp:194-203): each instance's object-space box through its localToWorld (IncludeBox)
+        pts = []
+        for mi, mat in data.instances:
+            p = np.asarray(data.meshes[mi]["positions"], np.float64)
+            if p.size == 0:
+                continue
+            blo, bhi = p.min(axis=0), p.max(axis=0)
+            corners = np.array([[bhi[0] if c & 1 else blo[0], bhi[1] if c & 2 else blo[1], bhi[2] if c & 4 else blo[2], 1.0] for c in range(8)])
+            pts.append((corners @ np.asarray(mat, np.float64).reshape(4, 4))[:, :3])
+        pts = np.concatenate(pts, axis=0)
+        lo, hi = pts.min(axis=0), pts.max(axis=0)
+    else:
+        lo = np.min([m["positions"].min(axis=0) for m in data.meshes], axis=0).astype(np.float64)
+        hi = np.max([m["positions"].max(axis=0) for m in data.meshes], axis=0).astype(np.float64)
     c = 0.5 * (lo + hi)
     return (float(c[0]), float(c[1]), float(c[2]), float(0.5 * np.linalg.norm(hi - lo)))

@@ -170,7 +170,7 @@ def write_baked(ref, root, scene):
     assert rc == 0
 
 
-def expected_flat_scene(scene):
+def expected_flat_scene(scene, with_ids=False):
     """What LoadBakedScene must build: meshes in subscene -> model -> mesh order with FindMeshMaterial-resolved materials, and the two
     instancing levels flattened (localToWorld = model * subscene)."""
     meshes, materials, ranges = [], [], []
@@ -213,11 +213,13 @@ def expected_flat_scene(scene):
                 meshes.append(d)
             sub_ranges.append((first, len(model["meshes"])))
         ranges.append(sub_ranges)
-    instances = []
-    for si, ms in scene["instances"]:
-        for mi, mm in scene["subscenes"][si]["instances"]:
+    instances, ids = [], []
+    for s_idx, (si, ms) in enumerate(scene["instances"]):
+        for m_idx, (mi, mm) in enumerate(scene["subscenes"][si]["instances"]):
             first, count = ranges[si][mi]
             m = mul44(mm, ms)
             instances += [(first + k, m) for k in range(count)]
+            # what a hit reports in the reference: instID[0] = subscene instance, instID[1] = model instance, geomID = mesh inside the model
+            ids += [(s_idx, m_idx, k) for k in range(count)]
     return capi.SceneData(meshes, np.array(materials), scene["lights"], scene["light_sets"], background=scene["background"], instances=instances,
-                          ibl=scene["ibl"])
+                          ibl=scene["ibl"], instance_ids=ids if with_ids else None)

@@ -217,7 +217,7 @@ def test_baked_scene_from_the_reference_serializer(host, ref, tmp_path):
     counts, mats, mesh, materials = _load_baked(host, tmp_path, scene["name"])
     assert counts[0] == len(want.meshes) == 4 and counts[1] == len(want.instances) == 12 and counts[3] == 3 and counts[4] == 1 and counts[5] == 1
     assert counts[6] == sum(want.meshes[i]["indices"].shape[0] * (2 if want.meshes[i]["indices"].shape[1] == 4 else 1) for i, _ in want.instances)
-    assert counts[7] == (1 | (1 << 8) | (1 << 32))  # IBL, one distinct texture ("checker"), one textured mesh
+    assert (counts[7] & ((1 << 62) - 1)) == (1 | (1 << 8) | (1 << 32)) and counts[7] >> 62 == 1  # IBL, one distinct texture ("checker"), one textured mesh
     np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])
     np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))  # bit-exact: same float32 summation order
     assert materials.tobytes() == want.materials.tobytes()
@@ -324,7 +324,7 @@ def test_baked_scene_golden(host):
     scene = baked.small_two_level_scene()
     want = baked.expected_flat_scene(scene)
     counts, mats, mesh, materials = _load_baked(host, GOLDEN / "baked_scene", scene["name"])
-    assert counts[:6] == [4, 12, len(want.materials), 3, 1, 1] and counts[7] == (1 | (1 << 8) | (1 << 32))
+    assert counts[:6] == [4, 12, len(want.materials), 3, 1, 1] and (counts[7] & ((1 << 62) - 1)) == (1 | (1 << 8) | (1 << 32)) and counts[7] >> 62 == 1
     np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])
     np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))
     assert materials.tobytes() == want.materials.tobytes()
@@ -342,3 +342,89 @@ def test_selas_render_baked_scene(host, tmp_path):
     assert stats["image"] == "main" and stats["paths"] == 96 * 64 * 16 and stats["occlusion_rays"] > 0
     img = read_hdr(tmp_path / "_Images" / "main_0.hdr")
     assert img.shape == (64, 96, 3) and np.isfinite(img).all() and img.mean() > 0.01
+
+
+def test_baked_scene_bounds_follow_the_instance_transforms(host):
+    """SceneResource::aaBox / boundingSphere (CalculateSceneBoundingBox, SceneResource.cpp:194-203): every instance's object-space box
+    through its localToWorld, not the raw mesh vertices -- the VCM integrator sizes its emission disc and merge radius with this sphere
+    (VCM.cpp:778, AreaLighting.cpp:274-275).  The committed two-level scene instances its meshes with translations / rotations / scales."""
+    from tests import baked
+
+    scene = baked.small_two_level_scene()
+    want = baked.expected_flat_scene(scene)
+    aabb, sphere = np.zeros(6, np.float32), np.zeros(4, np.float32)
+    err = C.create_string_buffer(512)
+    rc = host.selas_host_baked_scene_bounds(str(GOLDEN / "baked_scene").encode() + b"/", scene["name"].encode(), aabb.ctypes.data_as(C.c_void_p),
+                                            sphere.ctypes.data_as(C.c_void_p), err, 512)
+    assert rc == 0, err.value
+    # IncludeBox on every instance: the eight corners of the mesh's box through the instance matrix
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    raw_lo, raw_hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for mi, mat in want.instances:
+        p = np.asarray(want.meshes[mi]["positions"], np.float64)
+        blo, bhi = p.min(axis=0), p.max(axis=0)
+        raw_lo, raw_hi = np.minimum(raw_lo, blo), np.maximum(raw_hi, bhi)
+        corners = np.array([[bhi[0] if c & 1 else blo[0], bhi[1] if c & 2 else blo[1], bhi[2] if c & 4 else blo[2], 1.0] for c in range(8)])
+        w = (corners @ np.asarray(mat, np.float64).reshape(4, 4))[:, :3]
+        lo, hi = np.minimum(lo, w.min(axis=0)), np.maximum(hi, w.max(axis=0))
+    np.testing.assert_allclose(aabb[:3], lo, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(aabb[3:], hi, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sphere[:3], 0.5 * (lo + hi), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sphere[3], 0.5 * np.linalg.norm(hi - lo), rtol=1e-5)
+    assert np.abs(np.concatenate([lo - raw_lo, hi - raw_hi])).max() > 0.1  # the transforms matter in this scene
+    np.testing.assert_allclose(scenes.bounding_sphere(want), sphere, rtol=1e-5, atol=1e-5)
+    # every world-space vertex lies inside
+    for mi, mat in want.instances:
+        p = np.asarray(want.meshes[mi]["positions"], np.float64)
+        w = (np.concatenate([p, np.ones((len(p), 1))], axis=1) @ np.asarray(mat, np.float64).reshape(4, 4))[:, :3]
+        assert (w >= aabb[:3] - 1e-4).all() and (w <= aabb[3:] + 1e-4).all()
+
+
+def test_baked_scene_keeps_both_instance_levels(host):
+    """LoadBakedScene names every flattened instance by the reference's triple: instID[0] = subscene instance (SceneResource.cpp:135),
+    instID[1] = model instance inside the subscene (:136), geomID = mesh inside the model -- what ModelDataFromRayIds takes (:362-378)."""
+    from tests import baked
+
+    scene = baked.small_two_level_scene()
+    want = baked.expected_flat_scene(scene, with_ids=True)
+    ids = np.zeros((len(want.instances), 3), np.uint32)
+    err = C.create_string_buffer(512)
+    rc = host.selas_host_baked_scene_instance_ids(str(GOLDEN / "baked_scene").encode() + b"/", scene["name"].encode(), ids.ctypes.data_as(C.c_void_p),
+                                                  C.c_uint64(len(ids)), err, 512)
+    assert rc == 0, err.value
+    np.testing.assert_array_equal(ids, np.array(want.instance_ids, np.uint32))
+    assert len({tuple(r) for r in ids}) == len(ids) and ids[:, 0].max() > 0 and ids[:, 1].max() > 0
+
+
+@pytest.mark.gpu
+def test_hits_report_both_instance_levels(ctx, oracle):
+    """SELAS_SCENE_INSTANCE_IDS: the same rays against the same flattened / two-level scene with and without the id table -- geometry
+    identical, ids translated (instID0 = subscene instance, instID1 = model instance, geomID = mesh in model); the hits go back into
+    selas_cuda_surface_params unchanged, like HitParameters into ModelDataFromRayIds."""
+    from tests import baked, inputs
+
+    scene = baked.small_two_level_scene()
+    plain, named = baked.expected_flat_scene(scene), baked.expected_flat_scene(scene, with_ids=True)
+    table = np.array(named.instance_ids, np.uint32)
+    rays = inputs.scene_rays(77, 40000, radius=9.0)
+    for two_level in (False, True):
+        plain.two_level = named.two_level = two_level
+        a, b = capi.Scene(ctx, plain), capi.Scene(ctx, named)
+        ha, hb = a.intersect(rays), b.intersect(rays)
+        hit = ha["geomID"] != capi.SELAS_INVALID_ID
+        assert hit.mean() > 0.2 and np.array_equal(hit, hb["geomID"] != capi.SELAS_INVALID_ID)
+        for f in ("t", "u", "v", "primID"):
+            np.testing.assert_array_equal(ha[f], hb[f])
+        flat = ha["instID0"][hit]
+        np.testing.assert_array_equal(hb["instID0"][hit], table[flat, 0])
+        np.testing.assert_array_equal(hb["instID1"][hit], table[flat, 1])
+        np.testing.assert_array_equal(hb["geomID"][hit], table[flat, 2])
+        assert len(np.unique(hb["instID0"][hit])) > 1 and len(np.unique(hb["instID1"][hit])) > 1
+        sa, sb = a.surface_params(rays, ha), b.surface_params(rays, hb)
+        assert sa.tobytes() == sb.tobytes()
+        bad = hb[hit][:1].copy()
+        bad["instID1"] = 99
+        with pytest.raises(capi.SelasError):
+            b.surface_params(rays[hit][:1], bad)
+        a.close()
+        b.close()
