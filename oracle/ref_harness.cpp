@@ -85,7 +85,6 @@ Error ReadWholeFile(cpointer, void**, uint64*) { return Error_("oracle harness: 
 namespace Directory {
 void EnsureDirectoryExists(const char*) {}
 }
-Error StbImageWrite(cpointer, uint, uint, uint, StbImageFormats, void*) { return Error_("oracle harness: no image IO"); }
 // CSampler with a scriptable stream (MathLib/Sampler.cpp is not linked).
 void CSampler::Initialize(uint32 seed) {
     if (!g_mt) g_mt = new std::mt19937();
@@ -874,6 +873,11 @@ int ref_write_texture_blob(const SelasTextureDesc* t, const char* path) {
     int rc = writeFile(path, blob, blobSize);
     SelasAlignedFree(blob);
     return rc;
+}
+// FrameBuffer_Save's writer: StbImageWrite(..., HDR, ...) = stbi_write_hdr (TextureLib/StbImage.cpp:64-87 + Middleware/stb, unmodified)
+int ref_write_hdr(const char* path, uint32_t width, uint32_t height, const float* rgb) {
+    Error e = StbImageWrite(path, width, height, 3, HDR, const_cast<float*>(rgb));
+    return e.Failed() ? 1 : 0;
 }
 unsigned long long ref_asset_version(const char* type) {
     if (!strcmp(type, "IBL")) return ImageBasedLightResource::kDataVersion;

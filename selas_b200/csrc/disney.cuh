@@ -106,8 +106,11 @@ static SELAS_HDN V3 sampleVndf(V3 wo, float ax, float ay, float u1, float u2) { 
     float a = 1.0f / (1.0f + v.y);
     float r = sqrtf(u1);
     float phi = (u2 < a) ? (u2 / a) * SELAS_PI : SELAS_PI + (u2 - a) / (1.0f - a) * SELAS_PI;
-    float p1 = r * cosf(phi);
-    float p2 = r * sinf(phi) * ((u2 < a) ? 1.0f : v.y);
+    // sin / cos of the disc angle in double, rounded once: glibc's sinf / cosf (what the reference links) are correctly rounded in
+    // practice, CUDA's are within 2 ulp -- and for small u1 this sampler turns a 1-ulp difference of p1 / p2 into a jump of a whole
+    // float32 quantum of the result (1.5e-5 in wi, up to 6e-4 in the pdf: tests/test_gpu_parity.py::test_bsdf_sample_parity)
+    float p1 = r * (float)cos((double)phi);
+    float p2 = r * (float)sin((double)phi) * ((u2 < a) ? 1.0f : v.y);
     V3 n = p1 * t1 + p2 * t2 + sqrtf(maxf_(0.0f, 1.0f - p1 * p1 - p2 * p2)) * v;
     return normalize(v3(ax * n.x, n.y, ay * n.z));
 }
@@ -307,7 +310,7 @@ SELAS_HD bool sampleDisney(Rng& rng, const Surface& s, const DisneyFrame& f, V3 
         float cosT = sqrtf(maxf_(0.f, (1.0f - powf(a2, 1.0f - r0)) / (1.0f - a2)));
         float sinT = sqrtf(maxf_(0.f, 1.0f - cosT * cosT));
         float phi = SELAS_TWO_PI * r1;
-        V3 wm = v3(sinT * cosf(phi), cosT, sinT * sinf(phi));
+        V3 wm = v3(sinT * (float)cos((double)phi), cosT, sinT * (float)sin((double)phi));  // rounded once, like sampleVndf
         if (dot(wm, wo) < 0.0f) wm = -wm;
         V3 wi = reflect_(wm, wo);
         if (dot(wi, wo) < 0.0f) {
@@ -332,7 +335,7 @@ SELAS_HD bool sampleDisney(Rng& rng, const Surface& s, const DisneyFrame& f, V3 
         float r0 = rng.next(), r1 = rng.next();
         float r = sqrtf(r0);
         float theta = SELAS_TWO_PI * r1;
-        V3 wi = sign * v3(r * cosf(theta), sqrtf(maxf_(0.0f, 1 - r0)), r * sinf(theta));
+        V3 wi = sign * v3(r * (float)cos((double)theta), sqrtf(maxf_(0.0f, 1 - r0)), r * (float)sin((double)theta));  // rounded once
         V3 wm = normalize(wi + wo);
         float dotNL = cosTheta(wi);
         if (dotNL == 0.0f) {

@@ -231,30 +231,73 @@ void FrameBuffer_Scale(Framebuffer* frame, float scale) {  // Framebuffer.cpp:62
         }
 }
 
-// Radiance RGBE, flat (non-RLE) scanlines: "#?RADIANCE", FORMAT=32-bit_rle_rgbe, "-Y h +X w".
+// Radiance RGBE as FrameBuffer_Save's writer produces it (StbImageWrite(..., HDR, ...) = stbi_write_hdr, TextureLib/StbImage.cpp:76-78):
+// the same header lines, pixels as (mantissa r g b, shared exponent + 128) truncated -- not rounded -- from frexp of the largest channel,
+// black below 1e-32; scanlines of 8 <= width < 32768 in the format's adaptive run-length form (2 2 hi lo, then the four components one
+// after the other: literal chunks of <= 128 bytes, runs of >= 3 equal bytes as (128 + n <= 255, value)), others flat.  tests/test_host.py
+// compares the files byte for byte with the reference writer's.
+static void rgbeOf(const float3& p, unsigned char* o) {
+    const float r = p.x, g = p.y, b = p.z;
+    const float m = r > g ? (r > b ? r : b) : (g > b ? g : b);
+    if (!(m >= 1e-32f)) {
+        o[0] = o[1] = o[2] = o[3] = 0;
+        return;
+    }
+    int e;
+    const float norm = frexpf(m, &e) * 256.0f / m;
+    o[0] = (unsigned char)(r * norm);
+    o[1] = (unsigned char)(g * norm);
+    o[2] = (unsigned char)(b * norm);
+    o[3] = (unsigned char)(e + 128);
+}
+
+static void rleComponent(const unsigned char* c, uint32_t w, std::vector<unsigned char>& out) {
+    uint32_t x = 0;
+    while (x < w) {
+        uint32_t r = x;  // start of the next run of three equal bytes, or w
+        while (r + 2 < w && !(c[r] == c[r + 1] && c[r] == c[r + 2])) ++r;
+        if (r + 2 >= w) r = w;
+        while (x < r) {  // literals up to the run
+            const uint32_t n = std::min<uint32_t>(128, r - x);
+            out.push_back((unsigned char)n);
+            out.insert(out.end(), c + x, c + x + n);
+            x += n;
+        }
+        if (r + 2 < w) {  // the run itself
+            while (r < w && c[r] == c[x]) ++r;
+            while (x < r) {
+                const uint32_t n = std::min<uint32_t>(127, r - x);
+                out.push_back((unsigned char)(128 + n));
+                out.push_back(c[x]);
+                x += n;
+            }
+        }
+    }
+}
+
 Error WriteRadianceHdr(const char* path, uint32_t width, uint32_t height, const float3* pixels) {
     FILE* fp = fopen(path, "wb");
     if (!fp) return Error_("Failed to open %s for writing", path);
-    fprintf(fp, "#?RADIANCE\n# Written by selas-b200\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n-Y %u +X %u\n", height, width);
-    std::vector<unsigned char> row((size_t)width * 4);
+    // the header the reference's files carry (stb's comment line included, so the two writers' files compare equal)
+    fprintf(fp, "#?RADIANCE\n# Written by stb_image_write.h\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y %u +X %u\n", height, width);
+    std::vector<unsigned char> row((size_t)width * 4), planes((size_t)width * 4), out;
+    const bool rle = width >= 8 && width < 32768;
     for (uint32_t y = 0; y < height; ++y) {
-        for (uint32_t x = 0; x < width; ++x) {
-            const float3& p = pixels[(size_t)y * width + x];
-            float r = p.x > 0.f ? p.x : 0.f, g = p.y > 0.f ? p.y : 0.f, b = p.z > 0.f ? p.z : 0.f;
-            float m = r > g ? (r > b ? r : b) : (g > b ? g : b);
-            unsigned char* o = &row[(size_t)x * 4];
-            if (!(m >= 1e-32f) || !std::isfinite(m)) {
-                o[0] = o[1] = o[2] = o[3] = 0;
-            } else {
-                int e;
-                float norm = frexpf(m, &e) * 256.0f / m;
-                o[0] = (unsigned char)(r * norm);
-                o[1] = (unsigned char)(g * norm);
-                o[2] = (unsigned char)(b * norm);
-                o[3] = (unsigned char)(e + 128);
+        for (uint32_t x = 0; x < width; ++x) rgbeOf(pixels[(size_t)y * width + x], &row[(size_t)x * 4]);
+        out.clear();
+        if (rle) {
+            out.push_back(2);
+            out.push_back(2);
+            out.push_back((unsigned char)(width >> 8));
+            out.push_back((unsigned char)(width & 0xff));
+            for (int c = 0; c < 4; ++c) {
+                for (uint32_t x = 0; x < width; ++x) planes[(size_t)c * width + x] = row[(size_t)x * 4 + c];
+                rleComponent(&planes[(size_t)c * width], width, out);
             }
+        } else {
+            out = row;
         }
-        if (fwrite(row.data(), 1, row.size(), fp) != row.size()) {
+        if (fwrite(out.data(), 1, out.size(), fp) != out.size()) {
             fclose(fp);
             return Error_("short write on %s", path);
         }

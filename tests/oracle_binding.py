@@ -343,6 +343,12 @@ class Ref(ShadingOracle):
         rc = self.fn("write_texture_blob")(C.byref(td), str(path).encode())
         assert rc == 0, rc
 
+    def write_hdr(self, path, rgb):
+        """FrameBuffer_Save's writer: the reference's StbImageWrite(..., HDR, ...) = stbi_write_hdr, unmodified."""
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        rc = self.lib.ref_write_hdr(str(path).encode(), C.c_uint32(rgb.shape[1]), C.c_uint32(rgb.shape[0]), _ptr(rgb))
+        assert rc == 0, rc
+
     def asset_version(self, type_name):
         f = self.lib.ref_asset_version
         f.restype = C.c_ulonglong
