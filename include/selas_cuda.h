@@ -155,7 +155,8 @@ typedef struct SelasHit {
     uint32_t geomID;
     uint32_t instID0;
     uint32_t instID1;
-    uint32_t pad;
+    uint32_t pad;   /* 0 for triangles and quads; for a hit on a curve geometry the piece of the segment that was hit (csrc/curve.cuh), which
+                       selas_cuda_surface_params needs to rebuild the surface normal: hand hits back as they were returned */
 } SelasHit;
 
 /* TextureResourceData (TextureLib/TextureResource.h:15-39), level 0 only: the path samples mip 0 with the bilinear "Triangle" filter
@@ -185,6 +186,21 @@ typedef struct SelasMeshDesc {
                                                  material's constant baseColor (SurfaceParameters.cpp:209-214); sampled at the
                                                  interpolated uvs (0,0 without a uv buffer), sRGB -> linear, then pow 2.2 */
 } SelasMeshDesc;
+
+/* One curve geometry = one Embree RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE (ModelResource.cpp:300-333): control vertices {x, y, z, radius}
+ * (RTC_FORMAT_FLOAT4) and, per segment, the index of its first control vertex (four consecutive vertices make a uniform cubic B-spline
+ * segment).  The surface is the sweep of a circle of the interpolated radius along the curve; hits report u = parameter along the
+ * segment, v = 0, primID = segment, and Ng = the unnormalised surface normal (RTC_GEOMETRY_TYPE_CURVE.3embree3).  Curve geometries
+ * are numbered after the meshes: geomID = meshCount + index (the reference attaches a model's curves after its meshes,
+ * ModelResource.cpp:461-466), and SelasInstanceDesc.meshIndex may name one.  No attribute buffers, no textures (ModelResource.cpp:371-389). */
+typedef struct SelasCurveDesc {
+    const float*    vertices;      /* float4 per control vertex */
+    uint32_t        vertexCount;
+    const uint32_t* indices;       /* first control vertex of each segment; indices[i] + 3 < vertexCount */
+    uint32_t        segmentCount;
+    uint32_t        materialIndex;
+    uint32_t        lightSetIndex;
+} SelasCurveDesc;
 
 /* Instance of a mesh; localToWorld is a row-major row-vector 4x4 (translation in row 3). */
 typedef struct SelasInstanceDesc {
@@ -227,7 +243,8 @@ typedef struct SelasSceneDesc {
     float                     backgroundIntensity[4]; /* SceneResourceData::backgroundIntensity */
     const SelasIblDesc*       ibl;           /* SceneResource::iblResource, or NULL: constant background (AreaLighting.cpp:415-437) */
     uint32_t                  flags;         /* SELAS_SCENE_* */
-    uint32_t                  reserved;
+    uint32_t                  curveCount;
+    const SelasCurveDesc*     curves;        /* curve geometries, geomID = meshCount + index; NULL/0: none */
 } SelasSceneDesc;
 /* SelasSceneDesc.flags.  SELAS_SCENE_TWO_LEVEL_BVH: keep instanced geometry once -- one object-space BVH8 per mesh under a top-level BVH8
  * over the instances, rays transformed into object space on entry (what the reference gets from Embree instance geometries and its

@@ -34,6 +34,10 @@ struct Tri {
 struct RayHit {
     double t, u, v;
     uint32_t tri;  // index into tris, 0xFFFFFFFF = miss
+    // a hit on a curve segment (orc_curves.h; set by the scene-level trace of selas_oracle.cpp): index into the scene's segment list,
+    // and the unnormalised surface normal there
+    uint32_t curve = 0xFFFFFFFFu;
+    double ng[3] = {0.0, 0.0, 0.0};
 };
 
 template <typename Real>

@@ -53,7 +53,7 @@ static bool vcmRayPick(const Scene& sc, V3 o, V3 d, SelasRay& ray, SelasHit& h, 
     float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
     RayHit rh;
     ++ctr.closest;
-    bool hit = sc.bvh.trace<float>(oo, dd, ray.tnear, ray.tfar, false, rh);
+    bool hit = sc.trace<float>(oo, dd, ray.tnear, ray.tfar, false, rh);
     hitToRecord(sc, rh, ray, h, nullptr);
     return hit;
 }
@@ -63,7 +63,7 @@ static bool vcmOcclusionRay(const Scene& sc, const SelasSurface& surf, V3 direct
     float so[3] = {org.x, org.y, org.z}, sd[3] = {direction.x, direction.y, direction.z};
     RayHit sh;
     ++ctr.shadow;
-    return !sc.bvh.trace<float>(so, sd, surf.error, distance, true, sh);
+    return !sc.trace<float>(so, sd, surf.error, distance, true, sh);
 }
 // VcOcclusionRay, VCM.cpp:95-120
 static bool vcmVcOcclusionRay(const Scene& sc, const SelasSurface& surf, V3 direction, float distance, VcmCounters& ctr) {
@@ -72,7 +72,7 @@ static bool vcmVcOcclusionRay(const Scene& sc, const SelasSurface& surf, V3 dire
     float so[3] = {org.x, org.y, org.z}, sd[3] = {direction.x, direction.y, direction.z};
     RayHit sh;
     ++ctr.shadow;
-    return !sc.bvh.trace<float>(so, sd, surf.error, distance - 16.0f * absf(bias), true, sh);
+    return !sc.trace<float>(so, sd, surf.error, distance - 16.0f * absf(bias), true, sh);
 }
 
 // SampleBsdfScattering, VCM.cpp:412-446

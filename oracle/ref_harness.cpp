@@ -337,7 +337,7 @@ int ref_ibl_sample(void* s, size_t n, const float* u2, float* thetaPhiPdf3, uint
 
 // ---- tier-B CPU integrator: reference shading + restated ray cast --------------------------------------------
 int ref_scene_create(const SelasSceneDesc* d, void** out) {
-    if (d->instanceCount) return 5;  // the tier-B integrator handles the identity single-instance scenes only
+    if (d->instanceCount || d->curveCount) return 5;  // the tier-B integrator handles identity single-instance triangle / quad scenes only
     for (uint32_t m = 0; m < d->meshCount; ++m)
         if (d->meshes[m].baseColorTexture) return 5;  // refSurface has no texture fetch (the lookup itself is pinned by ref_texture_sample)
     RefScene* sc = new RefScene();

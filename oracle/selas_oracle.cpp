@@ -25,6 +25,7 @@
 #include <pmmintrin.h>
 
 #include "cpu_bvh.h"
+#include "orc_curves.h"
 #include "orc_shading.h"
 
 using namespace orc;
@@ -56,6 +57,27 @@ struct Scene {
     Ibl ibl;
     std::vector<float> iblMarginal, iblConditional, iblLight, iblMiss;
     Bvh bvh;
+    // curve geometries ride in `meshes` after the triangle meshes (indicesPerFace = 1: positions = float4 control vertices, indices =
+    // first control vertex per segment); their flattened world-space segments are tested exhaustively (orc_curves.h)
+    std::vector<orc::CurveSeg> curves;
+
+    // scene-level trace: the triangle BVH, then the curve segments in front of what it found.  Real = float reproduces the timed CPU
+    // path of the integrators, double is the hit-ID oracle; brute = exhaustive over the triangles too.
+    template <typename Real>
+    bool trace(const float o[3], const float d[3], float tnear, float tfar, bool anyHit, RayHit& out, bool brute = false) const {
+        bool hit = brute ? bvh.brute(o, d, tnear, tfar, out) : bvh.trace<Real>(o, d, tnear, tfar, anyHit, out);
+        if (curves.empty() || (hit && anyHit)) return hit;
+        uint32_t seg = 0;
+        orc::CurveHitD ch = {};
+        if (orc::traceCurves(curves, o, d, tnear, hit ? out.t : (double)tfar, anyHit, seg, ch)) {
+            out.t = ch.t; out.u = ch.u; out.v = 0.0;
+            out.tri = 0xFFFFFFFEu;
+            out.curve = seg;
+            for (int k = 0; k < 3; ++k) out.ng[k] = ch.ng[k];
+            return true;
+        }
+        return hit;
+    }
 };
 
 // Product RNG contract (DESIGN.md "Random numbers"): PCG-RXS-M-XS-32 stream per (seed, pixel, sample).
@@ -126,6 +148,19 @@ static void hitToRecord(const Scene& sc, const RayHit& h, const SelasRay& r, Sel
         if (Ng4) Ng4[0] = Ng4[1] = Ng4[2] = Ng4[3] = 0.f;
         return;
     }
+    if (h.curve != 0xFFFFFFFFu) {  // round curve: u along the segment, v = 0, Ng = surface normal (RTC_GEOMETRY_TYPE_CURVE.3embree3)
+        const orc::CurveSeg& S = sc.curves[h.curve];
+        out.t = (float)h.t;
+        out.u = (float)h.u;
+        out.v = 0.f;
+        out.primID = S.primID;
+        out.geomID = S.geomID;
+        out.instID0 = S.instID;
+        out.instID1 = 0;
+        out.pad = 0;
+        if (Ng4) { Ng4[0] = (float)h.ng[0]; Ng4[1] = (float)h.ng[1]; Ng4[2] = (float)h.ng[2]; Ng4[3] = 0.f; }
+        return;
+    }
     const Tri& T = sc.bvh.tris[h.tri];
     out.t = (float)h.t;
     out.u = T.second ? (float)(1.0 - h.u) : (float)h.u;
@@ -147,6 +182,7 @@ static void surfaceParams(const Scene& sc, const SelasRay& r, const SelasHit& h,
     const Mesh& mesh = sc.meshes[h.geomID];
     const Instance& inst = sc.instances[h.instID0];
     const SelasMaterial& mat = sc.materials[mesh.materialIndex];
+    const bool isCurve = mesh.indicesPerFace == 1;
     const uint32_t* idx = &mesh.indices[(size_t)h.primID * mesh.indicesPerFace];
     float u = h.u, v = h.v;
 
@@ -166,7 +202,18 @@ static void surfaceParams(const Scene& sc, const SelasRay& r, const SelasHit& h,
     };
 
     V3 normal;
-    if (!mesh.normals.empty()) {
+    if (isCurve) {
+        // hit->normal = Embree's Ng of a round curve = the surface normal; recovered by intersecting the segment again around the hit
+        normal = v3(0.0f, 1.0f, 0.0f);
+        for (const orc::CurveSeg& S : sc.curves) {
+            if (S.geomID != h.geomID || S.primID != h.primID || S.instID != h.instID0) continue;
+            const double o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
+            const double slack = 1e-3 * std::fabs((double)h.t) + 4.0 * std::fabs(S.c[1][3]) + 1e-6;
+            orc::CurveHitD ch;
+            if (orc::intersectCurveD(S, o, d, (double)h.t - slack, (double)h.t + slack, ch)) normal = v3((float)ch.ng[0], (float)ch.ng[1], (float)ch.ng[2]);
+            break;
+        }
+    } else if (!mesh.normals.empty()) {
         float nn[3];
         interp3(mesh.normals, 3, nn);
         normal = mulVec44(v3(nn), inst.m);
@@ -185,7 +232,7 @@ static void surfaceParams(const Scene& sc, const SelasRay& r, const SelasHit& h,
     }
     V3 n = normalize(normal);
     V3 t, b;
-    if (!mesh.tangents.empty()) {
+    if (!mesh.tangents.empty() && !isCurve) {
         float tt[4];
         interp3(mesh.tangents, 4, tt);
         t = mulVec44(v3(tt), inst.m);
@@ -203,7 +250,7 @@ static void surfaceParams(const Scene& sc, const SelasRay& r, const SelasHit& h,
         float rgb[3] = {0.0f, 0.0f, 0.0f};
         mesh.ptexEval(mesh.ptexUser, (int)h.primID, u, v, rgb);
         base = v3(rgb);
-    } else if (mesh.texture.texels) {  // SurfaceParameters.cpp:186-190, :209-214
+    } else if (mesh.texture.texels && !isCurve) {  // SurfaceParameters.cpp:186-190, :209-214
         float uv[2] = {0.0f, 0.0f};
         if (!mesh.uvs.empty()) interp3(mesh.uvs, 2, uv);
         base = sampleTextureFloat3(mesh.texture, uv[0], uv[1], true);
@@ -293,7 +340,7 @@ static void evaluatePath(const Scene& sc, const SelasCamera& cam, const SelasRen
         ray.tfar = rayDistance;
         RayHit rh;
         float o[3] = {ray.ox, ray.oy, ray.oz}, d[3] = {ray.dx, ray.dy, ray.dz};
-        bool hit = sc.bvh.trace<float>(o, d, 0.0f, rayDistance, false, rh);
+        bool hit = sc.trace<float>(o, d, 0.0f, rayDistance, false, rh);
         ++closest;
         SelasHit h;
         hitToRecord(sc, rh, ray, h, nullptr);
@@ -325,7 +372,7 @@ static void evaluatePath(const Scene& sc, const SelasCamera& cam, const SelasRen
                     float so[3] = {org.x, org.y, org.z};
                     RayHit sh;
                     ++shadow;
-                    bool occ = sc.bvh.trace<float>(so, ls.direction, surf.error, ls.distance, true, sh);
+                    bool occ = sc.trace<float>(so, ls.direction, surf.error, ls.distance, true, sh);
                     if (!occ) {
                         V3 smp = refl * v3(ls.radiance) * (1.0f / ls.pdfW);
                         Ld[1] = Ld[1] + smp * throughput;
@@ -409,14 +456,14 @@ static void evaluatePathDeferred(const Scene& sc, const SelasCamera& cam, const 
         float so[3] = {org.x, org.y, org.z}, sd[3] = {d.x, d.y, d.z};
         RayHit sh;
         ++shadow;
-        return sc.bvh.trace<float>(so, sd, 0.0f, distance, true, sh);  // ray.tnear = 0, :262
+        return sc.trace<float>(so, sd, 0.0f, distance, true, sh);  // ray.tnear = 0, :262
     };
     while (bounce < rs.maxPathLength) {
         ray.tnear = 0.0f;
         ray.tfar = kFloatMax;
         RayHit rh;
         float o[3] = {ray.ox, ray.oy, ray.oz}, d[3] = {ray.dx, ray.dy, ray.dz};
-        bool hit = sc.bvh.trace<float>(o, d, 0.0f, kFloatMax, false, rh);
+        bool hit = sc.trace<float>(o, d, 0.0f, kFloatMax, false, rh);
         ++closest;
         if (!hit) {  // :198-207
             V3 smp = v3(sc.background);
@@ -529,6 +576,17 @@ int orc_scene_create(const SelasSceneDesc* d, void** out) {
         M.materialIndex = md.materialIndex;
         M.lightSetIndex = md.lightSetIndex;
     }
+    for (uint32_t c = 0; c < d->curveCount; ++c) {  // curve geometries: geomID = meshCount + c
+        const SelasCurveDesc& cd = d->curves[c];
+        Mesh M;
+        M.positions.assign(cd.vertices, cd.vertices + 4 * (size_t)cd.vertexCount);
+        M.indices.assign(cd.indices, cd.indices + cd.segmentCount);
+        M.faceCount = cd.segmentCount;
+        M.indicesPerFace = 1;
+        M.materialIndex = cd.materialIndex;
+        M.lightSetIndex = cd.lightSetIndex;
+        sc->meshes.push_back(M);
+    }
     if (d->instanceCount) {
         for (uint32_t i = 0; i < d->instanceCount; ++i) {
             Instance in;
@@ -565,6 +623,29 @@ int orc_scene_create(const SelasSceneDesc* d, void** out) {
             if (in.mesh != 0xFFFFFFFFu && in.mesh != m) continue;
             const Mesh& M = sc->meshes[m];
             bool identity = in.mesh == 0xFFFFFFFFu;
+            if (M.indicesPerFace == 1) {  // curve geometry: world-space control vertices, radius scaled by the transform's cube-root volume change
+                const double det = identity ? 1.0
+                                            : (double)in.m[0] * ((double)in.m[5] * in.m[10] - (double)in.m[6] * in.m[9]) -
+                                                  (double)in.m[1] * ((double)in.m[4] * in.m[10] - (double)in.m[6] * in.m[8]) +
+                                                  (double)in.m[2] * ((double)in.m[4] * in.m[9] - (double)in.m[5] * in.m[8]);
+                const double rscale = std::cbrt(std::fabs(det));
+                for (uint32_t f = 0; f < M.faceCount; ++f) {
+                    orc::CurveSeg S;
+                    for (int k = 0; k < 4; ++k) {
+                        const float* cv = &M.positions[4 * (size_t)(M.indices[f] + k)];
+                        double p[3] = {cv[0], cv[1], cv[2]};
+                        if (!identity) {
+                            const double x = p[0], y = p[1], z = p[2];
+                            for (int a = 0; a < 3; ++a) p[a] = x * in.m[a] + y * in.m[4 + a] + z * in.m[8 + a] + in.m[12 + a];
+                        }
+                        S.c[k][0] = p[0]; S.c[k][1] = p[1]; S.c[k][2] = p[2]; S.c[k][3] = cv[3] * rscale;
+                    }
+                    S.primID = f; S.geomID = m; S.instID = ii;
+                    orc::curveBounds(S);
+                    sc->curves.push_back(S);
+                }
+                continue;
+            }
             auto P = [&](uint32_t vi) {
                 V3 p = v3(&M.positions[3 * (size_t)vi]);
                 return identity ? p : mulPoint44(p, in.m);
@@ -656,9 +737,9 @@ int orc_intersect(void* s, size_t n, const SelasRay* rays, SelasHit* hits, float
             const SelasRay& r = rays[i];
             float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
             RayHit h;
-            if (mode == 0) sc.bvh.trace<float>(o, d, r.tnear, r.tfar, false, h);
-            else if (mode == 1) sc.bvh.trace<double>(o, d, r.tnear, r.tfar, false, h);
-            else sc.bvh.brute(o, d, r.tnear, r.tfar, h);
+            if (mode == 0) sc.trace<float>(o, d, r.tnear, r.tfar, false, h);
+            else if (mode == 1) sc.trace<double>(o, d, r.tnear, r.tfar, false, h);
+            else sc.trace<double>(o, d, r.tnear, r.tfar, false, h, true);
             hitToRecord(sc, h, r, hits[i], Ng4 ? Ng4 + 4 * i : nullptr);
         }
     });
@@ -672,9 +753,9 @@ int orc_occluded(void* s, size_t n, const SelasRay* rays, uint8_t* occluded, int
             float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
             RayHit h;
             bool hit;
-            if (mode == 0) hit = sc.bvh.trace<float>(o, d, r.tnear, r.tfar, true, h);
-            else if (mode == 1) hit = sc.bvh.trace<double>(o, d, r.tnear, r.tfar, true, h);
-            else hit = sc.bvh.brute(o, d, r.tnear, r.tfar, h);
+            if (mode == 0) hit = sc.trace<float>(o, d, r.tnear, r.tfar, true, h);
+            else if (mode == 1) hit = sc.trace<double>(o, d, r.tnear, r.tfar, true, h);
+            else hit = sc.trace<double>(o, d, r.tnear, r.tfar, true, h, true);
             occluded[i] = hit ? 1 : 0;
         }
     });

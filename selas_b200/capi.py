@@ -71,11 +71,17 @@ class IblDesc(C.Structure):
                 ("rotationRadians", f32), ("exposureScale", f32)]
 
 
+class CurveDesc(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("vertexCount", u32), ("indices", C.c_void_p), ("segmentCount", u32), ("materialIndex", u32),
+                ("lightSetIndex", u32)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("meshes", C.POINTER(MeshDesc)), ("meshCount", u32), ("instances", C.POINTER(InstanceDesc)),
                 ("instanceCount", u32), ("materials", C.POINTER(Material)), ("materialCount", u32),
                 ("lights", C.POINTER(Light)), ("lightCount", u32), ("lightSets", C.POINTER(LightSetRange)),
-                ("lightSetCount", u32), ("backgroundIntensity", f32 * 4), ("ibl", C.POINTER(IblDesc)), ("flags", u32), ("reserved", u32)]
+                ("lightSetCount", u32), ("backgroundIntensity", f32 * 4), ("ibl", C.POINTER(IblDesc)), ("flags", u32), ("curveCount", u32),
+                ("curves", C.POINTER(CurveDesc))]
 
 
 class RenderSettings(C.Structure):
@@ -336,7 +342,7 @@ class SceneData:
     """
 
     def __init__(self, meshes, materials, lights=None, light_sets=None, background=(0, 0, 0, 0), instances=None, ibl=None, two_level=False,
-                 instance_ids=None):
+                 instance_ids=None, curves=None):
         self.two_level = two_level  # SELAS_SCENE_TWO_LEVEL_BVH: per-mesh object-space trees under a top-level tree over the instances
         self.ibl = ibl  # dict: light (H,W,3), marginal (H,), conditional (H,W), miss (h,w,3), rotation, exposure_scale -- see scenes.build_ibl
         self.meshes = []
@@ -363,6 +369,12 @@ class SceneData:
         self.instances = instances  # list of (meshIndex, 4x4) or None
         # per instance (instID0, instID1, geomID): the reference's two instancing levels as hits report them (SELAS_SCENE_INSTANCE_IDS), or None
         self.instance_ids = instance_ids
+        # curve geometries (RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE): dicts with vertices (n, 4) float32 {x, y, z, radius}, indices (first
+        # control vertex per segment), material, lightSet; their geomID = len(meshes) + position in this list
+        self.curves = [dict(c) for c in (curves or [])]
+        for c in self.curves:
+            c["vertices"] = np.ascontiguousarray(c["vertices"], np.float32).reshape(-1, 4)
+            c["indices"] = np.ascontiguousarray(c["indices"], np.uint32).reshape(-1)
 
     def triangle_count(self):
         return sum(m["indices"].shape[0] * (2 if m["indices"].shape[1] == 4 else 1) for m in self.meshes)
@@ -391,6 +403,14 @@ class SceneData:
         desc = SceneDesc()
         desc.meshes = md
         desc.meshCount = len(self.meshes)
+        if self.curves:
+            cd = (CurveDesc * len(self.curves))()
+            for i, c in enumerate(self.curves):
+                cd[i].vertices, cd[i].vertexCount = c["vertices"].ctypes.data, c["vertices"].shape[0]
+                cd[i].indices, cd[i].segmentCount = c["indices"].ctypes.data, c["indices"].size
+                cd[i].materialIndex, cd[i].lightSetIndex = int(c.get("material", 0)), int(c.get("lightSet", 0))
+            desc.curves, desc.curveCount = cd, len(self.curves)
+            keep.append(cd)
         if self.instances:
             inst = (InstanceDesc * len(self.instances))()
             for i, (mi, mat) in enumerate(self.instances):

@@ -200,10 +200,26 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
             }
     }
     for (uint32_t i = 0; i < d->instanceCount; ++i)
-        if (d->instances[i].meshIndex >= d->meshCount) {
-            setError(ctx, "instance %u: meshIndex %u out of range", i, d->instances[i].meshIndex);
+        if (d->instances[i].meshIndex >= d->meshCount + d->curveCount) {
+            setError(ctx, "instance %u: meshIndex %u out of range (%u meshes + %u curve geometries)", i, d->instances[i].meshIndex, d->meshCount, d->curveCount);
             return SELAS_ERR_ARGUMENT;
         }
+    if (d->curveCount && !d->curves) {
+        setError(ctx, "selas_cuda_scene_create: curveCount %u with a null curves pointer", d->curveCount);
+        return SELAS_ERR_ARGUMENT;
+    }
+    for (uint32_t c = 0; c < d->curveCount; ++c) {
+        const SelasCurveDesc& cd = d->curves[c];
+        if (cd.materialIndex >= d->materialCount || (cd.segmentCount && (!cd.vertices || !cd.indices))) {
+            setError(ctx, "curve geometry %u: material %u out of range or null buffers", c, cd.materialIndex);
+            return SELAS_ERR_ARGUMENT;
+        }
+        for (uint32_t k = 0; k < cd.segmentCount; ++k)
+            if ((uint64_t)cd.indices[k] + 3 >= cd.vertexCount) {
+                setError(ctx, "curve geometry %u: segment %u starts at control vertex %u of %u (it needs four)", c, k, cd.indices[k], cd.vertexCount);
+                return SELAS_ERR_ARGUMENT;
+            }
+    }
     for (uint32_t i = 0; i < d->lightSetCount; ++i)
         if ((uint64_t)d->lightSets[i].start + d->lightSets[i].count > d->lightCount) {
             setError(ctx, "light set %u: range [%u, +%u) exceeds %u lights", i, d->lightSets[i].start, d->lightSets[i].count, d->lightCount);
@@ -257,6 +273,21 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
         g.materialIndex = md.materialIndex;
         g.lightSetIndex = md.lightSetIndex;
     }
+    // curve geometries ride in the mesh table after the meshes (indicesPerFace = 1: positions = float4 control vertices, indices = first
+    // control vertex per segment), so instances, materials, light sets and the hit ids treat them like any other geometry
+    for (uint32_t c = 0; c < d->curveCount; ++c) {
+        const SelasCurveDesc& cd = d->curves[c];
+        MeshGpu g;
+        memset(&g, 0, sizeof(g));
+        SELAS_TRY(sceneUpload(scene, &g.positions, cd.vertices, 4 * (size_t)cd.vertexCount));
+        SELAS_TRY(sceneUpload(scene, &g.indices, cd.indices, (size_t)cd.segmentCount));
+        g.faceCount = cd.segmentCount;
+        g.indicesPerFace = 1;
+        g.materialIndex = cd.materialIndex;
+        g.lightSetIndex = cd.lightSetIndex;
+        meshes.push_back(g);
+    }
+    const uint32_t geometryCount = (uint32_t)meshes.size();
     std::vector<InstanceGpu> inst;
     if (d->instanceCount) {
         inst.resize(d->instanceCount);
@@ -280,11 +311,11 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
             SELAS_TRY(sceneUpload(scene, &scene->gpu.instanceIds, ids.data(), ids.size()));
         }
     } else if (d->flags & SELAS_SCENE_TWO_LEVEL_BVH) {  // one identity instance per mesh, instID0 = mesh index
-        inst.resize(d->meshCount ? d->meshCount : 1);
+        inst.resize(geometryCount ? geometryCount : 1);
         for (uint32_t i = 0; i < inst.size(); ++i) {
             memset(&inst[i], 0, sizeof(InstanceGpu));
             inst[i].m[0] = inst[i].m[5] = inst[i].m[10] = inst[i].m[15] = 1.0f;
-            inst[i].mesh = d->meshCount ? i : 0xFFFFFFFFu;
+            inst[i].mesh = geometryCount ? i : 0xFFFFFFFFu;
             inst[i].identity = 1;
         }
     } else {  // every mesh once, identity, instID0 = 0
@@ -300,7 +331,7 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
     SELAS_TRY(sceneUpload(scene, &g.materials, d->materials, d->materialCount));
     SELAS_TRY(sceneUpload(scene, &g.lights, d->lights, d->lightCount));
     SELAS_TRY(sceneUpload(scene, &g.lightSets, d->lightSets, d->lightSetCount));
-    g.meshCount = d->meshCount;
+    g.meshCount = geometryCount;  // meshes, then curve geometries
     g.instanceCount = (uint32_t)inst.size();
     g.materialCount = d->materialCount;
     g.lightCount = d->lightCount;
@@ -324,7 +355,7 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
         g.ibl.present = 1;
     }
 
-    if ((d->flags & SELAS_SCENE_TWO_LEVEL_BVH) && d->meshCount)
+    if ((d->flags & SELAS_SCENE_TWO_LEVEL_BVH) && geometryCount)
         SELAS_TRY(buildBvhTwoLevel(scene, meshes, inst));
     else
         SELAS_TRY(buildBvh(scene, meshes, inst, g.instances));

@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 
 #include "../../include/selas_cuda.h"
+#include "curve.cuh"
 #include "vec.cuh"
 
 namespace selas {
@@ -38,7 +39,11 @@ struct Bvh8 {
     // public entry points of a SELAS_SCENE_INSTANCE_IDS scene: per flat instance the {instID0, instID1, geomID} a hit reports (the
     // reference's two instancing levels); null inside the wavefront, whose queues keep {flat instance, mesh index}
     const uint4* instanceIds;
+    // curve pool: four float4 control vertices {x, y, z, radius} per curve segment of the tree (world space for the flattened form,
+    // object space under the two-level form); a leaf record with bit 30 of its third id word set names its entry in a.x
+    const float4* curves;
 };
+constexpr uint32_t kLeafCurveFlag = 1u << 30;
 
 #ifndef SELAS_STACK_SIZE
 #define SELAS_STACK_SIZE 48
@@ -57,6 +62,9 @@ struct TraceResult {
     float t, u, v;
     uint32_t tri;   // index into tris, 0xFFFFFFFF = none
     uint32_t inst;  // two-level form: flat instance index of the hit (the triangle record's own instID is 0 there)
+    // curve hits (kernels built with CURVES): element code of curve.cuh and the unnormalised surface normal; element == 0: a triangle
+    uint32_t element;
+    V3 ng;
 };
 
 // Quantised plane byte -> float without the conversion (XU) pipe.  The first version used (float)byte = I2F.U8, 48 per
@@ -230,17 +238,22 @@ SELAS_D void writeHit(const Bvh8& bvh, const TraceResult& r, float tfar, SelasHi
         const uint4* tp = reinterpret_cast<const uint4*>(bvh.tris + (size_t)r.tri * 3);
         uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         bool second = (c.w >> 31) != 0;
+        const bool curve = (c.w & kLeafCurveFlag) != 0;
         float u = second ? 1.0f - r.u : r.u, v = second ? 1.0f - r.v : r.v;
         h0 = make_uint4(__float_as_uint(r.t), __float_as_uint(u), __float_as_uint(v), a.w);
-        const uint32_t flat = INST ? r.inst : (c.w & 0x7fffffffu);
-        h1 = make_uint4(b.w, flat, 0u, 0u);
+        const uint32_t flat = INST ? r.inst : (c.w & 0x3fffffffu);
+        // round curves report v = 0 (RTC_GEOMETRY_TYPE_CURVE.3embree3); the last word carries the element that was hit, so that the
+        // shading stage rebuilds the normal exactly (curve.cuh); it is 0 for triangles
+        h1 = make_uint4(b.w, flat, 0u, curve ? r.element : 0u);
+        if (curve) h0.z = 0u;
         if (bvh.instanceIds) {  // SceneInstanceIntersectFunction: instID[0] = subscene instance, instID[1] = the subscene hit's instID[0]
             const uint4 ids = __ldg(bvh.instanceIds + flat);
-            h1 = make_uint4(ids.z, ids.x, ids.y, 0u);
+            h1 = make_uint4(ids.z, ids.x, ids.y, h1.w);
         }
         if (ng) {
-            V3 n = cross(v3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)),
-                         v3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z)));
+            V3 n = curve ? r.ng
+                         : cross(v3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z)),
+                                 v3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z)));
             *ng = make_float4(n.x, n.y, n.z, 0.f);
         }
     }

@@ -26,8 +26,21 @@ struct MeshDev {
 };
 
 struct BuildTri {  // 48 bytes: raw world-space vertices + ids
-    float4 a, b, c;  // a.w = primID, b.w = geomID, c.w = instID | second<<31
+    float4 a, b, c;  // a.w = primID, b.w = geomID, c.w = instID | curve << 30 | second << 31
 };
+constexpr uint32_t kPrimCurveFlag = 1u << 30;  // the record is a curve segment: a = box min, b = box max, c.x = index into the curve pool
+
+// bounds of a build record: the three vertices of a triangle, or the stored box of a curve segment
+SELAS_D void primBounds(const BuildTri& t, float* lo, float* hi) {
+    if (__float_as_uint(t.c.w) & kPrimCurveFlag) {
+        lo[0] = t.a.x; lo[1] = t.a.y; lo[2] = t.a.z;
+        hi[0] = t.b.x; hi[1] = t.b.y; hi[2] = t.b.z;
+    } else {
+        lo[0] = fminf(t.a.x, fminf(t.b.x, t.c.x)); hi[0] = fmaxf(t.a.x, fmaxf(t.b.x, t.c.x));
+        lo[1] = fminf(t.a.y, fminf(t.b.y, t.c.y)); hi[1] = fmaxf(t.a.y, fmaxf(t.b.y, t.c.y));
+        lo[2] = fminf(t.a.z, fminf(t.b.z, t.c.z)); hi[2] = fmaxf(t.a.z, fmaxf(t.b.z, t.c.z));
+    }
+}
 
 SELAS_D uint32_t floatFlip(float f) {  // order-preserving float -> uint
     uint32_t u = __float_as_uint(f);
@@ -90,6 +103,70 @@ __global__ void gatherTrianglesKernel(MeshDev mesh, const float* __restrict__ xf
     }
 }
 
+// Curve segments of one curve geometry (MeshDev.indicesPerFace == 1: positions = float4 control vertices, indices = first vertex of each
+// segment): the four control vertices go through the instance transform into the curve pool (radius scaled by the cube root of the
+// transform's volume change), and the build record carries the box of the segment's Bezier hull grown by its largest radius.
+__global__ void gatherCurvesKernel(MeshDev mesh, const float* __restrict__ xform, bool identity, uint32_t geomID, uint32_t instID,
+                                   BuildTri* __restrict__ out, uint32_t outBase, float4* __restrict__ pool, uint32_t poolBase,
+                                   uint32_t* __restrict__ bounds) {
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {SELAS_FLOAT_MAX, SELAS_FLOAT_MAX, SELAS_FLOAT_MAX}, hi[3] = {-SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX, -SELAS_FLOAT_MAX};
+    if (f < mesh.faceCount) {
+        const float4* cv = reinterpret_cast<const float4*>(mesh.positions) + mesh.indices[f];
+        float m[16];
+        float rscale = 1.0f;
+        if (!identity) {
+            for (int k = 0; k < 16; ++k) m[k] = xform[k];
+            const float det = m[0] * (m[5] * m[10] - m[6] * m[9]) - m[1] * (m[4] * m[10] - m[6] * m[8]) + m[2] * (m[4] * m[9] - m[5] * m[8]);
+            rscale = cbrtf(fabsf(det));
+        }
+        float4 c[4];
+        for (int k = 0; k < 4; ++k) {
+            const float4 p = cv[k];
+            V3 q = v3(p.x, p.y, p.z);
+            if (!identity) q = mulPoint44(q, m);
+            c[k] = make_float4(q.x, q.y, q.z, p.w * rscale);
+            pool[4 * (size_t)(poolBase + f) + k] = c[k];
+        }
+        // Bezier hull of the uniform B-spline segment
+        float4 b[4];
+        for (int a = 0; a < 4; ++a) {
+            const float w0 = a == 0 ? 1.f : 0.f, w1 = a == 0 ? 4.f : (a == 1 ? 4.f : (a == 2 ? 2.f : 1.f)),
+                        w2 = a == 0 ? 1.f : (a == 1 ? 2.f : (a == 2 ? 4.f : 4.f)), w3 = a == 3 ? 1.f : 0.f;
+            b[a] = make_float4((w0 * c[0].x + w1 * c[1].x + w2 * c[2].x + w3 * c[3].x) * (1.f / 6.f), (w0 * c[0].y + w1 * c[1].y + w2 * c[2].y + w3 * c[3].y) * (1.f / 6.f),
+                               (w0 * c[0].z + w1 * c[1].z + w2 * c[2].z + w3 * c[3].z) * (1.f / 6.f), (w0 * c[0].w + w1 * c[1].w + w2 * c[2].w + w3 * c[3].w) * (1.f / 6.f));
+        }
+        float r = 0.f;
+        for (int a = 0; a < 4; ++a) {
+            r = fmaxf(r, fabsf(b[a].w));
+            lo[0] = fminf(lo[0], b[a].x); hi[0] = fmaxf(hi[0], b[a].x);
+            lo[1] = fminf(lo[1], b[a].y); hi[1] = fmaxf(hi[1], b[a].y);
+            lo[2] = fminf(lo[2], b[a].z); hi[2] = fmaxf(hi[2], b[a].z);
+        }
+        for (int k = 0; k < 3; ++k) {  // radius plus a relative margin for the fp32 evaluation of the curve points
+            const float pad = r * 1.0001f + 1e-6f * fmaxf(fabsf(lo[k]), fabsf(hi[k]));
+            lo[k] -= pad;
+            hi[k] += pad;
+        }
+        BuildTri t;
+        t.a = make_float4(lo[0], lo[1], lo[2], __uint_as_float(f));
+        t.b = make_float4(hi[0], hi[1], hi[2], __uint_as_float(geomID));
+        t.c = make_float4(__uint_as_float(poolBase + f), 0.f, 0.f, __uint_as_float(instID | kPrimCurveFlag));
+        out[outBase + f] = t;
+    }
+    for (int k = 0; k < 3; ++k) {
+        float a = lo[k], b2 = hi[k];
+        for (int s = 16; s > 0; s >>= 1) {
+            a = fminf(a, __shfl_xor_sync(0xffffffffu, a, s));
+            b2 = fmaxf(b2, __shfl_xor_sync(0xffffffffu, b2, s));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(bounds + k, floatFlip(a));
+            atomicMax(bounds + 3 + k, floatFlip(b2));
+        }
+    }
+}
+
 SELAS_D uint64_t expandBits21(uint32_t v) {
     uint64_t x = v & 0x1fffffu;
     x = (x | x << 32) & 0x1f00000000ffffull;
@@ -117,9 +194,9 @@ __global__ void mortonKernel(const BuildTri* __restrict__ tris, uint32_t n, cons
         ext[0] = ext[1] = ext[2] = longest;
     }
     BuildTri t = tris[i];
-    float c[3] = {0.5f * (fminf(t.a.x, fminf(t.b.x, t.c.x)) + fmaxf(t.a.x, fmaxf(t.b.x, t.c.x))),
-                  0.5f * (fminf(t.a.y, fminf(t.b.y, t.c.y)) + fmaxf(t.a.y, fmaxf(t.b.y, t.c.y))),
-                  0.5f * (fminf(t.a.z, fminf(t.b.z, t.c.z)) + fmaxf(t.a.z, fmaxf(t.b.z, t.c.z)))};
+    float plo[3], phi[3];
+    primBounds(t, plo, phi);
+    float c[3] = {0.5f * (plo[0] + phi[0]), 0.5f * (plo[1] + phi[1]), 0.5f * (plo[2] + phi[2])};
     uint32_t q[3];
     for (int k = 0; k < 3; ++k) {
         float nrm = ext[k] > 0.f ? (c[k] - lo[k]) / ext[k] : 0.f;
@@ -174,8 +251,10 @@ __global__ void fitBoxesKernel(const BuildTri* __restrict__ tris, const uint32_t
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     BuildTri t = tris[sorted[j]];
-    float4 lo = make_float4(fminf(t.a.x, fminf(t.b.x, t.c.x)), fminf(t.a.y, fminf(t.b.y, t.c.y)), fminf(t.a.z, fminf(t.b.z, t.c.z)), 0.f);
-    float4 hi = make_float4(fmaxf(t.a.x, fmaxf(t.b.x, t.c.x)), fmaxf(t.a.y, fmaxf(t.b.y, t.c.y)), fmaxf(t.a.z, fmaxf(t.b.z, t.c.z)), 0.f);
+    float plo[3], phi[3];
+    primBounds(t, plo, phi);
+    float4 lo = make_float4(plo[0], plo[1], plo[2], 0.f);
+    float4 hi = make_float4(phi[0], phi[1], phi[2], 0.f);
     uint32_t id = (uint32_t)(n - 1) + (uint32_t)j;
     boxLo[id] = lo;
     boxHi[id] = hi;
@@ -344,6 +423,12 @@ __global__ void collapseLevelKernel(const CollapseTask* __restrict__ tasks, uint
             for (uint32_t q = 0; q < cnt[k]; ++q) {
                 BuildTri t = tris[sorted[first + q]];
                 float4* o = outTris + (size_t)(triBase + triOffset + q) * 3;
+                if (__float_as_uint(t.c.w) & kPrimCurveFlag) {  // curve segment: the leaf record only names the pool entry
+                    o[0] = make_float4(t.c.x, 0.f, 0.f, t.a.w);
+                    o[1] = make_float4(0.f, 0.f, 0.f, t.b.w);
+                    o[2] = make_float4(0.f, 0.f, 0.f, t.c.w);
+                    continue;
+                }
                 o[0] = t.a;
                 o[1] = make_float4(t.b.x - t.a.x, t.b.y - t.a.y, t.b.z - t.a.z, t.b.w);
                 o[2] = make_float4(t.c.x - t.a.x, t.c.y - t.a.y, t.c.z - t.a.z, t.c.w);

@@ -306,9 +306,11 @@ __global__ void sahSeedItemsKernel(uint32_t n, uint32_t C, const uint32_t* __res
     const uint2 cl = clusters[topOrder[lo]];
     const uint32_t prim = sorted[cl.x + (pos - excl[lo])];
     const BuildTri t = tris[prim];
+    float plo[3], phi[3];
+    primBounds(t, plo, phi);
     SahItem it;
-    it.lo = make_float4(fminf(t.a.x, fminf(t.b.x, t.c.x)), fminf(t.a.y, fminf(t.b.y, t.c.y)), fminf(t.a.z, fminf(t.b.z, t.c.z)), __uint_as_float(prim));
-    it.hi = make_float4(fmaxf(t.a.x, fmaxf(t.b.x, t.c.x)), fmaxf(t.a.y, fmaxf(t.b.y, t.c.y)), fmaxf(t.a.z, fmaxf(t.b.z, t.c.z)), 1.0f);
+    it.lo = make_float4(plo[0], plo[1], plo[2], __uint_as_float(prim));
+    it.hi = make_float4(phi[0], phi[1], phi[2], 1.0f);
     items[pos] = it;
 }
 

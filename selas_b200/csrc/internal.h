@@ -31,7 +31,7 @@ struct MeshGpu {
     const void* ptex;       // device PtexGpu* or null
     const TextureGpu* texture;  // base colour texture (non-Ptex materials) or null
     uint32_t faceCount;
-    uint32_t indicesPerFace;
+    uint32_t indicesPerFace;  // 3 triangles, 4 quads, 1: a curve geometry (positions = float4 control vertices, indices = first vertex per segment)
     uint32_t materialIndex;
     uint32_t lightSetIndex;
 };
@@ -68,6 +68,7 @@ struct SceneGpu {
     const float4* tris;
     uint32_t nodeCount, triCount;
     const InstanceTrace* traceInstances;  // null: one flattened world-space BVH8
+    const float4* curvePool;              // four control vertices per curve segment of the tree (bvh8.cuh), or null: no curve geometry
     const uint4* instanceIds;             // SELAS_SCENE_INSTANCE_IDS: per flat instance {instID0, instID1, geomID, -} the public hits report
     const MeshGpu* meshes;
     const InstanceGpu* instances;

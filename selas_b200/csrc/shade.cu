@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) surfaceParamsKernel(SceneGpu sc, size_t n
         SelasRay r = rays[i];
         Surface s;
         surfaceFromHit(sc, v3(r.ox, r.oy, r.oz), v3(r.dx, r.dy, r.dz), h.t, h.u, h.v, h.primID, h.geomID, h.instID0,
-                       ptexRgb ? ptexRgb + 3 * i : nullptr, s);
+                       ptexRgb ? ptexRgb + 3 * i : nullptr, s, h.pad);
         storeSurface(s, v3(-r.dx, -r.dy, -r.dz), o);
     }
     out[i] = o;
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGp
         Surface s;
         if (isHit) {
             surfaceFromHit(sc, o, d, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, geomID, h1.y,
-                           ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, s);
+                           ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, s, h1.w);
             rayDistance = length(s.position - o);  // :165-167
         }
         thr = thr * transmission(medium, rayDistance);  // :168-169

@@ -7,6 +7,7 @@
 // quads       t = (1-v)((1-u) t0 + u t1) + v ((1-u) t3 + u t2)          RTC_GEOMETRY_TYPE_QUAD.3embree3:52
 #pragma once
 #include "disney.cuh"
+#include "curve.cuh"
 #include "internal.h"
 #include "ptex_eval.cuh"
 
@@ -56,22 +57,41 @@ SELAS_D V3 sampleTextureFloat3(const TextureGpu& tex, float u, float v, bool sRG
 }
 
 // ptexRgb: this hit's Ptex lookup, made by the Ptex stage kernel (ptexStageKernel) before shading, or null.
+// element: last word of the hit record -- for a hit on a curve geometry the piece of the segment that was hit (curve.cuh), else 0.
 SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, float v, uint32_t primID, uint32_t geomID,
-                            uint32_t instID, const float* ptexRgb, Surface& s) {
+                            uint32_t instID, const float* ptexRgb, Surface& s, uint32_t element = 0u) {
     const MeshGpu mesh = sc.meshes[geomID];
     const InstanceGpu* inst = sc.instances + instID;
     const SelasMaterial* mat = sc.materials + mesh.materialIndex;
-    uint32_t ix[4];
-    const uint32_t* ip = mesh.indices + (size_t)primID * mesh.indicesPerFace;
-    ix[0] = __ldg(ip); ix[1] = __ldg(ip + 1); ix[2] = __ldg(ip + 2);
-    ix[3] = mesh.indicesPerFace == 4 ? __ldg(ip + 3) : 0u;
+    const bool isCurve = mesh.indicesPerFace == 1;
+    uint32_t ix[4] = {0u, 0u, 0u, 0u};
+    if (!isCurve) {
+        const uint32_t* ip = mesh.indices + (size_t)primID * mesh.indicesPerFace;
+        ix[0] = __ldg(ip); ix[1] = __ldg(ip + 1); ix[2] = __ldg(ip + 2);
+        ix[3] = mesh.indicesPerFace == 4 ? __ldg(ip + 3) : 0u;
+    }
     const bool identity = inst->identity != 0;
     float m[16];
     if (!identity)
         for (int k = 0; k < 16; ++k) m[k] = inst->m[k];
 
     V3 normal;
-    if (mesh.normals) {
+    if (isCurve) {
+        // hit->normal = Embree's Ng of a round curve: the surface normal (RTC_GEOMETRY_TYPE_CURVE.3embree3); curve geometries carry no
+        // attribute buffers (ModelResource.cpp:314-319).  Rebuilt from the element that was hit, with the control vertices taken to
+        // world space (for rotations and uniform scales the same as sending the object-space normal through localToWorld).
+        const float4* cv = reinterpret_cast<const float4*>(mesh.positions) + __ldg(mesh.indices + primID);
+        float4 c[4];
+        float rscale = 1.0f;
+        if (!identity) rscale = cbrtf(fabsf(m[0] * (m[5] * m[10] - m[6] * m[9]) - m[1] * (m[4] * m[10] - m[6] * m[8]) + m[2] * (m[4] * m[9] - m[5] * m[8])));
+        for (int k = 0; k < 4; ++k) {
+            const float4 p = __ldg(cv + k);
+            V3 q = v3(p.x, p.y, p.z);
+            if (!identity) q = mulPoint44(q, m);
+            c[k] = make_float4(q.x, q.y, q.z, p.w * rscale);
+        }
+        normal = curveElementNormal(c[0], c[1], c[2], c[3], element ? element : 1u, v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z));
+    } else if (mesh.normals) {
         normal = v3(interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 0, u, v), interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 1, u, v),
                     interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 2, u, v));
     } else {
@@ -84,10 +104,10 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
         normal = cross(p1 - p0, p2 - p0);
     }
     // QUIRK SurfaceParameters.cpp:165-171: normals go through localToWorld as plain vectors (no inverse transpose)
-    if (!identity) normal = mulVec44(normal, m);
+    if (!identity && !isCurve) normal = mulVec44(normal, m);
     V3 n = normalize(normal);
     V3 tg, b;
-    if (mesh.tangents) {
+    if (mesh.tangents && !isCurve) {
         V3 lt = v3(interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 0, u, v), interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 1, u, v),
                    interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 2, u, v));
         float w = interpAttr(mesh.tangents, ix, mesh.indicesPerFace, 4, 3, u, v);
@@ -106,7 +126,7 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
         // SurfaceParameters.cpp:196-208: filter->eval(faceid = primId, u, v, widths 0), then pow 2.2 only.  The lookup itself
         // was done by the Ptex stage that runs between the closest-hit and the shade kernels.
         base = v3(ptexRgb[0], ptexRgb[1], ptexRgb[2]);
-    } else if (mesh.texture) {
+    } else if (mesh.texture && !isCurve) {
         // SurfaceParameters.cpp:209-214: SampleTextureFloat3(baseColorTexture, uvs, sRGB = true, material baseColor); uvs = (0, 0)
         // without a uv buffer (:186-190)
         float tu = 0.0f, tv = 0.0f;

@@ -320,7 +320,7 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     // ---- count triangles per draw ----
     struct Draw { uint32_t mesh, inst, base, tris; };
     std::vector<Draw> draws;
-    uint64_t total = 0;
+    uint64_t total = 0, curveSegments = 0;
     for (uint32_t ii = 0; ii < inst.size(); ++ii)
         for (uint32_t m = 0; m < meshes.size(); ++m) {
             if (inst[ii].mesh != 0xFFFFFFFFu && inst[ii].mesh != m) continue;
@@ -328,9 +328,10 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
             if (t == 0) continue;
             draws.push_back({m, ii, (uint32_t)total, t});
             total += t;
+            if (meshes[m].indicesPerFace == 1) curveSegments += t;  // a curve geometry: one primitive and one pool entry per segment
         }
-    if (total >= 0x7fffffffull) {
-        setError(ctx, "scene has %llu triangles; the builder is limited to 2^31-1", (unsigned long long)total);
+    if (total >= 0x3fffffffull || inst.size() >= 0x3fffffffull) {
+        setError(ctx, "scene has %llu primitives; the builder is limited to 2^30-1", (unsigned long long)total);
         return SELAS_ERR_UNSUPPORTED;
     }
     const uint32_t n = (uint32_t)total;
@@ -341,6 +342,7 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     scene->gpu.nodeCount = 0;
     scene->gpu.triCount = 0;
     scene->gpu.traceInstances = nullptr;
+    scene->gpu.curvePool = nullptr;
     scene->topNodeCount = 0;
     if (n == 0) return SELAS_OK;
 
@@ -356,11 +358,23 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     tmp.ptrs.push_back(d_bounds);
     uint32_t boundsInit[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
     SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, st));
+    float4* d_pool = nullptr;
+    if (curveSegments) {
+        int rcPool = devAlloc(scene, &d_pool, (size_t)curveSegments * 4, true);
+        if (rcPool) return rcPool;
+    }
+    uint32_t poolBase = 0;
     for (const Draw& d : draws) {
         MeshDev md{meshes[d.mesh].positions, meshes[d.mesh].indices, meshes[d.mesh].faceCount, meshes[d.mesh].indicesPerFace};
-        gatherTrianglesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, d_instances[d.inst].m, inst[d.inst].identity != 0, d.mesh, d.inst,
-                                                                         d_tris, d.base, d_bounds);
+        if (md.indicesPerFace == 1) {
+            gatherCurvesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, d_instances[d.inst].m, inst[d.inst].identity != 0, d.mesh, d.inst, d_tris,
+                                                                          d.base, d_pool, poolBase, d_bounds);
+            poolBase += md.faceCount;
+        } else
+            gatherTrianglesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, d_instances[d.inst].m, inst[d.inst].identity != 0, d.mesh, d.inst,
+                                                                             d_tris, d.base, d_bounds);
     }
+    scene->gpu.curvePool = d_pool;
     TreeOut tree;
     int rc = buildTree(scene, d_tris, d_bounds, n, tree);
     if (tree.nodes) scene->allocations.push_back(tree.nodes);
@@ -378,7 +392,7 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     scene->gpu.triCount = n;
     scene->stats.nodeCount = tree.nodeCount;
     scene->stats.maxDepth = tree.levels;
-    scene->topNodeCount = chooseTopNodeCount(tree.levelEnds);
+    scene->topNodeCount = d_pool ? 0u : chooseTopNodeCount(tree.levelEnds);
     if (tree.levels > SELAS_STACK_SIZE) {  // one stack entry per level at most: a deeper tree would drop pushes silently
         setError(ctx, "BVH8 has %u levels; the traversal stack holds %d", tree.levels, SELAS_STACK_SIZE);
         return SELAS_ERR_UNSUPPORTED;
@@ -413,6 +427,7 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
     scene->gpu.nodeCount = 0;
     scene->gpu.triCount = 0;
     scene->gpu.traceInstances = nullptr;
+    scene->gpu.curvePool = nullptr;
     scene->topNodeCount = 0;
 
     struct Blas {
@@ -443,6 +458,15 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
         blas[in.mesh].used = true;
     }
     uint64_t uniqueTris = 0, instancedTris = 0;
+    uint64_t curveSegments2 = 0;
+    for (uint32_t m = 0; m < meshes.size(); ++m)
+        if (blas[m].used && meshes[m].indicesPerFace == 1) curveSegments2 += meshes[m].faceCount;
+    float4* d_pool2 = nullptr;
+    uint32_t poolBase2 = 0;
+    if (curveSegments2) {
+        int rcPool = devAlloc(scene, &d_pool2, (size_t)curveSegments2 * 4, true);
+        if (rcPool) return rcPool;
+    }
     for (uint32_t m = 0; m < meshes.size(); ++m) {
         const uint32_t t = meshes[m].faceCount * (meshes[m].indicesPerFace == 4 ? 2u : 1u);
         if (!blas[m].used || t == 0) {
@@ -462,7 +486,11 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
         uint32_t boundsInit[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, st));
         MeshDev md{meshes[m].positions, meshes[m].indices, meshes[m].faceCount, meshes[m].indicesPerFace};
-        gatherTrianglesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, nullptr, true, m, 0u, d_tris, 0u, d_bounds);
+        if (md.indicesPerFace == 1) {  // curve geometry: object-space control vertices into the pool
+            gatherCurvesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, nullptr, true, m, 0u, d_tris, 0u, d_pool2, poolBase2, d_bounds);
+            poolBase2 += md.faceCount;
+        } else
+            gatherTrianglesKernel<<<divUp(md.faceCount, 256), 256, 0, st>>>(md, nullptr, true, m, 0u, d_tris, 0u, d_bounds);
         int rc = buildTree(scene, d_tris, d_bounds, t, blas[m].tree);
         if (rc) return rc;
         uint32_t hb[6];
@@ -590,7 +618,8 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
     scene->gpu.nodeCount = (uint32_t)totalNodes;
     scene->gpu.triCount = (uint32_t)totalTris;
     scene->gpu.traceInstances = d_table;
-    scene->topNodeCount = chooseTopNodeCount(top.levelEnds);
+    scene->gpu.curvePool = d_pool2;
+    scene->topNodeCount = d_pool2 ? 0u : chooseTopNodeCount(top.levelEnds);
     scene->stats.nodeCount = (uint32_t)totalNodes;
     uint32_t deepestMesh = 0;
     for (const Blas& b : blas)
@@ -611,6 +640,7 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
 static Bvh8 bvhOf(const SelasScene* s, bool publicIds = false) {
     Bvh8 b;
     b.instanceIds = publicIds ? s->gpu.instanceIds : nullptr;
+    b.curves = s->gpu.curvePool;
     b.nodes = s->gpu.nodes;
     b.tris = s->gpu.tris;
     b.nodeCount = s->gpu.nodeCount;
@@ -641,18 +671,21 @@ static TraceLaunch traceLaunch(const SelasScene* scene, K kernel) {
 }
 // kernel variant by scene: two-level form only when the scene was built that way (the flattened form keeps its register budget), staged
 // top levels only when asked for
-#define SELAS_TRACE_GO2(MODE, COUNT, INST, TOP, ...)                                                              \
-    do {                                                                                                          \
-        TraceLaunch tl = traceLaunch(scene, traceKernel<MODE, COUNT, INST, TOP>);                                 \
-        traceKernel<MODE, COUNT, INST, TOP><<<tl.grid, SELAS_TRACE_THREADS, tl.smem, stream>>>(__VA_ARGS__);      \
+#define SELAS_TRACE_GO2(MODE, COUNT, INST, TOP, CURVES, ...)                                                       \
+    do {                                                                                                           \
+        TraceLaunch tl = traceLaunch(scene, traceKernel<MODE, COUNT, INST, TOP, CURVES>);                          \
+        traceKernel<MODE, COUNT, INST, TOP, CURVES><<<tl.grid, SELAS_TRACE_THREADS, tl.smem, stream>>>(__VA_ARGS__); \
     } while (0)
-#define SELAS_TRACE_GO(MODE, COUNT, ...)                                                                           \
-    do {                                                                                                          \
-        const bool inst__ = scene->gpu.traceInstances != nullptr, top__ = scene->topNodeCount != 0;               \
-        if (inst__ && top__) SELAS_TRACE_GO2(MODE, COUNT, true, true, __VA_ARGS__);                               \
-        else if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, __VA_ARGS__);                                  \
-        else if (top__) SELAS_TRACE_GO2(MODE, COUNT, false, true, __VA_ARGS__);                                   \
-        else SELAS_TRACE_GO2(MODE, COUNT, false, false, __VA_ARGS__);                                             \
+#define SELAS_TRACE_GO(MODE, COUNT, ...)                                                                            \
+    do {                                                                                                           \
+        const bool inst__ = scene->gpu.traceInstances != nullptr, top__ = scene->topNodeCount != 0;                \
+        if (scene->gpu.curvePool) { /* scenes with curve geometry: the variant that carries the curve leaf test */ \
+            if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, true, __VA_ARGS__);                              \
+            else SELAS_TRACE_GO2(MODE, COUNT, false, false, true, __VA_ARGS__);                                    \
+        } else if (inst__ && top__) SELAS_TRACE_GO2(MODE, COUNT, true, true, false, __VA_ARGS__);                  \
+        else if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, false, __VA_ARGS__);                            \
+        else if (top__) SELAS_TRACE_GO2(MODE, COUNT, false, true, false, __VA_ARGS__);                             \
+        else SELAS_TRACE_GO2(MODE, COUNT, false, false, false, __VA_ARGS__);                                       \
     } while (0)
 
 int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_ng4, uint32_t* d_counts,

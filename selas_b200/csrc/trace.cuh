@@ -47,8 +47,8 @@ SELAS_D void setupRayDirection(V3 d, V3& idir, bool& negx, bool& negy, bool& neg
     octInv4 = (7u - oct) * 0x01010101u;
 }
 
-template <int MODE, bool COUNT, bool INST = false, bool TOP = false>
-__global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT) ? 6 : SELAS_TRACE_CTAS_PER_SM) traceKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n,
+template <int MODE, bool COUNT, bool INST = false, bool TOP = false, bool CURVES = false>
+__global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES) ? 6 : SELAS_TRACE_CTAS_PER_SM) traceKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n,
                                                                    const uint32_t* __restrict__ nPtr,
                                                                    SelasHit* __restrict__ hits, uint8_t* __restrict__ occluded,
                                                                    float4* __restrict__ ng, uint32_t* __restrict__ counts,
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT) ? 6 : SEL
     bool negx = false, negy = false, negz = false;
     uint32_t octInv4 = 0;
     TraceResult res;
-    res.t = 0.f; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu; res.inst = 0u;
+    res.t = 0.f; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu; res.inst = 0u; res.element = 0u; res.ng = v3(0.f);
     // two-level state (INST only): world ray while inside an instance, stack mark, the instance's node / triangle bases
     V3 ow = v3(0.f), dw = v3(0.f);
     int spMark = 0;
@@ -212,7 +212,17 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT) ? 6 : SEL
                 float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 if (COUNT) ++nTris;
                 float t, u, v;
-                if (intersectTri(a, b, c, o, d, tnear, tmax, t, u, v)) {
+                if (CURVES && (__float_as_uint(c.w) & kLeafCurveFlag)) {
+                    // round B-spline curve segment (ModelResource.cpp:300-333): the leaf record names its four control vertices
+                    const float4* cp = bvh.curves + 4 * (size_t)__float_as_uint(a.x);
+                    CurveHit ch;
+                    if (intersectCurve(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3), o, d, tnear, tmax, ch)) {
+                        tmax = ch.t;
+                        res.t = ch.t; res.u = ch.u; res.v = 0.f; res.tri = ti; res.element = ch.element; res.ng = ch.ng;
+                        if (INST) res.inst = curInst;
+                        if (ANY) { finished = true; break; }
+                    }
+                } else if (intersectTri(a, b, c, o, d, tnear, tmax, t, u, v)) {
                     tmax = t;
                     res.t = t; res.u = u; res.v = v; res.tri = ti;
                     if (INST) res.inst = curInst;

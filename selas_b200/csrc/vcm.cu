@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(128) vcmLightShadeKernel(SceneGpu sc, SelasCam
             loadState(rays, thrIdx, mis, i, st);
             Surface s;
             surfaceFromHit(sc, st.position, st.direction, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, h1.x, h1.y,
-                           ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, s);
+                           ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, s, h1.w);
             V3 view = -st.direction;
             V3 dp = st.position - s.position;
             float connectionLengthSqr = dot(dp, dp);
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(128) vcmCameraShadeKernel(SceneGpu sc, VcmPara
         } else {
             Surface s;
             surfaceFromHit(sc, st.position, st.direction, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, h1.x, h1.y,
-                           ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, s);
+                           ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, s, h1.w);
             V3 view = -st.direction;
             V3 dp = st.position - s.position;
             float connectionLengthSqr = dot(dp, dp);
@@ -511,7 +511,7 @@ SELAS_D bool loadCameraVertex(const SceneGpu& sc, uint32_t i, const SelasRay* ra
     float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), t = __ldg(thrIdx + i), m = __ldg(vertexMis + i);
     V3 o = v3(r0.x, r0.y, r0.z), d = v3(r1.x, r1.y, r1.z);
     surfaceFromHit(sc, o, d, __uint_as_float(h0.x), __uint_as_float(h0.y), __uint_as_float(h0.z), h0.w, h1.x, h1.y,
-                   ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, cv.s);
+                   ptexRgb ? ptexRgb + 3 * (size_t)i : nullptr, cv.s, h1.w);
     makeDisneyFrame(cv.s, cv.s.shader == SELAS_SHADER_DISNEY_THIN, cv.frame);
     cv.view = -d;
     cv.throughput = v3(t.x, t.y, t.z);
@@ -572,7 +572,7 @@ SELAS_D bool connectPathVertices(const SceneGpu& sc, const VcmParams& prm, uint3
     Surface ls;  // CalculateSurfaceParams(context, &lightVertex.hit, lightSurface), :314-317
     V3 lo = v3(lr0.x, lr0.y, lr0.z), ld = v3(lr1.x, lr1.y, lr1.z);
     surfaceFromHit(sc, lo, ld, __uint_as_float(lh0.x), __uint_as_float(lh0.y), __uint_as_float(lh0.z), lh0.w, lh1.x, lh1.y,
-                   lvPtex ? lvPtex + 3 * (size_t)li : nullptr, ls);
+                   lvPtex ? lvPtex + 3 * (size_t)li : nullptr, ls, lh1.w);
     V3 direction = ls.position - cv.s.position;
     float distanceSquared = dot(direction, direction);
     float distance = sqrtf(distanceSquared);

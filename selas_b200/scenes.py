@@ -494,3 +494,37 @@ def bounding_sphere(data):
         hi = np.max([m["positions"].max(axis=0) for m in data.meshes], axis=0).astype(np.float64)
     c = 0.5 * (lo + hi)
     return (float(c[0]), float(c[1]), float(c[2]), float(0.5 * np.linalg.norm(hi - lo)))
+
+
+# ---- curves: a patch of grass (RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE, the geometry the reference's island scene grows everywhere) ----
+def grass_patch(blades=400, segments=3, seed=9, extent=4.0, height=(0.6, 1.4), radius=(0.03, 0.004), with_floor=True):
+    """`blades` tapered B-spline blades of `segments` segments each over a floor quad, one quad light above.  Returns SceneData with
+    one curve geometry (geomID = number of meshes).  Control vertices: x, y, z, radius; segment i of a blade starts at its i-th vertex."""
+    rng = np.random.default_rng(seed)
+    nv = segments + 3
+    verts, indices = [], []
+    for b in range(blades):
+        base = np.array([rng.uniform(-extent, extent), 0.0, rng.uniform(-extent, extent)])
+        h = rng.uniform(*height)
+        lean = rng.normal(scale=0.35, size=2)
+        sway = rng.normal(scale=0.15, size=2)
+        first = len(verts)
+        for k in range(nv):
+            s = (k - 1) / (nv - 3)  # the spline runs from s = 0 (vertex 1) to s = 1 (vertex nv - 2); the outer vertices are phantom ends
+            p = base + np.array([lean[0] * s * s + sway[0] * np.sin(3.0 * s), h * s, lean[1] * s * s + sway[1] * np.sin(2.0 * s + 1.0)])
+            r = radius[0] + (radius[1] - radius[0]) * min(max(s, 0.0), 1.0)
+            verts.append([p[0], p[1], p[2], r])
+        indices += [first + k for k in range(segments)]
+    meshes = []
+    if with_floor:
+        e = extent * 1.5
+        meshes.append(dict(positions=np.array([[-e, 0, -e], [-e, 0, e], [e, 0, e], [e, 0, -e]], np.float32), indices=np.array([[0, 1, 2, 3]], np.uint32),
+                           material=0, lightSet=0))
+    mats = np.array([material(**REFERENCE_MATERIALS["RoughDiffuse"]), material(shaderName="DisneySolid", baseColor=[0.25, 0.6, 0.15], roughness=0.6, sheen=0.4)])
+    lights = np.array([quad_light((0.0, 6.0, 0.0), (3.0, 0.0, 0.0), (0.0, 0.0, 3.0), (0.0, -1.0, 0.0), (40.0, 38.0, 34.0))])
+    curves = [dict(vertices=np.array(verts, np.float32), indices=np.array(indices, np.uint32), material=1, lightSet=0)]
+    return capi.SceneData(meshes, mats, lights, [(0, 1)], background=(0.3, 0.45, 0.7, 0.0), curves=curves)
+
+
+def grass_camera(width=320, height=180):
+    return capi.camera_init((0.0, 2.2, -7.5), (0.0, 0.5, 0.0), (0.0, 1.0, 0.0), 45.0, width, height)
