@@ -82,7 +82,8 @@ def test_ptex_fixtures_match_reference(ptexref):
 def test_record_layouts():
     assert capi.C.sizeof(capi.RenderSettings) == 52 and capi.C.sizeof(capi.RenderStats) == 96
     assert capi.C.sizeof(capi.VcmSettings) == 56 and capi.C.sizeof(capi.VcmStats) == 104 and capi.VCM_VERTEX_DTYPE.itemsize == 96
-    assert capi.C.sizeof(capi.MeshDesc) == 80 and capi.C.sizeof(capi.TextureDesc) == 24 and capi.C.sizeof(capi.SceneDesc) == 112 and capi.C.sizeof(capi.IblDesc) == 56
+    assert capi.C.sizeof(capi.MeshDesc) == 80 and capi.C.sizeof(capi.TextureDesc) == 24 and capi.C.sizeof(capi.SceneDesc) == 120 and capi.C.sizeof(capi.IblDesc) == 56
+    assert capi.C.sizeof(capi.CurveDesc) == 40 and capi.C.sizeof(capi.InstanceDesc) == 80 and capi.C.sizeof(capi.BvhStats) == 40
 
 
 def test_vcm_texture_deferred_golden(oracle):
