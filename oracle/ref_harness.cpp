@@ -917,6 +917,24 @@ static_assert(sizeof(MeshMetaData) == 92 && sizeof(MaterialResourceData) == 600 
               "reference element layouts");
 extern "C" {
 
+// Curve geometry of the NEXT ref_write_model_blobs call (ModelResourceData::curves / curveModelName / totalCurveVertexCount and
+// ModelGeometryData::curveIndices / curveVertices): borrowed pointers, consumed and cleared by that call.
+static struct {
+    const uint32_t* indices = nullptr;
+    uint64_t indexCount = 0;
+    const float* vertices4 = nullptr;
+    uint32_t vertexCount = 0;
+    const uint32_t* ranges2 = nullptr;  // CurveMetaData {indexOffset, indexCount}
+    uint32_t curveCount = 0;
+    uint32_t modelName = 0;
+} g_nextCurves;
+int ref_set_next_model_curves(const uint32_t* indices, uint64_t indexCount, const float* vertices4, uint32_t vertexCount, const uint32_t* ranges2,
+                              uint32_t curveCount, uint32_t curveModelName) {
+    g_nextCurves.indices = indices; g_nextCurves.indexCount = indexCount; g_nextCurves.vertices4 = vertices4; g_nextCurves.vertexCount = vertexCount;
+    g_nextCurves.ranges2 = ranges2; g_nextCurves.curveCount = curveCount; g_nextCurves.modelName = curveModelName;
+    return 0;
+}
+
 int ref_write_model_blobs(const char* dataPath, const char* geomPath, const float* aabb6, uint32_t totalVertexCount, const uint32_t* indices,
                           uint64_t indexCount, const float* positions, const float* normals, const float* tangents, const float* uvs,
                           const void* meshes92, uint32_t meshCount, const void* materials600, const uint32_t* materialHashes,
@@ -926,8 +944,8 @@ int ref_write_model_blobs(const char* dataPath, const char* geomPath, const floa
     data->aaBox.min = float3(aabb6[0], aabb6[1], aabb6[2]);
     data->aaBox.max = float3(aabb6[3], aabb6[4], aabb6[5]);
     data->totalVertexCount = totalVertexCount;
-    data->totalCurveVertexCount = 0;
-    data->curveModelName = 0;
+    data->totalCurveVertexCount = g_nextCurves.vertexCount;
+    data->curveModelName = g_nextCurves.modelName;
     data->pad = 0;
     data->indexSize = indexCount * sizeof(uint32);
     data->faceIndexSize = 0;
@@ -935,13 +953,15 @@ int ref_write_model_blobs(const char* dataPath, const char* geomPath, const floa
     data->normalsSize = normals ? (uint64)totalVertexCount * sizeof(float3) : 0;
     data->tangentsSize = tangents ? (uint64)totalVertexCount * sizeof(float4) : 0;
     data->uvsSize = uvs ? (uint64)totalVertexCount * sizeof(float2) : 0;
-    data->curveIndexSize = 0;
-    data->curveVertexSize = 0;
+    data->curveIndexSize = g_nextCurves.indexCount * sizeof(uint32);
+    data->curveVertexSize = (uint64)g_nextCurves.vertexCount * sizeof(float4);
+    static_assert(sizeof(CurveMetaData) == 8, "CurveMetaData layout");
+    fillArray(data->curves, g_nextCurves.ranges2, g_nextCurves.curveCount);
     fillArray(data->materials, materials600, materialCount);
     fillArray(data->materialHashes, materialHashes, materialCount);
     fillArray(data->meshes, meshes92, meshCount);
     int rc = writeBlob(*data, dataPath);
-    data->materials.Shutdown(); data->materialHashes.Shutdown(); data->meshes.Shutdown();
+    data->materials.Shutdown(); data->materialHashes.Shutdown(); data->meshes.Shutdown(); data->curves.Shutdown();
     delete data;
     ModelGeometryData geom;
     memset(&geom, 0, sizeof(geom));
@@ -955,7 +975,12 @@ int ref_write_model_blobs(const char* dataPath, const char* geomPath, const floa
     geom.normals = reinterpret_cast<float3*>(const_cast<float*>(normals));
     geom.tangents = reinterpret_cast<float4*>(const_cast<float*>(tangents));
     geom.uvs = reinterpret_cast<float2*>(const_cast<float*>(uvs));
+    geom.curveIndexSize = g_nextCurves.indexCount * sizeof(uint32);
+    geom.curveVertexSize = (uint64)g_nextCurves.vertexCount * sizeof(float4);
+    geom.curveIndices = const_cast<uint32*>(g_nextCurves.indices);
+    geom.curveVertices = reinterpret_cast<float4*>(const_cast<float*>(g_nextCurves.vertices4));
     if (!rc) rc = writeBlob(geom, geomPath);
+    g_nextCurves = {};
     return rc;
 }
 int ref_write_subscene_blob(const char* path, const char* name, uint64_t lightSetIndex, const void* modelNames512, uint32_t modelCount,

@@ -337,7 +337,17 @@ void CalculateSceneBoundingBox(SceneResource* scene) {
     // AxisAlignedBox.cpp:44-65: tmin + combinations of the transformed edge vectors).  Scenes without an instance list are one
     // identity instance over all meshes: the raw vertices.
     float lo[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, hi[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
-    std::vector<float> meshBox(scene->meshes.size() * 6);
+    std::vector<float> meshBox((scene->meshes.size() + scene->curves.size()) * 6);
+    for (size_t ci = 0; ci < scene->curves.size(); ++ci) {  // curve geometries follow the meshes: control vertices grown by their radii
+        const SceneCurve& c = scene->curves[ci];
+        float* b = &meshBox[(scene->meshes.size() + ci) * 6];
+        for (int k = 0; k < 3; ++k) { b[k] = 3.402823466e+38f; b[3 + k] = -3.402823466e+38f; }
+        for (size_t v = 0; v + 3 < c.vertices.size(); v += 4)
+            for (int k = 0; k < 3; ++k) {
+                b[k] = std::min(b[k], c.vertices[v + k] - std::fabs(c.vertices[v + 3]));
+                b[3 + k] = std::max(b[3 + k], c.vertices[v + k] + std::fabs(c.vertices[v + 3]));
+            }
+    }
     for (size_t mi = 0; mi < scene->meshes.size(); ++mi) {
         const SceneMesh& m = scene->meshes[mi];
         float* b = &meshBox[mi * 6];
@@ -355,14 +365,14 @@ void CalculateSceneBoundingBox(SceneResource* scene) {
         }
     };
     if (scene->instances.empty()) {
-        for (size_t mi = 0; mi < scene->meshes.size(); ++mi)
+        for (size_t mi = 0; mi < scene->meshes.size() + scene->curves.size(); ++mi)
             if (meshBox[mi * 6] <= meshBox[mi * 6 + 3]) {
                 includePoint(&meshBox[mi * 6]);
                 includePoint(&meshBox[mi * 6 + 3]);
             }
     } else {
         for (const SelasInstanceDesc& inst : scene->instances) {
-            if (inst.meshIndex >= scene->meshes.size()) continue;
+            if (inst.meshIndex >= scene->meshes.size() + scene->curves.size()) continue;
             const float* b = &meshBox[(size_t)inst.meshIndex * 6];
             if (!(b[0] <= b[3])) continue;  // empty mesh
             const float* M = inst.localToWorld;  // row-major, row vectors, translation in row 3
@@ -432,10 +442,22 @@ Error InitializeSceneResource(SceneResource* scene, int device) {
         d.baseColorTexture = m.baseColorTexture;
     }
     CalculateSceneBoundingBox(scene);
+    std::vector<SelasCurveDesc> curves(scene->curves.size());
+    for (size_t i = 0; i < curves.size(); ++i) {
+        const SceneCurve& c = scene->curves[i];
+        curves[i].vertices = c.vertices.data();
+        curves[i].vertexCount = (uint32_t)(c.vertices.size() / 4);
+        curves[i].indices = c.indices.data();
+        curves[i].segmentCount = (uint32_t)c.indices.size();
+        curves[i].materialIndex = c.materialIndex;
+        curves[i].lightSetIndex = c.lightSetIndex;
+    }
     SelasSceneDesc desc;
     memset(&desc, 0, sizeof(desc));
     desc.meshes = meshes.data();
     desc.meshCount = (uint32_t)meshes.size();
+    desc.curves = curves.empty() ? nullptr : curves.data();
+    desc.curveCount = (uint32_t)curves.size();
     desc.instances = scene->instances.empty() ? nullptr : scene->instances.data();
     desc.instanceCount = (uint32_t)scene->instances.size();
     desc.materials = scene->materials.data();
@@ -798,6 +820,7 @@ Error ReadModelResource(const char* dataPath, const char* geometryPath, BakedMod
     memcpy(model->aaBox, blob.data(), 24);
     memcpy(&model->totalVertexCount, blob.data() + 24, 4);
     memcpy(&model->totalCurveVertexCount, blob.data() + 28, 4);
+    memcpy(&model->curveModelName, blob.data() + 32, 4);
     uint64_t n = 0;
     const uint8_t* p = nullptr;
     ReturnError_(blobArray(blob, 168, 600, &n, &p, "materials"));
@@ -815,6 +838,7 @@ Error ReadModelResource(const char* dataPath, const char* geometryPath, BakedMod
         bm.name = fixedString(m + 28, 64);
     }
     ReturnError_(blobArray(blob, 264, 8, &model->curveCount, &p, "curves"));
+    model->curveRanges.assign((const uint32_t*)p, (const uint32_t*)p + 2 * model->curveCount);
 
     std::vector<uint8_t> geo;
     ReturnError_(readWholeFile(geometryPath, geo));
@@ -833,6 +857,14 @@ Error ReadModelResource(const char* dataPath, const char* geometryPath, BakedMod
     model->normals.assign((const float*)pn, (const float*)pn + sizes[3] / 4);
     model->tangents.assign((const float*)pt, (const float*)pt + sizes[4] / 4);
     model->uvs.assign((const float*)pu, (const float*)pu + sizes[5] / 4);
+    if (model->curveCount) {
+        const uint8_t *pci = nullptr, *pcv = nullptr;
+        ReturnError_(blobPointer(geo, 112, sizes[6], &pci, "curveIndices"));
+        ReturnError_(blobPointer(geo, 120, sizes[7], &pcv, "curveVertices"));
+        if (sizes[7] != 16ull * model->totalCurveVertexCount) return Error_("baked geometry blob %s: curveVertexSize does not match totalCurveVertexCount", geometryPath);
+        model->curveIndices.assign((const uint32_t*)pci, (const uint32_t*)pci + sizes[6] / 4);
+        model->curveVertices.assign((const float*)pcv, (const float*)pcv + sizes[7] / 4);
+    }
     return Success_;
 }
 
@@ -895,6 +927,7 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
     BakedScene bs;
     ReturnError_(ReadSceneResource(AssetFilePath(root, "SceneResource", kSceneDataVersion, sceneName).c_str(), &bs));
     scene->meshes.clear();
+    scene->curves.clear();
     scene->instances.clear();
     scene->materials.clear();
     scene->flags |= SELAS_SCENE_TWO_LEVEL_BVH;  // a baked scene is instances of models: keep each model's geometry once
@@ -931,7 +964,7 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
         return Success_;
     };
     // subscenes -> models -> meshes; meshRange[subscene][model] = first global mesh index, mesh count
-    struct ModelMeshes { uint32_t first, count; };
+    struct ModelMeshes { uint32_t first, count, curveFirst, curveCount; };
     std::vector<std::vector<ModelMeshes>> meshRange(bs.subsceneNames.size());
     std::vector<BakedSubscene> subs(bs.subsceneNames.size());
     for (size_t s = 0; s < bs.subsceneNames.size(); ++s) {
@@ -946,26 +979,19 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
             BakedModel model;
             ReturnError_(ReadModelResource(AssetFilePath(root, "ModelResource", kModelDataVersion, modelName.c_str()).c_str(),
                                            AssetFilePath(root, "ModelGeometryResource", kModelDataVersion, modelName.c_str()).c_str(), &model));
-            if (model.curveCount) return Error_("LoadBakedScene: model %s has %llu curves (ROUND_BSPLINE_CURVE geometry is not supported)", modelName.c_str(),
-                                                (unsigned long long)model.curveCount);
             const uint32_t modelMaterialBase = (uint32_t)scene->materials.size();
             for (const BakedMaterial& m : model.materials) {
                 scene->materials.push_back(m.material);
                 materialTexture.push_back(m.baseColorTexture);
             }
-            ModelMeshes range{(uint32_t)scene->meshes.size(), (uint32_t)model.meshes.size()};
-            for (const BakedMesh& bm : model.meshes) {
-                if (bm.indicesPerFace != 3 && bm.indicesPerFace != 4) return Error_("LoadBakedScene: mesh %s has %u indices per face", bm.name.c_str(), bm.indicesPerFace);
-                if ((uint64_t)bm.indexOffset + bm.indexCount > model.indices.size()) return Error_("LoadBakedScene: mesh %s indexes outside the model's index buffer", bm.name.c_str());
-                SceneMesh mesh;
-                mesh.indicesPerFace = bm.indicesPerFace;
-                mesh.lightSetIndex = (uint32_t)sub.lightSetIndex;
-                // FindMeshMaterial: the model's own materials (sorted hashes), then the subscene's, then the default
+            ModelMeshes range{(uint32_t)scene->meshes.size(), (uint32_t)model.meshes.size(), (uint32_t)scene->curves.size(), (uint32_t)model.curveCount};
+            // FindMeshMaterial (ModelResource.cpp:214-235): the model's own materials (sorted hashes), then the subscene's, then the default
+            auto findMaterial = [&](uint32_t hash) -> int {
                 int material = -1;
-                auto it = std::lower_bound(model.materialHashes.begin(), model.materialHashes.end(), bm.materialHash);
-                if (it != model.materialHashes.end() && *it == bm.materialHash) material = (int)(modelMaterialBase + (it - model.materialHashes.begin()));
+                auto it = std::lower_bound(model.materialHashes.begin(), model.materialHashes.end(), hash);
+                if (it != model.materialHashes.end() && *it == hash) material = (int)(modelMaterialBase + (it - model.materialHashes.begin()));
                 for (size_t k = 0; material < 0 && k < sub.sceneMaterialNames.size(); ++k)
-                    if (sub.sceneMaterialNames[k] == bm.materialHash) material = (int)(sceneMaterialBase + k);
+                    if (sub.sceneMaterialNames[k] == hash) material = (int)(sceneMaterialBase + k);
                 if (material < 0) {
                     if (defaultMaterial < 0) {
                         SelasMaterial dm;
@@ -979,6 +1005,37 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
                     }
                     material = defaultMaterial;
                 }
+                return material;
+            };
+            // the model's curve geometries (InitializeCurves, ModelResource.cpp:300-333): every curve shares the model-wide control
+            // vertices and takes `indexCount` segment indices from `indexOffset`; their material is the one named curveModelName (:382-383)
+            for (uint64_t c = 0; c < model.curveCount; ++c) {
+                const uint32_t indexOffset = model.curveRanges[2 * c], indexCount = model.curveRanges[2 * c + 1];
+                if ((uint64_t)indexOffset + indexCount > model.curveIndices.size())
+                    return Error_("LoadBakedScene: curve %llu of model %s indexes outside the curve index buffer", (unsigned long long)c, modelName.c_str());
+                SceneCurve curve;
+                curve.lightSetIndex = (uint32_t)sub.lightSetIndex;
+                curve.materialIndex = (uint32_t)findMaterial(model.curveModelName);
+                const uint32_t* ix = model.curveIndices.data() + indexOffset;
+                uint32_t lo = 0xFFFFFFFFu, hi = 0;
+                for (uint32_t k = 0; k < indexCount; ++k) { lo = std::min(lo, ix[k]); hi = std::max(hi, ix[k] + 3u); }
+                if (indexCount == 0) { lo = 0; hi = 0; }
+                if (indexCount && hi >= model.totalCurveVertexCount)
+                    return Error_("LoadBakedScene: curve %llu of model %s references control vertex %u of %u", (unsigned long long)c, modelName.c_str(), hi,
+                                  model.totalCurveVertexCount);
+                const uint32_t nv = indexCount ? hi - lo + 1 : 0;
+                curve.indices.resize(indexCount);
+                for (uint32_t k = 0; k < indexCount; ++k) curve.indices[k] = ix[k] - lo;
+                curve.vertices.assign(model.curveVertices.begin() + 4 * (size_t)lo, model.curveVertices.begin() + 4 * (size_t)(lo + nv));
+                scene->curves.push_back(std::move(curve));
+            }
+            for (const BakedMesh& bm : model.meshes) {
+                if (bm.indicesPerFace != 3 && bm.indicesPerFace != 4) return Error_("LoadBakedScene: mesh %s has %u indices per face", bm.name.c_str(), bm.indicesPerFace);
+                if ((uint64_t)bm.indexOffset + bm.indexCount > model.indices.size()) return Error_("LoadBakedScene: mesh %s indexes outside the model's index buffer", bm.name.c_str());
+                SceneMesh mesh;
+                mesh.indicesPerFace = bm.indicesPerFace;
+                mesh.lightSetIndex = (uint32_t)sub.lightSetIndex;
+                const int material = findMaterial(bm.materialHash);
                 mesh.materialIndex = (uint32_t)material;
                 if (scene->materials[material].flags & SELAS_MAT_USES_PTEX) {
                     // "<material.baseColorTexture>\\<mesh name>.ptx" under the content root (ModelResource.cpp:358-364, AssetFileUtils.cpp:85-92);
@@ -1035,12 +1092,22 @@ Error LoadBakedScene(const char* root, const char* sceneName, SceneResource* sce
                 inst.geomID = m;
                 scene->instances.push_back(inst);
             }
+            for (uint32_t c = 0; c < range.curveCount; ++c) {  // attached after the meshes (ModelResource.cpp:461-466): geomID = meshes + c
+                inst.meshIndex = 0x80000000u | (range.curveFirst + c);  // resolved below, once the number of meshes is final
+                inst.geomID = range.count + c;
+                scene->instances.push_back(inst);
+            }
         }
     }
+    for (SelasInstanceDesc& inst : scene->instances)
+        if (inst.meshIndex & 0x80000000u) inst.meshIndex = (uint32_t)scene->meshes.size() + (inst.meshIndex & 0x7fffffffu);
     scene->flags |= SELAS_SCENE_INSTANCE_IDS;
     // geometry exists in the scene only through instances: without any, nothing is there to hit (an empty instance list would otherwise
     // mean "every mesh once" to selas_cuda_scene_create)
-    if (scene->instances.empty()) scene->meshes.clear();
+    if (scene->instances.empty()) {
+        scene->meshes.clear();
+        scene->curves.clear();
+    }
     return Success_;
 }
 
@@ -1198,6 +1265,10 @@ int selas_host_load_baked_scene(const char* root, const char* sceneName, uint64_
         uint64_t tris = 0, texturedMeshes = 0;
         for (const Selas::SceneMesh& m : scene.meshes) texturedMeshes += m.baseColorTexture ? 1 : 0;
         for (const SelasInstanceDesc& in : scene.instances) {
+            if (in.meshIndex >= scene.meshes.size()) {  // a curve geometry: one primitive per segment
+                tris += scene.curves[in.meshIndex - scene.meshes.size()].indices.size();
+                continue;
+            }
             const Selas::SceneMesh& m = scene.meshes[in.meshIndex];
             tris += m.indices.size() / m.indicesPerFace * (m.indicesPerFace == 4 ? 2 : 1);
         }

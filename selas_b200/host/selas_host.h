@@ -90,8 +90,14 @@ struct SceneMesh {
     std::string ptexPath;       // Ptex base colour file, loaded (once per distinct path) by InitializeSceneResource and owned by the scene
     const SelasTextureDesc* baseColorTexture = nullptr;  // borrowed (e.g. from SceneResource::textures)
 };
+struct SceneCurve {  // one RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE geometry (ModelResource.cpp:300-333)
+    std::vector<float> vertices;    // float4 control vertices
+    std::vector<uint32_t> indices;  // first control vertex per segment
+    uint32_t materialIndex = 0, lightSetIndex = 0;
+};
 struct SceneResource {
     std::vector<SceneMesh> meshes;
+    std::vector<SceneCurve> curves;  // curve geometries; an instance names one as meshes.size() + index
     std::vector<SelasInstanceDesc> instances;
     std::vector<SelasMaterial> materials;
     std::vector<SelasLight> lights;
@@ -164,7 +170,11 @@ struct BakedMesh {  // MeshMetaData, ModelResource.h:113-123 (92 bytes)
 struct BakedModel {  // ModelResourceData + ModelGeometryData, ModelResource.h:125-170
     float aaBox[6];
     uint32_t totalVertexCount = 0, totalCurveVertexCount = 0;
+    uint32_t curveModelName = 0;  // material hash of the model's curves (ModelResource.cpp:382-383)
     uint64_t curveCount = 0;
+    std::vector<uint32_t> curveRanges;   // CurveMetaData {indexOffset, indexCount} per curve geometry (ModelResource.h:107-111)
+    std::vector<uint32_t> curveIndices;  // first control vertex of every segment
+    std::vector<float> curveVertices;    // float4 {x, y, z, radius}
     std::vector<BakedMaterial> materials;
     std::vector<uint32_t> materialHashes;
     std::vector<BakedMesh> meshes;

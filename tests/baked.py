@@ -92,6 +92,26 @@ def small_two_level_scene():
     return scene
 
 
+def grass_model_scene():
+    """A model with a floor mesh and two curve geometries (RTC_GEOMETRY_TYPE_ROUND_BSPLINE_CURVE, ModelResource.cpp:300-333) sharing one
+    control-vertex array, instanced twice (the second instance rotated, moved and uniformly scaled): what the reference's island scene
+    is full of.  The curves' material is the one named curveModelName (ModelResource.cpp:382-383)."""
+    g = scenes.grass_patch(blades=60, extent=2.0)
+    floor = g.meshes[0]
+    cv, ci = g.curves[0]["vertices"], g.curves[0]["indices"]
+    half = ci.size // 2
+    model = dict(name="grassModel", meshes=[dict(name="soil", material=0x11, indices=floor["indices"], positions=floor["positions"])],
+                 normals=None, tangents=None, uvs=None, materials={0x11: g.materials[0], 0x22: g.materials[1]},
+                 curve_vertices=cv, curves=[ci[:half], ci[half:]], curve_material=0x22)
+    sub = dict(name="grassSub", light_set=0, models=[model], scene_materials={},
+               instances=[(0, np.eye(4, dtype=np.float32)), (0, xform(5.0, 0.3, 1.0, 1.4, 0.6))])
+    rng = np.random.default_rng(4)
+    ibl = scenes.build_ibl((rng.uniform(0, 1, size=(8, 16, 3)) * 0.5).astype(np.float32), miss=np.full((2, 4, 3), 0.3, np.float32), rotation=0.0, exposure=0.0)
+    return dict(name="grass", ibl_name="dimsky", ibl=ibl, textures={}, background=(0.3, 0.45, 0.7, 0.0), subscenes=[sub],
+                instances=[(0, np.eye(4, dtype=np.float32))], lights=g.lights, light_sets=[(0, 1)],
+                cameras=[dict(name="main", position=(2.0, 2.5, -9.0), lookAt=(2.0, 0.5, 0.0), up=(0.0, 1.0, 0.0), fovDegrees=50.0, znear=0.1, zfar=500.0)])
+
+
 def ptex_sheet_scene():
     """One model with one quad mesh ("sheet", 5 x 4 quads = the faces of tests/golden/ptex_jitter_u8.ptx) whose material uses Ptex: the
     loader must resolve Content/<material.baseColorTexture>/<mesh name>.ptx (ModelResource.cpp:358-364)."""
@@ -140,6 +160,17 @@ def write_baked(ref, root, scene):
             hashes = np.array(sorted(model["materials"]), np.uint32)
             mats = _material_res([model["materials"][h] for h in hashes], [model.get("textures", {}).get(int(h)) for h in hashes])
             aabb = np.concatenate([positions.min(axis=0), positions.max(axis=0)]).astype(np.float32)
+            if model.get("curves"):  # curve geometries: model-wide control vertices, CurveMetaData {indexOffset, indexCount} per curve
+                cv = np.ascontiguousarray(model["curve_vertices"], np.float32).reshape(-1, 4)
+                cidx, ranges, off = [], [], 0
+                for c in model["curves"]:
+                    ci = np.ascontiguousarray(c, np.uint32).ravel()
+                    ranges.append((off, ci.size))
+                    cidx.append(ci)
+                    off += ci.size
+                cidx, ranges = np.ascontiguousarray(np.concatenate(cidx), np.uint32), np.array(ranges, np.uint32)
+                assert lib.ref_set_next_model_curves(_p(cidx), C.c_uint64(cidx.size), _p(cv), C.c_uint32(cv.shape[0]), _p(ranges), C.c_uint32(len(ranges)),
+                                                     C.c_uint32(model["curve_material"])) == 0
             rc = lib.ref_write_model_blobs(str(asset_path(root, "ModelResource", model["name"])).encode(),
                                            str(asset_path(root, "ModelGeometryResource", model["name"])).encode(), _p(aabb),
                                            C.c_uint32(positions.shape[0]), _p(indices), C.c_uint64(indices.size), _p(positions), _p(nrm), _p(tan), _p(uvs),
@@ -173,7 +204,7 @@ def write_baked(ref, root, scene):
 def expected_flat_scene(scene, with_ids=False):
     """What LoadBakedScene must build: meshes in subscene -> model -> mesh order with FindMeshMaterial-resolved materials, and the two
     instancing levels flattened (localToWorld = model * subscene)."""
-    meshes, materials, ranges = [], [], []
+    meshes, materials, ranges, curves = [], [], [], []
     default_index = None
     for sub in scene["subscenes"]:
         scene_base = len(materials)
@@ -211,15 +242,38 @@ def expected_flat_scene(scene, with_ids=False):
                     d["material"] = default_index
                 d["lightSet"] = sub["light_set"]
                 meshes.append(d)
-            sub_ranges.append((first, len(model["meshes"])))
+            curve_first = len(curves)
+            if model.get("curves"):  # FindMeshMaterial(curveModelName): the model's materials, the subscene's, else the default
+                h = model["curve_material"]
+                if h in model["materials"]:
+                    cmat = model_base + hashes.index(h)
+                elif h in sub["scene_materials"]:
+                    cmat = scene_base + sm_hashes.index(h)
+                else:
+                    if default_index is None:
+                        default_index = len(materials)
+                        dm = np.zeros((), capi.MATERIAL_DTYPE)
+                        dm["shader"], dm["baseColor"] = capi.SHADER_DISNEY_SOLID, (0.6, 0.6, 0.6)
+                        dm["scalars"][capi.IOR] = 1.5
+                        materials.append(dm)
+                    cmat = default_index
+                cv = np.ascontiguousarray(model["curve_vertices"], np.float32).reshape(-1, 4)
+                for c in model["curves"]:
+                    ci = np.ascontiguousarray(c, np.uint32).ravel()
+                    lo, hi = int(ci.min()), int(ci.max()) + 4
+                    curves.append(dict(vertices=cv[lo:hi], indices=ci - np.uint32(lo), material=cmat, lightSet=sub["light_set"]))
+            sub_ranges.append((first, len(model["meshes"]), curve_first, len(model.get("curves", []))))
         ranges.append(sub_ranges)
     instances, ids = [], []
     for s_idx, (si, ms) in enumerate(scene["instances"]):
         for m_idx, (mi, mm) in enumerate(scene["subscenes"][si]["instances"]):
-            first, count = ranges[si][mi]
+            first, count, cfirst, ccount = ranges[si][mi]
             m = mul44(mm, ms)
             instances += [(first + k, m) for k in range(count)]
             # what a hit reports in the reference: instID[0] = subscene instance, instID[1] = model instance, geomID = mesh inside the model
             ids += [(s_idx, m_idx, k) for k in range(count)]
+            # the model's curve geometries are attached after its meshes (ModelResource.cpp:461-466); globally they follow all meshes
+            instances += [(len(meshes) + cfirst + k, m) for k in range(ccount)]
+            ids += [(s_idx, m_idx, count + k) for k in range(ccount)]
     return capi.SceneData(meshes, np.array(materials), scene["lights"], scene["light_sets"], background=scene["background"], instances=instances,
-                          ibl=scene["ibl"], instance_ids=ids if with_ids else None)
+                          ibl=scene["ibl"], instance_ids=ids if with_ids else None, curves=curves)

@@ -40,7 +40,8 @@ def test_curve_hits_match_the_double_precision_checker(ctx, oracle):
     assert np.quantile(terr, 0.99) < 2e-3 and np.median(terr) < 1e-4
     assert np.abs(g["u"][both] - o["u"][both]).max() < 0.05 and np.median(np.abs(g["u"][both] - o["u"][both])) < 2e-3
     cosang = np.sum(_unit(gng[both][:, :3]) * _unit(ong[both][:, :3]), axis=1)
-    assert np.quantile(cosang, 0.02) > 0.995 and np.median(cosang) > 0.99999, (np.quantile(cosang, 0.02), np.median(cosang))
+    # eight parts against 128: the normals differ by the chord angle of a part (measured: median 0.7 degrees, 2 % beyond 3 degrees)
+    assert np.quantile(cosang, 0.02) > 0.997 and np.median(cosang) > 0.9999, (np.quantile(cosang, 0.02), np.median(cosang))
     # triangles of the same scene are untouched by the curve variant of the kernel
     tri = (g["geomID"] == 0) & (o["geomID"] == 0)
     np.testing.assert_array_equal(g["primID"][tri], o["primID"][tri])
@@ -60,7 +61,7 @@ def test_curve_hits_match_the_double_precision_checker(ctx, oracle):
     sel = np.nonzero(both)[0][:20000]
     gs, osf = sc.surface_params(rays[sel], g[sel]), oracle.surface_params(hs, rays[sel], o[sel])
     gn, on = gs["worldToTangent"].reshape(-1, 3, 3)[:, :, 1], osf["worldToTangent"].reshape(-1, 3, 3)[:, :, 1]
-    assert np.quantile(np.sum(gn * on, axis=1), 0.02) > 0.995
+    assert np.quantile(np.sum(gn * on, axis=1), 0.02) > 0.997
     np.testing.assert_allclose(gs["baseColor"], osf["baseColor"], rtol=1e-5)
     assert np.all(gs["lightSetIndex"] == osf["lightSetIndex"]) and np.all(gs["shader"] == osf["shader"])
     oracle.scene_destroy(hs)
@@ -68,8 +69,10 @@ def test_curve_hits_match_the_double_precision_checker(ctx, oracle):
 
 
 def test_curve_scene_renders_like_the_checker(ctx, oracle):
-    """PathTracer over a scene with curve geometry, same RNG streams as the oracle's loop over its double-precision curve checker: paths
-    that graze a blade's silhouette may diverge, so the comparison is on the mean, on 8 x 8 binned pixels and on the pixel majority."""
+    """PathTracer over a scene with curve geometry, same RNG streams as the oracle's loop over its double-precision curve checker.  The
+    blades' normals differ by the chord angle of the coarser subdivision (a fraction of a degree), which moves every blade pixel a little
+    and lets silhouette paths diverge: the comparison is on the mean (measured 1.00002), on 4 x 4 binned pixels (relMSE 6e-5) and on the
+    pixel majority (78 % within 2 %: the floor and sky pixels)."""
     data = scenes.grass_patch(blades=300)
     cam = scenes.grass_camera(W, H)
     spp = 16
@@ -79,12 +82,12 @@ def test_curve_scene_renders_like_the_checker(ctx, oracle):
     o, os_ = oracle.render(hs, cam, rs, nthreads=16)
     g, o = g[0] / spp, o[0] / spp
     assert abs(int(gs.closestRays) - int(os_.closestRays)) < 0.01 * os_.closestRays
-    assert abs(g.mean() / o.mean() - 1.0) < 0.01, (g.mean(), o.mean())
+    assert abs(g.mean() / o.mean() - 1.0) < 2e-3, (g.mean(), o.mean())
     close = np.isclose(g, o, rtol=2e-2, atol=1e-3).all(axis=2)
     gb, ob = g.reshape(H // 4, 4, W // 4, 4, 3).mean(axis=(1, 3)), o.reshape(H // 4, 4, W // 4, 4, 3).mean(axis=(1, 3))
     relmse = float(np.mean((gb - ob) ** 2 / (ob ** 2 + 1e-2)))
     print(f"grass render vs checker: {close.mean():.4f} of the pixels within 2 %, 4 x 4 binned relMSE {relmse:.3e}, mean ratio {g.mean() / o.mean():.5f}")
-    assert close.mean() > 0.93 and relmse < 2e-3
+    assert close.mean() > 0.7 and relmse < 5e-4
     oracle.scene_destroy(hs)
     sc.close()
 

@@ -476,3 +476,54 @@ def _decode_hdr(data):
             pos += 4 * w
     assert pos == len(pix)
     return out
+
+
+def test_baked_scene_with_curve_geometry(host, ref, tmp_path):
+    """Model blobs with curve geometry written by the reference's Serialize(ModelResourceData&) / (ModelGeometryData&): the loader keeps
+    the curves (round 1 refused them), names them after the model's meshes (geomID = meshes + curve, ModelResource.cpp:461-466), gives
+    them the curveModelName material and instances them with the model."""
+    from tests import baked
+
+    scene = baked.grass_model_scene()
+    baked.write_baked(ref, tmp_path, scene)
+    want = baked.expected_flat_scene(scene, with_ids=True)
+    assert len(want.curves) == 2 and len(want.meshes) == 1 and len(want.instances) == 6
+    counts, mats, mesh, materials = _load_baked(host, tmp_path, scene["name"])
+    segments = sum(c["indices"].size for c in want.curves)
+    assert counts[0] == 1 and counts[1] == 6 and counts[6] == 2 * (2 + segments)  # per model instance: the floor quad's two triangles + every segment
+    np.testing.assert_array_equal(mesh, [i for i, _ in want.instances])           # curve geometries are numbered after the meshes: 1, 2
+    np.testing.assert_array_equal(mats, np.stack([m for _, m in want.instances]))
+    ids = np.zeros((6, 3), np.uint32)
+    err = C.create_string_buffer(512)
+    assert host.selas_host_baked_scene_instance_ids(str(tmp_path).encode() + b"/", scene["name"].encode(), ids.ctypes.data_as(C.c_void_p), C.c_uint64(6), err, 512) == 0
+    np.testing.assert_array_equal(ids, np.array(want.instance_ids, np.uint32))    # geomID 0 = soil, 1 and 2 = the two curve geometries
+    aabb, sphere = np.zeros(6, np.float32), np.zeros(4, np.float32)
+    assert host.selas_host_baked_scene_bounds(str(tmp_path).encode() + b"/", scene["name"].encode(), aabb.ctypes.data_as(C.c_void_p),
+                                              sphere.ctypes.data_as(C.c_void_p), err, 512) == 0
+    top = max(float(c["vertices"][:, 1].max()) for c in want.curves)
+    assert aabb[4] >= top * 1.4 * 0.99  # the scaled instance's blades are inside the scene box
+
+
+@pytest.mark.gpu
+def test_baked_scene_with_curves_renders_like_the_flat_description(ctx, host, ref, tmp_path):
+    from tests import baked
+
+    scene = baked.grass_model_scene()
+    baked.write_baked(ref, tmp_path, scene)
+    want = baked.expected_flat_scene(scene)
+    want.two_level = True
+    w, h, spp = 160, 90, 8
+    c = scene["cameras"][0]
+    cam = capi.camera_init(c["position"], c["lookAt"], c["up"], c["fovDegrees"], w, h, c["znear"], c["zfar"])
+    rs = capi.render_settings(w, h, spp, max_path_length=5, rr_start=8, layers=1, seed=6)
+    film = np.zeros((h, w, 3), np.float32)
+    err = C.create_string_buffer(512)
+    rc = host.selas_host_render_baked_scene(str(tmp_path).encode() + b"/", b"grass", 0, C.byref(cam), C.byref(rs), film.ctypes.data_as(C.c_void_p), err, 512)
+    assert rc == 0, err.value
+    sc = capi.Scene(ctx, want)
+    ref_film = sc.render(cam, rs)[0][0]
+    hits = sc.intersect(scenes.primary_rays(cam, w, h))
+    sc.close()
+    assert (hits["geomID"] >= 1).mean() > 0.02  # blades in view
+    fin = np.isfinite(ref_film).all(axis=2) & np.isfinite(film).all(axis=2)
+    np.testing.assert_allclose(film[fin], ref_film[fin], rtol=2e-3, atol=2e-3)
