@@ -931,7 +931,7 @@ int vcmAlloc(SelasContext* ctx, VcmBuffers* w, T** p, size_t count) {
     return SELAS_OK;
 }
 
-int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
+static int allocateVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     SelasContext* ctx = scene->ctx;
     VcmBuffers* w = (VcmBuffers*)scene->vcm;
     const uint32_t stride = maxPathLength > 3 ? maxPathLength - 3 : 0;  // light vertices have pathLength 1 .. max-3 (VCM.cpp:509)
@@ -990,6 +990,17 @@ int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     SELAS_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&w->evCounts, cudaEventDisableTiming));
     // the hash grid is rebuilt every iteration over a varying number of vertices: size it once for the worst case
     return hashGridReserve(ctx, &w->grid, nv, vmCount);
+}
+
+// A failed allocation half-way (2 M paths x 7 vertex slots is 3 GB) must not leave a half-null buffer set behind that the next call would
+// take for "already the right size": whatever was allocated is released and the scene has no VCM scratch until a call succeeds.
+int ensureVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
+    const int rc = allocateVcm(scene, vmCount, maxPathLength);
+    if (rc) {
+        freeVcm(scene);
+        cudaGetLastError();
+    }
+    return rc;
 }
 
 struct EventSpans {
