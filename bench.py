@@ -118,16 +118,13 @@ class ClockSampler:
 
 
 def captured_traffic_per_ray():
-    """DRAM bytes per closest-hit ray from the committed `ncu --set full` capture of traceKernel<0> on this workload
-    (profiles/r1_trace_kernel_metrics.csv, bounce-0 launch of 8,294,400 rays): dram__bytes_read.sum + dram__bytes_write.sum."""
-    p = ROOT / "profiles" / "r1_trace_kernel_metrics.csv"
+    """DRAM bytes per closest-hit ray from the committed `ncu --set full` capture of EVERY traceKernel<0> launch of one 4-spp step of this
+    workload on the final tree (profiles/r2_trace_kernel_metrics.csv, summed in profiles/r2_trace_dram_per_step.json):
+    (dram__bytes_read.sum + dram__bytes_write.sum over the 16 closest-hit launches) / (closest-hit rays of that step)."""
+    p = ROOT / "profiles" / "r2_trace_dram_per_step.json"
     try:
-        import csv
-        rows = list(csv.reader(l for l in p.read_text().splitlines() if not l.startswith("#")))
-        hdr, first = rows[0], rows[1]
-        rd = float(first[hdr.index("dram__bytes_read.sum [Gbyte]")]) * 1e9
-        wr = float(first[hdr.index("dram__bytes_write.sum [Mbyte]")]) * 1e6
-        return (rd + wr) / (WIDTH * HEIGHT * 4), str(p.relative_to(ROOT))
+        d = json.loads(p.read_text())
+        return float(d["closest"]["dram"]) / float(d["closest"]["rays"]), str(p.relative_to(ROOT))
     except Exception:
         return None, None
 

@@ -109,6 +109,7 @@ struct SelasScene {
     std::vector<void*> allocations;  // everything cudaMalloc'ed for this scene
     SelasBvhStats stats{};
     bool usesPtex = false;  // any mesh carries a Ptex texture: selects the shade kernel built with the lookup
+    float boundsCenter[3] = {0.f, 0.f, 0.f};  // centre of the scene's box (ray binning quadrants)
     uint32_t topNodeCount = 0;  // leading BVH8 nodes (whole levels) the trace kernels stage in shared memory
     // SELAS_SCENE_INSTANCE_IDS: reported (instID0, instID1, geomID) -> flat instance index, for hits handed back to selas_cuda_surface_params
     std::map<std::array<uint32_t, 3>, uint32_t> instanceIdLookup;
@@ -145,7 +146,7 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
                            float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream);
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
-                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream);
+                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order = nullptr);
 
 // shade.cu
 constexpr uint32_t kMaterialBinWords = 64;  // = kBinCount of the pre-shade counting sort

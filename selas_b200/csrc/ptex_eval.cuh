@@ -663,6 +663,18 @@ SELAS_D void ptexApplyPiece(const PtexGpu& tx, const PtexFace& f, int faceid, co
     for (int y = 0; y < 4; ++y) {
         if (y < p.vw) {
             float row[3] = {0.f, 0.f, 0.f};
+            // u8 RGB rows: the 12 bytes of the four texels come in as four aligned 32-bit words and three funnel shifts instead of
+            // twelve single-byte loads (profiles/r1_ptex_kernel_metrics.csv: 48 byte loads per piece); the pool is padded by 16 bytes
+            // and every face block starts 16-byte aligned, so the words around the row are always inside the allocation
+            uint32_t packed[3] = {0u, 0u, 0u};
+            if (DT == 0 && NT == 3) {
+                const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(rowPtr) & 3u);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowPtr - a);
+                const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+                packed[0] = __funnelshift_r(w0, w1, a * 8u);
+                packed[1] = __funnelshift_r(w1, w2, a * 8u);
+                packed[2] = __funnelshift_r(w2, w3, a * 8u);
+            }
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 if (x < p.uw) {
@@ -670,7 +682,13 @@ SELAS_D void ptexApplyPiece(const PtexGpu& tx, const PtexFace& f, int faceid, co
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         if (NT == 3 || c < nchan) {
-                            float t = ptexTexelT<DT>(rowPtr, (size_t)(x * nt + c));
+                            float t;
+                            if (DT == 0 && NT == 3) {
+                                const int k = 3 * x + c;
+                                t = (float)((packed[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                            } else {
+                                t = ptexTexelT<DT>(rowPtr, (size_t)(x * nt + c));
+                            }
                             row[c] = (x == 0) ? t * w : row[c] + t * w;
                         }
                     }

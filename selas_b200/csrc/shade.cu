@@ -247,6 +247,7 @@ int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t str
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t kBinCount = 64;  // material bins of the pre-shade counting sort (63 materials + miss)
 constexpr uint32_t kCounterStride = 8;  // words per bounce in WavefrontBuffers::counters
+constexpr uint32_t kEstimateBounces = 64;  // bounces whose queue lengths are read back for the shade launches' grid estimates
 #define FLAG_DELTA_ONLY (1u << 16)
 #define FLAG_IN_MEDIUM (1u << 17)
 
@@ -302,6 +303,8 @@ struct WavefrontBuffers {
     float4* shadowPayload = nullptr;
     float* ptexRgb = nullptr;      // Ptex stage output, 3 floats per path (scenes with Ptex materials only)
     uint32_t* order = nullptr;     // material-sorted visiting order of the hit queue
+    uint32_t* rayOrder = nullptr;  // direction-sorted visiting order of the ray queue (SELAS_RAY_SORT)
+    uint32_t* rayBins = nullptr;   // per iteration: 64 counts + 64 cursors
     uint32_t* bins = nullptr;      // per iteration: 64 counts + 64 cursors
     // kCounterStride per iteration: [0] queue length of this iteration, [1] shadow rays made by the previous one, [2] closest-hit fetch
     // counter, [3] shadow fetch counter, [4] shade chunk counter
@@ -313,6 +316,13 @@ struct WavefrontBuffers {
     unsigned long long* totals = nullptr;
     unsigned long long* h_totals = nullptr;  // pinned readback
     uint32_t* h_counts = nullptr;            // pinned readback of one queue length (long paths: periodic early-out check)
+    // Queue lengths of an earlier pass, read back asynchronously at its end: the shade launches of later passes of the same shape size
+    // their one-shot grids with them (never waited for: used when the copy has arrived, else the persistent launch shape is taken).
+    uint32_t* h_passCounts = nullptr;        // pinned, kEstimateBounces * kCounterStride words
+    cudaEvent_t evPassCounts = nullptr;
+    bool passCountsPending = false;
+    std::vector<uint32_t> estimate;          // per bounce, 0 = unknown
+    uint32_t estimateCount = 0;              // pass size the estimates belong to
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool spanOpen = false;         // ev0 recorded at the first launch since the last collect
     uint64_t pendingSamples = 0, pendingLaunches = 0;
@@ -333,11 +343,15 @@ static void destroyWavefront(WavefrontBuffers* w) {
     cudaFree(w->shadowPayload);
     cudaFree(w->counters);
     cudaFree(w->order);
+    cudaFree(w->rayOrder);
+    cudaFree(w->rayBins);
     cudaFree(w->ptexRgb);
     cudaFree(w->bins);
     cudaFree(w->totals);
     if (w->h_totals) cudaFreeHost(w->h_totals);
     if (w->h_counts) cudaFreeHost(w->h_counts);
+    if (w->h_passCounts) cudaFreeHost(w->h_passCounts);
+    if (w->evPassCounts) cudaEventDestroy(w->evPassCounts);
     if (w->ev0) cudaEventDestroy(w->ev0);
     if (w->ev1) cudaEventDestroy(w->ev1);
     delete w;
@@ -383,11 +397,15 @@ static int ensureWavefront(SelasScene* scene, uint32_t capacity, uint32_t iterat
     alloc((void**)&w->shadowPayload, sizeof(float4) * (size_t)capacity * shadowPerPath);
     alloc((void**)&w->counters, sizeof(uint32_t) * w->counterSlots);
     alloc((void**)&w->order, sizeof(uint32_t) * (size_t)capacity);
+    alloc((void**)&w->rayOrder, sizeof(uint32_t) * (size_t)capacity);
+    alloc((void**)&w->rayBins, sizeof(uint32_t) * 2 * kBinCount * (size_t)binSets);
     if (scene->usesPtex) alloc((void**)&w->ptexRgb, sizeof(float) * 3 * (size_t)capacity);
     alloc((void**)&w->bins, sizeof(uint32_t) * 2 * kBinCount * (size_t)binSets);
     alloc((void**)&w->totals, sizeof(unsigned long long) * 8);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_totals, sizeof(unsigned long long) * 8);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_counts, sizeof(uint32_t) * 4);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&w->h_passCounts, sizeof(uint32_t) * kEstimateBounces * kCounterStride);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->evPassCounts, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&w->ev1);
     if (e == cudaSuccess) e = cudaMemsetAsync(w->totals, 0, sizeof(unsigned long long) * 8, stream);
@@ -507,6 +525,56 @@ __global__ void __launch_bounds__(256) binScatterKernel(SceneGpu sc, uint32_t n,
     }
 }
 
+// ---- ray binning: counting sort of a ray queue by direction octant and origin quadrant -------------------------------------------
+// The reference sorts the rays of a bounce by direction category before it traces them (PathTracingBatcher.cpp:162 DetermineRayCategory,
+// DeferredPathTracer.cpp:151-232).  Here: 8 octants x 4 quadrants of the scene's (x, z) extent = 32 bins; the trace kernel visits the
+// queue through the resulting order (trace.cuh).  Off by default: see SELAS_RAY_SORT in renderPathTracer.
+SELAS_D uint32_t rayBinOf(const SelasRay* rays, uint32_t i, float cx, float cz) {
+    const float4* rp = reinterpret_cast<const float4*>(rays + i);
+    const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+    return (r1.x < 0.f ? 4u : 0u) | (r1.y < 0.f ? 2u : 0u) | (r1.z < 0.f ? 1u : 0u) | (r0.x < cx ? 8u : 0u) | (r0.z < cz ? 16u : 0u);
+}
+__global__ void __launch_bounds__(256) rayBinCountKernel(uint32_t n, const uint32_t* __restrict__ nPtr, const SelasRay* __restrict__ rays, float cx, float cz,
+                                                         uint32_t* __restrict__ bins) {
+    __shared__ uint32_t local[kBinCount];
+    if (nPtr) n = min(n, *nPtr);
+    if (threadIdx.x < kBinCount) local[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&local[rayBinOf(rays, i, cx, cz)], 1u);
+    __syncthreads();
+    if (threadIdx.x < kBinCount && local[threadIdx.x]) atomicAdd(bins + threadIdx.x, local[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) rayBinScatterKernel(uint32_t n, const uint32_t* __restrict__ nPtr, const SelasRay* __restrict__ rays, float cx, float cz,
+                                                           uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+    if (nPtr) n = min(n, *nPtr);
+    __shared__ uint32_t local[kBinCount];
+    __shared__ uint32_t base[kBinCount];
+    const uint32_t tile = blockDim.x * 8;
+    for (uint32_t start = blockIdx.x * tile; start < n; start += gridDim.x * tile) {
+        if (threadIdx.x < kBinCount) local[threadIdx.x] = 0;
+        __syncthreads();
+        uint32_t key[8], rank[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t i = start + k * blockDim.x + threadIdx.x;
+            key[k] = 0xFFFFFFFFu;
+            if (i < n) {
+                key[k] = rayBinOf(rays, i, cx, cz);
+                rank[k] = atomicAdd(&local[key[k]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kBinCount) base[threadIdx.x] = local[threadIdx.x] ? atomicAdd(cursor + threadIdx.x, local[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t i = start + k * blockDim.x + threadIdx.x;
+            if (i < n) order[base[key[k]] + rank[k]] = i;
+        }
+        __syncthreads();
+    }
+}
+
 // Material-sorted visiting order of a hit queue for callers outside this file (the VCM light pass).  bins: 2 * kMaterialBinWords
 // zeroed words of scratch; order: n words.
 int launchMaterialOrder(SelasScene* scene, uint32_t n, const SelasHit* d_hits, uint32_t* d_bins, uint32_t* d_order, cudaStream_t stream) {
@@ -529,7 +597,7 @@ struct ShadeParams {
 #ifndef SELAS_SHADE_MIN_CTAS
 #define SELAS_SHADE_MIN_CTAS 4
 #endif
-template <int INTEGRATOR>
+template <int INTEGRATOR, bool ONESHOT>
 __global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGpu sc, ShadeParams prm, const uint32_t* __restrict__ order, uint32_t nMax,
                                                    const SelasRay* __restrict__ rays, const SelasHit* __restrict__ hits,
                                                    const float4* __restrict__ thrPix, const uint2* __restrict__ rngFlags,
@@ -542,17 +610,25 @@ __global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGp
     // The queue length lives in device memory (nPtr; nMax is the launch's upper bound), so the host never waits for it: the grid is
     // persistent and walks the queue with a CTA-uniform stride.
     const uint32_t n = nPtr ? min(nMax, *nPtr) : nMax;
-    // CTAs pull chunks of 128 queue slots from a counter, in queue order, so the resident CTAs always work on one contiguous window of
-    // the material-sorted queue.  Measured on configs[2] (ms of shade + material sort per 4-spp step): static grid-wide stride 4.7 (CTAs
-    // drift apart across materials), per-warp chunks of 32 slots 4.6 (four times the traffic on the one counter), these CTA chunks 4.3,
-    // the one-shot launch of round 1 -- whose grid the host had to size from a read-back queue length -- 3.9.
+    // Two launch shapes.  ONESHOT: the grid covers the queue (one chunk of 128 slots per CTA, the hardware hands out CTAs in queue
+    // order) -- possible when the host has an estimate of the queue length from an earlier pass (renderPathTracer); a stride loop covers
+    // what an estimate that came out too small leaves over.  Otherwise a persistent grid whose CTAs pull chunks from a counter, in queue
+    // order, so the resident CTAs always work on one contiguous window of the material-sorted queue.  Measured on configs[2] (ms of shade
+    // + material sort per 4-spp step): static grid-wide stride 4.7 (CTAs drift apart across materials), per-warp chunks of 32 slots
+    // 4.6, CTA chunks of 128 / 256 / 512 / 1024 slots 4.4 / 4.5 / 4.8 / 6.1, one-shot 3.9.
     __shared__ uint32_t sChunkBase;
-  for (;;) {
-    if (threadIdx.x == 0) sChunkBase = atomicAdd(chunkCounter, blockDim.x);
-    __syncthreads();
-    const uint32_t base = sChunkBase;
-    __syncthreads();
+  for (uint32_t turn = 0;; ++turn) {
+    uint32_t base;
+    if (ONESHOT) {
+        base = (blockIdx.x + turn * gridDim.x) * blockDim.x;
+    } else {
+        if (threadIdx.x == 0) sChunkBase = atomicAdd(chunkCounter, blockDim.x);
+        __syncthreads();
+        base = sChunkBase;
+        __syncthreads();
+    }
     if (base >= n) break;
+    {
     const uint32_t slotIndex = base + threadIdx.x;
     // material-sorted visiting order (binScatterKernel): lanes of a warp share a material, hence code path
     const uint32_t i = (order && slotIndex < n) ? __ldg(order + slotIndex) : slotIndex;
@@ -785,12 +861,13 @@ __global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGp
             shadowPayload[slot] = shPayload2;
         }
     }
+   }
   }
 }
 
 // Ray totals of one pass, summed on the device so that nothing has to be read back per bounce: closest-hit rays = sum of the queue lengths,
 // occlusion rays = sum of the shadow-queue lengths (counter layout: see renderPathTracer).
-__global__ void passTotalsKernel(const uint32_t* __restrict__ counters, uint32_t iterations, unsigned long long* __restrict__ totals) {
+__global__ void passTotalsKernel(uint32_t* __restrict__ counters, uint32_t iterations, unsigned long long* __restrict__ totals, uint32_t passSize) {
     unsigned long long closest = 0, shadow = 0;
     for (uint32_t it = threadIdx.x; it < iterations; it += 32) {
         closest += counters[kCounterStride * it];
@@ -803,6 +880,8 @@ __global__ void passTotalsKernel(const uint32_t* __restrict__ counters, uint32_t
     if (threadIdx.x == 0) {
         totals[0] += closest;
         totals[1] += shadow;
+        counters[5] = iterations;  // spare words of the first set: what the host needs to read the queue lengths as grid estimates
+        counters[6] = passSize;
     }
 }
 
@@ -893,10 +972,15 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     static int shadeResident[2] = {0, 0};
     if (!shadeResident[deferred ? 1 : 0]) {
         int r = 0;
-        cudaError_t e = deferred ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, shadeKernel<1>, 128, 0)
-                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, shadeKernel<0>, 128, 0);
+        cudaError_t e = deferred ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, shadeKernel<1, false>, 128, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&r, shadeKernel<0, false>, 128, 0);
         shadeResident[deferred ? 1 : 0] = (e == cudaSuccess && r > 0) ? r : 4;
     }
+    // SELAS_RAY_SORT=b: from bounce b on, the ray queue is traced in direction-octant / origin-quadrant order (the reference sorts its ray
+    // batches by direction category, PathTracingBatcher.cpp:162).  Default: off -- see DESIGN.md for the measurement.
+    static const uint32_t raySortFrom = getenv("SELAS_RAY_SORT") ? (uint32_t)atoi(getenv("SELAS_RAY_SORT")) : 0xFFFFFFFFu;
+    const float raySortCx = scene->boundsCenter[0], raySortCz = scene->boundsCenter[2];  // origin quadrants about the scene's centre
+    static const bool shadeOneShot = !(getenv("SELAS_SHADE_ONESHOT") && atoi(getenv("SELAS_SHADE_ONESHOT")) == 0);
     static const int shadeWaves = getenv("SELAS_SHADE_WAVES") ? std::max(1, atoi(getenv("SELAS_SHADE_WAVES"))) : 2;
 
     if (!w->spanOpen) {
@@ -907,8 +991,17 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     for (uint64_t first = 0; first < totalPaths; first += capacity) {
         const uint32_t count = (uint32_t)std::min<uint64_t>(capacity, totalPaths - first);
         const uint32_t slotSets = w->counterSlots / kCounterStride;
+        if (w->passCountsPending && cudaEventQuery(w->evPassCounts) == cudaSuccess) {  // an earlier pass's queue lengths have arrived
+            w->passCountsPending = false;
+            const uint32_t nb = std::min<uint32_t>(kEstimateBounces, w->h_passCounts[kCounterStride * 0 + 5]);
+            w->estimateCount = w->h_passCounts[kCounterStride * 0 + 6];
+            w->estimate.assign(nb, 0u);
+            for (uint32_t b = 0; b < nb; ++b) w->estimate[b] = std::max<uint32_t>(1u, w->h_passCounts[kCounterStride * b]);
+        }
+        cudaGetLastError();  // cudaErrorNotReady of the query is not an error
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->bins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)slotSets, stream));
+        if (raySortFrom < rs.maxPathLength) SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->rayBins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)slotSets, stream));
         size_t t0 = timers.begin(stream);
         generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, activePixels,
                                                               stride, rs.pixelSampler, w->rays[0], w->thrPix[0], w->rngFlags[0], w->counters);
@@ -922,7 +1015,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         for (uint32_t it = 0; it < rs.maxPathLength; ++it, ++slot) {
             if (longPaths && slot == kCheckEvery) {
                 // the sets in use are exhausted: fold them into the totals, look at the queue length, and start over at set 0
-                passTotalsKernel<<<1, 32, 0, stream>>>(w->counters, slot, w->totals);
+                passTotalsKernel<<<1, 32, 0, stream>>>(w->counters, slot, w->totals, count);
                 SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_counts, w->counters + kCounterStride * (size_t)slot, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
                 SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(stream));
                 const uint32_t alive = w->h_counts[0];
@@ -935,9 +1028,18 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             }
             uint32_t* ctr = w->counters + kCounterStride * (size_t)slot;  // [0] = this bounce's queue length
             uint32_t* next = ctr + kCounterStride;                         // [0] = next queue length, [1] = shadow rays of this bounce
-            // closest hit over the dense path queue
+            // closest hit over the dense path queue (optionally through a direction-sorted order)
             t0 = timers.begin(stream);
-            rc = launchIntersectIndirect(scene, ctr, count, w->rays[cur], w->hits, ctr + 2, d_totals, stream);
+            const uint32_t* rayOrder = nullptr;
+            if (it >= raySortFrom) {
+                uint32_t* rb = w->rayBins + 2 * kBinCount * (size_t)slot;
+                rayBinCountKernel<<<sortGrid, 256, 0, stream>>>(count, ctr, w->rays[cur], raySortCx, raySortCz, rb);
+                binScanKernel<<<1, 32, 0, stream>>>(rb, rb + kBinCount);
+                rayBinScatterKernel<<<sortGrid, 256, 0, stream>>>(count, ctr, w->rays[cur], raySortCx, raySortCz, rb + kBinCount, w->rayOrder);
+                rayOrder = w->rayOrder;
+                launches += 3;
+            }
+            rc = launchIntersectIndirect(scene, ctr, count, w->rays[cur], w->hits, ctr + 2, d_totals, stream, rayOrder);
             if (rc) return rc;
             timers.end(1, t0, stream);
             t0 = timers.begin(stream);
@@ -954,16 +1056,24 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 ptexStageKernel<<<ptexGrid, 128, 0, stream>>>(scene->gpu, count, w->hits, w->ptexRgb, ctr);
                 ++launches;
             }
-            if (deferred)
-                shadeKernel<1><<<shadeGrid, 128, 0, stream>>>(scene->gpu, prm, order, count, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
-                                                              w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
-                                                              w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, next, d_film,
-                                                              scene->usesPtex ? w->ptexRgb : nullptr, ctr, ctr + 4);
-            else
-                shadeKernel<0><<<shadeGrid, 128, 0, stream>>>(scene->gpu, prm, order, count, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur],
-                                                              w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],
-                                                              w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, next, d_film,
-                                                              scene->usesPtex ? w->ptexRgb : nullptr, ctr, ctr + 4);
+            // one-shot grid when an earlier pass of this shape told how long this bounce's queue gets (3 % + 8 CTAs of slack; what a low
+            // estimate leaves over is covered by the kernel's stride loop), else the persistent shape
+            const uint32_t est = (!longPaths && w->estimateCount == count && it < w->estimate.size()) ? w->estimate[it] : 0u;
+            const bool oneShot = est != 0u && shadeOneShot;
+            const int grid = oneShot ? (int)std::min<uint64_t>(divUp(count, 128), divUp((uint64_t)est + est / 32u, 128) + 8u) : shadeGrid;
+#define SELAS_SHADE_LAUNCH(INTEGRATOR, ONESHOT)                                                                                                  \
+    shadeKernel<INTEGRATOR, ONESHOT><<<grid, 128, 0, stream>>>(scene->gpu, prm, order, count, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur], \
+                                                              w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],       \
+                                                              w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, next, d_film,                 \
+                                                              scene->usesPtex ? w->ptexRgb : nullptr, ctr, ctr + 4)
+            if (deferred) {
+                if (oneShot) SELAS_SHADE_LAUNCH(1, true);
+                else SELAS_SHADE_LAUNCH(1, false);
+            } else {
+                if (oneShot) SELAS_SHADE_LAUNCH(0, true);
+                else SELAS_SHADE_LAUNCH(0, false);
+            }
+#undef SELAS_SHADE_LAUNCH
             timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             {
@@ -978,8 +1088,14 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             cur ^= 1;
         }
         if (slot) {
-            passTotalsKernel<<<1, 32, 0, stream>>>(w->counters, slot, w->totals);
+            passTotalsKernel<<<1, 32, 0, stream>>>(w->counters, slot, w->totals, count);
             ++launches;
+            if (!longPaths && !w->passCountsPending) {  // queue lengths of this pass for the grid estimates of later ones (not waited for)
+                SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(w->h_passCounts, w->counters, sizeof(uint32_t) * kCounterStride * std::min<uint32_t>(slot, kEstimateBounces),
+                                                      cudaMemcpyDeviceToHost, stream));
+                SELAS_CUDA_CHECK(ctx, cudaEventRecord(w->evPassCounts, stream));
+                w->passCountsPending = true;
+            }
         }
     }
     w->pendingSamples += totalPaths;

@@ -386,6 +386,11 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     cudaEventElapsedTime(&ms, ev0, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    {
+        uint32_t hb[6];
+        SELAS_CUDA_CHECK(ctx, cudaMemcpy(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 3; ++k) scene->boundsCenter[k] = 0.5f * (floatUnflip(hb[k]) + floatUnflip(hb[3 + k]));
+    }
     scene->gpu.nodes = tree.nodes;
     scene->gpu.tris = tree.tris;
     scene->gpu.nodeCount = tree.nodeCount;
@@ -618,6 +623,7 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
     scene->gpu.nodeCount = (uint32_t)totalNodes;
     scene->gpu.triCount = (uint32_t)totalTris;
     scene->gpu.traceInstances = d_table;
+    for (int k = 0; k < 3; ++k) scene->boundsCenter[k] = 0.5f * (tlo[k] + thi[k]);
     scene->gpu.curvePool = d_pool2;
     scene->topNodeCount = d_pool2 ? 0u : chooseTopNodeCount(top.levelEnds);
     scene->stats.nodeCount = (uint32_t)totalNodes;
@@ -717,12 +723,12 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
 // Wavefront variants: the queue length lives in device memory (or n is exact when d_n is null); d_rayCounter must
 // already be zero.  totals != null selects the counting build of the same kernel (SELAS_RENDER_COUNT_TRAVERSAL).
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
-                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
+                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order) {
     SelasContext* ctx = scene->ctx;
     if (d_totals)
-        SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, d_totals);
+        SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, d_totals, d_order);
     else
-        SELAS_TRACE_GO(0, false, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(0, false, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, nullptr, d_order);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
                                                                    float4* __restrict__ ng, uint32_t* __restrict__ counts,
                                                                    const float4* __restrict__ payload, float* __restrict__ film,
                                                                    uint32_t* __restrict__ nextRay,
-                                                                   unsigned long long* __restrict__ totals) {
+                                                                   unsigned long long* __restrict__ totals,
+                                                                   const uint32_t* __restrict__ order = nullptr) {
     constexpr bool ANY = MODE != 0;
     static_assert(!(INST && SELAS_TRI_POSTPONE_DIV), "parked triangle groups are not carried across instance boundaries");
     // TOP: hot top levels in shared memory (north star (1)): every ray starts at the root and the first levels are visited by all of
@@ -107,6 +108,9 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
             if (!active) {
                 uint32_t idx = base + __popc(idle & ltMask);
                 if (idx < n) {
+                    // order != null: the queue is visited in a direction-sorted order (rays of one octant and region side by side in a
+                    // warp); results still land at the ray's own index
+                    if (order) idx = __ldg(order + idx);
                     const float4* rp = reinterpret_cast<const float4*>(rays + idx);
                     float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
                     o = v3(r0.x, r0.y, r0.z);
