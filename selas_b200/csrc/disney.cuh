@@ -99,6 +99,14 @@ static SELAS_HDN float ggxD(V3 wm, float ax, float ay) {  // :75-84
     float hx2 = sq(wm.x), hy2 = sq(wm.z), c2 = cos2Theta(wm);
     return 1.0f / (SELAS_PI * ax * ay * sq(hx2 / sq(ax) + hy2 / sq(ay) + c2));
 }
+// sin / cos evaluated in double and rounded once (see sampleVndf); -DSELAS_FLOAT_SINCOS builds the plain sinf / cosf form for A/B
+#ifdef SELAS_FLOAT_SINCOS
+SELAS_HD float sinRounded(float x) { return sinf(x); }
+SELAS_HD float cosRounded(float x) { return cosf(x); }
+#else
+SELAS_HD float sinRounded(float x) { return (float)sin((double)x); }
+SELAS_HD float cosRounded(float x) { return (float)cos((double)x); }
+#endif
 static SELAS_HDN V3 sampleVndf(V3 wo, float ax, float ay, float u1, float u2) {  // :105-126
     V3 v = normalize(v3(wo.x * ax, wo.y, wo.z * ay));
     V3 t1 = (v.y < 0.9999f) ? normalize(cross(v, v3(0.f, 1.f, 0.f))) : v3(1.f, 0.f, 0.f);
@@ -109,8 +117,8 @@ static SELAS_HDN V3 sampleVndf(V3 wo, float ax, float ay, float u1, float u2) { 
     // sin / cos of the disc angle in double, rounded once: glibc's sinf / cosf (what the reference links) are correctly rounded in
     // practice, CUDA's are within 2 ulp -- and for small u1 this sampler turns a 1-ulp difference of p1 / p2 into a jump of a whole
     // float32 quantum of the result (1.5e-5 in wi, up to 6e-4 in the pdf: tests/test_gpu_parity.py::test_bsdf_sample_parity)
-    float p1 = r * (float)cos((double)phi);
-    float p2 = r * (float)sin((double)phi) * ((u2 < a) ? 1.0f : v.y);
+    float p1 = r * cosRounded(phi);
+    float p2 = r * sinRounded(phi) * ((u2 < a) ? 1.0f : v.y);
     V3 n = p1 * t1 + p2 * t2 + sqrtf(maxf_(0.0f, 1.0f - p1 * p1 - p2 * p2)) * v;
     return normalize(v3(ax * n.x, n.y, ay * n.z));
 }
@@ -310,7 +318,7 @@ SELAS_HD bool sampleDisney(Rng& rng, const Surface& s, const DisneyFrame& f, V3 
         float cosT = sqrtf(maxf_(0.f, (1.0f - powf(a2, 1.0f - r0)) / (1.0f - a2)));
         float sinT = sqrtf(maxf_(0.f, 1.0f - cosT * cosT));
         float phi = SELAS_TWO_PI * r1;
-        V3 wm = v3(sinT * (float)cos((double)phi), cosT, sinT * (float)sin((double)phi));  // rounded once, like sampleVndf
+        V3 wm = v3(sinT * cosRounded(phi), cosT, sinT * sinRounded(phi));  // rounded once, like sampleVndf
         if (dot(wm, wo) < 0.0f) wm = -wm;
         V3 wi = reflect_(wm, wo);
         if (dot(wi, wo) < 0.0f) {
@@ -335,7 +343,7 @@ SELAS_HD bool sampleDisney(Rng& rng, const Surface& s, const DisneyFrame& f, V3 
         float r0 = rng.next(), r1 = rng.next();
         float r = sqrtf(r0);
         float theta = SELAS_TWO_PI * r1;
-        V3 wi = sign * v3(r * (float)cos((double)theta), sqrtf(maxf_(0.0f, 1 - r0)), r * (float)sin((double)theta));  // rounded once
+        V3 wi = sign * v3(r * cosRounded(theta), sqrtf(maxf_(0.0f, 1 - r0)), r * sinRounded(theta));  // rounded once
         V3 wm = normalize(wi + wo);
         float dotNL = cosTheta(wi);
         if (dotNL == 0.0f) {

@@ -606,28 +606,30 @@ __global__ void __launch_bounds__(128, SELAS_SHADE_MIN_CTAS) shadeKernel(SceneGp
                                                    float4* __restrict__ mediumOut, SelasRay* __restrict__ shadowRays,
                                                    float4* __restrict__ shadowPayload, uint32_t* __restrict__ counters,
                                                    float* __restrict__ film, const float* __restrict__ ptexRgb, const uint32_t* __restrict__ nPtr,
-                                                   uint32_t* __restrict__ chunkCounter) {
+                                                   uint32_t* __restrict__ chunkCounter, uint32_t firstChunk) {
     // The queue length lives in device memory (nPtr; nMax is the launch's upper bound), so the host never waits for it: the grid is
     // persistent and walks the queue with a CTA-uniform stride.
     const uint32_t n = nPtr ? min(nMax, *nPtr) : nMax;
     // Two launch shapes.  ONESHOT: the grid covers the queue (one chunk of 128 slots per CTA, the hardware hands out CTAs in queue
-    // order) -- possible when the host has an estimate of the queue length from an earlier pass (renderPathTracer); a stride loop covers
-    // what an estimate that came out too small leaves over.  Otherwise a persistent grid whose CTAs pull chunks from a counter, in queue
-    // order, so the resident CTAs always work on one contiguous window of the material-sorted queue.  Measured on configs[2] (ms of shade
-    // + material sort per 4-spp step): static grid-wide stride 4.7 (CTAs drift apart across materials), per-warp chunks of 32 slots
-    // 4.6, CTA chunks of 128 / 256 / 512 / 1024 slots 4.4 / 4.5 / 4.8 / 6.1, one-shot 3.9.
+    // order) -- possible when the host has an estimate of the queue length from an earlier pass (renderPathTracer); what an estimate
+    // that came out too small leaves over is covered by a second, persistent launch starting at chunk `firstChunk` (a stride loop in the
+    // one-shot kernel itself costs 0.26 ms per step: profiles/r2_ab_shade_loop.jsonl).  Otherwise a persistent grid whose CTAs pull chunks
+    // from a counter, in queue order, so the resident CTAs always work on one contiguous window of the material-sorted queue.  Measured on
+    // configs[2] (ms of shade + material sort per 4-spp step): static grid-wide stride 4.7 (CTAs drift apart across materials), per-warp
+    // chunks of 32 slots 4.6, CTA chunks of 128 / 256 / 512 / 1024 slots 4.4 / 4.5 / 4.8 / 6.1, one-shot 4.0.
     __shared__ uint32_t sChunkBase;
   for (uint32_t turn = 0;; ++turn) {
     uint32_t base;
     if (ONESHOT) {
-        base = (blockIdx.x + turn * gridDim.x) * blockDim.x;
+        base = (firstChunk + blockIdx.x) * blockDim.x;
     } else {
         if (threadIdx.x == 0) sChunkBase = atomicAdd(chunkCounter, blockDim.x);
         __syncthreads();
-        base = sChunkBase;
+        base = firstChunk * blockDim.x + sChunkBase;
         __syncthreads();
     }
     if (base >= n) break;
+    if (ONESHOT && turn > 0) break;
     {
     const uint32_t slotIndex = base + threadIdx.x;
     // material-sorted visiting order (binScatterKernel): lanes of a warp share a material, hence code path
@@ -1057,23 +1059,28 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 ++launches;
             }
             // one-shot grid when an earlier pass of this shape told how long this bounce's queue gets (3 % + 8 CTAs of slack; what a low
-            // estimate leaves over is covered by the kernel's stride loop), else the persistent shape
+            // estimate leaves over is covered by a persistent launch behind it, which normally finds nothing), else the persistent shape
             const uint32_t est = (!longPaths && w->estimateCount == count && it < w->estimate.size()) ? w->estimate[it] : 0u;
             const bool oneShot = est != 0u && shadeOneShot;
-            const int grid = oneShot ? (int)std::min<uint64_t>(divUp(count, 128), divUp((uint64_t)est + est / 32u, 128) + 8u) : shadeGrid;
-#define SELAS_SHADE_LAUNCH(INTEGRATOR, ONESHOT)                                                                                                  \
-    shadeKernel<INTEGRATOR, ONESHOT><<<grid, 128, 0, stream>>>(scene->gpu, prm, order, count, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur], \
+            // SELAS_SHADE_ESTIMATE_PERCENT scales the estimate (tests under-size it to exercise the launch behind the one-shot grid)
+            const char* pct = getenv("SELAS_SHADE_ESTIMATE_PERCENT");
+            const uint64_t estScaled = pct ? std::max<uint64_t>(1u, (uint64_t)est * (uint64_t)std::max(1, atoi(pct)) / 100u) : (uint64_t)est + est / 32u;
+            const int grid = oneShot ? (int)std::min<uint64_t>(divUp(count, 128), divUp(estScaled, 128) + 8u) : shadeGrid;
+            const bool tail = oneShot && (uint32_t)grid < divUp(count, 128);
+#define SELAS_SHADE_LAUNCH(INTEGRATOR, ONESHOT, GRID, FIRST)                                                                                     \
+    shadeKernel<INTEGRATOR, ONESHOT><<<GRID, 128, 0, stream>>>(scene->gpu, prm, order, count, w->rays[cur], w->hits, w->thrPix[cur], w->rngFlags[cur], \
                                                               w->medium[cur], w->rays[cur ^ 1], w->thrPix[cur ^ 1], w->rngFlags[cur ^ 1],       \
                                                               w->medium[cur ^ 1], w->shadowRays, w->shadowPayload, next, d_film,                 \
-                                                              scene->usesPtex ? w->ptexRgb : nullptr, ctr, ctr + 4)
+                                                              scene->usesPtex ? w->ptexRgb : nullptr, ctr, ctr + 4, FIRST)
             if (deferred) {
-                if (oneShot) SELAS_SHADE_LAUNCH(1, true);
-                else SELAS_SHADE_LAUNCH(1, false);
+                if (oneShot) SELAS_SHADE_LAUNCH(1, true, grid, 0u);
+                if (!oneShot || tail) SELAS_SHADE_LAUNCH(1, false, oneShot ? ctx->smCount : grid, oneShot ? (uint32_t)grid : 0u);
             } else {
-                if (oneShot) SELAS_SHADE_LAUNCH(0, true);
-                else SELAS_SHADE_LAUNCH(0, false);
+                if (oneShot) SELAS_SHADE_LAUNCH(0, true, grid, 0u);
+                if (!oneShot || tail) SELAS_SHADE_LAUNCH(0, false, oneShot ? ctx->smCount : grid, oneShot ? (uint32_t)grid : 0u);
             }
 #undef SELAS_SHADE_LAUNCH
+            if (tail) ++launches;
             timers.end(2, t0, stream);
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
             {

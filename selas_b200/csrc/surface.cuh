@@ -57,6 +57,27 @@ SELAS_D V3 sampleTextureFloat3(const TextureGpu& tex, float u, float v, bool sRG
 }
 
 // ptexRgb: this hit's Ptex lookup, made by the Ptex stage kernel (ptexStageKernel) before shading, or null.
+// hit->normal of a hit on a curve geometry = Embree's Ng of a round curve: the surface normal (RTC_GEOMETRY_TYPE_CURVE.3embree3); curve
+// geometries carry no attribute buffers (ModelResource.cpp:314-319).  Rebuilt from the element that was hit, with the control vertices
+// taken to world space (for rotations and uniform scales the same as sending the object-space normal through localToWorld).  Out of
+// line: scenes without curves never come here, and the shade kernels stay as lean as they were (inlined it cost them 6 registers and
+// 6 % more instructions on configs[2], which has no curves at all).
+static __device__ __noinline__ V3 curveSurfaceNormal(const MeshGpu& mesh, const InstanceGpu* inst, uint32_t primID, uint32_t element, V3 p) {
+    const bool identity = inst->identity != 0;
+    const float4* cv = reinterpret_cast<const float4*>(mesh.positions) + __ldg(mesh.indices + primID);
+    float4 c[4];
+    float rscale = 1.0f;
+    const float* m = inst->m;
+    if (!identity) rscale = cbrtf(fabsf(m[0] * (m[5] * m[10] - m[6] * m[9]) - m[1] * (m[4] * m[10] - m[6] * m[8]) + m[2] * (m[4] * m[9] - m[5] * m[8])));
+    for (int k = 0; k < 4; ++k) {
+        const float4 q4 = __ldg(cv + k);
+        V3 q = v3(q4.x, q4.y, q4.z);
+        if (!identity) q = mulPoint44(q, m);
+        c[k] = make_float4(q.x, q.y, q.z, q4.w * rscale);
+    }
+    return curveElementNormal(c[0], c[1], c[2], c[3], element ? element : 1u, p);
+}
+
 // element: last word of the hit record -- for a hit on a curve geometry the piece of the segment that was hit (curve.cuh), else 0.
 SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, float v, uint32_t primID, uint32_t geomID,
                             uint32_t instID, const float* ptexRgb, Surface& s, uint32_t element = 0u) {
@@ -77,20 +98,7 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
 
     V3 normal;
     if (isCurve) {
-        // hit->normal = Embree's Ng of a round curve: the surface normal (RTC_GEOMETRY_TYPE_CURVE.3embree3); curve geometries carry no
-        // attribute buffers (ModelResource.cpp:314-319).  Rebuilt from the element that was hit, with the control vertices taken to
-        // world space (for rotations and uniform scales the same as sending the object-space normal through localToWorld).
-        const float4* cv = reinterpret_cast<const float4*>(mesh.positions) + __ldg(mesh.indices + primID);
-        float4 c[4];
-        float rscale = 1.0f;
-        if (!identity) rscale = cbrtf(fabsf(m[0] * (m[5] * m[10] - m[6] * m[9]) - m[1] * (m[4] * m[10] - m[6] * m[8]) + m[2] * (m[4] * m[9] - m[5] * m[8])));
-        for (int k = 0; k < 4; ++k) {
-            const float4 p = __ldg(cv + k);
-            V3 q = v3(p.x, p.y, p.z);
-            if (!identity) q = mulPoint44(q, m);
-            c[k] = make_float4(q.x, q.y, q.z, p.w * rscale);
-        }
-        normal = curveElementNormal(c[0], c[1], c[2], c[3], element ? element : 1u, v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z));
+        normal = curveSurfaceNormal(mesh, inst, primID, element, v3(o.x + t * d.x, o.y + t * d.y, o.z + t * d.z));
     } else if (mesh.normals) {
         normal = v3(interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 0, u, v), interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 1, u, v),
                     interpAttr(mesh.normals, ix, mesh.indicesPerFace, 3, 2, u, v));

@@ -154,3 +154,23 @@ def test_cornell512_same_streams_and_converged(ctx, oracle):
     ok = np.isfinite(g).all(axis=2) & np.isfinite(conv).all(axis=2)
     for c in range(3):
         assert abs(g[..., c][ok].mean() / conv[..., c][ok].mean() - 1.0) < 0.01
+
+
+def test_short_queue_estimate_is_covered_by_the_launch_behind_it(ctx, monkeypatch):
+    """The shade stage sizes a one-shot grid from the queue lengths an earlier pass read back (renderPathTracer); what an estimate that
+    is too small leaves over must be shaded by the persistent launch behind it.  The estimate is forced to 40 % here: the ray totals stay
+    those of the first render (whose grids were persistent: no estimate yet) and the films agree up to the order of the atomics."""
+    data = scenes.disney_heightfield(grid=32)
+    cam = scenes.heightfield_camera(160, 90)
+    rs = capi.render_settings(160, 90, 8, max_path_length=8, rr_start=8, layers=1, seed=5)
+    sc = capi.Scene(ctx, data)
+    film0, st0 = sc.render(cam, rs)
+    monkeypatch.setenv("SELAS_SHADE_ESTIMATE_PERCENT", "40")
+    for _ in range(3):  # the estimates arrive asynchronously; after the first of these they are in use
+        film, st = sc.render(cam, rs)
+        assert (st.closestRays, st.occlusionRays, st.pathSamples) == (st0.closestRays, st0.occlusionRays, st0.pathSamples)
+        np.testing.assert_allclose(film[0], film0[0], rtol=1e-4, atol=1e-5)
+    monkeypatch.setenv("SELAS_SHADE_ESTIMATE_PERCENT", "100")  # exact-size grid plus the 8 CTAs of slack
+    film, st = sc.render(cam, rs)
+    assert (st.closestRays, st.occlusionRays) == (st0.closestRays, st0.occlusionRays)
+    sc.close()
