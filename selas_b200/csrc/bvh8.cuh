@@ -72,6 +72,26 @@ struct TraceResult {
 // time are dropped into the mantissas of a half2 holding {1024, 1024} (one PRMT): 0x6400 | b == 1024 + b exactly; the
 // half -> float step is an HADD2.F32 on the FMA pipe, and the -1024 is folded into the plane offset (o - 1024 s), whose
 // rounding error is 2^-14 of a quantisation step, far inside the builder's 1e-3-step slack.
+#ifndef SELAS_NODE_BYTE_PRMT
+#define SELAS_NODE_BYTE_PRMT 0
+#endif
+#if SELAS_NODE_BYTE_PRMT
+// Round-2 experiment, OFF: one PRMT per byte and no conversion at all.  The byte is dropped into mantissa bits 8..15 of a float holding 2^23
+// ({0x00, b, 0x00, 0x4B}): the value is 2^23 + 256 b exactly, i.e. the plane index biased by 2^15 in units of 1/256 of a step.  The
+// slab test folds the 1/256 into the step and the bias into the plane offset (o - 2^23 s / 256); rounding that offset costs 2^-9 of a
+// quantisation step, inside the builder's 4e-3-step slack (bvh_build.cuh).  Per node: 48 PRMT instead of 24 PRMT + 48 HADD2.F32,
+// 16 instructions fewer in the kernel (640 -> 624 SASS) -- and 1.8 % SLOWER on configs[2] (closest hit 8.41 against 8.26 ms per step,
+// profiles/r2_ab_node_prmt.jsonl): PRMT issues on the ALU pipe, which LOP3 / SEL / FMNMX / FSETP / SHF already fill, while HADD2.F32
+// rides the FMA pipe next to the FFMAs.  The half2 path below stays the product.
+constexpr float kNodeByteBias = 8388608.0f, kNodeByteScale = 1.0f / 256.0f;
+SELAS_D void bytesToBiasedFloats(uint32_t w, float& f0, float& f1, float& f2, float& f3) {
+    f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7404));
+    f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7414));
+    f2 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7424));
+    f3 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7434));
+}
+#else
+constexpr float kNodeByteBias = 1024.0f, kNodeByteScale = 1.0f;
 SELAS_D void bytesToBiasedFloats(uint32_t w, float& f0, float& f1, float& f2, float& f3) {
     uint32_t lo = __byte_perm(w, 0x64646464u, 0x4140);  // {b0, 0x64, b1, 0x64}
     uint32_t hi = __byte_perm(w, 0x64646464u, 0x4342);  // {b2, 0x64, b3, 0x64}
@@ -82,16 +102,18 @@ SELAS_D void bytesToBiasedFloats(uint32_t w, float& f0, float& f1, float& f2, fl
     f3 = __high2float(hh);
 }
 
+#endif
+
 // Ray-vs-8-children slab test on the quantised boxes; returns the hit mask in traversal-bit order.
 SELAS_D uint32_t intersectNode(const float4 n0, const float4 n1, const float4 n2, const float4 n3, const float4 n4, V3 o,
                                V3 idir, bool negx, bool negy, bool negz, uint32_t octInv4, float tmin, float tmax) {
     uint32_t eimask = __float_as_uint(n0.w);
-    float sx = __uint_as_float(extractByte(eimask, 0) << 23) * idir.x;
-    float sy = __uint_as_float(extractByte(eimask, 1) << 23) * idir.y;
-    float sz = __uint_as_float(extractByte(eimask, 2) << 23) * idir.z;
-    // plane t = (origin + q*scale - o) * idir = q*s + ox, with q delivered as 1024 + q
-    float ox = fmaf(-1024.0f, sx, (n0.x - o.x) * idir.x), oy = fmaf(-1024.0f, sy, (n0.y - o.y) * idir.y),
-          oz = fmaf(-1024.0f, sz, (n0.z - o.z) * idir.z);
+    float sx = __uint_as_float(extractByte(eimask, 0) << 23) * (idir.x * kNodeByteScale);
+    float sy = __uint_as_float(extractByte(eimask, 1) << 23) * (idir.y * kNodeByteScale);
+    float sz = __uint_as_float(extractByte(eimask, 2) << 23) * (idir.z * kNodeByteScale);
+    // plane t = (origin + q*scale - o) * idir = q*s + ox, with q delivered as bias + q (in units of kNodeByteScale steps)
+    float ox = fmaf(-kNodeByteBias, sx, (n0.x - o.x) * idir.x), oy = fmaf(-kNodeByteBias, sy, (n0.y - o.y) * idir.y),
+          oz = fmaf(-kNodeByteBias, sz, (n0.z - o.z) * idir.z);
     uint32_t hitMask = 0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {

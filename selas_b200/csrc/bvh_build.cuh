@@ -403,8 +403,8 @@ __global__ void collapseLevelKernel(const CollapseTask* __restrict__ tasks, uint
         for (int a = 0; a < 3; ++a) {
             float xl = (lo3[a] - p3[a]) / scale[a], xh = (hi3[a] - p3[a]) / scale[a];
             float fl = floorf(xl), ch = ceilf(xh);
-            if (xl - fl < 1e-3f) fl -= 1.0f;  // keep a hair of slack against rounding in the traversal's slab test
-            if (ch - xh < 1e-3f) ch += 1.0f;
+            if (xl - fl < 4e-3f) fl -= 1.0f;  // keep a hair of slack against rounding in the traversal's slab test (bvh8.cuh: 2^-9 step)
+            if (ch - xh < 4e-3f) ch += 1.0f;
             qlo[a][s] = (uint32_t)fminf(fmaxf(fl, 0.f), 255.f);
             qhi[a][s] = (uint32_t)fminf(fmaxf(ch, 0.f), 255.f);
         }
