@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where the Ptex lookup's time goes: the same number of lookups restricted to kernel placements that stay inside the face,
-cross one edge, or cross a corner (8x8 uint8 faces, random face ids).  Prints one JSON object.
-  python scripts/ptex_classes.py [--grid 800] [--lookups 16000000]"""
+cross one edge, or cross a corner (8x8 uint8 faces, random face ids; --jitter 1: resolutions mixed 8 / 16 per axis).  Prints one JSON
+object.  python scripts/ptex_classes.py [--grid 800] [--lookups 16000000] [--jitter 1]"""
 import argparse
 import json
 import sys
@@ -21,13 +21,16 @@ def main():
     ap.add_argument("--grid", type=int, default=800)
     ap.add_argument("--lookups", type=int, default=16_000_000)
     ap.add_argument("--ptx", default="", help="reuse / keep the authored .ptx at this path (A/B runs)")
+    ap.add_argument("--log2", type=int, default=3, help="base face resolution (log2, both axes)")
+    ap.add_argument("--jitter", type=int, default=0, help="a third / a quarter of the faces get 2^jitter times the resolution along u / v "
+                    "(oracle/ptex_harness.cpp), so that most kernels that leave their face meet another resolution")
     args = ap.parse_args()
     import torch
 
     ptexref = oracle_binding.load_ptexref()
     tmp = Path(args.ptx) if args.ptx else Path(tempfile.mkdtemp()) / "c.ptx"
     if not tmp.exists():
-        ptexref.write_grid(tmp, args.grid, args.grid, 3, 3, 0, 0, 3, 4, True, 0)
+        ptexref.write_grid(tmp, args.grid, args.grid, args.log2, args.log2, args.jitter, 0, 3, 4, True, 0)
     ctx = capi.Context(0)
     tex = capi.Ptex(ctx, tmp)
     dev = torch.device("cuda", 0)

@@ -588,8 +588,8 @@ static __device__ __noinline__ void ptexSplitAndApply(const PtexGpu& tx, PtexEva
 // weight windows); measured at 1.1 G lookups/s it is far from the 104-B/lookup roofline.  The overwhelmingly common
 // cases -- a 4x4 kernel that stays inside its face, or crosses exactly one edge onto an ordinary neighbour of matching
 // resolution (or onto the mesh border) -- are handled here with compile-time indexed 4-element arrays.  Every sum is
-// formed in the same order as the general path, so the two agree bit for bit; anything else (corners, subfaces,
-// resolution mismatch, faces below 8 texels, kernels that are not 4 wide) returns false and takes the general path.
+// formed in the same order as the general path, so the two agree bit for bit; anything else (valence != 4 corners, subfaces,
+// faces below 8 texels, kernels that are not 4 wide) returns false and takes the general path.
 // ---------------------------------------------------------------------------------------------------------------
 struct PtexPiece {  // a (sub)kernel: window origin, extent and weights compacted to index 0
     int u, v, uw, vw;
@@ -645,18 +645,21 @@ SELAS_D float ptexTexelT(const uint8_t* base, size_t idx) {
 // PtexSeparableKernel::Apply on native-resolution data of a face (or applyConst for a constant face).  The data type is a template
 // parameter so that the per-texel switch is decided once per lookup; NT = 3 is the three-channel texture read with every texel at
 // a constant offset from one row pointer (the generic form spent 28 % of the kernel's instructions on 64-bit index arithmetic).
+// `data` / `ulog2`: the texel block the piece is applied to and its row length -- the face's native data, or the reduced copy
+// PtexReader::getData(faceid, k.res) hands a kernel whose resolution is below the face's (PtexReader.cpp:785-830); `constant`: the
+// face's constant pixel instead (constant face, or a kernel reduced to 1 x 1).
 template <int DT, int NT>
-SELAS_D void ptexApplyPiece(const PtexGpu& tx, const PtexFace& f, int faceid, const PtexPiece& p, int nchan, float* result) {
+SELAS_D void ptexApplyPiece(const PtexGpu& tx, bool constant, int faceid, const uint8_t* data, int ulog2, const PtexPiece& p, int nchan,
+                            float* result) {
     if (p.uw <= 0 || p.vw <= 0) return;
-    if (f.isConstant()) {
+    if (constant) {
         float w = ptexSum4(p.ku, p.uw) * ptexSum4(p.kv, p.vw);
         const uint8_t* px = tx.constData + (size_t)faceid * tx.pixelSize;
         for (int c = 0; c < nchan; ++c) result[c] += ptexTexelT<DT>(px, c) * w;
         return;
     }
     constexpr int kTexelBytes = DT == 0 ? 1 : (DT == 3 ? 4 : 2);
-    const uint8_t* data = tx.texels + (size_t)f.dataOffset16 * 16;
-    const int resu = 1 << f.ulog2, nt = NT ? NT : tx.nchan;
+    const int resu = 1 << ulog2, nt = NT ? NT : tx.nchan;
     const uint8_t* rowPtr = data + ((size_t)p.v * resu + p.u) * (size_t)(nt * kTexelBytes);
     const size_t rowStride = (size_t)resu * (size_t)(nt * kTexelBytes);
 #pragma unroll
@@ -768,15 +771,39 @@ SELAS_D void ptexMergeAxis(int& k0, int& kn, float* kk, int res, bool lowSide, i
     }
 }
 
+// PtexSeparableKernel::downresU / downresV (PtexSeparableKernel.h:313-367) on one axis of a piece: neighbouring weights are added in
+// pairs aligned to the coarser grid (an odd origin leaves the first weight alone), in the library's operand order.
+SELAS_D void ptexDownresAxis(int& k0, int& kn, float* kk) {
+    const float e0 = kk[0], e1 = kn > 1 ? kk[1] : 0.f, e2 = kn > 2 ? kk[2] : 0.f, e3 = kn > 3 ? kk[3] : 0.f;
+    if (k0 & 1) {
+        kk[0] = e0;
+        kk[1] = kn > 2 ? e1 + e2 : e1;
+        kk[2] = e3;
+        kk[3] = 0.f;
+        kn = 1 + (kn >> 1);  // 1 + ceil((kn - 1) / 2)
+    } else {
+        kk[0] = kn > 1 ? e0 + e1 : e0;
+        kk[1] = kn > 3 ? e2 + e3 : e2;
+        kk[2] = 0.f;
+        kk[3] = 0.f;
+        kn = (kn + 1) >> 1;
+    }
+    k0 >>= 1;
+}
+
 // splitAndApply (PtexSeparableFilter.cpp:135-213) for a 4x4 kernel on an ordinary face of >= 8x8 texels.  The library applies up to
 // four pieces in a fixed order -- across the corner, across the u edge, across the v edge, the face itself -- and this walks the same
 // four slots in ONE loop: per axis a slot's piece is the part that leaves the face, the part that stays, the whole window, or (at a
 // mesh border) the window with the overhang merged onto the edge texel.  One copy of the code serves every slot, a warp holding
 // interior, edge and corner lookups stays converged (slots a lane does not need are predicated off), and the sums are formed in
-// the library's order, so the result matches the general path bit for bit.  Anything else -- subfaces, resolution mismatch,
-// valence 5+ corners, faces below 8 texels, kernels that are not 4 wide -- returns false and takes the general path.  Written
+// the library's order, so the result matches the general path bit for bit.  Neighbours of another resolution are served here too
+// since round 2 (the piece is reduced, or the neighbour's reduced copy is read).  Anything else -- subfaces, valence 5+ corners,
+// faces below 8 texels, kernels that are not 4 wide -- returns false and takes the general path.  Written
 // with status flags instead of early exits: with `return` in the middle the compiler moved the warp's reconvergence point to the
 // end of the lookup and the variants ran one after the other (measured 17.7 ms for 16 M mixed lookups).
+#ifndef SELAS_PTEX_FAST_MIXED
+#define SELAS_PTEX_FAST_MIXED 1
+#endif
 enum { kAxisWhole = 0, kAxisLeaving = 1, kAxisStaying = 2, kAxisMerged = 3 };
 SELAS_D void ptexDeriveAxis(int k0, int kn, const float* kk, int res, bool lowSide, int how, int mode, int& o0, int& on, float* ko) {
     float t[4];
@@ -861,8 +888,31 @@ SELAS_D bool ptexEvalFastT(const PtexGpu& tx, const PtexFace& f, int faceid, flo
             if (ok && apply) {
                 int ul = f.ulog2, vl = f.vlog2;
                 ptexRotatePiece(p, rot, ul, vl);
-                ok = !tf.isSubface() && ul == tf.ulog2 && vl == tf.vlog2;  // else: downres / reduced data / subface logic
-                if (ok) ptexApplyPiece<DT, NT>(tx, tf, tfid, p, nchan, result);
+                ok = !tf.isSubface();  // else: the subface transitions of applyAcrossEdge / applyToCornerFace
+#if !SELAS_PTEX_FAST_MIXED
+                ok = ok && ul == tf.ulog2 && vl == tf.vlog2;  // round-1 behaviour (A/B): other resolutions take the general path
+#endif
+                if (ok) {
+                    // PtexSeparableFilter::apply (:346-401): a coarser face gets the piece reduced to its resolution, a finer one
+                    // is read through its reduced copy at the piece's resolution
+#pragma unroll 1
+                    while (ul > tf.ulog2) { ptexDownresAxis(p.u, p.uw, p.ku); --ul; }
+#pragma unroll 1
+                    while (vl > tf.vlog2) { ptexDownresAxis(p.v, p.vw, p.kv); --vl; }
+                    const bool constant = tf.isConstant() || (ul == 0 && vl == 0);
+                    const uint8_t* data = tx.texels + (size_t)tf.dataOffset16 * 16;
+                    bool found = true;
+                    if (!constant && (ul != tf.ulog2 || vl != tf.vlog2)) {
+                        const uint32_t want = (uint32_t)(ul & 0xff) | ((uint32_t)(vl & 0xff) << 8);
+                        found = false;
+                        for (uint32_t i = 0; i < tf.redCount && !found; ++i) {
+                            const PtexRed r = tx.reds[tf.redStart + i];
+                            if (r.res == want) { data = tx.texels + (size_t)r.offset16 * 16; found = true; }
+                        }
+                    }
+                    // a reduction the loader did not foresee contributes nothing (as in ptexApply)
+                    if (found) ptexApplyPiece<DT, NT>(tx, constant, tfid, data, ul, p, nchan, result);
+                }
             }
         }
     }

@@ -53,6 +53,36 @@ def test_ptex_lookup_live_reference_large(ctx, tmp_path):
     tex.close()
 
 
+@pytest.mark.parametrize("log2,jitter,dtype,mips", [(3, 2, 0, True), (3, 1, 1, False), (4, 1, 3, True), (3, 3, 2, True)])
+def test_ptex_mixed_resolution_neighbours_vs_live_reference(ctx, tmp_path, log2, jitter, dtype, mips):
+    """Kernels that leave their face onto a neighbour of another resolution (since round 2 the register path reduces
+    the piece, PtexSeparableKernel::downresU/V, or reads the neighbour's reduced copy, PtexReader::getData(faceid, res)): lookups hugging
+    the edges and corners of faces whose neighbours are 2^jitter times finer / coarser along u or v, with and without stored mip levels,
+    in all four data types, against the reference library itself."""
+    ptexref = oracle_binding.load_ptexref()
+    if ptexref is None:
+        pytest.skip("oracle/_ref/libptex_ref.so not present")
+    path = tmp_path / "mixed.ptx"
+    nu, nv = 24, 20
+    ptexref.write_grid(path, nu, nv, log2, log2, jitter, dtype, 3, 21 + jitter, mips, 11)
+    rng = np.random.default_rng(17 + log2)
+    n = 120_000
+    face = rng.integers(0, nu * nv, size=n).astype(np.int32)
+    # two thirds of the lookups within a texel and a half of an edge (both sides, both axes), the rest anywhere
+    near = rng.uniform(0.0, 1.5 / (1 << log2), size=(n, 2)).astype(np.float32)
+    side = rng.integers(0, 2, size=(n, 2))
+    uv = np.where(side == 1, 1.0 - near, near).astype(np.float32)
+    anywhere = rng.uniform(0, 1, size=(n, 2)).astype(np.float32)
+    pick = rng.integers(0, 3, size=(n, 2))
+    uv = np.where(pick == 0, anywhere, uv).astype(np.float32)
+    tex = capi.Ptex(ctx, path)
+    got = tex.eval(face, uv[:, 0].copy(), uv[:, 1].copy())
+    want = ptexref.eval(path, face, uv[:, 0].copy(), uv[:, 1].copy())
+    err = np.abs(got - want)
+    assert err.max() <= TOL, (float(err.max()), int((err > TOL).sum()))
+    tex.close()
+
+
 def test_ptex_errors(ctx, tmp_path):
     bad = tmp_path / "bad.ptx"
     bad.write_bytes(b"not a ptex file at all, just sixty-four bytes of text padding.........")
