@@ -105,7 +105,9 @@ __global__ void gatherTrianglesKernel(MeshDev mesh, const float* __restrict__ xf
 
 // Curve segments of one curve geometry (MeshDev.indicesPerFace == 1: positions = float4 control vertices, indices = first vertex of each
 // segment): the four control vertices go through the instance transform into the curve pool (radius scaled by the cube root of the
-// transform's volume change), and the build record carries the box of the segment's Bezier hull grown by its largest radius.
+// transform's volume change).  Every segment becomes SELAS_CURVE_PARTS build records, one per cone of curve.cuh, each with the box of
+// its two end spheres: blades of grass are long, thin and oblique, and with one box per segment (the first version) a ray through a
+// lawn met 60 segment boxes and ran the whole 8-cone test in each (48 M primary rays/s; per-part boxes: profiles/r2_curves.txt).
 __global__ void gatherCurvesKernel(MeshDev mesh, const float* __restrict__ xform, bool identity, uint32_t geomID, uint32_t instID,
                                    BuildTri* __restrict__ out, uint32_t outBase, float4* __restrict__ pool, uint32_t poolBase,
                                    uint32_t* __restrict__ bounds) {
@@ -128,31 +130,28 @@ __global__ void gatherCurvesKernel(MeshDev mesh, const float* __restrict__ xform
             c[k] = make_float4(q.x, q.y, q.z, p.w * rscale);
             pool[4 * (size_t)(poolBase + f) + k] = c[k];
         }
-        // Bezier hull of the uniform B-spline segment
-        float4 b[4];
-        for (int a = 0; a < 4; ++a) {
-            const float w0 = a == 0 ? 1.f : 0.f, w1 = a == 0 ? 4.f : (a == 1 ? 4.f : (a == 2 ? 2.f : 1.f)),
-                        w2 = a == 0 ? 1.f : (a == 1 ? 2.f : (a == 2 ? 4.f : 4.f)), w3 = a == 3 ? 1.f : 0.f;
-            b[a] = make_float4((w0 * c[0].x + w1 * c[1].x + w2 * c[2].x + w3 * c[3].x) * (1.f / 6.f), (w0 * c[0].y + w1 * c[1].y + w2 * c[2].y + w3 * c[3].y) * (1.f / 6.f),
-                               (w0 * c[0].z + w1 * c[1].z + w2 * c[2].z + w3 * c[3].z) * (1.f / 6.f), (w0 * c[0].w + w1 * c[1].w + w2 * c[2].w + w3 * c[3].w) * (1.f / 6.f));
+        float4 a = curvePoint(c[0], c[1], c[2], c[3], 0.0f);
+        for (int part = 0; part < SELAS_CURVE_PARTS; ++part) {
+            const float4 b = curvePoint(c[0], c[1], c[2], c[3], (float)(part + 1) * (1.0f / SELAS_CURVE_PARTS));
+            const float pa[3] = {a.x, a.y, a.z}, pb[3] = {b.x, b.y, b.z};
+            const float ra = fabsf(a.w), rb = fabsf(b.w);
+            float plo[3], phi[3];
+            for (int k = 0; k < 3; ++k) {  // the two end spheres, plus a relative margin for the fp32 evaluation of the curve points
+                plo[k] = fminf(pa[k] - ra, pb[k] - rb);
+                phi[k] = fmaxf(pa[k] + ra, pb[k] + rb);
+                const float pad = 1e-4f * fmaxf(ra, rb) + 2e-6f * fmaxf(fabsf(plo[k]), fabsf(phi[k]));
+                plo[k] -= pad;
+                phi[k] += pad;
+                lo[k] = fminf(lo[k], plo[k]);
+                hi[k] = fmaxf(hi[k], phi[k]);
+            }
+            BuildTri t;
+            t.a = make_float4(plo[0], plo[1], plo[2], __uint_as_float(f));
+            t.b = make_float4(phi[0], phi[1], phi[2], __uint_as_float(geomID));
+            t.c = make_float4(__uint_as_float(poolBase + f), __uint_as_float((uint32_t)part), 0.f, __uint_as_float(instID | kPrimCurveFlag));
+            out[outBase + (size_t)f * SELAS_CURVE_PARTS + part] = t;
+            a = b;
         }
-        float r = 0.f;
-        for (int a = 0; a < 4; ++a) {
-            r = fmaxf(r, fabsf(b[a].w));
-            lo[0] = fminf(lo[0], b[a].x); hi[0] = fmaxf(hi[0], b[a].x);
-            lo[1] = fminf(lo[1], b[a].y); hi[1] = fmaxf(hi[1], b[a].y);
-            lo[2] = fminf(lo[2], b[a].z); hi[2] = fmaxf(hi[2], b[a].z);
-        }
-        for (int k = 0; k < 3; ++k) {  // radius plus a relative margin for the fp32 evaluation of the curve points
-            const float pad = r * 1.0001f + 1e-6f * fmaxf(fabsf(lo[k]), fabsf(hi[k]));
-            lo[k] -= pad;
-            hi[k] += pad;
-        }
-        BuildTri t;
-        t.a = make_float4(lo[0], lo[1], lo[2], __uint_as_float(f));
-        t.b = make_float4(hi[0], hi[1], hi[2], __uint_as_float(geomID));
-        t.c = make_float4(__uint_as_float(poolBase + f), 0.f, 0.f, __uint_as_float(instID | kPrimCurveFlag));
-        out[outBase + f] = t;
     }
     for (int k = 0; k < 3; ++k) {
         float a = lo[k], b2 = hi[k];
@@ -423,8 +422,8 @@ __global__ void collapseLevelKernel(const CollapseTask* __restrict__ tasks, uint
             for (uint32_t q = 0; q < cnt[k]; ++q) {
                 BuildTri t = tris[sorted[first + q]];
                 float4* o = outTris + (size_t)(triBase + triOffset + q) * 3;
-                if (__float_as_uint(t.c.w) & kPrimCurveFlag) {  // curve segment: the leaf record only names the pool entry
-                    o[0] = make_float4(t.c.x, 0.f, 0.f, t.a.w);
+                if (__float_as_uint(t.c.w) & kPrimCurveFlag) {  // part of a curve segment: the leaf record names the pool entry and the part
+                    o[0] = make_float4(t.c.x, t.c.y, 0.f, t.a.w);
                     o[1] = make_float4(0.f, 0.f, 0.f, t.b.w);
                     o[2] = make_float4(0.f, 0.f, 0.f, t.c.w);
                     continue;

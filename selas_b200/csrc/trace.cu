@@ -34,6 +34,8 @@ struct TempFree {
 };
 
 inline uint32_t divUp(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+// build primitives per face: a quad is two triangles, a curve segment SELAS_CURVE_PARTS cones (curve.cuh)
+inline uint32_t primitivesPerFace(uint32_t indicesPerFace) { return indicesPerFace == 4 ? 2u : (indicesPerFace == 1 ? (uint32_t)SELAS_CURVE_PARTS : 1u); }
 
 }  // namespace
 
@@ -324,11 +326,11 @@ int buildBvh(SelasScene* scene, const std::vector<MeshGpu>& meshes, const std::v
     for (uint32_t ii = 0; ii < inst.size(); ++ii)
         for (uint32_t m = 0; m < meshes.size(); ++m) {
             if (inst[ii].mesh != 0xFFFFFFFFu && inst[ii].mesh != m) continue;
-            uint32_t t = meshes[m].faceCount * (meshes[m].indicesPerFace == 4 ? 2u : 1u);
+            uint32_t t = meshes[m].faceCount * primitivesPerFace(meshes[m].indicesPerFace);
             if (t == 0) continue;
             draws.push_back({m, ii, (uint32_t)total, t});
             total += t;
-            if (meshes[m].indicesPerFace == 1) curveSegments += t;  // a curve geometry: one primitive and one pool entry per segment
+            if (meshes[m].indicesPerFace == 1) curveSegments += meshes[m].faceCount;  // a curve geometry: one pool entry per segment
         }
     if (total >= 0x3fffffffull || inst.size() >= 0x3fffffffull) {
         setError(ctx, "scene has %llu primitives; the builder is limited to 2^30-1", (unsigned long long)total);
@@ -473,7 +475,7 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
         if (rcPool) return rcPool;
     }
     for (uint32_t m = 0; m < meshes.size(); ++m) {
-        const uint32_t t = meshes[m].faceCount * (meshes[m].indicesPerFace == 4 ? 2u : 1u);
+        const uint32_t t = meshes[m].faceCount * primitivesPerFace(meshes[m].indicesPerFace);
         if (!blas[m].used || t == 0) {
             blas[m].used = false;
             continue;
@@ -537,7 +539,7 @@ int buildBvhTwoLevel(SelasScene* scene, const std::vector<MeshGpu>& meshes, cons
         memcpy(&t.b.w, &inst[i].mesh, 4);  // geomID = mesh
         memcpy(&t.c.w, &i, 4);
         fake.push_back(t);
-        instancedTris += meshes[inst[i].mesh].faceCount * (meshes[inst[i].mesh].indicesPerFace == 4 ? 2u : 1u);
+        instancedTris += meshes[inst[i].mesh].faceCount * primitivesPerFace(meshes[inst[i].mesh].indicesPerFace);
     }
     scene->stats.triangleCount = (uint32_t)std::min<uint64_t>(uniqueTris, 0xFFFFFFFFull);
     if (fake.empty()) return SELAS_OK;

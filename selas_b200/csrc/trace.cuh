@@ -217,10 +217,10 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
                 if (COUNT) ++nTris;
                 float t, u, v;
                 if (CURVES && (__float_as_uint(c.w) & kLeafCurveFlag)) {
-                    // round B-spline curve segment (ModelResource.cpp:300-333): the leaf record names its four control vertices
+                    // part of a round B-spline curve segment (ModelResource.cpp:300-333): the leaf record names the segment's control vertices + the part
                     const float4* cp = bvh.curves + 4 * (size_t)__float_as_uint(a.x);
                     CurveHit ch;
-                    if (intersectCurve(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3), o, d, tnear, tmax, ch)) {
+                    if (intersectCurve(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3), __float_as_uint(a.y), o, d, tnear, tmax, ch)) {
                         tmax = ch.t;
                         res.t = ch.t; res.u = ch.u; res.v = 0.f; res.tri = ti; res.element = ch.element; res.ng = ch.ng;
                         if (INST) res.inst = curInst;

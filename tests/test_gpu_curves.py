@@ -141,5 +141,5 @@ def test_curve_descriptor_errors(ctx):
     with pytest.raises(capi.SelasError):
         capi.Scene(ctx, bad)
     sc = capi.Scene(ctx, data)
-    assert sc.bvh_stats().triangleCount == 2 + 4 * 3  # the floor quad's two triangles and twelve curve segments
+    assert sc.bvh_stats().triangleCount == 2 + 4 * 3 * 8  # the floor quad's two triangles and twelve curve segments of eight parts each
     sc.close()
