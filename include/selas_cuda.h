@@ -433,6 +433,31 @@ int selas_cuda_ibl_sample(SelasScene* scene, size_t n, const float* u2, float* t
  * = TextureFiltering::Triangle at level 0 (+ Math::SrgbToLinearPrecise when sRGB != 0), for parity checks of the lookup itself. */
 int selas_cuda_texture_sample(SelasContext* ctx, const SelasTextureDesc* texture, size_t n, const float* uv2, int sRGB, float* rgb3);
 
+/* ---- texture filters: TextureLib/TextureFiltering.h:54-234 over a batch of lookups -----------------------------------
+ * The reference's path only ever calls Triangle at level 0 (above); Point, Triangle at any level, Trilinear and EWA are the rest of that
+ * header, built here with the same arithmetic so that a caller that switches ForceNoMips_ off has them.  The texture is a
+ * TextureResourceData with its whole mip chain: level l is mipWidths[l] x mipHeights[l] texels of (format + 1) floats at byte offset
+ * mipOffsets[l] of `texels` (dataSize bytes).  Wrap mode Repeat, as hard-wired in the reference (including its unsigned modulo of
+ * negative coordinates).  st2 = 2 floats per lookup; dst0_2 / dst1_2 = the two texture-space derivative vectors (TRILINEAR, EWA, EWA_LEVEL;
+ * may be NULL for POINT and TRIANGLE); `level` is used by TRIANGLE and EWA_LEVEL (the per-level EWA the full EWA blends).  out =
+ * (format + 1) floats per lookup.  EWA weights: the 128-entry table of InitializeEWAFilterWeights (TextureFiltering.cpp:14-21), computed on the host
+ * with the C library's expf like the reference does.  (As written the reference never fills the table its EWA template reads -- the
+ * table is a per-translation-unit static in the header and only TextureFiltering.cpp's own copy is initialised -- so its EWA would return
+ * 0 / 0; the product uses the initialised table.) */
+enum { SELAS_FILTER_POINT = 0, SELAS_FILTER_TRIANGLE = 1, SELAS_FILTER_TRILINEAR = 2, SELAS_FILTER_EWA = 3, SELAS_FILTER_EWA_LEVEL = 4 };
+#define SELAS_TEXTURE_MAX_MIPS 16 /* TextureResourceData::MaxMipCount */
+typedef struct SelasTextureMipsDesc {
+    uint32_t     mipCount;
+    uint32_t     format;          /* SELAS_TEXTURE_* */
+    uint32_t     mipWidths[SELAS_TEXTURE_MAX_MIPS];
+    uint32_t     mipHeights[SELAS_TEXTURE_MAX_MIPS];
+    uint64_t     mipOffsets[SELAS_TEXTURE_MAX_MIPS];  /* bytes */
+    uint64_t     dataSize;        /* bytes */
+    const void*  texels;
+} SelasTextureMipsDesc;
+int selas_cuda_texture_filter(SelasContext* ctx, const SelasTextureMipsDesc* texture, int filter, int level, size_t n, const float* st2,
+                              const float* dst0_2, const float* dst1_2, float* out);
+
 /* ---- surface: CalculateSurfaceParams SurfaceParameters.cpp:144-247 over a batch of hits ---------- */
 int selas_cuda_surface_params(SelasScene* scene, size_t n, const SelasRay* rays, const SelasHit* hits,
                               SelasSurface* out);

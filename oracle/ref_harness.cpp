@@ -790,6 +790,62 @@ int ref_vcm_generate_camera(const SelasCamera* cam, float lightPathCount, size_t
     return 0;
 }
 
+// TextureFiltering::Point / Triangle / Trilinear / EWA (TextureLib/TextureFiltering.h:54-234), the reference's own templates over a
+// TextureResourceData built from the descriptor.  EWAFilterLut is a `static` array in that header, i.e. one copy per translation unit,
+// and InitializeEWAFilterWeights (TextureFiltering.cpp:14-21) only fills the copy of its own unit: any other caller of EWA reads zeros
+// and gets 0 / 0.  This unit therefore fills ITS copy with the same formula (Math::Expf) before the first lookup.
+}  // extern "C"
+template <typename T>
+static void refFilterOne(TextureResourceData* data, int filter, int level, float2 st, float2 d0, float2 d1, float* out, int comps) {
+    T r = T(0.0f);
+    switch (filter) {
+        case SELAS_FILTER_POINT: TextureFiltering::Point<T>(data, st, r); break;
+        case SELAS_FILTER_TRIANGLE: TextureFiltering::Triangle<T>(data, level, st, r); break;
+        case SELAS_FILTER_TRILINEAR: TextureFiltering::Trilinear<T>(data, st, d0, d1, r); break;
+        case SELAS_FILTER_EWA: TextureFiltering::EWA<T>(data, st, d0, d1, r); break;
+        default: TextureFiltering::EWA<T>(data, (int32)level, st, d0, d1, r); break;
+    }
+    memcpy(out, &r, sizeof(float) * comps);
+}
+extern "C" {
+int ref_texture_filter(const SelasTextureMipsDesc* t, int filter, int level, size_t n, const float* st2, const float* dst0, const float* dst1, float* out) {
+    setFtz();
+    static bool lutReady = false;
+    if (!lutReady) {
+        for (uint32_t i = 0; i < (uint32_t)EwaLutSize; ++i) {
+            float alpha = 2.0f;
+            float r2 = float(i) / (EwaLutSize - 1.0f);
+            EWAFilterLut[i] = Math::Expf(-alpha * r2) - Math::Expf(-alpha);
+        }
+        lutReady = true;
+    }
+    TextureResourceData data;
+    memset(&data, 0, sizeof(data));
+    data.mipCount = t->mipCount;
+    data.dataSize = (uint32)t->dataSize;
+    for (uint32_t l = 0; l < t->mipCount; ++l) {
+        data.mipWidths[l] = t->mipWidths[l];
+        data.mipHeights[l] = t->mipHeights[l];
+        data.mipOffsets[l] = t->mipOffsets[l];
+    }
+    data.format = (TextureResourceData::TextureDataType)t->format;
+    data.texture = reinterpret_cast<uint8*>(const_cast<void*>(t->texels));
+    const int comps = (int)t->format + 1;
+    for (size_t i = 0; i < n; ++i) {
+        float2 st(st2[2 * i], st2[2 * i + 1]);
+        float2 d0 = dst0 ? float2(dst0[2 * i], dst0[2 * i + 1]) : float2(0.0f, 0.0f);
+        float2 d1 = dst1 ? float2(dst1[2 * i], dst1[2 * i + 1]) : float2(0.0f, 0.0f);
+        float* o = out + i * comps;
+        switch (comps) {
+            case 1: refFilterOne<float>(&data, filter, level, st, d0, d1, o, 1); break;
+            case 2: refFilterOne<float2>(&data, filter, level, st, d0, d1, o, 2); break;
+            case 3: refFilterOne<float3>(&data, filter, level, st, d0, d1, o, 3); break;
+            default: refFilterOne<float4>(&data, filter, level, st, d0, d1, o, 4); break;
+        }
+    }
+    return 0;
+}
+
 // SampleTextureFloat3(texture, uvs, sRGB, default) of Shading/SurfaceParameters.cpp:97-118 (static there, and that translation unit
 // is not linked): the reference's own TextureFiltering::Triangle template (TextureLib/TextureFiltering.h:77-104) and
 // Math::SrgbToLinearPrecise (MathLib/ColorSpace.cpp) under the same format dispatch.

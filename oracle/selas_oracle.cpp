@@ -684,6 +684,127 @@ int orc_texture_sample(const SelasTextureDesc* t, size_t n, const float* uv2, in
     return 0;
 }
 
+// ---- TextureFiltering::Point / Triangle / Trilinear / EWA, TextureLib/TextureFiltering.h:54-234, restated over n components ----------
+namespace {
+struct MipTex {
+    const SelasTextureMipsDesc* d;
+    int comps;
+    // Sample with WrapMode::Repeat (:35-52); `s % w` is an unsigned modulo there (int32 % uint32)
+    const float* at(uint32_t level, uint32_t w, uint32_t h, int32_t s, int32_t t) const {
+        const uint32_t ss = (uint32_t)s % w, ts = (uint32_t)t % h;
+        return reinterpret_cast<const float*>(static_cast<const uint8_t*>(d->texels) + d->mipOffsets[level]) + ((size_t)ts * w + ss) * comps;
+    }
+};
+float gEwaLut[128];
+bool gEwaLutReady = false;
+void filterTriangle(const MipTex& t, int32_t levelIn, float sx, float sy, float* r) {  // :77-104
+    const uint32_t level = std::min<uint32_t>((uint32_t)levelIn, t.d->mipCount - 1u);
+    const uint32_t w = t.d->mipWidths[level], h = t.d->mipHeights[level];
+    const float s = sx * w - 0.5f, tt = sy * h - 0.5f;
+    const int32_t s0 = (int32_t)floorf(s), t0 = (int32_t)floorf(tt);
+    const float ds = s - s0, dt = tt - t0;
+    const float w00 = (1 - ds) * (1 - dt), w01 = (1 - ds) * dt, w10 = ds * (1 - dt), w11 = ds * dt;
+    const float *a = t.at(level, w, h, s0, t0), *b = t.at(level, w, h, s0, t0 + 1), *c = t.at(level, w, h, s0 + 1, t0), *e = t.at(level, w, h, s0 + 1, t0 + 1);
+    for (int k = 0; k < t.comps; ++k) r[k] = w00 * a[k] + w01 * b[k] + w10 * c[k] + w11 * e[k];
+}
+void filterEwaLevel(const MipTex& t, int32_t reqLevel, float sx, float sy, float d0x, float d0y, float d1x, float d1y, float* r) {  // :107-170
+    if (reqLevel >= (int32_t)t.d->mipCount) {
+        const float* p = t.at(t.d->mipCount - 1u, 1u, 1u, 0, 0);
+        for (int k = 0; k < t.comps; ++k) r[k] = p[k];
+        return;
+    }
+    const uint32_t level = (uint32_t)std::max(reqLevel, 0);
+    const uint32_t w = t.d->mipWidths[level], h = t.d->mipHeights[level];
+    sx = sx * w - 0.5f;
+    sy = sy * h - 0.5f;
+    d0x *= w; d0y *= h; d1x *= w; d1y *= h;
+    float A = d0y * d0y + d1y * d1y + 1;
+    float B = -2 * (d0x * d0y + d1x * d1y);
+    float C = d0x * d0x + d1x * d1x + 1;
+    const float invF = 1 / (A * C - B * B * 0.25f);
+    A *= invF; B *= invF; C *= invF;
+    const float det = -B * B + 4 * A * C;
+    const float invDet = 1 / det;
+    const float uSqrt = sqrtf(det * C), vSqrt = sqrtf(A * det);
+    const int32_t s0 = (int32_t)ceilf(sx - 2 * invDet * uSqrt), s1 = (int32_t)floorf(sx + 2 * invDet * uSqrt);
+    const int32_t t0 = (int32_t)ceilf(sy - 2 * invDet * vSqrt), t1 = (int32_t)floorf(sy + 2 * invDet * vSqrt);
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+    float sumWts = 0;
+    for (int32_t it = t0; it <= t1; ++it) {
+        const float tt = it - sy;
+        for (int32_t is = s0; is <= s1; ++is) {
+            const float ss = is - sx;
+            const float r2 = A * ss * ss + B * ss * tt + C * tt * tt;
+            if (r2 < 1) {
+                const int32_t index = std::min<int32_t>((int32_t)(r2 * 128), 127);
+                const float weight = gEwaLut[index];
+                const float* x = t.at(level, w, h, is, it);
+                for (int k = 0; k < t.comps; ++k) sum[k] += x[k] * weight;
+                sumWts += weight;
+            }
+        }
+    }
+    const float inv = 1.0f / sumWts;
+    for (int k = 0; k < t.comps; ++k) r[k] = sum[k] * inv;
+}
+void lerpN(const float* a, const float* b, float x, int n, float* r) {  // Lerp, FloatFuncs.h:369-387
+    for (int k = 0; k < n; ++k) r[k] = (1.0f - x) * a[k] + x * b[k];
+}
+}  // namespace
+int orc_texture_filter(const SelasTextureMipsDesc* d, int filter, int level, size_t n, const float* st2, const float* dst0, const float* dst1, float* out) {
+    setFtz();
+    if (!gEwaLutReady) {  // InitializeEWAFilterWeights, TextureFiltering.cpp:14-21
+        for (int i = 0; i < 128; ++i) {
+            const float alpha = 2.0f;
+            const float r2 = float(i) / (128 - 1.0f);
+            gEwaLut[i] = expf(-alpha * r2) - expf(-alpha);
+        }
+        gEwaLutReady = true;
+    }
+    MipTex t{d, (int)d->format + 1};
+    for (size_t i = 0; i < n; ++i) {
+        const float sx = st2[2 * i], sy = st2[2 * i + 1];
+        float d0x = dst0 ? dst0[2 * i] : 0.f, d0y = dst0 ? dst0[2 * i + 1] : 0.f, d1x = dst1 ? dst1[2 * i] : 0.f, d1y = dst1 ? dst1[2 * i + 1] : 0.f;
+        float* r = out + i * t.comps;
+        float r0[4], r1[4];
+        if (filter == SELAS_FILTER_POINT) {  // :55-74
+            const uint32_t w = d->mipWidths[0], h = d->mipHeights[0];
+            const float* p = t.at(0, w, h, (int32_t)floorf(sx * w), (int32_t)floorf(sy * h));
+            for (int k = 0; k < t.comps; ++k) r[k] = p[k];
+        } else if (filter == SELAS_FILTER_TRIANGLE) {
+            filterTriangle(t, level, sx, sy, r);
+        } else if (filter == SELAS_FILTER_TRILINEAR) {  // :173-194
+            const float majorLength = sqrtf(d0x * d0x + d0y * d0y), minorLength = sqrtf(d1x * d1x + d1y * d1y);
+            const float length = std::min(majorLength, minorLength);
+            if (length == 0) { filterTriangle(t, 0, sx, sy, r); continue; }
+            const float lod = std::max(0.0f, d->mipCount - 1.0f + log2f(length));
+            const float ilod = floorf(lod);
+            filterTriangle(t, (int32_t)ilod, sx, sy, r0);
+            filterTriangle(t, (int32_t)ilod + 1, sx, sy, r1);
+            lerpN(r0, r1, lod - ilod, t.comps, r);
+        } else if (filter == SELAS_FILTER_EWA) {  // :197-234
+            if (d0x * d0x + d0y * d0y < d1x * d1x + d1y * d1y) { std::swap(d0x, d1x); std::swap(d0y, d1y); }
+            const float majorLength = sqrtf(d0x * d0x + d0y * d0y);
+            float minorLength = sqrtf(d1x * d1x + d1y * d1y);
+            const float maxAnisotropy = 16.0f;
+            if (minorLength * maxAnisotropy < majorLength && minorLength > 0) {
+                const float scale = majorLength / (minorLength * maxAnisotropy);
+                d1x = d1x * scale; d1y = d1y * scale;
+                minorLength *= scale;
+            }
+            if (minorLength == 0) { filterTriangle(t, 0, sx, sy, r); continue; }
+            const float lod = std::max(0.0f, d->mipCount - 1.0f + log2f(minorLength));
+            const float ilod = floorf(lod);
+            filterEwaLevel(t, (int32_t)ilod, sx, sy, d0x, d0y, d1x, d1y, r0);
+            filterEwaLevel(t, (int32_t)ilod + 1, sx, sy, d0x, d0y, d1x, d1y, r1);
+            lerpN(r0, r1, lod - ilod, t.comps, r);
+        } else {
+            filterEwaLevel(t, level, sx, sy, d0x, d0y, d1x, d1y, r);
+        }
+    }
+    return 0;
+}
+
 int orc_scene_destroy(void* s) {
     delete (Scene*)s;
     return 0;

@@ -55,6 +55,33 @@ class TextureDesc(C.Structure):
     _fields_ = [("width", u32), ("height", u32), ("format", u32), ("reserved", u32), ("texels", C.c_void_p)]
 
 
+class TextureMipsDesc(C.Structure):
+    _fields_ = [("mipCount", u32), ("format", u32), ("mipWidths", u32 * 16), ("mipHeights", u32 * 16), ("mipOffsets", C.c_uint64 * 16),
+                ("dataSize", C.c_uint64), ("texels", C.c_void_p)]
+
+
+FILTER_POINT, FILTER_TRIANGLE, FILTER_TRILINEAR, FILTER_EWA, FILTER_EWA_LEVEL = range(5)
+
+
+def texture_mips_desc(levels):
+    """TextureResourceData (TextureLib/TextureResource.h:15-39) from a list of float32 arrays [h, w] or [h, w, comps], finest first; the
+    levels are laid out back to back like the baker does.  Returns (desc, keepalive)."""
+    levels = [np.ascontiguousarray(lv, np.float32) for lv in levels]
+    levels = [lv[:, :, None] if lv.ndim == 2 else lv for lv in levels]
+    comps = levels[0].shape[2]
+    assert 1 <= comps <= 4 and all(lv.shape[2] == comps for lv in levels) and len(levels) <= 16
+    blob = np.concatenate([lv.ravel() for lv in levels])
+    d = TextureMipsDesc()
+    d.mipCount, d.format = len(levels), comps - 1
+    off = 0
+    for i, lv in enumerate(levels):
+        d.mipWidths[i], d.mipHeights[i], d.mipOffsets[i] = lv.shape[1], lv.shape[0], off
+        off += lv.size * 4
+    d.dataSize = off
+    d.texels = blob.ctypes.data
+    return d, blob
+
+
 class MeshDesc(C.Structure):
     _fields_ = [("positions", C.c_void_p), ("vertexCount", u32), ("indices", C.c_void_p), ("faceCount", u32),
                 ("indicesPerFace", u32), ("normals", C.c_void_p), ("tangents", C.c_void_p), ("uvs", C.c_void_p),
@@ -148,7 +175,7 @@ EXPORTS = [
     "selas_cuda_intersect", "selas_cuda_occluded", "selas_cuda_intersect_device", "selas_cuda_occluded_device",
     "selas_cuda_intersect_counted", "selas_cuda_camera_init", "selas_cuda_camera_rays", "selas_cuda_cmj", "selas_cuda_bsdf_eval",
     "selas_cuda_bsdf_sample", "selas_cuda_light_sample", "selas_cuda_light_pdf", "selas_cuda_surface_params",
-    "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample", "selas_cuda_texture_sample",
+    "selas_cuda_ibl_lookup", "selas_cuda_ibl_sample", "selas_cuda_texture_sample", "selas_cuda_texture_filter",
     "selas_cuda_render_pathtracer", "selas_cuda_render_pathtracer_device", "selas_cuda_render_collect_stats", "selas_cuda_film_scale_device",
     "selas_cuda_reduce_film", "selas_cuda_render_vcm", "selas_cuda_render_vcm_device", "selas_cuda_vcm_light_pass", "selas_cuda_vcm_iteration_constants",
     "selas_cuda_hashgrid_build", "selas_cuda_hashgrid_destroy", "selas_cuda_hashgrid_read",
@@ -276,6 +303,19 @@ class Context:
         out = np.zeros((uv.shape[0], 3), np.float32)
         self.check(self.lib.selas_cuda_texture_sample(self.handle, C.byref(td), C.c_size_t(uv.shape[0]), _ptr(uv), C.c_int(1 if srgb else 0),
                                                       _ptr(out)))
+        return out
+
+    def texture_filter(self, levels, filter, st, dst0=None, dst1=None, level=0):
+        """TextureFiltering::Point / Triangle / Trilinear / EWA (TextureFiltering.h:54-234) over a batch; levels as texture_mips_desc."""
+        d, keep = texture_mips_desc(levels)
+        st = _f32(st).reshape(-1, 2)
+        n = st.shape[0]
+        dst0 = None if dst0 is None else _f32(dst0, (n, 2))
+        dst1 = None if dst1 is None else _f32(dst1, (n, 2))
+        out = np.zeros((n, d.format + 1), np.float32)
+        self.check(self.lib.selas_cuda_texture_filter(self.handle, C.byref(d), C.c_int(filter), C.c_int(level), C.c_size_t(n), _ptr(st),
+                                                      _ptr(dst0) if dst0 is not None else None, _ptr(dst1) if dst1 is not None else None, _ptr(out)))
+        del keep
         return out
 
     def light_sample(self, lights, position, normal, u3):

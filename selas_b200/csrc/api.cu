@@ -867,6 +867,45 @@ int selas_cuda_texture_sample(SelasContext* ctx, const SelasTextureDesc* t, size
     return rc;
 }
 
+int selas_cuda_texture_filter(SelasContext* ctx, const SelasTextureMipsDesc* t, int filter, int level, size_t n, const float* st2, const float* dst0,
+                              const float* dst1, float* out) {
+    SELAS_TRY(bind(ctx));
+    const bool needsDerivatives = filter == SELAS_FILTER_TRILINEAR || filter == SELAS_FILTER_EWA || filter == SELAS_FILTER_EWA_LEVEL;
+    bool ok = t && t->mipCount >= 1 && t->mipCount <= SELAS_TEXTURE_MAX_MIPS && t->format <= SELAS_TEXTURE_FLOAT4 && t->texels &&
+              filter >= SELAS_FILTER_POINT && filter <= SELAS_FILTER_EWA_LEVEL && (!n || (st2 && out && (!needsDerivatives || (dst0 && dst1)))) &&
+              !(filter == SELAS_FILTER_EWA_LEVEL && level < 0);
+    for (uint32_t l = 0; ok && l < t->mipCount; ++l) {
+        const uint64_t bytes = (uint64_t)t->mipWidths[l] * t->mipHeights[l] * (t->format + 1u) * sizeof(float);
+        ok = t->mipWidths[l] > 0 && t->mipHeights[l] > 0 && (t->mipOffsets[l] % sizeof(float)) == 0 && t->mipOffsets[l] + bytes <= t->dataSize;
+    }
+    if (!ok) {
+        setError(ctx, "selas_cuda_texture_filter: bad texture descriptor (mip chain outside dataSize?), filter, level or null buffers");
+        return SELAS_ERR_ARGUMENT;
+    }
+    if (!n) return SELAS_OK;
+    // InitializeEWAFilterWeights (TextureFiltering.cpp:14-21), with the C library's expf as in the reference
+    float lut[128];
+    for (int i = 0; i < 128; ++i) {
+        const float alpha = 2.0f;
+        const float r2 = float(i) / (128 - 1.0f);
+        lut[i] = expf(-alpha * r2) - expf(-alpha);
+    }
+    Scratch s(ctx);
+    uint8_t* d_tex;
+    float *d_st, *d_d0 = nullptr, *d_d1 = nullptr, *d_out;
+    SELAS_TRY(s.upload(&d_tex, static_cast<const uint8_t*>(t->texels), (size_t)t->dataSize));
+    SELAS_TRY(s.upload(&d_st, st2, 2 * n));
+    if (needsDerivatives) {
+        SELAS_TRY(s.upload(&d_d0, dst0, 2 * n));
+        SELAS_TRY(s.upload(&d_d1, dst1, 2 * n));
+    }
+    SELAS_TRY(s.alloc(&d_out, n * (t->format + 1u)));
+    SELAS_TRY(launchTextureFilter(ctx, *t, d_tex, lut, filter, level, n, d_st, d_d0, d_d1, d_out));
+    SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d_out, n * (t->format + 1u) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return SELAS_OK;
+}
+
 // ---- integrator ------------------------------------------------------------------------------------------------
 int selas_cuda_render_pathtracer_device(SelasScene* scene, const SelasCamera* camera, const SelasRenderSettings* settings, float* d_film,
                                         SelasRenderStats* stats, void* stream) {

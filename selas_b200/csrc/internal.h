@@ -168,6 +168,8 @@ int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t str
 int launchIblLookup(SelasScene* scene, size_t n, const float* d_wi3, float* d_rgb3, float* d_pdf, float* d_miss3);
 int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp3, uint32_t* d_xy2);
 int launchTextureSample(SelasContext* ctx, const TextureGpu& tex, size_t n, const float* d_uv2, int sRGB, float* d_rgb3);
+int launchTextureFilter(SelasContext* ctx, const SelasTextureMipsDesc& desc, const void* d_texels, const float* ewaLut128, int filter, int level, size_t n,
+                        const float* d_st2, const float* d_dst0, const float* d_dst1, float* d_out);
 int launchCmj(SelasContext* ctx, size_t count, const int32_t* d_s, int32_t m, int32_t n, const int32_t* d_p, float* d_out2);
 void freeWavefront(SelasScene* scene);
 

@@ -192,3 +192,34 @@ def rel_err(a, b, floor=1e-6):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
     return np.abs(a - b) / np.maximum(np.maximum(np.abs(a), np.abs(b)), floor)
+
+
+def mip_chain(size=64, comps=3, seed=3):
+    """A square power-of-two texture with its full box-filtered mip chain down to 1 x 1 (what the reference's baker stores,
+    TextureResourceData::mipCount levels), finest first."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:size, 0:size].astype(np.float32) / size
+    base = np.stack([0.5 + 0.5 * np.sin(6.0 * xx + c) * np.cos(4.0 * yy - c) for c in range(comps)], axis=2).astype(np.float32)
+    base = (base + 0.25 * rng.random(base.shape, dtype=np.float32)).astype(np.float32)
+    levels = [base]
+    while levels[-1].shape[0] > 1:
+        a = levels[-1]
+        levels.append((0.25 * (a[0::2, 0::2] + a[1::2, 0::2] + a[0::2, 1::2] + a[1::2, 1::2])).astype(np.float32))
+    return levels
+
+
+def filter_queries(n=4000, seed=4):
+    """Lookups for the texture filters: st a little outside [0, 1] too (Repeat wrap, incl. negative coordinates), derivative vectors from
+    sub-texel to a quarter of the texture, some degenerate (zero minor axis) and some strongly anisotropic."""
+    rng = np.random.default_rng(seed)
+    st = rng.uniform(-0.5, 1.5, size=(n, 2)).astype(np.float32)
+    mag = np.exp(rng.uniform(np.log(1e-3), np.log(0.25), size=(n, 1))).astype(np.float32)
+    ang = rng.uniform(0, 2 * np.pi, size=(n, 1)).astype(np.float32)
+    d0 = (mag * np.concatenate([np.cos(ang), np.sin(ang)], axis=1)).astype(np.float32)
+    ratio = np.exp(rng.uniform(np.log(1.0 / 64.0), 0.0, size=(n, 1))).astype(np.float32)
+    d1 = (mag * ratio * np.concatenate([-np.sin(ang), np.cos(ang)], axis=1) + 0.1 * mag * ratio * rng.normal(size=(n, 2))).astype(np.float32)
+    swap = rng.random(n) < 0.3
+    d0[swap], d1[swap] = d1[swap].copy(), d0[swap].copy()
+    d1[::97] = 0.0
+    d0[::193] = 0.0
+    return st, d0, d1

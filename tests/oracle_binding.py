@@ -154,6 +154,20 @@ class ShadingOracle(_Lib):
         assert rc == 0, rc
         return out
 
+    def texture_filter(self, levels, filter, st, dst0=None, dst1=None, level=0):
+        """TextureFiltering::Point / Triangle / Trilinear / EWA (TextureFiltering.h:54-234); levels as capi.texture_mips_desc."""
+        d, keep = capi.texture_mips_desc(levels)
+        st = _f32(st).reshape(-1, 2)
+        n = st.shape[0]
+        dst0 = None if dst0 is None else _f32(dst0, (n, 2))
+        dst1 = None if dst1 is None else _f32(dst1, (n, 2))
+        out = np.zeros((n, d.format + 1), np.float32)
+        rc = self.fn("texture_filter")(C.byref(d), C.c_int(filter), C.c_int(level), C.c_size_t(n), _ptr(st),
+                                       _ptr(dst0) if dst0 is not None else None, _ptr(dst1) if dst1 is not None else None, _ptr(out))
+        assert rc == 0, rc
+        del keep
+        return out
+
     # VCM building blocks (live code in the reference: AreaLighting.cpp:246-331, VCMCommon.cpp:37-112) ------------------
     def ibl_emit(self, h, sphere4, u4):
         u4 = _f32(u4).reshape(-1, 4)

@@ -84,6 +84,7 @@ def test_record_layouts():
     assert capi.C.sizeof(capi.VcmSettings) == 56 and capi.C.sizeof(capi.VcmStats) == 104 and capi.VCM_VERTEX_DTYPE.itemsize == 96
     assert capi.C.sizeof(capi.MeshDesc) == 80 and capi.C.sizeof(capi.TextureDesc) == 24 and capi.C.sizeof(capi.SceneDesc) == 120 and capi.C.sizeof(capi.IblDesc) == 56
     assert capi.C.sizeof(capi.CurveDesc) == 40 and capi.C.sizeof(capi.InstanceDesc) == 80 and capi.C.sizeof(capi.BvhStats) == 40
+    assert capi.C.sizeof(capi.TextureMipsDesc) == 8 + 64 + 64 + 128 + 8 + 8
 
 
 def test_vcm_texture_deferred_golden(oracle):
@@ -112,3 +113,22 @@ def test_vcm_texture_deferred_golden(oracle):
     np.testing.assert_allclose(film[0][fin], z["deferred_film"][fin], rtol=1e-5, atol=1e-6)
     np.testing.assert_array_equal(_bits(oracle.texture_sample(z["tex"], z["tex_uv"], True)), _bits(z["tex_srgb"]))
     np.testing.assert_array_equal(_bits(oracle.texture_sample(z["tex"], z["tex_uv"], False)), _bits(z["tex_linear"]))
+
+
+def test_texture_filter_golden(oracle):
+    """Point / Triangle(level) / Trilinear / EWA / EWA(level) against vectors written by the reference's own TextureFiltering templates
+    (tests/golden/make_texture_filter.py).  Trilinear and EWA go through log2f / expf of the C library that produced the fixture: they are
+    compared to 2e-6, everything else bit for bit."""
+    from tests import inputs
+    from tests.golden.make_texture_filter import CASES
+
+    z = np.load(G / "texture_filter.npz")
+    for comps in (1, 3, 4):
+        levels = inputs.mip_chain(32, comps, seed=30 + comps)
+        st, d0, d1 = inputs.filter_queries(600, seed=40 + comps)
+        for flt, level in CASES:
+            got, want = oracle.texture_filter(levels, flt, st, d0, d1, level), z[f"c{comps}_f{flt}_l{level}"]
+            if flt in (capi.FILTER_POINT, capi.FILTER_TRIANGLE):
+                np.testing.assert_array_equal(_bits(got), _bits(want))
+            else:
+                np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-7)

@@ -503,3 +503,30 @@ def test_ibl_parity_and_background(ctx, oracle):
     sc2.close()
     oracle.scene_destroy(hs)
     sc.close()
+
+
+@pytest.mark.parametrize("comps", [1, 3, 4])
+def test_texture_filters_vs_oracle(ctx, oracle, comps):
+    """SURVEY 8(f)4: TextureFiltering::Point / Triangle(level) / Trilinear / EWA (TextureFiltering.h:54-234) on the device against the
+    restatement that is bit-identical to the reference's templates (test_oracle_vs_ref.py).  The device code keeps the reference's
+    operation order under -fmad=false and takes the EWA weight table from the host C library: Point, Triangle and the per-level EWA are
+    bit-exact; Trilinear and the blended EWA go through log2f (1-2 ulp apart) and agree to 1e-5."""
+    from tests import inputs
+
+    levels = inputs.mip_chain(128, comps, seed=50 + comps)
+    st, d0, d1 = inputs.filter_queries(20000, seed=60 + comps)
+    for flt, level in ((capi.FILTER_POINT, 0), (capi.FILTER_TRIANGLE, 0), (capi.FILTER_TRIANGLE, 4), (capi.FILTER_TRIANGLE, 99), (capi.FILTER_EWA_LEVEL, 0),
+                       (capi.FILTER_EWA_LEVEL, 3), (capi.FILTER_EWA_LEVEL, 12)):
+        got, want = ctx.texture_filter(levels, flt, st, d0, d1, level), oracle.texture_filter(levels, flt, st, d0, d1, level)
+        np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32), err_msg=f"filter {flt} level {level}")
+    for flt in (capi.FILTER_TRILINEAR, capi.FILTER_EWA):
+        got, want = ctx.texture_filter(levels, flt, st, d0, d1), oracle.texture_filter(levels, flt, st, d0, d1)
+        assert np.isfinite(got).all()
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+    # error behaviour: derivative buffers are required by the filters that use them, the mip chain must lie inside dataSize
+    with pytest.raises(capi.SelasError):
+        ctx.texture_filter(levels, capi.FILTER_EWA, st)
+    with pytest.raises(capi.SelasError):
+        ctx.texture_filter(levels, capi.FILTER_EWA_LEVEL, st, d0, d1, level=-1)
+    with pytest.raises(capi.SelasError):
+        ctx.texture_filter(levels, 7, st, d0, d1)

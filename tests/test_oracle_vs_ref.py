@@ -424,3 +424,22 @@ def test_surface_params_bit_exact_vs_reference_calculate_surface_params(oracle, 
         np.testing.assert_array_equal(a[f].view(np.uint32), b[f].view(np.uint32), err_msg=f)
     oracle.scene_destroy(ha)
     ref.scene_destroy(hb)
+
+
+@pytest.mark.parametrize("comps", [1, 2, 3, 4])
+def test_texture_filters_bit_exact_vs_reference_templates(oracle, ref, comps):
+    """TextureFiltering::Point / Triangle(level) / Trilinear / EWA / EWA(level) (TextureFiltering.h:54-234; SURVEY 8(f)4): the restatement
+    against the reference's own templates instantiated for float / float2 / float3 / float4 over a 7-level mip chain."""
+    from tests import inputs
+
+    levels = inputs.mip_chain(64, comps, seed=10 + comps)
+    st, d0, d1 = inputs.filter_queries(3000, seed=20 + comps)
+    for flt, level in ((capi.FILTER_POINT, 0), (capi.FILTER_TRIANGLE, 0), (capi.FILTER_TRIANGLE, 3), (capi.FILTER_TRIANGLE, 40), (capi.FILTER_TRILINEAR, 0),
+                       (capi.FILTER_EWA, 0), (capi.FILTER_EWA_LEVEL, 2), (capi.FILTER_EWA_LEVEL, 9)):
+        a = oracle.texture_filter(levels, flt, st, d0, d1, level)
+        b = ref.texture_filter(levels, flt, st, d0, d1, level)
+        assert np.isfinite(b).all(), flt
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"filter {flt} level {level}")
+    # the filters do different things: EWA of a wide footprint is far from the point sample
+    wide = np.linalg.norm(d1, axis=1) > 0.05
+    assert np.abs(oracle.texture_filter(levels, capi.FILTER_EWA, st, d0, d1)[wide] - oracle.texture_filter(levels, capi.FILTER_POINT, st)[wide]).mean() > 0.02
