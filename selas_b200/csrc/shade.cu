@@ -982,6 +982,11 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     // batches by direction category, PathTracingBatcher.cpp:162).  Default: off -- see DESIGN.md for the measurement.
     static const uint32_t raySortFrom = getenv("SELAS_RAY_SORT") ? (uint32_t)atoi(getenv("SELAS_RAY_SORT")) : 0xFFFFFFFFu;
     const float raySortCx = scene->boundsCenter[0], raySortCz = scene->boundsCenter[2];  // origin quadrants about the scene's centre
+    // Warp-cooperative triangle stage (trace_coop.cuh) per bounce: camera rays are coherent and stay with traceKernel; everything after the
+    // first bounce, and the shadow rays from the first hit on, go through traceCoopKernel.  SELAS_COOP_CLOSEST_FROM / SELAS_COOP_SHADOW_FROM
+    // = first bounce that uses it (a large number switches it off).
+    static const uint32_t coopClosestFrom = getenv("SELAS_COOP_CLOSEST_FROM") ? (uint32_t)atoi(getenv("SELAS_COOP_CLOSEST_FROM")) : 1u;
+    static const uint32_t coopShadowFrom = getenv("SELAS_COOP_SHADOW_FROM") ? (uint32_t)atoi(getenv("SELAS_COOP_SHADOW_FROM")) : 0u;
     static const bool shadeOneShot = !(getenv("SELAS_SHADE_ONESHOT") && atoi(getenv("SELAS_SHADE_ONESHOT")) == 0);
     static const int shadeWaves = getenv("SELAS_SHADE_WAVES") ? std::max(1, atoi(getenv("SELAS_SHADE_WAVES"))) : 2;
 
@@ -1041,7 +1046,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 rayOrder = w->rayOrder;
                 launches += 3;
             }
-            rc = launchIntersectIndirect(scene, ctr, count, w->rays[cur], w->hits, ctr + 2, d_totals, stream, rayOrder);
+            rc = launchIntersectIndirect(scene, ctr, count, w->rays[cur], w->hits, ctr + 2, d_totals, stream, rayOrder, it >= coopClosestFrom ? 1 : 0);
             if (rc) return rc;
             timers.end(1, t0, stream);
             t0 = timers.begin(stream);
@@ -1087,7 +1092,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 float* filmRadiance = d_film + (rs.layerCount == 2 ? 3 * (size_t)pixels : 0);
                 t0 = timers.begin(stream);
                 rc = launchShadowAccumulate(scene, next + 1, count * w->shadowPerPath, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
-                                            d_totals ? d_totals + 2 : nullptr, stream);
+                                            d_totals ? d_totals + 2 : nullptr, stream, it >= coopShadowFrom ? 1 : 0);
                 if (rc) return rc;
                 timers.end(3, t0, stream);
             }

@@ -8,6 +8,7 @@
 #include "bvh_sah.cuh"
 #include "internal.h"
 #include "trace.cuh"
+#include "trace_coop.cuh"
 
 namespace selas {
 
@@ -677,6 +678,14 @@ static TraceLaunch traceLaunch(const SelasScene* scene, K kernel) {
     l.grid = scene->ctx->smCount * perSm;
     return l;
 }
+// SELAS_TRACE_COOP=1: flattened trees without curves go through the kernel with the warp-cooperative triangle stage (trace_coop.cuh)
+static bool traceCoopEnabled() {
+    static const bool on = getenv("SELAS_TRACE_COOP") && atoi(getenv("SELAS_TRACE_COOP")) != 0;
+    return on;
+}
+// the wavefront asks per launch (coop: -1 = the process default above, 0 / 1 = no / yes): primary rays are coherent and run better
+// through traceKernel, everything after the first bounce and the shadow rays through traceCoopKernel (measurements in trace_coop.cuh)
+static bool traceCoopFor(int coop) { return coop < 0 ? traceCoopEnabled() : coop != 0; }
 // kernel variant by scene: two-level form only when the scene was built that way (the flattened form keeps its register budget), staged
 // top levels only when asked for
 #define SELAS_TRACE_GO2(MODE, COUNT, INST, TOP, CURVES, ...)                                                       \
@@ -693,7 +702,10 @@ static TraceLaunch traceLaunch(const SelasScene* scene, K kernel) {
         } else if (inst__ && top__) SELAS_TRACE_GO2(MODE, COUNT, true, true, false, __VA_ARGS__);                  \
         else if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, false, __VA_ARGS__);                            \
         else if (top__) SELAS_TRACE_GO2(MODE, COUNT, false, true, false, __VA_ARGS__);                             \
-        else SELAS_TRACE_GO2(MODE, COUNT, false, false, false, __VA_ARGS__);                                       \
+        else if (coop__) {                                                                                          \
+            TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT>);                                     \
+            traceCoopKernel<MODE, COUNT><<<tl.grid, SELAS_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);                \
+        } else SELAS_TRACE_GO2(MODE, COUNT, false, false, false, __VA_ARGS__);                                     \
     } while (0)
 
 int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_ng4, uint32_t* d_counts,
@@ -701,6 +713,7 @@ int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, Selas
     if (n == 0) return SELAS_OK;
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
+    const bool coop__ = traceCoopEnabled();
     if (d_counts)
         SELAS_TRACE_GO(0, true, bvhOf(scene, true), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
@@ -714,6 +727,7 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
     if (n == 0) return SELAS_OK;
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
+    const bool coop__ = traceCoopEnabled();
     if (d_counts)
         SELAS_TRACE_GO(1, true, bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
@@ -725,8 +739,9 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
 // Wavefront variants: the queue length lives in device memory (or n is exact when d_n is null); d_rayCounter must
 // already be zero.  totals != null selects the counting build of the same kernel (SELAS_RENDER_COUNT_TRAVERSAL).
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
-                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order) {
+                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order, int coop) {
     SelasContext* ctx = scene->ctx;
+    const bool coop__ = traceCoopFor(coop);
     if (d_totals)
         SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, d_totals, d_order);
     else
@@ -736,8 +751,9 @@ int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t max
 }
 
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
-                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream) {
+                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop) {
     SelasContext* ctx = scene->ctx;
+    const bool coop__ = traceCoopFor(coop);
     if (d_totals)
         SELAS_TRACE_GO(2, true, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, d_totals);
     else

@@ -47,6 +47,52 @@ SELAS_D void setupRayDirection(V3 d, V3& idir, bool& negx, bool& negy, bool& neg
     octInv4 = (7u - oct) * 0x01010101u;
 }
 
+// Leaf triangles deferred by one node (round 2).  ncu on the bounce-0 launch (profiles/r2_trace_bounce0_sass_summary.txt): the triangle
+// tests were 30 % of the kernel's warp instructions at 3.3 lanes and HALF of its stall samples, most of them on the first use of the
+// triangle's LDGs -- a lane loaded the node, waited, tested it, then loaded the leaf triangles and waited again, twice the memory latency
+// per step with almost nothing in flight the second time.  With SELAS_TRI_DEFER the leaf hits of a node are parked in two registers and
+// tested in the NEXT iteration, after the loads of the next node have been issued: both latencies overlap, and because the parked
+// triangles are still tested before that node's slab test, the test sees the updated tmax (at most the choice of the next node is one
+// hit out of date).  Two-level scenes keep the direct order (a top-level "triangle" is an instance entry that changes the ray).
+// MEASURED (profiles/r2_ab_tri_defer*.jsonl): slower both ways -- holding the next node's five vectors in registers across the triangle
+// test spills the ray constants (closest hit 8.25 -> 8.72 ms per step), and the register-free form below (prefetch.global.L1 of the
+// triangles when they are found and of the next node before they are tested) costs the same (8.71): the extra turn of the loop for the
+// parked group and the prefetch instructions outweigh the latency, which the other seven warps of the scheduler were already hiding
+// (issue slots are 70 % busy).  Off; the stall samples on the triangle loads were not lost time.
+#ifndef SELAS_TRI_DEFER
+#define SELAS_TRI_DEFER 0
+#endif
+
+SELAS_D void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// The triangles (or curve parts) of one leaf group against the lane's ray; returns true when an any-hit ray is done.
+template <bool ANY, bool COUNT, bool CURVES>
+SELAS_D bool testLeafGroup(const Bvh8& bvh, uint2 triGroup, V3 o, V3 d, float tnear, float& tmax, TraceResult& res, uint32_t& nTris) {
+    while (triGroup.y != 0u) {
+        const uint32_t bit = 31u - __clz(triGroup.y);
+        triGroup.y &= ~(1u << bit);
+        const uint32_t ti = triGroup.x + bit;
+        const float4* tp = bvh.tris + (size_t)ti * 3;
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        if (COUNT) ++nTris;
+        float t, u, v;
+        if (CURVES && (__float_as_uint(c.w) & kLeafCurveFlag)) {
+            const float4* cp = bvh.curves + 4 * (size_t)__float_as_uint(a.x);
+            CurveHit ch;
+            if (intersectCurve(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3), __float_as_uint(a.y), o, d, tnear, tmax, ch)) {
+                tmax = ch.t;
+                res.t = ch.t; res.u = ch.u; res.v = 0.f; res.tri = ti; res.element = ch.element; res.ng = ch.ng;
+                if (ANY) return true;
+            }
+        } else if (intersectTri(a, b, c, o, d, tnear, tmax, t, u, v)) {
+            tmax = t;
+            res.t = t; res.u = u; res.v = v; res.tri = ti;
+            if (ANY) return true;
+        }
+    }
+    return false;
+}
+
 template <int MODE, bool COUNT, bool INST = false, bool TOP = false, bool CURVES = false>
 __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES) ? 6 : SELAS_TRACE_CTAS_PER_SM) traceKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n,
                                                                    const uint32_t* __restrict__ nPtr,
@@ -77,9 +123,8 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
     uint2 stack[SELAS_STACK_SIZE];
     int sp = 0;
     uint2 group = make_uint2(0u, 0u);
-#if SELAS_TRI_POSTPONE_DIV
-    uint2 pendTri = make_uint2(0u, 0u);
-#endif
+    uint2 pendTri = make_uint2(0u, 0u);  // parked leaf triangles (SELAS_TRI_DEFER / SELAS_TRI_POSTPONE_DIV)
+    (void)pendTri;
     V3 o = v3(0.f), d = v3(0.f), idir = v3(0.f);
     float tnear = 0.f, tfar = 0.f, tmax = 0.f;
     bool negx = false, negy = false, negz = false;
@@ -129,9 +174,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
                     group = make_uint2(0u, (bvh.nodeCount && valid) ? 0x80000000u : 0u);
                     rayIdx = idx;
                     nNodes = 0; nTris = 0;
-#if SELAS_TRI_POSTPONE_DIV
                     pendTri = make_uint2(0u, 0u);
-#endif
                     active = true;
                 }
             }
@@ -139,6 +182,73 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
         if (!__any_sync(0xffffffffu, active)) break;
 
         // ---- traverse until this lane finishes or the warp runs thin ----
+        if constexpr (SELAS_TRI_DEFER && !INST && !TOP && !SELAS_TRI_POSTPONE_DIV) {
+            while (active) {
+                bool finished = false;
+                const bool hasNode = (group.y & 0xff000000u) != 0u;
+                const float4* np = bvh.nodes;
+                if (hasNode) {
+                    const uint32_t hitsImask = group.y;
+                    const uint32_t childBit = 31u - __clz(hitsImask);
+                    group.y &= ~(1u << childBit);
+                    if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
+                    const uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
+                    const uint32_t rel = __popc(hitsImask & ~(0xffffffffu << slot));
+                    np = bvh.nodes + (size_t)(group.x + rel) * 5;
+                    if (pendTri.y != 0u) {  // the node's lines start their way up while the parked triangles are tested
+                        prefetchL1(np);
+                        prefetchL1(np + 4);
+                    }
+                    if (COUNT) ++nNodes;
+                }
+                // the previous node's leaf hits (prefetched when they were found)
+                if (pendTri.y != 0u) {
+                    finished = testLeafGroup<ANY, COUNT, CURVES>(bvh, pendTri, o, d, tnear, tmax, res, nTris);
+                    pendTri = make_uint2(0u, 0u);
+                }
+                if (hasNode && !finished) {
+                    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                    const uint32_t hitMask = intersectNode(n0, n1, n2, n3, n4, o, idir, negx, negy, negz, octInv4, tnear, tmax);
+                    group.x = __float_as_uint(n1.x);
+                    group.y = (hitMask & 0xff000000u) | extractByte(__float_as_uint(n0.w), 3);
+                    pendTri = make_uint2(__float_as_uint(n1.y), hitMask & 0x00ffffffu);
+                    if (pendTri.y != 0u) {
+                        const float4* tlo = bvh.tris + (size_t)(pendTri.x + (uint32_t)__ffs((int)pendTri.y) - 1u) * 3;
+                        const float4* thi = bvh.tris + (size_t)(pendTri.x + 31u - (uint32_t)__clz(pendTri.y)) * 3;
+                        prefetchL1(tlo);
+                        prefetchL1(tlo + 2);
+                        prefetchL1(thi);
+                        prefetchL1(thi + 2);
+                    }
+                }
+                if (!finished && (group.y & 0xff000000u) == 0u) {
+                    if (sp > 0) group = stack[--sp];
+                    else {
+                        group = make_uint2(0u, 0u);
+                        finished = pendTri.y == 0u;  // else one more turn for the parked triangles
+                    }
+                }
+                if (finished) {
+                    if (MODE == 1) occluded[rayIdx] = res.tri != 0xFFFFFFFFu ? 1 : 0;
+                    else if (MODE == 2) {
+                        if (res.tri == 0xFFFFFFFFu) {
+                            float4 pl = __ldg(payload + rayIdx);
+                            float* px = film + 3 * (size_t)__float_as_uint(pl.w);
+                            atomicAdd(px, pl.x);
+                            atomicAdd(px + 1, pl.y);
+                            atomicAdd(px + 2, pl.z);
+                        }
+                    } else writeHit<INST>(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
+                    if (COUNT) {
+                        if (counts) { counts[2 * (size_t)rayIdx] = nNodes; counts[2 * (size_t)rayIdx + 1] = nTris; }
+                        sumNodes += nNodes;
+                        sumTris += nTris;
+                    }
+                    active = false;
+                }
+                if (!exhausted && __popc(__activemask()) < SELAS_REFILL_THRESHOLD) break;
+            }
+        } else
         while (active) {
             bool finished = false;
             uint2 triGroup;

@@ -1,0 +1,243 @@
+// trace_coop.cuh -- the BVH8 ray-cast kernel with a warp-cooperative triangle stage (round-2 experiment, SELAS_TRACE_COOP=1).
+//
+// Why: ncu on the closest-hit launch of configs[2] (profiles/r2_trace_bounce0_sass_summary.txt) shows the leaf triangle tests as 30 % of
+// the kernel's warp instructions at 3.3 of 32 lanes: a ray meets its 3.2 leaf triangles at a handful of its 12 node visits, so in any
+// one iteration only a few lanes of the warp have triangles and each runs Moller-Trumbore alone.  Here a lane does not test the leaf
+// triangles its node test finds; it appends (lane, triangle) pairs to a per-warp queue in shared memory and goes on traversing.  When
+// the queue holds enough pairs (or rays are waiting on theirs) the WHOLE warp -- idle lanes included -- tests one pair per lane: the
+// source lane's ray comes over with eight shuffles, the hit goes back through a 64-bit atomicMin on {t, triangle} in shared memory.
+// Closest-hit results do not depend on the order of the tests (minimum over all candidates; equal t: the lower triangle index, so
+// reruns are bit-identical although the queue order is not), and tmax is only an optimisation for the slab test, so letting it lag a
+// few node visits is safe.
+//
+// Same interface, launch shape and ray pulling (ballot-ranked refill) as traceKernel; flattened trees without curves only.
+#pragma once
+#include "trace.cuh"
+
+namespace selas {
+
+#ifndef SELAS_COOP_QCAP
+#define SELAS_COOP_QCAP 96
+#endif
+#ifndef SELAS_COOP_FLUSH_MIN
+#define SELAS_COOP_FLUSH_MIN 16
+#endif
+#ifndef SELAS_COOP_REFILL_THRESHOLD
+#define SELAS_COOP_REFILL_THRESHOLD 24
+#endif
+#ifndef SELAS_COOP_WAIT_MAX
+#define SELAS_COOP_WAIT_MAX 4
+#endif
+SELAS_D uint32_t orderedFloatBits(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+SELAS_D float fromOrderedFloatBits(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(SELAS_TRACE_THREADS, COUNT ? 6 : SELAS_TRACE_CTAS_PER_SM)
+    traceCoopKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n, const uint32_t* __restrict__ nPtr, SelasHit* __restrict__ hits,
+                    uint8_t* __restrict__ occluded, float4* __restrict__ ng, uint32_t* __restrict__ counts, const float4* __restrict__ payload,
+                    float* __restrict__ film, uint32_t* __restrict__ nextRay, unsigned long long* __restrict__ totals,
+                    const uint32_t* __restrict__ order = nullptr) {
+    constexpr bool ANY = MODE != 0;
+    constexpr int WARPS = SELAS_TRACE_THREADS / 32;
+    constexpr uint32_t FULL = 0xffffffffu;
+    __shared__ uint32_t sQueue[WARPS][SELAS_COOP_QCAP];          // lane | triangle << 5
+    __shared__ uint32_t sTail[WARPS];                            // queue length
+    __shared__ float2 sUv[WARPS][32];                            // per source lane: (u, v) of its best hit
+    __shared__ unsigned long long sBest[WARPS][32];              // per source lane: ordered(t) << 32 | triangle
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    uint32_t* const q = sQueue[warp];
+    float2* const quv = sUv[warp];
+    unsigned long long* const best = sBest[warp];
+    uint32_t* const tail = &sTail[warp];
+    if (lane == 0) *tail = 0u;
+    __syncwarp();
+    if (nPtr) n = min(n, *nPtr);
+
+    uint2 stack[SELAS_STACK_SIZE];
+    int sp = 0;
+    uint2 group = make_uint2(0u, 0u);
+    V3 o = v3(0.f), d = v3(0.f), idir = v3(0.f);
+    float tnear = 0.f, tfar = 0.f, tmax = 0.f;
+    bool negx = false, negy = false, negz = false;
+    uint32_t octInv4 = 0;
+    TraceResult res;
+    res.t = 0.f; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu; res.inst = 0u; res.element = 0u; res.ng = v3(0.f);
+    uint32_t rayIdx = 0xFFFFFFFFu;
+    uint32_t nNodes = 0, nTris = 0;
+    unsigned long long sumNodes = 0, sumTris = 0;
+    bool active = false, exhausted = false;
+    bool outstanding = false;  // this lane has pairs in the queue
+    bool done = false;         // any-hit: a queued triangle was hit
+    uint32_t qCount = 0;       // warp-uniform
+
+    // the whole warp tests the queued pairs, one per lane and round
+    auto flush = [&]() {
+        __syncwarp();
+        best[lane] = ((unsigned long long)orderedFloatBits(tmax) << 32) | 0xFFFFFFFFull;
+        __syncwarp();
+        for (uint32_t base = 0; base < qCount; base += 32u) {
+            const uint32_t e = base + lane;
+            const bool valid = e < qCount;
+            const uint32_t entry = valid ? q[e] : 0u;
+            const uint32_t src = entry & 31u;
+            const V3 so = v3(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
+            const V3 sd = v3(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
+            const float stn = __shfl_sync(FULL, tnear, src), stm = __shfl_sync(FULL, tmax, src);
+            bool hit = false;
+            unsigned long long key = 0ull;
+            float t, u, v;
+            if (valid) {
+                const float4* tp = bvh.tris + (size_t)(entry >> 5) * 3;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                hit = intersectTri(a, b, c, so, sd, stn, stm, t, u, v);
+                if (hit) {
+                    key = ((unsigned long long)orderedFloatBits(t) << 32) | (unsigned long long)(entry >> 5);
+                    atomicMin(&best[src], key);
+                }
+            }
+            __syncwarp();
+            if (hit && best[src] == key) quv[src] = make_float2(u, v);  // the best so far (a later round's better hit overwrites it)
+            __syncwarp();
+        }
+        if (outstanding) {
+            const unsigned long long b = best[lane];
+            const uint32_t tri = (uint32_t)b;
+            if (tri != 0xFFFFFFFFu) {
+                const float t = fromOrderedFloatBits((uint32_t)(b >> 32));
+                const float2 uv = quv[lane];
+                tmax = t;
+                res.t = t; res.u = uv.x; res.v = uv.y; res.tri = tri;
+                if (ANY) done = true;
+            }
+            outstanding = false;
+        }
+        qCount = 0;
+        if (lane == 0) *tail = 0u;
+        __syncwarp();
+    };
+
+    for (;;) {
+        // ---- refill idle lanes once the warp runs thin ----
+        const uint32_t idle = __ballot_sync(FULL, !active);
+        if (!exhausted && 32 - __popc(idle) < SELAS_COOP_REFILL_THRESHOLD) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(nextRay, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= n) exhausted = true;
+            if (!active) {
+                uint32_t idx = base + __popc(idle & ltMask);
+                if (idx < n) {
+                    if (order) idx = __ldg(order + idx);
+                    const float4* rp = reinterpret_cast<const float4*>(rays + idx);
+                    const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                    o = v3(r0.x, r0.y, r0.z);
+                    d = v3(r1.x, r1.y, r1.z);
+                    tnear = r0.w;
+                    tfar = r1.w;
+                    tmax = tfar;
+                    setupRayDirection(d, idir, negx, negy, negz, octInv4);
+                    res.t = tfar; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
+                    sp = 0;
+                    const bool valid = isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z) &&
+                                       tnear <= tfar;
+                    group = make_uint2(0u, (bvh.nodeCount && valid) ? 0x80000000u : 0u);
+                    rayIdx = idx;
+                    nNodes = 0; nTris = 0;
+                    outstanding = false;
+                    done = false;
+                    active = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+
+        // ---- one node per traversing lane ----
+        uint32_t leafMask = 0u, leafBase = 0u;
+        if (active && (group.y & 0xff000000u)) {
+            const uint32_t hitsImask = group.y;
+            const uint32_t childBit = 31u - __clz(hitsImask);
+            group.y &= ~(1u << childBit);
+            if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
+            const uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
+            const uint32_t rel = __popc(hitsImask & ~(0xffffffffu << slot));
+            const float4* np = bvh.nodes + (size_t)(group.x + rel) * 5;
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if (COUNT) ++nNodes;
+            const uint32_t hitMask = intersectNode(n0, n1, n2, n3, n4, o, idir, negx, negy, negz, octInv4, tnear, tmax);
+            group.x = __float_as_uint(n1.x);
+            group.y = (hitMask & 0xff000000u) | extractByte(__float_as_uint(n0.w), 3);
+            leafBase = __float_as_uint(n1.y);
+            leafMask = hitMask & 0x00ffffffu;
+        }
+
+        // ---- leaf hits go to the warp's queue (slots by a shared-memory atomic: the order within the queue does not matter) ----
+        const uint32_t cnt = (uint32_t)__popc(leafMask);
+        const uint32_t total = __reduce_add_sync(FULL, cnt);
+        if (total) {
+            if (qCount + total > SELAS_COOP_QCAP && qCount) flush();
+            if (total > SELAS_COOP_QCAP) {
+                // more leaf hits in one step than the queue holds (up to 24 per lane): every lane tests its own, as traceKernel does
+                if (cnt) {
+                    uint32_t dummy = 0;
+                    if (testLeafGroup<ANY, false, false>(bvh, make_uint2(leafBase, leafMask), o, d, tnear, tmax, res, dummy)) done = true;
+                }
+            } else {
+                if (cnt) {
+                    uint32_t w = atomicAdd(tail, cnt);
+                    uint32_t m = leafMask;
+                    while (m) {
+                        const uint32_t bit = 31u - __clz(m);
+                        m &= ~(1u << bit);
+                        q[w++] = lane | ((leafBase + bit) << 5);
+                    }
+                    outstanding = true;
+                }
+                qCount += total;
+            }
+            if (COUNT) nTris += cnt;
+        }
+
+        // ---- next group; flush when the queue is full enough, rays are waiting on it, or nobody has a node left ----
+        if (active && (group.y & 0xff000000u) == 0u && sp > 0) group = stack[--sp];
+        const bool hasWork = active && !done && (group.y & 0xff000000u) != 0u;
+        const uint32_t waiting = __ballot_sync(FULL, active && !hasWork && outstanding);
+        const bool anyWork = __any_sync(FULL, hasWork);
+        if (qCount && (qCount >= SELAS_COOP_FLUSH_MIN || __popc(waiting) >= SELAS_COOP_WAIT_MAX || !anyWork)) flush();
+
+        // ---- rays with nothing left ----
+        if (active && !outstanding && (done || (group.y & 0xff000000u) == 0u)) {
+            if (MODE == 1) occluded[rayIdx] = res.tri != 0xFFFFFFFFu ? 1 : 0;
+            else if (MODE == 2) {
+                if (res.tri == 0xFFFFFFFFu) {
+                    const float4 pl = __ldg(payload + rayIdx);
+                    float* px = film + 3 * (size_t)__float_as_uint(pl.w);
+                    atomicAdd(px, pl.x);
+                    atomicAdd(px + 1, pl.y);
+                    atomicAdd(px + 2, pl.z);
+                }
+            } else writeHit<false>(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
+            if (COUNT) {
+                if (counts) { counts[2 * (size_t)rayIdx] = nNodes; counts[2 * (size_t)rayIdx + 1] = nTris; }
+                sumNodes += nNodes;
+                sumTris += nTris;
+            }
+            active = false;
+        }
+    }
+    if (COUNT && totals) {
+        for (int s = 16; s > 0; s >>= 1) {
+            sumNodes += __shfl_xor_sync(FULL, sumNodes, s);
+            sumTris += __shfl_xor_sync(FULL, sumTris, s);
+        }
+        if (lane == 0) {
+            atomicAdd(totals, sumNodes);
+            atomicAdd(totals + 1, sumTris);
+        }
+    }
+}
+
+}  // namespace selas
