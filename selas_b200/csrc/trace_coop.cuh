@@ -187,13 +187,14 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, COUNT ? 6 : SELAS_TRACE_C
                 }
             } else {
                 if (cnt) {
-                    uint32_t w = atomicAdd(tail, cnt);
+                    uint32_t* qp = q + atomicAdd(tail, cnt);
+                    const uint32_t entryBase = lane | (leafBase << 5);
                     uint32_t m = leafMask;
-                    while (m) {
+                    do {
                         const uint32_t bit = 31u - __clz(m);
-                        m &= ~(1u << bit);
-                        q[w++] = lane | ((leafBase + bit) << 5);
-                    }
+                        m ^= 1u << bit;
+                        *qp++ = entryBase + (bit << 5);
+                    } while (m);
                     outstanding = true;
                 }
                 qCount += total;
