@@ -931,6 +931,13 @@ int vcmAlloc(SelasContext* ctx, VcmBuffers* w, T** p, size_t count) {
     return SELAS_OK;
 }
 
+// Light sub-paths start in random directions from the sky and camera sub-paths are incoherent after the first hit: those launches, and all
+// shadow rays, go through the kernel with the warp-cooperative triangle stage (trace_coop.cuh); SELAS_VCM_COOP=0 keeps traceKernel.
+static int vcmCoop() {
+    static const int on = (getenv("SELAS_VCM_COOP") && atoi(getenv("SELAS_VCM_COOP")) == 0) ? 0 : 1;
+    return on;
+}
+
 static int allocateVcm(SelasScene* scene, uint32_t vmCount, uint32_t maxPathLength) {
     SelasContext* ctx = scene->ctx;
     VcmBuffers* w = (VcmBuffers*)scene->vcm;
@@ -1087,7 +1094,7 @@ int lightPass(SelasScene* scene, const SelasCamera& cam, const VcmParams& prm, f
     int cur = 0;
     for (uint32_t it = 0; it < prm.stride && n > 0; ++it) {
         uint32_t* ctr = w->counters + 4 * (size_t)it;
-        int rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, nullptr, stream);
+        int rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, nullptr, stream, nullptr, vcmCoop());
         if (rc) return rc;
         st.closestRays += n;
         if (scene->usesPtex) {
@@ -1115,7 +1122,7 @@ int lightPass(SelasScene* scene, const SelasCamera& cam, const VcmParams& prm, f
         SELAS_CUDA_CHECK(ctx, cudaEventRecord(w->evCounts, stream));
         st.kernelLaunches += 2;
         if (!(prm.flags & SELAS_VCM_NO_LIGHT_TRACING)) {
-            rc = launchShadowAccumulate(scene, ctr + 1, n, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream);
+            rc = launchShadowAccumulate(scene, ctr + 1, n, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream, vcmCoop());
             if (rc) return rc;
             ++st.kernelLaunches;
         }
@@ -1203,7 +1210,7 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
         int cur = 0;
         for (uint32_t it = 0; it + 1 < vs.maxPathLength && n > 0; ++it) {  // pathLength = it + 1 < maxPathLength
             uint32_t* ctr = w->counters + 4 * (size_t)it;
-            rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, nullptr, stream);
+            rc = launchIntersectIndirect(scene, nullptr, n, w->rays[cur], w->hits, ctr + 2, nullptr, stream, nullptr, it >= 1 ? vcmCoop() : 0);
             if (rc) return rc;
             st.closestRays += n;
             const float* ptexRgb = nullptr;
@@ -1258,7 +1265,7 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
                 st.kernelLaunches += 2;
             }
             // shadow rays of the direct connection and of the vertex connections: count read on the device
-            rc = launchShadowAccumulate(scene, ctr + 1, w->shadowCapacity, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream);
+            rc = launchShadowAccumulate(scene, ctr + 1, w->shadowCapacity, w->shadowRays, w->shadowPayload, d_film, ctr + 3, nullptr, stream, vcmCoop());
             if (rc) return rc;
             ++st.kernelLaunches;
             SELAS_CUDA_CHECK(ctx, cudaGetLastError());
