@@ -438,7 +438,7 @@ def main():
     kernel_ms = agg["closestMs"] + agg["shadeMs"] + agg["shadowMs"] + agg["generateMs"]
     rays_per_launch = agg["closestRays"] / max(1, agg["closestLaunches"])
     dram_per_ray, traffic_src = captured_traffic_per_ray()
-    roofline = {"bound": "hbm", "kernel": "traceKernel<0> (BVH8 closest hit)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "BVH8 closest hit: traceKernel<0> for the camera rays, traceCoopKernel<0> (warp-cooperative triangle stage) from the first bounce on", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
                 # bytes per launch: DRAM bytes per ray of the committed ncu capture (all launches of a step) x this run's average rays per launch
                 "traffic": dram_per_ray * rays_per_launch if dram_per_ray else None,
