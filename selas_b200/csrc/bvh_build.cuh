@@ -283,13 +283,89 @@ SELAS_D float halfArea(float4 lo, float4 hi) {
     return x * y + y * z + z * x;
 }
 
+// ---- cost-optimal collapse (after Ylitie, Karras, Laine 2017, section 3.1) ------------------------------------------------------------
+// C(x, j) = the smallest SAH cost of representing BVH2 subtree x with at most j child slots of its wide parent:
+//   C(x, 1) = min( leaf slot: A(x) * count * cPrim  (count <= 3),   wide node: A(x) * cNode + D(x, 8) )
+//   C(x, j) = min( C(x, j - 1), D(x, j) ),   D(x, j) = min over k of C(left, k) + C(right, j - k)
+// computed bottom-up (the second child to arrive does the parent, as in the refit), with the choices packed into one word per internal
+// node: bit 0 = leaf slot, bits 1-3 = k of D(x, 8), bits 4 + 3 (j - 2) .. = k of D(x, j) for j = 2..7 or 0 when C(x, j - 1) is kept.
+// The greedy collapse (open the largest box until eight slots are taken) dissolved small subtrees into many wide nodes of two to five
+// slots; with the costs in hand the bottom of the tree is made of well-filled nodes: configs[1] 144 k -> 96 k nodes, 12.18 -> 11.85
+// nodes per camera ray; configs[2] 12.29 -> 11.93 per closest-hit ray, 13.14 -> 12.68 per shadow ray, step 16.24 -> 15.90 ms
+// (profiles/r2_ab_collapse*.jsonl).  Used for wide nodes over at most `decisionMaxCount` primitives (default 32768): applied all the way to
+// the root it costs camera rays 8-20 % MORE node visits (13.1-14.8 per ray on configs[1] for any cPrim from 0.2 to 4) -- the cost model
+// knows nothing about front-to-back order, and the uneven children it picks near the root (one huge subtree beside seven small ones)
+// defeat the octant-ordered slots; any-hit rays do not care (4.27-4.35 G/s either way).
+__global__ void bvh2ParentsKernel(int n, const int2* __restrict__ children, uint32_t root, uint32_t* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int2 ch = children[i];
+    parent[ch.x] = (uint32_t)i;
+    parent[ch.y] = (uint32_t)i;
+    if ((uint32_t)i == root) parent[i] = 0xFFFFFFFFu;
+}
+
+__global__ void collapseCostKernel(int n, const int2* __restrict__ children, const uint2* __restrict__ range, const uint32_t* __restrict__ parent,
+                                   const float4* __restrict__ boxLo, const float4* __restrict__ boxHi, float cNode, float cPrim,
+                                   float* __restrict__ cost7, uint32_t* __restrict__ decision, uint32_t* __restrict__ arrivals) {
+    const int j0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j0 >= n || n == 1) return;
+    const uint32_t leafBase = (uint32_t)(n - 1);
+    uint32_t p = parent[leafBase + (uint32_t)j0];
+    while (p != 0xFFFFFFFFu) {
+        __threadfence();
+        if (atomicAdd(arrivals + p, 1u) == 0u) return;
+        const int2 ch = children[p];
+        float cl[8], cr[8];
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t id = (uint32_t)(side ? ch.y : ch.x);
+            float* c = side ? cr : cl;
+            if (id >= leafBase) {
+                const float a = halfArea(boxLo[id], boxHi[id]) * cPrim;
+                for (int k = 1; k <= 7; ++k) c[k] = a;
+            } else {
+                for (int k = 1; k <= 7; ++k) c[k] = __ldcg(cost7 + (size_t)id * 7 + (k - 1));
+            }
+        }
+        float D[9];
+        uint32_t K[9];
+        for (int j = 2; j <= 8; ++j) {
+            float best = SELAS_FLOAT_MAX;
+            uint32_t bk = 1;
+            for (int k = (j - 7 > 1 ? j - 7 : 1); k <= (j - 1 < 7 ? j - 1 : 7); ++k) {
+                const float v = cl[k] + cr[j - k];
+                if (v < best) { best = v; bk = (uint32_t)k; }
+            }
+            D[j] = best;
+            K[j] = bk;
+        }
+        const float area = halfArea(boxLo[p], boxHi[p]);
+        const uint2 r = range[p];
+        const uint32_t count = r.y - r.x + 1u;
+        const float cInt = area * cNode + D[8];
+        const float cLeaf = count <= 3u ? area * (float)count * cPrim : SELAS_FLOAT_MAX;
+        uint32_t word = (cLeaf <= cInt ? 1u : 0u) | (K[8] << 1);
+        float c = fminf(cLeaf, cInt);
+        cost7[(size_t)p * 7] = c;
+        for (int j = 2; j <= 7; ++j) {
+            if (D[j] < c) {
+                c = D[j];
+                word |= K[j] << (4 + 3 * (j - 2));
+            }
+            cost7[(size_t)p * 7 + (j - 1)] = c;
+        }
+        decision[p] = word;
+        p = parent[p];
+    }
+}
+
 __global__ void collapseLevelKernel(const CollapseTask* __restrict__ tasks, uint32_t taskCount, int n,
                                     const int2* __restrict__ children, const uint2* __restrict__ range,
                                     const float4* __restrict__ boxLo, const float4* __restrict__ boxHi,
                                     const BuildTri* __restrict__ tris, const uint32_t* __restrict__ sorted,
                                     float4* __restrict__ outNodes, float4* __restrict__ outTris, uint32_t* __restrict__ nodeCounter,
                                     uint32_t* __restrict__ triCounter, CollapseTask* __restrict__ nextTasks,
-                                    uint32_t* __restrict__ nextCount) {
+                                    uint32_t* __restrict__ nextCount, const uint32_t* __restrict__ decision, uint32_t decisionMaxCount) {
     uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
     if (ti >= taskCount) return;
     CollapseTask task = tasks[ti];
@@ -308,6 +384,37 @@ __global__ void collapseLevelKernel(const CollapseTask* __restrict__ tasks, uint
     int m = 0;
     if (task.bvh2 >= leafBase) {  // single-triangle scene
         member[0] = task.bvh2; cnt[0] = 1; area[0] = 0.f; m = 1;
+    } else if (decision && countOf(task.bvh2) <= decisionMaxCount) {
+        // the slots the cost recurrence chose: (subtree, slots) pairs are refined until every pair holds one slot
+        uint32_t stackId[8];
+        uint32_t stackJ[8];
+        int top = 0;
+        {
+            const int2 ch = children[task.bvh2];
+            const uint32_t k8 = (decision[task.bvh2] >> 1) & 7u;
+            stackId[top] = (uint32_t)ch.y; stackJ[top++] = 8u - k8;
+            stackId[top] = (uint32_t)ch.x; stackJ[top++] = k8;
+        }
+        while (top > 0) {
+            const uint32_t x = stackId[--top];
+            uint32_t j = stackJ[top];
+            if (x >= leafBase || j <= 1u) {
+                member[m] = x; cnt[m] = countOf(x); area[m] = 0.f;
+                ++m;
+                continue;
+            }
+            const uint32_t word = decision[x];
+            uint32_t k = 0;
+            while (j >= 2u && (k = (word >> (4 + 3 * (j - 2u))) & 7u) == 0u) --j;  // C(x, j) == C(x, j - 1): fewer slots do as well
+            if (j <= 1u) {
+                member[m] = x; cnt[m] = countOf(x); area[m] = 0.f;
+                ++m;
+                continue;
+            }
+            const int2 ch = children[x];
+            stackId[top] = (uint32_t)ch.y; stackJ[top++] = j - k;
+            stackId[top] = (uint32_t)ch.x; stackJ[top++] = k;
+        }
     } else {
         int2 ch = children[task.bvh2];
         member[0] = (uint32_t)ch.x; member[1] = (uint32_t)ch.y;

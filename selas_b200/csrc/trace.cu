@@ -261,6 +261,25 @@ static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* 
     }
     out.nodes = d_nodes;
     out.tris = d_outTris;
+    // cost-optimal slot assignment (bvh_build.cuh: collapseCostKernel) for wide nodes over at most SELAS_COLLAPSE_DP_MAX primitives, the
+    // largest-box-first expansion above them (and everywhere with SELAS_COLLAPSE=greedy): see the measurement note at collapseCostKernel
+    static const bool greedyCollapse = getenv("SELAS_COLLAPSE") && !strcmp(getenv("SELAS_COLLAPSE"), "greedy");
+    static const uint32_t collapseDpMax = getenv("SELAS_COLLAPSE_DP_MAX") ? (uint32_t)atoi(getenv("SELAS_COLLAPSE_DP_MAX")) : 32768u;
+    static const float cPrim = getenv("SELAS_COLLAPSE_CPRIM") ? (float)atof(getenv("SELAS_COLLAPSE_CPRIM")) : 0.3f;
+    uint32_t* d_decision = nullptr;
+    if (!greedyCollapse && n > 1) {
+        uint32_t *d_parent2, *d_arrivals2;
+        float* d_cost7;
+        if ((rc = tempAlloc((void**)&d_parent2, sizeof(uint32_t) * (2 * (size_t)n - 1)))) return rc;
+        if ((rc = tempAlloc((void**)&d_arrivals2, sizeof(uint32_t) * (size_t)n))) return rc;
+        if ((rc = tempAlloc((void**)&d_cost7, sizeof(float) * 7 * (size_t)n))) return rc;
+        if ((rc = tempAlloc((void**)&d_decision, sizeof(uint32_t) * (size_t)n))) return rc;
+        SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_arrivals2, 0, sizeof(uint32_t) * (size_t)n, st));
+        bvh2ParentsKernel<<<divUp(n - 1, 256), 256, 0, st>>>((int)n, b2.children, b2.root, d_parent2);
+        collapseCostKernel<<<divUp(n, 256), 256, 0, st>>>((int)n, b2.children, b2.range, d_parent2, b2.boxLo, b2.boxHi, 1.0f, cPrim, d_cost7, d_decision,
+                                                           d_arrivals2);
+        SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+    }
     CollapseTask *d_tasksA, *d_tasksB;
     uint32_t* d_ctr;  // [0]=nodeCounter [1]=triCounter [2..]=per-level next counts
     if ((rc = tempAlloc((void**)&d_tasksA, sizeof(CollapseTask) * maxNodes))) return rc;
@@ -282,7 +301,7 @@ static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* 
             return SELAS_ERR_UNSUPPORTED;
         }
         collapseLevelKernel<<<divUp(taskCount, 128), 128, 0, st>>>(d_tasksA, taskCount, (int)n, b2.children, b2.range, b2.boxLo, b2.boxHi, d_tris,
-                                                                    b2.sorted, d_nodes, d_outTris, d_ctr, d_ctr + 1, d_tasksB, d_ctr + 2 + level);
+                                                                    b2.sorted, d_nodes, d_outTris, d_ctr, d_ctr + 1, d_tasksB, d_ctr + 2 + level, d_decision, collapseDpMax);
         SELAS_CUDA_CHECK(ctx, cudaMemcpyAsync(&taskCount, d_ctr + 2 + level, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
         std::swap(d_tasksA, d_tasksB);
