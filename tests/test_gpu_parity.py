@@ -7,6 +7,8 @@ Tolerances (BASELINE.json north_star):
   (d) images within the reference's own noise floor (here stricter: the GPU and the oracle walk the same RNG streams)
 Integer/index work (hash grid, RNG, event flags, random-number consumption) is bit-exact.
 """
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -530,3 +532,48 @@ def test_texture_filters_vs_oracle(ctx, oracle, comps):
         ctx.texture_filter(levels, capi.FILTER_EWA_LEVEL, st, d0, d1, level=-1)
     with pytest.raises(capi.SelasError):
         ctx.texture_filter(levels, 7, st, d0, d1)
+
+
+def test_cooperative_triangle_kernel_matches_trace_kernel(ctx, tmp_path):
+    """traceCoopKernel (trace_coop.cuh: leaf triangles queued per warp and tested by the whole warp) against traceKernel on the same rays:
+    identical hit records and occlusion bytes (closest hit is a minimum over the same candidates; equal distances go to the lower triangle
+    index in one kernel and to the last one tested in the other, so ids are compared under the tie rule).  The kernel is selected per
+    process (SELAS_TRACE_COOP), hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    data = scenes.disney_heightfield(grid=160)
+    cam = scenes.heightfield_camera(480, 270)
+    rays = scenes.primary_rays(cam, 480, 270)
+    sc = capi.Scene(ctx, data)
+    hits, ng = sc.intersect(rays, want_ng=True)
+    bounce = scenes.cosine_bounce_rays(rays, hits, ng, seed=5)
+    shadow = scenes.shadow_rays_toward(rays, hits, ng, (0.0, 8.0, 0.0))
+    h2 = sc.intersect(bounce)
+    occ = sc.occluded(shadow)
+    sc.close()
+    np.savez(tmp_path / "in.npz", rays=rays, bounce=bounce, shadow=shadow)
+    script = tmp_path / "coop.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {str(Path(__file__).resolve().parent.parent)!r})\n"
+        "from selas_b200 import capi, scenes\n"
+        f"z = np.load({str(tmp_path / 'in.npz')!r})\n"
+        "ctx = capi.Context(0)\n"
+        "sc = capi.Scene(ctx, scenes.disney_heightfield(grid=160))\n"
+        "np.savez(sys.argv[1], h1=sc.intersect(z['rays'].view(capi.RAY_DTYPE)), h2=sc.intersect(z['bounce'].view(capi.RAY_DTYPE)),\n"
+        "         occ=sc.occluded(z['shadow'].view(capi.RAY_DTYPE)))\n")
+    env = dict(os.environ, SELAS_TRACE_COOP="1")
+    subprocess.run([sys.executable, str(script), str(tmp_path / "out.npz")], check=True, env=env, timeout=600)
+    z = np.load(tmp_path / "out.npz")
+    for got, want, name in ((z["h1"], hits, "camera rays"), (z["h2"], h2, "bounce rays")):
+        got = got.view(capi.HIT_DTYPE)
+        same = (got["primID"] == want["primID"]) & (got["geomID"] == want["geomID"])
+        tie = np.isclose(got["t"], want["t"], rtol=1e-6, atol=0)
+        assert (same | tie).all(), (name, int((~(same | tie)).sum()))
+        assert same.mean() > 0.9999, (name, same.mean())
+        np.testing.assert_array_equal(got["t"][same], want["t"][same])
+        np.testing.assert_array_equal(got["u"][same], want["u"][same])
+    np.testing.assert_array_equal(z["occ"], occ)
+    assert 0.02 < occ.mean() < 0.98
