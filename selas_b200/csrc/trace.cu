@@ -721,7 +721,7 @@ static bool traceCoopFor(int coop) { return coop < 0 ? traceCoopEnabled() : coop
         } else if (inst__ && top__) SELAS_TRACE_GO2(MODE, COUNT, true, true, false, __VA_ARGS__);                  \
         else if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, false, __VA_ARGS__);                            \
         else if (top__) SELAS_TRACE_GO2(MODE, COUNT, false, true, false, __VA_ARGS__);                             \
-        else if (coop__) {                                                                                          \
+        else if (coop__ && scene->gpu.triCount < (1u << 27)) { /* queue entries hold lane | triangle << 5 */       \
             TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT>);                                     \
             traceCoopKernel<MODE, COUNT><<<tl.grid, SELAS_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);                \
         } else SELAS_TRACE_GO2(MODE, COUNT, false, false, false, __VA_ARGS__);                                     \

@@ -10,6 +10,11 @@
 // reruns are bit-identical although the queue order is not), and tmax is only an optimisation for the slab test, so letting it lag a
 // few node visits is safe.
 //
+// Queue layout, measured: one 32-bit (lane, triangle) pair per slot, written by the lane that found it (a short loop at 3-4 lanes, 13 %
+// of the kernel's instructions).  Queueing {triangle base, hit mask, lane} once per lane and node instead and expanding to pairs inside
+// the flush (scan of the counts + __reduce_or of the entry heads per window of 32 pairs) removes that loop but makes every flush round
+// dearer: 16.00-16.05 ms per step against 15.88 (profiles/r2_ab_trace_coop_group_queue.jsonl).  Pairs stay.
+//
 // Same interface, launch shape and ray pulling (ballot-ranked refill) as traceKernel; flattened trees without curves only.
 #pragma once
 #include "trace.cuh"
