@@ -329,6 +329,16 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
     SELAS_TRY(sceneUpload(scene, &g.meshes, meshes.data(), meshes.size()));
     SELAS_TRY(sceneUpload(scene, &g.instances, inst.data(), inst.size()));
     SELAS_TRY(sceneUpload(scene, &g.materials, d->materials, d->materialCount));
+    {
+        void* p = nullptr;
+        if (cudaMalloc(&p, sizeof(float4) * (size_t)d->materialCount + 16) != cudaSuccess) {
+            setError(ctx, "cudaMalloc failed for the material table");
+            return SELAS_ERR_MEMORY;
+        }
+        scene->allocations.push_back(p);
+        g.materialBasePow = (const float4*)p;
+        SELAS_TRY(launchMaterialBasePow(ctx, g.materials, d->materialCount, (float4*)p));
+    }
     SELAS_TRY(sceneUpload(scene, &g.lights, d->lights, d->lightCount));
     SELAS_TRY(sceneUpload(scene, &g.lightSets, d->lightSets, d->lightSetCount));
     g.meshCount = geometryCount;  // meshes, then curve geometries

@@ -73,6 +73,9 @@ struct SceneGpu {
     const MeshGpu* meshes;
     const InstanceGpu* instances;
     const SelasMaterial* materials;
+    // pow(material baseColor, 2.2) (SurfaceParameters.cpp:204,:211-212) of every material, made once at upload by the same powf the surface
+    // stage would run per hit (materialBasePowKernel, shade.cu); used for meshes without a texture
+    const float4* materialBasePow;
     const SelasLight* lights;
     const SelasLightSetRange* lightSets;
     uint32_t meshCount, instanceCount, materialCount, lightCount, lightSetCount;
@@ -168,6 +171,7 @@ int collectRenderStats(SelasScene* scene, SelasRenderStats* out);
 int launchScale(SelasContext* ctx, float* d, size_t n, float s, cudaStream_t stream);
 int launchIblLookup(SelasScene* scene, size_t n, const float* d_wi3, float* d_rgb3, float* d_pdf, float* d_miss3);
 int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp3, uint32_t* d_xy2);
+int launchMaterialBasePow(SelasContext* ctx, const SelasMaterial* d_materials, uint32_t count, float4* d_out);
 int launchTextureSample(SelasContext* ctx, const TextureGpu& tex, size_t n, const float* d_uv2, int sRGB, float* d_rgb3);
 int launchTextureFilter(SelasContext* ctx, const SelasTextureMipsDesc& desc, const void* d_texels, const float* ewaLut128, int filter, int level, size_t n,
                         const float* d_st2, const float* d_dst0, const float* d_dst1, float* d_out);

@@ -157,6 +157,13 @@ __global__ void textureSampleKernel(TextureGpu tex, size_t n, const float* __res
     store3(rgb3 + 3 * i, sampleTextureFloat3(tex, uv2[2 * i], uv2[2 * i + 1], sRGB != 0));
 }
 
+__global__ void materialBasePowKernel(const SelasMaterial* __restrict__ materials, uint32_t n, float4* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 base = v3(materials[i].baseColor);
+    out[i] = make_float4(powf(base.x, 2.2f), powf(base.y, 2.2f), powf(base.z, 2.2f), 0.f);
+}
+
 __global__ void scaleKernel(float* __restrict__ d, size_t n, float s) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] *= s;
@@ -221,6 +228,12 @@ int launchIblSample(SelasScene* scene, size_t n, const float* d_u2, float* d_tpp
     if (!n) return SELAS_OK;
     iblSampleKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu.ibl, n, d_u2, d_tpp3, d_xy2);
     SELAS_CUDA_CHECK(scene->ctx, cudaGetLastError());
+    return SELAS_OK;
+}
+int launchMaterialBasePow(SelasContext* ctx, const SelasMaterial* d_materials, uint32_t count, float4* d_out) {
+    if (!count) return SELAS_OK;
+    materialBasePowKernel<<<divUp(count, 128), 128, 0, ctx->stream>>>(d_materials, count, d_out);
+    SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
 int launchTextureSample(SelasContext* ctx, const TextureGpu& tex, size_t n, const float* d_uv2, int sRGB, float* d_rgb3) {
