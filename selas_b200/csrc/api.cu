@@ -266,6 +266,7 @@ int selas_cuda_scene_create(SelasContext* ctx, const SelasSceneDesc* d, SelasSce
         if (md.uvs) SELAS_TRY(sceneUpload(scene, &g.uvs, md.uvs, 2 * (size_t)md.vertexCount));
         g.ptex = md.ptex ? ptexDevicePointer((SelasPtex*)md.ptex) : nullptr;
         if (g.ptex) scene->usesPtex = true;
+        if (g.ptex && ptexMixedResolutions((SelasPtex*)md.ptex)) scene->ptexMixedRes = true;
         if (md.baseColorTexture)
             g.texture = d_textures + (std::find(texDescs.begin(), texDescs.end(), md.baseColorTexture) - texDescs.begin());
         g.faceCount = md.faceCount;

@@ -112,6 +112,7 @@ struct SelasScene {
     std::vector<void*> allocations;  // everything cudaMalloc'ed for this scene
     SelasBvhStats stats{};
     bool usesPtex = false;  // any mesh carries a Ptex texture: selects the shade kernel built with the lookup
+    bool ptexMixedRes = false;  // one of them has faces of different resolutions: the Ptex stage runs the instantiation with the reduction logic
     float boundsCenter[3] = {0.f, 0.f, 0.f};  // centre of the scene's box (ray binning quadrants)
     uint32_t topNodeCount = 0;  // leading BVH8 nodes (whole levels) the trace kernels stage in shared memory
     // SELAS_SCENE_INSTANCE_IDS: reported (instID0, instID1, geomID) -> flat instance index, for hits handed back to selas_cuda_surface_params
@@ -194,5 +195,6 @@ void freeVcm(SelasScene* scene);
 
 // ptex.cu
 const void* ptexDevicePointer(SelasPtex* tex);
+bool ptexMixedResolutions(SelasPtex* tex);  // some face differs in resolution from the others: the lookup kernels need the reduction logic
 
 }  // namespace selas

@@ -42,6 +42,7 @@ struct SelasPtex {
 namespace selas {
 
 const void* ptexDevicePointer(SelasPtex* tex) { return tex ? tex->d_self : nullptr; }
+bool ptexMixedResolutions(SelasPtex* tex) { return tex && tex->host.mixedRes != 0; }
 
 namespace {
 
@@ -360,9 +361,10 @@ struct Loader {
     }
 };
 
+template <bool MIXED>
 __global__ void __launch_bounds__(128, SELAS_PTEX_MIN_CTAS) ptexEvalKernel(const PtexGpu* __restrict__ tex, size_t n, const int32_t* __restrict__ faceid,
                                                       const float* __restrict__ u, const float* __restrict__ v, float* __restrict__ rgb) {
-    ptexTileEval<128, 8>(
+    ptexTileEval<128, 8, MIXED>(
         n,
         [&](size_t i, const PtexGpu*& t, int& f, float& uu, float& vv) {
             t = tex;
@@ -556,7 +558,7 @@ int selas_cuda_ptex_load_memory(SelasContext* ctx, const void* bytes, size_t siz
     g.uMode = L.ext.ubordermode;
     g.vMode = L.ext.vbordermode;
     g.edgeFilterMode = L.ext.edgefiltermode;
-    g.pad = 0;
+    g.mixedRes = uniform ? 0 : 1;
     const PtexGpu* d_self = nullptr;
     if ((rc = uploadVec(tex, &d_self, &g, sizeof(PtexGpu)))) {
         selas_cuda_ptex_destroy(tex);
@@ -606,7 +608,8 @@ int selas_cuda_ptex_eval_device(SelasPtex* tex, size_t n, const int32_t* d_facei
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     unsigned grid = (unsigned)std::min<size_t>((n + 1023) / 1024, (size_t)ctx->smCount * 8);
-    ptexEvalKernel<<<grid, 128, 0, st>>>(tex->d_self, n, d_faceid, d_u, d_v, d_rgb3);
+    if (tex->host.mixedRes) ptexEvalKernel<true><<<grid, 128, 0, st>>>(tex->d_self, n, d_faceid, d_u, d_v, d_rgb3);
+    else ptexEvalKernel<false><<<grid, 128, 0, st>>>(tex->d_self, n, d_faceid, d_u, d_v, d_rgb3);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }

@@ -44,7 +44,7 @@ struct PtexGpu {
     int pixelSize;   // bytes
     int uMode, vMode;  // BorderMode: 0 clamp, 1 black, 2 periodic
     int edgeFilterMode;
-    int pad;
+    int mixedRes;  // 0: every face has the same square resolution (no kernel ever meets another resolution)
 };
 
 enum { kPtexFlagConstant = 1, kPtexFlagNbConstant = 4, kPtexFlagSubface = 8 };
@@ -822,7 +822,7 @@ SELAS_D void ptexDeriveAxis(int k0, int kn, const float* kk, int res, bool lowSi
     }
 }
 
-template <int DT, int NT>
+template <int DT, int NT, bool MIXED>
 SELAS_D bool ptexEvalFastT(const PtexGpu& tx, const PtexFace& f, int faceid, float u, float v, int nchan, float oneValue, float* rgb) {
     PtexPiece k;
     bool ok = !(f.isSubface() || f.isConstant() || f.ulog2 < 3 || f.vlog2 < 3);
@@ -889,10 +889,11 @@ SELAS_D bool ptexEvalFastT(const PtexGpu& tx, const PtexFace& f, int faceid, flo
                 int ul = f.ulog2, vl = f.vlog2;
                 ptexRotatePiece(p, rot, ul, vl);
                 ok = !tf.isSubface();  // else: the subface transitions of applyAcrossEdge / applyToCornerFace
-#if !SELAS_PTEX_FAST_MIXED
-                ok = ok && ul == tf.ulog2 && vl == tf.vlog2;  // round-1 behaviour (A/B): other resolutions take the general path
-#endif
-                if (ok) {
+                // !MIXED: the instantiation for textures whose faces all share one resolution -- without the reduction code the kernel keeps
+                // its registers (with it, uniform textures lose 6-10 %: profiles/r2_ptex_classes_mixed.json); a mismatch cannot occur there
+                if (!MIXED || !SELAS_PTEX_FAST_MIXED) ok = ok && ul == tf.ulog2 && vl == tf.vlog2;
+                if (ok && !MIXED) ptexApplyPiece<DT, NT>(tx, tf.isConstant(), tfid, tx.texels + (size_t)tf.dataOffset16 * 16, ul, p, nchan, result);
+                if (ok && MIXED) {
                     // PtexSeparableFilter::apply (:346-401): a coarser face gets the piece reduced to its resolution, a finer one
                     // is read through its reduced copy at the piece's resolution
 #pragma unroll 1
@@ -923,20 +924,21 @@ SELAS_D bool ptexEvalFastT(const PtexGpu& tx, const PtexFace& f, int faceid, flo
     return ok;
 }
 
+template <bool MIXED>
 SELAS_D bool ptexEvalFast(const PtexGpu& tx, const PtexFace& f, int faceid, float u, float v, int nchan, float oneValue, float* rgb) {
     if (tx.nchan == 3) {  // RGB texture, all three channels evaluated
         switch (tx.dataType) {
-            case 0: return ptexEvalFastT<0, 3>(tx, f, faceid, u, v, nchan, oneValue, rgb);
-            case 1: return ptexEvalFastT<1, 3>(tx, f, faceid, u, v, nchan, oneValue, rgb);
-            case 2: return ptexEvalFastT<2, 3>(tx, f, faceid, u, v, nchan, oneValue, rgb);
-            default: return ptexEvalFastT<3, 3>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+            case 0: return ptexEvalFastT<0, 3, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+            case 1: return ptexEvalFastT<1, 3, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+            case 2: return ptexEvalFastT<2, 3, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+            default: return ptexEvalFastT<3, 3, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
         }
     }
     switch (tx.dataType) {
-        case 0: return ptexEvalFastT<0, 0>(tx, f, faceid, u, v, nchan, oneValue, rgb);
-        case 1: return ptexEvalFastT<1, 0>(tx, f, faceid, u, v, nchan, oneValue, rgb);
-        case 2: return ptexEvalFastT<2, 0>(tx, f, faceid, u, v, nchan, oneValue, rgb);
-        default: return ptexEvalFastT<3, 0>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+        case 0: return ptexEvalFastT<0, 0, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+        case 1: return ptexEvalFastT<1, 0, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+        case 2: return ptexEvalFastT<2, 0, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
+        default: return ptexEvalFastT<3, 0, MIXED>(tx, f, faceid, u, v, nchan, oneValue, rgb);
     }
 }
 
@@ -1027,7 +1029,7 @@ static __device__ __noinline__ void ptexGeneral(const PtexGpu* texPtr, int facei
 // general path runs in dense warps and its latency is amortised over the whole tile instead of being paid once per warp.
 //   fetch(i, tex, faceid, u, v) -> bool   describes lookup i (false: nothing to do for i)
 //   store(i, rgb)                         receives the result
-template <int BLOCK, int PER_THREAD, typename Fetch, typename Store>
+template <int BLOCK, int PER_THREAD, bool MIXED, typename Fetch, typename Store>
 SELAS_D void ptexTileEval(size_t n, Fetch fetch, Store store) {
     struct Item {
         const PtexGpu* tex;
@@ -1056,7 +1058,7 @@ SELAS_D void ptexTileEval(size_t n, Fetch fetch, Store store) {
                 PtexFace f;
                 if (ptexPrologue(tx, faceid, u, v, f, rgb)) {
                     const float oneValue = tx.dataType == 0 ? 255.f : (tx.dataType == 1 ? 65535.f : 1.f);
-                    if (!ptexEvalFast(tx, f, faceid, u, v, tx.nchan < 3 ? tx.nchan : 3, oneValue, rgb)) {
+                    if (!ptexEvalFast<MIXED>(tx, f, faceid, u, v, tx.nchan < 3 ? tx.nchan : 3, oneValue, rgb)) {
                         int slot = atomicAdd(&failCount, 1);
                         failItem[slot] = Item{texPtr, (uint32_t)(i - base), faceid, u, v};
                         done = false;

@@ -208,7 +208,8 @@ int launchSurfaceParams(SelasScene* scene, size_t n, const SelasRay* d_rays, con
     if (scene->usesPtex) {
         SELAS_CUDA_CHECK(scene->ctx, cudaMalloc((void**)&d_rgb, sizeof(float) * 3 * n));
         unsigned grid = (unsigned)std::min<size_t>((n + 1023) / 1024, (size_t)scene->ctx->smCount * 8);
-        ptexStageKernel<<<grid, 128, 0, scene->ctx->stream>>>(scene->gpu, (uint32_t)n, d_hits, d_rgb);
+        if (scene->ptexMixedRes) ptexStageKernel<true><<<grid, 128, 0, scene->ctx->stream>>>(scene->gpu, (uint32_t)n, d_hits, d_rgb);
+        else ptexStageKernel<false><<<grid, 128, 0, scene->ctx->stream>>>(scene->gpu, (uint32_t)n, d_hits, d_rgb);
     }
     surfaceParamsKernel<<<divUp(n, 128), 128, 0, scene->ctx->stream>>>(scene->gpu, n, d_rays, d_hits, d_rgb, d_out);
     if (d_rgb) {
@@ -1073,7 +1074,8 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 launches += 3;
             }
             if (scene->usesPtex) {  // Ptex stage: base-colour lookups for the whole hit queue
-                ptexStageKernel<<<ptexGrid, 128, 0, stream>>>(scene->gpu, count, w->hits, w->ptexRgb, ctr);
+                if (scene->ptexMixedRes) ptexStageKernel<true><<<ptexGrid, 128, 0, stream>>>(scene->gpu, count, w->hits, w->ptexRgb, ctr);
+                else ptexStageKernel<false><<<ptexGrid, 128, 0, stream>>>(scene->gpu, count, w->hits, w->ptexRgb, ctr);
                 ++launches;
             }
             // one-shot grid when an earlier pass of this shape told how long this bounce's queue gets (3 % + 8 CTAs of slack; what a low

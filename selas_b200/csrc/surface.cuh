@@ -189,10 +189,11 @@ SELAS_D void surfaceFromHit(const SceneGpu& sc, V3 o, V3 d, float t, float u, fl
 
 // Ptex stage of the wavefront: base-colour lookups for every hit of the queue whose material uses Ptex
 // (SurfaceParameters.cpp:196-208), written as 3 floats per path for the shade kernel.
+template <bool MIXED>
 static __global__ void __launch_bounds__(128, SELAS_PTEX_MIN_CTAS) ptexStageKernel(SceneGpu sc, uint32_t n, const SelasHit* __restrict__ hits, float* __restrict__ rgbOut,
                                                                                   const uint32_t* __restrict__ nPtr = nullptr) {
     if (nPtr) n = min(n, *nPtr);  // wavefront queues: the length lives in device memory, n is the launch's upper bound
-    ptexTileEval<128, 8>(
+    ptexTileEval<128, 8, MIXED>(
         n,
         [&](size_t i, const PtexGpu*& t, int& f, float& uu, float& vv) {
             const uint4* hp = reinterpret_cast<const uint4*>(hits + i);

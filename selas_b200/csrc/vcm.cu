@@ -1099,7 +1099,8 @@ int lightPass(SelasScene* scene, const SelasCamera& cam, const VcmParams& prm, f
         st.closestRays += n;
         if (scene->usesPtex) {
             unsigned grid = (unsigned)std::min<uint32_t>(divUp(n, 1024), (uint32_t)ctx->smCount * 8);
-            ptexStageKernel<<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
+            if (scene->ptexMixedRes) ptexStageKernel<true><<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
+            else ptexStageKernel<false><<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
             ++st.kernelLaunches;
         }
         // light sub-paths leave the environment in random directions: a warp holds misses, diffuse and glass hits side by side (7.5 of
@@ -1216,7 +1217,8 @@ int renderVcm(SelasScene* scene, const SelasCamera& cam, const SelasVcmSettings&
             const float* ptexRgb = nullptr;
             if (scene->usesPtex) {
                 unsigned grid = (unsigned)std::min<uint32_t>(divUp(n, 1024), (uint32_t)ctx->smCount * 8);
-                ptexStageKernel<<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
+                if (scene->ptexMixedRes) ptexStageKernel<true><<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
+                else ptexStageKernel<false><<<grid, 128, 0, stream>>>(scene->gpu, n, w->hits, w->ptexRgb);
                 ptexRgb = w->ptexRgb;
                 ++st.kernelLaunches;
             }
