@@ -698,13 +698,20 @@ static TraceLaunch traceLaunch(const SelasScene* scene, K kernel) {
     return l;
 }
 // SELAS_TRACE_COOP=1: flattened trees without curves go through the kernel with the warp-cooperative triangle stage (trace_coop.cuh)
-static bool traceCoopEnabled() {
-    static const bool on = getenv("SELAS_TRACE_COOP") && atoi(getenv("SELAS_TRACE_COOP")) != 0;
-    return on;
+// SELAS_TRACE_COOP: 1 / 0 force it on / off for every launch; unset: the public intersect / occluded calls use traceKernel (camera rays
+// of triangle scenes are coherent) except on scenes with curve geometry, where the cooperative kernel wins for every kind of ray (a curve
+// part costs three times a triangle: 200 000 blades, camera rays 459 -> 709 M/s, shadow rays 1.64 -> 2.71 G/s, profiles/r2_curves.txt).
+static int traceCoopEnv() {
+    static const int v = getenv("SELAS_TRACE_COOP") ? (atoi(getenv("SELAS_TRACE_COOP")) != 0 ? 1 : 0) : -1;
+    return v;
 }
-// the wavefront asks per launch (coop: -1 = the process default above, 0 / 1 = no / yes): primary rays are coherent and run better
+static bool traceCoopEnabled(const SelasScene* scene) { return traceCoopEnv() >= 0 ? traceCoopEnv() == 1 : scene->gpu.curvePool != nullptr; }
+// the wavefront asks per launch (coop: -1 = the default above, 0 / 1 = no / yes): primary rays are coherent and run better
 // through traceKernel, everything after the first bounce and the shadow rays through traceCoopKernel (measurements in trace_coop.cuh)
-static bool traceCoopFor(int coop) { return coop < 0 ? traceCoopEnabled() : coop != 0; }
+static bool traceCoopFor(int coop, const SelasScene* scene) {
+    if (traceCoopEnv() >= 0) return traceCoopEnv() == 1;
+    return coop < 0 ? traceCoopEnabled(scene) : (coop != 0 || scene->gpu.curvePool != nullptr);
+}
 // kernel variant by scene: two-level form only when the scene was built that way (the flattened form keeps its register budget), staged
 // top levels only when asked for
 #define SELAS_TRACE_GO2(MODE, COUNT, INST, TOP, CURVES, ...)                                                       \
@@ -717,7 +724,10 @@ static bool traceCoopFor(int coop) { return coop < 0 ? traceCoopEnabled() : coop
         const bool inst__ = scene->gpu.traceInstances != nullptr, top__ = scene->topNodeCount != 0;                \
         if (scene->gpu.curvePool) { /* scenes with curve geometry: the variant that carries the curve leaf test */ \
             if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, true, __VA_ARGS__);                              \
-            else SELAS_TRACE_GO2(MODE, COUNT, false, false, true, __VA_ARGS__);                                    \
+            else if (coop__ && scene->gpu.triCount < (1u << 27)) {                                                 \
+                TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT, true>);                           \
+                traceCoopKernel<MODE, COUNT, true><<<tl.grid, SELAS_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);      \
+            } else SELAS_TRACE_GO2(MODE, COUNT, false, false, true, __VA_ARGS__);                                  \
         } else if (inst__ && top__) SELAS_TRACE_GO2(MODE, COUNT, true, true, false, __VA_ARGS__);                  \
         else if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, false, __VA_ARGS__);                            \
         else if (top__) SELAS_TRACE_GO2(MODE, COUNT, false, true, false, __VA_ARGS__);                             \
@@ -732,7 +742,7 @@ int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, Selas
     if (n == 0) return SELAS_OK;
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
-    const bool coop__ = traceCoopEnabled();
+    const bool coop__ = traceCoopEnabled(scene);
     if (d_counts)
         SELAS_TRACE_GO(0, true, bvhOf(scene, true), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
@@ -746,7 +756,7 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
     if (n == 0) return SELAS_OK;
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
-    const bool coop__ = traceCoopEnabled();
+    const bool coop__ = traceCoopEnabled(scene);
     if (d_counts)
         SELAS_TRACE_GO(1, true, bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
@@ -760,7 +770,7 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
                             uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order, int coop) {
     SelasContext* ctx = scene->ctx;
-    const bool coop__ = traceCoopFor(coop);
+    const bool coop__ = traceCoopFor(coop, scene);
     if (d_totals)
         SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, d_totals, d_order);
     else
@@ -772,7 +782,7 @@ int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t max
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
                            float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop) {
     SelasContext* ctx = scene->ctx;
-    const bool coop__ = traceCoopFor(coop);
+    const bool coop__ = traceCoopFor(coop, scene);
     if (d_totals)
         SELAS_TRACE_GO(2, true, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, d_totals);
     else

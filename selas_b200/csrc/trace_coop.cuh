@@ -15,7 +15,8 @@
 // the flush (scan of the counts + __reduce_or of the entry heads per window of 32 pairs) removes that loop but makes every flush round
 // dearer: 16.00-16.05 ms per step against 15.88 (profiles/r2_ab_trace_coop_group_queue.jsonl).  Pairs stay.
 //
-// Same interface, launch shape and ray pulling (ballot-ranked refill) as traceKernel; flattened trees without curves only.
+// Same interface, launch shape and ray pulling (ballot-ranked refill) as traceKernel; flattened trees only.  CURVES: leaves may be
+// parts of round B-spline curves (curve.cuh); the element code and normal of a curve hit travel back beside (u, v).
 #pragma once
 #include "trace.cuh"
 
@@ -39,8 +40,8 @@ SELAS_D uint32_t orderedFloatBits(float f) {
 }
 SELAS_D float fromOrderedFloatBits(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(SELAS_TRACE_THREADS, COUNT ? 6 : SELAS_TRACE_CTAS_PER_SM)
+template <int MODE, bool COUNT, bool CURVES = false>
+__global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : SELAS_TRACE_CTAS_PER_SM)
     traceCoopKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n, const uint32_t* __restrict__ nPtr, SelasHit* __restrict__ hits,
                     uint8_t* __restrict__ occluded, float4* __restrict__ ng, uint32_t* __restrict__ counts, const float4* __restrict__ payload,
                     float* __restrict__ film, uint32_t* __restrict__ nextRay, unsigned long long* __restrict__ totals,
@@ -52,11 +53,13 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, COUNT ? 6 : SELAS_TRACE_C
     __shared__ uint32_t sTail[WARPS];                            // queue length
     __shared__ float2 sUv[WARPS][32];                            // per source lane: (u, v) of its best hit
     __shared__ unsigned long long sBest[WARPS][32];              // per source lane: ordered(t) << 32 | triangle
+    __shared__ float4 sCurve[CURVES ? WARPS : 1][32];            // per source lane: curve normal and element code of its best hit
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t ltMask = (1u << lane) - 1u;
     uint32_t* const q = sQueue[warp];
     float2* const quv = sUv[warp];
     unsigned long long* const best = sBest[warp];
+    float4* const qcurve = sCurve[CURVES ? warp : 0];
     uint32_t* const tail = &sTail[warp];
     if (lane == 0) *tail = 0u;
     __syncwarp();
@@ -95,17 +98,31 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, COUNT ? 6 : SELAS_TRACE_C
             bool hit = false;
             unsigned long long key = 0ull;
             float t, u, v;
+            float4 curveOut = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 const float4* tp = bvh.tris + (size_t)(entry >> 5) * 3;
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                hit = intersectTri(a, b, c, so, sd, stn, stm, t, u, v);
+                if (CURVES && (__float_as_uint(c.w) & kLeafCurveFlag)) {
+                    const float4* cp = bvh.curves + 4 * (size_t)__float_as_uint(a.x);
+                    CurveHit ch;
+                    hit = intersectCurve(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2), __ldg(cp + 3), __float_as_uint(a.y), so, sd, stn, stm, ch);
+                    if (hit) {
+                        t = ch.t; u = ch.u; v = 0.f;
+                        curveOut = make_float4(ch.ng.x, ch.ng.y, ch.ng.z, __uint_as_float(ch.element));
+                    }
+                } else {
+                    hit = intersectTri(a, b, c, so, sd, stn, stm, t, u, v);
+                }
                 if (hit) {
                     key = ((unsigned long long)orderedFloatBits(t) << 32) | (unsigned long long)(entry >> 5);
                     atomicMin(&best[src], key);
                 }
             }
             __syncwarp();
-            if (hit && best[src] == key) quv[src] = make_float2(u, v);  // the best so far (a later round's better hit overwrites it)
+            if (hit && best[src] == key) {  // the best so far (a later round's better hit overwrites it)
+                quv[src] = make_float2(u, v);
+                if (CURVES) qcurve[src] = curveOut;
+            }
             __syncwarp();
         }
         if (outstanding) {
@@ -116,6 +133,11 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, COUNT ? 6 : SELAS_TRACE_C
                 const float2 uv = quv[lane];
                 tmax = t;
                 res.t = t; res.u = uv.x; res.v = uv.y; res.tri = tri;
+                if (CURVES) {
+                    const float4 cv = qcurve[lane];
+                    res.ng = v3(cv.x, cv.y, cv.z);
+                    res.element = __float_as_uint(cv.w);
+                }
                 if (ANY) done = true;
             }
             outstanding = false;
@@ -188,7 +210,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, COUNT ? 6 : SELAS_TRACE_C
                 // more leaf hits in one step than the queue holds (up to 24 per lane): every lane tests its own, as traceKernel does
                 if (cnt) {
                     uint32_t dummy = 0;
-                    if (testLeafGroup<ANY, false, false>(bvh, make_uint2(leafBase, leafMask), o, d, tnear, tmax, res, dummy)) done = true;
+                    if (testLeafGroup<ANY, false, CURVES>(bvh, make_uint2(leafBase, leafMask), o, d, tnear, tmax, res, dummy)) done = true;
                 }
             } else {
                 if (cnt) {

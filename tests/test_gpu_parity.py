@@ -534,8 +534,13 @@ def test_texture_filters_vs_oracle(ctx, oracle, comps):
         ctx.texture_filter(levels, 7, st, d0, d1)
 
 
-def test_cooperative_triangle_kernel_matches_trace_kernel(ctx, tmp_path):
-    """traceCoopKernel (trace_coop.cuh: leaf triangles queued per warp and tested by the whole warp) against traceKernel on the same rays:
+@pytest.mark.parametrize("env", [{"SELAS_TRACE_COOP": "1"}, {"SELAS_COLLAPSE": "greedy"}, {"SELAS_BVH_BUILD": "lbvh", "SELAS_TRACE_COOP": "1"}],
+                         ids=["cooperative-kernel", "greedy-collapse", "lbvh-tree-cooperative-kernel"])
+def test_kernel_and_builder_variants_return_the_same_hits(ctx, tmp_path, env):
+    """The process-wide variants against the defaults on the same rays: the cooperative triangle stage for the public calls
+    (SELAS_TRACE_COOP), the greedy BVH2 -> BVH8 collapse instead of the cost recurrence (SELAS_COLLAPSE), the Morton radix tree instead of
+    the binned-SAH tree (SELAS_BVH_BUILD).  A different tree or test order must not change what is hit.
+    traceCoopKernel (trace_coop.cuh: leaf triangles queued per warp and tested by the whole warp) against traceKernel on the same rays:
     identical hit records and occlusion bytes (closest hit is a minimum over the same candidates; equal distances go to the lower triangle
     index in one kernel and to the last one tested in the other, so ids are compared under the tie rule).  The kernel is selected per
     process (SELAS_TRACE_COOP), hence the subprocess."""
@@ -564,7 +569,7 @@ def test_cooperative_triangle_kernel_matches_trace_kernel(ctx, tmp_path):
         "sc = capi.Scene(ctx, scenes.disney_heightfield(grid=160))\n"
         "np.savez(sys.argv[1], h1=sc.intersect(z['rays'].view(capi.RAY_DTYPE)), h2=sc.intersect(z['bounce'].view(capi.RAY_DTYPE)),\n"
         "         occ=sc.occluded(z['shadow'].view(capi.RAY_DTYPE)))\n")
-    env = dict(os.environ, SELAS_TRACE_COOP="1")
+    env = dict(os.environ, **env)
     subprocess.run([sys.executable, str(script), str(tmp_path / "out.npz")], check=True, env=env, timeout=600)
     z = np.load(tmp_path / "out.npz")
     for got, want, name in ((z["h1"], hits, "camera rays"), (z["h2"], h2, "bounce rays")):
