@@ -719,22 +719,27 @@ static bool traceCoopFor(int coop, const SelasScene* scene) {
         TraceLaunch tl = traceLaunch(scene, traceKernel<MODE, COUNT, INST, TOP, CURVES>);                          \
         traceKernel<MODE, COUNT, INST, TOP, CURVES><<<tl.grid, SELAS_TRACE_THREADS, tl.smem, stream>>>(__VA_ARGS__); \
     } while (0)
+#define SELAS_TRACE_COOP_GO(MODE, COUNT, CURVES, INST, ...)                                                          \
+    do {                                                                                                           \
+        TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT, CURVES, INST>);                           \
+        traceCoopKernel<MODE, COUNT, CURVES, INST><<<tl.grid, SELAS_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);      \
+    } while (0)
 #define SELAS_TRACE_GO(MODE, COUNT, ...)                                                                            \
     do {                                                                                                           \
         const bool inst__ = scene->gpu.traceInstances != nullptr, top__ = scene->topNodeCount != 0;                \
-        if (scene->gpu.curvePool) { /* scenes with curve geometry: the variant that carries the curve leaf test */ \
+        const bool curves__ = scene->gpu.curvePool != nullptr;                                                     \
+        if (coop__ && !top__ && scene->gpu.triCount < (1u << 27)) { /* queue entries hold lane | triangle << 5 */  \
+            if (curves__ && inst__) SELAS_TRACE_COOP_GO(MODE, COUNT, true, true, __VA_ARGS__);                     \
+            else if (curves__) SELAS_TRACE_COOP_GO(MODE, COUNT, true, false, __VA_ARGS__);                         \
+            else if (inst__) SELAS_TRACE_COOP_GO(MODE, COUNT, false, true, __VA_ARGS__);                           \
+            else SELAS_TRACE_COOP_GO(MODE, COUNT, false, false, __VA_ARGS__);                                      \
+        } else if (curves__) { /* scenes with curve geometry: the variant that carries the curve leaf test */      \
             if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, true, __VA_ARGS__);                              \
-            else if (coop__ && scene->gpu.triCount < (1u << 27)) {                                                 \
-                TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT, true>);                           \
-                traceCoopKernel<MODE, COUNT, true><<<tl.grid, SELAS_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);      \
-            } else SELAS_TRACE_GO2(MODE, COUNT, false, false, true, __VA_ARGS__);                                  \
+            else SELAS_TRACE_GO2(MODE, COUNT, false, false, true, __VA_ARGS__);                                    \
         } else if (inst__ && top__) SELAS_TRACE_GO2(MODE, COUNT, true, true, false, __VA_ARGS__);                  \
         else if (inst__) SELAS_TRACE_GO2(MODE, COUNT, true, false, false, __VA_ARGS__);                            \
         else if (top__) SELAS_TRACE_GO2(MODE, COUNT, false, true, false, __VA_ARGS__);                             \
-        else if (coop__ && scene->gpu.triCount < (1u << 27)) { /* queue entries hold lane | triangle << 5 */       \
-            TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT>);                                     \
-            traceCoopKernel<MODE, COUNT><<<tl.grid, SELAS_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);                \
-        } else SELAS_TRACE_GO2(MODE, COUNT, false, false, false, __VA_ARGS__);                                     \
+        else SELAS_TRACE_GO2(MODE, COUNT, false, false, false, __VA_ARGS__);                                       \
     } while (0)
 
 int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, SelasHit* d_hits, float* d_ng4, uint32_t* d_counts,

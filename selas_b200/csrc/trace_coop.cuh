@@ -15,8 +15,11 @@
 // the flush (scan of the counts + __reduce_or of the entry heads per window of 32 pairs) removes that loop but makes every flush round
 // dearer: 16.00-16.05 ms per step against 15.88 (profiles/r2_ab_trace_coop_group_queue.jsonl).  Pairs stay.
 //
-// Same interface, launch shape and ray pulling (ballot-ranked refill) as traceKernel; flattened trees only.  CURVES: leaves may be
-// parts of round B-spline curves (curve.cuh); the element code and normal of a curve hit travel back beside (u, v).
+// Same interface, launch shape and ray pulling (ballot-ranked refill) as traceKernel.  CURVES: leaves may be parts of round B-spline
+// curves (curve.cuh); the element code and normal of a curve hit travel back beside (u, v).  INST: two-level trees (trace.cuh): a lane
+// enters and leaves instances as in traceKernel; the pairs it queues name the instance, and the lane that tests a pair maps the source
+// lane's WORLD ray into that instance's space itself (t means the same in both spaces), so a pair stays valid after its ray has left
+// the instance again.
 #pragma once
 #include "trace.cuh"
 
@@ -40,8 +43,8 @@ SELAS_D uint32_t orderedFloatBits(float f) {
 }
 SELAS_D float fromOrderedFloatBits(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
-template <int MODE, bool COUNT, bool CURVES = false>
-__global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : SELAS_TRACE_CTAS_PER_SM)
+template <int MODE, bool COUNT, bool CURVES = false, bool INST = false>
+__global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES || INST) ? 6 : SELAS_TRACE_CTAS_PER_SM)
     traceCoopKernel(Bvh8 bvh, const SelasRay* __restrict__ rays, uint32_t n, const uint32_t* __restrict__ nPtr, SelasHit* __restrict__ hits,
                     uint8_t* __restrict__ occluded, float4* __restrict__ ng, uint32_t* __restrict__ counts, const float4* __restrict__ payload,
                     float* __restrict__ film, uint32_t* __restrict__ nextRay, unsigned long long* __restrict__ totals,
@@ -54,12 +57,16 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
     __shared__ float2 sUv[WARPS][32];                            // per source lane: (u, v) of its best hit
     __shared__ unsigned long long sBest[WARPS][32];              // per source lane: ordered(t) << 32 | triangle
     __shared__ float4 sCurve[CURVES ? WARPS : 1][32];            // per source lane: curve normal and element code of its best hit
+    __shared__ uint32_t sQueueInst[INST ? WARPS : 1][INST ? SELAS_COOP_QCAP : 1];  // the pair's instance
+    __shared__ uint32_t sInst[INST ? WARPS : 1][32];             // per source lane: instance of its best hit
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t ltMask = (1u << lane) - 1u;
     uint32_t* const q = sQueue[warp];
     float2* const quv = sUv[warp];
     unsigned long long* const best = sBest[warp];
     float4* const qcurve = sCurve[CURVES ? warp : 0];
+    uint32_t* const qinst = sQueueInst[INST ? warp : 0];
+    uint32_t* const bestInst = sInst[INST ? warp : 0];
     uint32_t* const tail = &sTail[warp];
     if (lane == 0) *tail = 0u;
     __syncwarp();
@@ -80,6 +87,11 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
     bool active = false, exhausted = false;
     bool outstanding = false;  // this lane has pairs in the queue
     bool done = false;         // any-hit: a queued triangle was hit
+    // two-level state (INST): the world ray (always), stack mark, the instance's node / triangle bases; a popped remainder of top-level leaf hits
+    V3 ow = v3(0.f), dw = v3(0.f);
+    int spMark = 0;
+    uint32_t nodeBase = 0u, triBase = 0u, curInst = 0u;
+    bool inBlas = false, pendingLeaf = false;
     uint32_t qCount = 0;       // warp-uniform
 
     // the whole warp tests the queued pairs, one per lane and round
@@ -92,9 +104,19 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
             const bool valid = e < qCount;
             const uint32_t entry = valid ? q[e] : 0u;
             const uint32_t src = entry & 31u;
-            const V3 so = v3(__shfl_sync(FULL, o.x, src), __shfl_sync(FULL, o.y, src), __shfl_sync(FULL, o.z, src));
-            const V3 sd = v3(__shfl_sync(FULL, d.x, src), __shfl_sync(FULL, d.y, src), __shfl_sync(FULL, d.z, src));
+            V3 so = v3(__shfl_sync(FULL, INST ? ow.x : o.x, src), __shfl_sync(FULL, INST ? ow.y : o.y, src), __shfl_sync(FULL, INST ? ow.z : o.z, src));
+            V3 sd = v3(__shfl_sync(FULL, INST ? dw.x : d.x, src), __shfl_sync(FULL, INST ? dw.y : d.y, src), __shfl_sync(FULL, INST ? dw.z : d.z, src));
             const float stn = __shfl_sync(FULL, tnear, src), stm = __shfl_sync(FULL, tmax, src);
+            uint32_t pairInst = 0u;
+            if (INST && valid) {  // the world ray into the pair's instance (SceneInstanceIntersectFunction, SceneResource.cpp:87-142)
+                pairInst = qinst[e];
+                const float4* ip = reinterpret_cast<const float4*>(bvh.instances + pairInst);
+                const float4 m0 = __ldg(ip), m1 = __ldg(ip + 1), m2 = __ldg(ip + 2);
+                const V3 wo = so, wd = sd;
+                so = v3(wo.x * m0.x + wo.y * m0.w + wo.z * m1.z + m2.y, wo.x * m0.y + wo.y * m1.x + wo.z * m1.w + m2.z,
+                        wo.x * m0.z + wo.y * m1.y + wo.z * m2.x + m2.w);
+                sd = v3(wd.x * m0.x + wd.y * m0.w + wd.z * m1.z, wd.x * m0.y + wd.y * m1.x + wd.z * m1.w, wd.x * m0.z + wd.y * m1.y + wd.z * m2.x);
+            }
             bool hit = false;
             unsigned long long key = 0ull;
             float t, u, v;
@@ -122,6 +144,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
             if (hit && best[src] == key) {  // the best so far (a later round's better hit overwrites it)
                 quv[src] = make_float2(u, v);
                 if (CURVES) qcurve[src] = curveOut;
+                if (INST) bestInst[src] = pairInst;
             }
             __syncwarp();
         }
@@ -133,6 +156,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
                 const float2 uv = quv[lane];
                 tmax = t;
                 res.t = t; res.u = uv.x; res.v = uv.y; res.tri = tri;
+                if (INST) res.inst = bestInst[lane];
                 if (CURVES) {
                     const float4 cv = qcurve[lane];
                     res.ng = v3(cv.x, cv.y, cv.z);
@@ -169,6 +193,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
                     setupRayDirection(d, idir, negx, negy, negz, octInv4);
                     res.t = tfar; res.u = 0.f; res.v = 0.f; res.tri = 0xFFFFFFFFu;
                     sp = 0;
+                    if (INST) { ow = o; dw = d; inBlas = false; pendingLeaf = false; nodeBase = 0u; triBase = 0u; }
                     const bool valid = isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z) &&
                                        tnear <= tfar;
                     group = make_uint2(0u, (bvh.nodeCount && valid) ? 0x80000000u : 0u);
@@ -191,7 +216,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
             if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
             const uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
             const uint32_t rel = __popc(hitsImask & ~(0xffffffffu << slot));
-            const float4* np = bvh.nodes + (size_t)(group.x + rel) * 5;
+            const float4* np = bvh.nodes + (size_t)((INST ? nodeBase : 0u) + group.x + rel) * 5;
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
             if (COUNT) ++nNodes;
             const uint32_t hitMask = intersectNode(n0, n1, n2, n3, n4, o, idir, negx, negy, negz, octInv4, tnear, tmax);
@@ -199,6 +224,32 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
             group.y = (hitMask & 0xff000000u) | extractByte(__float_as_uint(n0.w), 3);
             leafBase = __float_as_uint(n1.y);
             leafMask = hitMask & 0x00ffffffu;
+        } else if (INST && active && pendingLeaf) {  // what an earlier top-level node left of its instance hits
+            leafBase = group.x;
+            leafMask = group.y & 0x00ffffffu;
+            group = make_uint2(0u, 0u);
+            pendingLeaf = false;
+        }
+        if (INST && leafMask != 0u && !inBlas) {
+            // top-level leaf hits are instances: enter the first one now (what is left of the hits and of the node waits on the stack, below
+            // the mark), as traceKernel does
+            const uint32_t bit = 31u - __clz(leafMask);
+            leafMask &= ~(1u << bit);
+            const uint32_t ii = __float_as_uint(__ldg(bvh.tris + (size_t)(leafBase + bit) * 3).w);
+            if (leafMask != 0u && sp < SELAS_STACK_SIZE) stack[sp++] = make_uint2(leafBase, leafMask);
+            if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
+            spMark = sp;
+            const float4* ip = reinterpret_cast<const float4*>(bvh.instances + ii);
+            const float4 m0 = __ldg(ip), m1 = __ldg(ip + 1), m2 = __ldg(ip + 2);
+            const uint4 m3 = __ldg(reinterpret_cast<const uint4*>(ip + 3));
+            o = v3(ow.x * m0.x + ow.y * m0.w + ow.z * m1.z + m2.y, ow.x * m0.y + ow.y * m1.x + ow.z * m1.w + m2.z,
+                   ow.x * m0.z + ow.y * m1.y + ow.z * m2.x + m2.w);
+            d = v3(dw.x * m0.x + dw.y * m0.w + dw.z * m1.z, dw.x * m0.y + dw.y * m1.x + dw.z * m1.w, dw.x * m0.z + dw.y * m1.y + dw.z * m2.x);
+            setupRayDirection(d, idir, negx, negy, negz, octInv4);
+            nodeBase = m3.x; triBase = m3.y; curInst = ii;
+            inBlas = true;
+            group = make_uint2(0u, 0x80000000u);
+            leafMask = 0u;
         }
 
         // ---- leaf hits go to the warp's queue (slots by a shared-memory atomic: the order within the queue does not matter) ----
@@ -210,17 +261,20 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
                 // more leaf hits in one step than the queue holds (up to 24 per lane): every lane tests its own, as traceKernel does
                 if (cnt) {
                     uint32_t dummy = 0;
-                    if (testLeafGroup<ANY, false, CURVES>(bvh, make_uint2(leafBase, leafMask), o, d, tnear, tmax, res, dummy)) done = true;
+                    const uint32_t before = res.tri;
+                    if (testLeafGroup<ANY, false, CURVES>(bvh, make_uint2(leafBase + (INST ? triBase : 0u), leafMask), o, d, tnear, tmax, res, dummy)) done = true;
+                    if (INST && res.tri != before) res.inst = curInst;
                 }
             } else {
                 if (cnt) {
-                    uint32_t* qp = q + atomicAdd(tail, cnt);
-                    const uint32_t entryBase = lane | (leafBase << 5);
+                    uint32_t w = atomicAdd(tail, cnt);
+                    const uint32_t entryBase = lane | ((leafBase + (INST ? triBase : 0u)) << 5);
                     uint32_t m = leafMask;
                     do {
                         const uint32_t bit = 31u - __clz(m);
                         m ^= 1u << bit;
-                        *qp++ = entryBase + (bit << 5);
+                        if (INST) qinst[w] = curInst;
+                        q[w++] = entryBase + (bit << 5);
                     } while (m);
                     outstanding = true;
                 }
@@ -230,14 +284,25 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
         }
 
         // ---- next group; flush when the queue is full enough, rays are waiting on it, or nobody has a node left ----
-        if (active && (group.y & 0xff000000u) == 0u && sp > 0) group = stack[--sp];
-        const bool hasWork = active && !done && (group.y & 0xff000000u) != 0u;
+        if (active && (group.y & 0xff000000u) == 0u) {
+            if (INST && inBlas && sp == spMark) {  // the instance's tree is exhausted: back to world space and to what was left at the top level
+                o = ow; d = dw;
+                setupRayDirection(d, idir, negx, negy, negz, octInv4);
+                inBlas = false;
+                nodeBase = 0u; triBase = 0u;
+            }
+            if (sp > 0) {
+                group = stack[--sp];
+                if (INST) pendingLeaf = (group.y & 0xff000000u) == 0u;  // only remainders of top-level leaf hits are pushed without inner bits
+            }
+        }
+        const bool hasWork = active && !done && ((group.y & 0xff000000u) != 0u || (INST && pendingLeaf));
         const uint32_t waiting = __ballot_sync(FULL, active && !hasWork && outstanding);
         const bool anyWork = __any_sync(FULL, hasWork);
         if (qCount && (qCount >= SELAS_COOP_FLUSH_MIN || __popc(waiting) >= SELAS_COOP_WAIT_MAX || !anyWork)) flush();
 
         // ---- rays with nothing left ----
-        if (active && !outstanding && (done || (group.y & 0xff000000u) == 0u)) {
+        if (active && !outstanding && (done || ((group.y & 0xff000000u) == 0u && !(INST && pendingLeaf)))) {
             if (MODE == 1) occluded[rayIdx] = res.tri != 0xFFFFFFFFu ? 1 : 0;
             else if (MODE == 2) {
                 if (res.tri == 0xFFFFFFFFu) {
@@ -247,7 +312,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES) ? 6 : S
                     atomicAdd(px + 1, pl.y);
                     atomicAdd(px + 2, pl.z);
                 }
-            } else writeHit<false>(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
+            } else writeHit<INST>(bvh, res, tfar, hits + rayIdx, ng ? ng + rayIdx : nullptr);
             if (COUNT) {
                 if (counts) { counts[2 * (size_t)rayIdx] = nNodes; counts[2 * (size_t)rayIdx + 1] = nTris; }
                 sumNodes += nNodes;
