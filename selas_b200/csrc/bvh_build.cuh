@@ -575,4 +575,67 @@ __global__ void collapseLevelKernel(const CollapseTask* __restrict__ tasks, uint
     o[4] = make_float4(__uint_as_float(pack4(qlo[2])), __uint_as_float(pack4(qlo[2] + 4)), __uint_as_float(pack4(qhi[2])), __uint_as_float(pack4(qhi[2] + 4)));
 }
 
+// ---- depth-first relayout of the finished BVH8 ------------------------------------------------------------------------------------------
+// The collapse numbers wide nodes level by level, so a ray's root-to-leaf walk touches one distant region of the node array per level.
+// Here every subtree becomes one contiguous range: a node's block of inner children, then the ranges of those children in order
+// (descStart(child i) = descStart(n) + k + sum of the inner-node counts below the earlier children).  The leaf triangles follow the same
+// order.  Only positions change -- childBase / triBase words are rewritten -- so traversal results are identical.
+SELAS_D uint32_t wideNodeInnerCount(const float4* nodes, uint32_t i) { return (uint32_t)__popc(__float_as_uint(nodes[(size_t)i * 5].w) >> 24); }
+SELAS_D uint32_t wideNodeLeafTriangles(const float4* nodes, uint32_t i) {
+    const float4 n1 = nodes[(size_t)i * 5 + 1];
+    uint32_t total = 0;
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t meta4 = __float_as_uint(h == 0 ? n1.z : n1.w);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t meta = (meta4 >> (8 * j)) & 0xffu;
+            if (meta != 0u && (meta & 0x1fu) < 24u) total += (uint32_t)__popc(meta >> 5);  // leaf slot: unary count | triangle offset
+        }
+    }
+    return total;
+}
+__global__ void relayoutSubtreeKernel(const float4* __restrict__ nodes, uint32_t begin, uint32_t end, uint32_t* __restrict__ below) {
+    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    const uint32_t k = wideNodeInnerCount(nodes, i), base = __float_as_uint(nodes[(size_t)i * 5 + 1].x);
+    uint32_t sum = 0;
+    for (uint32_t c = 0; c < k; ++c) sum += 1u + below[base + c];
+    below[i] = sum;
+}
+__global__ void relayoutPlaceKernel(const float4* __restrict__ nodes, uint32_t begin, uint32_t end, const uint32_t* __restrict__ below,
+                                    uint32_t* __restrict__ newIndex, uint32_t* __restrict__ descStart) {
+    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    if (i == 0u) { newIndex[0] = 0u; descStart[0] = 1u; }
+    const uint32_t k = wideNodeInnerCount(nodes, i), base = __float_as_uint(nodes[(size_t)i * 5 + 1].x);
+    const uint32_t start = i == 0u ? 1u : descStart[i];
+    uint32_t next = start + k;
+    for (uint32_t c = 0; c < k; ++c) {
+        newIndex[base + c] = start + c;
+        descStart[base + c] = next;
+        next += below[base + c];
+    }
+}
+__global__ void relayoutLeafCountKernel(const float4* __restrict__ nodes, uint32_t n, const uint32_t* __restrict__ newIndex, uint32_t* __restrict__ countsNewOrder) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    countsNewOrder[newIndex[i]] = wideNodeLeafTriangles(nodes, i);
+}
+__global__ void relayoutScatterKernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t n, const uint32_t* __restrict__ newIndex,
+                                      const uint32_t* __restrict__ descStart, const uint32_t* __restrict__ triStartNewOrder, float4* __restrict__ outNodes,
+                                      float4* __restrict__ outTris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = newIndex[i];
+    float4 n0 = nodes[(size_t)i * 5], n1 = nodes[(size_t)i * 5 + 1];
+    const uint32_t oldTriBase = __float_as_uint(n1.y), newTriBase = triStartNewOrder[j];
+    const uint32_t count = wideNodeLeafTriangles(nodes, i);
+    for (uint32_t t = 0; t < count; ++t)
+        for (int q = 0; q < 3; ++q) outTris[(size_t)(newTriBase + t) * 3 + q] = tris[(size_t)(oldTriBase + t) * 3 + q];
+    n1.x = __uint_as_float(wideNodeInnerCount(nodes, i) ? descStart[i] : 0u);
+    n1.y = __uint_as_float(count ? newTriBase : 0u);
+    outNodes[(size_t)j * 5] = n0;
+    outNodes[(size_t)j * 5 + 1] = n1;
+    for (int q = 2; q < 5; ++q) outNodes[(size_t)j * 5 + q] = nodes[(size_t)i * 5 + q];
+}
+
 }  // namespace selas

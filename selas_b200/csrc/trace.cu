@@ -317,6 +317,49 @@ static int buildTree(SelasScene* scene, const BuildTri* d_tris, const uint32_t* 
     out.nodeCount = finalCtr[0];
     out.triCount = n;
     out.levels = level;
+
+    // ---- depth-first relayout (bvh_build.cuh), SELAS_BVH_LAYOUT=dfs.  Measured neutral (configs[2] 15.65 against 15.69 ms per step, configs[1]
+    // within noise for camera, shadow and incoherent rays: profiles/r2_ab_layout.jsonl) -- the level order already keeps each level in the
+    // tree's spatial order and the kernels are bound by issue slots, not by where the nodes lie -- so the collapse's order is kept by default.
+    static const bool keepLevelOrder = !(getenv("SELAS_BVH_LAYOUT") && !strcmp(getenv("SELAS_BVH_LAYOUT"), "dfs"));
+    if (!keepLevelOrder && out.nodeCount > 1) {
+        const uint32_t N = out.nodeCount;
+        uint32_t *d_below, *d_newIndex, *d_descStart, *d_leafCounts, *d_triStart;
+        if ((rc = tempAlloc((void**)&d_below, sizeof(uint32_t) * (size_t)N))) return rc;
+        if ((rc = tempAlloc((void**)&d_newIndex, sizeof(uint32_t) * (size_t)N))) return rc;
+        if ((rc = tempAlloc((void**)&d_descStart, sizeof(uint32_t) * (size_t)N))) return rc;
+        if ((rc = tempAlloc((void**)&d_leafCounts, sizeof(uint32_t) * (size_t)N))) return rc;
+        if ((rc = tempAlloc((void**)&d_triStart, sizeof(uint32_t) * (size_t)N))) return rc;
+        float4 *d_nodes2 = nullptr, *d_tris2 = nullptr;
+        if (cudaMalloc((void**)&d_nodes2, (size_t)N * 5 * sizeof(float4) + 16) != cudaSuccess ||
+            cudaMalloc((void**)&d_tris2, (size_t)n * 3 * sizeof(float4) + 16) != cudaSuccess) {
+            cudaFree(d_nodes2);
+            cudaGetLastError();  // out of memory for the second copy: keep the level order
+        } else {
+            for (int L = (int)out.levelEnds.size() - 1; L >= 0; --L) {
+                const uint32_t b = L ? out.levelEnds[L - 1] : 0u, e = out.levelEnds[L];
+                if (e > b) relayoutSubtreeKernel<<<divUp(e - b, 256), 256, 0, st>>>(d_nodes, b, e, d_below);
+            }
+            for (size_t L = 0; L < out.levelEnds.size(); ++L) {
+                const uint32_t b = L ? out.levelEnds[L - 1] : 0u, e = out.levelEnds[L];
+                if (e > b) relayoutPlaceKernel<<<divUp(e - b, 256), 256, 0, st>>>(d_nodes, b, e, d_below, d_newIndex, d_descStart);
+            }
+            relayoutLeafCountKernel<<<divUp(N, 256), 256, 0, st>>>(d_nodes, N, d_newIndex, d_leafCounts);
+            size_t scanBytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, d_leafCounts, d_triStart, (int)N, st);
+            void* d_scanTemp;
+            if ((rc = tempAlloc(&d_scanTemp, scanBytes))) { cudaFree(d_nodes2); cudaFree(d_tris2); return rc; }
+            cub::DeviceScan::ExclusiveSum(d_scanTemp, scanBytes, d_leafCounts, d_triStart, (int)N, st);
+            relayoutScatterKernel<<<divUp(N, 128), 128, 0, st>>>(d_nodes, d_outTris, N, d_newIndex, d_descStart, d_triStart, d_nodes2, d_tris2);
+            SELAS_CUDA_CHECK(ctx, cudaGetLastError());
+            SELAS_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+            cudaFree(d_nodes);
+            cudaFree(d_outTris);
+            out.nodes = d_nodes2;
+            out.tris = d_tris2;
+            out.levelEnds.clear();  // the first nodes are no longer whole levels: nothing to stage in shared memory
+        }
+    }
     return SELAS_OK;
 }
 
