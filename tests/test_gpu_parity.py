@@ -534,12 +534,14 @@ def test_texture_filters_vs_oracle(ctx, oracle, comps):
         ctx.texture_filter(levels, 7, st, d0, d1)
 
 
-@pytest.mark.parametrize("env", [{"SELAS_TRACE_COOP": "1"}, {"SELAS_COLLAPSE": "greedy"}, {"SELAS_BVH_BUILD": "lbvh", "SELAS_TRACE_COOP": "1"}],
-                         ids=["cooperative-kernel", "greedy-collapse", "lbvh-tree-cooperative-kernel"])
+@pytest.mark.parametrize("env", [{"SELAS_TRACE_COOP": "1"}, {"SELAS_COLLAPSE": "greedy"}, {"SELAS_BVH_BUILD": "lbvh", "SELAS_TRACE_COOP": "1"},
+                                 {"SELAS_BVH_LAYOUT": "dfs"}],
+                         ids=["cooperative-kernel", "greedy-collapse", "lbvh-tree-cooperative-kernel", "depth-first-layout"])
 def test_kernel_and_builder_variants_return_the_same_hits(ctx, tmp_path, env):
     """The process-wide variants against the defaults on the same rays: the cooperative triangle stage for the public calls
     (SELAS_TRACE_COOP), the greedy BVH2 -> BVH8 collapse instead of the cost recurrence (SELAS_COLLAPSE), the Morton radix tree instead of
-    the binned-SAH tree (SELAS_BVH_BUILD).  A different tree or test order must not change what is hit.
+    the binned-SAH tree (SELAS_BVH_BUILD), the depth-first node layout (SELAS_BVH_LAYOUT).  A different tree, layout or test order must not
+    change what is hit.
     traceCoopKernel (trace_coop.cuh: leaf triangles queued per warp and tested by the whole warp) against traceKernel on the same rays:
     identical hit records and occlusion bytes (closest hit is a minimum over the same candidates; equal distances go to the lower triangle
     index in one kernel and to the last one tested in the other, so ids are compared under the tie rule).  The kernel is selected per
