@@ -297,7 +297,7 @@ typedef struct SelasRenderStats {
 } SelasRenderStats;
 
 typedef struct SelasBvhStats {
-    uint32_t triangleCount;  /* triangles stored (quads count twice) */
+    uint32_t triangleCount;  /* leaf primitives stored: triangles (quads count twice) and curve parts (8 per curve segment, csrc/curve.cuh) */
     uint32_t nodeCount;      /* 80-byte BVH8 nodes */
     uint32_t maxDepth;
     uint32_t reserved;
