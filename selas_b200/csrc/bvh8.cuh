@@ -152,6 +152,24 @@ SELAS_D uint32_t intersectNode(const float4 n0, const float4 n1, const float4 n2
     return hitMask;
 }
 
+// Which inner child of a group comes next.  The slots are octant-ordered, so the highest pending bit is the child a ray of this octant
+// meets first: closest-hit rays take it (front to back: tmax shrinks early), and so do the generic any-hit calls (selas_cuda_occluded).
+// The integrators' shadow rays (MODE 2: next-event estimation, VCM connections) take the LOWEST bit instead -- back to front, i.e. from
+// the light's end.  Such a ray leaves a surface on the side the light is on (the BSDF is zero otherwise and no ray is cast), so whatever
+// blocks it is rarely at its origin and usually further along; walking from the far end finds the blocker sooner and ends the ray:
+// configs[2] 12.73 -> 12.06 nodes per shadow ray, shadow kernel 3.83 -> 3.58 ms per step, VCM 430 -> 459 M sub-paths/s
+// (profiles/r2_ab_anyhit_order*.jsonl).  For shadow rays cast from ALL hit points regardless of facing (the configs[1] side benchmark,
+// half of whose rays start into the body they left) the near end is the better one (4.44 against 4.01 G rays/s), hence the split by mode.
+// SELAS_ANYHIT_BACK_TO_FRONT=0 restores front to back everywhere.
+#ifndef SELAS_ANYHIT_BACK_TO_FRONT
+#define SELAS_ANYHIT_BACK_TO_FRONT 1
+#endif
+template <bool BACK_TO_FRONT>
+SELAS_D uint32_t nextChildBit(uint32_t hitsImask) {
+    if (BACK_TO_FRONT && SELAS_ANYHIT_BACK_TO_FRONT) return (uint32_t)__ffs((int)(hitsImask & 0xff000000u)) - 1u;
+    return 31u - __clz(hitsImask);
+}
+
 // Moller-Trumbore on the {v0,e1,e2} record.  Accepts t in [tnear, tmax].
 SELAS_D bool intersectTri(const float4 a, const float4 b, const float4 c, V3 o, V3 d, float tnear, float tmax, float& t,
                           float& u, float& v) {
@@ -198,7 +216,7 @@ SELAS_D void traceRay(const Bvh8& bvh, V3 o, V3 d, float tnear, float tfar, Trac
         uint2 triGroup;
         if (group.y & 0xff000000u) {
             uint32_t hitsImask = group.y;
-            uint32_t childBit = 31u - __clz(hitsImask);
+            uint32_t childBit = nextChildBit<false>(hitsImask);
             group.y &= ~(1u << childBit);
             if (group.y & 0xff000000u) {
                 if (sp < SELAS_STACK_SIZE) stack[sp++] = group;

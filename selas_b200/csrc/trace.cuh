@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
                 const float4* np = bvh.nodes;
                 if (hasNode) {
                     const uint32_t hitsImask = group.y;
-                    const uint32_t childBit = 31u - __clz(hitsImask);
+                    const uint32_t childBit = nextChildBit<MODE == 2>(hitsImask);
                     group.y &= ~(1u << childBit);
                     if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
                     const uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (INST || COUNT || CURVES)
 
             if (group.y & 0xff000000u) {
                 uint32_t hitsImask = group.y;
-                uint32_t childBit = 31u - __clz(hitsImask);
+                uint32_t childBit = nextChildBit<MODE == 2>(hitsImask);
                 group.y &= ~(1u << childBit);
                 if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
                 uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);

@@ -15,6 +15,10 @@
 // the flush (scan of the counts + __reduce_or of the entry heads per window of 32 pairs) removes that loop but makes every flush round
 // dearer: 16.00-16.05 ms per step against 15.88 (profiles/r2_ab_trace_coop_group_queue.jsonl).  Pairs stay.
 //
+// A per-pixel shadow cache (the triangle that blocked the pixel's last first-bounce shadow ray, tried before any traversal) was built and
+// measured: 12.06 -> 12.04 nodes per shadow ray and 2 % slower (profiles/r2_ab_shadow_cache.jsonl) -- too few of configs[2]'s shadow rays
+// are blocked at all, and by the same triangle even fewer.  Removed.
+//
 // Same interface, launch shape and ray pulling (ballot-ranked refill) as traceKernel.  CURVES: leaves may be parts of round B-spline
 // curves (curve.cuh); the element code and normal of a curve hit travel back beside (u, v).  INST: two-level trees (trace.cuh): a lane
 // enters and leaves instances as in traceKernel; the pairs it queues name the instance, and the lane that tests a pair maps the source
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(SELAS_TRACE_THREADS, (COUNT || CURVES || INST)
         uint32_t leafMask = 0u, leafBase = 0u;
         if (active && (group.y & 0xff000000u)) {
             const uint32_t hitsImask = group.y;
-            const uint32_t childBit = 31u - __clz(hitsImask);
+            const uint32_t childBit = nextChildBit<MODE == 2>(hitsImask);
             group.y &= ~(1u << childBit);
             if ((group.y & 0xff000000u) && sp < SELAS_STACK_SIZE) stack[sp++] = group;
             const uint32_t slot = (childBit - 24u) ^ (octInv4 & 0xffu);
