@@ -1001,6 +1001,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     // = first bounce that uses it (a large number switches it off).
     static const uint32_t coopClosestFrom = getenv("SELAS_COOP_CLOSEST_FROM") ? (uint32_t)atoi(getenv("SELAS_COOP_CLOSEST_FROM")) : 1u;
     static const uint32_t coopShadowFrom = getenv("SELAS_COOP_SHADOW_FROM") ? (uint32_t)atoi(getenv("SELAS_COOP_SHADOW_FROM")) : 0u;
+    static const uint32_t kSortMinQueue = getenv("SELAS_SORT_MIN_QUEUE") ? (uint32_t)atoi(getenv("SELAS_SORT_MIN_QUEUE")) : 65536u;
     static const bool shadeOneShot = !(getenv("SELAS_SHADE_ONESHOT") && atoi(getenv("SELAS_SHADE_ONESHOT")) == 0);
     static const int shadeWaves = getenv("SELAS_SHADE_WAVES") ? std::max(1, atoi(getenv("SELAS_SHADE_WAVES"))) : 2;
 
@@ -1060,16 +1061,22 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 rayOrder = w->rayOrder;
                 launches += 3;
             }
-            rc = launchIntersectIndirect(scene, ctr, count, w->rays[cur], w->hits, ctr + 2, d_totals, stream, rayOrder, it >= coopClosestFrom ? 1 : 0);
+            // queue length of this bounce as an earlier pass of the same shape saw it (0 = not known yet)
+            const uint32_t est = (!longPaths && w->estimateCount == count && it < w->estimate.size()) ? w->estimate[it] : 0u;
+            rc = launchIntersectIndirect(scene, ctr, count, w->rays[cur], w->hits, ctr + 2, d_totals, stream, rayOrder, it >= coopClosestFrom ? 1 : 0, est);
             if (rc) return rc;
             timers.end(1, t0, stream);
             t0 = timers.begin(stream);
             const uint32_t* order = nullptr;
-            if (it >= sortFromBounce) {
+            // the material sort pays while a queue fills the machine; the last bounces' few thousand paths are shaded in queue order
+            // (three launches less per bounce), and the binning grids follow the estimate instead of the pass size
+            const bool sortThis = it >= sortFromBounce && !(est != 0u && est < kSortMinQueue);
+            if (sortThis) {
+                const int grid = est ? (int)std::min<uint32_t>((uint32_t)sortGrid, divUp(est + est / 16u + 2048u, 2048)) : sortGrid;
                 uint32_t* bins = w->bins + 2 * kBinCount * (size_t)slot;
-                binCountKernel<<<sortGrid, 256, 0, stream>>>(scene->gpu, count, ctr, w->hits, bins);
+                binCountKernel<<<grid, 256, 0, stream>>>(scene->gpu, count, ctr, w->hits, bins);
                 binScanKernel<<<1, 32, 0, stream>>>(bins, bins + kBinCount);
-                binScatterKernel<<<sortGrid, 256, 0, stream>>>(scene->gpu, count, ctr, w->hits, bins + kBinCount, w->order);
+                binScatterKernel<<<grid, 256, 0, stream>>>(scene->gpu, count, ctr, w->hits, bins + kBinCount, w->order);
                 order = w->order;
                 launches += 3;
             }
@@ -1080,7 +1087,6 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             }
             // one-shot grid when an earlier pass of this shape told how long this bounce's queue gets (3 % + 8 CTAs of slack; what a low
             // estimate leaves over is covered by a persistent launch behind it, which normally finds nothing), else the persistent shape
-            const uint32_t est = (!longPaths && w->estimateCount == count && it < w->estimate.size()) ? w->estimate[it] : 0u;
             const bool oneShot = est != 0u && shadeOneShot;
             // SELAS_SHADE_ESTIMATE_PERCENT scales the estimate (tests under-size it to exercise the launch behind the one-shot grid)
             const char* pct = getenv("SELAS_SHADE_ESTIMATE_PERCENT");
@@ -1107,7 +1113,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
                 float* filmRadiance = d_film + (rs.layerCount == 2 ? 3 * (size_t)pixels : 0);
                 t0 = timers.begin(stream);
                 rc = launchShadowAccumulate(scene, next + 1, count * w->shadowPerPath, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
-                                            d_totals ? d_totals + 2 : nullptr, stream, it >= coopShadowFrom ? 1 : 0);
+                                            d_totals ? d_totals + 2 : nullptr, stream, it >= coopShadowFrom ? 1 : 0, est ? est * w->shadowPerPath : 0u);
                 if (rc) return rc;
                 timers.end(3, t0, stream);
             }

@@ -727,7 +727,7 @@ struct TraceLaunch {
     size_t smem;
 };
 template <typename K>
-static TraceLaunch traceLaunch(const SelasScene* scene, K kernel) {
+static TraceLaunch traceLaunch(const SelasScene* scene, K kernel, uint32_t expected = 0) {
     TraceLaunch l;
     l.smem = (size_t)scene->topNodeCount * 80u;
     if (l.smem > 48u * 1024u) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l.smem);
@@ -738,6 +738,8 @@ static TraceLaunch traceLaunch(const SelasScene* scene, K kernel) {
             perSm = std::min(perSm, resident);
     }
     l.grid = scene->ctx->smCount * perSm;
+    // a short queue (the late bounces' few thousand rays) does not need the whole machine's worth of CTAs started: one CTA per 64 expected rays
+    if (expected) l.grid = std::max(1, std::min(l.grid, (int)((expected + expected / 8u + 63u) / 64u)));
     return l;
 }
 // SELAS_TRACE_COOP=1: flattened trees without curves go through the kernel with the warp-cooperative triangle stage (trace_coop.cuh)
@@ -759,12 +761,12 @@ static bool traceCoopFor(int coop, const SelasScene* scene) {
 // top levels only when asked for
 #define SELAS_TRACE_GO2(MODE, COUNT, INST, TOP, CURVES, ...)                                                       \
     do {                                                                                                           \
-        TraceLaunch tl = traceLaunch(scene, traceKernel<MODE, COUNT, INST, TOP, CURVES>);                          \
+        TraceLaunch tl = traceLaunch(scene, traceKernel<MODE, COUNT, INST, TOP, CURVES>, expected__);              \
         traceKernel<MODE, COUNT, INST, TOP, CURVES><<<tl.grid, SELAS_TRACE_THREADS, tl.smem, stream>>>(__VA_ARGS__); \
     } while (0)
 #define SELAS_TRACE_COOP_GO(MODE, COUNT, CURVES, INST, ...)                                                          \
     do {                                                                                                           \
-        TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT, CURVES, INST>);                           \
+        TraceLaunch tl = traceLaunch(scene, traceCoopKernel<MODE, COUNT, CURVES, INST>, expected__);               \
         traceCoopKernel<MODE, COUNT, CURVES, INST><<<tl.grid, SELAS_TRACE_THREADS, 0, stream>>>(__VA_ARGS__);      \
     } while (0)
 #define SELAS_TRACE_GO(MODE, COUNT, ...)                                                                            \
@@ -791,6 +793,7 @@ int launchIntersect(SelasScene* scene, uint32_t n, const SelasRay* d_rays, Selas
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
     const bool coop__ = traceCoopEnabled(scene);
+    const uint32_t expected__ = 0;
     if (d_counts)
         SELAS_TRACE_GO(0, true, bvhOf(scene, true), d_rays, n, nullptr, d_hits, nullptr, (float4*)d_ng4, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
@@ -805,6 +808,7 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
     SelasContext* ctx = scene->ctx;
     SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(d_rayCounter, 0, sizeof(uint32_t), stream));
     const bool coop__ = traceCoopEnabled(scene);
+    const uint32_t expected__ = 0;
     if (d_counts)
         SELAS_TRACE_GO(1, true, bvhOf(scene), d_rays, n, nullptr, nullptr, d_occ, nullptr, d_counts, nullptr, nullptr, d_rayCounter, nullptr);
     else
@@ -816,9 +820,10 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
 // Wavefront variants: the queue length lives in device memory (or n is exact when d_n is null); d_rayCounter must
 // already be zero.  totals != null selects the counting build of the same kernel (SELAS_RENDER_COUNT_TRAVERSAL).
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
-                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order, int coop) {
+                            uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order, int coop, uint32_t expected) {
     SelasContext* ctx = scene->ctx;
     const bool coop__ = traceCoopFor(coop, scene);
+    const uint32_t expected__ = expected;
     if (d_totals)
         SELAS_TRACE_GO(0, true, bvhOf(scene), d_rays, maxN, d_n, d_hits, nullptr, nullptr, nullptr, nullptr, nullptr, d_rayCounter, d_totals, d_order);
     else
@@ -828,9 +833,10 @@ int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t max
 }
 
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
-                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop) {
+                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop, uint32_t expected) {
     SelasContext* ctx = scene->ctx;
     const bool coop__ = traceCoopFor(coop, scene);
+    const uint32_t expected__ = expected;
     if (d_totals)
         SELAS_TRACE_GO(2, true, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, d_totals);
     else
