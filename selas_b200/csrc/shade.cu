@@ -1072,7 +1072,8 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             // (three launches less per bounce), and the binning grids follow the estimate instead of the pass size
             const bool sortThis = it >= sortFromBounce && !(est != 0u && est < kSortMinQueue);
             if (sortThis) {
-                const int grid = est ? (int)std::min<uint32_t>((uint32_t)sortGrid, divUp(est + est / 16u + 2048u, 2048)) : sortGrid;
+                // (not below one CTA per SM: a stale estimate must not serialise a long queue)
+                const int grid = est ? (int)std::min<uint32_t>((uint32_t)sortGrid, std::max<uint32_t>((uint32_t)ctx->smCount, divUp(est + est / 16u + 2048u, 2048))) : sortGrid;
                 uint32_t* bins = w->bins + 2 * kBinCount * (size_t)slot;
                 binCountKernel<<<grid, 256, 0, stream>>>(scene->gpu, count, ctr, w->hits, bins);
                 binScanKernel<<<1, 32, 0, stream>>>(bins, bins + kBinCount);

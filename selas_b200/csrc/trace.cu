@@ -739,7 +739,8 @@ static TraceLaunch traceLaunch(const SelasScene* scene, K kernel, uint32_t expec
     }
     l.grid = scene->ctx->smCount * perSm;
     // a short queue (the late bounces' few thousand rays) does not need the whole machine's worth of CTAs started: one CTA per 64 expected rays
-    if (expected) l.grid = std::max(1, std::min(l.grid, (int)((expected + expected / 8u + 63u) / 64u)));
+    // (never below two CTAs per SM: the estimate comes from an earlier pass and may be far too low after a camera change)
+    if (expected) l.grid = std::max(2 * scene->ctx->smCount, std::min(l.grid, (int)((expected + expected / 8u + 63u) / 64u)));
     return l;
 }
 // SELAS_TRACE_COOP=1: flattened trees without curves go through the kernel with the warp-cooperative triangle stage (trace_coop.cuh)
