@@ -174,3 +174,24 @@ def test_short_queue_estimate_is_covered_by_the_launch_behind_it(ctx, monkeypatc
     film, st = sc.render(cam, rs)
     assert (st.closestRays, st.occlusionRays) == (st0.closestRays, st0.occlusionRays)
     sc.close()
+
+
+def test_estimates_from_another_view_do_not_change_the_result(ctx):
+    """Launch shapes follow the queue lengths an EARLIER pass read back (one-shot shade grids, the material sort skipped for short queues,
+    binning / trace grids): after passes that looked at the empty sky (every queue after the camera rays is empty) a pass with the camera
+    on the terrain must give what a fresh scene gives -- stale estimates may only cost time."""
+    data = scenes.disney_heightfield(grid=48)
+    rs = capi.render_settings(192, 108, 8, max_path_length=10, rr_start=8, layers=1, seed=9)
+    cam = scenes.heightfield_camera(192, 108)
+    sky = capi.camera_init((0.0, 7.0, -16.0), (0.0, 60.0, -16.5), (0.0, 0.0, 1.0), 50.0, 192, 108)
+    fresh = capi.Scene(ctx, data)
+    want, wst = fresh.render(cam, rs)
+    fresh.close()
+    sc = capi.Scene(ctx, data)
+    for _ in range(3):
+        _, sst = sc.render(sky, rs)
+    assert sst.occlusionRays == 0 and sst.closestRays == 192 * 108 * 8
+    got, gst = sc.render(cam, rs)
+    assert (gst.closestRays, gst.occlusionRays) == (wst.closestRays, wst.occlusionRays)
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-4, atol=1e-5)
+    sc.close()
