@@ -1,4 +1,5 @@
-// trace_coop.cuh -- the BVH8 ray-cast kernel with a warp-cooperative triangle stage (round-2 experiment, SELAS_TRACE_COOP=1).
+// trace_coop.cuh -- the BVH8 ray-cast kernel with a warp-cooperative triangle stage (round 2).  The integrators use it from the first
+// bounce on and for all shadow rays, scenes with curve geometry for every launch; SELAS_TRACE_COOP=1 / 0 forces it on / off (trace.cu).
 //
 // Why: ncu on the closest-hit launch of configs[2] (profiles/r2_trace_bounce0_sass_summary.txt) shows the leaf triangle tests as 30 % of
 // the kernel's warp instructions at 3.3 of 32 lanes: a ray meets its 3.2 leaf triangles at a handful of its 12 node visits, so in any
@@ -29,6 +30,9 @@
 
 namespace selas {
 
+// Tuning (configs[2], ms per step, profiles/r2_ab_trace_coop*.jsonl): flush at 12 / 16 / 24 / 32 queued pairs 16.29 / 16.21 / 16.34 / 16.59;
+// flush when 1 / 2 / 4 / 6 / 8 rays wait on their pairs 16.98 / 16.80 / 16.21 / 16.21 / 16.74; refill below 16 / 20 / 24 / 28 / 32 busy lanes
+// 16.72 / 16.34 / 16.23 / 16.36 / 17.48; queue capacity 64 / 96: the same.
 #ifndef SELAS_COOP_QCAP
 #define SELAS_COOP_QCAP 96
 #endif
