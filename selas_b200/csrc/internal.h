@@ -148,7 +148,8 @@ int launchOccluded(SelasScene* scene, uint32_t n, const SelasRay* d_rays, uint8_
                    cudaStream_t stream);
 // shadow rays with film accumulation: payload = {contribution rgb, pixel}; film[pixel] += rgb when unoccluded
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
-                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop = -1, uint32_t expected = 0);
+                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop = -1, uint32_t expected = 0,
+                           const uint32_t* d_order = nullptr);
 int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, SelasHit* d_hits,
                             uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, const uint32_t* d_order = nullptr, int coop = -1, uint32_t expected = 0);
 // expected: an upper estimate of the queue length when the host has one (0 = unknown): the persistent grid is not launched wider than that many rays need

@@ -1002,6 +1002,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
     static const uint32_t coopClosestFrom = getenv("SELAS_COOP_CLOSEST_FROM") ? (uint32_t)atoi(getenv("SELAS_COOP_CLOSEST_FROM")) : 1u;
     static const uint32_t coopShadowFrom = getenv("SELAS_COOP_SHADOW_FROM") ? (uint32_t)atoi(getenv("SELAS_COOP_SHADOW_FROM")) : 0u;
     static const uint32_t kSortMinQueue = getenv("SELAS_SORT_MIN_QUEUE") ? (uint32_t)atoi(getenv("SELAS_SORT_MIN_QUEUE")) : 65536u;
+    static const uint32_t shadowSortBounces = getenv("SELAS_SHADOW_SORT") ? (uint32_t)atoi(getenv("SELAS_SHADOW_SORT")) : 0u;
     static const bool shadeOneShot = !(getenv("SELAS_SHADE_ONESHOT") && atoi(getenv("SELAS_SHADE_ONESHOT")) == 0);
     static const int shadeWaves = getenv("SELAS_SHADE_WAVES") ? std::max(1, atoi(getenv("SELAS_SHADE_WAVES"))) : 2;
 
@@ -1023,7 +1024,7 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
         cudaGetLastError();  // cudaErrorNotReady of the query is not an error
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->counters, 0, sizeof(uint32_t) * w->counterSlots, stream));
         SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->bins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)slotSets, stream));
-        if (raySortFrom < rs.maxPathLength) SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->rayBins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)slotSets, stream));
+        if (raySortFrom < rs.maxPathLength || shadowSortBounces > 0) SELAS_CUDA_CHECK(ctx, cudaMemsetAsync(w->rayBins, 0, sizeof(uint32_t) * 2 * kBinCount * (size_t)slotSets, stream));
         size_t t0 = timers.begin(stream);
         generateKernel<<<divUp(count, 256), 256, 0, stream>>>(cam, rs.width, rs.height, rs.seed, rs.firstSample, first, count, activePixels,
                                                               stride, rs.pixelSampler, w->rays[0], w->thrPix[0], w->rngFlags[0], w->counters);
@@ -1113,8 +1114,19 @@ int renderPathTracer(SelasScene* scene, const SelasCamera& cam, const SelasRende
             {
                 float* filmRadiance = d_film + (rs.layerCount == 2 ? 3 * (size_t)pixels : 0);
                 t0 = timers.begin(stream);
+                const uint32_t* shadowOrder = nullptr;
+                if (it < shadowSortBounces && w->shadowPerPath == 1 && raySortFrom >= rs.maxPathLength) {
+                    // SELAS_SHADOW_SORT=b: the first b bounces' shadow rays are traced in direction-octant / origin-quadrant order (rays towards
+                    // one light side by side); measured in DESIGN 4
+                    uint32_t* rb = w->rayBins + 2 * kBinCount * (size_t)slot;
+                    rayBinCountKernel<<<sortGrid, 256, 0, stream>>>(count, next + 1, w->shadowRays, raySortCx, raySortCz, rb);
+                    binScanKernel<<<1, 32, 0, stream>>>(rb, rb + kBinCount);
+                    rayBinScatterKernel<<<sortGrid, 256, 0, stream>>>(count, next + 1, w->shadowRays, raySortCx, raySortCz, rb + kBinCount, w->rayOrder);
+                    shadowOrder = w->rayOrder;
+                    launches += 3;
+                }
                 rc = launchShadowAccumulate(scene, next + 1, count * w->shadowPerPath, w->shadowRays, w->shadowPayload, filmRadiance, ctr + 3,
-                                            d_totals ? d_totals + 2 : nullptr, stream, it >= coopShadowFrom ? 1 : 0, est ? est * w->shadowPerPath : 0u);
+                                            d_totals ? d_totals + 2 : nullptr, stream, it >= coopShadowFrom ? 1 : 0, est ? est * w->shadowPerPath : 0u, shadowOrder);
                 if (rc) return rc;
                 timers.end(3, t0, stream);
             }

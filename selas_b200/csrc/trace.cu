@@ -834,14 +834,14 @@ int launchIntersectIndirect(SelasScene* scene, const uint32_t* d_n, uint32_t max
 }
 
 int launchShadowAccumulate(SelasScene* scene, const uint32_t* d_n, uint32_t maxN, const SelasRay* d_rays, const float4* d_payload,
-                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop, uint32_t expected) {
+                           float* d_film, uint32_t* d_rayCounter, unsigned long long* d_totals, cudaStream_t stream, int coop, uint32_t expected, const uint32_t* d_order) {
     SelasContext* ctx = scene->ctx;
     const bool coop__ = traceCoopFor(coop, scene);
     const uint32_t expected__ = expected;
     if (d_totals)
-        SELAS_TRACE_GO(2, true, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, d_totals);
+        SELAS_TRACE_GO(2, true, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, d_totals, d_order);
     else
-        SELAS_TRACE_GO(2, false, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, nullptr);
+        SELAS_TRACE_GO(2, false, bvhOf(scene), d_rays, maxN, d_n, nullptr, nullptr, nullptr, nullptr, d_payload, d_film, d_rayCounter, nullptr, d_order);
     SELAS_CUDA_CHECK(ctx, cudaGetLastError());
     return SELAS_OK;
 }
